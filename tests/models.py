@@ -1,0 +1,274 @@
+"""Model definitions shared by the golden generator, the oracle tests and the GPU parity tests.
+
+Every builder takes a namespace `ns` offering Plate / Group / Data / Timeseries / Normal /
+Bernoulli ... so that the SAME source text builds the model either with the reference
+(`ns = alan`, only in the build container) or with the declarative mirror
+(`ns = alan_b200.model`, everywhere).  Q parameters are referred to by name (they arrive in
+`inputs_params`), which is the reference's `extra_opt_params` mechanism
+(/root/reference/src/alan/BoundPlate.py:49-53), so parameter gradients are part of the goldens.
+
+Shapes follow BASELINE.json `configs`:
+  cfg1  /root/reference/tests/linear_gaussian_latents.py            (mixture-Q path, Split)
+  cfg2  /root/reference/examples/models/movielens/movielens.py:39-74 (MovieLens-shaped)
+  cfg3  /root/reference/examples/models/radon/radon.py:62-102 + HMC/radon (nested plates, Group, K^4 joint)
+  cfg4  /root/reference/tests/timeseries.py:15-30                    (Timeseries chain)
+"""
+import math
+
+import torch as t
+
+
+# --------------------------------------------------------------------------- cfg1
+def lgl_model(ns):
+    """tests/linear_gaussian_latents.py:28-45 verbatim structure."""
+    P = ns.Plate(
+        a=ns.Normal(2, 2),
+        T=ns.Plate(
+            z=ns.Normal('a', 1.3),
+            d=ns.Normal('z', 1.5),
+        ),
+    )
+    Q = ns.Plate(
+        a=ns.Normal(1, 4),
+        T=ns.Plate(
+            z=ns.Normal(lambda a: 1.5 * a, 3.5),
+            d=ns.Data(),
+        ),
+    )
+    return P, Q
+
+
+def lgl_inputs(T=10, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    data = {'d': (1.5 + t.randn(T, generator=g, dtype=t.float64)).to(dtype).refine_names('T')}
+    return dict(platesizes={'T': T}, data=data, inputs={}, params={})
+
+
+def lglp_model(ns):
+    """cfg1 with named Q parameters so that parameter gradients are exercised."""
+    P = ns.Plate(
+        a=ns.Normal(2, 2),
+        T=ns.Plate(
+            z=ns.Normal('a', 1.3),
+            d=ns.Normal('z', 1.5),
+        ),
+    )
+    Q = ns.Plate(
+        a=ns.Normal('qa_loc', lambda qa_ls: qa_ls.exp()),
+        T=ns.Plate(
+            z=ns.Normal(lambda a, qz_w, qz_b: qz_w * a + qz_b, lambda qz_ls: qz_ls.exp()),
+            d=ns.Data(),
+        ),
+    )
+    return P, Q
+
+
+def lglp_inputs(T=10, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    data = {'d': (1.5 + r(T)).refine_names('T')}
+    params = {
+        'qa_loc': t.tensor(1., dtype=dtype), 'qa_ls': t.tensor(math.log(4.), dtype=dtype),
+        'qz_w': (1.5 + 0.1 * r(T)).refine_names('T'), 'qz_b': (0.1 * r(T)).refine_names('T'),
+        'qz_ls': t.tensor(math.log(3.5), dtype=dtype),
+    }
+    return dict(platesizes={'T': T}, data=data, inputs={}, params=params)
+
+
+# --------------------------------------------------------------------------- cfg2
+def movielens_model(ns, d=18):
+    P = ns.Plate(
+        mu_z=ns.Normal(t.zeros((d,)), t.ones((d,))),
+        psi_z=ns.Normal(t.zeros((d,)), t.ones((d,))),
+        plate_1=ns.Plate(
+            z=ns.Normal("mu_z", lambda psi_z: psi_z.exp()),
+            plate_2=ns.Plate(
+                obs=ns.Bernoulli(logits=lambda z, x: z @ x),
+            ),
+        ),
+    )
+    Q = ns.Plate(
+        mu_z=ns.Normal("mu_z_loc", lambda mu_z_ls: mu_z_ls.exp()),
+        psi_z=ns.Normal("psi_z_loc", lambda psi_z_ls: psi_z_ls.exp()),
+        plate_1=ns.Plate(
+            z=ns.Normal("z_loc", lambda z_ls: z_ls.exp()),
+            plate_2=ns.Plate(
+                obs=ns.Data(),
+            ),
+        ),
+    )
+    return P, Q
+
+
+def movielens_inputs(M=300, N=5, d=18, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    x = (t.rand(M, N, d, generator=g) < 0.107).to(dtype)          # real features have mean 0.107
+    z_true = 0.5 * r(M, d)
+    obs = (t.rand(M, N, generator=g) < t.sigmoid((z_true[:, None, :].double() * x.double()).sum(-1))).to(dtype)
+    params = {
+        'mu_z_loc': 0.1 * r(d), 'mu_z_ls': -0.5 + 0.1 * r(d),
+        'psi_z_loc': 0.1 * r(d), 'psi_z_ls': -0.5 + 0.1 * r(d),
+        'z_loc': (0.1 * r(M, d)).refine_names('plate_1', None),
+        'z_ls': (-0.5 + 0.1 * r(M, d)).refine_names('plate_1', None),
+    }
+    return dict(platesizes={'plate_1': M, 'plate_2': N},
+                data={'obs': obs.refine_names('plate_1', 'plate_2')},
+                inputs={'x': x.refine_names('plate_1', 'plate_2', None)},
+                params=params)
+
+
+# --------------------------------------------------------------------------- cfg3
+def radon_model(ns):
+    """States x Counties x Zips hierarchical radon (HMC/radon/radon.py:24-40 in alan form);
+    the global pair is a Group in Q (radon/radon.py:85-88)."""
+    P = ns.Plate(
+        global_mean=ns.Normal(0., 1.),
+        global_log_sigma=ns.Normal(0., 1.),
+        States=ns.Plate(
+            State_mean=ns.Normal('global_mean', lambda global_log_sigma: global_log_sigma.exp()),
+            State_log_sigma=ns.Normal(0., 1.),
+            Counties=ns.Plate(
+                County_mean=ns.Normal('State_mean', lambda State_log_sigma: State_log_sigma.exp()),
+                County_log_sigma=ns.Normal(0., 1.),
+                Beta_u=ns.Normal(0., 1.),
+                Beta_basement=ns.Normal(0., 1.),
+                Zips=ns.Plate(
+                    obs=ns.Normal(
+                        lambda County_mean, basement, log_uranium, Beta_basement, Beta_u:
+                            County_mean + basement * Beta_basement + log_uranium * Beta_u,
+                        lambda County_log_sigma: County_log_sigma.exp()),
+                ),
+            ),
+        ),
+    )
+    Q = ns.Plate(
+        global_latents=ns.Group(
+            global_mean=ns.Normal('gm_loc', lambda gm_ls: gm_ls.exp()),
+            global_log_sigma=ns.Normal('gls_loc', lambda gls_ls: gls_ls.exp()),
+        ),
+        States=ns.Plate(
+            State_mean=ns.Normal('sm_loc', lambda sm_ls: sm_ls.exp()),
+            State_log_sigma=ns.Normal('sls_loc', lambda sls_ls: sls_ls.exp()),
+            Counties=ns.Plate(
+                County_mean=ns.Normal('cm_loc', lambda cm_ls: cm_ls.exp()),
+                County_log_sigma=ns.Normal('cls_loc', lambda cls_ls: cls_ls.exp()),
+                Beta_u=ns.Normal('bu_loc', lambda bu_ls: bu_ls.exp()),
+                Beta_basement=ns.Normal('bb_loc', lambda bb_ls: bb_ls.exp()),
+                Zips=ns.Plate(
+                    obs=ns.Data(),
+                ),
+            ),
+        ),
+    )
+    return P, Q
+
+
+def radon_inputs(S=7, C=10, Z=10, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    basement = (t.rand(S, C, Z, generator=g) < 0.65).to(dtype)
+    log_u = 0.53 + 0.74 * r(S, C, Z)
+    obs = 1.2 + 0.5 * r(S, C, 1) + 0.3 * basement + 0.4 * log_u + 0.7 * r(S, C, Z)
+    nm = lambda x, *names: x.refine_names(*names)
+    params = {
+        'gm_loc': 0.1 * r(), 'gm_ls': -0.3 + 0.1 * r(), 'gls_loc': 0.1 * r(), 'gls_ls': -0.3 + 0.1 * r(),
+        'sm_loc': nm(1.0 + 0.1 * r(S), 'States'), 'sm_ls': nm(-0.5 + 0.1 * r(S), 'States'),
+        'sls_loc': nm(-0.5 + 0.1 * r(S), 'States'), 'sls_ls': nm(-0.7 + 0.1 * r(S), 'States'),
+        'cm_loc': nm(1.0 + 0.1 * r(S, C), 'States', 'Counties'), 'cm_ls': nm(-0.7 + 0.1 * r(S, C), 'States', 'Counties'),
+        'cls_loc': nm(-0.3 + 0.1 * r(S, C), 'States', 'Counties'), 'cls_ls': nm(-1. + 0.1 * r(S, C), 'States', 'Counties'),
+        'bu_loc': nm(0.3 + 0.1 * r(S, C), 'States', 'Counties'), 'bu_ls': nm(-1. + 0.1 * r(S, C), 'States', 'Counties'),
+        'bb_loc': nm(0.3 + 0.1 * r(S, C), 'States', 'Counties'), 'bb_ls': nm(-1. + 0.1 * r(S, C), 'States', 'Counties'),
+    }
+    return dict(platesizes={'States': S, 'Counties': C, 'Zips': Z},
+                data={'obs': nm(obs, 'States', 'Counties', 'Zips')},
+                inputs={'basement': nm(basement, 'States', 'Counties', 'Zips'),
+                        'log_uranium': nm(log_u, 'States', 'Counties', 'Zips')},
+                params=params)
+
+
+# --------------------------------------------------------------------------- cfg4
+def timeseries_model(ns):
+    """tests/timeseries.py:15-30 (A=0.9, noise 0.1, obs noise 1)."""
+    P = ns.Plate(
+        init=ns.Normal(0, 1.),
+        T=ns.Plate(
+            ts=ns.Timeseries("init", ns.Normal(lambda prev: 0.9 * prev, 0.1)),
+            obs=ns.Normal('ts', 1.),
+        ),
+    )
+    Q = ns.Plate(
+        init=ns.Normal(0, 1),
+        T=ns.Plate(
+            ts=ns.Normal(0, 1),
+            obs=ns.Data(),
+        ),
+    )
+    return P, Q
+
+
+def timeseries_inputs(T=1000, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    x = t.zeros(T, dtype=t.float64)
+    prev = t.randn((), generator=g, dtype=t.float64)
+    for i in range(T):
+        prev = 0.9 * prev + 0.1 * t.randn((), generator=g, dtype=t.float64)
+        x[i] = prev
+    obs = (x + t.randn(T, generator=g, dtype=t.float64)).to(dtype)
+    return dict(platesizes={'T': T}, data={'obs': obs.refine_names('T')}, inputs={}, params={})
+
+
+# --------------------------------------------------------------------------- extra structure
+def model1_model(ns):
+    """tests/model1.py:5-30: Group in a nested plate, latent-dependent scale, dangling latents."""
+    P = ns.Plate(
+        ab=ns.Group(
+            a=ns.Normal(0, 1),
+            b=ns.Normal("a", 1),
+        ),
+        c=ns.Normal(0, lambda a: a.exp()),
+        p1=ns.Plate(
+            d=ns.Normal("a", 1),
+            p2=ns.Plate(
+                e=ns.Normal("d", 1.),
+            ),
+        ),
+    )
+    Q = ns.Plate(
+        ab=ns.Group(
+            a=ns.Normal("a_mean", 1),
+            b=ns.Normal("a", 1),
+        ),
+        c=ns.Normal(0, lambda a: a.exp()),
+        p1=ns.Plate(
+            d=ns.Normal("d_mean", 1),
+            p2=ns.Plate(
+                e=ns.Data(),
+            ),
+        ),
+    )
+    return P, Q
+
+
+def model1_inputs(p1=3, p2=4, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    return dict(platesizes={'p1': p1, 'p2': p2},
+                data={'e': r(p1, p2).refine_names('p1', 'p2')},
+                inputs={},
+                params={'a_mean': 0.1 * r(), 'd_mean': (0.1 * r(p1)).refine_names('p1')})
+
+
+CASES = {
+    # name: (model builder, inputs builder, kwargs for inputs, K, moment specs, joints, importance N or None)
+    'cfg1_lgl': (lgl_model, lgl_inputs, dict(T=10), 3, [('a', 'mean'), ('a', 'mean2'), ('z', 'mean'), ('z', 'mean2')], [], 7),
+    'cfg1_lglp': (lglp_model, lglp_inputs, dict(T=10), 4, [('a', 'mean'), ('z', 'mean2')], [], 5),
+    'cfg2_movielens': (movielens_model, movielens_inputs, dict(M=12, N=5, d=18), 6,
+                       [('z', 'mean'), ('mu_z', 'mean2')], [('mu_z', 'psi_z')], 6),
+    'cfg3_radon': (radon_model, radon_inputs, dict(S=3, C=4, Z=5), 4,
+                   [('County_mean', 'mean'), ('global_mean', 'mean2')], [('Beta_u', 'Beta_basement')], 9),
+    'cfg4_timeseries': (timeseries_model, timeseries_inputs, dict(T=37), 5, [('ts', 'mean'), ('ts', 'mean2')], [], None),
+    'model1': (model1_model, model1_inputs, dict(p1=3, p2=4), 4, [('d', 'mean'), ('c', 'mean2')], [('ab', 'c')], 5),
+}
+
+MOMENT_FUNCS = {'mean': (lambda x: x), 'mean2': (lambda x: x * x)}
