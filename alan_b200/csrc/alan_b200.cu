@@ -1,0 +1,475 @@
+// alan_b200.cu -- plan executor and C ABI (include/alan_b200.h) of the logPQ engine.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/alan_b200.h"
+#include "kernels.cuh"
+#include "fused.cuh"
+
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
+
+#define AB_MAGIC 0x0A1AB200
+#define AB_VERSION 1
+
+enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
+enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
+       OP_NORMAL_FAN = 8, OP_COPY = 9 };
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+
+struct alan_b200_plan {
+    std::vector<int32_t> blob;
+    int dtype, n_inputs, n_programs, n_fwd, n_bwd, sample_prog;
+    size_t ws_bytes;
+    std::vector<int> prog_start, prog_nops;
+    int sm_count;
+};
+
+struct Reader {
+    const int32_t* p;
+    int32_t i32() { return *p++; }
+    i64 i64v() { uint32_t lo = (uint32_t)p[0]; uint32_t hi = (uint32_t)p[1]; p += 2; return (i64)(((uint64_t)hi << 32) | lo); }
+    double f64() { i64 v = i64v(); double d; memcpy(&d, &v, 8); return d; }
+};
+
+struct Ctx {
+    const void* const* inputs;
+    void* const* outputs;
+    const void* const* aux;
+    char* ws;
+    cudaStream_t stream;
+    int sm_count;
+};
+
+static void* tref(Reader& r, const Ctx& c) {
+    int space = r.i32();
+    i64 v = r.i64v();
+    switch (space) {
+        case SP_WS: return c.ws + v;
+        case SP_INPUT: return (void*)c.inputs[v];
+        case SP_OUTPUT: return c.outputs[v];
+        case SP_AUX: return (void*)c.aux[v];
+    }
+    return nullptr;
+}
+
+static int grid_for(i64 n, int block, const Ctx& c, int per_sm = 8) {
+    i64 g = (n + block - 1) / block;
+    i64 cap = (i64)c.sm_count * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+static void read_dims(Reader& r, Dims& d, i64& na_total, i64& nb_total) {
+    d.n_a = r.i32();
+    int nb = r.i32();
+    d.nd = d.n_a + nb;
+    na_total = 1; nb_total = 1;
+    for (int k = 0; k < d.nd; ++k) {
+        d.size[k] = r.i32();
+        if (k < d.n_a) na_total *= d.size[k]; else nb_total *= d.size[k];
+    }
+}
+
+static void read_opnd(Reader& r, const Ctx& c, Opnd& o, int nd, bool with_mode) {
+    o.ptr = tref(r, c);
+    o.mode = 0; o.mdim = 0;
+    if (with_mode) { o.mode = r.i32(); o.mdim = r.i32(); }
+    for (int k = 0; k < nd; ++k) o.stride[k] = r.i64v();
+    for (int k = nd; k < AB_MAXD; ++k) o.stride[k] = 0;
+}
+
+template <typename T>
+static void read_prog(Reader& r, VMProg<T>& P) {
+    P.n_instr = r.i32();
+    for (int i = 0; i < P.n_instr; ++i) { P.ins[i][0] = (unsigned)r.i32(); P.ins[i][1] = (unsigned)r.i32(); }
+    int nc = r.i32();
+    for (int i = 0; i < nc; ++i) P.consts[i] = (T)r.f64();
+    P.res = r.i32();
+}
+
+template <typename T>
+static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool count_only, int* launches) {
+    Reader r{plan->blob.data() + plan->prog_start[program]};
+    int nl = 0;
+    for (int op_i = 0; op_i < plan->prog_nops[program]; ++op_i) {
+        const int32_t* op_begin = r.p;
+        int code = r.i32();
+        int nwords = r.i32();
+        if (count_only) {
+            if (code == OP_CHAIN || code == OP_CHAIN_BWD) {
+                r.p = op_begin + 2; Reader q = r;
+                // skip trefs to read T
+                int ntref = (code == OP_CHAIN) ? 3 : 5;
+                q.p += 3 * ntref;
+                q.i64v(); i64 T_ = q.i64v();
+                int lv = 0; for (i64 n = T_; n > 1; n = n / 2 + n % 2) lv++;
+                nl += lv + 1;
+            } else nl += 1;
+            r.p = op_begin + nwords;
+            continue;
+        }
+        switch (code) {
+            case OP_FILL: {
+                void* dst = tref(r, c);
+                i64 nbytes = r.i64v();
+                cudaMemsetAsync(dst, 0, (size_t)nbytes, c.stream);
+                break;
+            }
+            case OP_COPY: {
+                void* dst = tref(r, c);
+                void* src = tref(r, c);
+                i64 nbytes = r.i64v();
+                cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDeviceToDevice, c.stream);
+                break;
+            }
+            case OP_EXPR: {
+                ExprParams<T> p;
+                p.out = (T*)tref(r, c);
+                p.acc = r.i32();
+                p.scale = (T)r.f64();
+                read_dims(r, p.d, p.n_out, p.n_red);
+                p.n_leaves = r.i32();
+                for (int l = 0; l < p.n_leaves; ++l) read_opnd(r, c, p.leaf[l], p.d.nd, true);
+                read_prog(r, p.prog);
+                expr_fwd_kernel<T><<<grid_for(p.n_out, 256, c), 256, 0, c.stream>>>(p);
+                break;
+            }
+            case OP_EXPR_BWD: {
+                ExprBwdParams<T> p;
+                p.gleaf = (T*)tref(r, c);
+                p.acc = r.i32();
+                p.scale = (T)r.f64();
+                p.target = r.i32();
+                p.nsplit = r.i32();
+                read_dims(r, p.d, p.n_kept, p.n_loop);
+                read_opnd(r, c, p.gout, p.d.nd, false);
+                p.n_leaves = r.i32();
+                for (int l = 0; l < p.n_leaves; ++l) read_opnd(r, c, p.leaf[l], p.d.nd, true);
+                read_prog(r, p.prog);
+                expr_bwd_kernel<T><<<grid_for(p.n_kept * p.nsplit, 256, c), 256, 0, c.stream>>>(p);
+                break;
+            }
+            case OP_REDUCE: {
+                ReduceParams<T> p;
+                p.mode = r.i32();
+                p.out = (T*)tref(r, c);
+                p.acc = r.i32();
+                p.scale = (T)r.f64();
+                p.cadd = (T)r.f64();
+                p.nsplit = r.i32();
+                read_dims(r, p.d, p.n_out, p.n_red);
+                p.nf = r.i32();
+                for (int f = 0; f < p.nf; ++f) {
+                    p.coeff[f] = (T)r.f64();
+                    read_opnd(r, c, p.f[f], p.d.nd, false);
+                }
+                if (p.mode == R_WSUM) {
+                    read_opnd(r, c, p.lse, p.d.nd, false);
+                    read_opnd(r, c, p.gout, p.d.nd, false);
+                }
+                i64 per = (p.n_red + p.nsplit - 1) / p.nsplit;
+                if (per >= 16) {
+                    i64 threads = p.n_out * p.nsplit * 32;
+                    reduce_warp_kernel<T><<<grid_for(threads, 256, c), 256, 0, c.stream>>>(p);
+                } else {
+                    reduce_thread_kernel<T><<<grid_for(p.n_out * p.nsplit, 256, c), 256, 0, c.stream>>>(p);
+                }
+                break;
+            }
+            case OP_CHAIN: {
+                const T* ms = (const T*)tref(r, c);
+                T* levels = (T*)tref(r, c);
+                T* out = (T*)tref(r, c);
+                i64 outer = r.i64v(), Tn = r.i64v(), K = r.i64v();
+                size_t smem = (size_t)(2 * K * K + 2 * K) * sizeof(T);
+                if (smem > 48 * 1024)
+                    cudaFuncSetAttribute(chain_level_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                const T* X = ms;
+                T* Y = levels;
+                i64 n = Tn;
+                while (n > 1) {
+                    i64 no = n / 2 + n % 2;
+                    chain_level_kernel<T><<<dim3((unsigned)no, (unsigned)outer), 256, smem, c.stream>>>(X, Y, (int)n, (int)no, (int)K);
+                    X = Y;
+                    Y += outer * no * K * K;
+                    n = no;
+                }
+                chain_final_kernel<T><<<grid_for(outer * K, 128, c), 128, 0, c.stream>>>(X, out, outer * K, (int)K);
+                break;
+            }
+            case OP_CHAIN_BWD: {
+                const T* ms = (const T*)tref(r, c);
+                const T* levels = (const T*)tref(r, c);
+                const T* out = (const T*)tref(r, c);
+                const T* gout = (const T*)tref(r, c);
+                T* glevels = (T*)tref(r, c);
+                T* gms = (T*)tref(r, c);
+                i64 outer = r.i64v(), Tn = r.i64v(), K = r.i64v();
+                size_t smem = (size_t)(3 * K * K + 4 * K) * sizeof(T);
+                if (smem > 48 * 1024)
+                    cudaFuncSetAttribute(chain_level_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                // level table
+                std::vector<i64> ns; std::vector<i64> offs;
+                { i64 n = Tn, off = 0; while (n > 1) { i64 no = n / 2 + n % 2; ns.push_back(n); offs.push_back(off); off += outer * no * K * K; n = no; } }
+                int L = (int)ns.size();
+                // final: X_last is levels[offs[L-1]] (or ms when T == 1)
+                const T* Xlast = L ? levels + offs[L - 1] : ms;
+                T* gXlast = L ? glevels + offs[L - 1] : gms;
+                chain_final_bwd_kernel<T><<<grid_for(outer * K * K, 256, c), 256, 0, c.stream>>>(Xlast, out, gout, gXlast, outer * K, (int)K);
+                for (int l = L - 1; l >= 0; --l) {
+                    i64 n = ns[l], no = n / 2 + n % 2;
+                    const T* X = l ? levels + offs[l - 1] : ms;
+                    T* gX = l ? glevels + offs[l - 1] : gms;
+                    const T* gY = glevels + offs[l];
+                    chain_level_bwd_kernel<T><<<dim3((unsigned)no, (unsigned)outer), 256, smem, c.stream>>>(X, gY, gX, (int)n, (int)no, (int)K);
+                }
+                break;
+            }
+            case OP_SAMPLE: {
+                SampleParams<T> p;
+                memset(&p, 0, sizeof(p));
+                int nb = r.i32();
+                p.d.nd = nb; p.d.n_a = nb;
+                p.n_batch = 1;
+                for (int k = 0; k < nb; ++k) { p.d.size[k] = r.i32(); p.n_batch *= p.d.size[k]; }
+                p.nk = r.i32();
+                p.ktotal = 1;
+                for (int k = 0; k < p.nk; ++k) { p.ksize[k] = r.i32(); p.ktotal *= p.ksize[k]; }
+                p.nf = r.i32();
+                for (int f = 0; f < p.nf; ++f) {
+                    p.coeff[f] = (T)r.f64();
+                    read_opnd(r, c, p.f[f], nb, false);
+                    for (int k = 0; k < p.nk; ++k) p.kstride[f][k] = r.i64v();
+                    p.ng[f] = r.i32();
+                    for (int g = 0; g < p.ng[f]; ++g) { p.gstride[f][g] = r.i64v(); p.gsel[f][g] = r.i32(); }
+                }
+                p.n_idx = r.i32();
+                for (int t = 0; t < p.n_idx; ++t) {
+                    p.idxptr[t] = (const i64*)tref(r, c);
+                    for (int k = 0; k < nb; ++k) p.idxstride[t][k] = r.i64v();
+                }
+                p.u = (const double*)tref(r, c);
+                for (int k = 0; k < nb; ++k) p.ustride[k] = r.i64v();
+                for (int k = 0; k < p.nk; ++k) p.out[k] = (i64*)tref(r, c);
+                sample_kernel<T><<<grid_for(p.n_batch, 128, c), 128, 0, c.stream>>>(p);
+                break;
+            }
+            case OP_NORMAL_FAN: {
+                int rc = launch_normal_fan<T>(r, c.ws, c.inputs, c.outputs, c.stream, c.sm_count);
+                if (rc) return fail("normal_fan: bad configuration");
+                break;
+            }
+            default:
+                return fail("unknown opcode " + std::to_string(code));
+        }
+        if (r.p != op_begin + nwords)
+            return fail("blob/executor mismatch in op " + std::to_string(op_i) + " (code " + std::to_string(code) +
+                        "): consumed " + std::to_string((long)(r.p - op_begin)) + " of " + std::to_string(nwords) + " words");
+    }
+    if (launches) *launches = nl;
+    if (!count_only) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(std::string("CUDA launch error: ") + cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+extern "C" {
+
+int alan_b200_abi_version(void) { return AB_VERSION; }
+const char* alan_b200_last_error(void) { return g_err.c_str(); }
+
+int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** out) {
+    if (!blob || n_words < 10) return fail("plan blob too short");
+    if (blob[0] != AB_MAGIC) return fail("plan blob: bad magic");
+    if (blob[1] != AB_VERSION) return fail("plan blob: version mismatch");
+    alan_b200_plan* p = new alan_b200_plan();
+    p->blob.assign(blob, blob + n_words);
+    p->dtype = blob[2];
+    p->n_inputs = blob[3];
+    p->n_programs = blob[4];
+    p->ws_bytes = (size_t)(((uint64_t)(uint32_t)blob[6] << 32) | (uint32_t)blob[5]);
+    p->n_fwd = blob[7];
+    p->n_bwd = blob[8];
+    p->sample_prog = blob[9];
+    if (p->dtype != 0 && p->dtype != 1) { delete p; return fail("plan blob: dtype must be 0 (f32) or 1 (f64)"); }
+    if (n_words < (size_t)(10 + 2 * p->n_programs)) { delete p; return fail("plan blob truncated"); }
+    for (int i = 0; i < p->n_programs; ++i) {
+        p->prog_start.push_back(blob[10 + 2 * i]);
+        p->prog_nops.push_back(blob[10 + 2 * i + 1]);
+        if ((size_t)p->prog_start.back() > n_words) { delete p; return fail("plan blob: program offset out of range"); }
+    }
+    int dev = 0;
+    p->sm_count = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) p->sm_count = n;
+    } else {
+        cudaGetLastError();
+    }
+    *out = p;
+    return 0;
+}
+
+void alan_b200_plan_destroy(alan_b200_plan* p) { delete p; }
+size_t alan_b200_workspace_bytes(const alan_b200_plan* p) { return p->ws_bytes; }
+int alan_b200_num_inputs(const alan_b200_plan* p) { return p->n_inputs; }
+int alan_b200_num_programs(const alan_b200_plan* p) { return p->n_programs; }
+
+int alan_b200_program_launches(const alan_b200_plan* p, int program) {
+    if (program < 0 || program >= p->n_programs) return -1;
+    Ctx c{};
+    int n = 0;
+    if (p->dtype == 0) run_ops<float>(p, program, c, true, &n); else run_ops<double>(p, program, c, true, &n);
+    return n;
+}
+
+static int run_generic(const alan_b200_plan* p, int program, const void* const* inputs, void* const* outputs,
+                       const void* const* aux, void* ws, void* stream) {
+    if (!p) return fail("null plan");
+    if (program < 0 || program >= p->n_programs) return fail("program index out of range");
+    Ctx c{inputs, outputs, aux, (char*)ws, (cudaStream_t)stream, p->sm_count};
+    return p->dtype == 0 ? run_ops<float>(p, program, c, false, nullptr) : run_ops<double>(p, program, c, false, nullptr);
+}
+
+int alan_b200_run(const alan_b200_plan* p, int program, const void* const* inputs, void* const* outputs,
+                  void* ws, void* stream) {
+    return run_generic(p, program, inputs, outputs, nullptr, ws, stream);
+}
+
+int alan_b200_logpq_fwd(const alan_b200_plan* p, int segment, const void* const* inputs, void* lp_out,
+                        void* ws, void* stream) {
+    if (!p) return fail("null plan");
+    if (segment < 0 || segment >= p->n_fwd) return fail("forward segment out of range");
+    void* outs[1] = {lp_out};
+    return run_generic(p, segment, inputs, outs, nullptr, ws, stream);
+}
+
+int alan_b200_logpq_bwd(const alan_b200_plan* p, int segment, const void* const* inputs, const void* grad_lp,
+                        void* const* grads_out, void* ws, void* stream) {
+    if (!p) return fail("null plan");
+    if (segment < 0 || segment >= p->n_bwd) return fail("backward segment out of range");
+    const void* aux[1] = {grad_lp};
+    return run_generic(p, p->n_fwd + segment, inputs, grads_out, aux, ws, stream);
+}
+
+int alan_b200_resample(const alan_b200_plan* p, const void* const* inputs, const double* const* uniforms,
+                       int64_t* const* idx_out, void* ws, void* stream) {
+    if (!p) return fail("null plan");
+    if (p->sample_prog < 0) return fail("plan was built without a resampling program");
+    return run_generic(p, p->sample_prog, inputs, (void* const*)idx_out, (const void* const*)uniforms, ws, stream);
+}
+
+int alan_b200_gather(const void* x, const int64_t* idx, void* out, int elem_bytes, int64_t N, int64_t outer,
+                     int64_t K, int64_t inner, int64_t outer_div, void* stream) {
+    i64 total = N * outer * inner;
+    if (total <= 0) return 0;
+    int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    if (elem_bytes == 4)
+        gather_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const i64*)idx, (float*)out, N, outer, K, inner, outer_div);
+    else if (elem_bytes == 8)
+        gather_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x, (const i64*)idx, (double*)out, N, outer, K, inner, outer_div);
+    else return fail("gather: element size must be 4 or 8 bytes");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("CUDA launch error: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+// ---- unit-level ops --------------------------------------------------------------------
+
+extern "C++" template <typename T>
+int lse_eps_impl(const void* x, void* out, i64 n_out, i64 n_red, cudaStream_t st) {
+    ReduceParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.d.nd = 2; p.d.n_a = 1; p.d.size[0] = (int)n_out; p.d.size[1] = (int)n_red;
+    p.mode = R_LSE_EPS; p.nf = 1; p.f[0].ptr = x; p.f[0].stride[0] = n_red; p.f[0].stride[1] = 1;
+    p.coeff[0] = T(1); p.out = (T*)out; p.acc = 0; p.scale = T(1); p.cadd = T(0);
+    p.n_out = n_out; p.n_red = n_red; p.nsplit = 1;
+    i64 blocks = (n_out * 32 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+    reduce_warp_kernel<T><<<(int)blocks, 256, 0, st>>>(p);
+    return 0;
+}
+
+int alan_b200_lse_eps(const void* x, void* out, int64_t n_out, int64_t n_red, int dtype, void* stream) {
+    if (n_out <= 0 || n_red <= 0) return fail("lse_eps: empty input");
+    if (dtype == 0) lse_eps_impl<float>(x, out, n_out, n_red, (cudaStream_t)stream);
+    else if (dtype == 1) lse_eps_impl<double>(x, out, n_out, n_red, (cudaStream_t)stream);
+    else return fail("lse_eps: dtype must be 0 or 1");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("CUDA launch error: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int64_t alan_b200_chain_scratch_elems(int64_t outer, int64_t T, int64_t K) {
+    i64 n = T, tot = 0;
+    while (n > 1) { i64 no = n / 2 + n % 2; tot += outer * no * K * K; n = no; }
+    return tot > 0 ? tot : 1;
+}
+
+extern "C++" template <typename T>
+int chain_impl(const void* ms_, void* levels_, void* out_, i64 outer, i64 Tn, i64 K, cudaStream_t st) {
+    size_t smem = (size_t)(2 * K * K + 2 * K) * sizeof(T);
+    if (smem > 200 * 1024) return 1;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(chain_level_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const T* X = (const T*)ms_;
+    T* Y = (T*)levels_;
+    i64 n = Tn;
+    while (n > 1) {
+        i64 no = n / 2 + n % 2;
+        chain_level_kernel<T><<<dim3((unsigned)no, (unsigned)outer), 256, smem, st>>>(X, Y, (int)n, (int)no, (int)K);
+        X = Y; Y += outer * no * K * K; n = no;
+    }
+    i64 rows = outer * K;
+    chain_final_kernel<T><<<(int)((rows + 127) / 128), 128, 0, st>>>(X, (T*)out_, rows, (int)K);
+    return 0;
+}
+
+int alan_b200_logmmexp_chain(const void* ms, void* levels, void* out, int64_t outer, int64_t T, int64_t K,
+                             int dtype, void* stream) {
+    if (outer <= 0 || T <= 0 || K <= 0) return fail("logmmexp_chain: empty input");
+    int rc = dtype == 0 ? chain_impl<float>(ms, levels, out, outer, T, K, (cudaStream_t)stream)
+           : dtype == 1 ? chain_impl<double>(ms, levels, out, outer, T, K, (cudaStream_t)stream) : 2;
+    if (rc == 1) return fail("logmmexp_chain: K too large for shared memory");
+    if (rc == 2) return fail("logmmexp_chain: dtype must be 0 or 1");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("CUDA launch error: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C++" template <typename T>
+void normal_bcast_impl(const void* v, const void* loc, const void* scale, void* out, i64 nc, i64 ne,
+                              const int64_t* vs, const int64_t* ls, const int64_t* ss, cudaStream_t st) {
+    ExprParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.d.nd = 2; p.d.n_a = 1; p.d.size[0] = (int)nc; p.d.size[1] = (int)ne;
+    p.n_leaves = 3;
+    const void* ptrs[3] = {v, loc, scale};
+    const int64_t* strs[3] = {vs, ls, ss};
+    for (int l = 0; l < 3; ++l) { p.leaf[l].ptr = ptrs[l]; p.leaf[l].stride[0] = strs[l][0]; p.leaf[l].stride[1] = strs[l][1]; }
+    p.prog.n_instr = 4;
+    for (int l = 0; l < 3; ++l) { p.prog.ins[l][0] = V_LOAD | (l << 8) | (l << 16); p.prog.ins[l][1] = 0; }
+    p.prog.ins[3][0] = V_NORMAL | (3 << 8) | (0 << 16) | (1u << 24); p.prog.ins[3][1] = 2;
+    p.prog.res = 3;
+    p.out = (T*)out; p.acc = 0; p.scale = T(1); p.n_out = nc; p.n_red = ne;
+    i64 blocks = (nc + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+    expr_fwd_kernel<T><<<(int)blocks, 256, 0, st>>>(p);
+}
+
+int alan_b200_normal_logpdf_bcast(const void* value, const void* loc, const void* scale, void* out,
+                                  int64_t n_cells, int64_t n_event, const int64_t* vs, const int64_t* ls,
+                                  const int64_t* ss, int dtype, void* stream) {
+    if (n_cells <= 0 || n_event <= 0) return fail("normal_logpdf_bcast: empty input");
+    if (dtype == 0) normal_bcast_impl<float>(value, loc, scale, out, n_cells, n_event, vs, ls, ss, (cudaStream_t)stream);
+    else if (dtype == 1) normal_bcast_impl<double>(value, loc, scale, out, n_cells, n_event, vs, ls, ss, (cudaStream_t)stream);
+    else return fail("normal_logpdf_bcast: dtype must be 0 or 1");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("CUDA launch error: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

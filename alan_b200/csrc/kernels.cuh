@@ -1,0 +1,488 @@
+// kernels.cuh -- generic (any plate tree / any axes) kernels of the logPQ engine.
+//
+//   expr_fwd / expr_bwd   factor evaluation K1+K2 and its adjoint
+//   reduce_*              log-semiring contraction K3, plate sum K4, adjoint weights K6
+//   chain_*               Timeseries log-matmul chain K5 and its adjoint
+//   sample_kernel         posterior K resampling K7
+//   gather_kernel         sample gather K8
+//
+// All reductions are fixed-order (sequential per thread, xor-butterfly per warp, planner-
+// chosen split counts): results are bit-reproducible run to run; no float atomics anywhere.
+#pragma once
+#include "vm.cuh"
+
+// ------------------------------------------------------------------------------------------
+// leaf loads
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T load_leaf(const Opnd& L, i64 off, const int* idx) {
+    const T* p = (const T*)L.ptr;
+    if (L.mode == 0) return p[off];
+    if (L.mode == 1) return idx[L.mdim] >= 1 ? p[off - L.stride[L.mdim]] : T(0);   // prev[t] = x[t-1]
+    return idx[L.mdim] == 0 ? p[off] : T(0);                                         // init only at t = 0
+}
+
+// ------------------------------------------------------------------------------------------
+// K1/K2: factor expression, summed over the event dims
+//   reference: Dist.log_prob -> TorchDimDist.log_prob -> sum_non_dim (dist.py:297-302,
+//   TorchDimDist.py:127-162); lambdas of dist.py:221-227 fused in.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct ExprParams {
+    Dims d;                 // n_a = kept (output) dims, the rest are summed
+    int n_leaves;
+    Opnd leaf[AB_MAXL];
+    VMProg<T> prog;
+    T* out;
+    int acc;
+    T scale;
+    i64 n_out, n_red;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) expr_fwd_kernel(const __grid_constant__ ExprParams<T> p) {
+    T reg[AB_NREG];
+    T lv[AB_MAXL];
+    int idx[AB_MAXD];
+    i64 base[AB_MAXL];
+    for (i64 o = (i64)blockIdx.x * blockDim.x + threadIdx.x; o < p.n_out; o += (i64)gridDim.x * blockDim.x) {
+        unravel(o, p.d, 0, p.d.n_a, idx);
+        for (int l = 0; l < p.n_leaves; ++l) base[l] = dot_stride(p.leaf[l], idx, 0, p.d.n_a);
+        T sum = T(0);
+        for (i64 r = 0; r < p.n_red; ++r) {
+            unravel(r, p.d, p.d.n_a, p.d.nd, idx);
+            for (int l = 0; l < p.n_leaves; ++l)
+                lv[l] = load_leaf<T>(p.leaf[l], base[l] + dot_stride(p.leaf[l], idx, p.d.n_a, p.d.nd), idx);
+            sum += vm_eval(p.prog, lv, reg);
+        }
+        T v = p.scale * sum;
+        p.out[o] = p.acc ? p.out[o] + v : v;
+    }
+}
+
+// Adjoint w.r.t. one leaf, gather style: one thread per (leaf element, split); the thread
+// loops over every iteration point that read the element.  No atomics.
+template <typename T>
+struct ExprBwdParams {
+    Dims d;                 // n_a = dims the target leaf carries (thread index), rest are looped
+    int n_leaves;
+    Opnd leaf[AB_MAXL];
+    Opnd gout;              // adjoint of the expression output (stride 0 on event dims)
+    VMProg<T> prog;
+    int target;
+    T* gleaf;
+    int acc;
+    T scale;
+    i64 n_kept, n_loop;
+    int nsplit;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) expr_bwd_kernel(const __grid_constant__ ExprBwdParams<T> p) {
+    T reg[AB_NREG];
+    T adj[AB_NREG];
+    T lv[AB_MAXL];
+    int idx[AB_MAXD];
+    i64 base[AB_MAXL];
+    const Opnd& tg = p.leaf[p.target];
+    i64 total = p.n_kept * p.nsplit;
+    for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (i64)gridDim.x * blockDim.x) {
+        i64 e = w % p.n_kept;
+        int s = (int)(w / p.n_kept);
+        unravel(e, p.d, 0, p.d.n_a, idx);
+        bool live = true;
+        if (tg.mode == 1) {                       // leaf element t feeds iteration point t + 1
+            idx[tg.mdim] += 1;
+            live = idx[tg.mdim] < p.d.size[tg.mdim];
+        }
+        T sum = T(0);
+        if (live) {
+            for (int l = 0; l < p.n_leaves; ++l) base[l] = dot_stride(p.leaf[l], idx, 0, p.d.n_a);
+            i64 gbase = dot_stride(p.gout, idx, 0, p.d.n_a);
+            for (i64 j = s; j < p.n_loop; j += p.nsplit) {
+                unravel(j, p.d, p.d.n_a, p.d.nd, idx);
+                if (tg.mode == 2 && idx[tg.mdim] != 0) continue;
+                for (int l = 0; l < p.n_leaves; ++l)
+                    lv[l] = load_leaf<T>(p.leaf[l], base[l] + dot_stride(p.leaf[l], idx, p.d.n_a, p.d.nd), idx);
+                vm_eval(p.prog, lv, reg);
+                T g = vm_grad(p.prog, reg, adj, p.target);
+                T go = ((const T*)p.gout.ptr)[gbase + dot_stride(p.gout, idx, p.d.n_a, p.d.nd)];
+                sum += g * go;
+            }
+        }
+        T v = p.scale * sum;
+        if (p.nsplit > 1) p.gleaf[(i64)s * p.n_kept + e] = v;
+        else p.gleaf[e] = p.acc ? p.gleaf[e] + v : v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3/K4/K6: reductions over K axes / plate axes of a broadcast sum of factors
+//   mode 0 SUM      out[o] = sum_r s(o,r)                          (logpq.py:149 plate sum)
+//   mode 1 LSE_EPS  out[o] = log(sum_r exp(s - max_r s) + eps) + max_r s   (utils.py:207-222)
+//   mode 2 LSE      out[o] = logsumexp_r s                         (logpq.py:139)
+//   mode 3 WSUM     out[o] = sum_r gout(o,r) * exp(s(o,r) + cadd - lse(o,r))   (adjoint of LSE; cadd is the
+//                   constant the forward op added after its LSE, so that exp(.) is the softmax weight)
+//   with s(o,r) = sum_f coeff_f * F_f[o,r] (broadcast through zero strides).
+// ------------------------------------------------------------------------------------------
+enum { R_SUM = 0, R_LSE_EPS = 1, R_LSE = 2, R_WSUM = 3 };
+
+template <typename T>
+struct ReduceParams {
+    Dims d;                 // n_a = output dims, rest reduced
+    int mode;
+    int nf;
+    Opnd f[AB_MAXL];
+    T coeff[AB_MAXL];
+    Opnd lse, gout;         // WSUM only
+    T* out;
+    int acc;
+    T scale, cadd;
+    i64 n_out, n_red;
+    int nsplit;
+};
+
+template <typename T>
+__device__ __forceinline__ T factor_sum(const ReduceParams<T>& p, const i64* base, const int* idx) {
+    T s = T(0);
+    for (int f = 0; f < p.nf; ++f) {
+        i64 off = base[f] + dot_stride(p.f[f], idx, p.d.n_a, p.d.nd);
+        s += p.coeff[f] * ((const T*)p.f[f].ptr)[off];
+    }
+    return s;
+}
+
+template <typename T>
+__device__ __forceinline__ void reduce_store(const ReduceParams<T>& p, i64 o, int s, T res) {
+    if (p.nsplit > 1) { p.out[(i64)s * p.n_out + o] = res; return; }
+    T v = p.scale * res + (p.mode == R_WSUM ? T(0) : p.cadd);
+    p.out[o] = p.acc ? p.out[o] + v : v;
+}
+
+// one warp per (output, split); lanes stride over the reduced index
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_warp_kernel(const __grid_constant__ ReduceParams<T> p) {
+    int idx[AB_MAXD];
+    i64 base[AB_MAXL];
+    const int lane = threadIdx.x & 31;
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    const i64 total = p.n_out * p.nsplit;
+    const i64 chunk = (p.n_red + p.nsplit - 1) / p.nsplit;
+    for (i64 w = warp; w < total; w += nwarps) {
+        i64 o = w % p.n_out;
+        int s = (int)(w / p.n_out);
+        i64 lo = (i64)s * chunk, hi = lo + chunk < p.n_red ? lo + chunk : p.n_red;
+        unravel(o, p.d, 0, p.d.n_a, idx);
+        for (int f = 0; f < p.nf; ++f) base[f] = dot_stride(p.f[f], idx, 0, p.d.n_a);
+        T res;
+        if (p.mode == R_SUM) {
+            T a = T(0);
+            for (i64 j = lo + lane; j < hi; j += 32) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); a += factor_sum(p, base, idx); }
+            res = warp_sum(a);
+        } else if (p.mode == R_WSUM) {
+            i64 lbase = dot_stride(p.lse, idx, 0, p.d.n_a), gbase = dot_stride(p.gout, idx, 0, p.d.n_a);
+            T a = T(0);
+            for (i64 j = lo + lane; j < hi; j += 32) {
+                unravel(j, p.d, p.d.n_a, p.d.nd, idx);
+                T sv = factor_sum(p, base, idx);
+                T l = ((const T*)p.lse.ptr)[lbase + dot_stride(p.lse, idx, p.d.n_a, p.d.nd)];
+                T g = ((const T*)p.gout.ptr)[gbase + dot_stride(p.gout, idx, p.d.n_a, p.d.nd)];
+                a += g * ab_exp(sv + p.cadd - l);
+            }
+            res = warp_sum(a);
+        } else {
+            T m = neg_inf<T>();
+            for (i64 j = lo + lane; j < hi; j += 32) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); m = ab_max(m, factor_sum(p, base, idx)); }
+            m = warp_max(m);
+            T a = T(0);
+            for (i64 j = lo + lane; j < hi; j += 32) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); a += ab_exp(factor_sum(p, base, idx) - m); }
+            a = warp_sum(a);
+            res = (p.mode == R_LSE_EPS ? ab_log(a + Eps<T>::v()) : ab_log(a)) + m;
+        }
+        if (lane == 0) reduce_store(p, o, s, res);
+    }
+}
+
+// one thread per (output, split): small reduced extent (or none: plain broadcast add)
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_thread_kernel(const __grid_constant__ ReduceParams<T> p) {
+    int idx[AB_MAXD];
+    i64 base[AB_MAXL];
+    const i64 total = p.n_out * p.nsplit;
+    const i64 chunk = (p.n_red + p.nsplit - 1) / p.nsplit;
+    for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (i64)gridDim.x * blockDim.x) {
+        i64 o = w % p.n_out;
+        int s = (int)(w / p.n_out);
+        i64 lo = (i64)s * chunk, hi = lo + chunk < p.n_red ? lo + chunk : p.n_red;
+        unravel(o, p.d, 0, p.d.n_a, idx);
+        for (int f = 0; f < p.nf; ++f) base[f] = dot_stride(p.f[f], idx, 0, p.d.n_a);
+        T res;
+        if (p.mode == R_SUM) {
+            T a = T(0);
+            for (i64 j = lo; j < hi; ++j) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); a += factor_sum(p, base, idx); }
+            res = a;
+        } else if (p.mode == R_WSUM) {
+            i64 lbase = dot_stride(p.lse, idx, 0, p.d.n_a), gbase = dot_stride(p.gout, idx, 0, p.d.n_a);
+            T a = T(0);
+            for (i64 j = lo; j < hi; ++j) {
+                unravel(j, p.d, p.d.n_a, p.d.nd, idx);
+                T sv = factor_sum(p, base, idx);
+                T l = ((const T*)p.lse.ptr)[lbase + dot_stride(p.lse, idx, p.d.n_a, p.d.nd)];
+                T g = ((const T*)p.gout.ptr)[gbase + dot_stride(p.gout, idx, p.d.n_a, p.d.nd)];
+                a += g * ab_exp(sv + p.cadd - l);
+            }
+            res = a;
+        } else {
+            T m = neg_inf<T>();
+            for (i64 j = lo; j < hi; ++j) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); m = ab_max(m, factor_sum(p, base, idx)); }
+            T a = T(0);
+            for (i64 j = lo; j < hi; ++j) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); a += ab_exp(factor_sum(p, base, idx) - m); }
+            res = (p.mode == R_LSE_EPS ? ab_log(a + Eps<T>::v()) : ab_log(a)) + m;
+        }
+        reduce_store(p, o, s, res);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: Timeseries chain.  One CTA per (pair, outer).  reference utils.py:478-510.
+//   C[i,k] = log( sum_j exp(A[i,j]-a_i) exp(B[j,k]-b_k) + eps ) + a_i + b_k
+//   a_i = max_j A[i,j], b_k = max_j B[j,k]; the odd tail of a level is carried unreduced.
+// Dynamic smem: 2*K*K + 2*K elements.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) chain_level_kernel(const T* __restrict__ X, T* __restrict__ Y,
+                                                          int n_in, int n_outl, int K) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* EA = (T*)smem_raw;
+    T* EB = EA + K * K;
+    T* am = EB + K * K;
+    T* bm = am + K;
+    const int i_out = blockIdx.x, outer = blockIdx.y;
+    const i64 KK = (i64)K * K;
+    const T* Xo = X + (i64)outer * n_in * KK;
+    T* Yo = Y + (i64)outer * n_outl * KK + (i64)i_out * KK;
+    const int npairs = n_in / 2;
+    if (i_out >= npairs) {                      // carried remainder (last element of this level)
+        const T* src = Xo + (i64)(n_in - 1) * KK;
+        for (int e = threadIdx.x; e < KK; e += blockDim.x) Yo[e] = src[e];
+        return;
+    }
+    const T* A = Xo + (i64)(2 * i_out) * KK;
+    const T* B = A + KK;
+    for (int e = threadIdx.x; e < KK; e += blockDim.x) { EA[e] = A[e]; EB[e] = B[e]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        T m = neg_inf<T>();
+        for (int j = 0; j < K; ++j) m = ab_max(m, EA[i * K + j]);
+        am[i] = m;
+        T n = neg_inf<T>();
+        for (int j = 0; j < K; ++j) n = ab_max(n, EB[j * K + i]);
+        bm[i] = n;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < KK; e += blockDim.x) {
+        EA[e] = ab_exp(EA[e] - am[e / K]);
+        EB[e] = ab_exp(EB[e] - bm[e % K]);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < KK; e += blockDim.x) {
+        int i = e / K, k = e % K;
+        T acc = T(0);
+        for (int j = 0; j < K; ++j) acc += EA[i * K + j] * EB[j * K + k];
+        Yo[e] = ab_log(acc + Eps<T>::v()) + am[i] + bm[k];
+    }
+}
+
+// out[outer, i] = logsumexp_k X[outer, i, k]   (no eps; torch.logsumexp, logpq.py:139)
+template <typename T>
+__global__ void chain_final_kernel(const T* __restrict__ X, T* __restrict__ out, i64 n_rows, int K) {
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (i64)gridDim.x * blockDim.x) {
+        const T* x = X + r * K;
+        T m = neg_inf<T>();
+        for (int k = 0; k < K; ++k) m = ab_max(m, x[k]);
+        T mm = (m == neg_inf<T>()) ? T(0) : m;
+        T a = T(0);
+        for (int k = 0; k < K; ++k) a += ab_exp(x[k] - mm);
+        out[r] = ab_log(a) + mm;
+    }
+}
+
+template <typename T>
+__global__ void chain_final_bwd_kernel(const T* __restrict__ X, const T* __restrict__ out,
+                                       const T* __restrict__ gout, T* __restrict__ gX, i64 n_rows, int K) {
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n_rows * K; e += (i64)gridDim.x * blockDim.x) {
+        i64 r = e / K;
+        gX[e] = gout[r] * ab_exp(X[e] - out[r]);
+    }
+}
+
+// Adjoint of one chain level, one CTA per (output element, outer).  Includes the path through
+// the amax shifts (weight eps/(P+eps), split evenly among ties as torch.amax does): the shifted
+// product P can be << 1, so that term is visible at 1e-5 (SURVEY.md "hard parts").
+// Dynamic smem: 3*K*K + 4*K elements.
+template <typename T>
+__global__ void __launch_bounds__(256) chain_level_bwd_kernel(const T* __restrict__ X, const T* __restrict__ gY,
+                                                              T* __restrict__ gX, int n_in, int n_outl, int K) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* EA = (T*)smem_raw;
+    T* EB = EA + K * K;
+    T* D = EB + K * K;      // gY / (P + eps)
+    T* am = D + K * K;
+    T* bm = am + K;
+    T* ga = bm + K;         // adjoint of a_i
+    T* gb = ga + K;         // adjoint of b_k
+    const int i_out = blockIdx.x, outer = blockIdx.y;
+    const i64 KK = (i64)K * K;
+    const T* Xo = X + (i64)outer * n_in * KK;
+    T* gXo = gX + (i64)outer * n_in * KK;
+    const T* g = gY + (i64)outer * n_outl * KK + (i64)i_out * KK;
+    const int npairs = n_in / 2;
+    if (i_out >= npairs) {
+        T* dst = gXo + (i64)(n_in - 1) * KK;
+        for (int e = threadIdx.x; e < KK; e += blockDim.x) dst[e] = g[e];
+        return;
+    }
+    const T* A = Xo + (i64)(2 * i_out) * KK;
+    const T* B = A + KK;
+    T* gA = gXo + (i64)(2 * i_out) * KK;
+    T* gB = gA + KK;
+    for (int e = threadIdx.x; e < KK; e += blockDim.x) { EA[e] = A[e]; EB[e] = B[e]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        T m = neg_inf<T>(), n = neg_inf<T>();
+        for (int j = 0; j < K; ++j) { m = ab_max(m, EA[i * K + j]); n = ab_max(n, EB[j * K + i]); }
+        am[i] = m; bm[i] = n;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < KK; e += blockDim.x) {
+        EA[e] = ab_exp(EA[e] - am[e / K]);
+        EB[e] = ab_exp(EB[e] - bm[e % K]);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < KK; e += blockDim.x) {
+        int i = e / K, k = e % K;
+        T acc = T(0);
+        for (int j = 0; j < K; ++j) acc += EA[i * K + j] * EB[j * K + k];
+        D[e] = g[e] / (acc + Eps<T>::v());
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        T sa = T(0), sb = T(0);
+        for (int k = 0; k < K; ++k) { sa += D[i * K + k]; sb += D[k * K + i]; }
+        ga[i] = sa * Eps<T>::v();
+        gb[i] = sb * Eps<T>::v();
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < KK; e += blockDim.x) {
+        int i = e / K, j = e % K;
+        // gA[i,j]
+        T s = T(0);
+        for (int k = 0; k < K; ++k) s += D[i * K + k] * EB[j * K + k];
+        T v = s * EA[e];
+        if (A[e] == am[i]) { int ties = 0; for (int jj = 0; jj < K; ++jj) ties += (A[i * K + jj] == am[i]); v += ga[i] / T(ties); }
+        gA[e] = v;
+        // gB[i,j] viewed as B[j'=i, k=j]
+        int jr = i, k = j;
+        T s2 = T(0);
+        for (int ii = 0; ii < K; ++ii) s2 += EA[ii * K + jr] * D[ii * K + k];
+        T v2 = s2 * EB[e];
+        if (B[e] == bm[k]) { int ties = 0; for (int jj = 0; jj < K; ++jj) ties += (B[jj * K + k] == bm[k]); v2 += gb[k] / T(ties); }
+        gB[e] = v2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: posterior resampling of one contraction step (reference reduce_Ks.py:51-75).
+// One thread per (n, plate cell).  lp_j = sum_f coeff_f F_f gathered at the already-sampled
+// parent indices; p_j = exp(double(lp_j) - max); index = first j with cumsum_j >= u * total;
+// j is unravelled row-major over the step's K axes (unravel_index.py:97-100).
+// ------------------------------------------------------------------------------------------
+#define AB_MAXK 4
+#define AB_MAXG 6
+#define AB_MAXIDX 16
+template <typename T>
+struct SampleParams {
+    Dims d;                              // batch dims: [N, plates...]; n_a = nd
+    int nk; int ksize[AB_MAXK]; i64 ktotal;
+    int nf;
+    Opnd f[AB_MAXL];                     // strides over batch dims
+    T coeff[AB_MAXL];
+    i64 kstride[AB_MAXL][AB_MAXK];
+    int ng[AB_MAXL];
+    i64 gstride[AB_MAXL][AB_MAXG];
+    int gsel[AB_MAXL][AB_MAXG];          // which idx tensor
+    int n_idx;
+    const i64* idxptr[AB_MAXIDX];
+    i64 idxstride[AB_MAXIDX][AB_MAXD];
+    const double* u;
+    i64 ustride[AB_MAXD];
+    i64* out[AB_MAXK];
+    i64 n_batch;
+};
+
+template <typename T>
+__device__ __forceinline__ T sample_lp(const SampleParams<T>& p, const i64* base, i64 j) {
+    int kidx[AB_MAXK];
+    for (int k = p.nk - 1; k >= 0; --k) { kidx[k] = (int)(j % p.ksize[k]); j /= p.ksize[k]; }
+    T s = T(0);
+    for (int f = 0; f < p.nf; ++f) {
+        i64 off = base[f];
+        for (int k = 0; k < p.nk; ++k) off += (i64)kidx[k] * p.kstride[f][k];
+        s += p.coeff[f] * ((const T*)p.f[f].ptr)[off];
+    }
+    return s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) sample_kernel(const __grid_constant__ SampleParams<T> p) {
+    int idx[AB_MAXD];
+    i64 base[AB_MAXL];
+    i64 gv[AB_MAXIDX];
+    for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < p.n_batch; b += (i64)gridDim.x * blockDim.x) {
+        unravel(b, p.d, 0, p.d.nd, idx);
+        for (int t = 0; t < p.n_idx; ++t) {
+            i64 off = 0;
+            for (int k = 0; k < p.d.nd; ++k) off += (i64)idx[k] * p.idxstride[t][k];
+            gv[t] = p.idxptr[t][off];
+        }
+        for (int f = 0; f < p.nf; ++f) {
+            i64 off = dot_stride(p.f[f], idx, 0, p.d.nd);
+            for (int g = 0; g < p.ng[f]; ++g) off += gv[p.gsel[f][g]] * p.gstride[f][g];
+            base[f] = off;
+        }
+        i64 uoff = 0;
+        for (int k = 0; k < p.d.nd; ++k) uoff += (i64)idx[k] * p.ustride[k];
+        const double u = p.u[uoff];
+        T m = neg_inf<T>();
+        for (i64 j = 0; j < p.ktotal; ++j) m = ab_max(m, sample_lp(p, base, j));
+        double total = 0.0;
+        for (i64 j = 0; j < p.ktotal; ++j) total += exp((double)sample_lp(p, base, j) - (double)m);
+        const double thr = u * total;
+        double c = 0.0;
+        i64 pick = p.ktotal - 1;
+        for (i64 j = 0; j < p.ktotal; ++j) {
+            c += exp((double)sample_lp(p, base, j) - (double)m);
+            if (!(c < thr)) { pick = j; break; }
+        }
+        for (int k = p.nk - 1; k >= 0; --k) { p.out[k][b] = pick % p.ksize[k]; pick /= p.ksize[k]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K8: gather samples at resampled indices (reference Sample.py:359-381).
+// x: [outer, K, inner]; idx: [N, outer / outer_div]; out: [N, outer, inner]; 4- or 8-byte elements.
+// ------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void gather_kernel(const E* __restrict__ x, const i64* __restrict__ idx, E* __restrict__ out,
+                              i64 N, i64 outer, i64 K, i64 inner, i64 outer_div) {
+    const i64 total = N * outer * inner;
+    const i64 og = outer / outer_div;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        i64 in = e % inner;
+        i64 o = (e / inner) % outer;
+        i64 n = e / (inner * outer);
+        i64 k = idx[n * og + o / outer_div];
+        out[e] = x[(o * K + k) * inner + in];
+    }
+}

@@ -1,0 +1,1102 @@
+"""Plan compiler: model tree + tensor signature -> static program for libalan_b200.so.
+
+The reference walks the P/Q plate tree in Python on every call (src/alan/logpq.py:15-155,
+257-332), builds torch.distributions objects, and lets autograd + checkpointing derive the
+backward pass.  Here the walk happens ONCE per (model, shapes): it emits
+  * a forward program  (factor expressions, log-semiring contractions, plate sums, chains),
+  * a backward program (hand-derived adjoints of exactly those ops, pruned to what is needed),
+  * a resampling program (top-down categorical draws over the retained factors),
+as a flat list of ops over contiguous HBM tensors, serialised to an int32 blob that the C ABI
+(include/alan_b200.h) executes with one host call per program.
+
+Data layout in HBM: every tensor is contiguous row-major `[named axes..., positional dims...]`;
+named axes are plates (program order) followed by K axes (program order) unless a kernel asks
+for something else.  Factor tensors are materialised at their natural rank (cells), never at
+cells x event (the reference's `[M,Kz,d,Kmu,Kpsi]` broadcast never exists).
+"""
+from __future__ import annotations
+
+import math
+import struct
+import types
+import numbers
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from .model import Plate, Dist, Data, Timeseries, datagroup, Kname, function_arguments, DISCRETE_ARGS
+from .path import greedy_path
+from .trace import Expr, trace_function, UNARY, BINARY
+
+MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
+MAGIC, VERSION = 0x0A1AB200, 1
+SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
+OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY = range(1, 10)
+R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
+HOIST_RATIO = 16
+
+VOPS = {'load': 0, 'const': 1, 'add': 2, 'sub': 3, 'mul': 4, 'div': 5, 'neg': 6, 'exp': 7, 'log': 8, 'sigmoid': 9,
+        'square': 10, 'sqrt': 11, 'reciprocal': 12, 'softplus': 13, 'tanh': 14, 'abs': 15, 'log1p': 16, 'pow': 17,
+        'lgamma': 18, 'mov': 19,
+        'Normal': 32, 'Bernoulli_logits': 33, 'Bernoulli_probs': 34, 'LogNormal': 35, 'Laplace': 36,
+        'Exponential': 37, 'Gamma': 38, 'Beta': 39, 'Poisson': 40, 'Cauchy': 41, 'HalfNormal': 42, 'Uniform': 43,
+        'StudentT': 44}
+
+# density op -> order of the distribution arguments after the value operand
+DENSITY_ARGS = {
+    'Normal': ('loc', 'scale'), 'LogNormal': ('loc', 'scale'), 'Laplace': ('loc', 'scale'),
+    'Cauchy': ('loc', 'scale'), 'Exponential': ('rate',), 'Gamma': ('concentration', 'rate'),
+    'Beta': ('concentration1', 'concentration0'), 'Poisson': ('rate',), 'HalfNormal': ('scale',),
+    'Uniform': ('low', 'high'), 'StudentT': ('df', 'loc', 'scale'),
+}
+
+
+# ----------------------------------------------------------------------------------------
+# physical tensors and dims
+# ----------------------------------------------------------------------------------------
+class PT:
+    """A contiguous tensor in HBM: `[axes..., pos...]` row-major."""
+    _next = 0
+
+    def __init__(self, axes, pos_shape, sizes, space, index=0, offset=0, name=''):
+        self.id = PT._next
+        PT._next += 1
+        self.axes = tuple(axes)
+        self.pos_shape = tuple(int(s) for s in pos_shape)
+        self.shape = tuple(int(sizes[a]) for a in self.axes) + self.pos_shape
+        self.space, self.index, self.offset, self.name = space, index, offset, name
+
+    @property
+    def numel(self):
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+    def cstrides(self):
+        st, acc = [], 1
+        for s in reversed(self.shape):
+            st.append(acc)
+            acc *= s
+        return list(reversed(st))
+
+    def __repr__(self):
+        return f"PT#{self.id}<{self.name}:{self.axes}+{self.pos_shape}@{self.space}>"
+
+
+@dataclass(frozen=True)
+class LeafRef:
+    """How an op reads a tensor: optional axis renaming (Timeseries prev) and shift mode."""
+    pt: PT
+    rename: tuple = ()          # ((name seen by op, axis name of pt), ...)
+    mode: int = 0
+    mdim: Optional[str] = None  # named axis the mode refers to
+
+    def stride(self, dim):
+        kind, key, size = dim
+        st = self.pt.cstrides()
+        if kind == 'ax':
+            rn = dict(self.rename)
+            if key not in rn and key in rn.values():
+                return 0                       # the tensor's own axis is seen under another name here
+            name = rn.get(key, key)
+            if name in self.pt.axes:
+                i = self.pt.axes.index(name)
+                return st[i] if self.pt.shape[i] > 1 else 0
+            return 0
+        k = key                                # event dim, counted from the right
+        n = len(self.pt.pos_shape)
+        if k < n:
+            i = len(self.pt.axes) + n - 1 - k
+            return st[i] if self.pt.shape[i] > 1 else 0
+        return 0
+
+
+def plain(pt: PT) -> LeafRef:
+    return LeafRef(pt)
+
+
+# ----------------------------------------------------------------------------------------
+# blob writer
+# ----------------------------------------------------------------------------------------
+class W:
+    def __init__(self):
+        self.w = []
+
+    def i32(self, v):
+        v = int(v)
+        self.w.append(v if v < 2 ** 31 else v - 2 ** 32)
+
+    def i64(self, v):
+        v = int(v) & 0xFFFFFFFFFFFFFFFF
+        self.i32(v & 0xFFFFFFFF)
+        self.i32(v >> 32)
+
+    def f64(self, v):
+        self.i64(struct.unpack('<q', struct.pack('<d', float(v)))[0])
+
+    def tref(self, pt: PT):
+        if pt.space == 'ws':
+            self.i32(SP_WS); self.i64(pt.offset)
+        elif pt.space == 'input':
+            self.i32(SP_INPUT); self.i64(pt.index)
+        elif pt.space == 'output':
+            self.i32(SP_OUTPUT); self.i64(pt.index)
+        elif pt.space == 'aux':
+            self.i32(SP_AUX); self.i64(pt.index)
+        else:
+            raise Exception(f"bad space {pt.space}")
+
+
+class Op:
+    code = 0
+
+    def payload(self, w: W):
+        raise NotImplementedError
+
+    def serialize(self, w: W):
+        start = len(w.w)
+        w.i32(self.code)
+        w.i32(0)
+        self.payload(w)
+        w.w[start + 1] = len(w.w) - start
+
+
+def _dims(w, a, b):
+    if len(a) + len(b) > MAXD:
+        raise Exception(f"op needs {len(a) + len(b)} iteration dims; the kernels support {MAXD}")
+    w.i32(len(a)); w.i32(len(b))
+    for d in list(a) + list(b):
+        w.i32(d[2])
+
+
+def _opnd(w, leaf: LeafRef, dims, with_mode):
+    w.tref(leaf.pt)
+    if with_mode:
+        w.i32(leaf.mode)
+        mdim = 0
+        if leaf.mode:
+            keys = [(d[0], d[1]) for d in dims]
+            mdim = keys.index(('ax', leaf.mdim))
+        w.i32(mdim)
+    for d in dims:
+        w.i64(leaf.stride(d))
+
+
+def _strides_like(pt: PT, own_dims, dims):
+    """strides of a contiguous tensor laid out over own_dims, seen from the op dims `dims`."""
+    st, acc = {}, 1
+    for d in reversed(own_dims):
+        st[(d[0], d[1])] = acc if d[2] > 1 else 0
+        acc *= d[2]
+    return [st.get((d[0], d[1]), 0) for d in dims]
+
+
+@dataclass
+class Code:
+    instrs: list
+    consts: list
+    res: int
+    leaves: list            # LeafRef per leaf index
+
+    def write(self, w: W):
+        if len(self.instrs) > MAXI or len(self.consts) > MAXC:
+            raise Exception("traced expression is too long for the factor VM "
+                            f"({len(self.instrs)} instructions, {len(self.consts)} constants)")
+        w.i32(len(self.instrs))
+        for (op, dst, a, b, c, d) in self.instrs:
+            w.i32(op | (dst << 8) | (a << 16) | (b << 24))
+            w.i32(c | (d << 8))
+        w.i32(len(self.consts))
+        for c in self.consts:
+            w.f64(c)
+        w.i32(self.res)
+
+
+class FillOp(Op):
+    code = OP_FILL
+
+    def __init__(self, pt, nbytes):
+        self.pt, self.nbytes = pt, nbytes
+
+    def payload(self, w):
+        w.tref(self.pt); w.i64(self.nbytes)
+
+
+class ExprOp(Op):
+    """out[keep] (+)= scale * sum_red VM(leaves)   (csrc/kernels.cuh expr_fwd_kernel)"""
+    code = OP_EXPR
+
+    def __init__(self, out, keep, red, code: Code, acc=0, scale=1.0, tag=''):
+        self.out, self.keep, self.red, self.codeobj, self.acc, self.scale, self.tag = out, keep, red, code, acc, scale, tag
+
+    def payload(self, w):
+        w.tref(self.out); w.i32(self.acc); w.f64(self.scale)
+        dims = self.keep + self.red
+        _dims(w, self.keep, self.red)
+        if len(self.codeobj.leaves) > MAXL:
+            raise Exception("factor expression reads more than 10 tensors")
+        w.i32(len(self.codeobj.leaves))
+        for lf in self.codeobj.leaves:
+            _opnd(w, lf, dims, True)
+        self.codeobj.write(w)
+
+
+class ExprBwdOp(Op):
+    code = OP_EXPR_BWD
+
+    def __init__(self, gleaf, fwd: ExprOp, target, kept, loop, gout, nsplit=1, acc=1, scale=1.0):
+        self.gleaf, self.fwd, self.target, self.kept, self.loop = gleaf, fwd, target, kept, loop
+        self.gout, self.nsplit, self.acc, self.scale = gout, nsplit, acc, scale
+
+    def payload(self, w):
+        w.tref(self.gleaf); w.i32(self.acc); w.f64(self.scale); w.i32(self.target); w.i32(self.nsplit)
+        dims = self.kept + self.loop
+        _dims(w, self.kept, self.loop)
+        w.tref(self.gout)
+        for s in _strides_like(self.gout, self.fwd.keep, dims):
+            w.i64(s)
+        w.i32(len(self.fwd.codeobj.leaves))
+        for lf in self.fwd.codeobj.leaves:
+            _opnd(w, lf, dims, True)
+        self.fwd.codeobj.write(w)
+
+
+class ReduceOp(Op):
+    """out[od] (+)= scale * R_{rd}( sum_f coeff_f F_f ) + cadd     (csrc/kernels.cuh reduce_*)"""
+    code = OP_REDUCE
+
+    def __init__(self, mode, out, od, rd, factors, acc=0, scale=1.0, cadd=0.0, nsplit=1, lse=None, gout=None,
+                 lse_dims=None, gout_dims=None, tag=''):
+        self.mode, self.out, self.od, self.rd, self.factors = mode, out, od, rd, factors
+        self.acc, self.scale, self.cadd, self.nsplit = acc, scale, cadd, nsplit
+        self.lse, self.gout, self.lse_dims, self.gout_dims, self.tag = lse, gout, lse_dims, gout_dims, tag
+
+    def payload(self, w):
+        w.i32(self.mode); w.tref(self.out); w.i32(self.acc); w.f64(self.scale); w.f64(self.cadd); w.i32(self.nsplit)
+        dims = self.od + self.rd
+        _dims(w, self.od, self.rd)
+        if len(self.factors) > MAXL:
+            raise Exception("contraction step joins more than 10 factor tensors")
+        w.i32(len(self.factors))
+        for (lf, coeff) in self.factors:
+            w.f64(coeff)
+            _opnd(w, lf, dims, False)
+        if self.mode == R_WSUM:
+            for pt, own in ((self.lse, self.lse_dims), (self.gout, self.gout_dims)):
+                w.tref(pt)
+                for s in _strides_like(pt, own, dims):
+                    w.i64(s)
+
+
+class ChainOp(Op):
+    code = OP_CHAIN
+
+    def __init__(self, ms, levels, out, outer, T, K):
+        self.ms, self.levels, self.out, self.outer, self.T, self.K = ms, levels, out, outer, T, K
+
+    def payload(self, w):
+        w.tref(self.ms); w.tref(self.levels); w.tref(self.out)
+        w.i64(self.outer); w.i64(self.T); w.i64(self.K)
+
+
+class ChainBwdOp(Op):
+    code = OP_CHAIN_BWD
+
+    def __init__(self, fwd: ChainOp, gout, glevels, gms):
+        self.fwd, self.gout, self.glevels, self.gms = fwd, gout, glevels, gms
+
+    def payload(self, w):
+        f = self.fwd
+        w.tref(f.ms); w.tref(f.levels); w.tref(f.out); w.tref(self.gout); w.tref(self.glevels); w.tref(self.gms)
+        w.i64(f.outer); w.i64(f.T); w.i64(f.K)
+
+
+class SampleOp(Op):
+    code = OP_SAMPLE
+
+    def __init__(self, batch, ks, factors, idx_tensors, u, outs):
+        # batch: dims; ks: dims; factors: [(LeafRef, coeff, gathered [(axis, idx slot)])];
+        # idx_tensors: [(PT, own dims)]; u: (PT, own dims); outs: [PT]
+        self.batch, self.ks, self.factors, self.idx_tensors, self.u, self.outs = batch, ks, factors, idx_tensors, u, outs
+
+    def payload(self, w):
+        if len(self.batch) > MAXD or len(self.ks) > 4 or len(self.idx_tensors) > 16:
+            raise Exception("resampling step exceeds kernel limits")
+        w.i32(len(self.batch))
+        for d in self.batch:
+            w.i32(d[2])
+        w.i32(len(self.ks))
+        for d in self.ks:
+            w.i32(d[2])
+        w.i32(len(self.factors))
+        for (lf, coeff, gathered) in self.factors:
+            w.f64(coeff)
+            _opnd(w, lf, self.batch, False)
+            for d in self.ks:
+                w.i64(lf.stride(d))
+            if len(gathered) > 6:
+                raise Exception("factor depends on more than 6 already-sampled K axes")
+            w.i32(len(gathered))
+            for (axis, slot) in gathered:
+                w.i64(lf.stride(('ax', axis, 0)))
+                w.i32(slot)
+        w.i32(len(self.idx_tensors))
+        for (pt, own) in self.idx_tensors:
+            w.tref(pt)
+            for s in _strides_like(pt, own, self.batch):
+                w.i64(s)
+        pt, own = self.u
+        w.tref(pt)
+        for s in _strides_like(pt, own, self.batch):
+            w.i64(s)
+        for o in self.outs:
+            w.tref(o)
+
+
+# ----------------------------------------------------------------------------------------
+# signature of the call
+# ----------------------------------------------------------------------------------------
+@dataclass
+class TensorSig:
+    role: str                # 'sample' | 'param' | 'data' | 'elf'
+    axes: tuple
+    pos_shape: tuple
+    requires_grad: bool = False
+
+
+@dataclass
+class LogicalFactor:
+    tensors: list            # [(LeafRef, coeff)]
+    const: float
+    axes: tuple
+
+
+@dataclass
+class Step:
+    level: tuple             # active plates at this level
+    tensors: list            # [(LeafRef, coeff)]
+    ks: tuple                # K axes sampled jointly at this step (row-major order)
+
+
+class Plan:
+    def __init__(self):
+        self.dtype = None
+        self.input_names = []        # order of device pointers handed to the ABI
+        self.input_pts = {}
+        self.const_inputs = {}       # name -> torch tensor (uploaded once by the runtime)
+        self.programs = []           # list of op lists: fwd segments, bwd segments, sample
+        self.n_fwd = self.n_bwd = 0
+        self.sample_prog = -1
+        self.ws_bytes = 0
+        self.grad_inputs = []        # names of inputs whose gradient the bwd program writes
+        self.sample_steps = []       # [(batch axes (without N), ks)] in visiting order
+        self.sample_groups = []      # [(groupvarname, plate axes)] = idx outputs
+        self.sizes = {}
+        self.N = None
+        self.canon_axes = None
+        self.allreduce = None        # (PT of the tile, n elements) for plate sharding
+        self.global_grads = []       # grads that must be all-reduced across shards
+        self.blob = None
+        self.retained = {}           # debugging: name -> PT of interesting intermediates
+
+    def serialize(self):
+        w = W()
+        for v in (MAGIC, VERSION, 0 if self.dtype == torch.float32 else 1, len(self.input_names),
+                  len(self.programs)):
+            w.i32(v)
+        w.i64(self.ws_bytes)
+        w.i32(self.n_fwd); w.i32(self.n_bwd); w.i32(self.sample_prog)
+        table = len(w.w)
+        for _ in self.programs:
+            w.i32(0); w.i32(0)
+        for i, prog in enumerate(self.programs):
+            w.w[table + 2 * i] = len(w.w)
+            w.w[table + 2 * i + 1] = len(prog)
+            for op in prog:
+                op.serialize(w)
+        self.blob = torch.tensor(w.w, dtype=torch.int32)
+        return self.blob
+
+
+# ----------------------------------------------------------------------------------------
+# the planner
+# ----------------------------------------------------------------------------------------
+class Planner:
+    def __init__(self, P: Plate, Q: Plate, sig: dict, sizes: dict, dtype, extra_factors=(), want_sample_N=None,
+                 shard_plate=None, world_size=1, constants=None):
+        """sig: name -> TensorSig for samples, inputs/params, data and tensor-valued extra factors.
+        sizes: axis name -> extent (plates and K axes).
+        extra_factors: [(key, Expr)] expressions over input leaves, added as log factors at the plate
+        level matching their plate axes (reference Sample.py:69-108 `extra_log_factors`)."""
+        self.P, self.Q, self.sig, self.sizes, self.dtype = P, Q, sig, dict(sizes), dtype
+        self.itemsize = 4 if dtype == torch.float32 else 8
+        self.extra_factors = list(extra_factors)
+        self.N = want_sample_N
+        self.shard_plate, self.world_size = shard_plate, world_size
+        self.plan = Plan()
+        self.plan.dtype = dtype
+        self.plan.sizes = self.sizes
+        self.all_plates = P.all_platenames()
+        self.groups = Q.groupvarnames()
+        self.v2g = Q.varname2groupvarname()
+        self.g2plates = Q.groupvarname2platenames()
+        self.canon = list(self.all_plates) + [Kname(g) for g in self.groups]
+        self.plan.canon_axes = self.canon
+        self.ws_off = 0
+        self.fwd = []
+        self.fwd_segments = []
+        self.steps = []              # resampling steps in forward (bottom-up) creation order per level
+        self.level_steps = {}        # level tuple -> [Step]
+        self.level_order = []
+        self.consts = {}
+        self.inputs = {}
+        for name, s in sig.items():
+            self._add_input(name, s.axes, s.pos_shape)
+        self.scope = {}
+        for name, s in sig.items():
+            if s.role in ('sample', 'param'):
+                self.scope[name] = Expr.leaf(self.inputs[name], s.axes, s.pos_shape)
+
+    # -- allocation -------------------------------------------------------------------
+    def _add_input(self, name, axes, pos_shape):
+        for a in axes:
+            if a not in self.sizes:
+                raise Exception(f"{name}: axis {a} has no known size")
+        axes_c = self.canon_order(axes)
+        if tuple(axes_c) != tuple(axes):
+            raise Exception(f"input {name} must be laid out with named axes in canonical order {axes_c}, got {axes}")
+        pt = PT(axes, pos_shape, self.sizes, 'input', index=len(self.plan.input_names), name=name)
+        self.plan.input_names.append(name)
+        self.plan.input_pts[name] = pt
+        self.inputs[name] = pt
+        return pt
+
+    def const_input(self, value: torch.Tensor):
+        key = (tuple(value.shape), tuple(value.reshape(-1).tolist()))
+        if key not in self.consts:
+            name = f"__const{len(self.consts)}"
+            pt = self._add_input(name, (), tuple(value.shape))
+            self.plan.const_inputs[name] = value.to(self.dtype).contiguous()
+            self.consts[key] = pt
+        return self.consts[key]
+
+    def ws(self, axes, pos_shape=(), name='', numel=None, itemsize=None):
+        pt = PT(axes, pos_shape, self.sizes, 'ws', offset=self.ws_off, name=name)
+        n = pt.numel if numel is None else numel
+        nbytes = n * (itemsize or self.itemsize)
+        self.ws_off += (nbytes + 255) // 256 * 256
+        return pt
+
+    def ws_raw(self, numel, name=''):
+        pt = PT((), (max(int(numel), 1),), self.sizes, 'ws', offset=self.ws_off, name=name)
+        self.ws_off += (pt.numel * self.itemsize + 255) // 256 * 256
+        return pt
+
+    def canon_order(self, axes):
+        axes = list(axes)
+        known = [a for a in self.canon if a in axes]
+        extra = [a for a in axes if a not in self.canon]
+        return tuple(known + extra)
+
+    def axdim(self, a):
+        return ('ax', a, int(self.sizes[a]))
+
+    # -- expression lowering ------------------------------------------------------------
+    def _numel(self, e: Expr):
+        n = 1
+        for a in e.axes:
+            n *= self.sizes[a]
+        for s in e.pos_shape:
+            n *= s
+        return n
+
+    def materialize(self, e: Expr, tag='') -> Expr:
+        """Evaluate `e` into a workspace tensor; returns a leaf Expr reading it."""
+        if e.op == 'leaf' and e.mode == 0 and not e.rename:
+            return e
+        if e.op == 'sumlast':
+            body = self._prepare(e.args[0])
+            pt = self.emit_expr(body, nred=1, tag=tag or 'sumlast')
+        else:
+            body = self._prepare(e)
+            pt = self.emit_expr(body, nred=0, tag=tag or 'expr')
+        return Expr.leaf(pt, pt.axes, pt.pos_shape)
+
+    def _prepare(self, e: Expr, space=None) -> Expr:
+        """Replace inner reductions (and cheap-to-hoist subtrees) by materialised leaves."""
+        if e.op in ('leaf', 'const'):
+            return e
+        if e.op == 'sumlast':
+            return self.materialize(e)
+        args = [self._prepare(a, space) for a in e.args]
+        out = Expr(e.op, args, e.axes, e.pos_shape)
+        return out
+
+    def _hoist_args(self, args, space_numel):
+        out = []
+        for a in args:
+            if a.op not in ('leaf', 'const') and self._numel(a) * HOIST_RATIO <= space_numel:
+                a = self.materialize(a, tag='arg')
+            out.append(a)
+        return out
+
+    def _codegen(self, body: Expr) -> Code:
+        instrs, consts, leaves = [], [], []
+        memo = {}
+        leaf_slot = {}
+
+        def reg():
+            if len(instrs) >= NREG:
+                raise Exception("traced expression needs more than 32 VM registers")
+            return len(instrs)
+
+        def go(e: Expr):
+            if id(e) in memo:
+                return memo[id(e)]
+            if e.op == 'leaf':
+                lf = LeafRef(e.ref, tuple(sorted(e.rename.items())), e.mode, e.mdim)
+                if lf not in leaf_slot:
+                    leaf_slot[lf] = len(leaves)
+                    leaves.append(lf)
+                    r = reg()
+                    instrs.append((VOPS['load'], r, leaf_slot[lf], 0, 0, 0))
+                    memo[('L', lf)] = r
+                r = memo[('L', lf)]
+            elif e.op == 'const':
+                if e.value not in consts:
+                    consts.append(e.value)
+                r = reg()
+                instrs.append((VOPS['const'], r, consts.index(e.value), 0, 0, 0))
+            else:
+                rs = [go(a) for a in e.args]
+                while len(rs) < 4:
+                    rs.append(0)
+                r = reg()
+                instrs.append((VOPS[e.op], r, rs[0], rs[1], rs[2], rs[3]))
+            memo[id(e)] = r
+            return r
+        res = go(body)
+        return Code(instrs, consts, res, leaves)
+
+    def emit_expr(self, body: Expr, nred, tag='', out=None, acc=0, scale=1.0) -> PT:
+        """body: elementwise tree; nred = number of trailing positional dims summed ('all' = every one)."""
+        R = len(body.pos_shape)
+        if nred == 'all':
+            nred = R
+        axes = self.canon_order(body.axes)
+        keep = [self.axdim(a) for a in axes]
+        ev = [('ev', R - 1 - i, int(body.pos_shape[i])) for i in range(R)]
+        keep_ev, red_ev = ev[:R - nred], ev[R - nred:]
+        code = self._codegen(body)
+        if out is None:
+            out = self.ws(axes, body.pos_shape[:R - nred], name=tag)
+        op = ExprOp(out, keep + keep_ev, red_ev, code, acc=acc, scale=scale, tag=tag)
+        self.fwd.append(op)
+        return out
+
+    # -- distribution arguments ------------------------------------------------------------
+    def resolve_arg(self, family, argname, v, scope):
+        """dist.py:211-229: number / tensor / scope string / lambda -> Expr"""
+        if isinstance(v, str):
+            if v not in scope:
+                raise Exception(f"{v} is not in scope")
+            return scope[v]
+        if isinstance(v, types.FunctionType):
+            names = function_arguments(v)
+            for n in names:
+                if n not in scope:
+                    raise Exception(f"{n} is not in scope")
+            return trace_function(v, [scope[n] for n in names])
+        if isinstance(v, torch.Tensor):
+            if v.ndim == 0:
+                return Expr.const(float(v))
+            pt = self.const_input(v)
+            return Expr.leaf(pt, (), pt.pos_shape)
+        assert isinstance(v, numbers.Number)
+        return Expr.const(float(v))
+
+    def density(self, dist: Dist, value: Expr, scope, tag) -> PT:
+        """One factor tensor: sum over every positional dim of log p(value; args)
+        (TorchDimDist.py:157-162)."""
+        args = {k: self.resolve_arg(dist.family, k, v, scope) for k, v in dist.args.items()}
+        if dist.family in ('Bernoulli',):
+            opname = 'Bernoulli_logits' if 'logits' in args else 'Bernoulli_probs'
+            order = [args['logits'] if 'logits' in args else args['probs']]
+        elif dist.family in ('NegativeBinomial', 'Binomial'):
+            raise Exception(f"{dist.family} is declared but its factor kernel is not built yet")
+        else:
+            opname = dist.family
+            order = [args[k] for k in DENSITY_ARGS[dist.family]]
+        operands = [self._prepare(value)] + [self._prepare(a) for a in order]
+        probe = Expr(opname, operands, *_union(operands))
+        operands = [operands[0]] + self._hoist_args(operands[1:], self._numel(probe))
+        body = Expr(opname, operands, *_union(operands))
+        return self.emit_expr(body, nred='all', tag=tag)
+
+    # -- plate recursion (logpq.py:68-155, 257-332) -------------------------------------------
+    def plan_plate(self, name, P: Plate, Q: Plate, active, scope):
+        if name is not None:
+            active = (*active, name)
+        scope = dict(scope)
+        lfs = []
+        for key, e in self.extra_factors:
+            plates = set(a for a in e.axes if a in self.all_plates)
+            if plates == set(active):
+                lfs.append(self._extra_factor(key, e))
+        Knon, Kts, Kinits = [], [], []
+        for childname, childQ in Q.grouped_prog.items():
+            if isinstance(childQ, dict):
+                childP = {v: P.flat_prog[v] for v in childQ}
+                lf, a, b, c = self.plan_group(childname, childP, childQ, active, scope)
+            else:
+                lf = self.plan_plate(childname, P.flat_prog[childname], childQ, active, scope)
+                a = b = c = ()
+            lfs.append(lf)
+            Knon.extend(a); Kts.extend(b); Kinits.extend(c)
+        level_steps = []
+        lf = self.contract(lfs, tuple(Knon), active, level_steps)
+        self.level_steps[tuple(active)] = (level_steps, Q)
+        if name is None:
+            return lf
+        if Kinits:
+            return self.chain(lf, name, Kinits[0], Kts[0])
+        return self.plate_sum(lf, name)
+
+    def _extra_factor(self, key, e: Expr) -> LogicalFactor:
+        if len(e.pos_shape) > 0 or e.op != 'leaf':
+            pt = self.emit_expr(self._prepare(e), nred='all', tag=f'elf:{key}')
+        else:
+            pt = e.ref
+        return LogicalFactor([(plain(pt), 1.0)], 0.0, tuple(pt.axes))
+
+    def plan_group(self, name, prog_P, prog_Q, active, scope):
+        if datagroup(prog_Q):
+            k = next(iter(prog_Q))
+            if k not in self.sig or self.sig[k].role != 'data':
+                raise Exception(f"no data tensor was provided for {k}")
+            s = self.sig[k]
+            value = Expr.leaf(self.inputs[k], s.axes, s.pos_shape)
+            pt = self.density(prog_P[k], value, scope, tag=f'logP:{k}')
+            return LogicalFactor([(plain(pt), 1.0)], 0.0, pt.axes), (), (), ()
+
+        K_axis = Kname(name)
+        K = self.sizes[K_axis]
+        T_axis = active[-1] if active else None
+        tensors, q_tensors, Kinits = [], [], []
+        for k in prog_P:
+            dP, dQ = prog_P[k], prog_Q[k]
+            if k not in self.sig or self.sig[k].role != 'sample':
+                raise Exception(f"no sample was provided for latent variable {k}")
+            s = self.sig[k]
+            value = Expr.leaf(self.inputs[k], s.axes, s.pos_shape)
+            for which, d, store in (('P', dP, tensors), ('Q', dQ, q_tensors)):
+                sc = scope
+                if isinstance(d, Timeseries):
+                    sc, Kinit = self._timeseries_scope(d, k, value, scope, T_axis, K_axis)
+                    if which == 'P':
+                        Kinits.append(Kinit)
+                    d = d.trans
+                pt = self.density(d, value, sc, tag=f'log{which}:{k}')
+                store.append(pt)
+            scope[k] = value                     # later members of the group may refer to it
+        # mixture-Q reduction over parent Ks (Sampler.py:118-134)
+        q_axes = _union_axes([pt.axes for pt in q_tensors])
+        parents = tuple(a for a in q_axes if a != K_axis and a not in active)
+        facs = [(plain(pt), 1.0) for pt in tensors]
+        if parents:
+            rd = [self.axdim(a) for a in parents]
+            out_axes = self.canon_order([a for a in q_axes if a not in parents])
+            out = self.ws(out_axes, name=f'logQ~:{name}')
+            cadd = -sum(math.log(self.sizes[a]) for a in parents)
+            self.fwd.append(ReduceOp(R_LSE_EPS, out, [self.axdim(a) for a in out_axes], rd,
+                                     [(plain(pt), 1.0) for pt in q_tensors], cadd=cadd, tag=f'reduce_logQ:{name}'))
+            facs.append((plain(out), -1.0))
+        else:
+            facs.extend((plain(pt), -1.0) for pt in q_tensors)
+        axes = self.canon_order(_union_axes([lf.pt.axes for lf, _ in facs]))
+        lf = LogicalFactor(facs, -math.log(K), axes)
+        if Kinits:
+            return lf, (), (K_axis,), (Kinits[0],)
+        return lf, (K_axis,), (), ()
+
+    def _timeseries_scope(self, ts: Timeseries, varname, value: Expr, scope, T_axis, K_axis):
+        """Timeseries.py:203-245: prev[t] = x[t-1] with K renamed to the init variable's K; prev[0] = init."""
+        if ts.init not in scope:
+            raise Exception(f"Timeseries initial state {ts.init} is not in scope")
+        init = scope[ts.init]
+        Kinit = Kname(self.v2g[ts.init])
+        if Kinit not in init.axes or T_axis in init.axes:
+            raise Exception("Timeseries initial state must be a latent of the immediately enclosing plate")
+        prev_axes = tuple(Kinit if a == K_axis else a for a in value.axes)
+        shifted = Expr.leaf(value.ref, prev_axes, value.pos_shape, rename={Kinit: K_axis}, mode=1, mdim=T_axis)
+        first = Expr.leaf(init.ref, init.axes, init.pos_shape, mode=2, mdim=T_axis)
+        first.axes = tuple(init.axes) + (T_axis,)         # the masked load depends on t
+        prev = Expr.make('add', shifted, first)
+        return {**scope, 'prev': prev}, Kinit
+
+    # -- contraction (reduce_Ks.py:236-298) --------------------------------------------------
+    def contract(self, lfs, Ks_to_sum, active, level_steps):
+        if not lfs:
+            raise Exception("plate without factors")
+        path = greedy_path([lf.axes for lf in lfs], Ks_to_sum, self.sizes)
+        lfs = list(lfs)
+        for idxs in path:
+            chosen = [lfs[i] for i in idxs]
+            lfs = [lfs[i] for i in range(len(lfs)) if i not in idxs]
+            remaining = set(a for lf in lfs for a in lf.axes)
+            chosen_axes = _union_axes([lf.axes for lf in chosen])
+            ks = tuple(k for k in Ks_to_sum if k in chosen_axes and k not in remaining)
+            tensors = [tc for lf in chosen for tc in lf.tensors]
+            const = sum(lf.const for lf in chosen)
+            if not ks:
+                lfs.append(LogicalFactor(tensors, const, self.canon_order(chosen_axes)))
+                continue
+            out_axes = self.canon_order([a for a in chosen_axes if a not in ks])
+            out = self.ws(out_axes, name='lse[' + ','.join(ks) + ']')
+            self.fwd.append(ReduceOp(R_LSE_EPS, out, [self.axdim(a) for a in out_axes],
+                                     [self.axdim(a) for a in ks], tensors, cadd=const,
+                                     tag='contract:' + ','.join(ks)))
+            level_steps.append(Step(tuple(active), tensors, ks))
+            lfs.append(LogicalFactor([(plain(out), 1.0)], 0.0, out_axes))
+        assert len(lfs) == 1
+        return lfs[0]
+
+    def plate_sum(self, lf: LogicalFactor, plate):
+        out_axes = tuple(a for a in lf.axes if a != plate)
+        out = self.ws(out_axes, name=f'sum[{plate}]')
+        n = self.sizes[plate]
+        od = [self.axdim(a) for a in out_axes]
+        rd = [self.axdim(plate)]
+        n_out = max(1, _prod(d[2] for d in od))
+        nsplit = _choose_split(n_out, n)
+        if nsplit > 1:
+            part = self.ws_raw(nsplit * n_out, name=f'partial[{plate}]')
+            first = ReduceOp(R_SUM, part, od, rd, lf.tensors, nsplit=nsplit, tag=f'plate_sum_partial:{plate}')
+            first.autodiff_as = 'skip'
+            self.fwd.append(first)
+            sd = ('sp', 0, nsplit)
+            second = ReduceOp(R_SUM, out, od, [sd], [(_PartialRef(part, od, nsplit), 1.0)],
+                              cadd=lf.const * n, tag=f'plate_sum:{plate}')
+            # the adjoint is derived from the unsplit form of the same sum
+            second.autodiff_as = ReduceOp(R_SUM, out, od, rd, lf.tensors, cadd=lf.const * n)
+            self.fwd.append(second)
+        else:
+            self.fwd.append(ReduceOp(R_SUM, out, od, rd, lf.tensors, cadd=lf.const * n, tag=f'plate_sum:{plate}'))
+        if plate == self.shard_plate:
+            self.plan.allreduce = out
+            self.fwd_segments.append(self.fwd)
+            self.fwd = []
+        return LogicalFactor([(plain(out), 1.0)], 0.0, out_axes)
+
+    def chain(self, lf: LogicalFactor, T_axis, Kinit, Kts):
+        """logpq.py:131-143: order to [T, Kprev, Kcurr] (other axes batch), chain_logmmexp, logsumexp."""
+        outer = tuple(a for a in lf.axes if a not in (T_axis, Kinit, Kts))
+        ms_axes = outer + (T_axis, Kinit, Kts)
+        for a in (T_axis, Kinit, Kts):
+            if a not in lf.axes:
+                raise Exception(f"Timeseries factor lacks axis {a}")
+        if self.sizes[Kinit] != self.sizes[Kts]:
+            raise Exception("Timeseries needs the same K for the initial state and the chain")
+        ms = self.ws(ms_axes, name='chain_ms')
+        od = [self.axdim(a) for a in ms_axes]
+        self.fwd.append(ReduceOp(R_SUM, ms, od, [], lf.tensors, cadd=lf.const, tag='chain_ms'))
+        K, T = self.sizes[Kts], self.sizes[T_axis]
+        n_outer = _prod(self.sizes[a] for a in outer)
+        n, tot = T, 0
+        while n > 1:
+            n = n // 2 + n % 2
+            tot += n_outer * n * K * K
+        levels = self.ws_raw(max(tot, 1), name='chain_levels')
+        out = self.ws(outer + (Kinit,), name='chain_out')
+        self.fwd.append(ChainOp(ms, levels, out, n_outer, T, K))
+        return LogicalFactor([(plain(out), 1.0)], 0.0, out.axes)
+
+    # -- top level ----------------------------------------------------------------------------
+    def build(self, grad_names=(), with_sample=False) -> Plan:
+        lf = self.plan_plate(None, self.P, self.Q, (), self.scope)
+        if lf.axes != ():
+            raise Exception(f"log-evidence has leftover axes {lf.axes}")
+        lp = PT((), (), self.sizes, 'output', index=0, name='lp')
+        self.lp_ws = self.ws((), name='lp')
+        self.fwd.append(ReduceOp(R_SUM, self.lp_ws, [], [], lf.tensors, cadd=lf.const, tag='lp'))
+        self.fwd.append(ReduceOp(R_SUM, lp, [], [], [(plain(self.lp_ws), 1.0)], tag='lp_out'))
+        self.fwd_segments.append(self.fwd)
+        plan = self.plan
+        plan.programs = list(self.fwd_segments)
+        plan.n_fwd = len(self.fwd_segments)
+        bwd_segments = self.build_backward(grad_names)
+        plan.programs += bwd_segments
+        plan.n_bwd = len(bwd_segments)
+        if with_sample:
+            plan.sample_prog = len(plan.programs)
+            plan.programs.append(self.build_sampling())
+        plan.ws_bytes = max(self.ws_off, 256)
+        plan.serialize()
+        return plan
+
+    # -- backward -----------------------------------------------------------------------------
+    def build_backward(self, grad_names):
+        plan = self.plan
+        plan.grad_inputs = list(grad_names)
+        if not grad_names:
+            return []
+        all_fwd = []
+        seg_of = {}
+        sharded_ids = set()
+        for si, seg in enumerate(self.fwd_segments):
+            for op in seg:
+                lop = getattr(op, 'autodiff_as', None)
+                if isinstance(lop, str):
+                    continue
+                lop = lop if lop is not None else op
+                all_fwd.append(lop)
+                seg_of[id(lop)] = si
+                if si == 0:
+                    sharded_ids.add(id(lop))
+        needs = set(self.inputs[n].id for n in grad_names)
+
+        def op_inputs(op):
+            if isinstance(op, ExprOp):
+                return [lf.pt for lf in op.codeobj.leaves]
+            if isinstance(op, ReduceOp):
+                return [lf.pt for lf, _ in op.factors]
+            if isinstance(op, ChainOp):
+                return [op.ms]
+            return []
+        for op in all_fwd:
+            if any(p.id in needs for p in op_inputs(op)):
+                needs.add(op.out.id)
+        adj = {}
+        grad_out = {}
+        for i, n in enumerate(grad_names):
+            src = self.inputs[n]
+            g = PT(src.axes, src.pos_shape, self.sizes, 'output', index=i, name=f'g:{n}')
+            adj[src.id] = g
+            grad_out[n] = g
+        adj_lo = self.ws_off
+
+        def adjoint(pt):
+            if pt.id not in adj:
+                adj[pt.id] = self.ws(pt.axes, pt.pos_shape, name=f'adj:{pt.name}')
+            return adj[pt.id]
+
+        segs = [[] for _ in self.fwd_segments]
+        # seed: d lp / d lp_ws = upstream gradient (aux[0])
+        seed = PT((), (), self.sizes, 'aux', index=0, name='grad_lp')
+        adj[self.lp_ws.id] = seed
+        sharded_region = set()
+        if self.shard_plate is not None and len(self.fwd_segments) > 1:
+            sharded_region = sharded_ids
+        for op in reversed(all_fwd):
+            if op.out.space == 'output':
+                continue
+            if op.out.id not in needs or op.out.id not in adj:
+                continue
+            out_list = segs[len(self.fwd_segments) - 1 - seg_of[id(op)]]
+            # gradients of replicated (non-sharded) ops written into user-visible gradients are
+            # pre-divided by the world size so that one all-reduce(sum) restores them exactly.
+            rep_scale = 1.0
+            if self.shard_plate is not None and id(op) not in sharded_region:
+                rep_scale = 1.0 / self.world_size
+            gout = adj[op.out.id]
+            if isinstance(op, ExprOp):
+                dims = op.keep + op.red
+                for li, lf in enumerate(op.codeobj.leaves):
+                    if lf.pt.id not in needs:
+                        continue
+                    g = adjoint(lf.pt)
+                    kept = [d for d in dims if lf.stride(d) != 0]
+                    kept.sort(key=lambda d: -lf.stride(d))
+                    loop = [d for d in dims if lf.stride(d) == 0]
+                    n_kept = _prod(d[2] for d in kept)
+                    if n_kept != lf.pt.numel:
+                        raise Exception(f"adjoint of {lf.pt}: expression does not cover the tensor")
+                    n_loop = _prod(d[2] for d in loop)
+                    nsplit = _choose_split(n_kept, n_loop)
+                    scale = op.scale * (rep_scale if g.space == 'output' else 1.0)
+                    if nsplit > 1:
+                        part = self.ws_raw(nsplit * n_kept, name='partial_adj')
+                        out_list.append(ExprBwdOp(part, op, li, kept, loop, gout, nsplit=nsplit, acc=0, scale=scale))
+                        od = [('fl', 0, n_kept)]
+                        out_list.append(ReduceOp(R_SUM, g, od, [('sp', 0, nsplit)],
+                                                 [(_PartialRef(part, od, nsplit), 1.0)], acc=1))
+                    else:
+                        out_list.append(ExprBwdOp(g, op, li, kept, loop, gout, acc=1, scale=scale))
+            elif isinstance(op, ReduceOp):
+                dims = op.od + op.rd
+                for fi, (lf, coeff) in enumerate(op.factors):
+                    if lf.pt.id not in needs:
+                        continue
+                    if isinstance(lf, _PartialRef):
+                        raise Exception("internal: partial buffers are never differentiated")
+                    g = adjoint(lf.pt)
+                    kept = [d for d in dims if lf.stride(d) != 0]
+                    kept.sort(key=lambda d: -lf.stride(d))
+                    loop = [d for d in dims if lf.stride(d) == 0]
+                    n_kept = _prod(d[2] for d in kept)
+                    if n_kept != lf.pt.numel:
+                        raise Exception(f"adjoint of {lf.pt}: contraction does not cover the tensor")
+                    n_loop = _prod(d[2] for d in loop)
+                    nsplit = _choose_split(n_kept, n_loop)
+                    scale = op.scale * coeff * (rep_scale if g.space == 'output' else 1.0)
+                    if op.mode == R_SUM:
+                        mode, facs, kw = R_SUM, [(_OwnDims(gout, op.od), 1.0)], {}
+                    else:
+                        mode, facs = R_WSUM, op.factors
+                        kw = dict(lse=op.out, gout=gout, lse_dims=op.od, gout_dims=op.od, cadd=op.cadd)
+                    if nsplit > 1:
+                        part = self.ws_raw(nsplit * n_kept, name='partial_adj')
+                        out_list.append(ReduceOp(mode, part, kept, loop, facs, nsplit=nsplit, **kw))
+                        od = [('fl', 0, n_kept)]
+                        out_list.append(ReduceOp(R_SUM, g, od, [('sp', 0, nsplit)],
+                                                 [(_PartialRef(part, od, nsplit), 1.0)], acc=1, scale=scale))
+                    else:
+                        out_list.append(ReduceOp(mode, g, kept, loop, facs, acc=1, scale=scale, **kw))
+            elif isinstance(op, ChainOp):
+                if op.ms.id in needs:
+                    gms = adjoint(op.ms)
+                    glevels = self.ws_raw(op.levels.numel, name='chain_glevels')
+                    out_list.append(ChainBwdOp(op, gout, glevels, gms))
+        adj_hi = self.ws_off
+        # zero the adjoint region and the gradient outputs, then run the reversed ops
+        head = []
+        if adj_hi > adj_lo:
+            head.append(FillOp(PT((), (1,), self.sizes, 'ws', offset=adj_lo), adj_hi - adj_lo))
+        for n, g in grad_out.items():
+            head.append(FillOp(g, g.numel * self.itemsize))
+        segs[0] = head + segs[0]
+        if self.shard_plate is not None:
+            plan.global_grads = [n for n in grad_names if self.shard_plate not in self.inputs[n].axes]
+        return segs
+
+    # -- resampling (sample_logpq.py:17-107, reduce_Ks.py:35-83) ---------------------------------
+    def build_sampling(self):
+        if self.N is None:
+            raise Exception("resampling program needs the number of posterior samples N")
+        plan = self.plan
+        plan.N = self.N
+        sizes = dict(self.sizes)
+        sizes['N'] = self.N
+        idx_pt = {}
+        plan.sample_groups = []
+        for gi, g in enumerate(self.groups):
+            axes = ('N',) + tuple(self.g2plates[g])
+            idx_pt[Kname(g)] = (PT(axes, (), sizes, 'output', index=gi, name=f'idx:{g}'),
+                                [('ax', a, sizes[a]) for a in axes])
+            plan.sample_groups.append((g, tuple(self.g2plates[g])))
+        ops = []
+        sampled = set()
+
+        def visit(level, Q):
+            steps, _ = self.level_steps[level]
+            for st in reversed(steps):
+                batch_axes = tuple(a for a in self.all_plates
+                                   if any(a in lf.pt.axes for lf, _ in st.tensors))
+                if set(batch_axes) != set(level):
+                    raise Exception("resampling a step whose factors do not carry every active plate is not supported")
+                for k in st.ks:
+                    g = k[2:]
+                    if tuple(self.g2plates[g]) != tuple(batch_axes):
+                        raise Exception(f"resampling: group {g} plates {self.g2plates[g]} != step plates {batch_axes}")
+                batch = [('ax', 'N', self.N)] + [self.axdim(a) for a in batch_axes]
+                idx_tensors, slot_of = [], {}
+                facs = []
+                for lf, coeff in st.tensors:
+                    gathered = []
+                    for a in lf.pt.axes:
+                        if a.startswith('K_') and a not in st.ks:
+                            if a not in sampled:
+                                raise Exception(f"resampling order error: {a} needed before it was sampled")
+                            if a not in slot_of:
+                                slot_of[a] = len(idx_tensors)
+                                idx_tensors.append(idx_pt[a])
+                            gathered.append((a, slot_of[a]))
+                    facs.append((lf, coeff, gathered))
+                u_axes = batch_axes + ('N',)
+                ui = len(plan.sample_steps)
+                u = PT(u_axes, (), sizes, 'aux', index=ui, name=f'u{ui}')
+                plan.sample_steps.append((batch_axes, st.ks))
+                outs = [idx_pt[k][0] for k in st.ks]
+                ops.append(SampleOp(batch, [self.axdim(k) for k in st.ks], facs, idx_tensors,
+                                    (u, [('ax', a, sizes[a]) for a in u_axes]), outs))
+                sampled.update(st.ks)
+            for childname, childQ in Q.grouped_prog.items():
+                if isinstance(childQ, Plate):
+                    visit((*level, childname), childQ)
+        visit((), self.Q)
+        for g in self.groups:
+            if Kname(g) not in sampled:
+                raise Exception(f"importance_sample through a Timeseries is unfinished in the reference "
+                                f"(README.md:41-44) and not provided here (group {g})")
+        return ops
+
+
+class _PartialRef(LeafRef):
+    """Reads a split-partial buffer laid out [nsplit, own dims...]."""
+    def __init__(self, pt, own_dims, nsplit):
+        object.__setattr__(self, 'pt', pt)
+        object.__setattr__(self, 'rename', ())
+        object.__setattr__(self, 'mode', 0)
+        object.__setattr__(self, 'mdim', None)
+        object.__setattr__(self, 'own', [('sp', 0, nsplit)] + list(own_dims))
+
+    def stride(self, dim):
+        st, acc = {}, 1
+        for d in reversed(self.own):
+            st[(d[0], d[1])] = acc if d[2] > 1 else 0
+            acc *= d[2]
+        return st.get((dim[0], dim[1]), 0)
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, o):
+        return self is o
+
+
+class _OwnDims(_PartialRef):
+    """Reads a contiguous tensor through an explicit dim list (adjoint of a reduce output)."""
+    def __init__(self, pt, own_dims):
+        object.__setattr__(self, 'pt', pt)
+        object.__setattr__(self, 'rename', ())
+        object.__setattr__(self, 'mode', 0)
+        object.__setattr__(self, 'mdim', None)
+        object.__setattr__(self, 'own', list(own_dims))
+
+
+def _union(exprs):
+    axes, shape = [], ()
+    from .trace import _bshape
+    for e in exprs:
+        for a in e.axes:
+            if a not in axes:
+                axes.append(a)
+        shape = _bshape(shape, e.pos_shape)
+    return tuple(axes), shape
+
+
+def _union_axes(list_of_axes):
+    out = []
+    for ax in list_of_axes:
+        for a in ax:
+            if a not in out:
+                out.append(a)
+    return tuple(out)
+
+
+def _prod(it):
+    n = 1
+    for x in it:
+        n *= int(x)
+    return n
+
+
+def _choose_split(n_out, n_red, target=148 * 8 * 8):
+    """Split a long reduction with few outputs across CTAs; partials are summed in a fixed order by a
+    second launch, so the result does not depend on scheduling."""
+    if n_red < 512 or n_out * 32 >= target:
+        return 1
+    want = max(1, target // max(n_out * 32, 1))
+    return int(max(1, min(want, n_red // 128, 1024)))

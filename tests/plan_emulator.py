@@ -1,0 +1,258 @@
+"""TEST INFRASTRUCTURE ONLY -- a slow torch-CPU interpreter of plan ops.
+
+It executes the planner's op lists (alan_b200/plan.py) with the semantics the CUDA kernels
+implement, so that planner logic (dims, strides, adjoint wiring, resampling order) is checked
+against the oracle in the GPU-less build container.  Adjoint ops are evaluated with torch
+autograd on the gathered operands, i.e. independently of the hand-written VM reverse sweep
+that the CUDA kernels use.  It is never imported by the product.
+"""
+import math
+
+import torch as t
+
+from alan_b200 import plan as PL
+
+UN = {6: lambda a: -a, 7: t.exp, 8: t.log, 9: t.sigmoid, 10: lambda a: a * a, 11: t.sqrt,
+      12: lambda a: 1 / a, 13: t.nn.functional.softplus, 14: t.tanh, 15: t.abs, 16: t.log1p, 18: t.lgamma,
+      19: lambda a: a}
+BI = {2: t.add, 3: t.sub, 4: t.mul, 5: t.div, 17: t.pow}
+HALF_LOG_2PI = 0.91893853320467274178
+
+
+def _logsigmoid(x):
+    return t.minimum(x, t.zeros_like(x)) - t.log1p(t.exp(-x.abs()))
+
+
+def _density(op, r, a, b, c, d):
+    if op == 32:
+        dd = r[a] - r[b]
+        return -(dd * dd) / (2 * (r[c] * r[c])) - t.log(r[c]) - HALF_LOG_2PI
+    if op == 33:
+        return -((1 - r[a]) * r[b] - _logsigmoid(r[b]))
+    if op == 34:
+        eps = t.finfo(r[b].dtype).eps
+        pc = r[b].clamp(eps, 1 - eps)
+        x = t.log(pc) - t.log1p(-pc)
+        return -((1 - r[a]) * x - _logsigmoid(x))
+    if op == 37:
+        return t.log(r[b]) - r[b] * r[a]
+    if op == 36:
+        return -t.log(2 * r[c]) - (r[a] - r[b]).abs() / r[c]
+    if op == 38:
+        return t.xlogy(r[b], r[c]) + t.xlogy(r[b] - 1, r[a]) - r[c] * r[a] - t.lgamma(r[b])
+    if op == 39:
+        return (t.xlogy(r[b] - 1, r[a]) + t.xlogy(r[c] - 1, 1 - r[a]) + t.lgamma(r[b] + r[c])
+                - t.lgamma(r[b]) - t.lgamma(r[c]))
+    raise NotImplementedError(f"emulator: density op {op}")
+
+
+class Emu:
+    def __init__(self, plan, inputs, outputs=None, aux=None):
+        self.plan = plan
+        self.dtype = plan.dtype
+        self.item = 4 if self.dtype == t.float32 else 8
+        self.ws = t.zeros(plan.ws_bytes // self.item + 64, dtype=self.dtype)
+        self.inputs = [x.reshape(-1) for x in inputs]
+        self.outputs = outputs or {}
+        self.aux = aux or {}
+
+    def buf(self, pt):
+        if pt.space == 'ws':
+            return self.ws, pt.offset // self.item
+        if pt.space == 'input':
+            return self.inputs[pt.index], 0
+        if pt.space == 'output':
+            return self.outputs[pt.index], 0
+        if pt.space == 'aux':
+            return self.aux[pt.index], 0
+        raise Exception(pt.space)
+
+    @staticmethod
+    def grid(dims):
+        sizes = [d[2] for d in dims]
+        if not sizes:
+            return []
+        return list(t.meshgrid(*[t.arange(s) for s in sizes], indexing='ij'))
+
+    def offsets(self, strides, grid):
+        off = 0
+        for s, g in zip(strides, grid):
+            off = off + s * g
+        if not grid:
+            return t.zeros((), dtype=t.long)
+        return off + t.zeros_like(grid[0])
+
+    def load_leaf(self, lf, dims, grid):
+        buf, base = self.buf(lf.pt)
+        strides = [lf.stride(d) for d in dims]
+        off = self.offsets(strides, grid) + base
+        if lf.mode == 0:
+            return buf[off], off, None
+        k = [(d[0], d[1]) for d in dims].index(('ax', lf.mdim))
+        if lf.mode == 1:
+            mask = grid[k] >= 1
+            off2 = t.where(mask, off - strides[k], t.full_like(off, base))
+            return t.where(mask, buf[off2], t.zeros((), dtype=buf.dtype)), off2, mask
+        mask = grid[k] == 0
+        return t.where(mask, buf[off], t.zeros((), dtype=buf.dtype)), off, mask
+
+    def vm(self, code, leafvals):
+        r = {}
+        for i, (op, dst, a, b, c, d) in enumerate(code.instrs):
+            if op == 0:
+                r[dst] = leafvals[a]
+            elif op == 1:
+                r[dst] = t.tensor(code.consts[a], dtype=self.dtype)
+            elif op in UN:
+                r[dst] = UN[op](r[a])
+            elif op in BI:
+                r[dst] = BI[op](r[a], r[b])
+            else:
+                r[dst] = _density(op, r, a, b, c, d)
+        return r[code.res]
+
+    # ---- ops
+    def run(self, ops):
+        for op in ops:
+            getattr(self, 'op_' + type(op).__name__)(op)
+
+    def op_FillOp(self, op):
+        buf, base = self.buf(op.pt)
+        n = op.nbytes // self.item
+        buf[base:base + n] = 0
+
+    def op_ExprOp(self, op):
+        dims = op.keep + op.red
+        grid = self.grid(dims)
+        vals = [self.load_leaf(lf, dims, grid)[0] for lf in op.codeobj.leaves]
+        res = self.vm(op.codeobj, vals)
+        shape = [d[2] for d in dims]
+        res = res + t.zeros(shape, dtype=self.dtype) if shape else res
+        if op.red:
+            res = res.sum(tuple(range(len(op.keep), len(dims))))
+        buf, base = self.buf(op.out)
+        n = res.numel()
+        v = op.scale * res.reshape(-1)
+        buf[base:base + n] = buf[base:base + n] + v if op.acc else v
+
+    def op_ExprBwdOp(self, op):
+        f = op.fwd
+        dims = f.keep + f.red
+        grid = self.grid(dims)
+        loaded = [self.load_leaf(lf, dims, grid) for lf in f.codeobj.leaves]
+        shape = [d[2] for d in dims]
+        vals = []
+        for i, (v, off, mask) in enumerate(loaded):
+            v = (v + t.zeros(shape, dtype=self.dtype)).clone()
+            if i == op.target:
+                v.requires_grad_()
+            vals.append(v)
+        res = self.vm(f.codeobj, vals)
+        res = res + t.zeros(shape, dtype=self.dtype)
+        gbuf, gbase = self.buf(op.gout)
+        gstr = PL._strides_like(op.gout, f.keep, dims)
+        go = gbuf[self.offsets(gstr, grid) + gbase]
+        (g,) = t.autograd.grad((res * go).sum(), vals[op.target])
+        _, off, mask = loaded[op.target]
+        off = off + t.zeros(shape, dtype=t.long)
+        if mask is not None:
+            g = t.where(mask, g, t.zeros((), dtype=g.dtype))
+        tb, tbase = self.buf(f.codeobj.leaves[op.target].pt)
+        numel = f.codeobj.leaves[op.target].pt.numel
+        acc = t.zeros(numel, dtype=self.dtype)
+        acc.index_add_(0, (off - tbase).reshape(-1), g.reshape(-1))
+        acc = op.scale * acc
+        out, obase = self.buf(op.gleaf)
+        if op.nsplit > 1:
+            # partial layout [nsplit, n_kept]; emulate by putting everything in split 0
+            out[obase:obase + op.nsplit * numel] = 0
+            out[obase:obase + numel] = acc
+        else:
+            out[obase:obase + numel] = out[obase:obase + numel] + acc if op.acc else acc
+
+    def op_ReduceOp(self, op):
+        dims = op.od + op.rd
+        grid = self.grid(dims)
+        shape = [d[2] for d in dims]
+        s = t.zeros(shape, dtype=self.dtype)
+        for lf, coeff in op.factors:
+            buf, base = self.buf(lf.pt)
+            off = self.offsets([lf.stride(d) for d in dims], grid) + base
+            s = s + coeff * buf[off]
+        rdims = tuple(range(len(op.od), len(dims)))
+        if op.mode == PL.R_SUM:
+            res = s.sum(rdims) if rdims else s
+        elif op.mode == PL.R_WSUM:
+            lb, lbase = self.buf(op.lse)
+            gb, gbase = self.buf(op.gout)
+            l = lb[self.offsets(PL._strides_like(op.lse, op.lse_dims, dims), grid) + lbase]
+            g = gb[self.offsets(PL._strides_like(op.gout, op.gout_dims, dims), grid) + gbase]
+            w = g * t.exp(s + op.cadd - l)
+            res = w.sum(rdims) if rdims else w
+        else:
+            m = s.amax(rdims, keepdim=True)
+            a = t.exp(s - m).sum(rdims)
+            eps = t.finfo(self.dtype).eps if op.mode == PL.R_LSE_EPS else 0.0
+            res = t.log(a + eps) + m.reshape(a.shape)
+        out, obase = self.buf(op.out)
+        n = res.numel()
+        if op.nsplit > 1:
+            out[obase:obase + op.nsplit * n] = 0
+            out[obase:obase + n] = res.reshape(-1)
+            return
+        v = op.scale * res.reshape(-1) + (0.0 if op.mode == PL.R_WSUM else op.cadd)
+        out[obase:obase + n] = out[obase:obase + n] + v if op.acc else v
+
+    def _chain(self, ms):
+        from oracle.logpq_oracle import chain_logmmexp
+        r = chain_logmmexp(ms.movedim(1, 0))            # [T, outer, K, K] -> [outer, K, K]
+        return t.logsumexp(r, -1)
+
+    def op_ChainOp(self, op):
+        buf, base = self.buf(op.ms)
+        n = op.outer * op.T * op.K * op.K
+        ms = buf[base:base + n].reshape(op.outer, op.T, op.K, op.K)
+        out, obase = self.buf(op.out)
+        out[obase:obase + op.outer * op.K] = self._chain(ms).reshape(-1)
+
+    def op_ChainBwdOp(self, op):
+        f = op.fwd
+        buf, base = self.buf(f.ms)
+        n = f.outer * f.T * f.K * f.K
+        ms = buf[base:base + n].reshape(f.outer, f.T, f.K, f.K).clone().requires_grad_()
+        gb, gbase = self.buf(op.gout)
+        go = gb[gbase:gbase + f.outer * f.K].reshape(f.outer, f.K)
+        (g,) = t.autograd.grad((self._chain(ms) * go).sum(), ms)
+        out, obase = self.buf(op.gms)
+        out[obase:obase + n] = g.reshape(-1)
+
+    def op_SampleOp(self, op):
+        grid = self.grid(op.batch)
+        shape = [d[2] for d in op.batch]
+        gv = []
+        for pt, own in op.idx_tensors:
+            b, base = self.buf(pt)
+            gv.append(b[self.offsets(PL._strides_like(pt, own, op.batch), grid) + base])
+        ksz = [d[2] for d in op.ks]
+        ktot = math.prod(ksz)
+        kgrid = t.meshgrid(*[t.arange(s) for s in ksz], indexing='ij')
+        lp = t.zeros(shape + [ktot], dtype=self.dtype)
+        for lf, coeff, gathered in op.factors:
+            b, base = self.buf(lf.pt)
+            off = self.offsets([lf.stride(d) for d in op.batch], grid) + base
+            for axis, slot in gathered:
+                off = off + gv[slot] * lf.stride(('ax', axis, 0))
+            koff = sum(lf.stride(d) * g for d, g in zip(op.ks, kgrid)).reshape(-1)
+            lp = lp + coeff * b[off.unsqueeze(-1) + koff]
+        pt, own = op.u
+        ub, ubase = self.buf(pt)
+        u = ub[self.offsets(PL._strides_like(pt, own, op.batch), grid) + ubase]
+        m = lp.amax(-1, keepdim=True)
+        p = t.exp(lp.double() - m.double())
+        c = p.cumsum(-1)
+        thr = (u * c[..., -1]).unsqueeze(-1)
+        pick = (c < thr).sum(-1).clamp(max=ktot - 1)
+        for k in range(len(ksz) - 1, -1, -1):
+            o, obase = self.buf(op.outs[k])
+            o[obase:obase + pick.numel()] = (pick % ksz[k]).reshape(-1)
+            pick = pick // ksz[k]
