@@ -116,3 +116,125 @@ class Compiled:
                 t = t.to(device)
             out.append(t.to(self.dtype).contiguous())
         return out
+
+
+class _LogPQFunction(torch.autograd.Function):
+    """lp = logPQ(inputs); backward calls the hand-written adjoint program (no autograd
+    re-materialisation, reference logpq.py:62-66)."""
+
+    @staticmethod
+    def forward(ctx, runner, *tensors):
+        lp = runner.forward_raw(list(tensors))
+        ctx.runner = runner
+        ctx.save_for_backward(*tensors)
+        return lp
+
+    @staticmethod
+    def backward(ctx, grad_lp):
+        runner = ctx.runner
+        tensors = list(ctx.saved_tensors)
+        grads = runner.backward_raw(tensors, grad_lp)
+        out = [None] * len(tensors)
+        for name, g in grads.items():
+            out[runner.comp.plan.input_names.index(name)] = g
+        return (None, *out)
+
+
+class Runner:
+    """One compiled plan on one device."""
+    def __init__(self, comp: Compiled, device=None, process_group=None):
+        from . import runtime
+        self.comp = comp
+        self.dp = runtime.DevicePlan(comp.plan, device)
+        self.device = self.dp.device
+        self.dtype = comp.dtype
+        self.pg = process_group
+        self.lp = torch.zeros((), dtype=self.dtype, device=self.device)
+
+    # ---- raw calls on canonical device tensors ------------------------------------------
+    def forward_raw(self, tensors):
+        plan = self.comp.plan
+        lp = torch.empty((), dtype=self.dtype, device=self.device)
+        for seg in range(plan.n_fwd):
+            self.dp.fwd(seg, tensors, lp)
+            if seg + 1 < plan.n_fwd:
+                self._allreduce_tile()
+        return lp
+
+    def _allreduce_tile(self):
+        import torch.distributed as dist
+        tile = self.dp.ws_view(self.comp.plan.allreduce, self.dtype)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1:
+            dist.all_reduce(tile, group=self.pg)
+
+    def backward_raw(self, tensors, grad_lp=None):
+        plan = self.comp.plan
+        if grad_lp is None:
+            grad_lp = torch.ones((), dtype=self.dtype, device=self.device)
+        grad_lp = grad_lp.to(self.dtype).contiguous()
+        outs = [torch.empty(plan.input_pts[n].shape, dtype=self.dtype, device=self.device)
+                for n in plan.grad_inputs]
+        for seg in range(plan.n_bwd):
+            self.dp.bwd(seg, tensors, grad_lp, outs)
+        if plan.global_grads:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1:
+                flat = torch.cat([outs[plan.grad_inputs.index(n)].reshape(-1) for n in plan.global_grads])
+                dist.all_reduce(flat, group=self.pg)
+                off = 0
+                for n in plan.global_grads:
+                    o = outs[plan.grad_inputs.index(n)]
+                    o.copy_(flat[off:off + o.numel()].view_as(o))
+                    off += o.numel()
+        return dict(zip(plan.grad_inputs, outs))
+
+    def resample_raw(self, tensors, uniforms):
+        """uniforms: list of float64 device tensors, one per sampling step (plan.sample_steps order),
+        each laid out [batch plates..., N].  Returns {groupvarname: int64 [N, plates...]}."""
+        plan = self.comp.plan
+        if plan.sample_prog < 0:
+            raise Exception("this plan was compiled without a resampling program (pass N=...)")
+        if len(uniforms) != len(plan.sample_steps):
+            raise Exception(f"expected {len(plan.sample_steps)} uniform tensors, got {len(uniforms)}")
+        us = []
+        for u, (batch, ks) in zip(uniforms, plan.sample_steps):
+            shape = [self.comp.sizes[a] for a in batch] + [plan.N]
+            if list(u.shape) != shape or u.dtype != torch.float64:
+                raise Exception(f"uniforms for step over {ks} must be float64 of shape {shape}")
+            us.append(u.to(self.device).contiguous())
+        outs = [torch.empty([plan.N] + [self.comp.sizes[a] for a in plates], dtype=torch.int64, device=self.device)
+                for _, plates in plan.sample_groups]
+        self.dp.resample(tensors, us, outs)
+        return {g: NT(o, ('N',) + tuple(plates)) for (g, plates), o in zip(plan.sample_groups, outs)}
+
+    # ---- named-tensor calls -----------------------------------------------------------------
+    def device_inputs(self, sample, inputs_params, data, extra_log_factors=None, differentiable=False):
+        """Canonical device tensors.  With differentiable=True the permute/cast is left on the
+        autograd tape so that gradients flow back to the caller's tensors."""
+        comp = self.comp
+        if not differentiable:
+            return comp.canonical_inputs(sample, inputs_params, data, extra_log_factors, device=self.device)
+        src = {}
+        for d in (sample, inputs_params or {}, data or {}):
+            src.update(d)
+        elf = dict(extra_log_factors or {})
+        out = []
+        for name in comp.plan.input_names:
+            if name in comp.plan.const_inputs:
+                t = self.dp.consts[name]
+            elif name.startswith('__J'):
+                _, plates, pos = next(m for m in comp.moment_inputs if m[0] == name)
+                t = torch.zeros([comp.sizes[a] for a in plates] + list(pos), dtype=self.dtype, device=self.device)
+                t.requires_grad_(True)
+            else:
+                key, role, orig, axes = next(o for o in comp.order if o[0] == name)
+                v = elf[orig] if role == 'elf' else src[orig]
+                t = v.order(axes).t.to(self.device).to(self.dtype).contiguous()
+                if name not in comp.grad_names:
+                    t = t.detach()
+            out.append(t)
+        return out
+
+    def elbo(self, tensors):
+        """Differentiable log-evidence estimate on canonical device tensors."""
+        return _LogPQFunction.apply(self, *tensors)

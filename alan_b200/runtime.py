@@ -1,0 +1,203 @@
+"""ctypes binding of libalan_b200.so and the torch-side plumbing around it.
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every
+arithmetic step of the logPQ path runs in the hand-written kernels behind the C ABI
+(include/alan_b200.h).  The library is built in-tree by `__graft_entry__.build()`; if it is
+missing, or no CUDA device is present, every entry point raises -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libalan_b200.so")
+SRC = os.path.join(_HERE, "csrc", "alan_b200.cu")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+EXPORTS = [
+    "alan_b200_abi_version", "alan_b200_last_error", "alan_b200_plan_create", "alan_b200_plan_destroy",
+    "alan_b200_workspace_bytes", "alan_b200_num_inputs", "alan_b200_num_programs",
+    "alan_b200_program_launches", "alan_b200_run", "alan_b200_logpq_fwd", "alan_b200_logpq_bwd",
+    "alan_b200_resample", "alan_b200_gather", "alan_b200_lse_eps", "alan_b200_chain_scratch_elems",
+    "alan_b200_logmmexp_chain", "alan_b200_normal_logpdf_bcast",
+]
+
+
+def build_library(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> alan_b200/libalan_b200.so"""
+    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "alan_b200.h"))
+    if not force and os.path.exists(LIB_PATH):
+        if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, SRC]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the B200 engine has no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    L.alan_b200_abi_version.restype = i32
+    L.alan_b200_last_error.restype = ctypes.c_char_p
+    L.alan_b200_plan_create.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.alan_b200_plan_destroy.argtypes = [vp]
+    L.alan_b200_workspace_bytes.argtypes = [vp]
+    L.alan_b200_workspace_bytes.restype = ctypes.c_size_t
+    L.alan_b200_num_inputs.argtypes = [vp]
+    L.alan_b200_num_programs.argtypes = [vp]
+    L.alan_b200_program_launches.argtypes = [vp, i32]
+    L.alan_b200_run.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.alan_b200_logpq_fwd.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.alan_b200_logpq_bwd.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.alan_b200_resample.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.alan_b200_gather.argtypes = [vp, vp, vp, i32, i64, i64, i64, i64, i64, vp]
+    L.alan_b200_lse_eps.argtypes = [vp, vp, i64, i64, i32, vp]
+    L.alan_b200_chain_scratch_elems.argtypes = [i64, i64, i64]
+    L.alan_b200_chain_scratch_elems.restype = i64
+    L.alan_b200_logmmexp_chain.argtypes = [vp, vp, vp, i64, i64, i64, i32, vp]
+    L.alan_b200_normal_logpdf_bcast.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, i32, vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise Exception("alan_b200: " + lib().alan_b200_last_error().decode())
+
+
+def require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("alan_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device(device if device is not None else "cuda")
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * max(len(tensors), 1))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DevicePlan:
+    """A plan handle plus its device workspace."""
+    def __init__(self, plan, device):
+        self.plan = plan
+        self.device = require_cuda(device)
+        L = lib()
+        blob = plan.blob.contiguous()
+        self._blob = blob
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(L.alan_b200_plan_create(ctypes.c_void_p(blob.data_ptr()), blob.numel(), ctypes.byref(h)))
+        self.handle = h
+        nbytes = L.alan_b200_workspace_bytes(h)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.consts = {k: v.to(self.device) for k, v in plan.const_inputs.items()}
+        self.launches = [L.alan_b200_program_launches(h, i) for i in range(L.alan_b200_num_programs(h))]
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().alan_b200_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def fwd(self, segment, inputs, lp_out):
+        check(lib().alan_b200_logpq_fwd(self.handle, segment, _ptr_array(inputs),
+                                        ctypes.c_void_p(lp_out.data_ptr()), ctypes.c_void_p(self.ws.data_ptr()),
+                                        _stream()))
+
+    def bwd(self, segment, inputs, grad_lp, grads_out):
+        check(lib().alan_b200_logpq_bwd(self.handle, segment, _ptr_array(inputs),
+                                        ctypes.c_void_p(grad_lp.data_ptr()), _ptr_array(grads_out),
+                                        ctypes.c_void_p(self.ws.data_ptr()), _stream()))
+
+    def resample(self, inputs, uniforms, idx_out):
+        check(lib().alan_b200_resample(self.handle, _ptr_array(inputs), _ptr_array(uniforms),
+                                       _ptr_array(idx_out), ctypes.c_void_p(self.ws.data_ptr()), _stream()))
+
+    def ws_view(self, pt, dtype):
+        """torch view of a workspace tensor (used for the cross-GPU all-reduce of the plate tile)."""
+        item = torch.empty((), dtype=dtype).element_size()
+        return self.ws[pt.offset: pt.offset + pt.numel * item].view(dtype).view(pt.shape if pt.shape else ())
+
+
+# ---- unit-level ops (parity tests call these through the C ABI) --------------------------------
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.float64:
+        return 1
+    raise Exception("alan_b200 kernels compute in float32 or float64")
+
+
+def lse_eps(x: torch.Tensor) -> torch.Tensor:
+    """log(sum_r exp(x - max) + eps) + max over the last dim (reference utils.py:207-222)."""
+    require_cuda()
+    x = x.contiguous()
+    if x.numel() == 0:
+        raise Exception("lse_eps: empty input")
+    n_red = x.shape[-1]
+    out = torch.empty(x.shape[:-1], dtype=x.dtype, device=x.device)
+    check(lib().alan_b200_lse_eps(x.data_ptr(), out.data_ptr(), out.numel(), n_red, _dt(x), _stream()))
+    return out
+
+
+def logmmexp_chain(ms: torch.Tensor) -> torch.Tensor:
+    """ms [outer, T, K, K] -> logsumexp_Kcurr(chain_logmmexp(ms)) [outer, K] (utils.py:478-510, logpq.py:134-143)."""
+    require_cuda()
+    ms = ms.contiguous()
+    outer, T, K, K2 = ms.shape
+    assert K == K2
+    L = lib()
+    levels = torch.empty(L.alan_b200_chain_scratch_elems(outer, T, K), dtype=ms.dtype, device=ms.device)
+    out = torch.empty(outer, K, dtype=ms.dtype, device=ms.device)
+    check(L.alan_b200_logmmexp_chain(ms.data_ptr(), levels.data_ptr(), out.data_ptr(), outer, T, K, _dt(ms), _stream()))
+    return out
+
+
+def normal_logpdf_bcast(value, loc, scale, n_cells, n_event, vs, ls, ss) -> torch.Tensor:
+    """sum_e Normal(loc, scale).log_prob(value) over a broadcast [n_cells, n_event] space."""
+    require_cuda()
+    out = torch.empty(n_cells, dtype=value.dtype, device=value.device)
+    mk = lambda s: (ctypes.c_int64 * 2)(*s)
+    check(lib().alan_b200_normal_logpdf_bcast(value.data_ptr(), loc.data_ptr(), scale.data_ptr(), out.data_ptr(),
+                                              n_cells, n_event, mk(vs), mk(ls), mk(ss), _dt(value), _stream()))
+    return out
+
+
+def gather(x: torch.Tensor, idx: torch.Tensor, outer: int, K: int, inner: int) -> torch.Tensor:
+    """x [outer, K, inner], idx [N, outer] int64 -> out [N, outer, inner] (Sample.py:359-381)."""
+    require_cuda()
+    x, idx = x.contiguous(), idx.contiguous()
+    N = idx.shape[0]
+    out = torch.empty(N * outer * inner, dtype=x.dtype, device=x.device)
+    check(lib().alan_b200_gather(x.data_ptr(), idx.data_ptr(), out.data_ptr(), x.element_size(), N, outer, K,
+                                 inner, 1, _stream()))
+    return out

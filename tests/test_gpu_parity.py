@@ -1,0 +1,294 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (libalan_b200.so), against
+ (a) the golden vectors generated from the unmodified reference, and
+ (b) the CPU oracle on the same seeded inputs.
+Tolerances are north_star's: 1e-5 relative in fp32, 1e-10 in fp64 for log-evidence; gradients,
+marginals and moments (sums of many weighted terms) get a 30x allowance.  Indices: bit-exact
+against the same rule evaluated on the engine's own factor tensors."""
+import math
+
+import pytest
+import torch as t
+
+import models
+from alan_b200 import model as M
+from alan_b200.named import NT
+from golden_io import load, rel_err, tol, TAGS
+from uniforms import UniformSource
+
+pytestmark = pytest.mark.gpu
+CASES = list(models.CASES)
+
+
+def _engine():
+    from alan_b200.engine import Compiled, Runner
+    return Compiled, Runner
+
+
+def _as(nt_axes, tensor, axes):
+    return NT(tensor, nt_axes).order(axes).t if nt_axes else tensor
+
+
+# ------------------------------------------------------------------------------ unit-level ops
+@pytest.mark.parametrize("dtype", [t.float32, t.float64])
+@pytest.mark.parametrize("shape", [(1, 1), (7, 30), (300, 900), (5, 10000), (1000, 3)])
+def test_unit_lse_eps(dtype, shape):
+    from alan_b200 import runtime
+    from oracle.logpq_oracle import lse_eps, ONT
+    g = t.Generator().manual_seed(1)
+    x = (20 * t.randn(*shape, generator=g, dtype=t.float64)).to(dtype)
+    ref = lse_eps(ONT(x, ('o', 'r')), ('r',)).t
+    out = runtime.lse_eps(x.cuda()).cpu()
+    assert rel_err(out, ref) < (1e-6 if dtype == t.float32 else 1e-13)
+
+
+def test_unit_lse_eps_empty_raises():
+    from alan_b200 import runtime
+    with pytest.raises(Exception):
+        runtime.lse_eps(t.zeros(0, 4).cuda())
+
+
+@pytest.mark.parametrize("dtype", [t.float32, t.float64])
+@pytest.mark.parametrize("T,K,outer", [(1, 4, 1), (2, 3, 2), (37, 5, 1), (1000, 16, 1), (64, 30, 3), (9, 64, 1)])
+def test_unit_chain(dtype, T, K, outer):
+    from alan_b200 import runtime
+    from oracle.logpq_oracle import chain_logmmexp
+    g = t.Generator().manual_seed(T * 31 + K)
+    ms = (3 * t.randn(outer, T, K, K, generator=g, dtype=t.float64) - 2).to(dtype)
+    ref = t.logsumexp(chain_logmmexp(ms.movedim(1, 0)), -1)
+    out = runtime.logmmexp_chain(ms.cuda()).cpu()
+    assert rel_err(out, ref) < (2e-5 if dtype == t.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("dtype", [t.float32, t.float64])
+def test_unit_normal_bcast(dtype):
+    from alan_b200 import runtime
+    g = t.Generator().manual_seed(3)
+    nc, ne = 1000, 18
+    v = t.randn(nc, ne, generator=g, dtype=t.float64).to(dtype)
+    loc = t.randn(ne, generator=g, dtype=t.float64).to(dtype)
+    scale = t.rand(nc, generator=g, dtype=t.float64).add(0.5).to(dtype)
+    ref = t.distributions.Normal(loc[None, :], scale[:, None]).log_prob(v).sum(-1)
+    out = runtime.normal_logpdf_bcast(v.cuda(), loc.cuda(), scale.cuda(), nc, ne, (ne, 1), (0, 1), (1, 0)).cpu()
+    assert rel_err(out, ref) < (1e-6 if dtype == t.float32 else 1e-13)
+
+
+def test_unit_gather_bit_exact():
+    from alan_b200 import runtime
+    g = t.Generator().manual_seed(5)
+    outer, K, inner, N = 13, 7, 18, 11
+    x = t.randn(outer, K, inner, generator=g)
+    idx = t.randint(0, K, (N, outer), generator=g)
+    out = runtime.gather(x.cuda(), idx.cuda(), outer, K, inner).cpu().reshape(N, outer, inner)
+    ref = x[t.arange(outer)[None, :], idx]
+    assert t.equal(out, ref)
+
+
+# ------------------------------------------------------------------------------ goldens
+@pytest.mark.parametrize("tag", list(TAGS))
+@pytest.mark.parametrize("case", CASES)
+def test_elbo_and_grads_vs_reference_golden(case, tag):
+    Compiled, Runner = _engine()
+    g = load(case, tag)
+    P, Q = models.CASES[case][0](M)
+    names = list(g["grad_sample"]) + list(g["grad_params"])
+    comp = Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"], grad_names=names)
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(g["sample_nt"], g["inputs_params_nt"], g["data_nt"])
+    lp = run.forward_raw(tensors)
+    grads = run.backward_raw(tensors)
+    assert rel_err(lp.cpu(), g["elbo"]) < tol(tag)
+    for n in g["grad_sample"]:
+        pt = comp.plan.input_pts[n]
+        assert rel_err(_as(pt.axes, grads[n].cpu(), g["sample"][n][1]), g["grad_sample"][n]) < 30 * tol(tag), n
+    for n in g["grad_params"]:
+        pt = comp.plan.input_pts[n]
+        assert rel_err(_as(pt.axes, grads[n].cpu(), g["params"][n][1]), g["grad_params"][n]) < 30 * tol(tag), n
+    # autograd wrapper: same numbers through torch.autograd
+    tens = run.device_inputs(g["sample_nt"], g["inputs_params_nt"], g["data_nt"])
+    for i, n in enumerate(comp.plan.input_names):
+        if n in names:
+            tens[i].requires_grad_(True)
+    L = run.elbo(tens)
+    L.backward()
+    for n in names:
+        i = comp.plan.input_names.index(n)
+        assert t.equal(tens[i].grad, grads[n])
+
+
+@pytest.mark.parametrize("tag", list(TAGS))
+@pytest.mark.parametrize("case", CASES)
+def test_marginals_and_moments_vs_reference_golden(case, tag):
+    Compiled, Runner = _engine()
+    g = load(case, tag)
+    P, Q = models.CASES[case][0](M)
+    dtype = TAGS[tag]
+    g2p, groups = Q.groupvarname2platenames(), Q.groupvarnames()
+    sizes = {**{a: s for v in g["sample_nt"].values() for a, s in v.named_sizes.items()}, **g["platesizes"]}
+    elf = {}
+    for key in g["marginals"]:
+        gs = tuple(sorted(key, key=groups.index))
+        axes = tuple(M.Kname(x) for x in gs) + tuple(g2p[gs[0]])
+        elf[key] = NT(t.zeros([sizes[a] for a in axes], dtype=dtype), axes)
+    moms = [((v,), models.MOMENT_FUNCS[f]) for v, f in g["moment_specs"]]
+    comp = Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"], extra_log_factors=elf,
+                    moment_specs=moms, grad_names=list(elf.keys()))
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(g["sample_nt"], g["inputs_params_nt"], g["data_nt"], elf)
+    lp = run.forward_raw(tensors)
+    grads = run.backward_raw(tensors)
+    assert rel_err(lp.cpu(), g["elbo"]) < tol(tag)
+    for key, (ref, axes) in g["marginals"].items():
+        name = comp.elf_keys[key]
+        pt = comp.plan.input_pts[name]
+        assert rel_err(_as(pt.axes, grads[name].cpu(), axes), ref) < 30 * tol(tag), key
+    for (jname, plates, pos), (ref, axes) in zip(comp.moment_inputs, g["moments"]):
+        assert rel_err(_as(plates, grads[jname].cpu(), axes), ref) < 30 * tol(tag), jname
+
+
+@pytest.mark.parametrize("tag", list(TAGS))
+@pytest.mark.parametrize("case", [c for c in CASES if models.CASES[c][6] is not None])
+def test_resampling_indices(case, tag):
+    """(1) bit-exact against the same inverse-CDF rule applied on CPU to the engine's own factor
+    tensors (copied back from the device workspace); (2) against the reference's tree walk
+    (golden), where exp() is taken in a different precision: < 0.1 % may differ."""
+    from plan_emulator import Emu
+    Compiled, Runner = _engine()
+    g = load(case, tag)
+    P, Q = models.CASES[case][0](M)
+    N = g["N"]
+    comp = Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"], N=N)
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(g["sample_nt"], g["inputs_params_nt"], g["data_nt"])
+    run.forward_raw(tensors)
+    plan = comp.plan
+    src = UniformSource(g["uniform_seed"], N, g["platesizes"], list(g["platesizes"]))
+    us = [src.draw(batch)[0] for batch, ks in plan.sample_steps]
+    idx = run.resample_raw(tensors, [u.cuda() for u in us])
+    t.cuda.synchronize()
+    # (1) same rule on the device's factors
+    emu = Emu(plan, [x.cpu() for x in tensors])
+    ws = run.dp.ws.cpu()
+    n = (ws.numel() // emu.item) * emu.item
+    emu.ws[:n // emu.item] = ws[:n].view(plan.dtype)
+    emu.aux = {i: u.reshape(-1) for i, u in enumerate(us)}
+    emu.outputs = {gi: t.zeros(idx[grp].t.numel(), dtype=t.long) for gi, (grp, _) in enumerate(plan.sample_groups)}
+    emu.run(plan.programs[plan.sample_prog])
+    for gi, (grp, plates) in enumerate(plan.sample_groups):
+        assert t.equal(idx[grp].t.cpu().reshape(-1), emu.outputs[gi]), f"{grp}: indices are not bit-exact"
+    # (2) reference walk
+    total = bad = 0
+    for grp, (ref, axes) in g["indices"].items():
+        mine = idx[grp].order(axes).t.cpu()
+        total += ref.numel()
+        bad += (mine != ref).sum().item()
+    assert bad <= 1e-3 * total, f"{bad}/{total} indices differ from the reference walk"
+    # gather (index_into_sample) is a bit-exact copy
+    from alan_b200 import runtime
+    v2g = Q.varname2groupvarname()
+    for name, x in g["sample_nt"].items():
+        grp = v2g[name]
+        plates = tuple(Q.groupvarname2platenames()[grp])
+        xc = x.order(plates + (M.Kname(grp),)).t.contiguous()
+        outer = math.prod(g["platesizes"][a] for a in plates)
+        K = xc.shape[len(plates)]
+        inner = xc.numel() // (outer * K)
+        got = runtime.gather(xc.cuda(), idx[grp].t.reshape(N, outer), outer, K, inner).cpu().reshape(N, outer, inner)
+        ii = idx[grp].t.cpu().reshape(N, outer)
+        ref = xc.reshape(outer, K, inner)[t.arange(outer)[None, :], ii]
+        assert t.equal(got, ref)
+
+
+# ------------------------------------------------------------------------------ oracle at larger sizes
+def _random_sample(P, Q, inp, K, dtype, seed):
+    """Any sample works: parity is defined on identical samples."""
+    g = t.Generator().manual_seed(seed)
+    sizes = dict(inp['platesizes'])
+    out = {}
+    g2p = Q.groupvarname2platenames()
+    v2g = Q.varname2groupvarname()
+    shapes = inp.get('event_shapes', {})
+    for v, grp in v2g.items():
+        axes = tuple(g2p[grp]) + (M.Kname(grp),)
+        shp = [sizes[a] if a in sizes else K for a in axes] + list(shapes.get(v, ()))
+        out[v] = NT((0.7 * t.randn(shp, generator=g, dtype=t.float64)).to(dtype), axes)
+    return out
+
+
+def _nt(d):
+    from alan_b200.named import from_torch_named
+    return {k: from_torch_named(v) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("dtype,M_,K", [(t.float32, 300, 30), (t.float64, 40, 12)])
+def test_movielens_full_size_vs_oracle(dtype, M_, K):
+    """BASELINE cfg-2 at its full size (300 x 5, d=18, K=30): fwd + RWS backward vs the oracle."""
+    from oracle import logpq_oracle as O
+    Compiled, Runner = _engine()
+    P, Q = models.movielens_model(M)
+    inp = models.movielens_inputs(M=M_, N=5, d=18, seed=1, dtype=dtype)
+    inp['event_shapes'] = {'mu_z': (18,), 'psi_z': (18,), 'z': (18,)}
+    sample = _random_sample(P, Q, inp, K, dtype, 2)
+    ip = {**_nt(inp['inputs']), **_nt(inp['params'])}
+    data = _nt(inp['data'])
+    names = list(inp['params'])
+    comp = Compiled(P, Q, sample, ip, data, grad_names=names)
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(sample, ip, data)
+    lp = run.forward_raw(tensors)
+    grads = run.backward_raw(tensors)
+    lp2 = run.forward_raw(tensors)
+    assert t.equal(lp, lp2), "forward is not bit-reproducible"
+    ipg = {k: NT(v.t.clone().requires_grad_() if k in names else v.t, v.axes) for k, v in ip.items()}
+    ref = O.elbo(P, Q, sample, ipg, data)
+    rg = t.autograd.grad(ref, [ipg[k].t for k in names])
+    tl = 1e-5 if dtype == t.float32 else 1e-10
+    assert rel_err(lp.cpu(), ref) < tl
+    for k, r in zip(names, rg):
+        pt = comp.plan.input_pts[k]
+        assert rel_err(_as(pt.axes, grads[k].cpu(), ipg[k].axes), r) < 30 * tl, k
+
+
+def test_timeseries_T1000_K16_vs_oracle():
+    """BASELINE cfg-4: T=1000, K=16 log-evidence and smoothed moments."""
+    from oracle import logpq_oracle as O
+    Compiled, Runner = _engine()
+    P, Q = models.timeseries_model(M)
+    inp = models.timeseries_inputs(T=1000, seed=4)
+    sample = _random_sample(P, Q, inp, 16, t.float32, 5)
+    data = _nt(inp['data'])
+    moms = [(('ts',), models.MOMENT_FUNCS['mean']), (('ts',), models.MOMENT_FUNCS['mean2'])]
+    comp = Compiled(P, Q, sample, {}, data, moment_specs=moms)
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(sample, {}, data)
+    lp = run.forward_raw(tensors)
+    grads = run.backward_raw(tensors)
+    ref = O.elbo(P, Q, sample, {}, data)
+    assert rel_err(lp.cpu(), ref) < 1e-5
+    rm = O.moments(P, Q, sample, {}, data, moms)
+    for (jname, plates, pos), r in zip(comp.moment_inputs, rm):
+        assert rel_err(_as(plates, grads[jname].cpu(), r.axes), r.t) < 3e-4, jname
+
+
+def test_radon_default_size_vs_oracle():
+    """BASELINE cfg-3 default size S=7, C=10, Z=10, K=10: marginals (K^4 joint contraction)."""
+    from oracle import logpq_oracle as O
+    Compiled, Runner = _engine()
+    P, Q = models.radon_model(M)
+    inp = models.radon_inputs(S=7, C=10, Z=10, seed=6)
+    sample = _random_sample(P, Q, inp, 10, t.float32, 7)
+    ip = {**_nt(inp['inputs']), **_nt(inp['params'])}
+    data = _nt(inp['data'])
+    comp = Compiled(P, Q, sample, ip, data)
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(sample, ip, data)
+    lp = run.forward_raw(tensors)
+    ref = O.elbo(P, Q, sample, ip, data)
+    assert rel_err(lp.cpu(), ref) < 1e-5
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from alan_b200 import runtime
+    monkeypatch.setattr(runtime, "_lib", None)
+    monkeypatch.setattr(runtime, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError):
+        runtime.lib()
