@@ -92,11 +92,13 @@ static void read_prog(Reader& r, VMProg<T>& P) {
 }
 
 template <typename T>
-static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool count_only, int* launches) {
+static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool count_only, int* launches,
+                   std::vector<cudaEvent_t>* events = nullptr) {
     Reader r{plan->blob.data() + plan->prog_start[program]};
     int nl = 0;
     for (int op_i = 0; op_i < plan->prog_nops[program]; ++op_i) {
         const int32_t* op_begin = r.p;
+        if (events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c.stream); events->push_back(e); }
         int code = r.i32();
         int nwords = r.i32();
         if (count_only) {
@@ -108,7 +110,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 q.i64v(); i64 T_ = q.i64v();
                 int lv = 0; for (i64 n = T_; n > 1; n = n / 2 + n % 2) lv++;
                 nl += lv + 1;
-            } else nl += 1;
+            } else if (code != OP_FILL && code != OP_COPY) nl += 1;
             r.p = op_begin + nwords;
             continue;
         }
@@ -161,6 +163,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 p.scale = (T)r.f64();
                 p.cadd = (T)r.f64();
                 p.nsplit = r.i32();
+                int thread_hint = r.i32();
                 read_dims(r, p.d, p.n_out, p.n_red);
                 p.nf = r.i32();
                 for (int f = 0; f < p.nf; ++f) {
@@ -172,7 +175,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                     read_opnd(r, c, p.gout, p.d.nd, false);
                 }
                 i64 per = (p.n_red + p.nsplit - 1) / p.nsplit;
-                if (per >= 16) {
+                if (per >= 16 && !thread_hint) {
                     i64 threads = p.n_out * p.nsplit * 32;
                     reduce_warp_kernel<T><<<grid_for(threads, 256, c), 256, 0, c.stream>>>(p);
                 } else {
@@ -270,6 +273,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
             return fail("blob/executor mismatch in op " + std::to_string(op_i) + " (code " + std::to_string(code) +
                         "): consumed " + std::to_string((long)(r.p - op_begin)) + " of " + std::to_string(nwords) + " words");
     }
+    if (events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c.stream); events->push_back(e); }
     if (launches) *launches = nl;
     if (!count_only) {
         cudaError_t e = cudaGetLastError();
@@ -334,6 +338,21 @@ static int run_generic(const alan_b200_plan* p, int program, const void* const* 
     if (program < 0 || program >= p->n_programs) return fail("program index out of range");
     Ctx c{inputs, outputs, aux, (char*)ws, (cudaStream_t)stream, p->sm_count};
     return p->dtype == 0 ? run_ops<float>(p, program, c, false, nullptr) : run_ops<double>(p, program, c, false, nullptr);
+}
+
+int alan_b200_profile(const alan_b200_plan* p, int program, const void* const* inputs, void* const* outputs,
+                      const void* const* aux, void* ws, void* stream, float* ms_per_op, int max_ops) {
+    if (!p) return -1;
+    if (program < 0 || program >= p->n_programs) { fail("program index out of range"); return -1; }
+    Ctx c{inputs, outputs, aux, (char*)ws, (cudaStream_t)stream, p->sm_count};
+    std::vector<cudaEvent_t> ev;
+    int rc = p->dtype == 0 ? run_ops<float>(p, program, c, false, nullptr, &ev)
+                           : run_ops<double>(p, program, c, false, nullptr, &ev);
+    cudaStreamSynchronize(c.stream);
+    int n = (int)ev.size() - 1;
+    for (int i = 0; i < n && i < max_ops; ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
+    for (auto e : ev) cudaEventDestroy(e);
+    return rc ? -1 : n;
 }
 
 int alan_b200_run(const alan_b200_plan* p, int program, const void* const* inputs, void* const* outputs,

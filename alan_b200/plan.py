@@ -268,13 +268,15 @@ class ReduceOp(Op):
     code = OP_REDUCE
 
     def __init__(self, mode, out, od, rd, factors, acc=0, scale=1.0, cadd=0.0, nsplit=1, lse=None, gout=None,
-                 lse_dims=None, gout_dims=None, tag=''):
+                 lse_dims=None, gout_dims=None, tag='', thread_hint=None):
         self.mode, self.out, self.od, self.rd, self.factors = mode, out, od, rd, factors
+        self.thread_hint = _outputs_contiguous(factors, od, rd) if thread_hint is None else thread_hint
         self.acc, self.scale, self.cadd, self.nsplit = acc, scale, cadd, nsplit
         self.lse, self.gout, self.lse_dims, self.gout_dims, self.tag = lse, gout, lse_dims, gout_dims, tag
 
     def payload(self, w):
         w.i32(self.mode); w.tref(self.out); w.i32(self.acc); w.f64(self.scale); w.f64(self.cadd); w.i32(self.nsplit)
+        w.i32(1 if self.thread_hint else 0)
         dims = self.od + self.rd
         _dims(w, self.od, self.rd)
         if len(self.factors) > MAXL:
@@ -1093,10 +1095,24 @@ def _prod(it):
     return n
 
 
-def _choose_split(n_out, n_red, target=148 * 8 * 8):
+def _outputs_contiguous(factors, od, rd):
+    """True when, in the largest factor, consecutive OUTPUT cells are adjacent in memory and the
+    reduced axes are strided: then one thread per output (coalesced across threads) beats one warp
+    per output (lanes striding over the reduced axis)."""
+    if not factors or not od or not rd:
+        return False
+    big = max(factors, key=lambda fc: fc[0].pt.numel)[0]
+    so = [big.stride(d) for d in od if d[2] > 1]
+    sr = [big.stride(d) for d in rd if d[2] > 1]
+    so = [x for x in so if x] or [0]
+    sr = [x for x in sr if x] or [0]
+    return min(so) != 0 and (min(sr) == 0 or min(so) < min(sr))
+
+
+def _choose_split(n_out, n_red, target=148 * 2048):
     """Split a long reduction with few outputs across CTAs; partials are summed in a fixed order by a
     second launch, so the result does not depend on scheduling."""
-    if n_red < 512 or n_out * 32 >= target:
+    if n_red < 256 or n_out >= target:
         return 1
-    want = max(1, target // max(n_out * 32, 1))
-    return int(max(1, min(want, n_red // 128, 1024)))
+    want = max(1, target // max(n_out, 1))
+    return int(max(1, min(want, n_red // 32, 1024)))

@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = [
     "alan_b200_abi_version", "alan_b200_last_error", "alan_b200_plan_create", "alan_b200_plan_destroy",
     "alan_b200_workspace_bytes", "alan_b200_num_inputs", "alan_b200_num_programs",
-    "alan_b200_program_launches", "alan_b200_run", "alan_b200_logpq_fwd", "alan_b200_logpq_bwd",
+    "alan_b200_program_launches", "alan_b200_run", "alan_b200_profile", "alan_b200_logpq_fwd", "alan_b200_logpq_bwd",
     "alan_b200_resample", "alan_b200_gather", "alan_b200_lse_eps", "alan_b200_chain_scratch_elems",
     "alan_b200_logmmexp_chain", "alan_b200_normal_logpdf_bcast",
 ]
@@ -67,6 +67,7 @@ def lib():
     L.alan_b200_num_programs.argtypes = [vp]
     L.alan_b200_program_launches.argtypes = [vp, i32]
     L.alan_b200_run.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.alan_b200_profile.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32]
     L.alan_b200_logpq_fwd.argtypes = [vp, i32, vp, vp, vp, vp]
     L.alan_b200_logpq_bwd.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.alan_b200_resample.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -140,6 +141,16 @@ class DevicePlan:
     def resample(self, inputs, uniforms, idx_out):
         check(lib().alan_b200_resample(self.handle, _ptr_array(inputs), _ptr_array(uniforms),
                                        _ptr_array(idx_out), ctypes.c_void_p(self.ws.data_ptr()), _stream()))
+
+    def profile(self, program, inputs, outputs, aux):
+        """per-op device milliseconds of one program run (CUDA events around every op)."""
+        n = len(self.plan.programs[program])
+        ms = (ctypes.c_float * max(n, 1))()
+        got = lib().alan_b200_profile(self.handle, program, _ptr_array(inputs), _ptr_array(outputs),
+                                      _ptr_array(aux), ctypes.c_void_p(self.ws.data_ptr()), _stream(), ms, n)
+        if got < 0:
+            raise Exception("alan_b200: " + lib().alan_b200_last_error().decode())
+        return [ms[i] for i in range(got)]
 
     def ws_view(self, pt, dtype):
         """torch view of a workspace tensor (used for the cross-GPU all-reduce of the plate tile)."""

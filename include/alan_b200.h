@@ -58,6 +58,14 @@ int alan_b200_program_launches(const alan_b200_plan* plan, int program);
 int alan_b200_run(const alan_b200_plan* plan, int program, const void* const* inputs,
                   void* const* outputs, void* workspace, void* stream);
 
+/* Measurement aid: run `program` with a CUDA event recorded on `stream` before and after every
+ * op, synchronise, and return the per-op device times in milliseconds (returns the number of
+ * ops, or -1 on error).  Used by bench.py for the roofline of the dominant kernel; never on
+ * the timed path. */
+int alan_b200_profile(const alan_b200_plan* plan, int program, const void* const* inputs,
+                      void* const* outputs, const void* const* aux, void* workspace, void* stream,
+                      float* ms_per_op, int max_ops);
+
 /* Forward: log-evidence estimate (0-d, plan dtype) written to lp_out.
  * replaces: logPQ_plate(name=None, ...) -> lp      (src/alan/logpq.py:15-60)
  *   factor evaluation   logPQ_gdt / Dist.log_prob   (logpq.py:157-254, dist.py:297-302,
