@@ -174,13 +174,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                     read_opnd(r, c, p.lse, p.d.nd, false);
                     read_opnd(r, c, p.gout, p.d.nd, false);
                 }
-                i64 per = (p.n_red + p.nsplit - 1) / p.nsplit;
-                if (per >= 16 && !thread_hint) {
-                    i64 threads = p.n_out * p.nsplit * 32;
-                    reduce_warp_kernel<T><<<grid_for(threads, 256, c), 256, 0, c.stream>>>(p);
-                } else {
-                    reduce_thread_kernel<T><<<grid_for(p.n_out * p.nsplit, 256, c), 256, 0, c.stream>>>(p);
-                }
+                launch_reduce<T>(p, thread_hint != 0, c.stream, c.sm_count);
                 break;
             }
             case OP_CHAIN: {
@@ -262,8 +256,23 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 break;
             }
             case OP_NORMAL_FAN: {
-                int rc = launch_normal_fan<T>(r, c.ws, c.inputs, c.outputs, c.stream, c.sm_count);
-                if (rc) return fail("normal_fan: bad configuration");
+                FanParams<T> p;
+                memset(&p, 0, sizeof(p));
+                p.out = (T*)tref(r, c);
+                int D = r.i32();
+                int nrd = r.i32();
+                p.rd.nd = nrd; p.rd.n_a = nrd;
+                p.n_rows = 1;
+                for (int k = 0; k < nrd; ++k) { p.rd.size[k] = r.i32(); p.n_rows *= p.rd.size[k]; }
+                for (int k = 0; k < nrd; ++k) p.vstride[k] = r.i64v();
+                for (int k = 0; k < nrd; ++k) p.lstride[k] = r.i64v();
+                for (int k = 0; k < nrd; ++k) p.ostride[k] = r.i64v();
+                p.v = (const T*)tref(r, c); p.v_ev = r.i64v();
+                p.l = (const T*)tref(r, c); p.l_ev = r.i64v();
+                p.s = (const T*)tref(r, c); p.s_f = r.i64v(); p.s_ev = r.i64v();
+                p.F = r.i32();
+                p.o_f = r.i64v();
+                if (launch_fan<T>(p, D, c.stream, c.sm_count)) return fail("normal_fan: unsupported event extent");
                 break;
             }
             default:
@@ -409,7 +418,7 @@ int lse_eps_impl(const void* x, void* out, i64 n_out, i64 n_red, cudaStream_t st
     p.coeff[0] = T(1); p.out = (T*)out; p.acc = 0; p.scale = T(1); p.cadd = T(0);
     p.n_out = n_out; p.n_red = n_red; p.nsplit = 1;
     i64 blocks = (n_out * 32 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
-    reduce_warp_kernel<T><<<(int)blocks, 256, 0, st>>>(p);
+    reduce_warp_kernel<T, 1><<<(int)blocks, 256, 0, st>>>(p);
     return 0;
 }
 

@@ -142,13 +142,33 @@ struct ReduceParams {
     int nsplit;
 };
 
-template <typename T>
-__device__ __forceinline__ T factor_sum(const ReduceParams<T>& p, const i64* base, const int* idx) {
-    T s = T(0);
-    for (int f = 0; f < p.nf; ++f) {
-        i64 off = base[f] + dot_stride(p.f[f], idx, p.d.n_a, p.d.nd);
-        s += p.coeff[f] * ((const T*)p.f[f].ptr)[off];
+// offset contributed by the reduced index j; NRED = number of reduced dims known at compile time
+// (1 or 2 on the hot paths), 0 = generic.
+template <int NRED>
+__device__ __forceinline__ i64 red_off(const Dims& d, const Opnd& o, i64 j) {
+    if (NRED == 1) return j * o.stride[d.n_a];
+    if (NRED == 2) {
+        int s1 = d.size[d.n_a + 1];
+        i64 q = j / s1;
+        return q * o.stride[d.n_a] + (j - q * s1) * o.stride[d.n_a + 1];
     }
+    i64 off = 0;
+#pragma unroll 1
+    for (int k = d.nd - 1; k >= d.n_a; --k) {
+        int s = d.size[k];
+        i64 q = j / s;
+        off += (j - q * s) * o.stride[k];
+        j = q;
+    }
+    return off;
+}
+
+template <typename T, int NRED>
+__device__ __forceinline__ T factor_sum(const ReduceParams<T>& p, const i64* base, i64 j) {
+    T s = T(0);
+#pragma unroll 1
+    for (int f = 0; f < p.nf; ++f)
+        s += p.coeff[f] * ((const T*)p.f[f].ptr)[base[f] + red_off<NRED>(p.d, p.f[f], j)];
     return s;
 }
 
@@ -159,8 +179,9 @@ __device__ __forceinline__ void reduce_store(const ReduceParams<T>& p, i64 o, in
     p.out[o] = p.acc ? p.out[o] + v : v;
 }
 
-// one warp per (output, split); lanes stride over the reduced index
-template <typename T>
+// one warp per (output, split); lanes stride over the reduced index.  For reduced extents up to
+// 128 the lane keeps its (at most four) values in registers, so the factors are read once.
+template <typename T, int NRED>
 __global__ void __launch_bounds__(256) reduce_warp_kernel(const __grid_constant__ ReduceParams<T> p) {
     int idx[AB_MAXD];
     i64 base[AB_MAXL];
@@ -178,25 +199,39 @@ __global__ void __launch_bounds__(256) reduce_warp_kernel(const __grid_constant_
         T res;
         if (p.mode == R_SUM) {
             T a = T(0);
-            for (i64 j = lo + lane; j < hi; j += 32) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); a += factor_sum(p, base, idx); }
+            for (i64 j = lo + lane; j < hi; j += 32) a += factor_sum<T, NRED>(p, base, j);
             res = warp_sum(a);
         } else if (p.mode == R_WSUM) {
             i64 lbase = dot_stride(p.lse, idx, 0, p.d.n_a), gbase = dot_stride(p.gout, idx, 0, p.d.n_a);
             T a = T(0);
             for (i64 j = lo + lane; j < hi; j += 32) {
-                unravel(j, p.d, p.d.n_a, p.d.nd, idx);
-                T sv = factor_sum(p, base, idx);
-                T l = ((const T*)p.lse.ptr)[lbase + dot_stride(p.lse, idx, p.d.n_a, p.d.nd)];
-                T g = ((const T*)p.gout.ptr)[gbase + dot_stride(p.gout, idx, p.d.n_a, p.d.nd)];
+                T sv = factor_sum<T, NRED>(p, base, j);
+                T l = ((const T*)p.lse.ptr)[lbase + red_off<NRED>(p.d, p.lse, j)];
+                T g = ((const T*)p.gout.ptr)[gbase + red_off<NRED>(p.d, p.gout, j)];
                 a += g * ab_exp(sv + p.cadd - l);
             }
             res = warp_sum(a);
-        } else {
+        } else if (hi - lo <= 128) {
+            T v[4];
             T m = neg_inf<T>();
-            for (i64 j = lo + lane; j < hi; j += 32) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); m = ab_max(m, factor_sum(p, base, idx)); }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                i64 j = lo + lane + 32 * q;
+                v[q] = j < hi ? factor_sum<T, NRED>(p, base, j) : neg_inf<T>();
+                m = ab_max(m, v[q]);
+            }
             m = warp_max(m);
             T a = T(0);
-            for (i64 j = lo + lane; j < hi; j += 32) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); a += ab_exp(factor_sum(p, base, idx) - m); }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a += (lo + lane + 32 * q < hi) ? ab_exp(v[q] - m) : T(0);
+            a = warp_sum(a);
+            res = (p.mode == R_LSE_EPS ? ab_log(a + Eps<T>::v()) : ab_log(a)) + m;
+        } else {
+            T m = neg_inf<T>();
+            for (i64 j = lo + lane; j < hi; j += 32) m = ab_max(m, factor_sum<T, NRED>(p, base, j));
+            m = warp_max(m);
+            T a = T(0);
+            for (i64 j = lo + lane; j < hi; j += 32) a += ab_exp(factor_sum<T, NRED>(p, base, j) - m);
             a = warp_sum(a);
             res = (p.mode == R_LSE_EPS ? ab_log(a + Eps<T>::v()) : ab_log(a)) + m;
         }
@@ -204,8 +239,8 @@ __global__ void __launch_bounds__(256) reduce_warp_kernel(const __grid_constant_
     }
 }
 
-// one thread per (output, split): small reduced extent (or none: plain broadcast add)
-template <typename T>
+// one thread per (output, split): outputs contiguous in memory / small reduced extent / none
+template <typename T, int NRED>
 __global__ void __launch_bounds__(256) reduce_thread_kernel(const __grid_constant__ ReduceParams<T> p) {
     int idx[AB_MAXD];
     i64 base[AB_MAXL];
@@ -220,27 +255,45 @@ __global__ void __launch_bounds__(256) reduce_thread_kernel(const __grid_constan
         T res;
         if (p.mode == R_SUM) {
             T a = T(0);
-            for (i64 j = lo; j < hi; ++j) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); a += factor_sum(p, base, idx); }
+            for (i64 j = lo; j < hi; ++j) a += factor_sum<T, NRED>(p, base, j);
             res = a;
         } else if (p.mode == R_WSUM) {
             i64 lbase = dot_stride(p.lse, idx, 0, p.d.n_a), gbase = dot_stride(p.gout, idx, 0, p.d.n_a);
             T a = T(0);
             for (i64 j = lo; j < hi; ++j) {
-                unravel(j, p.d, p.d.n_a, p.d.nd, idx);
-                T sv = factor_sum(p, base, idx);
-                T l = ((const T*)p.lse.ptr)[lbase + dot_stride(p.lse, idx, p.d.n_a, p.d.nd)];
-                T g = ((const T*)p.gout.ptr)[gbase + dot_stride(p.gout, idx, p.d.n_a, p.d.nd)];
+                T sv = factor_sum<T, NRED>(p, base, j);
+                T l = ((const T*)p.lse.ptr)[lbase + red_off<NRED>(p.d, p.lse, j)];
+                T g = ((const T*)p.gout.ptr)[gbase + red_off<NRED>(p.d, p.gout, j)];
                 a += g * ab_exp(sv + p.cadd - l);
             }
             res = a;
         } else {
             T m = neg_inf<T>();
-            for (i64 j = lo; j < hi; ++j) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); m = ab_max(m, factor_sum(p, base, idx)); }
+            for (i64 j = lo; j < hi; ++j) m = ab_max(m, factor_sum<T, NRED>(p, base, j));
             T a = T(0);
-            for (i64 j = lo; j < hi; ++j) { unravel(j, p.d, p.d.n_a, p.d.nd, idx); a += ab_exp(factor_sum(p, base, idx) - m); }
+            for (i64 j = lo; j < hi; ++j) a += ab_exp(factor_sum<T, NRED>(p, base, j) - m);
             res = (p.mode == R_LSE_EPS ? ab_log(a + Eps<T>::v()) : ab_log(a)) + m;
         }
         reduce_store(p, o, s, res);
+    }
+}
+
+template <typename T>
+static void launch_reduce(const ReduceParams<T>& p, bool thread_hint, cudaStream_t stream, int sm_count) {
+    const int nred = p.d.nd - p.d.n_a;
+    const i64 per = (p.n_red + p.nsplit - 1) / p.nsplit;
+    const bool warp = per >= 16 && !thread_hint;
+    i64 threads = p.n_out * p.nsplit * (warp ? 32 : 1);
+    i64 g = (threads + 255) / 256, cap = (i64)sm_count * 8;
+    int grid = (int)(g > cap ? cap : (g < 1 ? 1 : g));
+    if (warp) {
+        if (nred == 1) reduce_warp_kernel<T, 1><<<grid, 256, 0, stream>>>(p);
+        else if (nred == 2) reduce_warp_kernel<T, 2><<<grid, 256, 0, stream>>>(p);
+        else reduce_warp_kernel<T, 0><<<grid, 256, 0, stream>>>(p);
+    } else {
+        if (nred == 1) reduce_thread_kernel<T, 1><<<grid, 256, 0, stream>>>(p);
+        else if (nred == 2) reduce_thread_kernel<T, 2><<<grid, 256, 0, stream>>>(p);
+        else reduce_thread_kernel<T, 0><<<grid, 256, 0, stream>>>(p);
     }
 }
 

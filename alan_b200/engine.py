@@ -35,7 +35,8 @@ def working_dtype(*dicts):
 class Compiled:
     """Plan + the canonical (contiguous, canonical axis order, working dtype) input list."""
     def __init__(self, P: Plate, Q: Plate, sample, inputs_params, data, extra_log_factors=None,
-                 moment_specs=(), grad_names=(), N=None, shard_plate=None, world_size=1, dtype=None):
+                 moment_specs=(), grad_names=(), N=None, shard_plate=None, world_size=1, dtype=None,
+                 fast_paths=True):
         sample, inputs_params, data = dict(sample), dict(inputs_params or {}), dict(data or {})
         elf = dict(extra_log_factors or {})
         check_PQ(P, Q, set(data.keys()))
@@ -68,7 +69,7 @@ class Compiled:
             if role == 'elf':
                 self.elf_keys[orig] = key
         planner = Planner(P, Q, sig, sizes, self.dtype, want_sample_N=N, shard_plate=shard_plate,
-                          world_size=world_size)
+                          world_size=world_size, fast_paths=fast_paths)
         for orig, key in self.elf_keys.items():
             s = sig[key]
             extra.append((orig, Expr.leaf(planner.inputs[key], s.axes, s.pos_shape)))

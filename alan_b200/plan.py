@@ -292,6 +292,31 @@ class ReduceOp(Op):
                     w.i64(s)
 
 
+class NormalFanOp(Op):
+    """out[rows, f] = sum_d log N(v[rows,d]; l[rows,d], s[f,d])   (csrc/fused.cuh normal_fan_kernel)"""
+    code = OP_NORMAL_FAN
+
+    def __init__(self, out, D, rows, v, l, s, fan_axis, F, tag=''):
+        self.out, self.D, self.rows, self.v, self.l, self.s = out, D, rows, v, l, s
+        self.fan_axis, self.F, self.tag = fan_axis, F, tag
+
+    def payload(self, w):
+        w.tref(self.out); w.i32(self.D); w.i32(len(self.rows))
+        for d in self.rows:
+            w.i32(d[2])
+        o = plain(self.out)
+        for lf in (self.v, self.l, o):
+            for d in self.rows:
+                w.i64(lf.stride(d))
+        ev = ('ev', 0, self.D)
+        w.tref(self.v.pt); w.i64(self.v.stride(ev))
+        w.tref(self.l.pt); w.i64(self.l.stride(ev))
+        fdim = ('ax', self.fan_axis, self.F) if self.fan_axis else None
+        w.tref(self.s.pt); w.i64(self.s.stride(fdim) if fdim else 0); w.i64(self.s.stride(ev))
+        w.i32(self.F)
+        w.i64(o.stride(fdim) if fdim else 0)
+
+
 class ChainOp(Op):
     code = OP_CHAIN
 
@@ -427,7 +452,7 @@ class Plan:
 # ----------------------------------------------------------------------------------------
 class Planner:
     def __init__(self, P: Plate, Q: Plate, sig: dict, sizes: dict, dtype, extra_factors=(), want_sample_N=None,
-                 shard_plate=None, world_size=1, constants=None):
+                 shard_plate=None, world_size=1, constants=None, fast_paths=True):
         """sig: name -> TensorSig for samples, inputs/params, data and tensor-valued extra factors.
         sizes: axis name -> extent (plates and K axes).
         extra_factors: [(key, Expr)] expressions over input leaves, added as log factors at the plate
@@ -436,6 +461,7 @@ class Planner:
         self.itemsize = 4 if dtype == torch.float32 else 8
         self.extra_factors = list(extra_factors)
         self.N = want_sample_N
+        self.fast_paths = fast_paths
         self.shard_plate, self.world_size = shard_plate, world_size
         self.plan = Plan()
         self.plan.dtype = dtype
@@ -582,8 +608,9 @@ class Planner:
         res = go(body)
         return Code(instrs, consts, res, leaves)
 
-    def emit_expr(self, body: Expr, nred, tag='', out=None, acc=0, scale=1.0) -> PT:
-        """body: elementwise tree; nred = number of trailing positional dims summed ('all' = every one)."""
+    def emit_expr(self, body: Expr, nred, tag='', out=None, acc=0, scale=1.0, append=True):
+        """body: elementwise tree; nred = number of trailing positional dims summed ('all' = every one).
+        Returns the output tensor (and the op itself when append=False)."""
         R = len(body.pos_shape)
         if nred == 'all':
             nred = R
@@ -595,6 +622,8 @@ class Planner:
         if out is None:
             out = self.ws(axes, body.pos_shape[:R - nred], name=tag)
         op = ExprOp(out, keep + keep_ev, red_ev, code, acc=acc, scale=scale, tag=tag)
+        if not append:
+            return out, op
         self.fwd.append(op)
         return out
 
@@ -635,7 +664,43 @@ class Planner:
         probe = Expr(opname, operands, *_union(operands))
         operands = [operands[0]] + self._hoist_args(operands[1:], self._numel(probe))
         body = Expr(opname, operands, *_union(operands))
-        return self.emit_expr(body, nred='all', tag=tag)
+        out, op = self.emit_expr(body, nred='all', tag=tag, append=False)
+        fan = self._try_normal_fan(opname, operands, body, out, tag) if self.fast_paths else None
+        if fan is not None:
+            fan.autodiff_as = op            # adjoints are derived from the generic form of the same factor
+            self.fwd.append(fan)
+        else:
+            self.fwd.append(op)
+        return out
+
+    FAN_EVENT_EXTENTS = (1, 2, 3, 4, 6, 8, 12, 16, 18, 24, 32)
+
+    def _try_normal_fan(self, opname, operands, body, out, tag):
+        """Pattern of csrc/fused.cuh normal_fan_kernel: Normal whose value/loc carry the row axes and
+        whose scale carries (at most) one K axis of its own."""
+        if opname != 'Normal' or len(body.pos_shape) > 1:
+            return None
+        D = body.pos_shape[0] if body.pos_shape else 1
+        if D not in self.FAN_EVENT_EXTENTS:
+            return None
+        leaves = []
+        for e in operands:
+            if e.op == 'const':
+                e = Expr.leaf(self.const_input(torch.tensor(e.value)), (), ())
+            if e.op != 'leaf' or e.mode != 0 or e.rename or e.pos_shape not in ((), (D,)):
+                return None
+            leaves.append(e)
+        v, l, sc = leaves
+        fan_axes = [a for a in sc.axes if a not in v.axes and a not in l.axes]
+        if len(fan_axes) > 1 or any(a not in fan_axes for a in sc.axes):
+            return None
+        row_axes = [a for a in out.axes if a not in fan_axes]
+        n_rows = _prod(self.sizes[a] for a in row_axes)
+        F = self.sizes[fan_axes[0]] if fan_axes else 1
+        if n_rows * F < 4096 or len(row_axes) > MAXD:
+            return None
+        return NormalFanOp(out, D, [self.axdim(a) for a in row_axes], plain(v.ref), plain(l.ref), plain(sc.ref),
+                           fan_axes[0] if fan_axes else None, F, tag)
 
     # -- plate recursion (logpq.py:68-155, 257-332) -------------------------------------------
     def plan_plate(self, name, P: Plate, Q: Plate, active, scope):

@@ -142,6 +142,14 @@ def op_model(op, itemsize):
         if name == "ExprBwdOp":
             flops *= 3
         tag = getattr(f, "tag", "")
+    elif name == "NormalFanOp":
+        rows = math.prod(d[2] for d in op.rows)
+        for lf in (op.v, op.l, op.s):
+            add(lf.pt)
+        add(op.out)
+        pts = rows * op.F
+        flops = 2 * pts * op.D + 2 * rows * op.D
+        tag = op.tag
     elif name == "ReduceOp":
         pts = math.prod(d[2] for d in op.od + op.rd)
         for lf, _ in op.factors:

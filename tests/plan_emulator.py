@@ -135,6 +135,9 @@ class Emu:
         v = op.scale * res.reshape(-1)
         buf[base:base + n] = buf[base:base + n] + v if op.acc else v
 
+    def op_NormalFanOp(self, op):
+        self.op_ExprOp(op.autodiff_as)
+
     def op_ExprBwdOp(self, op):
         f = op.fwd
         dims = f.keep + f.red
