@@ -14,7 +14,7 @@
 
 enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
 enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
-       OP_NORMAL_FAN = 8, OP_COPY = 9 };
+       OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11 };
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -273,6 +273,48 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 p.F = r.i32();
                 p.o_f = r.i64v();
                 if (launch_fan<T>(p, D, c.stream, c.sm_count)) return fail("normal_fan: unsupported event extent");
+                break;
+            }
+            case OP_FAN_LSE: {
+                FanLseParams<T> p;
+                memset(&p, 0, sizeof(p));
+                int bwd = r.i32();
+                T* o = (T*)tref(r, c);
+                if (bwd) { p.lse = o; p.gout = (const T*)tref(r, c); p.gS = (T*)tref(r, c); } else p.out = o;
+                int D = r.i32();
+                int nrd = r.i32();
+                p.rd.nd = nrd; p.rd.n_a = nrd;
+                p.n_rho = 1;
+                for (int k = 0; k < nrd; ++k) { p.rd.size[k] = r.i32(); p.n_rho *= p.rd.size[k]; }
+                for (int k = 0; k < nrd; ++k) p.vstride[k] = r.i64v();
+                for (int k = 0; k < nrd; ++k) p.lstride[k] = r.i64v();
+                for (int k = 0; k < nrd; ++k) p.ostride[k] = r.i64v();
+                p.Kk = r.i32(); p.v_k = r.i64v(); p.l_k = r.i64v();
+                p.v = (const T*)tref(r, c); p.v_ev = r.i64v();
+                p.l = (const T*)tref(r, c); p.l_ev = r.i64v();
+                p.s = (const T*)tref(r, c); p.s_f = r.i64v(); p.s_ev = r.i64v();
+                p.F = r.i32(); p.o_f = r.i64v();
+                p.nb = r.i32();
+                for (int i = 0; i < p.nb; ++i) {
+                    p.bcoeff[i] = (T)r.f64();
+                    p.b[i] = (const T*)tref(r, c);
+                    for (int k = 0; k < nrd; ++k) p.bstride[i][k] = r.i64v();
+                    p.b_k[i] = r.i64v();
+                }
+                p.cadd = (T)r.f64();
+                int rc = launch_fan_lse<T>(p, D, bwd != 0, c.stream, c.sm_count);
+                if (rc) return fail(rc == 1 ? "fan_lse: unsupported event extent" : "fan_lse: tile does not fit shared memory");
+                break;
+            }
+            case OP_DOT: {
+                DotParams<T> p;
+                p.out = (T*)tref(r, c);
+                read_dims(r, p.d, p.n_out, p.n_red);
+                if (p.d.nd - p.d.n_a > 1) return fail("dot: more than one reduced dim");
+                read_opnd(r, c, p.a, p.d.nd, false);
+                read_opnd(r, c, p.b, p.d.nd, false);
+                if (p.d.nd == p.d.n_a) { p.a.stride[p.d.n_a] = 0; p.b.stride[p.d.n_a] = 0; }
+                dot_kernel<T><<<grid_for(p.n_out, 256, c), 256, 0, c.stream>>>(p);
                 break;
             }
             default:

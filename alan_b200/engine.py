@@ -87,6 +87,7 @@ class Compiled:
         planner.extra_factors = extra
         gnames = [self._key_of(n) for n in grad_names] + [j for j, _, _ in self.moment_inputs]
         self.grad_names = gnames
+        planner.set_grad_names(gnames)
         self.plan: Plan = planner.build(grad_names=gnames, with_sample=N is not None)
         self.planner = planner
 

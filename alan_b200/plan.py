@@ -32,7 +32,8 @@ from .trace import Expr, trace_function, UNARY, BINARY
 MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
 SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
-OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY = range(1, 10)
+OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY, OP_DOT, \
+    OP_FAN_LSE = range(1, 12)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
 
@@ -123,6 +124,7 @@ def plain(pt: PT) -> LeafRef:
 class W:
     def __init__(self):
         self.w = []
+        self.seen = {}          # id -> PT of every workspace tensor referenced while writing
 
     def i32(self, v):
         v = int(v)
@@ -138,7 +140,8 @@ class W:
 
     def tref(self, pt: PT):
         if pt.space == 'ws':
-            self.i32(SP_WS); self.i64(pt.offset)
+            self.seen[pt.id] = pt
+            self.i32(SP_WS); self.i64(pt.offset if pt.offset is not None else 0)
         elif pt.space == 'input':
             self.i32(SP_INPUT); self.i64(pt.index)
         elif pt.space == 'output':
@@ -184,6 +187,46 @@ def _opnd(w, leaf: LeafRef, dims, with_mode):
         w.i64(leaf.stride(d))
 
 
+def _coalesce(sizes, n_a, strides_list, pinned=()):
+    """Drop extent-1 dims and merge adjacent dims that every operand walks contiguously
+    (stride[i] == size[i+1] * stride[i+1]); never across the n_a boundary nor through `pinned`
+    dims (shift / first-step dims).  Returns (sizes, n_a, strides_list, index map old->new)."""
+    nd = len(sizes)
+    keep = [i for i in range(nd) if sizes[i] > 1 or i in pinned]
+    groups = []                       # list of lists of old dim indices
+    for i in keep:
+        if groups:
+            j = groups[-1][-1]
+            same_side = (j < n_a) == (i < n_a)
+            ok = same_side and i not in pinned and j not in pinned and \
+                all(st[j] == sizes[i] * st[i] for st in strides_list)
+            if ok:
+                groups[-1].append(i)
+                continue
+        groups.append([i])
+    new_sizes, new_strides, remap = [], [[] for _ in strides_list], {}
+    new_na = 0
+    for g in groups:
+        sz = 1
+        for i in g:
+            sz *= sizes[i]
+            remap[i] = len(new_sizes)
+        new_sizes.append(sz)
+        if g[0] < n_a:
+            new_na += 1
+        for k, st in enumerate(strides_list):
+            new_strides[k].append(st[g[-1]])
+    return new_sizes, new_na, new_strides, remap
+
+
+def _write_dims(w, sizes, n_a):
+    if len(sizes) > MAXD:
+        raise Exception(f"op needs {len(sizes)} iteration dims; the kernels support {MAXD}")
+    w.i32(n_a); w.i32(len(sizes) - n_a)
+    for sz in sizes:
+        w.i32(sz)
+
+
 def _strides_like(pt: PT, own_dims, dims):
     """strides of a contiguous tensor laid out over own_dims, seen from the op dims `dims`."""
     st, acc = {}, 1
@@ -224,6 +267,26 @@ class FillOp(Op):
         w.tref(self.pt); w.i64(self.nbytes)
 
 
+class FillRegionOp(FillOp):
+    """Zero the whole adjoint region of the workspace (resolved when offsets are assigned)."""
+    def __init__(self, plan):
+        self.plan = plan
+
+    def payload(self, w):
+        lo, hi = self.plan.adj_region
+        w.i32(SP_WS); w.i64(lo); w.i64(max(hi - lo, 0))
+
+    @property
+    def pt(self):
+        lo, hi = self.plan.adj_region
+        return PT((), (1,), {}, 'ws', offset=lo)
+
+    @property
+    def nbytes(self):
+        lo, hi = self.plan.adj_region
+        return hi - lo
+
+
 class ExprOp(Op):
     """out[keep] (+)= scale * sum_red VM(leaves)   (csrc/kernels.cuh expr_fwd_kernel)"""
     code = OP_EXPR
@@ -234,12 +297,20 @@ class ExprOp(Op):
     def payload(self, w):
         w.tref(self.out); w.i32(self.acc); w.f64(self.scale)
         dims = self.keep + self.red
-        _dims(w, self.keep, self.red)
-        if len(self.codeobj.leaves) > MAXL:
+        leaves = self.codeobj.leaves
+        if len(leaves) > MAXL:
             raise Exception("factor expression reads more than 10 tensors")
-        w.i32(len(self.codeobj.leaves))
-        for lf in self.codeobj.leaves:
-            _opnd(w, lf, dims, True)
+        keys = [(d[0], d[1]) for d in dims]
+        pinned = {keys.index(('ax', lf.mdim)) for lf in leaves if lf.mode}
+        strides = [[lf.stride(d) for d in dims] for lf in leaves]
+        sizes, n_a, strides, remap = _coalesce([d[2] for d in dims], len(self.keep), strides, pinned)
+        _write_dims(w, sizes, n_a)
+        w.i32(len(leaves))
+        for lf, st in zip(leaves, strides):
+            w.tref(lf.pt); w.i32(lf.mode)
+            w.i32(remap[keys.index(('ax', lf.mdim))] if lf.mode else 0)
+            for x in st:
+                w.i64(x)
         self.codeobj.write(w)
 
 
@@ -253,13 +324,21 @@ class ExprBwdOp(Op):
     def payload(self, w):
         w.tref(self.gleaf); w.i32(self.acc); w.f64(self.scale); w.i32(self.target); w.i32(self.nsplit)
         dims = self.kept + self.loop
-        _dims(w, self.kept, self.loop)
+        leaves = self.fwd.codeobj.leaves
+        keys = [(d[0], d[1]) for d in dims]
+        pinned = {keys.index(('ax', lf.mdim)) for lf in leaves if lf.mode}
+        strides = [_strides_like(self.gout, self.fwd.keep, dims)] + [[lf.stride(d) for d in dims] for lf in leaves]
+        sizes, n_a, strides, remap = _coalesce([d[2] for d in dims], len(self.kept), strides, pinned)
+        _write_dims(w, sizes, n_a)
         w.tref(self.gout)
-        for s in _strides_like(self.gout, self.fwd.keep, dims):
-            w.i64(s)
-        w.i32(len(self.fwd.codeobj.leaves))
-        for lf in self.fwd.codeobj.leaves:
-            _opnd(w, lf, dims, True)
+        for x in strides[0]:
+            w.i64(x)
+        w.i32(len(leaves))
+        for lf, st in zip(leaves, strides[1:]):
+            w.tref(lf.pt); w.i32(lf.mode)
+            w.i32(remap[keys.index(('ax', lf.mdim))] if lf.mode else 0)
+            for x in st:
+                w.i64(x)
         self.fwd.codeobj.write(w)
 
 
@@ -278,18 +357,25 @@ class ReduceOp(Op):
         w.i32(self.mode); w.tref(self.out); w.i32(self.acc); w.f64(self.scale); w.f64(self.cadd); w.i32(self.nsplit)
         w.i32(1 if self.thread_hint else 0)
         dims = self.od + self.rd
-        _dims(w, self.od, self.rd)
         if len(self.factors) > MAXL:
             raise Exception("contraction step joins more than 10 factor tensors")
-        w.i32(len(self.factors))
-        for (lf, coeff) in self.factors:
-            w.f64(coeff)
-            _opnd(w, lf, dims, False)
+        strides = [[lf.stride(d) for d in dims] for lf, _ in self.factors]
+        extra = []
         if self.mode == R_WSUM:
-            for pt, own in ((self.lse, self.lse_dims), (self.gout, self.gout_dims)):
-                w.tref(pt)
-                for s in _strides_like(pt, own, dims):
-                    w.i64(s)
+            extra = [(self.lse, self.lse_dims), (self.gout, self.gout_dims)]
+            strides += [_strides_like(pt, own, dims) for pt, own in extra]
+        sizes, n_a, strides, _ = _coalesce([d[2] for d in dims], len(self.od), strides)
+        _write_dims(w, sizes, n_a)
+        w.i32(len(self.factors))
+        for (lf, coeff), st in zip(self.factors, strides):
+            w.f64(coeff)
+            w.tref(lf.pt)
+            for x in st:
+                w.i64(x)
+        for (pt, own), st in zip(extra, strides[len(self.factors):]):
+            w.tref(pt)
+            for x in st:
+                w.i64(x)
 
 
 class NormalFanOp(Op):
@@ -315,6 +401,77 @@ class NormalFanOp(Op):
         w.tref(self.s.pt); w.i64(self.s.stride(fdim) if fdim else 0); w.i64(self.s.stride(ev))
         w.i32(self.F)
         w.i64(o.stride(fdim) if fdim else 0)
+
+
+class FanLseOp(Op):
+    """out[rho, f] = LSE_eps over kappa of (Normal factor + small factors) + cadd, nothing materialised
+    (csrc/fused.cuh fan_lse_kernel).  gen_expr / gen_reduce are the unfused ops it stands for."""
+    code = OP_FAN_LSE
+
+    def __init__(self, out, D, rho, kappa, v, l, s, fan_axis, F, bfactors, cadd, gen_expr, gen_reduce, tag=''):
+        self.out, self.D, self.rho, self.kappa, self.v, self.l, self.s = out, D, rho, kappa, v, l, s
+        self.fan_axis, self.F, self.bfactors, self.cadd = fan_axis, F, bfactors, cadd
+        self.gen_expr, self.gen_reduce, self.tag = gen_expr, gen_reduce, tag
+
+    def _body(self, w):
+        w.i32(self.D); w.i32(len(self.rho))
+        for d in self.rho:
+            w.i32(d[2])
+        o = plain(self.out)
+        for lf in (self.v, self.l, o):
+            for d in self.rho:
+                w.i64(lf.stride(d))
+        w.i32(self.kappa[2]); w.i64(self.v.stride(self.kappa)); w.i64(self.l.stride(self.kappa))
+        ev = ('ev', 0, self.D)
+        fdim = ('ax', self.fan_axis, self.F)
+        w.tref(self.v.pt); w.i64(self.v.stride(ev))
+        w.tref(self.l.pt); w.i64(self.l.stride(ev))
+        w.tref(self.s.pt); w.i64(self.s.stride(fdim)); w.i64(self.s.stride(ev))
+        w.i32(self.F); w.i64(o.stride(fdim))
+        if len(self.bfactors) > MAXL:
+            raise Exception("fused contraction joins more than 10 small factors")
+        w.i32(len(self.bfactors))
+        for lf, coeff in self.bfactors:
+            w.f64(coeff); w.tref(lf.pt)
+            for d in self.rho:
+                w.i64(lf.stride(d))
+            w.i64(lf.stride(self.kappa))
+        w.f64(self.cadd)
+
+    def payload(self, w):
+        w.i32(0); w.tref(self.out)
+        self._body(w)
+
+
+class FanLseBwdOp(Op):
+    """gS[rho, kappa] = sum_f gout[rho,f] * softmax weight: adjoint of the small-factor sum."""
+    code = OP_FAN_LSE
+
+    def __init__(self, fwd: FanLseOp, gout, gS):
+        self.fwd, self.gout, self.gS = fwd, gout, gS
+
+    def payload(self, w):
+        w.i32(1); w.tref(self.fwd.out); w.tref(self.gout); w.tref(self.gS)
+        self.fwd._body(w)
+
+
+class DotOp(Op):
+    """out[keep] = sum_e a * b   (csrc/fused.cuh dot_kernel)"""
+    code = OP_DOT
+
+    def __init__(self, out, keep, red, a, b, tag=''):
+        self.out, self.keep, self.red, self.a, self.b, self.tag = out, keep, red, a, b, tag
+
+    def payload(self, w):
+        w.tref(self.out)
+        dims = self.keep + self.red
+        strides = [[lf.stride(d) for d in dims] for lf in (self.a, self.b)]
+        sizes, n_a, strides, _ = _coalesce([d[2] for d in dims], len(self.keep), strides)
+        _write_dims(w, sizes, n_a)
+        for lf, st in zip((self.a, self.b), strides):
+            w.tref(lf.pt)
+            for x in st:
+                w.i64(x)
 
 
 class ChainOp(Op):
@@ -428,6 +585,27 @@ class Plan:
         self.blob = None
         self.retained = {}           # debugging: name -> PT of interesting intermediates
 
+    def assign_offsets(self, itemsize):
+        """Dry-run serialisation to find the workspace tensors the emitted ops really touch, then lay
+        them out: forward tensors first, adjoints/partials after (one contiguous region to zero)."""
+        self.adj_region = (0, 0)
+        w = W()
+        for prog in self.programs:
+            for op in prog:
+                op.serialize(w)
+        off = 0
+        for group in (0, 1):
+            if group == 1:
+                lo = off
+            for pt in sorted(w.seen.values(), key=lambda p: p.id):
+                if getattr(pt, 'group', 0) != group:
+                    continue
+                pt.offset = off
+                nbytes = getattr(pt, 'alloc_numel', pt.numel) * itemsize
+                off += (nbytes + 255) // 256 * 256
+        self.adj_region = (lo, off)
+        self.ws_bytes = max(off, 256)
+
     def serialize(self):
         w = W()
         for v in (MAGIC, VERSION, 0 if self.dtype == torch.float32 else 1, len(self.input_names),
@@ -452,7 +630,7 @@ class Plan:
 # ----------------------------------------------------------------------------------------
 class Planner:
     def __init__(self, P: Plate, Q: Plate, sig: dict, sizes: dict, dtype, extra_factors=(), want_sample_N=None,
-                 shard_plate=None, world_size=1, constants=None, fast_paths=True):
+                 shard_plate=None, world_size=1, constants=None, fast_paths=True, grad_names=()):
         """sig: name -> TensorSig for samples, inputs/params, data and tensor-valued extra factors.
         sizes: axis name -> extent (plates and K axes).
         extra_factors: [(key, Expr)] expressions over input leaves, added as log factors at the plate
@@ -473,6 +651,10 @@ class Planner:
         self.canon = list(self.all_plates) + [Kname(g) for g in self.groups]
         self.plan.canon_axes = self.canon
         self.ws_off = 0
+        self.alloc_group = 0
+        self.grad_names = list(grad_names)
+        self.needs = set()
+        self.fan_by_out = {}
         self.fwd = []
         self.fwd_segments = []
         self.steps = []              # resampling steps in forward (bottom-up) creation order per level
@@ -486,6 +668,30 @@ class Planner:
         for name, s in sig.items():
             if s.role in ('sample', 'param'):
                 self.scope[name] = Expr.leaf(self.inputs[name], s.axes, s.pos_shape)
+
+    def set_grad_names(self, names):
+        self.grad_names = list(names)
+        self.needs = set(self.inputs[n].id for n in self.grad_names)
+
+    @staticmethod
+    def op_inputs(op):
+        op = getattr(op, 'autodiff_as', None) or op
+        if isinstance(op, ExprOp):
+            return [lf.pt for lf in op.codeobj.leaves]
+        if isinstance(op, ReduceOp):
+            return [lf.pt for lf, _ in op.factors]
+        if isinstance(op, ChainOp):
+            return [op.ms]
+        if isinstance(op, FanLseOp):
+            return [lf.pt for lf, _ in op.bfactors] + [op.v.pt, op.l.pt, op.s.pt]
+        return []
+
+    def emit(self, op):
+        """Append a forward op and propagate 'needs a gradient' to its output."""
+        self.fwd.append(op)
+        if not isinstance(getattr(op, 'autodiff_as', None), str):
+            if any(p.id in self.needs for p in self.op_inputs(op)):
+                self.needs.add(op.out.id)
 
     # -- allocation -------------------------------------------------------------------
     def _add_input(self, name, axes, pos_shape):
@@ -510,16 +716,14 @@ class Planner:
             self.consts[key] = pt
         return self.consts[key]
 
-    def ws(self, axes, pos_shape=(), name='', numel=None, itemsize=None):
-        pt = PT(axes, pos_shape, self.sizes, 'ws', offset=self.ws_off, name=name)
-        n = pt.numel if numel is None else numel
-        nbytes = n * (itemsize or self.itemsize)
-        self.ws_off += (nbytes + 255) // 256 * 256
+    def ws(self, axes, pos_shape=(), name=''):
+        pt = PT(axes, pos_shape, self.sizes, 'ws', offset=None, name=name)
+        pt.group = self.alloc_group
         return pt
 
     def ws_raw(self, numel, name=''):
-        pt = PT((), (max(int(numel), 1),), self.sizes, 'ws', offset=self.ws_off, name=name)
-        self.ws_off += (pt.numel * self.itemsize + 255) // 256 * 256
+        pt = PT((), (max(int(numel), 1),), self.sizes, 'ws', offset=None, name=name)
+        pt.group = self.alloc_group
         return pt
 
     def canon_order(self, axes):
@@ -546,7 +750,14 @@ class Planner:
             return e
         if e.op == 'sumlast':
             body = self._prepare(e.args[0])
-            pt = self.emit_expr(body, nred=1, tag=tag or 'sumlast')
+            pt, op = self.emit_expr(body, nred=1, tag=tag or 'sumlast', append=False)
+            a_b = body.args if body.op == 'mul' else ()
+            if self.fast_paths and len(a_b) == 2 and all(x.op == 'leaf' and x.mode == 0 and not x.rename for x in a_b):
+                dot = DotOp(pt, op.keep, op.red, plain(a_b[0].ref), plain(a_b[1].ref), tag='dot')
+                dot.autodiff_as = op
+                self.emit(dot)
+            else:
+                self.emit(op)
         else:
             body = self._prepare(e)
             pt = self.emit_expr(body, nred=0, tag=tag or 'expr')
@@ -624,7 +835,7 @@ class Planner:
         op = ExprOp(out, keep + keep_ev, red_ev, code, acc=acc, scale=scale, tag=tag)
         if not append:
             return out, op
-        self.fwd.append(op)
+        self.emit(op)
         return out
 
     # -- distribution arguments ------------------------------------------------------------
@@ -668,9 +879,10 @@ class Planner:
         fan = self._try_normal_fan(opname, operands, body, out, tag) if self.fast_paths else None
         if fan is not None:
             fan.autodiff_as = op            # adjoints are derived from the generic form of the same factor
-            self.fwd.append(fan)
+            self.fan_by_out[out.id] = fan
+            self.emit(fan)
         else:
-            self.fwd.append(op)
+            self.emit(op)
         return out
 
     FAN_EVENT_EXTENTS = (1, 2, 3, 4, 6, 8, 12, 16, 18, 24, 32)
@@ -777,7 +989,7 @@ class Planner:
             out_axes = self.canon_order([a for a in q_axes if a not in parents])
             out = self.ws(out_axes, name=f'logQ~:{name}')
             cadd = -sum(math.log(self.sizes[a]) for a in parents)
-            self.fwd.append(ReduceOp(R_LSE_EPS, out, [self.axdim(a) for a in out_axes], rd,
+            self.emit(ReduceOp(R_LSE_EPS, out, [self.axdim(a) for a in out_axes], rd,
                                      [(plain(pt), 1.0) for pt in q_tensors], cadd=cadd, tag=f'reduce_logQ:{name}'))
             facs.append((plain(out), -1.0))
         else:
@@ -822,13 +1034,47 @@ class Planner:
                 continue
             out_axes = self.canon_order([a for a in chosen_axes if a not in ks])
             out = self.ws(out_axes, name='lse[' + ','.join(ks) + ']')
-            self.fwd.append(ReduceOp(R_LSE_EPS, out, [self.axdim(a) for a in out_axes],
-                                     [self.axdim(a) for a in ks], tensors, cadd=const,
-                                     tag='contract:' + ','.join(ks)))
+            red = ReduceOp(R_LSE_EPS, out, [self.axdim(a) for a in out_axes],
+                           [self.axdim(a) for a in ks], tensors, cadd=const, tag='contract:' + ','.join(ks))
+            fused = self._try_fan_lse(red, tensors, ks, const) if self.fast_paths else None
+            self.emit(fused if fused is not None else red)
             level_steps.append(Step(tuple(active), tensors, ks))
             lfs.append(LogicalFactor([(plain(out), 1.0)], 0.0, out_axes))
         assert len(lfs) == 1
         return lfs[0]
+
+    def _try_fan_lse(self, red, tensors, ks, const):
+        """Fuse a normal_fan factor into the LSE step that consumes it (csrc/fused.cuh fan_lse_kernel)
+        when nobody else needs the materialised factor: no resampling program, no adjoint of the
+        factor itself (RWS / marginals of other groups only need the small factors' adjoints)."""
+        if len(ks) != 1 or getattr(self, 'with_sample', False):
+            return None
+        kappa = ks[0]
+        cands = [(lf, c) for lf, c in tensors if lf.pt.id in self.fan_by_out and c == 1.0 and type(lf) is LeafRef]
+        if len(cands) != 1:
+            return None
+        big, _ = cands[0]
+        fan = self.fan_by_out[big.pt.id]
+        if fan not in self.fwd or big.pt.id in self.needs or fan.fan_axis is None or fan.F < 8:
+            return None
+        row_axes = [d[1] for d in fan.rows]
+        if kappa not in row_axes or self.sizes[kappa] > 128 or kappa == fan.fan_axis:
+            return None
+        small = [(lf, c) for lf, c in tensors if lf is not big]
+        for lf, c in small:
+            if type(lf) is not LeafRef or lf.rename or lf.mode or lf.pt.pos_shape:
+                return None
+            if any(a not in row_axes for a in lf.pt.axes):
+                return None
+        if fan.v.stride(self.axdim(kappa)) == 0 and fan.l.stride(self.axdim(kappa)) == 0:
+            return None
+        rho = [d for d in fan.rows if d[1] != kappa]
+        tile = self.sizes[kappa] * ((fan.D + 3) // 4 * 4 + 1) * 8 * self.itemsize
+        if tile > 150 * 1024:
+            return None
+        self.fwd.remove(fan)
+        return FanLseOp(red.out, fan.D, rho, self.axdim(kappa), fan.v, fan.l, fan.s, fan.fan_axis, fan.F,
+                        small, const, fan.autodiff_as, red, tag='fan_lse:' + fan.tag)
 
     def plate_sum(self, lf: LogicalFactor, plate):
         out_axes = tuple(a for a in lf.axes if a != plate)
@@ -842,15 +1088,15 @@ class Planner:
             part = self.ws_raw(nsplit * n_out, name=f'partial[{plate}]')
             first = ReduceOp(R_SUM, part, od, rd, lf.tensors, nsplit=nsplit, tag=f'plate_sum_partial:{plate}')
             first.autodiff_as = 'skip'
-            self.fwd.append(first)
+            self.emit(first)
             sd = ('sp', 0, nsplit)
             second = ReduceOp(R_SUM, out, od, [sd], [(_PartialRef(part, od, nsplit), 1.0)],
                               cadd=lf.const * n, tag=f'plate_sum:{plate}')
             # the adjoint is derived from the unsplit form of the same sum
             second.autodiff_as = ReduceOp(R_SUM, out, od, rd, lf.tensors, cadd=lf.const * n)
-            self.fwd.append(second)
+            self.emit(second)
         else:
-            self.fwd.append(ReduceOp(R_SUM, out, od, rd, lf.tensors, cadd=lf.const * n, tag=f'plate_sum:{plate}'))
+            self.emit(ReduceOp(R_SUM, out, od, rd, lf.tensors, cadd=lf.const * n, tag=f'plate_sum:{plate}'))
         if plate == self.shard_plate:
             self.plan.allreduce = out
             self.fwd_segments.append(self.fwd)
@@ -868,7 +1114,7 @@ class Planner:
             raise Exception("Timeseries needs the same K for the initial state and the chain")
         ms = self.ws(ms_axes, name='chain_ms')
         od = [self.axdim(a) for a in ms_axes]
-        self.fwd.append(ReduceOp(R_SUM, ms, od, [], lf.tensors, cadd=lf.const, tag='chain_ms'))
+        self.emit(ReduceOp(R_SUM, ms, od, [], lf.tensors, cadd=lf.const, tag='chain_ms'))
         K, T = self.sizes[Kts], self.sizes[T_axis]
         n_outer = _prod(self.sizes[a] for a in outer)
         n, tot = T, 0
@@ -877,18 +1123,21 @@ class Planner:
             tot += n_outer * n * K * K
         levels = self.ws_raw(max(tot, 1), name='chain_levels')
         out = self.ws(outer + (Kinit,), name='chain_out')
-        self.fwd.append(ChainOp(ms, levels, out, n_outer, T, K))
+        self.emit(ChainOp(ms, levels, out, n_outer, T, K))
         return LogicalFactor([(plain(out), 1.0)], 0.0, out.axes)
 
     # -- top level ----------------------------------------------------------------------------
     def build(self, grad_names=(), with_sample=False) -> Plan:
+        if grad_names or not self.grad_names:
+            self.set_grad_names(grad_names)
+        self.with_sample = with_sample
         lf = self.plan_plate(None, self.P, self.Q, (), self.scope)
         if lf.axes != ():
             raise Exception(f"log-evidence has leftover axes {lf.axes}")
         lp = PT((), (), self.sizes, 'output', index=0, name='lp')
         self.lp_ws = self.ws((), name='lp')
-        self.fwd.append(ReduceOp(R_SUM, self.lp_ws, [], [], lf.tensors, cadd=lf.const, tag='lp'))
-        self.fwd.append(ReduceOp(R_SUM, lp, [], [], [(plain(self.lp_ws), 1.0)], tag='lp_out'))
+        self.emit(ReduceOp(R_SUM, self.lp_ws, [], [], lf.tensors, cadd=lf.const, tag='lp'))
+        self.emit(ReduceOp(R_SUM, lp, [], [], [(plain(self.lp_ws), 1.0)], tag='lp_out'))
         self.fwd_segments.append(self.fwd)
         plan = self.plan
         plan.programs = list(self.fwd_segments)
@@ -899,7 +1148,7 @@ class Planner:
         if with_sample:
             plan.sample_prog = len(plan.programs)
             plan.programs.append(self.build_sampling())
-        plan.ws_bytes = max(self.ws_off, 256)
+        plan.assign_offsets(self.itemsize)
         plan.serialize()
         return plan
 
@@ -922,19 +1171,8 @@ class Planner:
                 seg_of[id(lop)] = si
                 if si == 0:
                     sharded_ids.add(id(lop))
-        needs = set(self.inputs[n].id for n in grad_names)
-
-        def op_inputs(op):
-            if isinstance(op, ExprOp):
-                return [lf.pt for lf in op.codeobj.leaves]
-            if isinstance(op, ReduceOp):
-                return [lf.pt for lf, _ in op.factors]
-            if isinstance(op, ChainOp):
-                return [op.ms]
-            return []
-        for op in all_fwd:
-            if any(p.id in needs for p in op_inputs(op)):
-                needs.add(op.out.id)
+        needs = self.needs
+        self.alloc_group = 1
         adj = {}
         grad_out = {}
         for i, n in enumerate(grad_names):
@@ -942,7 +1180,6 @@ class Planner:
             g = PT(src.axes, src.pos_shape, self.sizes, 'output', index=i, name=f'g:{n}')
             adj[src.id] = g
             grad_out[n] = g
-        adj_lo = self.ws_off
 
         def adjoint(pt):
             if pt.id not in adj:
@@ -1021,16 +1258,38 @@ class Planner:
                                                  [(_PartialRef(part, od, nsplit), 1.0)], acc=1, scale=scale))
                     else:
                         out_list.append(ReduceOp(mode, g, kept, loop, facs, acc=1, scale=scale, **kw))
+            elif isinstance(op, FanLseOp):
+                bs = [(lf, coeff) for lf, coeff in op.bfactors if lf.pt.id in needs]
+                if bs:
+                    rows = op.rho + [op.kappa]
+                    gS = self.ws(tuple(d[1] for d in rows), name='adj:small_factor_sum')
+                    out_list.append(FanLseBwdOp(op, gout, gS))
+                    for lf, coeff in bs:
+                        g = adjoint(lf.pt)
+                        kept = [d for d in rows if lf.stride(d) != 0]
+                        kept.sort(key=lambda d: -lf.stride(d))
+                        loop = [d for d in rows if lf.stride(d) == 0]
+                        n_kept = _prod(d[2] for d in kept)
+                        if n_kept != lf.pt.numel:
+                            raise Exception(f"adjoint of {lf.pt}: fused contraction does not cover the tensor")
+                        scale = coeff * (rep_scale if g.space == 'output' else 1.0)
+                        nsplit = _choose_split(n_kept, _prod(d[2] for d in loop))
+                        facs = [(_OwnDims(gS, rows), 1.0)]
+                        if nsplit > 1:
+                            part = self.ws_raw(nsplit * n_kept, name='partial_adj')
+                            out_list.append(ReduceOp(R_SUM, part, kept, loop, facs, nsplit=nsplit))
+                            od = [('fl', 0, n_kept)]
+                            out_list.append(ReduceOp(R_SUM, g, od, [('sp', 0, nsplit)],
+                                                     [(_PartialRef(part, od, nsplit), 1.0)], acc=1, scale=scale))
+                        else:
+                            out_list.append(ReduceOp(R_SUM, g, kept, loop, facs, acc=1, scale=scale))
             elif isinstance(op, ChainOp):
                 if op.ms.id in needs:
                     gms = adjoint(op.ms)
                     glevels = self.ws_raw(op.levels.numel, name='chain_glevels')
                     out_list.append(ChainBwdOp(op, gout, glevels, gms))
-        adj_hi = self.ws_off
         # zero the adjoint region and the gradient outputs, then run the reversed ops
-        head = []
-        if adj_hi > adj_lo:
-            head.append(FillOp(PT((), (1,), self.sizes, 'ws', offset=adj_lo), adj_hi - adj_lo))
+        head = [FillRegionOp(plan)]
         for n, g in grad_out.items():
             head.append(FillOp(g, g.numel * self.itemsize))
         segs[0] = head + segs[0]

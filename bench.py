@@ -142,6 +142,23 @@ def op_model(op, itemsize):
         if name == "ExprBwdOp":
             flops *= 3
         tag = getattr(f, "tag", "")
+    elif name in ("FanLseOp", "FanLseBwdOp"):
+        f = op if name == "FanLseOp" else op.fwd
+        rows = math.prod(d[2] for d in f.rho) * f.kappa[2]
+        for lf in (f.v, f.l, f.s):
+            add(lf.pt)
+        for lf, _ in f.bfactors:
+            add(lf.pt)
+        add(f.out)
+        if name == "FanLseBwdOp":
+            add(op.gout); add(op.gS)
+        pts = rows * f.F
+        flops = 2 * pts * f.D + 6 * pts + 2 * rows * f.D
+        tag = f.tag + (":adjoint" if name == "FanLseBwdOp" else "")
+    elif name == "DotOp":
+        pts = math.prod(d[2] for d in op.keep + op.red)
+        add(op.a.pt); add(op.b.pt); add(op.out)
+        flops, tag = 2 * pts, op.tag
     elif name == "NormalFanOp":
         rows = math.prod(d[2] for d in op.rows)
         for lf in (op.v, op.l, op.s):

@@ -55,9 +55,14 @@ class Emu:
         self.inputs = [x.reshape(-1) for x in inputs]
         self.outputs = outputs or {}
         self.aux = aux or {}
+        self.side = {}
 
     def buf(self, pt):
         if pt.space == 'ws':
+            if pt.offset is None:             # tensor that only the unfused form of an op would touch
+                if pt.id not in self.side:
+                    self.side[pt.id] = t.zeros(pt.numel, dtype=self.dtype)
+                return self.side[pt.id], 0
             return self.ws, pt.offset // self.item
         if pt.space == 'input':
             return self.inputs[pt.index], 0
@@ -134,6 +139,26 @@ class Emu:
         n = res.numel()
         v = op.scale * res.reshape(-1)
         buf[base:base + n] = buf[base:base + n] + v if op.acc else v
+
+    def op_FillRegionOp(self, op):
+        lo, hi = self.plan.adj_region
+        self.ws[lo // self.item: hi // self.item] = 0
+
+    def op_FanLseOp(self, op):
+        self.op_ExprOp(op.gen_expr)
+        self.op_ReduceOp(op.gen_reduce)
+
+    def op_FanLseBwdOp(self, op):
+        f = op.fwd
+        self.op_ExprOp(f.gen_expr)
+        rows = f.rho + [f.kappa]
+        fdim = [('ax', f.fan_axis, f.F)]
+        r = f.gen_reduce
+        self.op_ReduceOp(PL.ReduceOp(PL.R_WSUM, op.gS, rows, fdim, r.factors, lse=r.out, gout=op.gout,
+                                     lse_dims=r.od, gout_dims=r.od, cadd=r.cadd))
+
+    def op_DotOp(self, op):
+        self.op_ExprOp(op.autodiff_as)
 
     def op_NormalFanOp(self, op):
         self.op_ExprOp(op.autodiff_as)

@@ -292,3 +292,51 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(runtime, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError):
         runtime.lib()
+
+
+@pytest.mark.parametrize("dtype", [t.float32, t.float64])
+@pytest.mark.parametrize("M_,N_,K", [(20, 3, 8), (64, 5, 30), (33, 7, 17)])
+def test_fused_kernels_match_generic_kernels_and_oracle(dtype, M_, N_, K):
+    """normal_fan / fan_lse / dot (csrc/fused.cuh) against the generic VM + reduce kernels on the same
+    inputs, and both against the oracle.  Ragged sizes on purpose (K=17, M=33: partial warps/tiles)."""
+    from oracle import logpq_oracle as O
+    Compiled, Runner = _engine()
+    P, Q = models.movielens_model(M)
+    inp = models.movielens_inputs(M=M_, N=N_, d=18, seed=3, dtype=dtype)
+    inp['event_shapes'] = {'mu_z': (18,), 'psi_z': (18,), 'z': (18,)}
+    sample = _random_sample(P, Q, inp, K, dtype, 11)
+    ip = {**_nt(inp['inputs']), **_nt(inp['params'])}
+    data = _nt(inp['data'])
+    names = list(inp['params'])
+    res = {}
+    for fast in (True, False):
+        comp = Compiled(P, Q, sample, ip, data, grad_names=names, fast_paths=fast)
+        kinds = [type(op).__name__ for prog in comp.plan.programs for op in prog]
+        assert ('FanLseOp' in kinds) == fast
+        run = Runner(comp, "cuda:0")
+        tensors = run.device_inputs(sample, ip, data)
+        lp = run.forward_raw(tensors)
+        grads = run.backward_raw(tensors)
+        res[fast] = (lp.cpu(), {k: v.cpu() for k, v in grads.items()}, comp)
+    ipg = {k: NT(v.t.clone().requires_grad_() if k in names else v.t, v.axes) for k, v in ip.items()}
+    ref = O.elbo(P, Q, sample, ipg, data)
+    rg = t.autograd.grad(ref, [ipg[k].t for k in names])
+    tl = 1e-5 if dtype == t.float32 else 1e-10
+    for fast in (True, False):
+        lp, grads, comp = res[fast]
+        assert rel_err(lp, ref) < tl, fast
+        for k, r in zip(names, rg):
+            pt = comp.plan.input_pts[k]
+            assert rel_err(_as(pt.axes, grads[k], ipg[k].axes), r) < 30 * tl, (fast, k)
+    # VI-style gradients (w.r.t. the samples) use normal_fan + generic adjoint
+    comp = Compiled(P, Q, sample, ip, data, grad_names=['z', 'mu_z', 'psi_z'])
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(sample, ip, data)
+    run.forward_raw(tensors)
+    grads = run.backward_raw(tensors)
+    sg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in sample.items()}
+    ref = O.elbo(P, Q, sg, ip, data)
+    rg = t.autograd.grad(ref, [sg[k].t for k in ('z', 'mu_z', 'psi_z')])
+    for k, r in zip(('z', 'mu_z', 'psi_z'), rg):
+        pt = comp.plan.input_pts[k]
+        assert rel_err(_as(pt.axes, grads[k].cpu(), sg[k].axes), r) < 30 * tl, k

@@ -114,3 +114,39 @@ def test_resampling(case, tag):
         total += ref.numel()
         bad += (mine != ref).sum().item()
     assert bad <= 1e-3 * total, f"{bad}/{total}"
+
+
+@pytest.mark.parametrize("dtype", [t.float32, t.float64])
+def test_fused_paths_selected_and_match_oracle(dtype):
+    """At sizes where the planner picks the tuned kernels (normal_fan fused with its LSE, dot), the
+    plan still reproduces the oracle's log-evidence and RWS gradients (emulated semantics)."""
+    from oracle import logpq_oracle as O
+    from alan_b200.named import from_torch_named
+    P, Q = models.movielens_model(M)
+    inp = models.movielens_inputs(M=20, N=3, d=18, seed=3, dtype=dtype)
+    g = t.Generator().manual_seed(9)
+    K = 8
+    r = lambda *s: (0.7 * t.randn(s, generator=g, dtype=t.float64)).to(dtype)
+    sample = {'mu_z': NT(r(K, 18), ('K_mu_z',)), 'psi_z': NT(r(K, 18) - 0.5, ('K_psi_z',)),
+              'z': NT(r(20, K, 18), ('plate_1', 'K_z'))}
+    ip = {k: from_torch_named(v) for k, v in {**inp['inputs'], **inp['params']}.items()}
+    data = {k: from_torch_named(v) for k, v in inp['data'].items()}
+    names = list(inp['params'])
+    comp = Compiled(P, Q, sample, ip, data, grad_names=names)
+    kinds = [type(op).__name__ for prog in comp.plan.programs for op in prog]
+    assert 'FanLseOp' in kinds and 'FanLseBwdOp' in kinds and 'DotOp' in kinds
+    comp_slow = Compiled(P, Q, sample, ip, data, grad_names=names, fast_paths=False)
+    assert 'FanLseOp' not in [type(op).__name__ for prog in comp_slow.plan.programs for op in prog]
+    inputs = comp.canonical_inputs(sample, ip, data)
+    lp, grads, _ = run_fwd_bwd(comp, inputs)
+    ipg = {k: NT(v.t.clone().requires_grad_() if k in names else v.t, v.axes) for k, v in ip.items()}
+    ref = O.elbo(P, Q, sample, ipg, data)
+    rg = t.autograd.grad(ref, [ipg[k].t for k in names])
+    tl = 1e-5 if dtype == t.float32 else 1e-10
+    assert rel_err(lp, ref) < tl
+    for k, rr in zip(names, rg):
+        assert rel_err(grad_as(comp, grads, k, ipg[k].axes), rr) < 30 * tl, k
+    # a VI-style request (gradient w.r.t. the sample) must fall back to the materialised factor
+    comp_vi = Compiled(P, Q, sample, ip, data, grad_names=names + ['z', 'mu_z'])
+    kinds = [type(op).__name__ for prog in comp_vi.plan.programs for op in prog]
+    assert 'FanLseOp' not in kinds and 'NormalFanOp' in kinds
