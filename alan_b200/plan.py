@@ -1193,17 +1193,33 @@ class Planner:
         sharded_region = set()
         if self.shard_plate is not None and len(self.fwd_segments) > 1:
             sharded_region = sharded_ids
+        # Sharded plans: an adjoint that lacks the shard axis holds either a value replicated on every
+        # rank (it only depends on the all-reduced tile) or a per-shard PARTIAL sum.  `partial_adj` =
+        # tensors whose adjoint is partial: consumed, directly or transitively, inside the sharded
+        # region.  User-visible global gradients are all-reduced once, so replicated contributions
+        # into them (and into partial adjoints) are pre-divided by the world size (exact for 2/4/8).
+        partial_adj = set()
+        if self.shard_plate is not None:
+            for op in reversed(all_fwd):
+                if _iterates(op, self.shard_plate) or op.out.id in partial_adj:
+                    for x in self.op_inputs(op):
+                        if self.shard_plate not in x.axes:
+                            partial_adj.add(x.id)
+
+        def contribution_scale(op, target_pt, g):
+            if self.shard_plate is None or self.shard_plate in target_pt.axes:
+                return 1.0
+            if not (g.space == 'output' or target_pt.id in partial_adj):
+                return 1.0
+            is_partial = _iterates(op, self.shard_plate) or op.out.id in partial_adj
+            return 1.0 if is_partial else 1.0 / self.world_size
+
         for op in reversed(all_fwd):
             if op.out.space == 'output':
                 continue
             if op.out.id not in needs or op.out.id not in adj:
                 continue
             out_list = segs[len(self.fwd_segments) - 1 - seg_of[id(op)]]
-            # gradients of replicated (non-sharded) ops written into user-visible gradients are
-            # pre-divided by the world size so that one all-reduce(sum) restores them exactly.
-            rep_scale = 1.0
-            if self.shard_plate is not None and id(op) not in sharded_region:
-                rep_scale = 1.0 / self.world_size
             gout = adj[op.out.id]
             if isinstance(op, ExprOp):
                 dims = op.keep + op.red
@@ -1219,7 +1235,7 @@ class Planner:
                         raise Exception(f"adjoint of {lf.pt}: expression does not cover the tensor")
                     n_loop = _prod(d[2] for d in loop)
                     nsplit = _choose_split(n_kept, n_loop)
-                    scale = op.scale * (rep_scale if g.space == 'output' else 1.0)
+                    scale = op.scale * contribution_scale(op, lf.pt, g)
                     if nsplit > 1:
                         part = self.ws_raw(nsplit * n_kept, name='partial_adj')
                         out_list.append(ExprBwdOp(part, op, li, kept, loop, gout, nsplit=nsplit, acc=0, scale=scale))
@@ -1244,7 +1260,7 @@ class Planner:
                         raise Exception(f"adjoint of {lf.pt}: contraction does not cover the tensor")
                     n_loop = _prod(d[2] for d in loop)
                     nsplit = _choose_split(n_kept, n_loop)
-                    scale = op.scale * coeff * (rep_scale if g.space == 'output' else 1.0)
+                    scale = op.scale * coeff * contribution_scale(op, lf.pt, g)
                     if op.mode == R_SUM:
                         mode, facs, kw = R_SUM, [(_OwnDims(gout, op.od), 1.0)], {}
                     else:
@@ -1272,7 +1288,7 @@ class Planner:
                         n_kept = _prod(d[2] for d in kept)
                         if n_kept != lf.pt.numel:
                             raise Exception(f"adjoint of {lf.pt}: fused contraction does not cover the tensor")
-                        scale = coeff * (rep_scale if g.space == 'output' else 1.0)
+                        scale = coeff * contribution_scale(op, lf.pt, g)
                         nsplit = _choose_split(n_kept, _prod(d[2] for d in loop))
                         facs = [(_OwnDims(gS, rows), 1.0)]
                         if nsplit > 1:
@@ -1390,6 +1406,21 @@ class _OwnDims(_PartialRef):
         object.__setattr__(self, 'mode', 0)
         object.__setattr__(self, 'mdim', None)
         object.__setattr__(self, 'own', list(own_dims))
+
+
+def _iterates(op, plate):
+    """True if the op walks the given plate axis, i.e. it belongs to the sharded region."""
+    if isinstance(op, ExprOp):
+        dims = op.keep + op.red
+    elif isinstance(op, ReduceOp):
+        dims = op.od + op.rd
+    elif isinstance(op, FanLseOp):
+        dims = op.rho + [op.kappa]
+    elif isinstance(op, ChainOp):
+        return plate in op.ms.axes
+    else:
+        dims = []
+    return any(d[0] == 'ax' and d[1] == plate for d in dims)
 
 
 def _union(exprs):
