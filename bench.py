@@ -231,6 +231,12 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
     ms_per_step = total_ms / args.steps
     value = W / (ms_per_step * 1e-3)
 
+    if args.device_only:
+        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "ms_per_step": ms_per_step, "config": {"workload": cfg["name"]},
+                          "gpu_launches": sum(run.dp.launches[:plan.n_fwd + plan.n_bwd]) * args.steps,
+                          "note": "device-only short run (profiling aid), not a bench line"}))
+        sys.exit(0)
     # ---- e2e: host (pinned) buffers -> device -> fwd+bwd -> lp and gradients back to the host
     h2d = sum(x.numel() * x.element_size() for x in host)
     gout_host = None
@@ -361,6 +367,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true",
+                    help="skip the e2e / cfg2 / cpu legs (short command for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -384,6 +392,8 @@ def main():
         return
 
     import torch.distributed as dist
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the single JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=t.device(f"cuda:{local_rank}"))
     line = run_b200(args, cfg, rank, world, local_rank)
