@@ -211,68 +211,96 @@ struct FanLseParams {
 
 #define FANLSE_WARPS 8
 
+// base-2 exponent / logarithm on the SFU for the fp32 instantiation (one MUFU each); the fp64
+// instantiation keeps exp()/log().  Inputs are pre-scaled by log2(e) once per tile, so the inner
+// loop has no multiply in front of the exponential.
+template <typename T> struct FastExp;
+template <> struct FastExp<float> {
+    static __device__ __forceinline__ float scale() { return 1.4426950408889634f; }     // log2(e)
+    static __device__ __forceinline__ float unscale() { return 0.6931471805599453f; }   // ln(2)
+    static __device__ __forceinline__ float ex(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+};
+template <> struct FastExp<double> {
+    static __device__ __forceinline__ double scale() { return 1.0; }
+    static __device__ __forceinline__ double unscale() { return 1.0; }
+    static __device__ __forceinline__ double ex(double x) { return exp(x); }
+};
+
 template <typename T, int D, bool BWD>
 __global__ void __launch_bounds__(FANLSE_WARPS * 32) fan_lse_kernel(const __grid_constant__ FanLseParams<T> p) {
     extern __shared__ __align__(16) unsigned char fan_smem[];
     constexpr int DP = (D + 3) & ~3;
     const int FP = (p.F + 3) & ~3;
-    T* Wt = (T*)fan_smem;                 // [D][FP]
-    T* cc = Wt + D * FP;                  // [FP]
+    const int K4 = (p.Kk + 3) & ~3;         // kappa padded to a multiple of four rows
+    T* Wt = (T*)fan_smem;                   // [D][FP]   w * log2e
+    T* cc = Wt + D * FP;                    // [FP]      c * log2e
     T* warp_base = cc + FP;
     const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_warp = p.Kk * DP + ((p.Kk + 3) & ~3);
-    T* Tt = warp_base + (i64)warp_in_cta * per_warp;    // [Kk][DP]
-    T* Bs = Tt + p.Kk * DP;                             // [Kk]
+    const int per_warp = K4 * DP + K4;
+    T* Tt = warp_base + warp_in_cta * per_warp;         // [K4][DP]  squared residuals
+    T* Bs = Tt + K4 * DP;                               // [K4]      small-factor sum * log2e (-inf on padding)
+    const T LS = FastExp<T>::scale();
 
     for (int i = threadIdx.x; i < D * FP; i += blockDim.x) {
         int d = i / FP, f = i - d * FP;
         T w = T(0);
-        if (f < p.F) { T sc = p.s[f * p.s_f + d * p.s_ev]; w = T(1) / (T(2) * (sc * sc)); }
+        if (f < p.F) { T sc = p.s[f * p.s_f + d * p.s_ev]; w = LS / (T(2) * (sc * sc)); }
         Wt[i] = w;
     }
     for (int f = threadIdx.x; f < FP; f += blockDim.x) {
         T c = T(0);
         if (f < p.F) {
             for (int d = 0; d < D; ++d) c += ab_log(p.s[f * p.s_f + d * p.s_ev]);
-            c += T(D) * T(HALF_LOG_2PI);
+            c = (c + T(D) * T(HALF_LOG_2PI)) * LS;
         }
         cc[f] = c;
     }
+    // padding rows / columns of the per-warp tile never change
+    for (int e = lane; e < K4 * DP; e += 32) Tt[e] = T(0);
+    for (int k = lane; k < K4; k += 32) Bs[k] = neg_inf<T>();
     __syncthreads();
 
-    const i64 warp = (i64)blockIdx.x * FANLSE_WARPS + warp_in_cta;
-    const i64 nwarps = (i64)gridDim.x * FANLSE_WARPS;
-    for (i64 rho = warp; rho < p.n_rho; rho += nwarps) {
+    const unsigned n_rho = (unsigned)p.n_rho;
+    const unsigned warp = blockIdx.x * FANLSE_WARPS + warp_in_cta;
+    const unsigned nwarps = gridDim.x * FANLSE_WARPS;
+    const bool contig = (p.v_ev == 1 && p.v_k == D);    // value rows of one rho are one contiguous run
+    for (unsigned rho = warp; rho < n_rho; rho += nwarps) {
         i64 voff = 0, loff = 0, ooff = 0;
         i64 boff[AB_MAXL];
-        for (int i = 0; i < p.nb; ++i) boff[i] = 0;
+#pragma unroll
+        for (int i = 0; i < AB_MAXL; ++i) boff[i] = 0;
         {
-            i64 lin = rho;
+            unsigned lin = rho;
 #pragma unroll 1
             for (int k = p.rd.nd - 1; k >= 0; --k) {
-                int sz = p.rd.size[k];
-                i64 q = lin / sz;
-                int ix = (int)(lin - q * sz);
+                unsigned sz = (unsigned)p.rd.size[k];
+                unsigned q = lin / sz;
+                unsigned ix = lin - q * sz;
                 lin = q;
                 voff += ix * p.vstride[k]; loff += ix * p.lstride[k]; ooff += ix * p.ostride[k];
-                for (int i = 0; i < p.nb; ++i) boff[i] += ix * p.bstride[i][k];
+#pragma unroll
+                for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) boff[i] += ix * p.bstride[i][k];
             }
         }
-        // squared residual tile of this rho
-        for (int e = lane; e < p.Kk * D; e += 32) {
-            int k = e / D, d = e - k * D;
-            T df = p.v[voff + k * p.v_k + d * p.v_ev] - p.l[loff + k * p.l_k + d * p.l_ev];
-            Tt[k * DP + d] = df * df;
-        }
-        if (DP != D)
-            for (int e = lane; e < p.Kk * (DP - D); e += 32) {
-                int k = e / (DP - D), d = D + (e - k * (DP - D));
-                Tt[k * DP + d] = T(0);
+        // squared residual tile of this rho: T[k][d] = (v - l)^2
+        {
+            const T* vp = p.v + voff;
+            const T* lp = p.l + loff;
+            int k = lane / D, d = lane - k * D;             // (k, d) of element e = lane, stepped by 32
+            constexpr int SK = 32 / D, SD = 32 - SK * D;
+            for (int e = lane; e < p.Kk * D; e += 32) {
+                T vv = contig ? vp[e] : vp[k * p.v_k + d * p.v_ev];
+                T df = vv - lp[k * p.l_k + d * p.l_ev];
+                Tt[k * DP + d] = df * df;
+                k += SK; d += SD;
+                if (d >= D) { d -= D; k += 1; }
             }
+        }
         for (int k = lane; k < p.Kk; k += 32) {
             T b = T(0);
-            for (int i = 0; i < p.nb; ++i) b += p.bcoeff[i] * p.b[i][boff[i] + k * p.b_k[i]];
-            Bs[k] = b;
+#pragma unroll
+            for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) b += p.bcoeff[i] * p.b[i][boff[i] + k * p.b_k[i]];
+            Bs[k] = b * LS;
         }
         __syncwarp();
 
@@ -286,44 +314,67 @@ __global__ void __launch_bounds__(FANLSE_WARPS * 32) fan_lse_kernel(const __grid
             const T cf = active ? cc[f] : T(0);
             if (!BWD) {
                 T m = neg_inf<T>(), sum = T(0);
-                for (int k0 = 0; k0 < p.Kk; k0 += 4) {
+                for (int k0 = 0; k0 < K4; k0 += 4) {
                     T sv[4];
+                    const Vec4<T> b4 = *reinterpret_cast<const Vec4<T>*>(&Bs[k0]);
+                    const T bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int k = k0 + j;
-                        if (k < p.Kk) {
-                            T acc = T(0);
+                        const T* row = Tt + (k0 + j) * DP;
+                        T a0 = T(0), a1 = T(0);
 #pragma unroll
-                            for (int d = 0; d < DP; d += 4) {
-                                const Vec4<T> t4 = *reinterpret_cast<const Vec4<T>*>(&Tt[k * DP + d]);
-                                acc += t4.x * wr[d]; acc += t4.y * wr[d + 1];
-                                acc += t4.z * wr[d + 2]; acc += t4.w * wr[d + 3];
-                            }
-                            sv[j] = Bs[k] - acc - cf;
-                        } else sv[j] = neg_inf<T>();
+                        for (int d = 0; d < DP; d += 4) {
+                            const Vec4<T> t4 = *reinterpret_cast<const Vec4<T>*>(row + d);
+                            a0 += t4.x * wr[d];
+                            if (d + 1 < D) a1 += t4.y * wr[d + 1];
+                            if (d + 2 < D) a0 += t4.z * wr[d + 2];
+                            if (d + 3 < D) a1 += t4.w * wr[d + 3];
+                        }
+                        sv[j] = bb[j] - (a0 + a1) - cf;
                     }
-                    T mx = ab_max(ab_max(sv[0], sv[1]), ab_max(sv[2], sv[3]));
-                    T mn = ab_max(m, mx);
-                    sum = sum * ab_exp(m - mn);
+                    T mn = ab_max(ab_max(ab_max(sv[0], sv[1]), ab_max(sv[2], sv[3])), m);
+                    sum = sum * FastExp<T>::ex(m - mn);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) sum += ab_exp(sv[j] - mn);
+                    for (int j = 0; j < 4; ++j) sum += FastExp<T>::ex(sv[j] - mn);
                     m = mn;
                 }
-                if (active) p.out[ooff + (i64)f * p.o_f] = ab_log(sum + Eps<T>::v()) + m + p.cadd;
+                if (active)
+                    p.out[ooff + (i64)f * p.o_f] = ab_log(sum + Eps<T>::v()) + m * FastExp<T>::unscale() + p.cadd;
             } else {
-                const T lz = active ? p.lse[ooff + (i64)f * p.o_f] : T(0);
+                const T lz = active ? (p.lse[ooff + (i64)f * p.o_f] - p.cadd) * LS : -neg_inf<T>();   // idle lanes: weight 0
                 const T gz = active ? p.gout[ooff + (i64)f * p.o_f] : T(0);
-                for (int k = 0; k < p.Kk; ++k) {
-                    T acc = T(0);
+                for (int kb = 0; kb < K4; kb += 32) {
+                    T wv[32];
 #pragma unroll
-                    for (int d = 0; d < DP; d += 4) {
-                        const Vec4<T> t4 = *reinterpret_cast<const Vec4<T>*>(&Tt[k * DP + d]);
-                        acc += t4.x * wr[d]; acc += t4.y * wr[d + 1];
-                        acc += t4.z * wr[d + 2]; acc += t4.w * wr[d + 3];
+                    for (int j = 0; j < 32; ++j) {
+                        wv[j] = T(0);
+                        if (kb + j < K4) {                                  // warp-uniform
+                            const T* row = Tt + (kb + j) * DP;
+                            T a0 = T(0), a1 = T(0);
+#pragma unroll
+                            for (int d = 0; d < DP; d += 4) {
+                                const Vec4<T> t4 = *reinterpret_cast<const Vec4<T>*>(row + d);
+                                a0 += t4.x * wr[d];
+                                if (d + 1 < D) a1 += t4.y * wr[d + 1];
+                                if (d + 2 < D) a0 += t4.z * wr[d + 2];
+                                if (d + 3 < D) a1 += t4.w * wr[d + 3];
+                            }
+                            wv[j] = gz * FastExp<T>::ex(Bs[kb + j] - (a0 + a1) - cf - lz);   // 0 on padding rows
+                        }
                     }
-                    T wv = active ? gz * ab_exp(Bs[k] - acc - cf + p.cadd - lz) : T(0);
-                    T tot = warp_sum(wv);
-                    if ((k & 31) == lane) keep[(k >> 5) & 3] += tot;
+                    // fixed-order butterfly reduce-scatter over the lanes (f): lane j ends with the sum for
+                    // kappa = kb + j in wv[0]; 31 shuffles for 32 kappas instead of 5 per kappa.
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const bool up = (lane & off) != 0;
+                            T send = up ? wv[i] : wv[i + off];
+                            T mine = up ? wv[i + off] : wv[i];
+                            wv[i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    keep[(kb >> 5) & 3] += wv[0];
                 }
             }
         }
@@ -331,7 +382,7 @@ __global__ void __launch_bounds__(FANLSE_WARPS * 32) fan_lse_kernel(const __grid
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 int k = lane + 32 * q;
-                if (k < p.Kk) p.gS[rho * p.Kk + k] = keep[q];
+                if (k < p.Kk) p.gS[(i64)rho * p.Kk + k] = keep[q];
             }
         }
         __syncwarp();
@@ -343,7 +394,8 @@ static int launch_fan_lse_D(const FanLseParams<T>& p, bool bwd, cudaStream_t str
     constexpr int DP = (D + 3) & ~3;
     const int FP = (p.F + 3) & ~3;
     if (bwd && p.Kk > 128) return 2;
-    size_t smem = (size_t)(D * FP + FP + FANLSE_WARPS * (p.Kk * DP + ((p.Kk + 3) & ~3))) * sizeof(T);
+    const int K4 = (p.Kk + 3) & ~3;
+    size_t smem = (size_t)(D * FP + FP + FANLSE_WARPS * (K4 * DP + K4)) * sizeof(T);
     if (smem > 200 * 1024) return 2;
     i64 blocks = (p.n_rho + FANLSE_WARPS - 1) / FANLSE_WARPS;
     i64 cap = (i64)sm_count * 6;
