@@ -303,7 +303,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 }
                 p.cadd = (T)r.f64();
                 int rc = launch_fan_lse<T>(p, D, bwd != 0, c.stream, c.sm_count);
-                if (rc) return fail(rc == 1 ? "fan_lse: unsupported event extent" : "fan_lse: tile does not fit shared memory");
+                if (rc) return fail(rc == 1 ? "fan_lse: unsupported event extent" : rc == 2 ? "fan_lse: tile does not fit shared memory" : "fan_lse: strides exceed 32-bit tile addressing");
                 break;
             }
             case OP_DOT: {

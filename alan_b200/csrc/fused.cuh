@@ -209,206 +209,361 @@ struct FanLseParams {
     i64 n_rho;
 };
 
-#define FANLSE_WARPS 8
-
-// base-2 exponent / logarithm on the SFU for the fp32 instantiation (one MUFU each); the fp64
-// instantiation keeps exp()/log().  Inputs are pre-scaled by log2(e) once per tile, so the inner
-// loop has no multiply in front of the exponential.
+// base-2 exponent on the SFU for the fp32 instantiation (one MUFU each); the fp64 instantiation keeps
+// exp().  Inputs are pre-scaled by log2(e) once per tile, so the inner loop has no multiply in
+// front of the exponential.
 template <typename T> struct FastExp;
 template <> struct FastExp<float> {
     static __device__ __forceinline__ float scale() { return 1.4426950408889634f; }     // log2(e)
     static __device__ __forceinline__ float unscale() { return 0.6931471805599453f; }   // ln(2)
     static __device__ __forceinline__ float ex(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    static __device__ __forceinline__ float lowest() { return -3.0e38f; }
 };
 template <> struct FastExp<double> {
     static __device__ __forceinline__ double scale() { return 1.0; }
     static __device__ __forceinline__ double unscale() { return 1.0; }
     static __device__ __forceinline__ double ex(double x) { return exp(x); }
+    static __device__ __forceinline__ double lowest() { return -1.0e300; }
 };
 
-template <typename T, int D, bool BWD>
-__global__ void __launch_bounds__(FANLSE_WARPS * 32) fan_lse_kernel(const __grid_constant__ FanLseParams<T> p) {
-    extern __shared__ __align__(16) unsigned char fan_smem[];
-    constexpr int DP = (D + 3) & ~3;
-    const int FP = (p.F + 3) & ~3;
-    const int K4 = (p.Kk + 3) & ~3;         // kappa padded to a multiple of four rows
-    T* Wt = (T*)fan_smem;                   // [D][FP]   w * log2e
-    T* cc = Wt + D * FP;                    // [FP]      c * log2e
-    T* warp_base = cc + FP;
-    const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_warp = K4 * DP + K4;
-    T* Tt = warp_base + warp_in_cta * per_warp;         // [K4][DP]  squared residuals
-    T* Bs = Tt + K4 * DP;                               // [K4]      small-factor sum * log2e (-inf on padding)
-    const T LS = FastExp<T>::scale();
+// Packed pairs: fp32 pairs go through FFMA2 (fma.rn.f32x2, sm_100): one issue slot per two FMAs,
+// which leaves issue bandwidth for the LDS / MUFU traffic of the same warp.
+template <typename T> struct Pair2;
+template <> struct Pair2<float>  { typedef float2 type; };
+template <> struct Pair2<double> { typedef double2 type; };
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ double2 fma2(double2 a, double2 b, double2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
 
-    for (int i = threadIdx.x; i < D * FP; i += blockDim.x) {
-        int d = i / FP, f = i - d * FP;
-        T w = T(0);
-        if (f < p.F) { T sc = p.s[f * p.s_f + d * p.s_ev]; w = LS / (T(2) * (sc * sc)); }
-        Wt[i] = w;
+// one tile row -> NPU register pairs with 16-byte shared-memory loads (rows are 16-byte aligned)
+template <int NPU>
+__device__ __forceinline__ void load_row_pairs(const float* row, float2* t2) {
+#pragma unroll
+    for (int q4 = 0; q4 < (NPU + 1) / 2; ++q4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(row + 4 * q4);
+        t2[2 * q4] = make_float2(t4.x, t4.y);
+        if (2 * q4 + 1 < NPU) t2[2 * q4 + 1] = make_float2(t4.z, t4.w);
     }
-    for (int f = threadIdx.x; f < FP; f += blockDim.x) {
-        T c = T(0);
-        if (f < p.F) {
-            for (int d = 0; d < D; ++d) c += ab_log(p.s[f * p.s_f + d * p.s_ev]);
-            c = (c + T(D) * T(HALF_LOG_2PI)) * LS;
-        }
-        cc[f] = c;
+}
+template <int NPU>
+__device__ __forceinline__ void load_row_pairs(const double* row, double2* t2) {
+#pragma unroll
+    for (int q = 0; q < NPU; ++q) t2[q] = *reinterpret_cast<const double2*>(row + 2 * q);
+}
+
+#define FL2_WARPS 4
+// fan columns (f) owned by one lane: the lane keeps w[f, 0..D) for FPL columns in registers
+// (FPL * D values), so every squared residual read from shared memory feeds FPL FMAs.  Measured on
+// B200 (tools/microbench.cu): broadcast LDS.128 delivers ~59 floats/clk/SM against 128 FMA/clk/SM,
+// so FPL >= 3 is needed to be FMA- rather than LDS-bound; 6 leaves headroom.
+template <typename T, int D> struct FanTile {
+    // row layout: [0, D) squared residuals, [D] the row's small-factor sum (bias), [D+1] the constant 1;
+    // the matching w "columns" hold 1 and -c[f], so the whole S = b - c - sum_d T w comes out of the
+    // FFMA2 chain with a zero initial accumulator.
+    static constexpr int DP = (D + 2 + 3) & ~3;             // shared-memory row pitch (16-byte rows)
+    static constexpr int NPU = (D + 2 + 1) / 2;             // register pairs per row actually used
+    static constexpr int W32 = NPU * 2 * (int)(sizeof(T) / 4);
+    static constexpr int FPL_ = 120 / W32;
+    static constexpr int FPL = FPL_ >= 6 ? 6 : (FPL_ >= 4 ? 4 : (FPL_ >= 3 ? 3 : (FPL_ >= 2 ? 2 : 1)));
+};
+
+struct FanLse2Cfg {
+    int FG;          // lanes per rho (each owns FPL fan columns)
+    int RPW;         // rho processed concurrently by one warp (RPW * FG <= 32)
+    int KP;          // kappa padded to a multiple of RB
+    int FC;          // fan columns per chunk = FG * FPL
+    int n_chunks;
+    int vec2;        // value / loc rows are 2-element aligned and contiguous: 64-bit loads
+    int tile_pitch;  // elements between the tiles of one warp (== 4 mod 32: distinct banks per tile)
+    int warp_elems;  // shared-memory elements (T) per warp
+    int off_words;   // i64 words per warp for the per-rho offsets
+};
+
+// One warp owns RPW rho at a time.  It builds their tiles T[kappa][d] = (v - l)^2 (plus the bias and
+// constant slots) in its shared-memory slice with coalesced 64-bit reads of v, then lane (rs, fg) walks
+// the kappa rows of rho rs for its FPL fan columns: each row is DP/4 LDS.128 feeding FPL * NPU FFMA2,
+// and the LSE over kappa is a blocked online max/rescale in registers (RB rows per block) -- no
+// cross-lane traffic at all in the forward pass.  The adjoint recomputes S the same way and reduces
+// the softmax weights over the fan axis through a per-warp shared-memory transpose in a fixed order.
+template <typename T, int D, int RB, bool BWD>
+__global__ void __launch_bounds__(FL2_WARPS * 32, 2) fan_lse2_kernel(const __grid_constant__ FanLseParams<T> p,
+                                                                    const __grid_constant__ FanLse2Cfg cfg) {
+    typedef FanTile<T, D> FT;
+    typedef typename Pair2<T>::type P2;
+    constexpr int DP = FT::DP, NPU = FT::NPU, FPL = FT::FPL;
+    extern __shared__ __align__(16) unsigned char fan_smem[];
+    const int FG = cfg.FG, RPW = cfg.RPW, KP = cfg.KP, FC = cfg.FC, TP = cfg.tile_pitch;
+    const int KPo = KP | 1;
+    T* Wt = (T*)fan_smem;                       // [FC][DP]  -w * log2e of the current fan chunk, then (1, -c * log2e)
+    const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T* Tt = Wt + FC * DP + (size_t)warp_in_cta * cfg.warp_elems;     // [RPW] tiles of [KP][DP], pitch TP
+    T* Pp = Tt + RPW * TP;                      // bwd: [32][KPo] per-lane partial weights
+    i64* offs = (i64*)(fan_smem + (((size_t)(FC * DP + FL2_WARPS * cfg.warp_elems) * sizeof(T) + 15) & ~(size_t)15))
+                + (size_t)warp_in_cta * cfg.off_words;          // [RPW][3 + nb]
+    const int NO = 3 + p.nb;
+    const T LS = FastExp<T>::scale();
+    const int rs = lane / FG, fg = lane - rs * FG;
+    const bool lane_on = rs < RPW;
+    const int Kk = p.Kk;
+
+    // padding rows / columns of the per-warp tiles never change: T = 0, bias = -inf, constant slot = 1
+    for (int e = lane; e < RPW * TP; e += 32) Tt[e] = T(0);
+    __syncwarp();
+    for (int e = lane; e < RPW * KP; e += 32) {
+        int t = e / KP, k = e - t * KP;
+        Tt[t * TP + k * DP + D] = neg_inf<T>();
+        Tt[t * TP + k * DP + D + 1] = T(1);
     }
-    // padding rows / columns of the per-warp tile never change
-    for (int e = lane; e < K4 * DP; e += 32) Tt[e] = T(0);
-    for (int k = lane; k < K4; k += 32) Bs[k] = neg_inf<T>();
-    __syncthreads();
+    __syncwarp();
 
     const unsigned n_rho = (unsigned)p.n_rho;
-    const unsigned warp = blockIdx.x * FANLSE_WARPS + warp_in_cta;
-    const unsigned nwarps = gridDim.x * FANLSE_WARPS;
-    const bool contig = (p.v_ev == 1 && p.v_k == D);    // value rows of one rho are one contiguous run
-    for (unsigned rho = warp; rho < n_rho; rho += nwarps) {
-        i64 voff = 0, loff = 0, ooff = 0;
-        i64 boff[AB_MAXL];
-#pragma unroll
-        for (int i = 0; i < AB_MAXL; ++i) boff[i] = 0;
-        {
-            unsigned lin = rho;
-#pragma unroll 1
-            for (int k = p.rd.nd - 1; k >= 0; --k) {
-                unsigned sz = (unsigned)p.rd.size[k];
-                unsigned q = lin / sz;
-                unsigned ix = lin - q * sz;
-                lin = q;
-                voff += ix * p.vstride[k]; loff += ix * p.lstride[k]; ooff += ix * p.ostride[k];
-#pragma unroll
-                for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) boff[i] += ix * p.bstride[i][k];
-            }
-        }
-        // squared residual tile of this rho: T[k][d] = (v - l)^2
-        {
-            const T* vp = p.v + voff;
-            const T* lp = p.l + loff;
-            int k = lane / D, d = lane - k * D;             // (k, d) of element e = lane, stepped by 32
-            constexpr int SK = 32 / D, SD = 32 - SK * D;
-            for (int e = lane; e < p.Kk * D; e += 32) {
-                T vv = contig ? vp[e] : vp[k * p.v_k + d * p.v_ev];
-                T df = vv - lp[k * p.l_k + d * p.l_ev];
-                Tt[k * DP + d] = df * df;
-                k += SK; d += SD;
-                if (d >= D) { d -= D; k += 1; }
-            }
-        }
-        for (int k = lane; k < p.Kk; k += 32) {
-            T b = T(0);
-#pragma unroll
-            for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) b += p.bcoeff[i] * p.b[i][boff[i] + k * p.b_k[i]];
-            Bs[k] = b * LS;
-        }
-        __syncwarp();
+    const unsigned n_groups = (n_rho + RPW - 1) / RPW;
+    const unsigned warp = blockIdx.x * FL2_WARPS + warp_in_cta;
+    const unsigned nwarps = gridDim.x * FL2_WARPS;
+    // 32-bit strides of the tile walk (the host checks that they fit)
+    const int vk = (int)p.v_k, lk = (int)p.l_k, vev = (int)p.v_ev, lev = (int)p.l_ev;
 
-        T keep[4] = {T(0), T(0), T(0), T(0)};       // bwd: gS for kappa = lane + 32 q
-        for (int f0 = 0; f0 < p.F; f0 += 32) {
-            const int f = f0 + lane;
-            const bool active = f < p.F;
-            T wr[DP];
+    for (int chunk = 0; chunk < cfg.n_chunks; ++chunk) {
+        const int f_base = chunk * FC;
+        __syncthreads();
+        for (int i = threadIdx.x; i < FC * DP; i += blockDim.x) {
+            int fl = i / DP, d = i - fl * DP, f = f_base + fl;
+            T w = T(0);
+            if (f < p.F) {
+                if (d < D) { T sc = p.s[f * p.s_f + d * p.s_ev]; w = -LS / (T(2) * (sc * sc)); }
+                else if (d == D) w = T(1);
+                else if (d == D + 1) {
+                    T c = T(0);
+                    for (int dd = 0; dd < D; ++dd) c += ab_log(p.s[f * p.s_f + dd * p.s_ev]);
+                    w = -(c + T(D) * T(HALF_LOG_2PI)) * LS;
+                }
+            }
+            Wt[i] = w;
+        }
+        __syncthreads();
+        // this lane's fan columns stay in registers for the whole chunk
+        P2 W2[FPL][NPU];
 #pragma unroll
-            for (int d = 0; d < DP; ++d) wr[d] = (active && d < D) ? Wt[d * FP + f] : T(0);
-            const T cf = active ? cc[f] : T(0);
+        for (int j = 0; j < FPL; ++j) {
+            const T* wrow = Wt + (lane_on ? fg * FPL + j : 0) * DP;
+#pragma unroll
+            for (int q = 0; q < NPU; ++q) W2[j][q] = mk2(wrow[2 * q], wrow[2 * q + 1]);
+        }
+
+        for (unsigned g = warp; g < n_groups; g += nwarps) {
+            const unsigned rho0 = g * RPW;
+            // per-rho offsets: lane t decodes rho0 + t
+            if (lane < RPW) {
+                i64 voff = 0, loff = 0, ooff = 0;
+                i64 boff[AB_MAXL];
+#pragma unroll
+                for (int i = 0; i < AB_MAXL; ++i) boff[i] = 0;
+                unsigned lin = rho0 + lane < n_rho ? rho0 + lane : n_rho - 1;
+#pragma unroll 1
+                for (int k = p.rd.nd - 1; k >= 0; --k) {
+                    unsigned sz = (unsigned)p.rd.size[k];
+                    unsigned q = lin / sz;
+                    unsigned ix = lin - q * sz;
+                    lin = q;
+                    voff += ix * p.vstride[k]; loff += ix * p.lstride[k]; ooff += ix * p.ostride[k];
+#pragma unroll
+                    for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) boff[i] += ix * p.bstride[i][k];
+                }
+                i64* o = offs + lane * NO;
+                o[0] = voff; o[1] = loff; o[2] = ooff;
+#pragma unroll
+                for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) o[3 + i] = boff[i];
+            }
+            __syncwarp();
+            // squared residual tiles: T[t][k][d] = (v - l)^2; (k, d) advance incrementally, 32-bit
+            for (int t = 0; t < RPW; ++t) {
+                const T* vp = p.v + offs[t * NO];
+                const T* lp = p.l + offs[t * NO + 1];
+                T* tile = Tt + t * TP;
+                if (cfg.vec2) {
+                    constexpr int DV = D / 2 > 0 ? D / 2 : 1;
+                    constexpr int SK = 32 / DV, SD = 32 % DV;
+                    int k = lane / DV, dv = lane - k * DV;
+                    int vo = k * vk + 2 * dv, lo = k * lk + 2 * dv, to = k * DP + 2 * dv;
+                    const int n_pairs = Kk * DV;
+                    for (int e = lane; e < n_pairs; e += 32) {
+                        const P2 vv = *reinterpret_cast<const P2*>(vp + vo);
+                        const P2 ll = *reinterpret_cast<const P2*>(lp + lo);
+                        const T d0 = vv.x - ll.x, d1 = vv.y - ll.y;
+                        *reinterpret_cast<P2*>(tile + to) = mk2(d0 * d0, d1 * d1);
+                        dv += SD; vo += SK * vk + 2 * SD; lo += SK * lk + 2 * SD; to += SK * DP + 2 * SD;
+                        if (dv >= DV) { dv -= DV; vo += vk - 2 * DV; lo += lk - 2 * DV; to += DP - 2 * DV; }
+                    }
+                } else {
+                    constexpr int SK = 32 / D, SD = 32 % D;
+                    int k = lane / D, d = lane - k * D;
+                    int vo = k * vk + d * vev, lo = k * lk + d * lev, to = k * DP + d;
+                    const int n_el = Kk * D;
+                    for (int e = lane; e < n_el; e += 32) {
+                        const T df = vp[vo] - lp[lo];
+                        tile[to] = df * df;
+                        d += SD; vo += SK * vk + SD * vev; lo += SK * lk + SD * lev; to += SK * DP + SD;
+                        if (d >= D) { d -= D; vo += vk - D * vev; lo += lk - D * lev; to += DP - D; }
+                    }
+                }
+            }
+            // bias slot: sum of the small factors of (rho, kappa), pre-scaled by log2e
+            for (int t = 0; t < RPW; ++t) {
+                for (int k = lane; k < Kk; k += 32) {
+                    T b = T(0);
+#pragma unroll
+                    for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) b += p.bcoeff[i] * p.b[i][offs[t * NO + 3 + i] + k * p.b_k[i]];
+                    Tt[t * TP + k * DP + D] = b * LS;
+                }
+            }
+            __syncwarp();
+
+            const bool live = lane_on && rho0 + rs < n_rho;
+            const int rsc = lane_on ? rs : 0;
+            const T* tile = Tt + rsc * TP;
+            const i64 ooff = offs[rsc * NO + 2];
             if (!BWD) {
-                T m = neg_inf<T>(), sum = T(0);
-                for (int k0 = 0; k0 < K4; k0 += 4) {
-                    T sv[4];
-                    const Vec4<T> b4 = *reinterpret_cast<const Vec4<T>*>(&Bs[k0]);
-                    const T bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                T m[FPL], sum[FPL];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const T* row = Tt + (k0 + j) * DP;
-                        T a0 = T(0), a1 = T(0);
+                for (int j = 0; j < FPL; ++j) { m[j] = FastExp<T>::lowest(); sum[j] = T(0); }
+#pragma unroll 1
+                for (int k0 = 0; k0 < KP; k0 += RB) {
+                    T s[RB][FPL];
 #pragma unroll
-                        for (int d = 0; d < DP; d += 4) {
-                            const Vec4<T> t4 = *reinterpret_cast<const Vec4<T>*>(row + d);
-                            a0 += t4.x * wr[d];
-                            if (d + 1 < D) a1 += t4.y * wr[d + 1];
-                            if (d + 2 < D) a0 += t4.z * wr[d + 2];
-                            if (d + 3 < D) a1 += t4.w * wr[d + 3];
+                    for (int r = 0; r < RB; ++r) {
+                        P2 t2[NPU];
+                        load_row_pairs<NPU>(tile + (k0 + r) * DP, t2);
+#pragma unroll
+                        for (int j = 0; j < FPL; ++j) {
+                            P2 acc = mk2(T(0), T(0));
+#pragma unroll
+                            for (int q = 0; q < NPU; ++q) acc = fma2(t2[q], W2[j][q], acc);
+                            s[r][j] = acc.x + acc.y;
                         }
-                        sv[j] = bb[j] - (a0 + a1) - cf;
                     }
-                    T mn = ab_max(ab_max(ab_max(sv[0], sv[1]), ab_max(sv[2], sv[3])), m);
-                    sum = sum * FastExp<T>::ex(m - mn);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) sum += FastExp<T>::ex(sv[j] - mn);
-                    m = mn;
+                    for (int j = 0; j < FPL; ++j) {
+                        T mn = m[j];
+#pragma unroll
+                        for (int r = 0; r < RB; ++r) mn = ab_max(mn, s[r][j]);
+                        T a = sum[j] * FastExp<T>::ex(m[j] - mn);
+#pragma unroll
+                        for (int r = 0; r < RB; ++r) a += FastExp<T>::ex(s[r][j] - mn);
+                        sum[j] = a; m[j] = mn;
+                    }
                 }
-                if (active)
-                    p.out[ooff + (i64)f * p.o_f] = ab_log(sum + Eps<T>::v()) + m * FastExp<T>::unscale() + p.cadd;
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < FPL; ++j) {
+                        const int f = f_base + fg * FPL + j;
+                        if (f < p.F) p.out[ooff + (i64)f * p.o_f] = ab_log(sum[j] + Eps<T>::v()) + m[j] * FastExp<T>::unscale() + p.cadd;
+                    }
+                }
             } else {
-                const T lz = active ? (p.lse[ooff + (i64)f * p.o_f] - p.cadd) * LS : -neg_inf<T>();   // idle lanes: weight 0
-                const T gz = active ? p.gout[ooff + (i64)f * p.o_f] : T(0);
-                for (int kb = 0; kb < K4; kb += 32) {
-                    T wv[32];
+                // fold -lse into the constant column: exponent = S - lse comes straight out of the chain
+                T gz[FPL];
+                P2 wl[FPL];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        wv[j] = T(0);
-                        if (kb + j < K4) {                                  // warp-uniform
-                            const T* row = Tt + (kb + j) * DP;
-                            T a0 = T(0), a1 = T(0);
+                for (int j = 0; j < FPL; ++j) {
+                    const int f = f_base + fg * FPL + j;
+                    const bool on = live && f < p.F;
+                    const T lz = on ? (p.lse[ooff + (i64)f * p.o_f] - p.cadd) * LS : -neg_inf<T>();   // idle columns: weight 0
+                    gz[j] = on ? p.gout[ooff + (i64)f * p.o_f] : T(0);
+                    wl[j] = W2[j][NPU - 1];
+                    if (((D + 1) & 1) == 0) wl[j].x -= lz; else wl[j].y -= lz;           // slot D + 1 holds -c
+                }
+                T* mine = Pp + lane * KPo;
+#pragma unroll 1
+                for (int k0 = 0; k0 < KP; k0 += RB) {
 #pragma unroll
-                            for (int d = 0; d < DP; d += 4) {
-                                const Vec4<T> t4 = *reinterpret_cast<const Vec4<T>*>(row + d);
-                                a0 += t4.x * wr[d];
-                                if (d + 1 < D) a1 += t4.y * wr[d + 1];
-                                if (d + 2 < D) a0 += t4.z * wr[d + 2];
-                                if (d + 3 < D) a1 += t4.w * wr[d + 3];
-                            }
-                            wv[j] = gz * FastExp<T>::ex(Bs[kb + j] - (a0 + a1) - cf - lz);   // 0 on padding rows
+                    for (int r = 0; r < RB; ++r) {
+                        P2 t2[NPU];
+                        load_row_pairs<NPU>(tile + (k0 + r) * DP, t2);
+                        T w = T(0);
+#pragma unroll
+                        for (int j = 0; j < FPL; ++j) {
+                            P2 acc = mk2(T(0), T(0));
+#pragma unroll
+                            for (int q = 0; q < NPU - 1; ++q) acc = fma2(t2[q], W2[j][q], acc);
+                            acc = fma2(t2[NPU - 1], wl[j], acc);
+                            w += gz[j] * FastExp<T>::ex(acc.x + acc.y);          // 0 on padding rows (bias = -inf)
+                        }
+                        mine[k0 + r] = w;
+                    }
+                }
+                __syncwarp();
+                // fixed-order sum over the FG lanes of each rho; one (rho, kappa) per thread, coalesced store
+                for (int t = 0; t < RPW; ++t) {
+                    if (rho0 + t < n_rho) {
+                        for (int k = lane; k < Kk; k += 32) {
+                            T a = T(0);
+                            for (int q = 0; q < FG; ++q) a += Pp[(t * FG + q) * KPo + k];
+                            const i64 gi = (i64)(rho0 + t) * Kk + k;
+                            if (chunk > 0) a += p.gS[gi];
+                            p.gS[gi] = a;
                         }
                     }
-                    // fixed-order butterfly reduce-scatter over the lanes (f): lane j ends with the sum for
-                    // kappa = kb + j in wv[0]; 31 shuffles for 32 kappas instead of 5 per kappa.
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const bool up = (lane & off) != 0;
-                            T send = up ? wv[i] : wv[i + off];
-                            T mine = up ? wv[i + off] : wv[i];
-                            wv[i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
-                        }
-                    }
-                    keep[(kb >> 5) & 3] += wv[0];
                 }
             }
+            __syncwarp();
         }
-        if (BWD) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                int k = lane + 32 * q;
-                if (k < p.Kk) p.gS[(i64)rho * p.Kk + k] = keep[q];
-            }
-        }
-        __syncwarp();
     }
+}
+
+template <typename T, int D, int RB>
+static int launch_fan_lse_DR(const FanLseParams<T>& p, bool bwd, cudaStream_t stream, int sm_count) {
+    typedef FanTile<T, D> FT;
+    FanLse2Cfg c;
+    const int fgn = (p.F + FT::FPL - 1) / FT::FPL;
+    c.FG = fgn < 32 ? fgn : 32;
+    c.FC = c.FG * FT::FPL;
+    c.n_chunks = (p.F + c.FC - 1) / c.FC;
+    c.KP = (p.Kk + RB - 1) / RB * RB;
+    c.tile_pitch = c.KP * FT::DP;
+    while (c.tile_pitch % 32 != 4) c.tile_pitch += 4;
+    const int KPo = c.KP | 1;
+    const size_t tile_bytes = (size_t)c.tile_pitch * sizeof(T);
+    int rpw = 32 / c.FG;
+    const size_t budget = 18 * 1024;                     // per-warp tile budget: 4 warps x 2 CTAs per SM
+    while (rpw > 1 && rpw * tile_bytes > budget) --rpw;
+    if (tile_bytes > 44 * 1024) return 2;
+    c.RPW = rpw;
+    const i64 lim = (i64)1 << 30;
+    if (p.v_k >= lim || p.l_k >= lim || p.v_ev >= lim || p.l_ev >= lim || (i64)p.Kk * (p.v_k > p.l_k ? p.v_k : p.l_k) >= lim) return 3;
+    bool ev2 = (D % 2 == 0) && p.v_ev == 1 && p.l_ev == 1 && p.v_k % 2 == 0 && p.l_k % 2 == 0 &&
+               ((uintptr_t)p.v % (2 * sizeof(T)) == 0) && ((uintptr_t)p.l % (2 * sizeof(T)) == 0);
+    for (int k = 0; k < p.rd.nd && ev2; ++k) ev2 = (p.vstride[k] % 2 == 0) && (p.lstride[k] % 2 == 0);
+    c.vec2 = ev2 ? 1 : 0;
+    c.warp_elems = c.RPW * c.tile_pitch + (bwd ? ((32 * KPo + 3) & ~3) : 0);
+    c.off_words = c.RPW * (3 + p.nb);
+    size_t smem = (((size_t)(c.FC * FT::DP + FL2_WARPS * c.warp_elems) * sizeof(T) + 15) & ~(size_t)15)
+                  + (size_t)FL2_WARPS * c.off_words * sizeof(i64);
+    if (smem > 200 * 1024) return 2;
+    const i64 n_groups = (p.n_rho + c.RPW - 1) / c.RPW;
+    i64 blocks = (n_groups + FL2_WARPS - 1) / FL2_WARPS;
+    int per_sm = (int)(220 * 1024 / (smem + 1024));
+    if (per_sm > 2) per_sm = 2;
+    if (per_sm < 1) per_sm = 1;
+    i64 cap = (i64)sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (bwd) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(fan_lse2_kernel<T, D, RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fan_lse2_kernel<T, D, RB, true><<<(int)blocks, FL2_WARPS * 32, smem, stream>>>(p, c);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(fan_lse2_kernel<T, D, RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fan_lse2_kernel<T, D, RB, false><<<(int)blocks, FL2_WARPS * 32, smem, stream>>>(p, c);
+    }
+    return 0;
 }
 
 template <typename T, int D>
 static int launch_fan_lse_D(const FanLseParams<T>& p, bool bwd, cudaStream_t stream, int sm_count) {
-    constexpr int DP = (D + 3) & ~3;
-    const int FP = (p.F + 3) & ~3;
-    if (bwd && p.Kk > 128) return 2;
-    const int K4 = (p.Kk + 3) & ~3;
-    size_t smem = (size_t)(D * FP + FP + FANLSE_WARPS * (K4 * DP + K4)) * sizeof(T);
-    if (smem > 200 * 1024) return 2;
-    i64 blocks = (p.n_rho + FANLSE_WARPS - 1) / FANLSE_WARPS;
-    i64 cap = (i64)sm_count * 6;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    if (bwd) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(fan_lse_kernel<T, D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        fan_lse_kernel<T, D, true><<<(int)blocks, FANLSE_WARPS * 32, smem, stream>>>(p);
-    } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(fan_lse_kernel<T, D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        fan_lse_kernel<T, D, false><<<(int)blocks, FANLSE_WARPS * 32, smem, stream>>>(p);
-    }
-    return 0;
+    // rows per online-LSE block: 5 when that pads kappa less than 4 does (K = 30 -> no padding)
+    const int pad4 = (p.Kk + 3) / 4 * 4, pad5 = (p.Kk + 4) / 5 * 5;
+    if (pad5 < pad4) return launch_fan_lse_DR<T, D, 5>(p, bwd, stream, sm_count);
+    return launch_fan_lse_DR<T, D, 4>(p, bwd, stream, sm_count);
 }
 
 template <typename T>

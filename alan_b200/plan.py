@@ -1069,8 +1069,11 @@ class Planner:
         if fan.v.stride(self.axdim(kappa)) == 0 and fan.l.stride(self.axdim(kappa)) == 0:
             return None
         rho = [d for d in fan.rows if d[1] != kappa]
-        tile = self.sizes[kappa] * ((fan.D + 3) // 4 * 4 + 1) * 8 * self.itemsize
-        if tile > 150 * 1024:
+        # shared-memory footprint of csrc/fused.cuh fan_lse2_kernel with one rho per warp (its minimum)
+        DP, KP = (fan.D + 5) // 4 * 4, self.sizes[kappa] + 4
+        tile = KP * DP + 32
+        smem = (4 * (tile + 32 * (KP + 1)) + 32 * 6 * DP) * self.itemsize + 4 * 13 * 8
+        if smem > 190 * 1024 or tile * self.itemsize > 44 * 1024:
             return None
         self.fwd.remove(fan)
         return FanLseOp(red.out, fan.D, rho, self.axdim(kappa), fan.v, fan.l, fan.s, fan.fan_axis, fan.F,

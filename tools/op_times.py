@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Per-op device times of one workload (CUDA events around every op via alan_b200_profile).
+Profiling aid: prints a table, never a bench line.   python tools/op_times.py [cfg5|cfg2] [reps]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch as t
+import bench
+from alan_b200.engine import Compiled, Runner
+
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg5"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+cfg = bench.WORKLOADS[name]
+P, Q, sample, ip, data, params = bench.make_problem(cfg, 0, cfg["M"])
+comp = Compiled(P, Q, sample, ip, data, grad_names=params)
+run = Runner(comp, "cuda:0")
+plan = comp.plan
+tensors = [x.cuda() for x in comp.canonical_inputs(sample, ip, data)]
+flush = t.empty(64 * 1024 * 1024, dtype=t.float32, device="cuda")
+lp_d = t.empty((), dtype=comp.dtype, device="cuda")
+one = t.ones((), dtype=comp.dtype, device="cuda")
+gouts = [t.empty(plan.input_pts[n].shape, dtype=comp.dtype, device="cuda") for n in plan.grad_inputs]
+acc = {}
+for rep in range(reps + 1):
+    flush.fill_(1.0)
+    for prog in range(plan.n_fwd + plan.n_bwd):
+        outs, aux = ([lp_d], []) if prog < plan.n_fwd else (gouts, [one])
+        ms = run.dp.profile(prog, tensors, outs, aux)
+        if rep:
+            for j, m in enumerate(ms):
+                acc[(prog, j)] = acc.get((prog, j), 0.0) + m / reps
+tot = sum(acc.values())
+print(f"{name}: sum of per-op times {tot:.3f} ms over {len(acc)} ops")
+for (p, j), ms in acc.items():
+    m = bench.op_model(plan.programs[p][j], 4)
+    gbs = m["bytes"] / (ms * 1e-3) / 1e9 if ms > 0 else 0
+    print(f"  p{p} #{j:02d} {ms*1e3:9.1f} us {100*ms/tot:5.1f}%  {m['kind']:12s} {m['tag']:30s} pts={m['points']:>10} "
+          f"alg_bytes={m['bytes']:>10} ({gbs:7.1f} GB/s)")
