@@ -14,7 +14,7 @@
 
 enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
 enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
-       OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11 };
+       OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12 };
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -137,7 +137,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 p.n_leaves = r.i32();
                 for (int l = 0; l < p.n_leaves; ++l) read_opnd(r, c, p.leaf[l], p.d.nd, true);
                 read_prog(r, p.prog);
-                expr_fwd_kernel<T><<<grid_for(p.n_out, 256, c), 256, 0, c.stream>>>(p);
+                launch_expr_fwd<T>(p, c.stream, c.sm_count);
                 break;
             }
             case OP_EXPR_BWD: {
@@ -152,7 +152,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 p.n_leaves = r.i32();
                 for (int l = 0; l < p.n_leaves; ++l) read_opnd(r, c, p.leaf[l], p.d.nd, true);
                 read_prog(r, p.prog);
-                expr_bwd_kernel<T><<<grid_for(p.n_kept * p.nsplit, 256, c), 256, 0, c.stream>>>(p);
+                launch_expr_bwd<T>(p, c.stream, c.sm_count);
                 break;
             }
             case OP_REDUCE: {
@@ -315,6 +315,19 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 read_opnd(r, c, p.b, p.d.nd, false);
                 if (p.d.nd == p.d.n_a) { p.a.stride[p.d.n_a] = 0; p.b.stride[p.d.n_a] = 0; }
                 dot_kernel<T><<<grid_for(p.n_out, 256, c), 256, 0, c.stream>>>(p);
+                break;
+            }
+            case OP_BERN_DOT: {
+                BernDotParams<T> p;
+                memset(&p, 0, sizeof(p));
+                p.out = (T*)tref(r, c);
+                p.cadd = (T)r.f64();
+                int D = r.i32();
+                read_dims(r, p.d, p.n_out, p.n_red);
+                read_opnd(r, c, p.a, p.d.nd, false); p.a_ev = r.i64v();
+                read_opnd(r, c, p.b, p.d.nd, false); p.b_ev = r.i64v();
+                read_opnd(r, c, p.y, p.d.nd, false);
+                if (launch_bern_dot<T>(p, D, c.stream, c.sm_count)) return fail("bern_dot_sum: unsupported event extent");
                 break;
             }
             default:
@@ -526,8 +539,7 @@ void normal_bcast_impl(const void* v, const void* loc, const void* scale, void* 
     p.prog.ins[3][0] = V_NORMAL | (3 << 8) | (0 << 16) | (1u << 24); p.prog.ins[3][1] = 2;
     p.prog.res = 3;
     p.out = (T*)out; p.acc = 0; p.scale = T(1); p.n_out = nc; p.n_red = ne;
-    i64 blocks = (nc + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
-    expr_fwd_kernel<T><<<(int)blocks, 256, 0, st>>>(p);
+    launch_expr_fwd<T>(p, st, 148);
 }
 
 int alan_b200_normal_logpdf_bcast(const void* value, const void* loc, const void* scale, void* out,

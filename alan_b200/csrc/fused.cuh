@@ -236,6 +236,106 @@ __device__ __forceinline__ double2 fma2(double2 a, double2 b, double2 c) { retur
 __device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
 
+// ------------------------------------------------------------------------------------------
+// bern_dot_sum: data factor of logistic-regression-like likelihoods, fused with the plate sum that
+// consumes it (MovieLens `obs ~ Bernoulli(logits = z @ x)` inside plate_2):
+//
+//     out[o] = cadd + sum_n  log Bernoulli(y[o, n]; logits = sum_d a[o, d] * b[o, n, d])
+//
+// o runs over the kept axes (plates and K axes), n over the summed plate, d over the event dim.  One
+// thread per o keeps its a-row (D values) in registers; the b rows are the same for all threads that
+// differ only in axes b does not carry (the K axis of z), so their loads are L1 broadcasts.  Neither
+// the logits nor the per-(o, n) log-likelihoods are ever written: HBM traffic is a + b + y + out.
+// reference: the lambda `z @ x` (movielens.py:40) -> TorchDimDist.log_prob (TorchDimDist.py:127-162)
+// -> lp.sum(plate) (logpq.py:149).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct BernDotParams {
+    Dims d;                 // n_a = kept dims, the rest are the summed plate dims
+    Opnd a, b, y;           // strides over d (a has stride 0 on the summed dims)
+    i64 a_ev, b_ev;         // event strides
+    T cadd;
+    T* out;
+    i64 n_out, n_red;
+    int vec2;               // a / b rows are contiguous and 2-element aligned
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) bern_dot_sum_kernel(const __grid_constant__ BernDotParams<T> p) {
+    typedef typename Pair2<T>::type P2;
+    int idx[AB_MAXD];
+    const T* A = (const T*)p.a.ptr;
+    const T* B = (const T*)p.b.ptr;
+    const T* Y = (const T*)p.y.ptr;
+    const int nred = p.d.nd - p.d.n_a;
+    for (i64 o = (i64)blockIdx.x * blockDim.x + threadIdx.x; o < p.n_out; o += (i64)gridDim.x * blockDim.x) {
+        unravel(o, p.d, 0, p.d.n_a, idx);
+        const i64 ab = dot_stride(p.a, idx, 0, p.d.n_a), bb = dot_stride(p.b, idx, 0, p.d.n_a), yb = dot_stride(p.y, idx, 0, p.d.n_a);
+        T ar[D];
+        if (p.vec2) {
+#pragma unroll
+            for (int q = 0; q < D / 2; ++q) { const P2 v = *reinterpret_cast<const P2*>(A + ab + 2 * q); ar[2 * q] = v.x; ar[2 * q + 1] = v.y; }
+        } else {
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) ar[dd] = A[ab + dd * p.a_ev];
+        }
+        T acc = T(0);
+        for (i64 n = 0; n < p.n_red; ++n) {
+            i64 bo = bb, yo = yb;
+            if (nred == 1) { bo += n * p.b.stride[p.d.n_a]; yo += n * p.y.stride[p.d.n_a]; }
+            else {
+                unravel(n, p.d, p.d.n_a, p.d.nd, idx);
+                bo += dot_stride(p.b, idx, p.d.n_a, p.d.nd); yo += dot_stride(p.y, idx, p.d.n_a, p.d.nd);
+            }
+            T l0 = T(0), l1 = T(0);
+            if (p.vec2) {
+#pragma unroll
+                for (int q = 0; q < D / 2; ++q) {
+                    const P2 v = *reinterpret_cast<const P2*>(B + bo + 2 * q);
+                    l0 += ar[2 * q] * v.x; l1 += ar[2 * q + 1] * v.y;
+                }
+            } else {
+#pragma unroll
+                for (int dd = 0; dd < D; ++dd) l0 += ar[dd] * B[bo + dd * p.b_ev];
+            }
+            acc += bern_logits_lp(Y[yo], l0 + l1);
+        }
+        p.out[o] = acc + p.cadd;
+    }
+}
+
+template <typename T, int D>
+static void launch_bern_dot_D(BernDotParams<T> p, cudaStream_t stream, int sm_count) {
+    bool v2 = (D % 2 == 0) && p.a_ev == 1 && p.b_ev == 1 && ((uintptr_t)p.a.ptr % (2 * sizeof(T)) == 0) &&
+              ((uintptr_t)p.b.ptr % (2 * sizeof(T)) == 0);
+    for (int k = 0; k < p.d.nd && v2; ++k) v2 = (p.a.stride[k] % 2 == 0) && (p.b.stride[k] % 2 == 0);
+    p.vec2 = v2 ? 1 : 0;
+    i64 blocks = (p.n_out + 255) / 256, cap = (i64)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    bern_dot_sum_kernel<T, D><<<(int)blocks, 256, 0, stream>>>(p);
+}
+
+template <typename T>
+static int launch_bern_dot(const BernDotParams<T>& p, int D, cudaStream_t stream, int sm_count) {
+    switch (D) {
+        case 1: launch_bern_dot_D<T, 1>(p, stream, sm_count); break;
+        case 2: launch_bern_dot_D<T, 2>(p, stream, sm_count); break;
+        case 3: launch_bern_dot_D<T, 3>(p, stream, sm_count); break;
+        case 4: launch_bern_dot_D<T, 4>(p, stream, sm_count); break;
+        case 6: launch_bern_dot_D<T, 6>(p, stream, sm_count); break;
+        case 8: launch_bern_dot_D<T, 8>(p, stream, sm_count); break;
+        case 12: launch_bern_dot_D<T, 12>(p, stream, sm_count); break;
+        case 16: launch_bern_dot_D<T, 16>(p, stream, sm_count); break;
+        case 18: launch_bern_dot_D<T, 18>(p, stream, sm_count); break;
+        case 24: launch_bern_dot_D<T, 24>(p, stream, sm_count); break;
+        case 32: launch_bern_dot_D<T, 32>(p, stream, sm_count); break;
+        default: return 1;
+    }
+    return 0;
+}
+
+
 // one tile row -> NPU register pairs with 16-byte shared-memory loads (rows are 16-byte aligned)
 template <int NPU>
 __device__ __forceinline__ void load_row_pairs(const float* row, float2* t2) {

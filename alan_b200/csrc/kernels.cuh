@@ -39,28 +39,86 @@ struct ExprParams {
     i64 n_out, n_red;
 };
 
+// Specialisation selector: the overwhelmingly common factor program is "three loads + Normal"
+// (every mean-field Gaussian Q and most priors).  Those run as straight-line code instead of through
+// the VM loop; NORMAL3 = true means leaf order is (value, loc, scale) = nl[0..3).
+struct Normal3 { int on; int nl[3]; };
+
 template <typename T>
-__global__ void __launch_bounds__(256) expr_fwd_kernel(const __grid_constant__ ExprParams<T> p) {
-    T reg[AB_NREG];
+static Normal3 detect_normal3(const VMProg<T>& P) {
+    Normal3 n; n.on = 0; n.nl[0] = n.nl[1] = n.nl[2] = 0;
+    if (P.n_instr != 4) return n;
+    int leaf_of_reg[AB_NREG];
+    for (int r = 0; r < AB_NREG; ++r) leaf_of_reg[r] = -1;
+    for (int i = 0; i < 3; ++i) {
+        unsigned w0 = P.ins[i][0];
+        if ((w0 & 0xff) != V_LOAD) return n;
+        leaf_of_reg[(w0 >> 8) & 0xff] = (w0 >> 16) & 0xff;
+    }
+    unsigned w0 = P.ins[3][0], w1 = P.ins[3][1];
+    if ((w0 & 0xff) != V_NORMAL || (int)((w0 >> 8) & 0xff) != P.res) return n;
+    int ra = (w0 >> 16) & 0xff, rb = (w0 >> 24) & 0xff, rc = w1 & 0xff;
+    if (leaf_of_reg[ra] < 0 || leaf_of_reg[rb] < 0 || leaf_of_reg[rc] < 0) return n;
+    n.nl[0] = leaf_of_reg[ra]; n.nl[1] = leaf_of_reg[rb]; n.nl[2] = leaf_of_reg[rc];
+    n.on = 1;
+    return n;
+}
+
+// WARP = false: one thread per output, sequential over the summed event dims.
+// WARP = true : one warp per output, lanes stride over the summed dims, fixed-order butterfly sum
+//               (few outputs: the work is latency-bound unless the event loop is spread over lanes).
+template <typename T, bool WARP, bool N3>
+__global__ void __launch_bounds__(256) expr_fwd_kernel(const __grid_constant__ ExprParams<T> p, const Normal3 n3) {
+    T reg[N3 ? 1 : AB_NREG];
     T lv[AB_MAXL];
     int idx[AB_MAXD];
     i64 base[AB_MAXL];
-    for (i64 o = (i64)blockIdx.x * blockDim.x + threadIdx.x; o < p.n_out; o += (i64)gridDim.x * blockDim.x) {
+    const int lane = WARP ? (threadIdx.x & 31) : 0, nl = WARP ? 32 : 1;
+    const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x, tn = (i64)gridDim.x * blockDim.x;
+    for (i64 o = WARP ? (t0 >> 5) : t0; o < p.n_out; o += WARP ? (tn >> 5) : tn) {
         unravel(o, p.d, 0, p.d.n_a, idx);
         for (int l = 0; l < p.n_leaves; ++l) base[l] = dot_stride(p.leaf[l], idx, 0, p.d.n_a);
         T sum = T(0);
-        for (i64 r = 0; r < p.n_red; ++r) {
+        for (i64 r = lane; r < p.n_red; r += nl) {
             unravel(r, p.d, p.d.n_a, p.d.nd, idx);
-            for (int l = 0; l < p.n_leaves; ++l)
-                lv[l] = load_leaf<T>(p.leaf[l], base[l] + dot_stride(p.leaf[l], idx, p.d.n_a, p.d.nd), idx);
-            sum += vm_eval(p.prog, lv, reg);
+            if (N3) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const Opnd& L = p.leaf[n3.nl[q]];
+                    lv[q] = load_leaf<T>(L, base[n3.nl[q]] + dot_stride(L, idx, p.d.n_a, p.d.nd), idx);
+                }
+                sum += normal_lp(lv[0], lv[1], lv[2]);
+            } else {
+                for (int l = 0; l < p.n_leaves; ++l)
+                    lv[l] = load_leaf<T>(p.leaf[l], base[l] + dot_stride(p.leaf[l], idx, p.d.n_a, p.d.nd), idx);
+                sum += vm_eval(p.prog, lv, reg);
+            }
         }
-        T v = p.scale * sum;
-        p.out[o] = p.acc ? p.out[o] + v : v;
+        if (WARP) sum = warp_sum(sum);
+        if (lane == 0) {
+            T v = p.scale * sum;
+            p.out[o] = p.acc ? p.out[o] + v : v;
+        }
     }
 }
 
-// Adjoint w.r.t. one leaf, gather style: one thread per (leaf element, split); the thread
+template <typename T>
+static void launch_expr_fwd(const ExprParams<T>& p, cudaStream_t stream, int sm_count) {
+    const Normal3 n3 = detect_normal3(p.prog);
+    const bool warp = p.n_out < 16384 && p.n_red >= 8;
+    i64 threads = p.n_out * (warp ? 32 : 1);
+    i64 g = (threads + 255) / 256, cap = (i64)sm_count * 8;
+    int grid = (int)(g > cap ? cap : (g < 1 ? 1 : g));
+    if (warp) {
+        if (n3.on) expr_fwd_kernel<T, true, true><<<grid, 256, 0, stream>>>(p, n3);
+        else expr_fwd_kernel<T, true, false><<<grid, 256, 0, stream>>>(p, n3);
+    } else {
+        if (n3.on) expr_fwd_kernel<T, false, true><<<grid, 256, 0, stream>>>(p, n3);
+        else expr_fwd_kernel<T, false, false><<<grid, 256, 0, stream>>>(p, n3);
+    }
+}
+
+// Adjoint w.r.t. one leaf, gather style: one thread (or warp) per (leaf element, split); it
 // loops over every iteration point that read the element.  No atomics.
 template <typename T>
 struct ExprBwdParams {
@@ -77,16 +135,20 @@ struct ExprBwdParams {
     int nsplit;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256) expr_bwd_kernel(const __grid_constant__ ExprBwdParams<T> p) {
-    T reg[AB_NREG];
-    T adj[AB_NREG];
+template <typename T, bool WARP, bool N3>
+__global__ void __launch_bounds__(256) expr_bwd_kernel(const __grid_constant__ ExprBwdParams<T> p, const Normal3 n3) {
+    T reg[N3 ? 1 : AB_NREG];
+    T adj[N3 ? 1 : AB_NREG];
     T lv[AB_MAXL];
     int idx[AB_MAXD];
     i64 base[AB_MAXL];
     const Opnd& tg = p.leaf[p.target];
-    i64 total = p.n_kept * p.nsplit;
-    for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (i64)gridDim.x * blockDim.x) {
+    const i64 total = p.n_kept * p.nsplit;
+    const int lane = WARP ? (threadIdx.x & 31) : 0, nl = WARP ? 32 : 1;
+    const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x, tn = (i64)gridDim.x * blockDim.x;
+    // which argument of the Normal the target leaf is (it may be more than one)
+    const bool tv = N3 && n3.nl[0] == p.target, tl = N3 && n3.nl[1] == p.target, ts = N3 && n3.nl[2] == p.target;
+    for (i64 w = WARP ? (t0 >> 5) : t0; w < total; w += WARP ? (tn >> 5) : tn) {
         i64 e = w % p.n_kept;
         int s = (int)(w / p.n_kept);
         unravel(e, p.d, 0, p.d.n_a, idx);
@@ -99,20 +161,54 @@ __global__ void __launch_bounds__(256) expr_bwd_kernel(const __grid_constant__ E
         if (live) {
             for (int l = 0; l < p.n_leaves; ++l) base[l] = dot_stride(p.leaf[l], idx, 0, p.d.n_a);
             i64 gbase = dot_stride(p.gout, idx, 0, p.d.n_a);
-            for (i64 j = s; j < p.n_loop; j += p.nsplit) {
+            for (i64 j = s + (i64)lane * p.nsplit; j < p.n_loop; j += (i64)p.nsplit * nl) {
                 unravel(j, p.d, p.d.n_a, p.d.nd, idx);
                 if (tg.mode == 2 && idx[tg.mdim] != 0) continue;
-                for (int l = 0; l < p.n_leaves; ++l)
-                    lv[l] = load_leaf<T>(p.leaf[l], base[l] + dot_stride(p.leaf[l], idx, p.d.n_a, p.d.nd), idx);
-                vm_eval(p.prog, lv, reg);
-                T g = vm_grad(p.prog, reg, adj, p.target);
+                T g;
+                if (N3) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const Opnd& L = p.leaf[n3.nl[q]];
+                        lv[q] = load_leaf<T>(L, base[n3.nl[q]] + dot_stride(L, idx, p.d.n_a, p.d.nd), idx);
+                    }
+                    const T sc = lv[2], df = lv[0] - lv[1], iv = T(1) / (sc * sc);
+                    g = T(0);
+                    if (tv) g -= df * iv;
+                    if (tl) g += df * iv;
+                    if (ts) g += (df * df * iv - T(1)) / sc;
+                } else {
+                    for (int l = 0; l < p.n_leaves; ++l)
+                        lv[l] = load_leaf<T>(p.leaf[l], base[l] + dot_stride(p.leaf[l], idx, p.d.n_a, p.d.nd), idx);
+                    vm_eval(p.prog, lv, reg);
+                    g = vm_grad(p.prog, reg, adj, p.target);
+                }
                 T go = ((const T*)p.gout.ptr)[gbase + dot_stride(p.gout, idx, p.d.n_a, p.d.nd)];
                 sum += g * go;
             }
         }
-        T v = p.scale * sum;
-        if (p.nsplit > 1) p.gleaf[(i64)s * p.n_kept + e] = v;
-        else p.gleaf[e] = p.acc ? p.gleaf[e] + v : v;
+        if (WARP) sum = warp_sum(sum);
+        if (lane == 0) {
+            T v = p.scale * sum;
+            if (p.nsplit > 1) p.gleaf[(i64)s * p.n_kept + e] = v;
+            else p.gleaf[e] = p.acc ? p.gleaf[e] + v : v;
+        }
+    }
+}
+
+template <typename T>
+static void launch_expr_bwd(const ExprBwdParams<T>& p, cudaStream_t stream, int sm_count) {
+    const Normal3 n3 = detect_normal3(p.prog);
+    const i64 total = p.n_kept * p.nsplit;
+    const bool warp = total < 16384 && p.n_loop / p.nsplit >= 8;
+    i64 threads = total * (warp ? 32 : 1);
+    i64 g = (threads + 255) / 256, cap = (i64)sm_count * 8;
+    int grid = (int)(g > cap ? cap : (g < 1 ? 1 : g));
+    if (warp) {
+        if (n3.on) expr_bwd_kernel<T, true, true><<<grid, 256, 0, stream>>>(p, n3);
+        else expr_bwd_kernel<T, true, false><<<grid, 256, 0, stream>>>(p, n3);
+    } else {
+        if (n3.on) expr_bwd_kernel<T, false, true><<<grid, 256, 0, stream>>>(p, n3);
+        else expr_bwd_kernel<T, false, false><<<grid, 256, 0, stream>>>(p, n3);
     }
 }
 
@@ -282,7 +378,7 @@ template <typename T>
 static void launch_reduce(const ReduceParams<T>& p, bool thread_hint, cudaStream_t stream, int sm_count) {
     const int nred = p.d.nd - p.d.n_a;
     const i64 per = (p.n_red + p.nsplit - 1) / p.nsplit;
-    const bool warp = per >= 16 && !thread_hint;
+    const bool warp = per >= 16 && (!thread_hint || (p.n_out * p.nsplit < 16384 && per >= 32));
     i64 threads = p.n_out * p.nsplit * (warp ? 32 : 1);
     i64 g = (threads + 255) / 256, cap = (i64)sm_count * 8;
     int grid = (int)(g > cap ? cap : (g < 1 ? 1 : g));

@@ -33,7 +33,7 @@ MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
 SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
 OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY, OP_DOT, \
-    OP_FAN_LSE = range(1, 12)
+    OP_FAN_LSE, OP_BERN_DOT = range(1, 13)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
 
@@ -474,6 +474,30 @@ class DotOp(Op):
                 w.i64(x)
 
 
+class BernDotSumOp(Op):
+    """out[od] = cadd + sum_rd log Bernoulli(y; logits = sum_e a * b)   (csrc/fused.cuh bern_dot_sum_kernel).
+    `gen_ops` = the unfused (dot, expression, plate sum) ops it stands for."""
+    code = OP_BERN_DOT
+
+    def __init__(self, out, od, rd, D, a, b, y, cadd, gen_ops, tag=''):
+        self.out, self.od, self.rd, self.D, self.a, self.b, self.y = out, od, rd, D, a, b, y
+        self.cadd, self.gen_ops, self.tag = cadd, gen_ops, tag
+
+    def payload(self, w):
+        w.tref(self.out); w.f64(self.cadd); w.i32(self.D)
+        dims = self.od + self.rd
+        strides = [[lf.stride(d) for d in dims] for lf in (self.a, self.b, self.y)]
+        sizes, n_a, strides, _ = _coalesce([d[2] for d in dims], len(self.od), strides)
+        _write_dims(w, sizes, n_a)
+        ev = ('ev', 0, self.D)
+        for lf, st, has_ev in zip((self.a, self.b, self.y), strides, (True, True, False)):
+            w.tref(lf.pt)
+            for x in st:
+                w.i64(x)
+            if has_ev:
+                w.i64(lf.stride(ev))
+
+
 class ChainOp(Op):
     code = OP_CHAIN
 
@@ -655,6 +679,7 @@ class Planner:
         self.grad_names = list(grad_names)
         self.needs = set()
         self.fan_by_out = {}
+        self.producer = {}
         self.fwd = []
         self.fwd_segments = []
         self.steps = []              # resampling steps in forward (bottom-up) creation order per level
@@ -684,11 +709,16 @@ class Planner:
             return [op.ms]
         if isinstance(op, FanLseOp):
             return [lf.pt for lf, _ in op.bfactors] + [op.v.pt, op.l.pt, op.s.pt]
+        if isinstance(op, BernDotSumOp):
+            return [op.a.pt, op.b.pt, op.y.pt]
+        if isinstance(op, DotOp):
+            return [op.a.pt, op.b.pt]
         return []
 
     def emit(self, op):
         """Append a forward op and propagate 'needs a gradient' to its output."""
         self.fwd.append(op)
+        self.producer[op.out.id] = op
         if not isinstance(getattr(op, 'autodiff_as', None), str):
             if any(p.id in self.needs for p in self.op_inputs(op)):
                 self.needs.add(op.out.id)
@@ -1087,7 +1117,10 @@ class Planner:
         rd = [self.axdim(plate)]
         n_out = max(1, _prod(d[2] for d in od))
         nsplit = _choose_split(n_out, n)
-        if nsplit > 1:
+        fused = self._try_bern_dot_sum(lf, out, od, rd, n) if (self.fast_paths and nsplit == 1) else None
+        if fused is not None:
+            self.emit(fused)
+        elif nsplit > 1:
             part = self.ws_raw(nsplit * n_out, name=f'partial[{plate}]')
             first = ReduceOp(R_SUM, part, od, rd, lf.tensors, nsplit=nsplit, tag=f'plate_sum_partial:{plate}')
             first.autodiff_as = 'skip'
@@ -1105,6 +1138,44 @@ class Planner:
             self.fwd_segments.append(self.fwd)
             self.fwd = []
         return LogicalFactor([(plain(out), 1.0)], 0.0, out_axes)
+
+    def _try_bern_dot_sum(self, lf, out, od, rd, n):
+        """Fuse  dot -> Bernoulli(logits) -> plate sum  into csrc/fused.cuh bern_dot_sum_kernel when nobody
+        else needs the intermediates (no resampling program, no gradient through the factor)."""
+        if getattr(self, 'with_sample', False) or len(lf.tensors) != 1:
+            return None
+        ref, coeff = lf.tensors[0]
+        if coeff != 1.0 or type(ref) is not LeafRef or ref.rename or ref.mode:
+            return None
+        E = self.producer.get(ref.pt.id)
+        if not isinstance(E, ExprOp) or E not in self.fwd or E.red or E.acc or E.scale != 1.0:
+            return None
+        code = E.codeobj
+        ops = [ins[0] for ins in code.instrs]
+        if ops != [VOPS['load'], VOPS['load'], VOPS['Bernoulli_logits']] or len(code.leaves) != 2:
+            return None
+        _, _, ra, rb, _, _ = code.instrs[2]
+        leaf_of = {code.instrs[i][1]: code.leaves[code.instrs[i][2]] for i in (0, 1)}
+        y, lg = leaf_of[ra], leaf_of[rb]
+        Dt = self.producer.get(lg.pt.id)
+        if not isinstance(Dt, DotOp) or Dt not in self.fwd or len(Dt.red) != 1 or lg.rename or lg.mode or y.rename or y.mode:
+            return None
+        D = Dt.red[0][2]
+        if D not in self.FAN_EVENT_EXTENTS:
+            return None
+        if any(x.id in self.needs for x in (ref.pt, lg.pt, Dt.a.pt, Dt.b.pt, y.pt)):
+            return None
+        a, b = Dt.a, Dt.b
+        if any(a.stride(d) != 0 for d in rd):
+            a, b = b, a
+        if any(a.stride(d) != 0 for d in rd):
+            return None
+        if set((d[0], d[1]) for d in E.keep) != set((d[0], d[1]) for d in od + rd):
+            return None
+        R = ReduceOp(R_SUM, out, od, rd, lf.tensors, cadd=lf.const * n)
+        self.fwd.remove(E)
+        self.fwd.remove(Dt)
+        return BernDotSumOp(out, od, rd, D, a, b, y, lf.const * n, [Dt, E, R], tag='bern_dot_sum:' + E.tag)
 
     def chain(self, lf: LogicalFactor, T_axis, Kinit, Kts):
         """logpq.py:131-143: order to [T, Kprev, Kcurr] (other axes batch), chain_logmmexp, logsumexp."""
@@ -1419,6 +1490,8 @@ def _iterates(op, plate):
         dims = op.od + op.rd
     elif isinstance(op, FanLseOp):
         dims = op.rho + [op.kappa]
+    elif isinstance(op, BernDotSumOp):
+        dims = op.od + op.rd
     elif isinstance(op, ChainOp):
         return plate in op.ms.axes
     else:

@@ -155,6 +155,10 @@ def op_model(op, itemsize):
         pts = rows * f.F
         flops = 2 * pts * f.D + 6 * pts + 2 * rows * f.D
         tag = f.tag + (":adjoint" if name == "FanLseBwdOp" else "")
+    elif name == "BernDotSumOp":
+        pts = math.prod(d[2] for d in op.od + op.rd)
+        add(op.a.pt); add(op.b.pt); add(op.y.pt); add(op.out)
+        flops, tag = pts * (2 * op.D + 12), op.tag
     elif name == "DotOp":
         pts = math.prod(d[2] for d in op.keep + op.red)
         add(op.a.pt); add(op.b.pt); add(op.out)

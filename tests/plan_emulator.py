@@ -157,6 +157,10 @@ class Emu:
         self.op_ReduceOp(PL.ReduceOp(PL.R_WSUM, op.gS, rows, fdim, r.factors, lse=r.out, gout=op.gout,
                                      lse_dims=r.od, gout_dims=r.od, cadd=r.cadd))
 
+    def op_BernDotSumOp(self, op):
+        for g in op.gen_ops:
+            getattr(self, 'op_' + type(g).__name__)(g)
+
     def op_DotOp(self, op):
         self.op_ExprOp(op.autodiff_as)
 

@@ -134,7 +134,7 @@ def test_fused_paths_selected_and_match_oracle(dtype):
     names = list(inp['params'])
     comp = Compiled(P, Q, sample, ip, data, grad_names=names)
     kinds = [type(op).__name__ for prog in comp.plan.programs for op in prog]
-    assert 'FanLseOp' in kinds and 'FanLseBwdOp' in kinds and 'DotOp' in kinds
+    assert 'FanLseOp' in kinds and 'FanLseBwdOp' in kinds and 'BernDotSumOp' in kinds
     comp_slow = Compiled(P, Q, sample, ip, data, grad_names=names, fast_paths=False)
     assert 'FanLseOp' not in [type(op).__name__ for prog in comp_slow.plan.programs for op in prog]
     inputs = comp.canonical_inputs(sample, ip, data)
@@ -149,4 +149,4 @@ def test_fused_paths_selected_and_match_oracle(dtype):
     # a VI-style request (gradient w.r.t. the sample) must fall back to the materialised factor
     comp_vi = Compiled(P, Q, sample, ip, data, grad_names=names + ['z', 'mu_z'])
     kinds = [type(op).__name__ for prog in comp_vi.plan.programs for op in prog]
-    assert 'FanLseOp' not in kinds and 'NormalFanOp' in kinds
+    assert 'FanLseOp' not in kinds and 'NormalFanOp' in kinds and 'DotOp' in kinds
