@@ -1,0 +1,237 @@
+"""Host-side mirror of the reference's call surface for the logPQ path.
+
+    prob = Problem(P, Q, data, inputs=..., params=...)          # reference: src/alan/Problem.py:18-69
+    s = prob.sample_from(samples)                               # samples of Q, K per latent group
+    s.elbo_vi() / s.elbo_rws() / s.elbo_nograd()                # Sample.py:110-148
+    s.marginals(joints=...) / s.moments([...]) / s.ess()        # Sample.py:274-346, Marginals.py:31-61
+    s.importance_sample(N)                                      # Sample.py:185-206
+
+Same names, argument meaning and error behaviour (Python `Exception` with prose) as the reference for
+this path.  What is NOT here is the step before it: ancestral sampling of Q with permutation
+resampling (`Plate.sample`) stays the reference's; `sample_from` takes its
+output (or any `[K, plates..., event]` tensors).  Everything below `Sample` runs in the CUDA engine
+through the C ABI; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from .engine import Compiled, Runner
+from .model import Plate, Kname, check_PQ
+from .named import NT, from_torch_named
+from . import runtime
+
+
+def _as_nt(x) -> NT:
+    if isinstance(x, NT):
+        return x
+    if isinstance(x, torch.Tensor):
+        return from_torch_named(x) if any(n is not None for n in x.names) else NT(x, ())
+    raise Exception(f"expected a tensor or NT, got {type(x)}")
+
+
+class Problem:
+    def __init__(self, P: Plate, Q: Plate, data: dict, inputs: Optional[dict] = None, params: Optional[dict] = None,
+                 device="cuda", process_group=None, shard_plate=None):
+        self.P, self.Q = P, Q
+        self.data = {k: _as_nt(v) for k, v in (data or {}).items()}
+        self.inputs = {k: _as_nt(v) for k, v in (inputs or {}).items()}
+        self.params = {k: _as_nt(v) for k, v in (params or {}).items()}
+        dup = set(self.inputs) & set(self.params)
+        if dup:
+            raise Exception(f"names {sorted(dup)} are used both as inputs and as parameters")
+        check_PQ(P, Q, set(self.data.keys()))
+        self.device = runtime.require_cuda(device)
+        self.pg, self.shard_plate = process_group, shard_plate
+
+    def inputs_params(self) -> dict:
+        """reference Problem.inputs_params (Problem.py:113-118), flat."""
+        return {**self.inputs, **self.params}
+
+    def sample_from(self, sample: dict, reparam: bool = False) -> "Sample":
+        return Sample(self, {k: _as_nt(v) for k, v in sample.items()}, reparam)
+
+
+class Marginals:
+    """Posterior marginal weights over K (reference src/alan/Marginals.py)."""
+    def __init__(self, sample: "Sample", weights: dict):
+        self.sample, self.weights = sample, weights
+
+    def ess(self) -> dict:
+        """1 / sum_K w^2 per latent group (Marginals.py:52-61)."""
+        out = {}
+        for key, w in self.weights.items():
+            if len(key) == 1:
+                kdims = tuple(i for i, a in enumerate(w.axes) if a.startswith("K_"))
+                out[key[0]] = NT(1.0 / (w.t * w.t).sum(kdims), tuple(a for a in w.axes if not a.startswith("K_")))
+        return out
+
+
+class Sample:
+    def __init__(self, problem: Problem, sample: dict, reparam: bool):
+        self.problem, self.sample, self.reparam = problem, sample, reparam
+        groups = problem.Q.groupvarnames()
+        v2g = problem.Q.varname2groupvarname()
+        for name in v2g:
+            if name not in sample:
+                raise Exception(f"no sample was provided for latent variable {name}")
+        self.K = {}
+        for name, v in sample.items():
+            if name not in v2g:
+                raise Exception(f"{name} is not a latent variable of Q")
+            kax = Kname(v2g[name])
+            if kax not in v.axes:
+                raise Exception(f"sample {name} must carry its K axis {kax}")
+            self.K[v2g[name]] = v.named_sizes[kax]
+        self.groups = groups
+        self._cache = {}
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _runner(self, grad_names=(), elf=None, moment_specs=(), N=None) -> Runner:
+        p = self.problem
+        key = (tuple(grad_names), tuple(sorted((elf or {}).keys(), key=str)), len(moment_specs), N)
+        if key not in self._cache:
+            world = 1
+            if p.shard_plate is not None and torch.distributed.is_available() and torch.distributed.is_initialized():
+                world = torch.distributed.get_world_size(p.pg)
+            comp = Compiled(p.P, p.Q, self.sample, p.inputs_params(), p.data, extra_log_factors=elf,
+                            moment_specs=moment_specs, grad_names=list(grad_names), N=N,
+                            shard_plate=p.shard_plate if world > 1 else None, world_size=world)
+            self._cache[key] = Runner(comp, p.device, p.pg)
+        return self._cache[key]
+
+    def _elbo(self, grad_names):
+        run = self._runner(grad_names)
+        p = self.problem
+        tens = run.device_inputs(self.sample, p.inputs_params(), p.data, differentiable=bool(grad_names))
+        if not grad_names:
+            return run.forward_raw(tens)
+        return run.elbo(tens)
+
+    def _diff_names(self, with_sample):
+        names = [k for k, v in self.problem.params.items() if v.t.requires_grad]
+        if with_sample:
+            names += [k for k, v in self.sample.items() if v.t.requires_grad]
+        return names
+
+    # ------------------------------------------------------------------ reference surface
+    def elbo_vi(self):
+        """Reparameterised ELBO: gradients flow to parameters and to the samples (Sample.py:110-122)."""
+        if not self.reparam:
+            raise Exception("To compute the ELBO with the right gradients for VI you must construct a "
+                            "reparameterised sample using `problem.sample_from(samples, reparam=True)`")
+        return self._elbo(self._diff_names(True))
+
+    def elbo_rws(self):
+        """Samples detached; gradients flow to the parameters only (Sample.py:124-134)."""
+        return self._elbo(self._diff_names(False))
+
+    def elbo_nograd(self):
+        with torch.no_grad():
+            return self._elbo(())
+
+    def _J_axes(self, key):
+        g2p = self.problem.Q.groupvarname2platenames()
+        gs = tuple(sorted(key, key=self.groups.index))
+        plates = g2p[gs[0]]
+        for g in gs[1:]:
+            if tuple(g2p[g]) != tuple(plates):
+                raise Exception(f"joint marginal {key}: groups must live in the same plates")
+        return tuple(Kname(g) for g in gs) + tuple(plates)
+
+    def marginals(self, joints: Sequence = ()) -> Marginals:
+        """Posterior marginals over K for every latent group (+ the requested joints): the gradient of the
+        log-evidence w.r.t. zero source terms J (Sample.py:208-289)."""
+        v2g = self.problem.Q.varname2groupvarname()
+        keys = [(g,) for g in self.groups]
+        for j in joints:
+            gs = tuple(dict.fromkeys(v2g.get(x, x) for x in j))
+            for g in gs:
+                if g not in self.groups:
+                    raise Exception(f"{g} is not a latent variable or group of Q")
+            keys.append(tuple(sorted(gs, key=self.groups.index)))
+        sizes = self._sizes()
+        dtype = self._dtype()
+        elf = {}
+        for key in keys:
+            axes = self._J_axes(key)
+            elf[key] = NT(torch.zeros([sizes[a] for a in axes], dtype=dtype), axes)
+        run = self._runner(grad_names=list(elf.keys()), elf=elf)
+        p = self.problem
+        tens = run.device_inputs(self.sample, p.inputs_params(), p.data, elf)
+        run.forward_raw(tens)
+        grads = run.backward_raw(tens)
+        out = {}
+        for key in keys:
+            name = run.comp.elf_keys[key]
+            out[key] = NT(grads[name], run.comp.plan.input_pts[name].axes)
+        return Marginals(self, out)
+
+    def moments(self, specs):
+        """specs: [(varname or tuple of varnames, f)] -> list of NT `E_post[f(x)]` with axes = plates of the
+        variables (Sample.py:291-346; gradient w.r.t. the zero source term of the factor sum f(x) * J)."""
+        moms = [((v,) if isinstance(v, str) else tuple(v), f) for v, f in specs]
+        for vs, _ in moms:
+            for v in vs:
+                if v not in self.sample:
+                    raise Exception(f"{v} is not a latent variable of Q")
+        run = self._runner(moment_specs=moms)
+        p = self.problem
+        tens = run.device_inputs(self.sample, p.inputs_params(), p.data)
+        run.forward_raw(tens)
+        grads = run.backward_raw(tens)
+        return [NT(grads[j], plates) for j, plates, _ in run.comp.moment_inputs]
+
+    def importance_sample(self, N: int, uniforms=None, seed: Optional[int] = None) -> dict:
+        """N joint posterior samples: K indices drawn top-down over the plate tree, then gathered
+        (Sample.py:150-206).  `uniforms` (one float64 tensor `[plates..., N]` per sampling step, in
+        `plan.sample_steps` order) makes the draw reproducible and bit-comparable; by default they
+        are drawn on the device from `seed`."""
+        if N < 1:
+            raise Exception("importance_sample needs N >= 1")
+        run = self._runner(N=N)
+        p = self.problem
+        plan = run.comp.plan
+        tens = run.device_inputs(self.sample, p.inputs_params(), p.data)
+        run.forward_raw(tens)
+        if uniforms is None:
+            g = torch.Generator(device=run.device)
+            g.manual_seed(0 if seed is None else seed)
+            uniforms = [torch.rand([run.comp.sizes[a] for a in batch] + [N], dtype=torch.float64, device=run.device,
+                                   generator=g) for batch, _ in plan.sample_steps]
+        idx = run.resample_raw(tens, uniforms)
+        self.indices = idx
+        v2g = p.Q.varname2groupvarname()
+        g2p = p.Q.groupvarname2platenames()
+        out = {}
+        for name, x in self.sample.items():
+            grp = v2g[name]
+            plates = tuple(g2p[grp])
+            xc = x.order(plates + (Kname(grp),)).t.to(run.device).contiguous()
+            outer = math.prod(run.comp.sizes[a] for a in plates)
+            K = xc.shape[len(plates)]
+            inner = xc.numel() // max(outer * K, 1)
+            got = runtime.gather(xc, idx[grp].t.reshape(N, outer), outer, K, inner)
+            out[name] = NT(got.reshape([N] + [run.comp.sizes[a] for a in plates] + list(x.pos_shape)),
+                           ('N',) + plates)
+        return out
+
+    # ------------------------------------------------------------------ helpers
+    def _sizes(self):
+        sizes = {}
+        p = self.problem
+        for d in (self.sample, p.inputs_params(), p.data):
+            for v in d.values():
+                sizes.update(v.named_sizes)
+        return sizes
+
+    def _dtype(self):
+        p = self.problem
+        for d in (self.sample, p.inputs_params(), p.data):
+            for v in d.values():
+                if v.t.dtype == torch.float64:
+                    return torch.float64
+        return torch.float32
