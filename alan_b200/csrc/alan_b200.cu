@@ -3,6 +3,9 @@
 #include "../../include/alan_b200.h"
 #include "kernels.cuh"
 #include "fused.cuh"
+#include "fan_tc.cuh"
+#include <type_traits>
+#include <cstdlib>
 
 #include <string>
 #include <vector>
@@ -302,7 +305,12 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                     p.b_k[i] = r.i64v();
                 }
                 p.cadd = (T)r.f64();
-                int rc = launch_fan_lse<T>(p, D, bwd != 0, c.stream, c.sm_count);
+                int rc = -1;
+                if constexpr (std::is_same<T, float>::value) {
+                    static const bool no_tc = getenv("ALAN_B200_NO_TC") != nullptr;
+                    if (!no_tc && tc::fan_lse_tc_supported(p, D)) rc = tc::launch_fan_lse_tc(p, D, bwd != 0, c.stream, c.sm_count);
+                }
+                if (rc < 0) rc = launch_fan_lse<T>(p, D, bwd != 0, c.stream, c.sm_count);
                 if (rc) return fail(rc == 1 ? "fan_lse: unsupported event extent" : rc == 2 ? "fan_lse: tile does not fit shared memory" : "fan_lse: strides exceed 32-bit tile addressing");
                 break;
             }

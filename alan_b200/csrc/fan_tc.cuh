@@ -1,0 +1,381 @@
+// fan_tc.cuh -- fan_lse on the 5th-generation tensor cores (tcgen05 + TMEM), fp32 data, 3xTF32.
+//
+// Same contract as fan_lse2_kernel (fused.cuh):
+//     out[rho, f] = LSE_eps_kappa( b[rho,kappa] - c[f] - sum_d (v - l)^2 w[f,d] ) + cadd
+// but the d-contraction -- a genuinely dense  [f, d] x [d, kappa]  product per rho -- runs as
+// tcgen05.mma.kind::tf32 with the accumulator in tensor memory.  The LSE reduces over kappa, so kappa
+// must land on TMEM *columns* (registers of one thread after tcgen05.ld), not on lanes (threads).
+// That is arranged by making the constant operand block-diagonal:
+//
+//   A (TMEM, written once per CTA)   rows  i = (rs, f)       rs in 0..3, f in 0..31      M = 128
+//                                    cols  k = (rs', dd)     dd in 0..KB                  K = 4 KB
+//                                    A[i,k] = [rs == rs'] * { -w[f,dd] log2e | 1 | -c[f] log2e }
+//   B (smem, one stage per tile)     rows  n = kappa (32),   cols k = (rs', dd)
+//                                    B[n,k] = { (v - l)^2 of rho = 4 tile + rs' | bias b | 1 }
+//   D (TMEM) = A B^T                 D[(rs,f), kappa] = log2e * S[rho_rs, kappa, f]   complete, incl. bias
+//
+// so thread (rs, f) of the epilogue reads its 32 kappa values with ONE tcgen05.ld and does the whole
+// max / exp2 / sum in registers.  fp32 accuracy comes from the 3xTF32 split  A_hi B_hi + A_lo B_hi +
+// A_hi B_lo  (relative error ~2^-21 per product; the dropped lo*lo term is 2^-22).
+//
+// Roles (9 warps, 2 CTAs per SM; persistent over tiles of 4 rho):
+//   warps 0-3  epilogue: TMEM lanes 32w..32w+31 = (rs = w, f = lane)
+//   warp  4    MMA issuer (one thread), TMEM allocator
+//   warps 5-8  builders: warp 5 + rs writes the K-columns of rho = 4 tile + rs, lane = kappa
+// Pipelines: smem stages full/empty (builders <-> MMA), TMEM accumulators tfull/tempty (MMA <->
+// epilogue); mbarriers, tcgen05.commit for the MMA-side arrivals.
+#pragma once
+#include "fused.cuh"
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug must fault (trap), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin)
+        if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return u; }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, M = 128, N = 32, K = 8
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 bytes; LBO = byte step between the two 16-byte K chunks
+// of one MMA, SBO = byte step between 8-row groups (cute::UMMA::SmemDescriptor, version 1 = sm_100).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+#define TC_LD32(r, addr)                                                                                      \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                    \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                    \
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"     \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),       \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
+                 : "r"(addr) : "memory")
+
+#define TC_ST8(addr, r, o)                                                                                    \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"              \
+                 :: "r"(addr), "r"(r[o]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), \
+                    "r"(r[o + 6]), "r"(r[o + 7]) : "memory")
+
+constexpr int TC_WARPS = 9;
+constexpr int TC_STAGES = 3;      // smem stages of the B operand
+constexpr int TC_ACC = 2;         // TMEM accumulator stages
+constexpr int TC_TMEM_COLS = 256; // A_hi + A_lo (<= 80 each) + 2 x 32 accumulator columns
+
+// NC = 16-byte K chunks per rho block: KB = 4 NC >= D + 2
+template <int D, bool BWD>
+__global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __grid_constant__ FanLseParams<float> p, const int vec2) {
+    constexpr int NC = (D + 2 + 3) / 4, KB = 4 * NC, KT = 4 * KB;          // KT = K extent of the MMA (<= 80)
+    constexpr int KSTEPS = KT / 8;
+    constexpr uint32_t LBO = 32 * 16, SBO = 8 * 16;                        // [chunk][32 rows][16 B]
+    constexpr uint32_t OPER = 4 * NC * LBO;                                // bytes of one operand part of one stage
+    constexpr uint32_t A_HI = 0, A_LO = KT, D_COL = 2 * KT;
+    static_assert(2 * KT + TC_ACC * 32 <= TC_TMEM_COLS, "TMEM budget");
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    unsigned char* stage_base = tc_smem;                                   // TC_STAGES x (B_hi | B_lo)
+    uint64_t* bars = (uint64_t*)(tc_smem + TC_STAGES * 2 * OPER);
+    uint64_t* full = bars;                                                 // [TC_STAGES]  builders -> MMA
+    uint64_t* empty = bars + TC_STAGES;                                    // [TC_STAGES]  MMA -> builders
+    uint64_t* tfull = bars + 2 * TC_STAGES;                                // [TC_ACC]     MMA -> epilogue
+    uint64_t* tempty = bars + 2 * TC_STAGES + TC_ACC;                      // [TC_ACC]     epilogue -> MMA
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 2 * TC_ACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float LS = 1.4426950408889634f;
+    const int Kk = p.Kk;
+    const unsigned n_rho = (unsigned)p.n_rho;
+    const unsigned n_tiles = (n_rho + 3) / 4;
+
+    // zero the B stages once: padding rows (kappa >= Kk) and padding K columns stay zero forever
+    for (uint32_t i = threadIdx.x; i < TC_STAGES * 2 * OPER / 16; i += blockDim.x)
+        reinterpret_cast<float4*>(stage_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < TC_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        // ---------------------------------------------------------------- A operand, once
+        const int rs = warp, f = lane;
+        {
+            float wv[KB];
+#pragma unroll
+            for (int dd = 0; dd < KB; ++dd) wv[dd] = 0.f;
+            if (f < p.F) {
+                float c = 0.f;
+#pragma unroll
+                for (int dd = 0; dd < D; ++dd) {
+                    const float sc = p.s[f * p.s_f + dd * p.s_ev];
+                    wv[dd] = -LS / (2.f * (sc * sc));
+                    c += logf(sc);
+                }
+                wv[D] = 1.f;
+                wv[D + 1] = -(c + float(D) * float(HALF_LOG_2PI)) * LS;
+            }
+            const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
+#pragma unroll
+            for (int g = 0; g < KT / 8; ++g) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int kk = 8 * g + e;
+                    const int blk = kk / KB, dd = kk - blk * KB;
+                    float x = 0.f;
+#pragma unroll
+                    for (int q = 0; q < KB; ++q) if (q == dd) x = wv[q];
+                    if (blk != rs) x = 0.f;
+                    hi[e] = to_tf32(x);
+                    lo[e] = __float_as_uint(x - __uint_as_float(hi[e]));
+                }
+                TC_ST8(lane_base + A_HI + 8 * g, hi, 0);
+                TC_ST8(lane_base + A_LO + 8 * g, lo, 0);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp < 4) {
+        // ---------------------------------------------------------------- epilogue
+        const int rs = warp, f = lane;
+        unsigned it = 0;
+        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int a = it % TC_ACC;
+            const uint32_t pa = (it / TC_ACC) & 1;
+            const unsigned rho = 4 * tile + rs;
+            const bool live = rho < n_rho && f < p.F;
+            // output offset of this rho (warp-uniform decode)
+            i64 ooff = 0;
+            {
+                unsigned lin = rho < n_rho ? rho : n_rho - 1;
+#pragma unroll 1
+                for (int k = p.rd.nd - 1; k >= 0; --k) {
+                    unsigned sz = (unsigned)p.rd.size[k];
+                    unsigned q = lin / sz;
+                    ooff += (lin - q * sz) * p.ostride[k];
+                    lin = q;
+                }
+            }
+            float lz = 0.f, gz = 0.f;
+            if (BWD) {
+                lz = live ? (p.lse[ooff + (i64)f * p.o_f] - p.cadd) * LS : INFINITY;     // idle rows: weight 0
+                gz = live ? p.gout[ooff + (i64)f * p.o_f] : 0.f;
+            }
+            mbar_wait(&tfull[a], pa);
+            tc_fence_after();
+            uint32_t r[32];
+            TC_LD32(r, tmem + ((uint32_t)(32 * warp) << 16) + D_COL + 32 * a);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(&tempty[a]);
+            if (!BWD) {
+                float m = -3.0e38f;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) if (k < Kk) m = fmaxf(m, __uint_as_float(r[k]));
+                float sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) if (k < Kk) sum += FastExp<float>::ex(__uint_as_float(r[k]) - m);
+                if (live) p.out[ooff + (i64)f * p.o_f] = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + p.cadd;
+            } else {
+                float wv[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) wv[k] = (k < Kk) ? gz * FastExp<float>::ex(__uint_as_float(r[k]) - lz) : 0.f;
+                // fixed-order butterfly reduce-scatter over the lanes (f): lane j ends with the sum for kappa = j
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const bool up = (lane & off) != 0;
+                        const float send = up ? wv[i] : wv[i + off];
+                        const float mine = up ? wv[i + off] : wv[i];
+                        wv[i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                if (rho < n_rho && lane < Kk) p.gS[(i64)rho * Kk + lane] = wv[0];
+            }
+        }
+    } else if (warp == 4) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            unsigned it = 0;
+            for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int s = it % TC_STAGES, a = it % TC_ACC;
+                const uint32_t ps = (it / TC_STAGES) & 1, pa = (it / TC_ACC) & 1;
+                mbar_wait(&full[s], ps);
+                mbar_wait(&tempty[a], pa ^ 1);
+                tc_fence_after();
+                const uint32_t bhi = smem_u32(stage_base + (size_t)s * 2 * OPER), blo = bhi + OPER;
+                const uint32_t d = tmem + D_COL + 32 * a;
+#pragma unroll
+                for (int j = 0; j < KSTEPS; ++j) {
+                    const uint64_t dh = smem_desc(bhi + j * 2 * LBO, LBO, SBO), dl = smem_desc(blo + j * 2 * LBO, LBO, SBO);
+                    mma_tf32_ts(d, tmem + A_HI + 8 * j, dh, IDESC, j > 0 ? 1u : 0u);
+                    mma_tf32_ts(d, tmem + A_LO + 8 * j, dh, IDESC, 1u);
+                    mma_tf32_ts(d, tmem + A_HI + 8 * j, dl, IDESC, 1u);
+                }
+                tc_commit(&empty[s]);
+                tc_commit(&tfull[a]);
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- builders: warp 5 + rs, lane = kappa
+        const int rs = warp - 5, kz = lane;
+        const int vk = (int)p.v_k, lk = (int)p.l_k, vev = (int)p.v_ev, lev = (int)p.l_ev;
+        unsigned it = 0;
+        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % TC_STAGES;
+            const uint32_t ps = (it / TC_STAGES) & 1;
+            i64 voff = 0, loff = 0;
+            i64 boff[AB_MAXL];
+#pragma unroll
+            for (int i = 0; i < AB_MAXL; ++i) boff[i] = 0;
+            {
+                unsigned lin = 4 * tile + rs < n_rho ? 4 * tile + rs : n_rho - 1;
+#pragma unroll 1
+                for (int k = p.rd.nd - 1; k >= 0; --k) {
+                    unsigned sz = (unsigned)p.rd.size[k];
+                    unsigned q = lin / sz;
+                    unsigned ix = lin - q * sz;
+                    lin = q;
+                    voff += ix * p.vstride[k]; loff += ix * p.lstride[k];
+#pragma unroll
+                    for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) boff[i] += ix * p.bstride[i][k];
+                }
+            }
+            float t[KB];
+#pragma unroll
+            for (int dd = 0; dd < KB; ++dd) t[dd] = 0.f;
+            if (kz < Kk) {
+                const float* vp = p.v + voff + kz * vk;
+                const float* lp = p.l + loff + kz * lk;
+                if (vec2) {
+#pragma unroll
+                    for (int q = 0; q < D / 2; ++q) {
+                        const float2 vv = *reinterpret_cast<const float2*>(vp + 2 * q);
+                        const float2 ll = *reinterpret_cast<const float2*>(lp + 2 * q);
+                        const float d0 = vv.x - ll.x, d1 = vv.y - ll.y;
+                        t[2 * q] = d0 * d0; t[2 * q + 1] = d1 * d1;
+                    }
+                } else {
+#pragma unroll
+                    for (int dd = 0; dd < D; ++dd) { const float df = vp[dd * vev] - lp[dd * lev]; t[dd] = df * df; }
+                }
+                float b = 0.f;
+#pragma unroll
+                for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) b += p.bcoeff[i] * p.b[i][boff[i] + kz * p.b_k[i]];
+                t[D] = b * LS;
+                t[D + 1] = 1.f;
+            }
+            mbar_wait(&empty[s], ps ^ 1);
+            if (kz < Kk) {
+                float* bh = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER);
+                float* bl = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    float4 h, l;
+                    uint32_t u;
+                    u = to_tf32(t[4 * c + 0]); h.x = __uint_as_float(u); l.x = t[4 * c + 0] - h.x;
+                    u = to_tf32(t[4 * c + 1]); h.y = __uint_as_float(u); l.y = t[4 * c + 1] - h.y;
+                    u = to_tf32(t[4 * c + 2]); h.z = __uint_as_float(u); l.z = t[4 * c + 2] - h.z;
+                    u = to_tf32(t[4 * c + 3]); h.w = __uint_as_float(u); l.w = t[4 * c + 3] - h.w;
+                    const int off = ((rs * NC + c) * 32 + kz) * 4;
+                    *reinterpret_cast<float4*>(bh + off) = h;
+                    *reinterpret_cast<float4*>(bl + off) = l;
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(&full[s]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+template <int D>
+static int launch_fan_lse_tc_D(const FanLseParams<float>& p, bool bwd, cudaStream_t stream, int sm_count) {
+    constexpr int NC = (D + 2 + 3) / 4;
+    const size_t smem = (size_t)TC_STAGES * 2 * (4 * NC * 32 * 16) + (2 * TC_STAGES + 2 * TC_ACC) * 8 + 16;
+    bool ev2 = (D % 2 == 0) && p.v_ev == 1 && p.l_ev == 1 && p.v_k % 2 == 0 && p.l_k % 2 == 0 &&
+               ((uintptr_t)p.v % 8 == 0) && ((uintptr_t)p.l % 8 == 0);
+    for (int k = 0; k < p.rd.nd && ev2; ++k) ev2 = (p.vstride[k] % 2 == 0) && (p.lstride[k] % 2 == 0);
+    const i64 n_tiles = (p.n_rho + 3) / 4;
+    i64 blocks = n_tiles < (i64)sm_count * 2 ? n_tiles : (i64)sm_count * 2;
+    if (blocks < 1) blocks = 1;
+    if (bwd) {
+        cudaFuncSetAttribute(fan_lse_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fan_lse_tc_kernel<D, true><<<(int)blocks, TC_WARPS * 32, smem, stream>>>(p, ev2 ? 1 : 0);
+    } else {
+        cudaFuncSetAttribute(fan_lse_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fan_lse_tc_kernel<D, false><<<(int)blocks, TC_WARPS * 32, smem, stream>>>(p, ev2 ? 1 : 0);
+    }
+    return 0;
+}
+
+// The tensor-core path covers the shapes of the hierarchical-Gaussian hot path: fp32, fan and kappa
+// extents up to 32 (K <= 32), event extent up to 18; everything else runs fan_lse2_kernel.
+static bool fan_lse_tc_supported(const FanLseParams<float>& p, int D) {
+    if (p.F > 32 || p.Kk > 32 || p.F < 8 || p.n_rho < 64) return false;
+    const i64 lim = (i64)1 << 30;
+    if (p.v_k >= lim || p.l_k >= lim || p.v_ev >= lim || p.l_ev >= lim) return false;
+    switch (D) { case 2: case 4: case 6: case 8: case 12: case 16: case 18: return true; }
+    return false;
+}
+
+static int launch_fan_lse_tc(const FanLseParams<float>& p, int D, bool bwd, cudaStream_t stream, int sm_count) {
+    switch (D) {
+        case 2: return launch_fan_lse_tc_D<2>(p, bwd, stream, sm_count);
+        case 4: return launch_fan_lse_tc_D<4>(p, bwd, stream, sm_count);
+        case 6: return launch_fan_lse_tc_D<6>(p, bwd, stream, sm_count);
+        case 8: return launch_fan_lse_tc_D<8>(p, bwd, stream, sm_count);
+        case 12: return launch_fan_lse_tc_D<12>(p, bwd, stream, sm_count);
+        case 16: return launch_fan_lse_tc_D<16>(p, bwd, stream, sm_count);
+        case 18: return launch_fan_lse_tc_D<18>(p, bwd, stream, sm_count);
+    }
+    return 1;
+}
+
+}  // namespace tc
