@@ -18,10 +18,12 @@
 // max / exp2 / sum in registers.  fp32 accuracy comes from the 3xTF32 split  A_hi B_hi + A_lo B_hi +
 // A_hi B_lo  (relative error ~2^-21 per product; the dropped lo*lo term is 2^-22).
 //
-// Roles (9 warps, 2 CTAs per SM; persistent over tiles of 4 rho):
-//   warps 0-3  epilogue: TMEM lanes 32w..32w+31 = (rs = w, f = lane)
-//   warp  4    MMA issuer (one thread), TMEM allocator
-//   warps 5-8  builders: warp 5 + rs writes the K-columns of rho = 4 tile + rs, lane = kappa
+// Roles (21 warps, one persistent CTA per SM, tiles of 4 rho):
+//   warps 0-7   epilogue, two teams of four: warp % 4 = TMEM lane quadrant = rs, lane = f; team e takes
+//               tiles it % 2 == e
+//   warp  8     MMA issuer (one thread), TMEM allocator
+//   warps 9-20  builders, three sets of four: warp (set, rs) writes the K-columns of rho = 4 tile + rs,
+//               lane = kappa; set b takes tiles it % 3 == b, so three tiles' global loads are in flight
 // Pipelines: smem stages full/empty (builders <-> MMA), TMEM accumulators tfull/tempty (MMA <->
 // epilogue); mbarriers, tcgen05.commit for the MMA-side arrivals.
 #pragma once
@@ -82,21 +84,28 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
                  :: "r"(addr), "r"(r[o]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), \
                     "r"(r[o + 6]), "r"(r[o + 7]) : "memory")
 
-constexpr int TC_WARPS = 9;
-constexpr int TC_STAGES = 3;      // smem stages of the B operand
-constexpr int TC_ACC = 2;         // TMEM accumulator stages
-constexpr int TC_TMEM_COLS = 256; // A_hi + A_lo (<= 80 each) + 2 x 32 accumulator columns
+constexpr int TC_G = 4;           // rho groups per supertile: N = 32 TC_G kappa columns per MMA (N = 128: below
+                                  // that a tcgen05.mma still costs ~64 cycles, measured: N = 32 ran at 64 clk / MMA)
+constexpr int TC_N = 32 * TC_G;
+constexpr int TC_RHO = 4 * TC_G;  // rho per supertile
+constexpr int TC_EPI = 2;         // epilogue teams of 4 warps (warp % 4 = TMEM lane quadrant = rs)
+constexpr int TC_BW = 4 * TC_G;   // builder warps: one per (g, rs)
+constexpr int TC_MMA_WARP = 4 * TC_EPI;
+constexpr int TC_WARPS = 4 * TC_EPI + 1 + TC_BW;
+constexpr int TC_STAGES = 2;      // smem stages of the B operand (80 KB each at D = 18)
+constexpr int TC_ACC = 2;         // TMEM accumulator stages (multiple of TC_EPI)
+constexpr int TC_TMEM_COLS = 512; // A_hi + A_lo (<= 80 each) + 2 x 128 accumulator columns; one CTA per SM
 
 // NC = 16-byte K chunks per rho block: KB = 4 NC >= D + 2
 template <int D, bool BWD>
-__global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __grid_constant__ FanLseParams<float> p, const int vec2) {
+__global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __grid_constant__ FanLseParams<float> p, const int vec2) {
     constexpr int NC = (D + 2 + 3) / 4, KB = 4 * NC, KT = 4 * KB;          // KT = K extent of the MMA (<= 80)
     constexpr int KSTEPS = KT / 8;
-    constexpr uint32_t LBO = 32 * 16, SBO = 8 * 16;                        // [chunk][32 rows][16 B]
+    constexpr uint32_t LBO = TC_N * 16, SBO = 8 * 16;                      // [chunk][TC_N rows][16 B]
     constexpr uint32_t OPER = 4 * NC * LBO;                                // bytes of one operand part of one stage
     constexpr uint32_t A_HI = 0, A_LO = KT, D_COL = 2 * KT;
-    static_assert(2 * KT + TC_ACC * 32 <= TC_TMEM_COLS, "TMEM budget");
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+    static_assert(2 * KT + TC_ACC * TC_N <= TC_TMEM_COLS, "TMEM budget");
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((128u >> 4) << 24);
 
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     unsigned char* stage_base = tc_smem;                                   // TC_STAGES x (B_hi | B_lo)
@@ -111,17 +120,30 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __gr
     const float LS = 1.4426950408889634f;
     const int Kk = p.Kk;
     const unsigned n_rho = (unsigned)p.n_rho;
-    const unsigned n_tiles = (n_rho + 3) / 4;
+    const unsigned n_tiles = (n_rho + TC_RHO - 1) / TC_RHO;
 
-    // zero the B stages once: padding rows (kappa >= Kk) and padding K columns stay zero forever
+    // zero the B stages once: padding K columns stay zero forever
     for (uint32_t i = threadIdx.x; i < TC_STAGES * 2 * OPER / 16; i += blockDim.x)
         reinterpret_cast<float4*>(stage_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    // padding rows (kappa >= Kk) carry a hugely negative bias so that the epilogue needs no column mask
+    {
+        const float big = -1.0e30f, bh = __uint_as_float(to_tf32(big)), bl = big - bh;
+        const int npad = 32 - Kk, per_stage = TC_G * 4 * npad;
+        for (int i = threadIdx.x; i < TC_STAGES * per_stage; i += blockDim.x) {
+            const int s = i / per_stage, r = i - s * per_stage, gr = r / npad, kz = Kk + r - gr * npad;
+            const int g = gr >> 2, rs = gr & 3;
+            const int off = ((rs * NC + D / 4) * TC_N + 32 * g + kz) * 4 + (D & 3);
+            reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER)[off] = bh;
+            reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER)[off] = bl;
+        }
+    }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], TC_BW * 32); mbar_init(&empty[s], 1); }
         for (int a = 0; a < TC_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -134,106 +156,112 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __gr
     if (warp < 4) {
         // ---------------------------------------------------------------- A operand, once
         const int rs = warp, f = lane;
-        {
-            float wv[KB];
+        float wv[KB];
 #pragma unroll
-            for (int dd = 0; dd < KB; ++dd) wv[dd] = 0.f;
-            if (f < p.F) {
-                float c = 0.f;
+        for (int dd = 0; dd < KB; ++dd) wv[dd] = 0.f;
+        if (f < p.F) {
+            float c = 0.f;
 #pragma unroll
-                for (int dd = 0; dd < D; ++dd) {
-                    const float sc = p.s[f * p.s_f + dd * p.s_ev];
-                    wv[dd] = -LS / (2.f * (sc * sc));
-                    c += logf(sc);
-                }
-                wv[D] = 1.f;
-                wv[D + 1] = -(c + float(D) * float(HALF_LOG_2PI)) * LS;
+            for (int dd = 0; dd < D; ++dd) {
+                const float sc = p.s[f * p.s_f + dd * p.s_ev];
+                wv[dd] = -LS / (2.f * (sc * sc));
+                c += logf(sc);
             }
-            const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
-#pragma unroll
-            for (int g = 0; g < KT / 8; ++g) {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int kk = 8 * g + e;
-                    const int blk = kk / KB, dd = kk - blk * KB;
-                    float x = 0.f;
-#pragma unroll
-                    for (int q = 0; q < KB; ++q) if (q == dd) x = wv[q];
-                    if (blk != rs) x = 0.f;
-                    hi[e] = to_tf32(x);
-                    lo[e] = __float_as_uint(x - __uint_as_float(hi[e]));
-                }
-                TC_ST8(lane_base + A_HI + 8 * g, hi, 0);
-                TC_ST8(lane_base + A_LO + 8 * g, lo, 0);
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            wv[D] = 1.f;
+            wv[D + 1] = -(c + float(D) * float(HALF_LOG_2PI)) * LS;
         }
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
+#pragma unroll
+        for (int g = 0; g < KT / 8; ++g) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int kk = 8 * g + e;
+                const int blk = kk / KB, dd = kk - blk * KB;
+                float x = 0.f;
+#pragma unroll
+                for (int q = 0; q < KB; ++q) if (q == dd) x = wv[q];
+                if (blk != rs) x = 0.f;
+                hi[e] = to_tf32(x);
+                lo[e] = __float_as_uint(x - __uint_as_float(hi[e]));
+            }
+            TC_ST8(lane_base + A_HI + 8 * g, hi, 0);
+            TC_ST8(lane_base + A_LO + 8 * g, lo, 0);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
-    if (warp < 4) {
-        // ---------------------------------------------------------------- epilogue
-        const int rs = warp, f = lane;
-        unsigned it = 0;
-        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    if (warp < 4 * TC_EPI) {
+        // ---------------------------------------------------------------- epilogue (team = warp / 4)
+        const int rs = warp & 3, f = lane;
+        for (unsigned it = warp >> 2; blockIdx.x + (i64)it * gridDim.x < n_tiles; it += TC_EPI) {
+            const unsigned tile = blockIdx.x + it * gridDim.x;
             const int a = it % TC_ACC;
             const uint32_t pa = (it / TC_ACC) & 1;
-            const unsigned rho = 4 * tile + rs;
-            const bool live = rho < n_rho && f < p.F;
-            // output offset of this rho (warp-uniform decode)
-            i64 ooff = 0;
-            {
+            // output offsets of this thread's TC_G rho (warp-uniform decode) and, for the adjoint, lse / gout
+            i64 ooff[TC_G];
+            float lz[TC_G], gz[TC_G];
+#pragma unroll
+            for (int g = 0; g < TC_G; ++g) {
+                const unsigned rho = TC_RHO * tile + 4 * g + rs;
                 unsigned lin = rho < n_rho ? rho : n_rho - 1;
+                i64 o = 0;
 #pragma unroll 1
                 for (int k = p.rd.nd - 1; k >= 0; --k) {
                     unsigned sz = (unsigned)p.rd.size[k];
                     unsigned q = lin / sz;
-                    ooff += (lin - q * sz) * p.ostride[k];
+                    o += (lin - q * sz) * p.ostride[k];
                     lin = q;
                 }
-            }
-            float lz = 0.f, gz = 0.f;
-            if (BWD) {
-                lz = live ? (p.lse[ooff + (i64)f * p.o_f] - p.cadd) * LS : INFINITY;     // idle rows: weight 0
-                gz = live ? p.gout[ooff + (i64)f * p.o_f] : 0.f;
+                ooff[g] = o;
+                lz[g] = 0.f; gz[g] = 0.f;
+                if (BWD) {
+                    const bool live = rho < n_rho && f < p.F;
+                    lz[g] = live ? (p.lse[o + (i64)f * p.o_f] - p.cadd) * LS : INFINITY;     // idle rows: weight 0
+                    gz[g] = live ? p.gout[o + (i64)f * p.o_f] : 0.f;
+                }
             }
             mbar_wait(&tfull[a], pa);
             tc_fence_after();
-            uint32_t r[32];
-            TC_LD32(r, tmem + ((uint32_t)(32 * warp) << 16) + D_COL + 32 * a);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            mbar_arrive(&tempty[a]);
-            if (!BWD) {
-                float m = -3.0e38f;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) if (k < Kk) m = fmaxf(m, __uint_as_float(r[k]));
-                float sum = 0.f;
+            for (int g = 0; g < TC_G; ++g) {
+                const unsigned rho = TC_RHO * tile + 4 * g + rs;
+                uint32_t r[32];
+                TC_LD32(r, tmem + ((uint32_t)(32 * rs) << 16) + D_COL + TC_N * a + 32 * g);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (g == TC_G - 1) { tc_fence_before(); mbar_arrive(&tempty[a]); }
+                if (!BWD) {
+                    float m = __uint_as_float(r[0]);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) if (k < Kk) sum += FastExp<float>::ex(__uint_as_float(r[k]) - m);
-                if (live) p.out[ooff + (i64)f * p.o_f] = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + p.cadd;
-            } else {
-                float wv[32];
+                    for (int k = 1; k < 32; ++k) m = fmaxf(m, __uint_as_float(r[k]));
+                    float sum = 0.f;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) wv[k] = (k < Kk) ? gz * FastExp<float>::ex(__uint_as_float(r[k]) - lz) : 0.f;
-                // fixed-order butterfly reduce-scatter over the lanes (f): lane j ends with the sum for kappa = j
+                    for (int k = 0; k < 32; ++k) sum += FastExp<float>::ex(__uint_as_float(r[k]) - m);
+                    if (rho < n_rho && f < p.F)
+                        p.out[ooff[g] + (i64)f * p.o_f] = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + p.cadd;
+                } else {
+                    float wv[32];
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
+                    for (int k = 0; k < 32; ++k) wv[k] = gz[g] * FastExp<float>::ex(__uint_as_float(r[k]) - lz[g]);
+                    // fixed-order butterfly reduce-scatter over the lanes (f): lane j ends with the sum for kappa = j
 #pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const bool up = (lane & off) != 0;
-                        const float send = up ? wv[i] : wv[i + off];
-                        const float mine = up ? wv[i + off] : wv[i];
-                        wv[i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+                    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const bool up = (lane & off) != 0;
+                            const float send = up ? wv[i] : wv[i + off];
+                            const float mine = up ? wv[i + off] : wv[i];
+                            wv[i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
                     }
+                    if (rho < n_rho && lane < Kk) p.gS[(i64)rho * Kk + lane] = wv[0];
                 }
-                if (rho < n_rho && lane < Kk) p.gS[(i64)rho * Kk + lane] = wv[0];
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == TC_MMA_WARP) {
         // ---------------------------------------------------------------- MMA issuer
         if (lane == 0) {
             unsigned it = 0;
@@ -244,7 +272,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __gr
                 mbar_wait(&tempty[a], pa ^ 1);
                 tc_fence_after();
                 const uint32_t bhi = smem_u32(stage_base + (size_t)s * 2 * OPER), blo = bhi + OPER;
-                const uint32_t d = tmem + D_COL + 32 * a;
+                const uint32_t d = tmem + D_COL + TC_N * a;
 #pragma unroll
                 for (int j = 0; j < KSTEPS; ++j) {
                     const uint64_t dh = smem_desc(bhi + j * 2 * LBO, LBO, SBO), dl = smem_desc(blo + j * 2 * LBO, LBO, SBO);
@@ -257,8 +285,8 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __gr
             }
         }
     } else {
-        // ---------------------------------------------------------------- builders: warp 5 + rs, lane = kappa
-        const int rs = warp - 5, kz = lane;
+        // ---------------------------------------------------------------- builders: warp (g, rs), lane = kappa
+        const int bw = warp - TC_MMA_WARP - 1, g = bw >> 2, rs = bw & 3, kz = lane;
         const int vk = (int)p.v_k, lk = (int)p.l_k, vev = (int)p.v_ev, lev = (int)p.l_ev;
         unsigned it = 0;
         for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -269,7 +297,8 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __gr
 #pragma unroll
             for (int i = 0; i < AB_MAXL; ++i) boff[i] = 0;
             {
-                unsigned lin = 4 * tile + rs < n_rho ? 4 * tile + rs : n_rho - 1;
+                const unsigned rho = TC_RHO * tile + 4 * g + rs;
+                unsigned lin = rho < n_rho ? rho : n_rho - 1;
 #pragma unroll 1
                 for (int k = p.rd.nd - 1; k >= 0; --k) {
                     unsigned sz = (unsigned)p.rd.size[k];
@@ -285,6 +314,9 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __gr
 #pragma unroll
             for (int dd = 0; dd < KB; ++dd) t[dd] = 0.f;
             if (kz < Kk) {
+                float b = 0.f;
+#pragma unroll
+                for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) b += p.bcoeff[i] * p.b[i][boff[i] + kz * p.b_k[i]];
                 const float* vp = p.v + voff + kz * vk;
                 const float* lp = p.l + loff + kz * lk;
                 if (vec2) {
@@ -299,9 +331,6 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __gr
 #pragma unroll
                     for (int dd = 0; dd < D; ++dd) { const float df = vp[dd * vev] - lp[dd * lev]; t[dd] = df * df; }
                 }
-                float b = 0.f;
-#pragma unroll
-                for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) b += p.bcoeff[i] * p.b[i][boff[i] + kz * p.b_k[i]];
                 t[D] = b * LS;
                 t[D + 1] = 1.f;
             }
@@ -317,7 +346,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __gr
                     u = to_tf32(t[4 * c + 1]); h.y = __uint_as_float(u); l.y = t[4 * c + 1] - h.y;
                     u = to_tf32(t[4 * c + 2]); h.z = __uint_as_float(u); l.z = t[4 * c + 2] - h.z;
                     u = to_tf32(t[4 * c + 3]); h.w = __uint_as_float(u); l.w = t[4 * c + 3] - h.w;
-                    const int off = ((rs * NC + c) * 32 + kz) * 4;
+                    const int off = ((rs * NC + c) * TC_N + 32 * g + kz) * 4;
                     *reinterpret_cast<float4*>(bh + off) = h;
                     *reinterpret_cast<float4*>(bl + off) = l;
                 }
@@ -329,7 +358,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __gr
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TC_TMEM_COLS) : "memory");
     }
@@ -338,12 +367,12 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 2) fan_lse_tc_kernel(const __gr
 template <int D>
 static int launch_fan_lse_tc_D(const FanLseParams<float>& p, bool bwd, cudaStream_t stream, int sm_count) {
     constexpr int NC = (D + 2 + 3) / 4;
-    const size_t smem = (size_t)TC_STAGES * 2 * (4 * NC * 32 * 16) + (2 * TC_STAGES + 2 * TC_ACC) * 8 + 16;
+    const size_t smem = (size_t)TC_STAGES * 2 * (4 * NC * TC_N * 16) + (2 * TC_STAGES + 2 * TC_ACC) * 8 + 16;
     bool ev2 = (D % 2 == 0) && p.v_ev == 1 && p.l_ev == 1 && p.v_k % 2 == 0 && p.l_k % 2 == 0 &&
                ((uintptr_t)p.v % 8 == 0) && ((uintptr_t)p.l % 8 == 0);
     for (int k = 0; k < p.rd.nd && ev2; ++k) ev2 = (p.vstride[k] % 2 == 0) && (p.lstride[k] % 2 == 0);
-    const i64 n_tiles = (p.n_rho + 3) / 4;
-    i64 blocks = n_tiles < (i64)sm_count * 2 ? n_tiles : (i64)sm_count * 2;
+    const i64 n_tiles = (p.n_rho + TC_RHO - 1) / TC_RHO;
+    i64 blocks = n_tiles < (i64)sm_count ? n_tiles : (i64)sm_count;
     if (blocks < 1) blocks = 1;
     if (bwd) {
         cudaFuncSetAttribute(fan_lse_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
