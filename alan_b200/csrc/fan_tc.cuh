@@ -55,7 +55,9 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return u; }
+// round-to-nearest (ties away) to TF32's 10 mantissa bits: add half an ulp, clear the 13 low bits.  (cvt.rna.tf32.f32
+// compiles to a six-instruction emulation on sm_100a; the operands here are finite.)
+__device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
 // D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, M = 128, N = 32, K = 8
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -196,32 +198,32 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
 
     if (warp < 4 * TC_EPI) {
         // ---------------------------------------------------------------- epilogue (team = warp / 4)
-        const int rs = warp & 3, f = lane;
+        const int rs = warp & 3, f = lane, o_f = (int)p.o_f;
         for (unsigned it = warp >> 2; blockIdx.x + (i64)it * gridDim.x < n_tiles; it += TC_EPI) {
             const unsigned tile = blockIdx.x + it * gridDim.x;
             const int a = it % TC_ACC;
             const uint32_t pa = (it / TC_ACC) & 1;
             // output offsets of this thread's TC_G rho (warp-uniform decode) and, for the adjoint, lse / gout
-            i64 ooff[TC_G];
+            int ooff[TC_G];
             float lz[TC_G], gz[TC_G];
 #pragma unroll
             for (int g = 0; g < TC_G; ++g) {
                 const unsigned rho = TC_RHO * tile + 4 * g + rs;
                 unsigned lin = rho < n_rho ? rho : n_rho - 1;
-                i64 o = 0;
+                int o = 0;
 #pragma unroll 1
                 for (int k = p.rd.nd - 1; k >= 0; --k) {
-                    unsigned sz = (unsigned)p.rd.size[k];
-                    unsigned q = lin / sz;
-                    o += (lin - q * sz) * p.ostride[k];
+                    const unsigned sz = (unsigned)p.rd.size[k];
+                    const unsigned q = lin / sz;
+                    o += (int)(lin - q * sz) * (int)p.ostride[k];
                     lin = q;
                 }
                 ooff[g] = o;
                 lz[g] = 0.f; gz[g] = 0.f;
                 if (BWD) {
                     const bool live = rho < n_rho && f < p.F;
-                    lz[g] = live ? (p.lse[o + (i64)f * p.o_f] - p.cadd) * LS : INFINITY;     // idle rows: weight 0
-                    gz[g] = live ? p.gout[o + (i64)f * p.o_f] : 0.f;
+                    lz[g] = live ? (p.lse[o + f * o_f] - p.cadd) * LS : INFINITY;     // idle rows: weight 0
+                    gz[g] = live ? p.gout[o + f * o_f] : 0.f;
                 }
             }
             mbar_wait(&tfull[a], pa);
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
 #pragma unroll
                     for (int k = 0; k < 32; ++k) sum += FastExp<float>::ex(__uint_as_float(r[k]) - m);
                     if (rho < n_rho && f < p.F)
-                        p.out[ooff[g] + (i64)f * p.o_f] = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + p.cadd;
+                        p.out[ooff[g] + f * o_f] = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + p.cadd;
                 } else {
                     float wv[32];
 #pragma unroll
@@ -287,13 +289,13 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
     } else {
         // ---------------------------------------------------------------- builders: warp (g, rs), lane = kappa
         const int bw = warp - TC_MMA_WARP - 1, g = bw >> 2, rs = bw & 3, kz = lane;
-        const int vk = (int)p.v_k, lk = (int)p.l_k, vev = (int)p.v_ev, lev = (int)p.l_ev;
+        const int vk = (int)p.v_k, lk = (int)p.l_k, vev = (int)p.v_ev, lev = (int)p.l_ev, nb = p.nb;
         unsigned it = 0;
         for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ps = (it / TC_STAGES) & 1;
-            i64 voff = 0, loff = 0;
-            i64 boff[AB_MAXL];
+            int voff = 0, loff = 0;
+            int boff[AB_MAXL];
 #pragma unroll
             for (int i = 0; i < AB_MAXL; ++i) boff[i] = 0;
             {
@@ -301,13 +303,13 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
                 unsigned lin = rho < n_rho ? rho : n_rho - 1;
 #pragma unroll 1
                 for (int k = p.rd.nd - 1; k >= 0; --k) {
-                    unsigned sz = (unsigned)p.rd.size[k];
-                    unsigned q = lin / sz;
-                    unsigned ix = lin - q * sz;
+                    const unsigned sz = (unsigned)p.rd.size[k];
+                    const unsigned q = lin / sz;
+                    const int ix = (int)(lin - q * sz);
                     lin = q;
-                    voff += ix * p.vstride[k]; loff += ix * p.lstride[k];
+                    voff += ix * (int)p.vstride[k]; loff += ix * (int)p.lstride[k];
 #pragma unroll
-                    for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) boff[i] += ix * p.bstride[i][k];
+                    for (int i = 0; i < AB_MAXL; ++i) if (i < nb) boff[i] += ix * (int)p.bstride[i][k];
                 }
             }
             float t[KB];
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
             if (kz < Kk) {
                 float b = 0.f;
 #pragma unroll
-                for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) b += p.bcoeff[i] * p.b[i][boff[i] + kz * p.b_k[i]];
+                for (int i = 0; i < AB_MAXL; ++i) if (i < nb) b += p.bcoeff[i] * p.b[i][boff[i] + kz * (int)p.b_k[i]];
                 const float* vp = p.v + voff + kz * vk;
                 const float* lp = p.l + loff + kz * lk;
                 if (vec2) {
@@ -388,8 +390,16 @@ static int launch_fan_lse_tc_D(const FanLseParams<float>& p, bool bwd, cudaStrea
 // extents up to 32 (K <= 32), event extent up to 18; everything else runs fan_lse2_kernel.
 static bool fan_lse_tc_supported(const FanLseParams<float>& p, int D) {
     if (p.F > 32 || p.Kk > 32 || p.F < 8 || p.n_rho < 64) return false;
-    const i64 lim = (i64)1 << 30;
-    if (p.v_k >= lim || p.l_k >= lim || p.v_ev >= lim || p.l_ev >= lim) return false;
+    // 32-bit element offsets inside the kernel: every operand must span fewer than 2^31 elements
+    const i64 lim = (i64)1 << 31;
+    i64 vspan = (i64)p.Kk * p.v_k + 32 * p.v_ev, lspan = (i64)p.Kk * p.l_k + 32 * p.l_ev, ospan = 32 * p.o_f;
+    i64 bspan = 0;
+    for (int k = 0; k < p.rd.nd; ++k) {
+        vspan += (i64)p.rd.size[k] * p.vstride[k]; lspan += (i64)p.rd.size[k] * p.lstride[k];
+        ospan += (i64)p.rd.size[k] * p.ostride[k];
+        for (int i = 0; i < p.nb; ++i) { i64 b = (i64)p.rd.size[k] * p.bstride[i][k] + (i64)p.Kk * p.b_k[i]; if (b > bspan) bspan = b; }
+    }
+    if (vspan >= lim || lspan >= lim || ospan >= lim || bspan >= lim || p.n_rho * (i64)p.Kk >= lim) return false;
     switch (D) { case 2: case 4: case 6: case 8: case 12: case 16: case 18: return true; }
     return false;
 }
