@@ -86,6 +86,51 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
                  :: "r"(addr), "r"(r[o]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), \
                     "r"(r[o + 6]), "r"(r[o + 7]) : "memory")
 
+// Geometry of the rho iteration space remapped by the host into four right-aligned dim slots (unused
+// slots have extent 1, stride 0), all 32-bit: compile-time slot indices make every stride a constant-
+// bank operand, and the multi-index of a role advances incrementally (add-with-carry) -- no divisions
+// and no parameter-array walks in the per-tile loops.
+#define TC_ND 4
+#define TC_NB 4
+struct TcGeom {
+    int sz[TC_ND];
+    int vs[TC_ND], ls[TC_ND], os[TC_ND];
+    int bs[TC_NB][TC_ND];
+    int bk[TC_NB];
+    float bc[TC_NB];
+    int nb;
+    int vec2;
+};
+
+struct TcIdx {
+    int i[TC_ND];
+    __device__ __forceinline__ void set(unsigned lin, const TcGeom& g) {
+#pragma unroll
+        for (int k = TC_ND - 1; k >= 0; --k) {
+            const unsigned sz = (unsigned)g.sz[k];
+            const unsigned q = lin / sz;
+            i[k] = (int)(lin - q * sz);
+            lin = q;
+        }
+    }
+    // this += step (both valid multi-indices); overflow of the top slot wraps (callers mask rho >= n_rho)
+    __device__ __forceinline__ void add(const TcIdx& st, const TcGeom& g) {
+        int carry = 0;
+#pragma unroll
+        for (int k = TC_ND - 1; k >= 0; --k) {
+            const int v = i[k] + st.i[k] + carry;
+            carry = v >= g.sz[k] ? 1 : 0;
+            i[k] = carry ? v - g.sz[k] : v;
+        }
+    }
+    __device__ __forceinline__ int dot(const int* st) const {
+        int o = 0;
+#pragma unroll
+        for (int k = 0; k < TC_ND; ++k) o += i[k] * st[k];
+        return o;
+    }
+};
+
 constexpr int TC_G = 4;           // rho groups per supertile: N = 32 TC_G kappa columns per MMA (N = 128: below
                                   // that a tcgen05.mma still costs ~64 cycles, measured: N = 32 ran at 64 clk / MMA)
 constexpr int TC_N = 32 * TC_G;
@@ -100,7 +145,7 @@ constexpr int TC_TMEM_COLS = 512; // A_hi + A_lo (<= 80 each) + 2 x 128 accumula
 
 // NC = 16-byte K chunks per rho block: KB = 4 NC >= D + 2
 template <int D, bool BWD>
-__global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __grid_constant__ FanLseParams<float> p, const int vec2) {
+__global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __grid_constant__ FanLseParams<float> p, const __grid_constant__ TcGeom geo) {
     constexpr int NC = (D + 2 + 3) / 4, KB = 4 * NC, KT = 4 * KB;          // KT = K extent of the MMA (<= 80)
     constexpr int KSTEPS = KT / 8;
     constexpr uint32_t LBO = TC_N * 16, SBO = 8 * 16;                      // [chunk][TC_N rows][16 B]
@@ -199,32 +244,34 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
     if (warp < 4 * TC_EPI) {
         // ---------------------------------------------------------------- epilogue (team = warp / 4)
         const int rs = warp & 3, f = lane, o_f = (int)p.o_f;
+        // multi-index of rho = TC_RHO * tile + rs for this team's first tile, and its per-iteration step
+        TcIdx base, step, four;
+        base.set(TC_RHO * (blockIdx.x + (warp >> 2) * gridDim.x) + rs, geo);
+        step.set(TC_RHO * TC_EPI * gridDim.x, geo);
+        four.set(4, geo);
         for (unsigned it = warp >> 2; blockIdx.x + (i64)it * gridDim.x < n_tiles; it += TC_EPI) {
             const unsigned tile = blockIdx.x + it * gridDim.x;
             const int a = it % TC_ACC;
             const uint32_t pa = (it / TC_ACC) & 1;
-            // output offsets of this thread's TC_G rho (warp-uniform decode) and, for the adjoint, lse / gout
+            // output offsets of this thread's TC_G rho (warp-uniform) and, for the adjoint, lse / gout
             int ooff[TC_G];
             float lz[TC_G], gz[TC_G];
+            {
+                TcIdx cur = base;
 #pragma unroll
-            for (int g = 0; g < TC_G; ++g) {
-                const unsigned rho = TC_RHO * tile + 4 * g + rs;
-                unsigned lin = rho < n_rho ? rho : n_rho - 1;
-                int o = 0;
-#pragma unroll 1
-                for (int k = p.rd.nd - 1; k >= 0; --k) {
-                    const unsigned sz = (unsigned)p.rd.size[k];
-                    const unsigned q = lin / sz;
-                    o += (int)(lin - q * sz) * (int)p.ostride[k];
-                    lin = q;
+                for (int g = 0; g < TC_G; ++g) {
+                    const unsigned rho = TC_RHO * tile + 4 * g + rs;
+                    const int o = cur.dot(geo.os);
+                    ooff[g] = o;
+                    lz[g] = 0.f; gz[g] = 0.f;
+                    if (BWD) {
+                        const bool live = rho < n_rho && f < p.F;
+                        lz[g] = live ? (p.lse[o + f * o_f] - p.cadd) * LS : INFINITY;     // idle rows: weight 0
+                        gz[g] = live ? p.gout[o + f * o_f] : 0.f;
+                    }
+                    cur.add(four, geo);
                 }
-                ooff[g] = o;
-                lz[g] = 0.f; gz[g] = 0.f;
-                if (BWD) {
-                    const bool live = rho < n_rho && f < p.F;
-                    lz[g] = live ? (p.lse[o + f * o_f] - p.cadd) * LS : INFINITY;     // idle rows: weight 0
-                    gz[g] = live ? p.gout[o + f * o_f] : 0.f;
-                }
+                base.add(step, geo);
             }
             mbar_wait(&tfull[a], pa);
             tc_fence_after();
@@ -289,36 +336,27 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
     } else {
         // ---------------------------------------------------------------- builders: warp (g, rs), lane = kappa
         const int bw = warp - TC_MMA_WARP - 1, g = bw >> 2, rs = bw & 3, kz = lane;
-        const int vk = (int)p.v_k, lk = (int)p.l_k, vev = (int)p.v_ev, lev = (int)p.l_ev, nb = p.nb;
+        const int vk = (int)p.v_k, lk = (int)p.l_k, vev = (int)p.v_ev, lev = (int)p.l_ev, nb = geo.nb, vec2 = geo.vec2;
+        TcIdx cur, step;
+        cur.set(TC_RHO * blockIdx.x + 4 * g + rs, geo);
+        step.set(TC_RHO * gridDim.x, geo);
         unsigned it = 0;
         for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ps = (it / TC_STAGES) & 1;
-            int voff = 0, loff = 0;
-            int boff[AB_MAXL];
+            const bool live = TC_RHO * tile + 4 * g + rs < n_rho && kz < Kk;
+            const int voff = cur.dot(geo.vs), loff = cur.dot(geo.ls);
+            int boff[TC_NB];
 #pragma unroll
-            for (int i = 0; i < AB_MAXL; ++i) boff[i] = 0;
-            {
-                const unsigned rho = TC_RHO * tile + 4 * g + rs;
-                unsigned lin = rho < n_rho ? rho : n_rho - 1;
-#pragma unroll 1
-                for (int k = p.rd.nd - 1; k >= 0; --k) {
-                    const unsigned sz = (unsigned)p.rd.size[k];
-                    const unsigned q = lin / sz;
-                    const int ix = (int)(lin - q * sz);
-                    lin = q;
-                    voff += ix * (int)p.vstride[k]; loff += ix * (int)p.lstride[k];
-#pragma unroll
-                    for (int i = 0; i < AB_MAXL; ++i) if (i < nb) boff[i] += ix * (int)p.bstride[i][k];
-                }
-            }
+            for (int i = 0; i < TC_NB; ++i) boff[i] = cur.dot(geo.bs[i]);
+            cur.add(step, geo);
             float t[KB];
 #pragma unroll
             for (int dd = 0; dd < KB; ++dd) t[dd] = 0.f;
-            if (kz < Kk) {
+            if (live) {
                 float b = 0.f;
 #pragma unroll
-                for (int i = 0; i < AB_MAXL; ++i) if (i < nb) b += p.bcoeff[i] * p.b[i][boff[i] + kz * (int)p.b_k[i]];
+                for (int i = 0; i < TC_NB; ++i) if (i < nb) b += geo.bc[i] * p.b[i][boff[i] + kz * geo.bk[i]];
                 const float* vp = p.v + voff + kz * vk;
                 const float* lp = p.l + loff + kz * lk;
                 if (vec2) {
@@ -337,7 +375,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
                 t[D + 1] = 1.f;
             }
             mbar_wait(&empty[s], ps ^ 1);
-            if (kz < Kk) {
+            if (kz < Kk) {                       // rows of rho >= n_rho are written as zeros: finite, masked later
                 float* bh = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER);
                 float* bl = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER);
 #pragma unroll
@@ -376,12 +414,24 @@ static int launch_fan_lse_tc_D(const FanLseParams<float>& p, bool bwd, cudaStrea
     const i64 n_tiles = (p.n_rho + TC_RHO - 1) / TC_RHO;
     i64 blocks = n_tiles < (i64)sm_count ? n_tiles : (i64)sm_count;
     if (blocks < 1) blocks = 1;
+    TcGeom geo;
+    memset(&geo, 0, sizeof(geo));
+    for (int j = 0; j < TC_ND; ++j) geo.sz[j] = 1;
+    for (int k = 0; k < p.rd.nd; ++k) {
+        const int j = TC_ND - p.rd.nd + k;
+        geo.sz[j] = p.rd.size[k];
+        geo.vs[j] = (int)p.vstride[k]; geo.ls[j] = (int)p.lstride[k]; geo.os[j] = (int)p.ostride[k];
+        for (int i = 0; i < p.nb; ++i) geo.bs[i][j] = (int)p.bstride[i][k];
+    }
+    for (int i = 0; i < p.nb; ++i) { geo.bk[i] = (int)p.b_k[i]; geo.bc[i] = p.bcoeff[i]; }
+    geo.nb = p.nb;
+    geo.vec2 = ev2 ? 1 : 0;
     if (bwd) {
         cudaFuncSetAttribute(fan_lse_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        fan_lse_tc_kernel<D, true><<<(int)blocks, TC_WARPS * 32, smem, stream>>>(p, ev2 ? 1 : 0);
+        fan_lse_tc_kernel<D, true><<<(int)blocks, TC_WARPS * 32, smem, stream>>>(p, geo);
     } else {
         cudaFuncSetAttribute(fan_lse_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        fan_lse_tc_kernel<D, false><<<(int)blocks, TC_WARPS * 32, smem, stream>>>(p, ev2 ? 1 : 0);
+        fan_lse_tc_kernel<D, false><<<(int)blocks, TC_WARPS * 32, smem, stream>>>(p, geo);
     }
     return 0;
 }
@@ -389,7 +439,7 @@ static int launch_fan_lse_tc_D(const FanLseParams<float>& p, bool bwd, cudaStrea
 // The tensor-core path covers the shapes of the hierarchical-Gaussian hot path: fp32, fan and kappa
 // extents up to 32 (K <= 32), event extent up to 18; everything else runs fan_lse2_kernel.
 static bool fan_lse_tc_supported(const FanLseParams<float>& p, int D) {
-    if (p.F > 32 || p.Kk > 32 || p.F < 8 || p.n_rho < 64) return false;
+    if (p.F > 32 || p.Kk > 32 || p.F < 8 || p.n_rho < 64 || p.rd.nd > TC_ND || p.nb > TC_NB) return false;
     // 32-bit element offsets inside the kernel: every operand must span fewer than 2^31 elements
     const i64 lim = (i64)1 << 31;
     i64 vspan = (i64)p.Kk * p.v_k + 32 * p.v_ev, lspan = (i64)p.Kk * p.l_k + 32 * p.l_ev, ospan = 32 * p.o_f;
