@@ -305,6 +305,10 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                     p.b_k[i] = r.i64v();
                 }
                 p.cadd = (T)r.f64();
+                if (bwd) {
+                    for (int k = 0; k < nrd; ++k) p.gstride[k] = r.i64v();
+                    p.g_f = r.i64v();
+                }
                 int rc = -1;
                 if constexpr (std::is_same<T, float>::value) {
                     static const bool no_tc = getenv("ALAN_B200_NO_TC") != nullptr;

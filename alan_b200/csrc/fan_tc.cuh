@@ -94,7 +94,8 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
 #define TC_NB 4
 struct TcGeom {
     int sz[TC_ND];
-    int vs[TC_ND], ls[TC_ND], os[TC_ND];
+    int vs[TC_ND], ls[TC_ND], os[TC_ND], gs[TC_ND];
+    int g_f;
     int bs[TC_NB][TC_ND];
     int bk[TC_NB];
     float bc[TC_NB];
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
                     if (BWD) {
                         const bool live = rho < n_rho && f < p.F;
                         lz[g] = live ? (p.lse[o + f * o_f] - p.cadd) * LS : INFINITY;     // idle rows: weight 0
-                        gz[g] = live ? p.gout[o + f * o_f] : 0.f;
+                        gz[g] = live ? p.gout[cur.dot(geo.gs) + f * geo.g_f] : 0.f;
                     }
                     cur.add(four, geo);
                 }
@@ -420,11 +421,12 @@ static int launch_fan_lse_tc_D(const FanLseParams<float>& p, bool bwd, cudaStrea
     for (int k = 0; k < p.rd.nd; ++k) {
         const int j = TC_ND - p.rd.nd + k;
         geo.sz[j] = p.rd.size[k];
-        geo.vs[j] = (int)p.vstride[k]; geo.ls[j] = (int)p.lstride[k]; geo.os[j] = (int)p.ostride[k];
+        geo.vs[j] = (int)p.vstride[k]; geo.ls[j] = (int)p.lstride[k]; geo.os[j] = (int)p.ostride[k]; geo.gs[j] = (int)p.gstride[k];
         for (int i = 0; i < p.nb; ++i) geo.bs[i][j] = (int)p.bstride[i][k];
     }
     for (int i = 0; i < p.nb; ++i) { geo.bk[i] = (int)p.b_k[i]; geo.bc[i] = p.bcoeff[i]; }
     geo.nb = p.nb;
+    geo.g_f = (int)p.g_f;
     geo.vec2 = ev2 ? 1 : 0;
     if (bwd) {
         cudaFuncSetAttribute(fan_lse_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -205,6 +205,7 @@ struct FanLseParams {
     T cadd;
     T* out;                               // fwd: result; bwd: unused
     const T* lse; const T* gout;          // bwd
+    i64 gstride[AB_MAXD]; i64 g_f;        // bwd: strides of gout over the rho dims / fan axis (0 = broadcast)
     T* gS;                                // bwd: [rho, kappa] contiguous
     i64 n_rho;
 };
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(FL2_WARPS * 32, 2) fan_lse2_kernel(const __gri
     T* Pp = Tt + RPW * TP;                      // bwd: [32][KPo] per-lane partial weights
     i64* offs = (i64*)(fan_smem + (((size_t)(FC * DP + FL2_WARPS * cfg.warp_elems) * sizeof(T) + 15) & ~(size_t)15))
                 + (size_t)warp_in_cta * cfg.off_words;          // [RPW][3 + nb]
-    const int NO = 3 + p.nb;
+    const int NO = 4 + p.nb;
     const T LS = FastExp<T>::scale();
     const int rs = lane / FG, fg = lane - rs * FG;
     const bool lane_on = rs < RPW;
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(FL2_WARPS * 32, 2) fan_lse2_kernel(const __gri
             const unsigned rho0 = g * RPW;
             // per-rho offsets: lane t decodes rho0 + t
             if (lane < RPW) {
-                i64 voff = 0, loff = 0, ooff = 0;
+                i64 voff = 0, loff = 0, ooff = 0, goff = 0;
                 i64 boff[AB_MAXL];
 #pragma unroll
                 for (int i = 0; i < AB_MAXL; ++i) boff[i] = 0;
@@ -467,13 +468,14 @@ __global__ void __launch_bounds__(FL2_WARPS * 32, 2) fan_lse2_kernel(const __gri
                     unsigned ix = lin - q * sz;
                     lin = q;
                     voff += ix * p.vstride[k]; loff += ix * p.lstride[k]; ooff += ix * p.ostride[k];
+                    if (BWD) goff += ix * p.gstride[k];
 #pragma unroll
                     for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) boff[i] += ix * p.bstride[i][k];
                 }
                 i64* o = offs + lane * NO;
-                o[0] = voff; o[1] = loff; o[2] = ooff;
+                o[0] = voff; o[1] = loff; o[2] = ooff; o[3] = goff;
 #pragma unroll
-                for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) o[3 + i] = boff[i];
+                for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) o[4 + i] = boff[i];
             }
             __syncwarp();
             // squared residual tiles: T[t][k][d] = (v - l)^2; (k, d) advance incrementally, 32-bit
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(FL2_WARPS * 32, 2) fan_lse2_kernel(const __gri
                 for (int k = lane; k < Kk; k += 32) {
                     T b = T(0);
 #pragma unroll
-                    for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) b += p.bcoeff[i] * p.b[i][offs[t * NO + 3 + i] + k * p.b_k[i]];
+                    for (int i = 0; i < AB_MAXL; ++i) if (i < p.nb) b += p.bcoeff[i] * p.b[i][offs[t * NO + 4 + i] + k * p.b_k[i]];
                     Tt[t * TP + k * DP + D] = b * LS;
                 }
             }
@@ -569,7 +571,7 @@ __global__ void __launch_bounds__(FL2_WARPS * 32, 2) fan_lse2_kernel(const __gri
                     const int f = f_base + fg * FPL + j;
                     const bool on = live && f < p.F;
                     const T lz = on ? (p.lse[ooff + (i64)f * p.o_f] - p.cadd) * LS : -neg_inf<T>();   // idle columns: weight 0
-                    gz[j] = on ? p.gout[ooff + (i64)f * p.o_f] : T(0);
+                    gz[j] = on ? p.gout[offs[rsc * NO + 3] + (i64)f * p.g_f] : T(0);
                     wl[j] = W2[j][NPU - 1];
                     if (((D + 1) & 1) == 0) wl[j].x -= lz; else wl[j].y -= lz;           // slot D + 1 holds -c
                 }
@@ -636,7 +638,7 @@ static int launch_fan_lse_DR(const FanLseParams<T>& p, bool bwd, cudaStream_t st
     for (int k = 0; k < p.rd.nd && ev2; ++k) ev2 = (p.vstride[k] % 2 == 0) && (p.lstride[k] % 2 == 0);
     c.vec2 = ev2 ? 1 : 0;
     c.warp_elems = c.RPW * c.tile_pitch + (bwd ? ((32 * KPo + 3) & ~3) : 0);
-    c.off_words = c.RPW * (3 + p.nb);
+    c.off_words = c.RPW * (4 + p.nb);
     size_t smem = (((size_t)(c.FC * FT::DP + FL2_WARPS * c.warp_elems) * sizeof(T) + 15) & ~(size_t)15)
                   + (size_t)FL2_WARPS * c.off_words * sizeof(i64);
     if (smem > 200 * 1024) return 2;

@@ -447,12 +447,23 @@ class FanLseBwdOp(Op):
     """gS[rho, kappa] = sum_f gout[rho,f] * softmax weight: adjoint of the small-factor sum."""
     code = OP_FAN_LSE
 
-    def __init__(self, fwd: FanLseOp, gout, gS):
-        self.fwd, self.gout, self.gS = fwd, gout, gS
+    def __init__(self, fwd: FanLseOp, gout, gS, gout_dims=None):
+        # gout_dims: dims the gout tensor is laid out over (default: like fwd.out); a plate-sum adjoint is
+        # read in place through zero strides instead of being broadcast into a full-size tensor first
+        self.fwd, self.gout, self.gS, self.gout_dims = fwd, gout, gS, gout_dims
 
     def payload(self, w):
         w.i32(1); w.tref(self.fwd.out); w.tref(self.gout); w.tref(self.gS)
         self.fwd._body(w)
+        f = self.fwd
+        fdim = ('ax', f.fan_axis, f.F)
+        if self.gout_dims is None:
+            o = plain(f.out)
+            st = [o.stride(d) for d in f.rho] + [o.stride(fdim)]
+        else:
+            st = _strides_like(self.gout, self.gout_dims, f.rho + [fdim])
+        for x in st:
+            w.i64(x)
 
 
 class DotOp(Op):
@@ -1247,6 +1258,11 @@ class Planner:
                     sharded_ids.add(id(lop))
         needs = self.needs
         self.alloc_group = 1
+        n_uses = {}
+        for op in all_fwd:
+            for x in self.op_inputs(op):
+                n_uses[x.id] = n_uses.get(x.id, 0) + 1
+        lazy_bcast = {}              # pt.id -> (small gout PT, its dims): adjoint = broadcast, never materialised
         adj = {}
         grad_out = {}
         for i, n in enumerate(grad_names):
@@ -1291,10 +1307,10 @@ class Planner:
         for op in reversed(all_fwd):
             if op.out.space == 'output':
                 continue
-            if op.out.id not in needs or op.out.id not in adj:
+            if op.out.id not in needs or (op.out.id not in adj and op.out.id not in lazy_bcast):
                 continue
             out_list = segs[len(self.fwd_segments) - 1 - seg_of[id(op)]]
-            gout = adj[op.out.id]
+            gout = adj.get(op.out.id)
             if isinstance(op, ExprOp):
                 dims = op.keep + op.red
                 for li, lf in enumerate(op.codeobj.leaves):
@@ -1335,6 +1351,14 @@ class Planner:
                     n_loop = _prod(d[2] for d in loop)
                     nsplit = _choose_split(n_kept, n_loop)
                     scale = op.scale * coeff * contribution_scale(op, lf.pt, g)
+                    if (op.mode == R_SUM and self.fast_paths and not loop and scale == 1.0 and n_uses.get(lf.pt.id) == 1
+                            and isinstance(self.producer.get(lf.pt.id), FanLseOp) and g.space == 'ws'
+                            and type(lf) is LeafRef and not lf.rename and not lf.mode):
+                        # pure broadcast into the only consumer-less adjoint of a fused contraction: hand the
+                        # small tensor to the adjoint kernel instead (it reads it through zero strides)
+                        lazy_bcast[lf.pt.id] = (gout, op.od)
+                        del adj[lf.pt.id]
+                        continue
                     if op.mode == R_SUM:
                         mode, facs, kw = R_SUM, [(_OwnDims(gout, op.od), 1.0)], {}
                     else:
@@ -1353,7 +1377,11 @@ class Planner:
                 if bs:
                     rows = op.rho + [op.kappa]
                     gS = self.ws(tuple(d[1] for d in rows), name='adj:small_factor_sum')
-                    out_list.append(FanLseBwdOp(op, gout, gS))
+                    if op.out.id in lazy_bcast:
+                        gsmall, gdims = lazy_bcast[op.out.id]
+                        out_list.append(FanLseBwdOp(op, gsmall, gS, gout_dims=gdims))
+                    else:
+                        out_list.append(FanLseBwdOp(op, gout, gS))
                     for lf, coeff in bs:
                         g = adjoint(lf.pt)
                         kept = [d for d in rows if lf.stride(d) != 0]

@@ -155,7 +155,8 @@ class Emu:
         fdim = [('ax', f.fan_axis, f.F)]
         r = f.gen_reduce
         self.op_ReduceOp(PL.ReduceOp(PL.R_WSUM, op.gS, rows, fdim, r.factors, lse=r.out, gout=op.gout,
-                                     lse_dims=r.od, gout_dims=r.od, cadd=r.cadd))
+                                     lse_dims=r.od, gout_dims=op.gout_dims if op.gout_dims is not None else r.od,
+                                     cadd=r.cadd))
 
     def op_BernDotSumOp(self, op):
         for g in op.gen_ops:
