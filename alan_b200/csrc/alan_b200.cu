@@ -11,6 +11,7 @@
 #include <vector>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #define AB_MAGIC 0x0A1AB200
 #define AB_VERSION 1
@@ -22,12 +23,37 @@ enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, O
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
 
+// One instantiated CUDA graph of a program for one binding of pointers (inputs, outputs, aux,
+// workspace) and one stream.  A program is a fixed sequence of launches, so after the first call the
+// whole sequence is replayed with a single cudaGraphLaunch: no per-op host work, no launch gaps.
+struct GraphEntry {
+    std::vector<const void*> key;
+    cudaGraphExec_t exec;
+    unsigned long long last_use;
+};
+
 struct alan_b200_plan {
     std::vector<int32_t> blob;
     int dtype, n_inputs, n_programs, n_fwd, n_bwd, sample_prog;
     size_t ws_bytes;
     std::vector<int> prog_start, prog_nops;
     int sm_count;
+    // graph cache (mutable state behind a const handle: guarded by mu)
+    mutable std::mutex mu;
+    mutable std::vector<std::vector<GraphEntry>> graphs;
+    mutable std::vector<int> n_out, n_aux;          // per program, learnt on the first run (-1 = unknown)
+    mutable unsigned long long tick = 0;
+    bool use_graphs = true;
+    // graphs cannot be captured on / launched into the legacy default stream: calls that arrive on it are
+    // forwarded to this private stream, ordered by a pair of events
+    mutable cudaStream_t side = nullptr;
+    mutable cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    ~alan_b200_plan() {
+        for (auto& v : graphs) for (auto& g : v) cudaGraphExecDestroy(g.exec);
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_out) cudaEventDestroy(ev_out);
+        if (side) cudaStreamDestroy(side);
+    }
 };
 
 struct Reader {
@@ -44,6 +70,7 @@ struct Ctx {
     char* ws;
     cudaStream_t stream;
     int sm_count;
+    mutable int max_out = -1, max_aux = -1;        // highest output / aux slot the program touched
 };
 
 static void* tref(Reader& r, const Ctx& c) {
@@ -52,8 +79,8 @@ static void* tref(Reader& r, const Ctx& c) {
     switch (space) {
         case SP_WS: return c.ws + v;
         case SP_INPUT: return (void*)c.inputs[v];
-        case SP_OUTPUT: return c.outputs[v];
-        case SP_AUX: return (void*)c.aux[v];
+        case SP_OUTPUT: if ((int)v > c.max_out) c.max_out = (int)v; return c.outputs[v];
+        case SP_AUX: if ((int)v > c.max_aux) c.max_aux = (int)v; return (void*)c.aux[v];
     }
     return nullptr;
 }
@@ -383,6 +410,13 @@ int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** 
         p->prog_nops.push_back(blob[10 + 2 * i + 1]);
         if ((size_t)p->prog_start.back() > n_words) { delete p; return fail("plan blob: program offset out of range"); }
     }
+    p->graphs.resize(p->n_programs);
+    p->n_out.assign(p->n_programs, -1);
+    p->n_aux.assign(p->n_programs, -1);
+    // Opt-in: measured on B200 (gpurun_out/bench6*.json) a program replay costs ~30 us of launch latency more than
+    // the already asynchronous per-op launches it replaces (device-timed step +7 %), while saving host time per call
+    // (end-to-end +5..20 %).  ALAN_B200_GRAPH=1 turns it on for host-bound callers.
+    p->use_graphs = getenv("ALAN_B200_GRAPH") != nullptr;
     int dev = 0;
     p->sm_count = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) {
@@ -408,12 +442,107 @@ int alan_b200_program_launches(const alan_b200_plan* p, int program) {
     return n;
 }
 
+static int run_direct(const alan_b200_plan* p, int program, const Ctx& c) {
+    return p->dtype == 0 ? run_ops<float>(p, program, c, false, nullptr) : run_ops<double>(p, program, c, false, nullptr);
+}
+
+static int run_graphed(const alan_b200_plan* p, int program, const Ctx& c, const void* const* inputs, void* const* outputs,
+                       const void* const* aux, void* ws);
+
 static int run_generic(const alan_b200_plan* p, int program, const void* const* inputs, void* const* outputs,
                        const void* const* aux, void* ws, void* stream) {
     if (!p) return fail("null plan");
     if (program < 0 || program >= p->n_programs) return fail("program index out of range");
     Ctx c{inputs, outputs, aux, (char*)ws, (cudaStream_t)stream, p->sm_count};
-    return p->dtype == 0 ? run_ops<float>(p, program, c, false, nullptr) : run_ops<double>(p, program, c, false, nullptr);
+    if (!p->use_graphs) return run_direct(p, program, c);
+    const cudaStream_t user = (cudaStream_t)stream;
+    const bool legacy = user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread;
+    if (!legacy) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(user, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+            return run_direct(p, program, c);
+        }
+        return run_graphed(p, program, c, inputs, outputs, aux, ws);
+    }
+    {
+        std::lock_guard<std::mutex> g(p->mu);
+        if (!p->side) {
+            if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                p->side = nullptr;
+            }
+        }
+    }
+    if (!p->side) return run_direct(p, program, c);
+    cudaEventRecord(p->ev_in, user);
+    cudaStreamWaitEvent(p->side, p->ev_in, 0);
+    c.stream = p->side;
+    int rc = run_graphed(p, program, c, inputs, outputs, aux, ws);
+    cudaEventRecord(p->ev_out, p->side);
+    cudaStreamWaitEvent(user, p->ev_out, 0);
+    return rc;
+}
+
+static int run_graphed(const alan_b200_plan* p, int program, const Ctx& c, const void* const* inputs, void* const* outputs,
+                       const void* const* aux, void* ws) {
+    void* stream = (void*)c.stream;
+    std::unique_lock<std::mutex> lock(p->mu);
+    const int no = p->n_out[program], na = p->n_aux[program];
+    std::vector<const void*> key;
+    if (no >= 0 && na >= 0) {
+        key.reserve(2 + p->n_inputs + no + na);
+        key.push_back(ws); key.push_back(stream);
+        for (int i = 0; i < p->n_inputs; ++i) key.push_back(inputs[i]);
+        for (int i = 0; i < no; ++i) key.push_back(outputs[i]);
+        for (int i = 0; i < na; ++i) key.push_back(aux[i]);
+        for (auto& g : p->graphs[program]) {
+            if (g.key == key) {
+                g.last_use = ++p->tick;
+                cudaGraphExec_t exec = g.exec;
+                lock.unlock();
+                cudaError_t e = cudaGraphLaunch(exec, c.stream);
+                if (e != cudaSuccess) return fail(std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+                return 0;
+            }
+        }
+    }
+    // miss: capture this call's launches, instantiate, remember, launch
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        lock.unlock();
+        return run_direct(p, program, c);
+    }
+    int rc = run_direct(p, program, c);
+    cudaError_t e = cudaStreamEndCapture(c.stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess || !graph) { cudaGetLastError(); lock.unlock(); return run_direct(p, program, c); }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaGetLastError(); lock.unlock(); return run_direct(p, program, c); }
+    p->n_out[program] = c.max_out + 1;
+    p->n_aux[program] = c.max_aux + 1;
+    key.clear();
+    key.push_back(ws); key.push_back(stream);
+    for (int i = 0; i < p->n_inputs; ++i) key.push_back(inputs[i]);
+    for (int i = 0; i <= c.max_out; ++i) key.push_back(outputs[i]);
+    for (int i = 0; i <= c.max_aux; ++i) key.push_back(aux[i]);
+    auto& vec = p->graphs[program];
+    if (vec.size() >= 8) {                              // small LRU: training loops rebind a handful of buffers
+        size_t victim = 0;
+        for (size_t i = 1; i < vec.size(); ++i) if (vec[i].last_use < vec[victim].last_use) victim = i;
+        cudaGraphExecDestroy(vec[victim].exec);
+        vec.erase(vec.begin() + victim);
+    }
+    vec.push_back(GraphEntry{key, exec, ++p->tick});
+    lock.unlock();
+    e = cudaGraphLaunch(exec, c.stream);
+    if (e != cudaSuccess) return fail(std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+    return 0;
 }
 
 int alan_b200_profile(const alan_b200_plan* p, int program, const void* const* inputs, void* const* outputs,

@@ -9,10 +9,12 @@
 A step = one RWS iteration of the hot path on one batch of synthetic input: forward log-evidence
 + backward (gradients of every Q parameter) of the MovieLens-shaped model
 (/root/reference/examples/models/movielens/movielens.py:39-74) at K=30, d=18.
-Workloads (BASELINE.json configs): `cfg2` = 300 users x 5 films, `cfg5` = 10 000 users x 50 films with
-the user plate sharded across the ranks (replaces Split's sequential chunks).  The default workload is
-cfg5 at every N so that the 1/2/4/8-GPU numbers are the same job ("scaling": "strong"); the cfg2
-numbers (the >=50x target config) are measured in the same run at N=1 and reported under "cfg2".
+Workloads (BASELINE.json configs): `cfg2` = 300 users x 5 films, `cfg5` = 10 000 users x 50 films.  The
+user plate is sharded across the ranks (this replaces Split's sequential chunks): every GPU holds
+10 000 users of the same model ("scaling": "weak" -- N GPUs evaluate 10 000 N users; the only
+collectives are the all-reduce of the [K_mu, K_psi] tile and of the global-parameter gradients).
+`--scaling strong` keeps 10 000 users in total instead.  The cfg2 numbers (the >=50x target config) are
+measured in the same run at N=1 and reported under "cfg2".
 
 Unit of work ("cell") = one (plate element, K tuple) entry of a factor tensor the reference
 materialises:  W = M*K^3 (z) + M*N*K (obs) + M*K (Q of z) + K^2 + 4K.
@@ -49,8 +51,9 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return dict(hbm_gbs=p["hbm_gbs"], sm_max_mhz=p.get("sm_max_mhz", 1965.0), source="measured")
-    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p.get("bf16_tflops", 1590.0), sm_max_mhz=p.get("sm_max_mhz", 1965.0),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, sm_max_mhz=1965.0, source="fallback")
 
 
 # ------------------------------------------------------------------------------------------
@@ -189,6 +192,8 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
     from alan_b200.engine import Compiled, Runner
     dev = t.device(f"cuda:{local_rank}")
     t.cuda.set_device(dev)
+    if args.scaling == "weak" and world > 1:
+        cfg = dict(cfg, M=cfg["M"] * world, name=cfg["name"] + f"_x{world}_users")
     M = cfg["M"]
     per = (M + world - 1) // world
     lo, hi = rank * per, min(M, (rank + 1) * per)
@@ -273,10 +278,11 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
     launches = sum(run.dp.launches[:plan.n_fwd + plan.n_bwd])
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "users": cfg["M"], "films": cfg["N"], "d": cfg["d"], "K": cfg["K"],
-                   "cells_per_step": W, "parallelism": f"plate_1 sharded over {world} rank(s)",
+                   "cells_per_step": W, "users_per_gpu": hi - lo,
+                   "parallelism": f"plate_1 sharded over {world} rank(s)",
                    "l2": "256 MB buffer written between timed steps (L2 flush)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches * args.steps,
@@ -311,10 +317,24 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
             op = plan.programs[prog][j]
             m = op_model(op, 4)
             clk = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
-            fp32_peak = 148 * 128 * 2 * clk * 1e6 / 1e12                       # TFLOP/s at the clock seen under load
+            # pipe peaks measured on this pool's B200 (tools/microbench.cu, profiles/r01_microbench.txt):
+            # 121 FMA/clk/SM (FFMA and FFMA2), 15.9 ex2/clk/SM
+            fp32_peak = 148 * 121 * 2 * clk * 1e6 / 1e12                       # TFLOP/s at the clock seen under load
+            mufu_peak = 148 * 15.9 * clk * 1e6                                 # ex2 / s
             t_hbm = m["bytes"] / (pk["hbm_gbs"] * 1e9)
             t_fp = m["flops"] / (fp32_peak * 1e12)
-            if t_hbm >= t_fp:
+            tc_path = m["kind"] in ("FanLseOp", "FanLseBwdOp") and comp.dtype == t.float32 and \
+                not os.environ.get("ALAN_B200_NO_TC")
+            if tc_path:
+                # fan_lse on tcgen05 (csrc/fan_tc.cuh): fp32-accurate 3xTF32, block-diagonal constant operand.
+                # Algorithmic flops against the measured dense bf16 peak; the ceiling this formulation can reach
+                # is peak / 2 (tf32) / 3 (split) / 4 (block-diagonal zeros).
+                roof = dict(bound="tensor", achieved=m["flops"] / (top_ms * 1e-3) / 1e12, peak=pk["bf16_tflops"],
+                            unit="TFLOP/s")
+                roof["formulation_ceiling"] = pk["bf16_tflops"] / 24
+                roof["frac_of_formulation_ceiling"] = roof["achieved"] / roof["formulation_ceiling"]
+                roof["path"] = "tcgen05.mma kind::tf32, 3xTF32 split, A in TMEM (UTCHMMA / LDTM in SASS)"
+            elif t_hbm >= t_fp:
                 roof = dict(bound="hbm", achieved=m["bytes"] / (top_ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s")
             else:
                 roof = dict(bound="fp32", achieved=m["flops"] / (top_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s")
@@ -323,7 +343,10 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
                         share_of_step=top_ms / total, peak_source=pk["source"],
                         algorithmic_bytes=m["bytes"], algorithmic_flops=m["flops"],
                         hbm_frac=m["bytes"] / (top_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                        fp32_fma_frac=m["flops"] / (top_ms * 1e-3) / 1e12 / fp32_peak,
                         timing="per-op CUDA events on the launch stream, separate profiled pass, mean of %d" % reps)
+            if m["kind"] in ("FanLseOp", "FanLseBwdOp"):
+                roof["mufu_frac"] = m["points"] / (top_ms * 1e-3) / mufu_peak   # one ex2 per cell is the algorithmic minimum
             line["roofline"] = roof
             tops = sorted(acc.items(), key=lambda kv: -kv[1])[:6]
             line["top_ops"] = [dict(op=f"{op_model(plan.programs[p][k], 4)['kind']}:{op_model(plan.programs[p][k], 4)['tag']}",
@@ -370,6 +393,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=list(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--device-only", action="store_true",
                     help="skip the e2e / cfg2 / cpu legs (short command for ncu launch lists)")
@@ -387,7 +411,7 @@ def main():
         r = run_reference(args, cfg, iters=steps, warmup=min(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": cfg["name"], "users": cfg["M"], "films": cfg["N"], "d": cfg["d"], "K": cfg["K"]},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
