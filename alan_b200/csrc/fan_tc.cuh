@@ -49,6 +49,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin)
         if (spin > (1u << 26)) __trap();
 }
+#ifdef TC_DEBUG_SPIN
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
+#define MBAR_WAIT(bar, par, acc) mbar_wait_t(bar, par, acc)
+#else
+#define MBAR_WAIT(bar, par, acc) mbar_wait(bar, par)
+#endif
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -163,6 +173,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
     uint64_t* tfull = bars + 2 * TC_STAGES;                                // [TC_ACC]     MMA -> epilogue
     uint64_t* tempty = bars + 2 * TC_STAGES + TC_ACC;                      // [TC_ACC]     epilogue -> MMA
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 2 * TC_ACC);
+    float* xpose = (float*)(tmem_slot + 4);                                // adjoint: [8 epilogue warps][32][36]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float LS = 1.4426950408889634f;
@@ -188,7 +199,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], TC_BW * 32); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < TC_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        for (int a = 0; a < TC_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128 * TC_EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_MMA_WARP) {
@@ -200,6 +211,8 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    long long dbg0 = 0, dbg1 = 0, dbg2 = 0; (void)dbg0; (void)dbg1; (void)dbg2;
+    const long long dbg_t0 = clock64(); (void)dbg_t0;
 
     if (warp < 4) {
         // ---------------------------------------------------------------- A operand, once
@@ -246,69 +259,105 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
         // ---------------------------------------------------------------- epilogue (team = warp / 4)
         const int rs = warp & 3, f = lane, o_f = (int)p.o_f;
         // multi-index of rho = TC_RHO * tile + rs for this team's first tile, and its per-iteration step
+        // every team works on every supertile: team e takes the rho groups [e GPT, (e + 1) GPT), so an accumulator
+        // stage is held for GPT (not TC_G) row computations before it goes back to the MMA issuer
+        constexpr int GPT = TC_G / TC_EPI;
+        const int g0 = (warp >> 2) * GPT;
         TcIdx base, step, four;
-        base.set(TC_RHO * (blockIdx.x + (warp >> 2) * gridDim.x) + rs, geo);
-        step.set(TC_RHO * TC_EPI * gridDim.x, geo);
+        base.set(TC_RHO * blockIdx.x + 4 * g0 + rs, geo);
+        step.set(TC_RHO * gridDim.x, geo);
         four.set(4, geo);
-        for (unsigned it = warp >> 2; blockIdx.x + (i64)it * gridDim.x < n_tiles; it += TC_EPI) {
+        // offsets and (adjoint) the raw lse / gout values are fetched ONE supertile ahead: their global-load
+        // latency overlaps the previous supertile's work instead of sitting in front of every accumulator read
+        int n_ooff[GPT];
+        float n_lse[GPT], n_g[GPT];
+        auto fetch = [&](unsigned tile) {
+            TcIdx cur = base;
+#pragma unroll
+            for (int g = 0; g < GPT; ++g) {
+                const unsigned rho = TC_RHO * tile + 4 * (g0 + g) + rs;
+                const int o = cur.dot(geo.os);
+                n_ooff[g] = o;
+                n_lse[g] = INFINITY; n_g[g] = 0.f;                               // idle rows: weight 0
+                if (BWD && rho < n_rho && f < p.F) {
+                    n_lse[g] = p.lse[o + f * o_f];
+                    n_g[g] = p.gout[cur.dot(geo.gs) + f * geo.g_f];
+                }
+                cur.add(four, geo);
+            }
+            base.add(step, geo);
+        };
+        if (blockIdx.x < n_tiles) fetch(blockIdx.x);
+        for (unsigned it = 0; blockIdx.x + (i64)it * gridDim.x < n_tiles; ++it) {
             const unsigned tile = blockIdx.x + it * gridDim.x;
             const int a = it % TC_ACC;
             const uint32_t pa = (it / TC_ACC) & 1;
-            // output offsets of this thread's TC_G rho (warp-uniform) and, for the adjoint, lse / gout
-            int ooff[TC_G];
-            float lz[TC_G], gz[TC_G];
-            {
-                TcIdx cur = base;
+            int ooff[GPT];
+            float lz[GPT], gz[GPT];
 #pragma unroll
-                for (int g = 0; g < TC_G; ++g) {
-                    const unsigned rho = TC_RHO * tile + 4 * g + rs;
-                    const int o = cur.dot(geo.os);
-                    ooff[g] = o;
-                    lz[g] = 0.f; gz[g] = 0.f;
-                    if (BWD) {
-                        const bool live = rho < n_rho && f < p.F;
-                        lz[g] = live ? (p.lse[o + f * o_f] - p.cadd) * LS : INFINITY;     // idle rows: weight 0
-                        gz[g] = live ? p.gout[cur.dot(geo.gs) + f * geo.g_f] : 0.f;
-                    }
-                    cur.add(four, geo);
-                }
-                base.add(step, geo);
+            for (int g = 0; g < GPT; ++g) {
+                ooff[g] = n_ooff[g];
+                lz[g] = BWD ? (n_lse[g] - p.cadd) * LS : 0.f;
+                gz[g] = n_g[g];
             }
-            mbar_wait(&tfull[a], pa);
+            if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
+            MBAR_WAIT(&tfull[a], pa, dbg0);
             tc_fence_after();
 #pragma unroll
-            for (int g = 0; g < TC_G; ++g) {
-                const unsigned rho = TC_RHO * tile + 4 * g + rs;
+            for (int g = 0; g < GPT; ++g) {
+                const unsigned rho = TC_RHO * tile + 4 * (g0 + g) + rs;
                 uint32_t r[32];
-                TC_LD32(r, tmem + ((uint32_t)(32 * rs) << 16) + D_COL + TC_N * a + 32 * g);
+#ifdef TC_DEBUG_SPIN
+                const long long tA = clock64();
+#endif
+                TC_LD32(r, tmem + ((uint32_t)(32 * rs) << 16) + D_COL + TC_N * a + 32 * (g0 + g));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (g == TC_G - 1) { tc_fence_before(); mbar_arrive(&tempty[a]); }
+                if (g == GPT - 1) { tc_fence_before(); mbar_arrive(&tempty[a]); }
+#ifdef TC_DEBUG_SPIN
+                const long long tB = clock64(); dbg1 += tB - tA;
+#endif
                 if (!BWD) {
                     float m = __uint_as_float(r[0]);
 #pragma unroll
                     for (int k = 1; k < 32; ++k) m = fmaxf(m, __uint_as_float(r[k]));
-                    float sum = 0.f;
+                    // packed subtract / accumulate (add.f32x2): half the FADD issue slots around the 32 ex2
+                    const float2 nm2 = make_float2(-m, -m);
+                    float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) sum += FastExp<float>::ex(__uint_as_float(r[k]) - m);
+                    for (int k = 0; k < 32; k += 2) {
+                        const float2 d2 = __fadd2_rn(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), nm2);
+                        acc2 = __fadd2_rn(acc2, make_float2(FastExp<float>::ex(d2.x), FastExp<float>::ex(d2.y)));
+                    }
+                    const float sum = acc2.x + acc2.y;
                     if (rho < n_rho && f < p.F)
                         p.out[ooff[g] + f * o_f] = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + p.cadd;
                 } else {
-                    float wv[32];
+                    // weights of this (rho, f) row, then the sum over f (the 32 lanes of this warp) through a
+                    // per-warp shared-memory transpose: 8 STS.128 + 32 LDS per lane, fixed summation order
+                    const float2 nl2 = make_float2(-lz[g], -lz[g]), g2 = make_float2(gz[g], gz[g]);
+                    float* trow = xpose + (size_t)warp * (32 * 36);
+                    __syncwarp();
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) wv[k] = gz[g] * FastExp<float>::ex(__uint_as_float(r[k]) - lz[g]);
-                    // fixed-order butterfly reduce-scatter over the lanes (f): lane j ends with the sum for kappa = j
+                    for (int k = 0; k < 32; k += 4) {
+                        const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), nl2);
+                        const float2 d1 = __fadd2_rn(make_float2(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3])), nl2);
+                        const float2 e0 = __fmul2_rn(make_float2(FastExp<float>::ex(d0.x), FastExp<float>::ex(d0.y)), g2);
+                        const float2 e1 = __fmul2_rn(make_float2(FastExp<float>::ex(d1.x), FastExp<float>::ex(d1.y)), g2);
+                        *reinterpret_cast<float4*>(trow + lane * 36 + k) = make_float4(e0.x, e0.y, e1.x, e1.y);
+                    }
+                    __syncwarp();
+                    float wv[1];
+                    {
+                        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const bool up = (lane & off) != 0;
-                            const float send = up ? wv[i] : wv[i + off];
-                            const float mine = up ? wv[i + off] : wv[i];
-                            wv[i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
-                        }
+                        for (int q = 0; q < 32; q += 2) { a0 += trow[q * 36 + lane]; a1 += trow[(q + 1) * 36 + lane]; }
+                        wv[0] = a0 + a1;
                     }
                     if (rho < n_rho && lane < Kk) p.gS[(i64)rho * Kk + lane] = wv[0];
                 }
+#ifdef TC_DEBUG_SPIN
+                dbg2 += clock64() - tB;
+#endif
             }
         }
     } else if (warp == TC_MMA_WARP) {
@@ -318,8 +367,8 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
             for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const int s = it % TC_STAGES, a = it % TC_ACC;
                 const uint32_t ps = (it / TC_STAGES) & 1, pa = (it / TC_ACC) & 1;
-                mbar_wait(&full[s], ps);
-                mbar_wait(&tempty[a], pa ^ 1);
+                MBAR_WAIT(&full[s], ps, dbg0);
+                MBAR_WAIT(&tempty[a], pa ^ 1, dbg1);
                 tc_fence_after();
                 const uint32_t bhi = smem_u32(stage_base + (size_t)s * 2 * OPER), blo = bhi + OPER;
                 const uint32_t d = tmem + D_COL + TC_N * a;
@@ -375,18 +424,19 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
                 t[D] = b * LS;
                 t[D + 1] = 1.f;
             }
-            mbar_wait(&empty[s], ps ^ 1);
+            MBAR_WAIT(&empty[s], ps ^ 1, dbg0);
             if (kz < Kk) {                       // rows of rho >= n_rho are written as zeros: finite, masked later
                 float* bh = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER);
                 float* bl = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
+                    // the tensor core reads only the 19 TF32 bits of each word: the raw fp32 value IS the "hi" part
+                    // (truncated by the hardware) and lo = t - trunc(t) is its exact remainder
                     float4 h, l;
-                    uint32_t u;
-                    u = to_tf32(t[4 * c + 0]); h.x = __uint_as_float(u); l.x = t[4 * c + 0] - h.x;
-                    u = to_tf32(t[4 * c + 1]); h.y = __uint_as_float(u); l.y = t[4 * c + 1] - h.y;
-                    u = to_tf32(t[4 * c + 2]); h.z = __uint_as_float(u); l.z = t[4 * c + 2] - h.z;
-                    u = to_tf32(t[4 * c + 3]); h.w = __uint_as_float(u); l.w = t[4 * c + 3] - h.w;
+                    h.x = t[4 * c + 0]; l.x = h.x - __uint_as_float(__float_as_uint(h.x) & 0xFFFFE000u);
+                    h.y = t[4 * c + 1]; l.y = h.y - __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u);
+                    h.z = t[4 * c + 2]; l.z = h.z - __uint_as_float(__float_as_uint(h.z) & 0xFFFFE000u);
+                    h.w = t[4 * c + 3]; l.w = h.w - __uint_as_float(__float_as_uint(h.w) & 0xFFFFE000u);
                     const int off = ((rs * NC + c) * TC_N + 32 * g + kz) * 4;
                     *reinterpret_cast<float4*>(bh + off) = h;
                     *reinterpret_cast<float4*>(bl + off) = l;
@@ -397,6 +447,10 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
         }
     }
 
+#ifdef TC_DEBUG_SPIN
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1 || warp == TC_MMA_WARP + 6))
+        printf("bwd=%d warp %d total %lld wait0 %lld wait1/ldtm %lld compute %lld\n", (int)BWD, warp, clock64() - dbg_t0, dbg0, dbg1, dbg2);
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == TC_MMA_WARP) {
@@ -408,7 +462,8 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
 template <int D>
 static int launch_fan_lse_tc_D(const FanLseParams<float>& p, bool bwd, cudaStream_t stream, int sm_count) {
     constexpr int NC = (D + 2 + 3) / 4;
-    const size_t smem = (size_t)TC_STAGES * 2 * (4 * NC * TC_N * 16) + (2 * TC_STAGES + 2 * TC_ACC) * 8 + 16;
+    const size_t smem = (size_t)TC_STAGES * 2 * (4 * NC * TC_N * 16) + (2 * TC_STAGES + 2 * TC_ACC) * 8 + 16 +
+                        (bwd ? (size_t)4 * TC_EPI * 32 * 36 * 4 : 0);
     bool ev2 = (D % 2 == 0) && p.v_ev == 1 && p.l_ev == 1 && p.v_k % 2 == 0 && p.l_k % 2 == 0 &&
                ((uintptr_t)p.v % 8 == 0) && ((uintptr_t)p.l % 8 == 0);
     for (int k = 0; k < p.rd.nd && ev2; ++k) ev2 = (p.vstride[k] % 2 == 0) && (p.lstride[k] % 2 == 0);

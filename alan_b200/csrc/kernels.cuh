@@ -79,6 +79,15 @@ __global__ void __launch_bounds__(256) expr_fwd_kernel(const __grid_constant__ E
         unravel(o, p.d, 0, p.d.n_a, idx);
         for (int l = 0; l < p.n_leaves; ++l) base[l] = dot_stride(p.leaf[l], idx, 0, p.d.n_a);
         T sum = T(0);
+        if (N3 && p.d.nd - p.d.n_a == 1 && p.leaf[n3.nl[0]].mode == 0 && p.leaf[n3.nl[1]].mode == 0 && p.leaf[n3.nl[2]].mode == 0) {
+            // one summed event dim, plain leaves: walk it with three constant strides (no index decoding)
+            const int kd = p.d.n_a;
+            const T* pv = (const T*)p.leaf[n3.nl[0]].ptr + base[n3.nl[0]];
+            const T* pl = (const T*)p.leaf[n3.nl[1]].ptr + base[n3.nl[1]];
+            const T* ps = (const T*)p.leaf[n3.nl[2]].ptr + base[n3.nl[2]];
+            const i64 sv = p.leaf[n3.nl[0]].stride[kd], sl = p.leaf[n3.nl[1]].stride[kd], ss = p.leaf[n3.nl[2]].stride[kd];
+            for (i64 r = lane; r < p.n_red; r += nl) sum += normal_lp(pv[r * sv], pl[r * sl], ps[r * ss]);
+        } else
         for (i64 r = lane; r < p.n_red; r += nl) {
             unravel(r, p.d, p.d.n_a, p.d.nd, idx);
             if (N3) {
@@ -161,6 +170,24 @@ __global__ void __launch_bounds__(256) expr_bwd_kernel(const __grid_constant__ E
         if (live) {
             for (int l = 0; l < p.n_leaves; ++l) base[l] = dot_stride(p.leaf[l], idx, 0, p.d.n_a);
             i64 gbase = dot_stride(p.gout, idx, 0, p.d.n_a);
+            if (N3 && p.d.nd - p.d.n_a == 1 && p.leaf[n3.nl[0]].mode == 0 && p.leaf[n3.nl[1]].mode == 0 && p.leaf[n3.nl[2]].mode == 0) {
+                // one looped dim, plain leaves: constant strides, no index decoding
+                const int kd = p.d.n_a;
+                const T* pv = (const T*)p.leaf[n3.nl[0]].ptr + base[n3.nl[0]];
+                const T* pl = (const T*)p.leaf[n3.nl[1]].ptr + base[n3.nl[1]];
+                const T* ps = (const T*)p.leaf[n3.nl[2]].ptr + base[n3.nl[2]];
+                const T* pg = (const T*)p.gout.ptr + gbase;
+                const i64 sv = p.leaf[n3.nl[0]].stride[kd], sl = p.leaf[n3.nl[1]].stride[kd], ss = p.leaf[n3.nl[2]].stride[kd],
+                          sg = p.gout.stride[kd];
+                for (i64 j = s + (i64)lane * p.nsplit; j < p.n_loop; j += (i64)p.nsplit * nl) {
+                    const T sc = ps[j * ss], df = pv[j * sv] - pl[j * sl], iv = T(1) / (sc * sc);
+                    T g = T(0);
+                    if (tv) g -= df * iv;
+                    if (tl) g += df * iv;
+                    if (ts) g += (df * df * iv - T(1)) / sc;
+                    sum += g * pg[j * sg];
+                }
+            } else
             for (i64 j = s + (i64)lane * p.nsplit; j < p.n_loop; j += (i64)p.nsplit * nl) {
                 unravel(j, p.d, p.d.n_a, p.d.nd, idx);
                 if (tg.mode == 2 && idx[tg.mdim] != 0) continue;

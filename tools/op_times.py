@@ -3,7 +3,7 @@
 Profiling aid: prints a table, never a bench line.   python tools/op_times.py [cfg5|cfg2] [reps]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
     sys.path.insert(0, p)
 import torch as t
 import bench
@@ -11,12 +11,34 @@ from alan_b200.engine import Compiled, Runner
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg5"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-cfg = bench.WORKLOADS[name]
-P, Q, sample, ip, data, params = bench.make_problem(cfg, 0, cfg["M"])
-comp = Compiled(P, Q, sample, ip, data, grad_names=params)
-run = Runner(comp, "cuda:0")
-plan = comp.plan
-tensors = [x.cuda() for x in comp.canonical_inputs(sample, ip, data)]
+if name.startswith("radon"):
+    # cfg3: marginals of the radon-shaped model (grad w.r.t. zero source terms), default or scaled shape
+    import models, bench_configs as BC
+    from alan_b200 import model as M
+    from alan_b200.named import NT, from_torch_named
+    S, C, Z = (64, 32, 32) if name == "radon_big" else (7, 10, 10)
+    inp = models.radon_inputs(S=S, C=C, Z=Z)
+    P, Q = models.radon_model(M)
+    nt = lambda d: {k: from_torch_named(v) if any(n is not None for n in v.names) else NT(v, ()) for k, v in d.items()}
+    sample, ip, data = BC.radon_sample(S, C, Z, 10), {**nt(inp['inputs']), **nt(inp['params'])}, nt(inp['data'])
+    g2p, sizes = Q.groupvarname2platenames(), {**inp['platesizes']}
+    for v in sample.values():
+        sizes.update(v.named_sizes)
+    elf = {}
+    for grp in Q.groupvarnames():
+        axes = ('K_' + grp,) + tuple(g2p[grp])
+        elf[(grp,)] = NT(t.zeros([sizes[a] for a in axes]), axes)
+    comp = Compiled(P, Q, sample, ip, data, extra_log_factors=elf, grad_names=list(elf.keys()))
+    run = Runner(comp, "cuda:0")
+    plan = comp.plan
+    tensors = [x.cuda() for x in comp.canonical_inputs(sample, ip, data, elf)]
+else:
+    cfg = bench.WORKLOADS[name]
+    P, Q, sample, ip, data, params = bench.make_problem(cfg, 0, cfg["M"])
+    comp = Compiled(P, Q, sample, ip, data, grad_names=params)
+    run = Runner(comp, "cuda:0")
+    plan = comp.plan
+    tensors = [x.cuda() for x in comp.canonical_inputs(sample, ip, data)]
 flush = t.empty(64 * 1024 * 1024, dtype=t.float32, device="cuda")
 lp_d = t.empty((), dtype=comp.dtype, device="cuda")
 one = t.ones((), dtype=comp.dtype, device="cuda")
