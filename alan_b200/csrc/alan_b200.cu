@@ -44,6 +44,7 @@ struct alan_b200_plan {
     mutable std::vector<int> n_out, n_aux;          // per program, learnt on the first run (-1 = unknown)
     mutable unsigned long long tick = 0;
     bool use_graphs = true;
+    bool use_tc = true;            // fan_lse on tcgen05 where the shape allows (ALAN_B200_NO_TC=1 at plan creation: FFMA2 kernel)
     // graphs cannot be captured on / launched into the legacy default stream: calls that arrive on it are
     // forwarded to this private stream, ordered by a pair of events
     mutable cudaStream_t side = nullptr;
@@ -338,8 +339,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 }
                 int rc = -1;
                 if constexpr (std::is_same<T, float>::value) {
-                    static const bool no_tc = getenv("ALAN_B200_NO_TC") != nullptr;
-                    if (!no_tc && tc::fan_lse_tc_supported(p, D)) rc = tc::launch_fan_lse_tc(p, D, bwd != 0, c.stream, c.sm_count);
+                    if (plan->use_tc && tc::fan_lse_tc_supported(p, D)) rc = tc::launch_fan_lse_tc(p, D, bwd != 0, c.stream, c.sm_count);
                 }
                 if (rc < 0) rc = launch_fan_lse<T>(p, D, bwd != 0, c.stream, c.sm_count);
                 if (rc) return fail(rc == 1 ? "fan_lse: unsupported event extent" : rc == 2 ? "fan_lse: tile does not fit shared memory" : "fan_lse: strides exceed 32-bit tile addressing");
@@ -417,6 +417,7 @@ int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** 
     // the already asynchronous per-op launches it replaces (device-timed step +7 %), while saving host time per call
     // (end-to-end +5..20 %).  ALAN_B200_GRAPH=1 turns it on for host-bound callers.
     p->use_graphs = getenv("ALAN_B200_GRAPH") != nullptr;
+    p->use_tc = getenv("ALAN_B200_NO_TC") == nullptr;
     int dev = 0;
     p->sm_count = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) {

@@ -340,3 +340,84 @@ def test_fused_kernels_match_generic_kernels_and_oracle(dtype, M_, N_, K):
     for k, r in zip(('z', 'mu_z', 'psi_z'), rg):
         pt = comp.plan.input_pts[k]
         assert rel_err(_as(pt.axes, grads[k].cpu(), sg[k].axes), r) < 30 * tl, k
+
+
+# ------------------------------------------------------------------------------ tcgen05 path vs FFMA2 path
+def _movielens_case(M_, N_, K, d, seed):
+    P, Q = models.movielens_model(M, d=d)
+    inp = models.movielens_inputs(M=M_, N=N_, d=d, seed=seed, dtype=t.float32)
+    inp['event_shapes'] = {'mu_z': (d,), 'psi_z': (d,), 'z': (d,)}
+    sample = _random_sample(P, Q, inp, K, t.float32, seed + 1)
+    ip = {**_nt(inp['inputs']), **_nt(inp['params'])}
+    return P, Q, sample, ip, _nt(inp['data']), list(inp['params'])
+
+
+def _run_paths(P, Q, sample, ip, data, names, monkeypatch):
+    """(lp, grads) with fan_lse on the tensor cores and on the FFMA2 kernel (ALAN_B200_NO_TC at plan creation)."""
+    Compiled, Runner = _engine()
+    comp = Compiled(P, Q, sample, ip, data, grad_names=names)
+    assert 'FanLseOp' in [type(op).__name__ for prog in comp.plan.programs for op in prog]
+    out = {}
+    for tc in (True, False):
+        if tc:
+            monkeypatch.delenv("ALAN_B200_NO_TC", raising=False)
+        else:
+            monkeypatch.setenv("ALAN_B200_NO_TC", "1")
+        run = Runner(comp, "cuda:0")
+        tensors = run.device_inputs(sample, ip, data)
+        lp = run.forward_raw(tensors)
+        grads = run.backward_raw(tensors)
+        out[tc] = (lp.clone(), {k: v.clone() for k, v in grads.items()}, run, tensors)
+    monkeypatch.delenv("ALAN_B200_NO_TC", raising=False)
+    return out
+
+
+@pytest.mark.parametrize("M_,N_,K,d", [(20, 3, 8, 18), (33, 4, 17, 18), (64, 5, 30, 18), (40, 3, 32, 18),
+                                         (50, 2, 12, 8), (37, 2, 9, 2), (25, 3, 30, 16)])
+def test_tcgen05_fan_lse_matches_ffma_kernel(M_, N_, K, d, monkeypatch):
+    """csrc/fan_tc.cuh (3xTF32 tcgen05.mma, accumulator in TMEM) against csrc/fused.cuh fan_lse2 (fp32 FFMA2) on
+    identical inputs: ragged tiles (n_rho not a multiple of 16), K < 32 padding columns, K = 32, several D."""
+    P, Q, sample, ip, data, names = _movielens_case(M_, N_, K, d, seed=21)
+    out = _run_paths(P, Q, sample, ip, data, names, monkeypatch)
+    (lp_tc, g_tc, _, _), (lp_ff, g_ff, _, _) = out[True], out[False]
+    assert rel_err(lp_tc.cpu(), lp_ff.cpu()) < 2e-6
+    for k in names:
+        assert rel_err(g_tc[k].cpu(), g_ff[k].cpu()) < 1e-4, k
+
+
+def test_full_size_cfg5_properties(monkeypatch):
+    """BASELINE cfg-5 at its full size (10 000 users x 50 films, d=18, K=30), where the oracle is too slow:
+    size-independent properties instead -- (1) the tensor-core and FFMA2 paths agree, (2) runs are bit-
+    reproducible, (3) the log-evidence of the full problem equals the top-level contraction of the SUM of the
+    plate tiles of two half problems (plate elements are conditionally independent: logpq.py:149-153)."""
+    import bench
+    Compiled, Runner = _engine()
+    cfg = bench.WORKLOADS["cfg5"]
+    P, Q, sample, ip, data, names = bench.make_problem(cfg, 0, cfg["M"])
+    out = _run_paths(P, Q, sample, ip, data, names, monkeypatch)
+    (lp_tc, g_tc, run, tensors), (lp_ff, g_ff, _, _) = out[True], out[False]
+    assert t.isfinite(lp_tc)
+    assert rel_err(lp_tc.cpu(), lp_ff.cpu()) < 1e-6
+    for k in names:
+        assert rel_err(g_tc[k].cpu(), g_ff[k].cpu()) < 1e-4, k
+    lp2 = run.forward_raw(tensors)
+    g2 = run.backward_raw(tensors)
+    assert t.equal(lp2, lp_tc) and all(t.equal(g2[k], g_tc[k]) for k in names)
+    # two halves, tiles summed by hand (what the cross-GPU all-reduce does)
+    tiles = []
+    halves = []
+    for lo, hi in ((0, 5000), (5000, 10000)):
+        Ph, Qh, sh, iph, dh, _ = bench.make_problem(cfg, lo, hi)
+        comp = Compiled(Ph, Qh, sh, iph, dh, grad_names=names, shard_plate='plate_1', world_size=2)
+        r = Runner(comp, "cuda:0")
+        tens = r.device_inputs(sh, iph, dh)
+        lp_dummy = t.empty((), device="cuda:0")
+        r.dp.fwd(0, tens, lp_dummy)
+        tiles.append(r.dp.ws_view(comp.plan.allreduce, t.float32).clone())
+        halves.append((r, tens))
+    total = tiles[0] + tiles[1]
+    r, tens = halves[0]
+    r.dp.ws_view(r.comp.plan.allreduce, t.float32).copy_(total)
+    lp_sum = t.empty((), device="cuda:0")
+    r.dp.fwd(1, tens, lp_sum)
+    assert rel_err(lp_sum.cpu(), lp_tc.cpu()) < 1e-6
