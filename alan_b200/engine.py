@@ -240,3 +240,113 @@ class Runner:
     def elbo(self, tensors):
         """Differentiable log-evidence estimate on canonical device tensors."""
         return _LogPQFunction.apply(self, *tensors)
+
+
+class StreamedRunner:
+    """Host-buffer entry point: forward + backward with the outermost plate streamed through the GPU in
+    `chunks` contiguous blocks, so that the host->device copy of block c+1 overlaps the kernels of block c.
+
+    This is the reference's `Split(plate, size)` (src/alan/Split.py:44-130, logpq.py:43-57) done the B200 way:
+    the blocks are the same conditionally independent shards the multi-GPU path uses (`shard_plate`), here
+    laid side by side in one GPU's memory.  Each block runs forward segment 0 as soon as its inputs have
+    landed; the `[K_parents]` tiles are summed (what the all-reduce does across GPUs); segment 1 and the
+    backward run per block; per-element gradients are written straight into slices of the full-size
+    outputs, global-parameter gradients are summed over the blocks.
+    """
+    def __init__(self, P, Q, sample, inputs_params, data, grad_names, stream_plate, chunks, device=None):
+        self.plate, self.C = stream_plate, int(chunks)
+        full = {}
+        for d in (sample, inputs_params or {}, data or {}):
+            full.update(d)
+        M = None
+        for v in full.values():
+            if stream_plate in v.axes:
+                M = v.named_sizes[stream_plate]
+        if M is None:
+            raise Exception(f"no input carries the plate {stream_plate}")
+        if M % self.C:
+            raise Exception(f"plate {stream_plate} of size {M} does not split into {self.C} equal blocks")
+        self.M, self.m = M, M // self.C
+
+        def head(d):
+            out = {}
+            for k, v in (d or {}).items():
+                if stream_plate in v.axes:
+                    ax = v.axes.index(stream_plate)
+                    out[k] = NT(v.t.narrow(ax, 0, self.m), v.axes)
+                else:
+                    out[k] = v
+            return out
+        self.comp = Compiled(P, Q, head(sample), head(inputs_params), head(data), grad_names=list(grad_names),
+                             shard_plate=stream_plate, world_size=self.C)
+        plan = self.comp.plan
+        if plan.n_fwd != 2:
+            raise Exception(f"plate {stream_plate} is not a shardable top-level plate of this model")
+        self.runs = [Runner(self.comp, device) for _ in range(self.C)]
+        self.device = self.runs[0].device
+        self.dtype = self.comp.dtype
+        # which plan inputs carry the plate (canonical layout: plates lead, so a block is a contiguous slab)
+        self.carries = []
+        for name in plan.input_names:
+            pt = plan.input_pts[name]
+            if stream_plate in pt.axes and pt.axes[0] != stream_plate:
+                raise Exception(f"{name}: the streamed plate must be the outermost axis")
+            self.carries.append(stream_plate in pt.axes)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.events = [torch.cuda.Event() for _ in range(self.C)]
+        self.dev = None
+        self.one = torch.ones((), dtype=self.dtype, device=self.device)
+
+    def pin(self, sample, inputs_params, data):
+        """Canonical FULL-SIZE host tensors in pinned memory (what `step` consumes), in plan input order."""
+        return [x.pin_memory() for x in self.comp.canonical_inputs(sample, inputs_params, data)]
+
+    def step(self, host):
+        """host: full-size canonical pinned tensors (see `pin`).  Returns (lp, {name: grad}) on the device;
+        gradients of per-element parameters are full size."""
+        plan = self.comp.plan
+        cur = torch.cuda.current_stream(self.device)
+        if self.dev is None:
+            self.dev = [torch.empty_like(h, device=self.device) for h in host]
+            self.grads = {n: torch.empty(([self.M] + list(plan.input_pts[n].shape[1:])) if self.plate in plan.input_pts[n].axes
+                                         else list(plan.input_pts[n].shape), dtype=self.dtype, device=self.device)
+                          for n in plan.grad_inputs}
+        self.copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self.copy_stream):
+            for c in range(self.C):
+                for h, d, carries in zip(host, self.dev, self.carries):
+                    if carries:
+                        d[c * self.m:(c + 1) * self.m].copy_(h[c * self.m:(c + 1) * self.m], non_blocking=True)
+                    elif c == 0:
+                        d.copy_(h, non_blocking=True)
+                self.events[c].record(self.copy_stream)
+        tens = [[d[c * self.m:(c + 1) * self.m] if carries else d for d, carries in zip(self.dev, self.carries)]
+                for c in range(self.C)]
+        lp = torch.empty((), dtype=self.dtype, device=self.device)
+        for c, run in enumerate(self.runs):
+            cur.wait_event(self.events[c])
+            run.dp.fwd(0, tens[c], lp)
+        tiles = [run.dp.ws_view(plan.allreduce, self.dtype) for run in self.runs]
+        total = tiles[0].clone()
+        for tl in tiles[1:]:
+            total += tl
+        for tl in tiles:
+            tl.copy_(total)
+        for c, run in enumerate(self.runs):
+            run.dp.fwd(1, tens[c], lp)
+        gsum = {n: None for n in plan.global_grads}
+        for c, run in enumerate(self.runs):
+            outs = []
+            for n in plan.grad_inputs:
+                if n in gsum:
+                    outs.append(torch.empty(plan.input_pts[n].shape, dtype=self.dtype, device=self.device))
+                else:
+                    outs.append(self.grads[n][c * self.m:(c + 1) * self.m])
+            for seg in range(plan.n_bwd):
+                run.dp.bwd(seg, tens[c], self.one, outs)
+            for n, o in zip(plan.grad_inputs, outs):
+                if n in gsum:
+                    gsum[n] = o if gsum[n] is None else gsum[n] + o
+        for n, g in gsum.items():
+            self.grads[n].copy_(g)
+        return lp, self.grads

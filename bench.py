@@ -246,19 +246,28 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
                           "gpu_launches": sum(run.dp.launches[:plan.n_fwd + plan.n_bwd]) * args.steps,
                           "note": "device-only short run (profiling aid), not a bench line"}))
         sys.exit(0)
-    # ---- e2e: host (pinned) buffers -> device -> fwd+bwd -> lp and gradients back to the host
+    # ---- e2e: host (pinned) buffers -> device -> fwd+bwd -> lp and gradients back to the host, through the
+    # public host-buffer entry point engine.StreamedRunner (the user plate streamed in `--chunks` blocks so that
+    # the H2D copy of a block overlaps the kernels of the previous one); --chunks 1 = copy everything, then run
     h2d = sum(x.numel() * x.element_size() for x in host)
     gout_host = None
     ev2 = [(t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     lp_host = t.empty((), dtype=comp.dtype).pin_memory()
+    streamed = None
+    if args.chunks > 1 and world == 1 and (hi - lo) % args.chunks == 0:
+        from alan_b200.engine import StreamedRunner
+        streamed = StreamedRunner(P, Q, sample, ip, data, params, 'plate_1', args.chunks, device=dev)
     for i in range(args.warmup + args.steps):
         k = i - args.warmup
         if k >= 0:
             flush.fill_(1.0)
             ev2[k][0].record()
-        for dst, src in zip(tensors, host):
-            dst.copy_(src, non_blocking=True)
-        lp, grads = step()
+        if streamed is not None:
+            lp, grads = streamed.step(host)
+        else:
+            for dst, src in zip(tensors, host):
+                dst.copy_(src, non_blocking=True)
+            lp, grads = step()
         lp_host.copy_(lp, non_blocking=True)
         if gout_host is None:
             gout_host = {n: t.empty(g.shape, dtype=g.dtype).pin_memory() for n, g in grads.items()}
@@ -284,7 +293,9 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
                    "cells_per_step": W, "users_per_gpu": hi - lo,
                    "parallelism": f"plate_1 sharded over {world} rank(s)",
                    "l2": "256 MB buffer written between timed steps (L2 flush)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": (f"engine.StreamedRunner.step, plate_1 in {args.chunks} blocks (H2D of block c+1 overlaps block c)"
+                        if streamed is not None else "H2D copies, Runner.forward_raw + backward_raw, D2H")},
         "gpu_launches": launches * args.steps,
         "lp": float(lp_host),
         "wall_s_timed_region": wall,
@@ -394,6 +405,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=list(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--chunks", type=int, default=1,
+                    help="blocks of the user plate in the e2e (host buffer) path; >1 streams them through "
+                         "engine.StreamedRunner (measured slower on B200 today: per-block host work dominates)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--device-only", action="store_true",
                     help="skip the e2e / cfg2 / cpu legs (short command for ncu launch lists)")

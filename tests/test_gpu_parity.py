@@ -421,3 +421,27 @@ def test_full_size_cfg5_properties(monkeypatch):
     lp_sum = t.empty((), device="cuda:0")
     r.dp.fwd(1, tens, lp_sum)
     assert rel_err(lp_sum.cpu(), lp_tc.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("chunks", [2, 4])
+def test_streamed_runner_matches_single_pass(chunks):
+    """engine.StreamedRunner (the plate streamed in blocks with copy/compute overlap = Split done on the GPU)
+    against one pass over the whole plate: same log-evidence and gradients (tests/test_problem_vs_itself.py
+    test_compstrat_* make the same comparison between the reference's Split and no_checkpoint)."""
+    from alan_b200.engine import StreamedRunner
+    Compiled, Runner = _engine()
+    P, Q, sample, ip, data, names = _movielens_case(64, 5, 30, 18, seed=31)
+    comp = Compiled(P, Q, sample, ip, data, grad_names=names)
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(sample, ip, data)
+    lp = run.forward_raw(tensors)
+    grads = run.backward_raw(tensors)
+    sr = StreamedRunner(P, Q, sample, ip, data, names, 'plate_1', chunks, device="cuda:0")
+    host = sr.pin(sample, ip, data)
+    for _ in range(2):                       # second call reuses the device buffers
+        lp_s, grads_s = sr.step(host)
+    assert rel_err(lp_s.cpu(), lp.cpu()) < 1e-6
+    for k in names:
+        assert rel_err(grads_s[k].cpu().reshape(-1), grads[k].cpu().reshape(-1)) < 1e-5, k
+    with pytest.raises(Exception, match="equal blocks"):
+        StreamedRunner(P, Q, sample, ip, data, names, 'plate_1', 7, device="cuda:0")
