@@ -111,9 +111,49 @@ __global__ void __launch_bounds__(256) expr_fwd_kernel(const __grid_constant__ E
     }
 }
 
+// Large scalar-event expressions (nothing summed, plain leaves): each thread owns B consecutive cells of the
+// innermost output dim, decodes their common outer index once and interprets every VM instruction once for
+// the whole batch (vm_eval_batch).
+template <typename T, int B>
+__global__ void __launch_bounds__(256) expr_fwd_batch_kernel(const __grid_constant__ ExprParams<T> p) {
+    T reg[AB_NREG][B];
+    T lv[AB_MAXL][B];
+    int idx[AB_MAXD];
+    const int kin = p.d.n_a - 1;                      // innermost kept dim; its extent is a multiple of B
+    const i64 n_groups = p.n_out / B;
+    for (i64 gidx = (i64)blockIdx.x * blockDim.x + threadIdx.x; gidx < n_groups; gidx += (i64)gridDim.x * blockDim.x) {
+        const i64 o = gidx * B;
+        unravel(o, p.d, 0, p.d.n_a, idx);
+        for (int l = 0; l < p.n_leaves; ++l) {
+            const T* ptr = (const T*)p.leaf[l].ptr + dot_stride(p.leaf[l], idx, 0, p.d.n_a);
+            const i64 st = p.leaf[l].stride[kin];
+#pragma unroll
+            for (int q = 0; q < B; ++q) lv[l][q] = ptr[q * st];
+        }
+        vm_eval_batch<T, B>(p.prog, lv, reg);
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+            const T v = p.scale * reg[p.prog.res][q];
+            p.out[o + q] = p.acc ? p.out[o + q] + v : v;
+        }
+    }
+}
+
 template <typename T>
 static void launch_expr_fwd(const ExprParams<T>& p, cudaStream_t stream, int sm_count) {
     const Normal3 n3 = detect_normal3(p.prog);
+    if (!n3.on && p.n_red == 1 && p.d.n_a >= 1 && p.n_out >= (1 << 16)) {
+        bool plain = true;
+        for (int l = 0; l < p.n_leaves; ++l) plain = plain && p.leaf[l].mode == 0;
+        const int inner = p.d.size[p.d.n_a - 1];
+        if (plain) {
+            const i64 cap = (i64)sm_count * 8;
+#define AB_BATCH(BB) if (inner % BB == 0) { i64 g = (p.n_out / BB + 255) / 256; \
+                expr_fwd_batch_kernel<T, BB><<<(int)(g > cap ? cap : g), 256, 0, stream>>>(p); return; }
+            AB_BATCH(8) AB_BATCH(5) AB_BATCH(4) AB_BATCH(3) AB_BATCH(2)
+#undef AB_BATCH
+        }
+    }
     const bool warp = p.n_out < 16384 && p.n_red >= 8;
     i64 threads = p.n_out * (warp ? 32 : 1);
     i64 g = (threads + 255) / 256, cap = (i64)sm_count * 8;

@@ -130,6 +130,67 @@ __device__ __forceinline__ T vm_eval(const VMProg<T>& P, const T* leaf, T* reg) 
     return reg[P.res];
 }
 
+// Batched interpreter: one decode + one dispatch per VM instruction for B iteration points (the B consecutive
+// cells of the innermost output dim a thread owns).  Instruction decode and the switch are the dominant cost of
+// the scalar interpreter, so large factor expressions (radon's K^4 regression likelihood, Timeseries transitions)
+// run several times faster here; arithmetic per point is identical to vm_eval (same expressions, same order).
+#define VMB(EXPR) { _Pragma("unroll") for (int q = 0; q < B; ++q) { const T a = A[q], b = Bq[q], c = Cq[q], d = Dq[q]; (void)a; (void)b; (void)c; (void)d; Y[q] = (EXPR); } } break
+template <typename T, int B>
+__device__ __forceinline__ void vm_eval_batch(const VMProg<T>& P, const T (*leaf)[B], T (*reg)[B]) {
+#pragma unroll 1
+    for (int i = 0; i < P.n_instr; ++i) {
+        const unsigned w0 = P.ins[i][0], w1 = P.ins[i][1];
+        const int op = w0 & 0xff, dst = (w0 >> 8) & 0xff, ia = (w0 >> 16) & 0xff, ib = (w0 >> 24) & 0xff;
+        const int ic = w1 & 0xff, id = (w1 >> 8) & 0xff;
+        const T* A = reg[ia < AB_NREG ? ia : 0];
+        const T* Bq = reg[ib < AB_NREG ? ib : 0];
+        const T* Cq = reg[ic < AB_NREG ? ic : 0];
+        const T* Dq = reg[id < AB_NREG ? id : 0];
+        T Y[B];
+        switch (op) {
+            case V_LOAD: { _Pragma("unroll") for (int q = 0; q < B; ++q) Y[q] = leaf[ia][q]; } break;
+            case V_CONST: { _Pragma("unroll") for (int q = 0; q < B; ++q) Y[q] = P.consts[ia]; } break;
+            case V_ADD: VMB(a + b);
+            case V_SUB: VMB(a - b);
+            case V_MUL: VMB(a * b);
+            case V_DIV: VMB(a / b);
+            case V_NEG: VMB(-a);
+            case V_EXP: VMB(ab_exp(a));
+            case V_LOG: VMB(ab_log(a));
+            case V_SIGMOID: VMB(ab_sigmoid(a));
+            case V_SQUARE: VMB(a * a);
+            case V_SQRT: VMB(ab_sqrt(a));
+            case V_RECIP: VMB(T(1) / a);
+            case V_SOFTPLUS: VMB(ab_softplus(a));
+            case V_TANH: VMB(ab_tanh(a));
+            case V_ABS: VMB(ab_abs(a));
+            case V_LOG1P: VMB(ab_log1p(a));
+            case V_POW: VMB(ab_pow(a, b));
+            case V_LGAMMA: VMB(ab_lgamma(a));
+            case V_MOV: VMB(a);
+            case V_NORMAL: VMB(normal_lp(a, b, c));
+            case V_BERN_LOGITS: VMB(bern_logits_lp(a, b));
+            case V_BERN_PROBS: VMB(bern_logits_lp(a, probs_to_logits(b)));
+            case V_LOGNORMAL: VMB(normal_lp(ab_log(a), b, c) - ab_log(a));
+            case V_LAPLACE: VMB(-ab_log(T(2) * c) - ab_abs(a - b) / c);
+            case V_EXPONENTIAL: VMB(ab_log(b) - b * a);
+            case V_GAMMA: VMB(ab_xlogy(b, c) + ab_xlogy(b - T(1), a) - c * a - ab_lgamma(b));
+            case V_BETA: VMB(ab_xlogy(b - T(1), a) + ab_xlogy(c - T(1), T(1) - a) + ab_lgamma(b + c) - ab_lgamma(b) - ab_lgamma(c));
+            case V_POISSON: VMB(ab_xlogy(a, b) - b - ab_lgamma(a + T(1)));
+            case V_CAUCHY: VMB(-T(LOG_PI) - ab_log(c) - ab_log1p(((a - b) / c) * ((a - b) / c)));
+            case V_HALFNORMAL: VMB((a >= T(0)) ? normal_lp(a, T(0), b) + T(LOG_2) : neg_inf<T>());
+            case V_UNIFORM: VMB((b <= a && c > a) ? -ab_log(c - b) : neg_inf<T>());
+            case V_STUDENTT: VMB(-T(0.5) * (b + T(1)) * ab_log1p(((a - c) / d) * ((a - c) / d) / b)
+                                 - (ab_log(d) + T(0.5) * ab_log(b) + T(0.5 * LOG_PI) + ab_lgamma(T(0.5) * b)
+                                    - ab_lgamma(T(0.5) * (b + T(1)))));
+            default: { _Pragma("unroll") for (int q = 0; q < B; ++q) Y[q] = T(0); } break;
+        }
+#pragma unroll
+        for (int q = 0; q < B; ++q) reg[dst][q] = Y[q];
+    }
+}
+#undef VMB
+
 // Reverse sweep.  reg[] must hold the forward values.  Returns d(result)/d(leaf `target`)
 // (sum over every LOAD of that leaf).  adj[] is scratch of AB_NREG entries.
 template <typename T>
