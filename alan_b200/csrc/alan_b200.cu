@@ -44,6 +44,7 @@ struct alan_b200_plan {
     mutable std::vector<int> n_out, n_aux;          // per program, learnt on the first run (-1 = unknown)
     mutable unsigned long long tick = 0;
     bool use_graphs = true;
+    bool use_seq = false;          // run consecutive small ops as one launch (ALAN_B200_SEQ=1 at plan creation: on)
     bool use_tc = true;            // fan_lse on tcgen05 where the shape allows (ALAN_B200_NO_TC=1 at plan creation: FFMA2 kernel)
     // graphs cannot be captured on / launched into the legacy default stream: calls that arrive on it are
     // forwarded to this private stream, ordered by a pair of events
@@ -79,9 +80,9 @@ static void* tref(Reader& r, const Ctx& c) {
     i64 v = r.i64v();
     switch (space) {
         case SP_WS: return c.ws + v;
-        case SP_INPUT: return (void*)c.inputs[v];
-        case SP_OUTPUT: if ((int)v > c.max_out) c.max_out = (int)v; return c.outputs[v];
-        case SP_AUX: if ((int)v > c.max_aux) c.max_aux = (int)v; return (void*)c.aux[v];
+        case SP_INPUT: return c.inputs ? (void*)c.inputs[v] : nullptr;
+        case SP_OUTPUT: if ((int)v > c.max_out) c.max_out = (int)v; return c.outputs ? c.outputs[v] : nullptr;
+        case SP_AUX: if ((int)v > c.max_aux) c.max_aux = (int)v; return c.aux ? (void*)c.aux[v] : nullptr;
     }
     return nullptr;
 }
@@ -127,12 +128,23 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                    std::vector<cudaEvent_t>* events = nullptr) {
     Reader r{plan->blob.data() + plan->prog_start[program]};
     int nl = 0;
+    // consecutive small ops are collected and run by one launch of small_seq_kernel (kernels.cuh)
+    const bool batching = plan->use_seq && events == nullptr;
+    SeqParams<T> seq;
+    auto flush = [&]() {
+        if (seq.n == 0) return;
+        if (count_only) ++nl;
+        else small_seq_kernel<T><<<1, 1024, 0, c.stream>>>(seq);
+        seq.n = 0;
+    };
     for (int op_i = 0; op_i < plan->prog_nops[program]; ++op_i) {
         const int32_t* op_begin = r.p;
         if (events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c.stream); events->push_back(e); }
         int code = r.i32();
         int nwords = r.i32();
-        if (count_only) {
+        const bool seqable = code == OP_FILL || code == OP_EXPR || code == OP_EXPR_BWD || code == OP_REDUCE;
+        if (!seqable) flush();
+        if (count_only && !seqable) {
             if (code == OP_CHAIN || code == OP_CHAIN_BWD) {
                 r.p = op_begin + 2; Reader q = r;
                 // skip trefs to read T
@@ -149,6 +161,14 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
             case OP_FILL: {
                 void* dst = tref(r, c);
                 i64 nbytes = r.i64v();
+                if (batching && nbytes <= 4 * AB_SEQ_POINTS && nbytes % 4 == 0) {
+                    if (seq.n == AB_SEQ_MAX) flush();
+                    SeqOp<T>& o = seq.op[seq.n++];
+                    o.kind = SK_FILL; o.warp = 0; o.f.ptr = dst; o.f.nbytes = nbytes;
+                    break;
+                }
+                flush();
+                if (count_only) break;               // memsets are not counted as kernel launches
                 cudaMemsetAsync(dst, 0, (size_t)nbytes, c.stream);
                 break;
             }
@@ -168,6 +188,14 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 p.n_leaves = r.i32();
                 for (int l = 0; l < p.n_leaves; ++l) read_opnd(r, c, p.leaf[l], p.d.nd, true);
                 read_prog(r, p.prog);
+                if (batching && p.n_out * p.n_red <= AB_SEQ_POINTS) {
+                    if (seq.n == AB_SEQ_MAX) flush();
+                    SeqOp<T>& o = seq.op[seq.n++];
+                    o.kind = SK_EXPR; o.warp = (p.n_red >= 8) ? 1 : 0; o.n3 = detect_normal3(p.prog); o.e = p;
+                    break;
+                }
+                flush();
+                if (count_only) { ++nl; break; }
                 launch_expr_fwd<T>(p, c.stream, c.sm_count);
                 break;
             }
@@ -183,6 +211,14 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 p.n_leaves = r.i32();
                 for (int l = 0; l < p.n_leaves; ++l) read_opnd(r, c, p.leaf[l], p.d.nd, true);
                 read_prog(r, p.prog);
+                if (batching && p.n_kept * p.n_loop <= AB_SEQ_POINTS) {
+                    if (seq.n == AB_SEQ_MAX) flush();
+                    SeqOp<T>& o = seq.op[seq.n++];
+                    o.kind = SK_EXPR_BWD; o.warp = (p.n_loop / p.nsplit >= 8) ? 1 : 0; o.n3 = detect_normal3(p.prog); o.b = p;
+                    break;
+                }
+                flush();
+                if (count_only) { ++nl; break; }
                 launch_expr_bwd<T>(p, c.stream, c.sm_count);
                 break;
             }
@@ -205,6 +241,14 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                     read_opnd(r, c, p.lse, p.d.nd, false);
                     read_opnd(r, c, p.gout, p.d.nd, false);
                 }
+                if (batching && p.n_out * p.n_red <= AB_SEQ_POINTS) {
+                    if (seq.n == AB_SEQ_MAX) flush();
+                    SeqOp<T>& o = seq.op[seq.n++];
+                    o.kind = SK_REDUCE; o.warp = reduce_uses_warps(p, thread_hint != 0) ? 1 : 0; o.r = p;
+                    break;
+                }
+                flush();
+                if (count_only) { ++nl; break; }
                 launch_reduce<T>(p, thread_hint != 0, c.stream, c.sm_count);
                 break;
             }
@@ -376,6 +420,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
             return fail("blob/executor mismatch in op " + std::to_string(op_i) + " (code " + std::to_string(code) +
                         "): consumed " + std::to_string((long)(r.p - op_begin)) + " of " + std::to_string(nwords) + " words");
     }
+    flush();
     if (events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c.stream); events->push_back(e); }
     if (launches) *launches = nl;
     if (!count_only) {
@@ -418,6 +463,9 @@ int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** 
     // (end-to-end +5..20 %).  ALAN_B200_GRAPH=1 turns it on for host-bound callers.
     p->use_graphs = getenv("ALAN_B200_GRAPH") != nullptr;
     p->use_tc = getenv("ALAN_B200_NO_TC") == nullptr;
+    // Opt-in: halves the launch count of a step, but measured on B200 the device time does not move (the small ops
+    // are bound by the latency of their own dependent instruction chains, not by launch overhead).
+    p->use_seq = getenv("ALAN_B200_SEQ") != nullptr;
     int dev = 0;
     p->sm_count = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) {

@@ -68,13 +68,12 @@ static Normal3 detect_normal3(const VMProg<T>& P) {
 // WARP = true : one warp per output, lanes stride over the summed dims, fixed-order butterfly sum
 //               (few outputs: the work is latency-bound unless the event loop is spread over lanes).
 template <typename T, bool WARP, bool N3>
-__global__ void __launch_bounds__(256) expr_fwd_kernel(const __grid_constant__ ExprParams<T> p, const Normal3 n3) {
+__device__ __forceinline__ void expr_fwd_body(const ExprParams<T>& p, const Normal3& n3, const i64 t0, const i64 tn) {
     T reg[N3 ? 1 : AB_NREG];
     T lv[AB_MAXL];
     int idx[AB_MAXD];
     i64 base[AB_MAXL];
     const int lane = WARP ? (threadIdx.x & 31) : 0, nl = WARP ? 32 : 1;
-    const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x, tn = (i64)gridDim.x * blockDim.x;
     for (i64 o = WARP ? (t0 >> 5) : t0; o < p.n_out; o += WARP ? (tn >> 5) : tn) {
         unravel(o, p.d, 0, p.d.n_a, idx);
         for (int l = 0; l < p.n_leaves; ++l) base[l] = dot_stride(p.leaf[l], idx, 0, p.d.n_a);
@@ -109,6 +108,11 @@ __global__ void __launch_bounds__(256) expr_fwd_kernel(const __grid_constant__ E
             p.out[o] = p.acc ? p.out[o] + v : v;
         }
     }
+}
+
+template <typename T, bool WARP, bool N3>
+__global__ void __launch_bounds__(256) expr_fwd_kernel(const __grid_constant__ ExprParams<T> p, const Normal3 n3) {
+    expr_fwd_body<T, WARP, N3>(p, n3, (i64)blockIdx.x * blockDim.x + threadIdx.x, (i64)gridDim.x * blockDim.x);
 }
 
 // Large scalar-event expressions (nothing summed, plain leaves): each thread owns B consecutive cells of the
@@ -185,7 +189,7 @@ struct ExprBwdParams {
 };
 
 template <typename T, bool WARP, bool N3>
-__global__ void __launch_bounds__(256) expr_bwd_kernel(const __grid_constant__ ExprBwdParams<T> p, const Normal3 n3) {
+__device__ __forceinline__ void expr_bwd_body(const ExprBwdParams<T>& p, const Normal3& n3, const i64 t0, const i64 tn) {
     T reg[N3 ? 1 : AB_NREG];
     T adj[N3 ? 1 : AB_NREG];
     T lv[AB_MAXL];
@@ -194,7 +198,6 @@ __global__ void __launch_bounds__(256) expr_bwd_kernel(const __grid_constant__ E
     const Opnd& tg = p.leaf[p.target];
     const i64 total = p.n_kept * p.nsplit;
     const int lane = WARP ? (threadIdx.x & 31) : 0, nl = WARP ? 32 : 1;
-    const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x, tn = (i64)gridDim.x * blockDim.x;
     // which argument of the Normal the target leaf is (it may be more than one)
     const bool tv = N3 && n3.nl[0] == p.target, tl = N3 && n3.nl[1] == p.target, ts = N3 && n3.nl[2] == p.target;
     for (i64 w = WARP ? (t0 >> 5) : t0; w < total; w += WARP ? (tn >> 5) : tn) {
@@ -260,6 +263,11 @@ __global__ void __launch_bounds__(256) expr_bwd_kernel(const __grid_constant__ E
             else p.gleaf[e] = p.acc ? p.gleaf[e] + v : v;
         }
     }
+}
+
+template <typename T, bool WARP, bool N3>
+__global__ void __launch_bounds__(256) expr_bwd_kernel(const __grid_constant__ ExprBwdParams<T> p, const Normal3 n3) {
+    expr_bwd_body<T, WARP, N3>(p, n3, (i64)blockIdx.x * blockDim.x + threadIdx.x, (i64)gridDim.x * blockDim.x);
 }
 
 template <typename T>
@@ -345,12 +353,12 @@ __device__ __forceinline__ void reduce_store(const ReduceParams<T>& p, i64 o, in
 // one warp per (output, split); lanes stride over the reduced index.  For reduced extents up to
 // 128 the lane keeps its (at most four) values in registers, so the factors are read once.
 template <typename T, int NRED>
-__global__ void __launch_bounds__(256) reduce_warp_kernel(const __grid_constant__ ReduceParams<T> p) {
+__device__ __forceinline__ void reduce_warp_body(const ReduceParams<T>& p, const i64 t0, const i64 tn) {
     int idx[AB_MAXD];
     i64 base[AB_MAXL];
     const int lane = threadIdx.x & 31;
-    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    const i64 warp = t0 >> 5;
+    const i64 nwarps = tn >> 5;
     const i64 total = p.n_out * p.nsplit;
     const i64 chunk = (p.n_red + p.nsplit - 1) / p.nsplit;
     for (i64 w = warp; w < total; w += nwarps) {
@@ -402,14 +410,19 @@ __global__ void __launch_bounds__(256) reduce_warp_kernel(const __grid_constant_
     }
 }
 
+template <typename T, int NRED>
+__global__ void __launch_bounds__(256) reduce_warp_kernel(const __grid_constant__ ReduceParams<T> p) {
+    reduce_warp_body<T, NRED>(p, (i64)blockIdx.x * blockDim.x + threadIdx.x, (i64)gridDim.x * blockDim.x);
+}
+
 // one thread per (output, split): outputs contiguous in memory / small reduced extent / none
 template <typename T, int NRED>
-__global__ void __launch_bounds__(256) reduce_thread_kernel(const __grid_constant__ ReduceParams<T> p) {
+__device__ __forceinline__ void reduce_thread_body(const ReduceParams<T>& p, const i64 t0, const i64 tn) {
     int idx[AB_MAXD];
     i64 base[AB_MAXL];
     const i64 total = p.n_out * p.nsplit;
     const i64 chunk = (p.n_red + p.nsplit - 1) / p.nsplit;
-    for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (i64)gridDim.x * blockDim.x) {
+    for (i64 w = t0; w < total; w += tn) {
         i64 o = w % p.n_out;
         int s = (int)(w / p.n_out);
         i64 lo = (i64)s * chunk, hi = lo + chunk < p.n_red ? lo + chunk : p.n_red;
@@ -441,11 +454,21 @@ __global__ void __launch_bounds__(256) reduce_thread_kernel(const __grid_constan
     }
 }
 
+template <typename T, int NRED>
+__global__ void __launch_bounds__(256) reduce_thread_kernel(const __grid_constant__ ReduceParams<T> p) {
+    reduce_thread_body<T, NRED>(p, (i64)blockIdx.x * blockDim.x + threadIdx.x, (i64)gridDim.x * blockDim.x);
+}
+
+template <typename T>
+static bool reduce_uses_warps(const ReduceParams<T>& p, bool thread_hint) {
+    const i64 per = (p.n_red + p.nsplit - 1) / p.nsplit;
+    return per >= 16 && (!thread_hint || (p.n_out * p.nsplit < 16384 && per >= 32));
+}
+
 template <typename T>
 static void launch_reduce(const ReduceParams<T>& p, bool thread_hint, cudaStream_t stream, int sm_count) {
     const int nred = p.d.nd - p.d.n_a;
-    const i64 per = (p.n_red + p.nsplit - 1) / p.nsplit;
-    const bool warp = per >= 16 && (!thread_hint || (p.n_out * p.nsplit < 16384 && per >= 32));
+    const bool warp = reduce_uses_warps(p, thread_hint);
     i64 threads = p.n_out * p.nsplit * (warp ? 32 : 1);
     i64 g = (threads + 255) / 256, cap = (i64)sm_count * 8;
     int grid = (int)(g > cap ? cap : (g < 1 ? 1 : g));
@@ -457,6 +480,66 @@ static void launch_reduce(const ReduceParams<T>& p, bool thread_hint, cudaStream
         if (nred == 1) reduce_thread_kernel<T, 1><<<grid, 256, 0, stream>>>(p);
         else if (nred == 2) reduce_thread_kernel<T, 2><<<grid, 256, 0, stream>>>(p);
         else reduce_thread_kernel<T, 0><<<grid, 256, 0, stream>>>(p);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Small-op sequences.  A plate tree has dozens of ops whose whole iteration space is a few thousand
+// points (global latents, top-level contractions, their adjoints): as separate launches each costs a
+// launch latency plus a drain, several microseconds for nanoseconds of work.  Consecutive small ops of
+// a program are therefore executed by ONE launch of one 1024-thread CTA that runs them back to back,
+// __syncthreads() between ops (same CTA, so global-memory results of one op are visible to the next).
+// The op bodies are the very same device functions the stand-alone kernels call.
+// ------------------------------------------------------------------------------------------
+enum { SK_EXPR = 0, SK_EXPR_BWD = 1, SK_REDUCE = 2, SK_FILL = 3 };
+#define AB_SEQ_MAX 16
+#define AB_SEQ_POINTS 2048        // an op is "small" when its iteration space has at most this many points
+
+template <typename T>
+struct SeqOp {
+    int kind;
+    int warp;                    // lanes over the reduced / looped index
+    Normal3 n3;
+    union {
+        ExprParams<T> e;
+        ExprBwdParams<T> b;
+        ReduceParams<T> r;
+        struct { void* ptr; i64 nbytes; } f;
+    };
+    __host__ __device__ SeqOp() {}
+};
+
+template <typename T>
+struct SeqParams {
+    int n;
+    SeqOp<T> op[AB_SEQ_MAX];
+    __host__ __device__ SeqParams() : n(0) {}
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024) small_seq_kernel(const __grid_constant__ SeqParams<T> sp) {
+    const i64 t0 = threadIdx.x, tn = blockDim.x;
+    for (int i = 0; i < sp.n; ++i) {
+        const SeqOp<T>& o = sp.op[i];
+        switch (o.kind) {
+            case SK_EXPR:
+                if (o.warp) { if (o.n3.on) expr_fwd_body<T, true, true>(o.e, o.n3, t0, tn); else expr_fwd_body<T, true, false>(o.e, o.n3, t0, tn); }
+                else { if (o.n3.on) expr_fwd_body<T, false, true>(o.e, o.n3, t0, tn); else expr_fwd_body<T, false, false>(o.e, o.n3, t0, tn); }
+                break;
+            case SK_EXPR_BWD:
+                if (o.warp) { if (o.n3.on) expr_bwd_body<T, true, true>(o.b, o.n3, t0, tn); else expr_bwd_body<T, true, false>(o.b, o.n3, t0, tn); }
+                else { if (o.n3.on) expr_bwd_body<T, false, true>(o.b, o.n3, t0, tn); else expr_bwd_body<T, false, false>(o.b, o.n3, t0, tn); }
+                break;
+            case SK_REDUCE:
+                if (o.warp) reduce_warp_body<T, 0>(o.r, t0, tn); else reduce_thread_body<T, 0>(o.r, t0, tn);
+                break;
+            case SK_FILL: {
+                unsigned* w = (unsigned*)o.f.ptr;                       // 4-byte granularity (all our tensors)
+                for (i64 k = t0; k < o.f.nbytes / 4; k += tn) w[k] = 0u;
+                break;
+            }
+        }
+        __syncthreads();
     }
 }
 

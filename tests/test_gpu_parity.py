@@ -445,3 +445,30 @@ def test_streamed_runner_matches_single_pass(chunks):
         assert rel_err(grads_s[k].cpu().reshape(-1), grads[k].cpu().reshape(-1)) < 1e-5, k
     with pytest.raises(Exception, match="equal blocks"):
         StreamedRunner(P, Q, sample, ip, data, names, 'plate_1', 7, device="cuda:0")
+
+
+@pytest.mark.parametrize("case", ["cfg1_lglp", "cfg3_radon", "cfg4_timeseries"])
+def test_optional_executor_modes_keep_results(case, monkeypatch):
+    """ALAN_B200_SEQ=1 (consecutive small ops in one launch) and ALAN_B200_GRAPH=1 (CUDA-graph replay of a
+    program) are execution strategies only: bit-identical log-evidence and gradients."""
+    Compiled, Runner = _engine()
+    g = load(case, "f32")
+    P, Q = models.CASES[case][0](M)
+    names = list(g["grad_sample"]) + list(g["grad_params"])
+    comp = Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"], grad_names=names)
+    res = []
+    for env in (None, "ALAN_B200_SEQ", "ALAN_B200_GRAPH"):
+        for e in ("ALAN_B200_SEQ", "ALAN_B200_GRAPH"):
+            monkeypatch.delenv(e, raising=False)
+        if env:
+            monkeypatch.setenv(env, "1")
+        run = Runner(comp, "cuda:0")
+        tensors = run.device_inputs(g["sample_nt"], g["inputs_params_nt"], g["data_nt"])
+        for _ in range(2):                   # the second pass replays the captured graph
+            lp = run.forward_raw(tensors)
+            grads = run.backward_raw(tensors)
+        res.append((lp.clone(), {k: v.clone() for k, v in grads.items()}))
+    for lp, grads in res[1:]:
+        assert t.equal(lp, res[0][0])
+        for k in names:
+            assert t.equal(grads[k], res[0][1][k]), k
