@@ -261,6 +261,17 @@ struct BernDotParams {
     int vec2;               // a / b rows are contiguous and 2-element aligned
 };
 
+// log Bernoulli(y; logits = x) = y x - softplus(x) = -(1 - y) x + min(x, 0) - log1p(exp(-|x|)).  fp32: the
+// log1p(exp(.)) tail on the SFU (ex2 / lg2, two MUFU instead of ~45 libdevice instructions); its absolute error is
+// <= 1e-7 on a term of magnitude |x| that is then summed over the plate.  fp64 keeps the libdevice path.
+__device__ __forceinline__ float bern_logits_fast(float y, float x) {
+    float t, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-fabsf(x) * 1.4426950408889634f));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + t));
+    return -((1.0f - y) * x) + fminf(x, 0.0f) - l * 0.6931471805599453f;
+}
+__device__ __forceinline__ double bern_logits_fast(double y, double x) { return bern_logits_lp(y, x); }
+
 template <typename T, int D>
 __global__ void __launch_bounds__(256) bern_dot_sum_kernel(const __grid_constant__ BernDotParams<T> p) {
     typedef typename Pair2<T>::type P2;
@@ -299,7 +310,7 @@ __global__ void __launch_bounds__(256) bern_dot_sum_kernel(const __grid_constant
 #pragma unroll
                 for (int dd = 0; dd < D; ++dd) l0 += ar[dd] * B[bo + dd * p.b_ev];
             }
-            acc += bern_logits_lp(Y[yo], l0 + l1);
+            acc += bern_logits_fast(Y[yo], l0 + l1);
         }
         p.out[o] = acc + p.cadd;
     }
