@@ -939,7 +939,7 @@ class Planner:
         leaves = []
         for e in operands:
             if e.op == 'const':
-                e = Expr.leaf(self.const_input(torch.tensor(e.value)), (), ())
+                e = Expr.leaf(self.const_input(torch.tensor(e.value, dtype=torch.float64)), (), ())
             if e.op != 'leaf' or e.mode != 0 or e.rename or e.pos_shape not in ((), (D,)):
                 return None
             leaves.append(e)

@@ -472,3 +472,76 @@ def test_optional_executor_modes_keep_results(case, monkeypatch):
         assert t.equal(lp, res[0][0])
         for k in names:
             assert t.equal(grads[k], res[0][1][k]), k
+
+
+# ------------------------------------------------------------------------------ edge shapes
+def _hier_scalar_model(ns):
+    """Scalar-event hierarchical Gaussian: the fan factor with D = 1 (no event dim) and a Normal likelihood."""
+    P = ns.Plate(
+        mu=ns.Normal(0., 1.),
+        ls=ns.Normal(-0.5, 0.5),
+        p=ns.Plate(
+            z=ns.Normal('mu', lambda ls: ls.exp()),
+            q=ns.Plate(
+                y=ns.Normal('z', 0.7),
+            ),
+        ),
+    )
+    Q = ns.Plate(
+        mu=ns.Normal('mu_loc', lambda mu_ls: mu_ls.exp()),
+        ls=ns.Normal('ls_loc', lambda ls_ls: ls_ls.exp()),
+        p=ns.Plate(
+            z=ns.Normal('z_loc', lambda z_ls: z_ls.exp()),
+            q=ns.Plate(
+                y=ns.Data(),
+            ),
+        ),
+    )
+    return P, Q
+
+
+def _hier_scalar_inputs(Mp, Nq, dtype, seed):
+    g = t.Generator().manual_seed(seed)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    data = {'y': NT(0.5 + r(Mp, Nq), ('p', 'q'))}
+    params = {'mu_loc': NT(0.1 * r(), ()), 'mu_ls': NT(-0.3 + 0.1 * r(), ()), 'ls_loc': NT(-0.5 + 0.1 * r(), ()),
+              'ls_ls': NT(-0.7 + 0.1 * r(), ()), 'z_loc': NT(0.3 * r(Mp), ('p',)), 'z_ls': NT(-0.5 + 0.1 * r(Mp), ('p',))}
+    return data, params
+
+
+@pytest.mark.parametrize("dtype", [t.float32, t.float64])
+@pytest.mark.parametrize("Mp,Nq,K", [(1, 1, 1), (1, 3, 5), (7, 1, 2), (300, 4, 30), (257, 3, 33), (64, 2, 64), (40, 2, 128)])
+def test_edge_shapes_scalar_hierarchy_vs_oracle(dtype, Mp, Nq, K):
+    """K = 1, plates of extent 1, K just above the tensor-core limit (33), K = 64 and 128, a scalar event (D = 1):
+    log-evidence, parameter gradients and marginals against the oracle."""
+    from oracle import logpq_oracle as O
+    Compiled, Runner = _engine()
+    P, Q = _hier_scalar_model(M)
+    data, params = _hier_scalar_inputs(Mp, Nq, dtype, seed=Mp + K)
+    g = t.Generator().manual_seed(K)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    sample = {'mu': NT(0.5 * r(K), ('K_mu',)), 'ls': NT(-0.5 + 0.3 * r(K), ('K_ls',)), 'z': NT(0.5 + 0.6 * r(Mp, K), ('p', 'K_z'))}
+    names = list(params)
+    comp = Compiled(P, Q, sample, params, data, grad_names=names)
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(sample, params, data)
+    lp = run.forward_raw(tensors)
+    grads = run.backward_raw(tensors)
+    ipg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in params.items()}
+    ref = O.elbo(P, Q, sample, ipg, data)
+    rg = t.autograd.grad(ref, [ipg[k].t for k in names])
+    tl = 1e-5 if dtype == t.float32 else 1e-10
+    assert rel_err(lp.cpu(), ref) < tl
+    for k, rr in zip(names, rg):
+        pt = comp.plan.input_pts[k]
+        assert rel_err(_as(pt.axes, grads[k].cpu(), ipg[k].axes), rr) < 30 * tl, k
+    # marginals through the Problem / Sample surface
+    from alan_b200.problem import Problem
+    prob = Problem(P, Q, data, params=params, device="cuda:0")
+    marg = prob.sample_from(sample).marginals()
+    ref_m = O.marginals(P, Q, sample, params, data)
+    for key, w in marg.weights.items():
+        rw = ref_m[frozenset(key)]
+        assert rel_err(w.order(rw.axes).t.cpu(), rw.t) < 30 * tl, key
+        s_ = w.t.sum(tuple(i for i, a in enumerate(w.axes) if a.startswith('K_')))
+        assert t.allclose(s_, t.ones_like(s_), atol=1e-4 if dtype == t.float32 else 1e-9)
