@@ -695,6 +695,8 @@ class Planner:
         self.fwd_segments = []
         self.steps = []              # resampling steps in forward (bottom-up) creation order per level
         self.level_steps = {}        # level tuple -> [Step]
+        self.level_factors = {}      # level tuple -> (factors before contraction, Ks summed there)
+        self.level_paths = {}        # level tuple -> forward contraction path
         self.level_order = []
         self.consts = {}
         self.inputs = {}
@@ -976,6 +978,7 @@ class Planner:
             lfs.append(lf)
             Knon.extend(a); Kts.extend(b); Kinits.extend(c)
         level_steps = []
+        self.level_factors[tuple(active)] = (list(lfs), tuple(Knon))
         lf = self.contract(lfs, tuple(Knon), active, level_steps)
         self.level_steps[tuple(active)] = (level_steps, Q)
         if name is None:
@@ -1061,6 +1064,7 @@ class Planner:
         if not lfs:
             raise Exception("plate without factors")
         path = greedy_path([lf.axes for lf in lfs], Ks_to_sum, self.sizes)
+        self.level_paths[tuple(active)] = path
         lfs = list(lfs)
         for idxs in path:
             chosen = [lfs[i] for i in idxs]
@@ -1433,8 +1437,43 @@ class Planner:
         ops = []
         sampled = set()
 
-        def visit(level, Q):
+        def steps_for_sampling(level):
+            """The reference re-runs collect_lps at sampling time on factors that were already gathered at the
+            sampled parent indices (sample_logpq.py:75-81): every parent K axis has become the sample axis N, so
+            the contraction ORDER -- and with it the order in which the level's Ks are drawn and the uniforms are
+            consumed -- can differ from the forward pass.  Gathering commutes with the LSE over this level's Ks,
+            so the same order is replayed here on the ungathered factors (parent Ks kept as batch axes; the
+            sample kernel gathers), re-using the forward intermediates when the order is the same."""
             steps, _ = self.level_steps[level]
+            lfs, Ks_here = self.level_factors[level]
+            if not Ks_here:
+                return steps
+            seen = lambda axes: tuple(dict.fromkeys('N' if (a.startswith('K_') and a not in Ks_here) else a for a in axes))
+            path_s = greedy_path([seen(lf.axes) for lf in lfs], Ks_here, sizes)
+            if path_s == self.level_paths[level]:
+                return steps
+            out_steps = []
+            cur = list(lfs)
+            for idxs in path_s:
+                chosen = [cur[i] for i in idxs]
+                cur = [cur[i] for i in range(len(cur)) if i not in idxs]
+                remaining = set(a for lf in cur for a in lf.axes)
+                chosen_axes = _union_axes([lf.axes for lf in chosen])
+                ks = tuple(k for k in Ks_here if k in chosen_axes and k not in remaining)
+                tensors = [tc for lf in chosen for tc in lf.tensors]
+                if not ks:
+                    cur.append(LogicalFactor(tensors, 0.0, self.canon_order(chosen_axes)))
+                    continue
+                out_axes = self.canon_order([a for a in chosen_axes if a not in ks])
+                out = self.ws(out_axes, name='lse_s[' + ','.join(ks) + ']')
+                ops.append(ReduceOp(R_LSE_EPS, out, [self.axdim(a) for a in out_axes], [self.axdim(a) for a in ks],
+                                    tensors, tag='contract_for_sampling:' + ','.join(ks)))
+                out_steps.append(Step(tuple(level), tensors, ks))
+                cur.append(LogicalFactor([(plain(out), 1.0)], 0.0, out_axes))
+            return out_steps
+
+        def visit(level, Q):
+            steps = steps_for_sampling(level)
             for st in reversed(steps):
                 batch_axes = tuple(a for a in self.all_plates
                                    if any(a in lf.pt.axes for lf, _ in st.tensors))

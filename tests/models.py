@@ -259,6 +259,58 @@ def model1_inputs(p1=3, p2=4, seed=0, dtype=t.float32):
                 params={'a_mean': 0.1 * r(), 'd_mean': (0.1 * r(p1)).refine_names('p1')})
 
 
+# --------------------------------------------------------------------------- more of the reference's own test models
+def ref_bernoulli_model(ns):
+    """tests/bernoulli_no_plate.py:5-17 (Beta prior, Bernoulli(probs) likelihood)."""
+    P = ns.Plate(p=ns.Beta(2, 1), T=ns.Plate(coin=ns.Bernoulli('p')))
+    Q = ns.Plate(p=ns.Beta(1, 1), T=ns.Plate(coin=ns.Data()))
+    return P, Q
+
+
+def ref_bernoulli_inputs(T=10, seed=0, dtype=t.float32):
+    coin = t.cat([t.zeros(3), t.ones(T - 3)]).to(dtype)
+    return dict(platesizes={'T': T}, data={'coin': coin.refine_names('T')}, inputs={}, params={})
+
+
+def ref_corr_q_model(ns):
+    """tests/linear_gaussian_two_params_corr_Q.py:31-46 (two unplated latents, correlated Q)."""
+    P = ns.Plate(a=ns.Normal(2, 1), b=ns.Normal('a', 1), T=ns.Plate(d=ns.Normal('b', 3)))
+    Q = ns.Plate(a=ns.Normal(1, 4), b=ns.Normal('a', 1.2), T=ns.Plate(d=ns.Data()))
+    return P, Q
+
+
+def ref_dangling_model(ns):
+    """tests/linear_gaussian_latents_dangling.py:28-47 (a plated latent nothing depends on)."""
+    P = ns.Plate(
+        a=ns.Normal(2, 2),
+        T=ns.Plate(z=ns.Normal('a', 1.3), zp=ns.Normal('a', 1.), d=ns.Normal('z', 1.5)),
+    )
+    Q = ns.Plate(
+        a=ns.Normal(1, 4),
+        T=ns.Plate(z=ns.Normal(lambda a: 1.5 * a, 3.5), zp=ns.Normal(lambda a: 1.5 * a, 3.5), d=ns.Data()),
+    )
+    return P, Q
+
+
+def ref_batch_model(ns):
+    """tests/linear_gaussian_latents_batch.py:22-37 (event shape [2], tensor-valued constant arguments)."""
+    P = ns.Plate(
+        a=ns.Normal(t.tensor([0.3, -0.8]), t.tensor([1., 2.])),
+        T=ns.Plate(z=ns.Normal('a', t.tensor([1.3, 1.6])), d=ns.Normal('z', t.tensor([2., 3.]))),
+    )
+    Q = ns.Plate(
+        a=ns.Normal(t.zeros(2), 4),
+        T=ns.Plate(z=ns.Normal(lambda a: 0.5 * a, 6), d=ns.Data()),
+    )
+    return P, Q
+
+
+def ref_batch_inputs(T=10, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    data = {'d': (1.5 + t.randn(T, 2, generator=g, dtype=t.float64)).to(dtype).refine_names('T', None)}
+    return dict(platesizes={'T': T}, data=data, inputs={}, params={})
+
+
 CASES = {
     # name: (model builder, inputs builder, kwargs for inputs, K, moment specs, joints, importance N or None)
     'cfg1_lgl': (lgl_model, lgl_inputs, dict(T=10), 3, [('a', 'mean'), ('a', 'mean2'), ('z', 'mean'), ('z', 'mean2')], [], 7),
@@ -269,6 +321,21 @@ CASES = {
                    [('County_mean', 'mean'), ('global_mean', 'mean2')], [('Beta_u', 'Beta_basement')], 9),
     'cfg4_timeseries': (timeseries_model, timeseries_inputs, dict(T=37), 5, [('ts', 'mean'), ('ts', 'mean2')], [], None),
     'model1': (model1_model, model1_inputs, dict(p1=3, p2=4), 4, [('d', 'mean'), ('c', 'mean2')], [('ab', 'c')], 5),
+    'ref_bernoulli': (ref_bernoulli_model, ref_bernoulli_inputs, dict(T=10), 5, [('p', 'mean')], [], 6),
+    'ref_corr_q': (ref_corr_q_model, lgl_inputs, dict(T=10), 4, [('a', 'mean'), ('b', 'mean2')], [('a', 'b')], 5),
+    'ref_dangling': (ref_dangling_model, lgl_inputs, dict(T=10), 3, [('a', 'mean'), ('zp', 'mean')], [], 4),
+    'ref_batch': (ref_batch_model, ref_batch_inputs, dict(T=10), 3, [('a', 'mean'), ('z', 'mean2')], [], 4),
 }
 
 MOMENT_FUNCS = {'mean': (lambda x: x), 'mean2': (lambda x: x * x)}
+
+
+def build(case, ns, dtype=t.float32):
+    """Build the (P, Q) of a case with tensor-valued constants created in `dtype` (the golden generator builds the
+    reference model under torch.set_default_dtype(dtype), so `t.tensor([1.3, 1.6])` means different bits per tag)."""
+    old = t.get_default_dtype()
+    t.set_default_dtype(dtype)
+    try:
+        return CASES[case][0](ns)
+    finally:
+        t.set_default_dtype(old)

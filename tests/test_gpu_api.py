@@ -17,7 +17,7 @@ CASES = list(models.CASES)
 
 def _problem(g, case, requires_grad=False):
     from alan_b200.problem import Problem
-    P, Q = models.CASES[case][0](M)
+    P, Q = models.build(case, M, t.float64 if g['dtype'] == 'torch.float64' else t.float32)
     nt = lambda d, rg=False: {k: NT(v[0].clone().requires_grad_(rg), v[1]) for k, v in d.items()}
     params = nt(g["params"], requires_grad)
     prob = Problem(P, Q, nt(g["data"]), inputs=nt(g["inputs"]), params=params, device="cuda:0")

@@ -89,7 +89,7 @@ def test_unit_gather_bit_exact():
 def test_elbo_and_grads_vs_reference_golden(case, tag):
     Compiled, Runner = _engine()
     g = load(case, tag)
-    P, Q = models.CASES[case][0](M)
+    P, Q = models.build(case, M, TAGS[tag])
     names = list(g["grad_sample"]) + list(g["grad_params"])
     comp = Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"], grad_names=names)
     run = Runner(comp, "cuda:0")
@@ -120,7 +120,7 @@ def test_elbo_and_grads_vs_reference_golden(case, tag):
 def test_marginals_and_moments_vs_reference_golden(case, tag):
     Compiled, Runner = _engine()
     g = load(case, tag)
-    P, Q = models.CASES[case][0](M)
+    P, Q = models.build(case, M, TAGS[tag])
     dtype = TAGS[tag]
     g2p, groups = Q.groupvarname2platenames(), Q.groupvarnames()
     sizes = {**{a: s for v in g["sample_nt"].values() for a, s in v.named_sizes.items()}, **g["platesizes"]}
@@ -154,7 +154,7 @@ def test_resampling_indices(case, tag):
     from plan_emulator import Emu
     Compiled, Runner = _engine()
     g = load(case, tag)
-    P, Q = models.CASES[case][0](M)
+    P, Q = models.build(case, M, TAGS[tag])
     N = g["N"]
     comp = Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"], N=N)
     run = Runner(comp, "cuda:0")
@@ -453,7 +453,7 @@ def test_optional_executor_modes_keep_results(case, monkeypatch):
     program) are execution strategies only: bit-identical log-evidence and gradients."""
     Compiled, Runner = _engine()
     g = load(case, "f32")
-    P, Q = models.CASES[case][0](M)
+    P, Q = models.build(case, M, t.float32)
     names = list(g["grad_sample"]) + list(g["grad_params"])
     comp = Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"], grad_names=names)
     res = []

@@ -40,7 +40,7 @@ def grad_as(comp, grads, name, axes):
 @pytest.mark.parametrize("case", CASES)
 def test_elbo_and_grads(case, tag):
     g = load(case, tag)
-    P, Q = models.CASES[case][0](M)
+    P, Q = models.build(case, M, TAGS[tag])
     names = list(g["grad_sample"]) + list(g["grad_params"])
     comp = Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"], grad_names=names)
     inputs = comp.canonical_inputs(g["sample_nt"], g["inputs_params_nt"], g["data_nt"])
@@ -56,7 +56,7 @@ def test_elbo_and_grads(case, tag):
 @pytest.mark.parametrize("case", CASES)
 def test_marginals_and_moments(case, tag):
     g = load(case, tag)
-    P, Q = models.CASES[case][0](M)
+    P, Q = models.build(case, M, TAGS[tag])
     dtype = TAGS[tag]
     g2p = Q.groupvarname2platenames()
     groups = Q.groupvarnames()
@@ -86,7 +86,7 @@ def test_marginals_and_moments(case, tag):
 @pytest.mark.parametrize("case", [c for c in CASES if models.CASES[c][6] is not None])
 def test_resampling(case, tag):
     g = load(case, tag)
-    P, Q = models.CASES[case][0](M)
+    P, Q = models.build(case, M, TAGS[tag])
     N = g["N"]
     comp = Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"], N=N)
     inputs = comp.canonical_inputs(g["sample_nt"], g["inputs_params_nt"], g["data_nt"])
