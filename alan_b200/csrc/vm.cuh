@@ -16,7 +16,7 @@ enum VOp {
     V_LOG1P = 16, V_POW = 17, V_LGAMMA = 18, V_MOV = 19,
     V_NORMAL = 32, V_BERN_LOGITS = 33, V_BERN_PROBS = 34, V_LOGNORMAL = 35, V_LAPLACE = 36,
     V_EXPONENTIAL = 37, V_GAMMA = 38, V_BETA = 39, V_POISSON = 40, V_CAUCHY = 41, V_HALFNORMAL = 42,
-    V_UNIFORM = 43, V_STUDENTT = 44
+    V_UNIFORM = 43, V_STUDENTT = 44, V_NEGBIN_LOGITS = 45, V_NEGBIN_PROBS = 46, V_BINOM_LOGITS = 47, V_BINOM_PROBS = 48
 };
 
 template <typename T>
@@ -72,6 +72,19 @@ template <typename T> __device__ __forceinline__ T normal_lp(T v, T loc, T scale
     return -(d * d) / (T(2) * (scale * scale)) - ab_log(scale) - T(HALF_LOG_2PI);
 }
 
+// torch negative_binomial.py:114-130: value a, total_count n, logits x
+template <typename T> __device__ __forceinline__ T negbin_lp(T a, T n, T x) {
+    T unnorm = n * ab_logsigmoid(-x) + a * ab_logsigmoid(x);
+    T norm = -ab_lgamma(n + a) + ab_lgamma(T(1) + a) + ab_lgamma(n);
+    if (n + a == T(0)) norm = T(0);
+    return unnorm - norm;
+}
+// torch binomial.py:127-147: value k, total_count n, logits x
+template <typename T> __device__ __forceinline__ T binom_lp(T k, T n, T x) {
+    T normalize = n * (x > T(0) ? x : T(0)) + n * ab_log1p(ab_exp(-ab_abs(x))) - ab_lgamma(n + T(1));
+    return k * x - ab_lgamma(k + T(1)) - ab_lgamma(n - k + T(1)) - normalize;
+}
+
 template <typename T>
 __device__ __forceinline__ T vm_eval(const VMProg<T>& P, const T* leaf, T* reg) {
 #pragma unroll 1
@@ -123,6 +136,10 @@ __device__ __forceinline__ T vm_eval(const VMProg<T>& P, const T* leaf, T* reg) 
                 T Z = ab_log(s) + T(0.5) * ab_log(df) + T(0.5 * LOG_PI) + ab_lgamma(T(0.5) * df)
                       - ab_lgamma(T(0.5) * (df + T(1)));
                 y = -T(0.5) * (df + T(1)) * ab_log1p(z * z / df) - Z; break; }
+            case V_NEGBIN_LOGITS: y = negbin_lp(a, b, reg[ic]); break;
+            case V_NEGBIN_PROBS: y = negbin_lp(a, b, probs_to_logits(reg[ic])); break;
+            case V_BINOM_LOGITS: y = binom_lp(a, b, reg[ic]); break;
+            case V_BINOM_PROBS: y = binom_lp(a, b, probs_to_logits(reg[ic])); break;
             default: y = T(0);
         }
         reg[dst] = y;
@@ -183,6 +200,10 @@ __device__ __forceinline__ void vm_eval_batch(const VMProg<T>& P, const T (*leaf
             case V_STUDENTT: VMB(-T(0.5) * (b + T(1)) * ab_log1p(((a - c) / d) * ((a - c) / d) / b)
                                  - (ab_log(d) + T(0.5) * ab_log(b) + T(0.5 * LOG_PI) + ab_lgamma(T(0.5) * b)
                                     - ab_lgamma(T(0.5) * (b + T(1)))));
+            case V_NEGBIN_LOGITS: VMB(negbin_lp(a, b, c));
+            case V_NEGBIN_PROBS: VMB(negbin_lp(a, b, probs_to_logits(c)));
+            case V_BINOM_LOGITS: VMB(binom_lp(a, b, c));
+            case V_BINOM_PROBS: VMB(binom_lp(a, b, probs_to_logits(c)));
             default: { _Pragma("unroll") for (int q = 0; q < B; ++q) Y[q] = T(0); } break;
         }
 #pragma unroll
@@ -268,6 +289,22 @@ __device__ __forceinline__ T vm_grad(const VMProg<T>& P, const T* reg, T* adj, i
                 adj[ib] += g * (-T(0.5) * ab_log1p(u) + T(0.5) * (df + T(1)) * u / (df * (T(1) + u))
                                 - T(0.5) / df - T(0.5) * ab_digamma(T(0.5) * df)
                                 + T(0.5) * ab_digamma(T(0.5) * (df + T(1)))); break; }
+            case V_NEGBIN_LOGITS: case V_NEGBIN_PROBS: {      // value a (discrete: no gradient), total_count b, logits / probs reg[ic]
+                T pr = reg[ic], e = Eps<T>::v();
+                T x = (op == V_NEGBIN_PROBS) ? probs_to_logits(pr) : pr;
+                T sg = ab_sigmoid(x);
+                T gx = g * (a * (T(1) - sg) - b * sg);       // d/dx [ n logsig(-x) + a logsig(x) ]
+                if (op == V_NEGBIN_PROBS) { if (pr >= e && pr <= T(1) - e) adj[ic] += gx / (pr * (T(1) - pr)); }
+                else adj[ic] += gx;
+                adj[ib] += g * (ab_logsigmoid(-x) + ab_digamma(b + a) - ab_digamma(b));
+                break; }
+            case V_BINOM_LOGITS: case V_BINOM_PROBS: {        // value a, total_count b (discrete), logits / probs reg[ic]
+                T pr = reg[ic], e = Eps<T>::v();
+                T x = (op == V_BINOM_PROBS) ? probs_to_logits(pr) : pr;
+                T gx = g * (a - b * ab_sigmoid(x));
+                if (op == V_BINOM_PROBS) { if (pr >= e && pr <= T(1) - e) adj[ic] += gx / (pr * (T(1) - pr)); }
+                else adj[ic] += gx;
+                break; }
             default: break;
         }
     }

@@ -42,7 +42,8 @@ VOPS = {'load': 0, 'const': 1, 'add': 2, 'sub': 3, 'mul': 4, 'div': 5, 'neg': 6,
         'lgamma': 18, 'mov': 19,
         'Normal': 32, 'Bernoulli_logits': 33, 'Bernoulli_probs': 34, 'LogNormal': 35, 'Laplace': 36,
         'Exponential': 37, 'Gamma': 38, 'Beta': 39, 'Poisson': 40, 'Cauchy': 41, 'HalfNormal': 42, 'Uniform': 43,
-        'StudentT': 44}
+        'StudentT': 44, 'NegativeBinomial_logits': 45, 'NegativeBinomial_probs': 46, 'Binomial_logits': 47,
+        'Binomial_probs': 48}
 
 # density op -> order of the distribution arguments after the value operand
 DENSITY_ARGS = {
@@ -910,7 +911,9 @@ class Planner:
             opname = 'Bernoulli_logits' if 'logits' in args else 'Bernoulli_probs'
             order = [args['logits'] if 'logits' in args else args['probs']]
         elif dist.family in ('NegativeBinomial', 'Binomial'):
-            raise Exception(f"{dist.family} is declared but its factor kernel is not built yet")
+            which = 'logits' if 'logits' in args else 'probs'
+            opname = f'{dist.family}_{which}'
+            order = [args['total_count'], args[which]]
         else:
             opname = dist.family
             order = [args[k] for k in DENSITY_ARGS[dist.family]]

@@ -43,6 +43,20 @@ def _density(op, r, a, b, c, d):
     if op == 39:
         return (t.xlogy(r[b] - 1, r[a]) + t.xlogy(r[c] - 1, 1 - r[a]) + t.lgamma(r[b] + r[c])
                 - t.lgamma(r[b]) - t.lgamma(r[c]))
+    if op in (45, 46, 47, 48):
+        x = r[c]
+        if op in (46, 48):
+            eps = t.finfo(x.dtype).eps
+            pc = x.clamp(eps, 1 - eps)
+            x = t.log(pc) - t.log1p(-pc)
+        if op in (45, 46):
+            return t.distributions.NegativeBinomial(r[b], logits=x, validate_args=False).log_prob(r[a])
+        return t.distributions.Binomial(r[b], logits=x, validate_args=False).log_prob(r[a])
+    if op == 40:
+        return t.xlogy(r[a], r[b]) - r[b] - t.lgamma(r[a] + 1)
+    if op == 35:
+        lx = t.log(r[a]); dd = lx - r[b]
+        return -(dd * dd) / (2 * (r[c] * r[c])) - t.log(r[c]) - HALF_LOG_2PI - lx
     raise NotImplementedError(f"emulator: density op {op}")
 
 

@@ -545,3 +545,66 @@ def test_edge_shapes_scalar_hierarchy_vs_oracle(dtype, Mp, Nq, K):
         assert rel_err(w.order(rw.axes).t.cpu(), rw.t) < 30 * tl, key
         s_ = w.t.sum(tuple(i for i, a in enumerate(w.axes) if a.startswith('K_')))
         assert t.allclose(s_, t.ones_like(s_), atol=1e-4 if dtype == t.float32 else 1e-9)
+
+
+# ------------------------------------------------------------------------------ every density family of the VM
+_FAMILIES = {
+    # name: (likelihood builder over ns, data generator)
+    'Normal': (lambda ns: ns.Normal('a', lambda b: b.exp()), lambda r, n: r(n)),
+    'LogNormal': (lambda ns: ns.LogNormal('a', 0.7), lambda r, n: r(n).exp()),
+    'Laplace': (lambda ns: ns.Laplace('a', lambda b: b.exp()), lambda r, n: r(n)),
+    'Cauchy': (lambda ns: ns.Cauchy('a', 1.2), lambda r, n: r(n)),
+    'StudentT': (lambda ns: ns.StudentT(4.0, 'a', lambda b: b.exp()), lambda r, n: r(n)),
+    'HalfNormal': (lambda ns: ns.HalfNormal(lambda a: a.exp()), lambda r, n: r(n).abs() + 0.1),
+    'Exponential': (lambda ns: ns.Exponential(lambda a: a.exp()), lambda r, n: r(n).abs() + 0.1),
+    'Gamma': (lambda ns: ns.Gamma(lambda a: a.exp() + 0.5, lambda b: b.exp()), lambda r, n: r(n).abs() + 0.2),
+    'Beta': (lambda ns: ns.Beta(lambda a: a.exp() + 0.5, 2.0), lambda r, n: r(n).sigmoid()),
+    'Uniform': (lambda ns: ns.Uniform(-9.0, lambda a: 9.0 + a.exp()), lambda r, n: r(n)),
+    'Poisson': (lambda ns: ns.Poisson(lambda a: a.exp()), lambda r, n: (r(n).abs() * 2).floor()),
+    'Bernoulli_logits': (lambda ns: ns.Bernoulli(logits='a'), lambda r, n: (r(n) > 0).to(r(1).dtype)),
+    'Bernoulli_probs': (lambda ns: ns.Bernoulli(probs=lambda a: a.sigmoid()), lambda r, n: (r(n) > 0).to(r(1).dtype)),
+    'NegativeBinomial_logits': (lambda ns: ns.NegativeBinomial(5, logits='a'), lambda r, n: (r(n).abs() * 3).floor()),
+    'NegativeBinomial_probs': (lambda ns: ns.NegativeBinomial(lambda b: b.exp() + 1.0, probs=lambda a: a.sigmoid()),
+                               lambda r, n: (r(n).abs() * 3).floor()),
+    'Binomial_logits': (lambda ns: ns.Binomial(7, logits='a'), lambda r, n: (r(n).abs() * 2).floor().clamp(max=7)),
+    'Binomial_probs': (lambda ns: ns.Binomial(7, probs=lambda a: a.sigmoid()), lambda r, n: (r(n).abs() * 2).floor().clamp(max=7)),
+}
+
+
+@pytest.mark.parametrize("dtype", [t.float32, t.float64])
+@pytest.mark.parametrize("family", list(_FAMILIES))
+def test_density_families_vs_oracle(family, dtype):
+    """Each log-density of the factor VM (csrc/vm.cuh) and its hand-written derivative against torch.distributions
+    + autograd in the oracle (dist.py:297-302 -> TorchDimDist.py:127-162): log-evidence, gradients w.r.t. the Q
+    parameters (they reach the likelihood through the reparameterised samples a, b) and marginals."""
+    from oracle import logpq_oracle as O
+    Compiled, Runner = _engine()
+    like, gen = _FAMILIES[family]
+    P = M.Plate(a=M.Normal(0., 1.), b=M.Normal(-0.3, 0.5), T=M.Plate(y=like(M)))
+    Q = M.Plate(a=M.Normal('a_loc', lambda a_ls: a_ls.exp()), b=M.Normal('b_loc', lambda b_ls: b_ls.exp()),
+                T=M.Plate(y=M.Data()))
+    T_, K = 23, 7
+    g = t.Generator().manual_seed(hash(family) % 1000)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    data = {'y': NT(gen(r, T_), ('T',))}
+    params = {'a_loc': NT(0.1 * r(), ()), 'a_ls': NT(-0.5 + 0.1 * r(), ()), 'b_loc': NT(-0.3 + 0.1 * r(), ()),
+              'b_ls': NT(-0.7 + 0.1 * r(), ())}
+    sample = {'a': NT(0.6 * r(K), ('K_a',)), 'b': NT(-0.3 + 0.4 * r(K), ('K_b',))}
+    names = ['a', 'b'] + list(params)
+    comp = Compiled(P, Q, sample, params, data, grad_names=names)
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(sample, params, data)
+    lp = run.forward_raw(tensors)
+    grads = run.backward_raw(tensors)
+    sg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in sample.items()}
+    pg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in params.items()}
+    ref = O.elbo(P, Q, sg, pg, data)
+    rg = t.autograd.grad(ref, [sg['a'].t, sg['b'].t] + [pg[k].t for k in params], allow_unused=True)
+    tl = 2e-5 if dtype == t.float32 else 1e-10
+    assert t.isfinite(ref)
+    assert rel_err(lp.cpu(), ref) < tl
+    for k, rr in zip(names, rg):
+        if rr is None:
+            assert float(grads[k].abs().max()) == 0.0, k
+            continue
+        assert rel_err(grads[k].cpu().reshape(rr.shape), rr) < 50 * tl, k
