@@ -123,3 +123,17 @@ def test_importance_sample(case):
     a = s.importance_sample(N, seed=3)
     b = s.importance_sample(N, seed=3)
     assert all(t.equal(a[k].t, b[k].t) for k in a)
+
+
+def test_plans_are_cached_per_problem():
+    """A new Sample of the same problem and shapes (every training iteration draws one) reuses the compiled plan
+    and its device workspace."""
+    g = load("cfg2_movielens", "f32")
+    prob, _ = _problem(g, "cfg2_movielens", requires_grad=True)
+    s1 = prob.sample_from({k: NT(*v) for k, v in g["sample"].items()})
+    L1 = s1.elbo_rws()
+    n = len(prob._runners)
+    s2 = prob.sample_from({k: NT(v[0] * 1.0, v[1]) for k, v in g["sample"].items()})
+    L2 = s2.elbo_rws()
+    assert len(prob._runners) == n
+    assert t.equal(L1.detach(), L2.detach())
