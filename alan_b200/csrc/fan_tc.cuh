@@ -59,6 +59,13 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long
 #else
 #define MBAR_WAIT(bar, par, acc) mbar_wait(bar, par)
 #endif
+// one lane of a converged warp (the way the MMA issuer is elected: the surrounding code stays warp-uniform, so
+// descriptors and TMEM addresses live in uniform registers instead of being re-broadcast for every UTCHMMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -362,16 +369,16 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
         }
     } else if (warp == TC_MMA_WARP) {
         // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            unsigned it = 0;
-            for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int s = it % TC_STAGES, a = it % TC_ACC;
-                const uint32_t ps = (it / TC_STAGES) & 1, pa = (it / TC_ACC) & 1;
-                MBAR_WAIT(&full[s], ps, dbg0);
-                MBAR_WAIT(&tempty[a], pa ^ 1, dbg1);
-                tc_fence_after();
-                const uint32_t bhi = smem_u32(stage_base + (size_t)s * 2 * OPER), blo = bhi + OPER;
-                const uint32_t d = tmem + D_COL + TC_N * a;
+        unsigned it = 0;
+        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % TC_STAGES, a = it % TC_ACC;
+            const uint32_t ps = (it / TC_STAGES) & 1, pa = (it / TC_ACC) & 1;
+            MBAR_WAIT(&full[s], ps, dbg0);
+            MBAR_WAIT(&tempty[a], pa ^ 1, dbg1);
+            tc_fence_after();
+            const uint32_t bhi = smem_u32(stage_base + (size_t)s * 2 * OPER), blo = bhi + OPER;
+            const uint32_t d = tmem + D_COL + TC_N * a;
+            if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < KSTEPS; ++j) {
                     const uint64_t dh = smem_desc(bhi + j * 2 * LBO, LBO, SBO), dl = smem_desc(blo + j * 2 * LBO, LBO, SBO);
@@ -382,6 +389,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
                 tc_commit(&empty[s]);
                 tc_commit(&tfull[a]);
             }
+            __syncwarp();
         }
     } else {
         // ---------------------------------------------------------------- builders: warp (g, rs), lane = kappa
