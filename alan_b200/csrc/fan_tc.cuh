@@ -18,14 +18,14 @@
 // max / exp2 / sum in registers.  fp32 accuracy comes from the 3xTF32 split  A_hi B_hi + A_lo B_hi +
 // A_hi B_lo  (relative error ~2^-21 per product; the dropped lo*lo term is 2^-22).
 //
-// Roles (21 warps, one persistent CTA per SM, tiles of 4 rho):
-//   warps 0-7   epilogue, two teams of four: warp % 4 = TMEM lane quadrant = rs, lane = f; team e takes
-//               tiles it % 2 == e
-//   warp  8     MMA issuer (one thread), TMEM allocator
-//   warps 9-20  builders, three sets of four: warp (set, rs) writes the K-columns of rho = 4 tile + rs,
-//               lane = kappa; set b takes tiles it % 3 == b, so three tiles' global loads are in flight
-// Pipelines: smem stages full/empty (builders <-> MMA), TMEM accumulators tfull/tempty (MMA <->
-// epilogue); mbarriers, tcgen05.commit for the MMA-side arrivals.
+// Roles (25 warps, one persistent CTA per SM; a supertile = 4 groups x 4 rho slots = 16 rho, N = 128 kappa columns):
+//   epilogue  teams of four warps: warp % 4 = TMEM lane quadrant = rho slot rs, lane = f; team e takes the rho
+//             groups [e GPT, (e + 1) GPT) of EVERY supertile (forward: 2 teams, adjoint: 4 teams)
+//   MMA       one warp, one elected lane issues the 30 tcgen05.mma of a supertile; it also owns the TMEM allocation
+//   builders  warp (gq, rs) writes the K-columns of rho slot rs of its group(s), lane = kappa (forward: 16 warps
+//             with one rho each, adjoint: 8 warps with two rho each)
+// Pipelines: smem stages full/empty (builders <-> MMA), TMEM accumulators tfull/tempty (MMA <-> epilogue);
+// mbarriers, tcgen05.commit for the MMA-side arrivals; every wait is a bounded spin that traps.
 #pragma once
 #include "fused.cuh"
 
@@ -153,10 +153,18 @@ constexpr int TC_G = 4;           // rho groups per supertile: N = 32 TC_G kappa
                                   // that a tcgen05.mma still costs ~64 cycles, measured: N = 32 ran at 64 clk / MMA)
 constexpr int TC_N = 32 * TC_G;
 constexpr int TC_RHO = 4 * TC_G;  // rho per supertile
-constexpr int TC_EPI = 2;         // epilogue teams of 4 warps (warp % 4 = TMEM lane quadrant = rs)
-constexpr int TC_BW = 4 * TC_G;   // builder warps: one per (g, rs)
-constexpr int TC_MMA_WARP = 4 * TC_EPI;
-constexpr int TC_WARPS = 4 * TC_EPI + 1 + TC_BW;
+// Warp roles differ per direction (25 warps either way): the forward pass is bound by the MMA issuer and needs all
+// 16 builder warps to keep it fed (2 epilogue teams suffice); the adjoint is bound by its heavier epilogue
+// (exp2, multiply, cross-lane sum over f) and runs 4 epilogue teams with 8 builder warps building two rho each.
+template <bool BWD> struct TcRoles {
+    static constexpr int EPI = BWD ? 4 : 2;          // epilogue teams of 4 warps (warp % 4 = TMEM lane quadrant = rs)
+    static constexpr int BPW = BWD ? 2 : 1;          // rho built per builder warp and supertile
+    static constexpr int BW = 4 * TC_G / BPW;        // builder warps: warp (gq, rs) builds groups gq, gq + TC_G / BPW, ...
+    static constexpr int MMA_WARP = 4 * EPI;
+    static constexpr int WARPS = 4 * EPI + 1 + BW;
+};
+constexpr int TC_WARPS = 25;
+static_assert(TcRoles<true>::WARPS == TC_WARPS && TcRoles<false>::WARPS == TC_WARPS, "role split must keep 25 warps");
 constexpr int TC_STAGES = 2;      // smem stages of the B operand (80 KB each at D = 18)
 constexpr int TC_ACC = 2;         // TMEM accumulator stages (multiple of TC_EPI)
 constexpr int TC_TMEM_COLS = 512; // A_hi + A_lo (<= 80 each) + 2 x 128 accumulator columns; one CTA per SM
@@ -166,6 +174,8 @@ template <int D, bool BWD>
 __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __grid_constant__ FanLseParams<float> p, const __grid_constant__ TcGeom geo) {
     constexpr int NC = (D + 2 + 3) / 4, KB = 4 * NC, KT = 4 * KB;          // KT = K extent of the MMA (<= 80)
     constexpr int KSTEPS = KT / 8;
+    constexpr int TC_EPI = TcRoles<BWD>::EPI, TC_BPW = TcRoles<BWD>::BPW, TC_BW = TcRoles<BWD>::BW,
+                  TC_MMA_WARP = TcRoles<BWD>::MMA_WARP;
     constexpr uint32_t LBO = TC_N * 16, SBO = 8 * 16;                      // [chunk][TC_N rows][16 B]
     constexpr uint32_t OPER = 4 * NC * LBO;                                // bytes of one operand part of one stage
     constexpr uint32_t A_HI = 0, A_LO = KT, D_COL = 2 * KT;
@@ -180,7 +190,6 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
     uint64_t* tfull = bars + 2 * TC_STAGES;                                // [TC_ACC]     MMA -> epilogue
     uint64_t* tempty = bars + 2 * TC_STAGES + TC_ACC;                      // [TC_ACC]     epilogue -> MMA
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 2 * TC_ACC);
-    float* xpose = (float*)(tmem_slot + 4);                                // adjoint: [8 epilogue warps][32][36]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float LS = 1.4426950408889634f;
@@ -339,26 +348,25 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
                     if (rho < n_rho && f < p.F)
                         p.out[ooff[g] + f * o_f] = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + p.cadd;
                 } else {
-                    // weights of this (rho, f) row, then the sum over f (the 32 lanes of this warp) through a
-                    // per-warp shared-memory transpose: 8 STS.128 + 32 LDS per lane, fixed summation order
+                    // weights of this (rho, f) row, then the sum over f (the 32 lanes of this warp): fixed-order
+                    // butterfly reduce-scatter, lane j ends with the sum for kappa = j (31 shuffles for 32 columns)
                     const float2 nl2 = make_float2(-lz[g], -lz[g]), g2 = make_float2(gz[g], gz[g]);
-                    float* trow = xpose + (size_t)warp * (32 * 36);
-                    __syncwarp();
+                    float wv[32];
 #pragma unroll
-                    for (int k = 0; k < 32; k += 4) {
+                    for (int k = 0; k < 32; k += 2) {
                         const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), nl2);
-                        const float2 d1 = __fadd2_rn(make_float2(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3])), nl2);
                         const float2 e0 = __fmul2_rn(make_float2(FastExp<float>::ex(d0.x), FastExp<float>::ex(d0.y)), g2);
-                        const float2 e1 = __fmul2_rn(make_float2(FastExp<float>::ex(d1.x), FastExp<float>::ex(d1.y)), g2);
-                        *reinterpret_cast<float4*>(trow + lane * 36 + k) = make_float4(e0.x, e0.y, e1.x, e1.y);
+                        wv[k] = e0.x; wv[k + 1] = e0.y;
                     }
-                    __syncwarp();
-                    float wv[1];
-                    {
-                        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                        for (int q = 0; q < 32; q += 2) { a0 += trow[q * 36 + lane]; a1 += trow[(q + 1) * 36 + lane]; }
-                        wv[0] = a0 + a1;
+                    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const bool up = (lane & off) != 0;
+                            const float send = up ? wv[i] : wv[i + off];
+                            const float mine = up ? wv[i + off] : wv[i];
+                            wv[i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
                     }
                     if (rho < n_rho && lane < Kk) p.gS[(i64)rho * Kk + lane] = wv[0];
                 }
@@ -393,61 +401,70 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
         }
     } else {
         // ---------------------------------------------------------------- builders: warp (g, rs), lane = kappa
-        const int bw = warp - TC_MMA_WARP - 1, g = bw >> 2, rs = bw & 3, kz = lane;
+        const int bw = warp - TC_MMA_WARP - 1, gq = bw >> 2, rs = bw & 3, kz = lane;
         const int vk = (int)p.v_k, lk = (int)p.l_k, vev = (int)p.v_ev, lev = (int)p.l_ev, nb = geo.nb, vec2 = geo.vec2;
-        TcIdx cur, step;
-        cur.set(TC_RHO * blockIdx.x + 4 * g + rs, geo);
+        TcIdx cur[TC_BPW], step;
+#pragma unroll
+        for (int h = 0; h < TC_BPW; ++h) cur[h].set(TC_RHO * blockIdx.x + 4 * (gq + h * (TC_G / TC_BPW)) + rs, geo);
         step.set(TC_RHO * gridDim.x, geo);
         unsigned it = 0;
         for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ps = (it / TC_STAGES) & 1;
-            const bool live = TC_RHO * tile + 4 * g + rs < n_rho && kz < Kk;
-            const int voff = cur.dot(geo.vs), loff = cur.dot(geo.ls);
-            int boff[TC_NB];
+            float t[TC_BPW][KB];
 #pragma unroll
-            for (int i = 0; i < TC_NB; ++i) boff[i] = cur.dot(geo.bs[i]);
-            cur.add(step, geo);
-            float t[KB];
+            for (int h = 0; h < TC_BPW; ++h) {
+                const int g = gq + h * (TC_G / TC_BPW);
+                const bool live = TC_RHO * tile + 4 * g + rs < n_rho && kz < Kk;
+                const int voff = cur[h].dot(geo.vs), loff = cur[h].dot(geo.ls);
+                int boff[TC_NB];
 #pragma unroll
-            for (int dd = 0; dd < KB; ++dd) t[dd] = 0.f;
-            if (live) {
-                float b = 0.f;
+                for (int i = 0; i < TC_NB; ++i) boff[i] = cur[h].dot(geo.bs[i]);
+                cur[h].add(step, geo);
 #pragma unroll
-                for (int i = 0; i < TC_NB; ++i) if (i < nb) b += geo.bc[i] * p.b[i][boff[i] + kz * geo.bk[i]];
-                const float* vp = p.v + voff + kz * vk;
-                const float* lp = p.l + loff + kz * lk;
-                if (vec2) {
+                for (int dd = 0; dd < KB; ++dd) t[h][dd] = 0.f;
+                if (live) {
+                    float b = 0.f;
 #pragma unroll
-                    for (int q = 0; q < D / 2; ++q) {
-                        const float2 vv = *reinterpret_cast<const float2*>(vp + 2 * q);
-                        const float2 ll = *reinterpret_cast<const float2*>(lp + 2 * q);
-                        const float d0 = vv.x - ll.x, d1 = vv.y - ll.y;
-                        t[2 * q] = d0 * d0; t[2 * q + 1] = d1 * d1;
+                    for (int i = 0; i < TC_NB; ++i) if (i < nb) b += geo.bc[i] * p.b[i][boff[i] + kz * geo.bk[i]];
+                    const float* vp = p.v + voff + kz * vk;
+                    const float* lp = p.l + loff + kz * lk;
+                    if (vec2) {
+#pragma unroll
+                        for (int q = 0; q < D / 2; ++q) {
+                            const float2 vv = *reinterpret_cast<const float2*>(vp + 2 * q);
+                            const float2 ll = *reinterpret_cast<const float2*>(lp + 2 * q);
+                            const float d0 = vv.x - ll.x, d1 = vv.y - ll.y;
+                            t[h][2 * q] = d0 * d0; t[h][2 * q + 1] = d1 * d1;
+                        }
+                    } else {
+#pragma unroll
+                        for (int dd = 0; dd < D; ++dd) { const float df = vp[dd * vev] - lp[dd * lev]; t[h][dd] = df * df; }
                     }
-                } else {
-#pragma unroll
-                    for (int dd = 0; dd < D; ++dd) { const float df = vp[dd * vev] - lp[dd * lev]; t[dd] = df * df; }
+                    t[h][D] = b * LS;
+                    t[h][D + 1] = 1.f;
                 }
-                t[D] = b * LS;
-                t[D + 1] = 1.f;
             }
             MBAR_WAIT(&empty[s], ps ^ 1, dbg0);
             if (kz < Kk) {                       // rows of rho >= n_rho are written as zeros: finite, masked later
                 float* bh = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER);
                 float* bl = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER);
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    // the tensor core reads only the 19 TF32 bits of each word: the raw fp32 value IS the "hi" part
-                    // (truncated by the hardware) and lo = t - trunc(t) is its exact remainder
-                    float4 h, l;
-                    h.x = t[4 * c + 0]; l.x = h.x - __uint_as_float(__float_as_uint(h.x) & 0xFFFFE000u);
-                    h.y = t[4 * c + 1]; l.y = h.y - __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u);
-                    h.z = t[4 * c + 2]; l.z = h.z - __uint_as_float(__float_as_uint(h.z) & 0xFFFFE000u);
-                    h.w = t[4 * c + 3]; l.w = h.w - __uint_as_float(__float_as_uint(h.w) & 0xFFFFE000u);
-                    const int off = ((rs * NC + c) * TC_N + 32 * g + kz) * 4;
-                    *reinterpret_cast<float4*>(bh + off) = h;
-                    *reinterpret_cast<float4*>(bl + off) = l;
+                for (int h = 0; h < TC_BPW; ++h) {
+                    const int g = gq + h * (TC_G / TC_BPW);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        // the tensor core reads only the 19 TF32 bits of each word: the raw fp32 value IS the "hi" part
+                        // (truncated by the hardware) and lo = t - trunc(t) is its exact remainder
+                        float4 hh, l;
+                        hh.x = t[h][4 * c + 0]; l.x = hh.x - __uint_as_float(__float_as_uint(hh.x) & 0xFFFFE000u);
+                        hh.y = t[h][4 * c + 1]; l.y = hh.y - __uint_as_float(__float_as_uint(hh.y) & 0xFFFFE000u);
+                        hh.z = t[h][4 * c + 2]; l.z = hh.z - __uint_as_float(__float_as_uint(hh.z) & 0xFFFFE000u);
+                        hh.w = t[h][4 * c + 3]; l.w = hh.w - __uint_as_float(__float_as_uint(hh.w) & 0xFFFFE000u);
+                        const int off = ((rs * NC + c) * TC_N + 32 * g + kz) * 4;
+                        *reinterpret_cast<float4*>(bh + off) = hh;
+                        *reinterpret_cast<float4*>(bl + off) = l;
+                    }
                 }
             }
             fence_async_smem();
@@ -470,8 +487,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) fan_lse_tc_kernel(const __gr
 template <int D>
 static int launch_fan_lse_tc_D(const FanLseParams<float>& p, bool bwd, cudaStream_t stream, int sm_count) {
     constexpr int NC = (D + 2 + 3) / 4;
-    const size_t smem = (size_t)TC_STAGES * 2 * (4 * NC * TC_N * 16) + (2 * TC_STAGES + 2 * TC_ACC) * 8 + 16 +
-                        (bwd ? (size_t)4 * TC_EPI * 32 * 36 * 4 : 0);
+    const size_t smem = (size_t)TC_STAGES * 2 * (4 * NC * TC_N * 16) + (2 * TC_STAGES + 2 * TC_ACC) * 8 + 16;
     bool ev2 = (D % 2 == 0) && p.v_ev == 1 && p.l_ev == 1 && p.v_k % 2 == 0 && p.l_k % 2 == 0 &&
                ((uintptr_t)p.v % 8 == 0) && ((uintptr_t)p.l % 8 == 0);
     for (int k = 0; k < p.rd.nd && ev2; ++k) ev2 = (p.vstride[k] % 2 == 0) && (p.lstride[k] % 2 == 0);
