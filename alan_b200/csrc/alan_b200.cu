@@ -18,7 +18,7 @@
 
 enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
 enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
-       OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12 };
+       OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13 };
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -398,6 +398,32 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 read_opnd(r, c, p.b, p.d.nd, false);
                 if (p.d.nd == p.d.n_a) { p.a.stride[p.d.n_a] = 0; p.b.stride[p.d.n_a] = 0; }
                 dot_kernel<T><<<grid_for(p.n_out, 256, c), 256, 0, c.stream>>>(p);
+                break;
+            }
+            case OP_FAN_BWD: {
+                FanBwdParams<T> q;
+                memset(&q, 0, sizeof(q));
+                FanParams<T>& p = q.f;
+                int which = r.i32();
+                p.out = (T*)tref(r, c);                      // G: adjoint of the factor
+                q.R = (T*)tref(r, c);
+                q.partial = (T*)tref(r, c);
+                q.partial_w = (T*)tref(r, c);
+                q.n_cta = r.i32();
+                int D = r.i32();
+                int nrd = r.i32();
+                p.rd.nd = nrd; p.rd.n_a = nrd;
+                p.n_rows = 1;
+                for (int k = 0; k < nrd; ++k) { p.rd.size[k] = r.i32(); p.n_rows *= p.rd.size[k]; }
+                for (int k = 0; k < nrd; ++k) p.vstride[k] = r.i64v();
+                for (int k = 0; k < nrd; ++k) p.lstride[k] = r.i64v();
+                for (int k = 0; k < nrd; ++k) p.ostride[k] = r.i64v();
+                p.v = (const T*)tref(r, c); p.v_ev = r.i64v();
+                p.l = (const T*)tref(r, c); p.l_ev = r.i64v();
+                p.s = (const T*)tref(r, c); p.s_f = r.i64v(); p.s_ev = r.i64v();
+                p.F = r.i32();
+                p.o_f = r.i64v();
+                if (launch_fan_bwd<T>(q, D, which, c.stream, c.sm_count)) return fail("fan_bwd: unsupported event extent");
                 break;
             }
             case OP_BERN_DOT: {

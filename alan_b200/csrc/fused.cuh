@@ -142,6 +142,141 @@ static int launch_fan(const FanParams<T>& p, int D, cudaStream_t stream, int sm_
 }
 
 
+// ------------------------------------------------------------------------------------------
+// Adjoint of normal_fan (the VI / reparameterised path: gradients w.r.t. the sample values, the
+// location and the scale).  G[row, f] is the adjoint of out[row, f]; with T = (v - l)^2,
+//     R[row, d]  = 2 (v - l) sum_f G[row, f] w[f, d]          -> d/dv = -R, d/dl = +R (summed by reduce ops)
+//     V[f, d]    = sum_row G[row, f] T[row, d],  Wsum[f] = sum_row G[row, f]
+//                                                          -> d/dscale[f, d] = V / scale^3 - Wsum / scale
+// Two kernels: fan_bwd_rows (one thread per row, w broadcast from shared memory) writes R;
+// fan_bwd_scale (lanes = f, warps stride over rows) writes per-CTA partials [cta][f][D] and [cta][f] that a
+// fixed-order reduce op sums.  reference: autograd through TorchDimDist.log_prob (TorchDimDist.py:127-162).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct FanBwdParams {
+    FanParams<T> f;                       // geometry of the forward factor; f.out = G (adjoint of out)
+    T* R;                                 // [n_rows, D] contiguous
+    T* partial;                           // [n_cta, F, D]   per-CTA partials of V
+    T* partial_w;                         // [n_cta, F]      per-CTA partials of Wsum
+    int n_cta;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) fan_bwd_rows_kernel(const __grid_constant__ FanBwdParams<T> q) {
+    const FanParams<T>& p = q.f;
+    extern __shared__ __align__(16) unsigned char fan_smem[];
+    T* W = (T*)fan_smem;                  // [F][D]   1 / (2 scale^2)
+    for (int i = threadIdx.x; i < p.F * D; i += blockDim.x) {
+        int f = i / D, d = i - f * D;
+        T sc = p.s[f * p.s_f + d * p.s_ev];
+        W[i] = T(1) / (T(2) * (sc * sc));
+    }
+    __syncthreads();
+    for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < p.n_rows; row += (i64)gridDim.x * blockDim.x) {
+        i64 voff = 0, loff = 0, goff = 0, lin = row;
+#pragma unroll 1
+        for (int k = p.rd.nd - 1; k >= 0; --k) {
+            int sz = p.rd.size[k];
+            i64 qq = lin / sz;
+            int ix = (int)(lin - qq * sz);
+            lin = qq;
+            voff += ix * p.vstride[k]; loff += ix * p.lstride[k]; goff += ix * p.ostride[k];
+        }
+        T df[D], U[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) { df[d] = p.v[voff + d * p.v_ev] - p.l[loff + d * p.l_ev]; U[d] = T(0); }
+        for (int f = 0; f < p.F; ++f) {
+            const T g = p.out[goff + (i64)f * p.o_f];
+            const T* w = W + f * D;
+#pragma unroll
+            for (int d = 0; d < D; ++d) U[d] += g * w[d];
+        }
+        // out = -sum T w - c  =>  d out / d v = -2 (v - l) w
+#pragma unroll
+        for (int d = 0; d < D; ++d) q.R[row * D + d] = T(2) * df[d] * U[d];
+    }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) fan_bwd_scale_kernel(const __grid_constant__ FanBwdParams<T> q) {
+    const FanParams<T>& p = q.f;
+    __shared__ T red[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const i64 rows_per_cta = (p.n_rows + gridDim.x - 1) / gridDim.x;
+    const i64 r0 = (i64)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < p.n_rows ? r0 + rows_per_cta : p.n_rows;
+    for (int f0 = 0; f0 < p.F; f0 += 32) {
+        const int f = f0 + lane;
+        T acc[D + 1];
+#pragma unroll
+        for (int d = 0; d <= D; ++d) acc[d] = T(0);
+        for (i64 row = r0 + wid; row < r1; row += nw) {
+            i64 voff = 0, loff = 0, goff = 0, lin = row;
+#pragma unroll 1
+            for (int k = p.rd.nd - 1; k >= 0; --k) {
+                int sz = p.rd.size[k];
+                i64 qq = lin / sz;
+                int ix = (int)(lin - qq * sz);
+                lin = qq;
+                voff += ix * p.vstride[k]; loff += ix * p.lstride[k]; goff += ix * p.ostride[k];
+            }
+            const T g = f < p.F ? p.out[goff + (i64)f * p.o_f] : T(0);
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const T df = p.v[voff + d * p.v_ev] - p.l[loff + d * p.l_ev];      // same address on every lane: broadcast
+                acc[d] += g * (df * df);
+            }
+            acc[D] += g;
+        }
+        // fixed-order sum over the warps of the CTA
+#pragma unroll 1
+        for (int d = 0; d <= D; ++d) {
+            red[wid][lane] = acc[d];
+            __syncthreads();
+            if (wid == 0 && f < p.F) {
+                T a = T(0);
+                for (int w = 0; w < nw; ++w) a += red[w][lane];
+                if (d < D) q.partial[((i64)blockIdx.x * p.F + f) * D + d] = a;
+                else q.partial_w[(i64)blockIdx.x * p.F + f] = a;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <typename T, int D>
+static void launch_fan_bwd_D(const FanBwdParams<T>& q, int which, cudaStream_t stream, int sm_count) {
+    if (which == 0) {
+        size_t smem = (size_t)q.f.F * D * sizeof(T);
+        i64 blocks = (q.f.n_rows + 255) / 256, cap = (i64)sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(fan_bwd_rows_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fan_bwd_rows_kernel<T, D><<<(int)blocks, 256, smem, stream>>>(q);
+    } else {
+        fan_bwd_scale_kernel<T, D><<<q.n_cta, 256, 0, stream>>>(q);
+    }
+}
+
+template <typename T>
+static int launch_fan_bwd(const FanBwdParams<T>& q, int D, int which, cudaStream_t stream, int sm_count) {
+    switch (D) {
+        case 1: launch_fan_bwd_D<T, 1>(q, which, stream, sm_count); break;
+        case 2: launch_fan_bwd_D<T, 2>(q, which, stream, sm_count); break;
+        case 3: launch_fan_bwd_D<T, 3>(q, which, stream, sm_count); break;
+        case 4: launch_fan_bwd_D<T, 4>(q, which, stream, sm_count); break;
+        case 6: launch_fan_bwd_D<T, 6>(q, which, stream, sm_count); break;
+        case 8: launch_fan_bwd_D<T, 8>(q, which, stream, sm_count); break;
+        case 12: launch_fan_bwd_D<T, 12>(q, which, stream, sm_count); break;
+        case 16: launch_fan_bwd_D<T, 16>(q, which, stream, sm_count); break;
+        case 18: launch_fan_bwd_D<T, 18>(q, which, stream, sm_count); break;
+        case 24: launch_fan_bwd_D<T, 24>(q, which, stream, sm_count); break;
+        case 32: launch_fan_bwd_D<T, 32>(q, which, stream, sm_count); break;
+        default: return 1;
+    }
+    return 0;
+}
+
+
 // dot: out[o] = sum_e a[o,e] * b[o,e] over the trailing event dim, both operands broadcast
 // through strides.  Covers `lambda z, x: z @ x` (movielens.py:40) without the factor VM.
 template <typename T>

@@ -33,7 +33,7 @@ MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
 SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
 OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY, OP_DOT, \
-    OP_FAN_LSE, OP_BERN_DOT = range(1, 13)
+    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD = range(1, 14)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
 
@@ -401,6 +401,36 @@ class NormalFanOp(Op):
         fdim = ('ax', self.fan_axis, self.F) if self.fan_axis else None
         w.tref(self.s.pt); w.i64(self.s.stride(fdim) if fdim else 0); w.i64(self.s.stride(ev))
         w.i32(self.F)
+        w.i64(o.stride(fdim) if fdim else 0)
+
+
+class NormalFanBwdOp(Op):
+    """Adjoint of NormalFanOp (csrc/fused.cuh fan_bwd_rows_kernel / fan_bwd_scale_kernel).
+    which = 0: R[rows, d] = 2 (v - l) sum_f G[rows, f] / (2 scale[f,d]^2);
+    which = 1: per-CTA partials of V[f, d] = sum_rows G (v - l)^2 and Wsum[f] = sum_rows G."""
+    code = OP_FAN_BWD
+
+    def __init__(self, which, fan, gout, R, partial, partial_w, n_cta):
+        self.which, self.fan, self.gout, self.R, self.partial, self.partial_w, self.n_cta = \
+            which, fan, gout, R, partial, partial_w, n_cta
+
+    def payload(self, w):
+        f = self.fan
+        w.i32(self.which); w.tref(self.gout); w.tref(self.R); w.tref(self.partial); w.tref(self.partial_w)
+        w.i32(self.n_cta)
+        w.i32(f.D); w.i32(len(f.rows))
+        for d in f.rows:
+            w.i32(d[2])
+        o = plain(f.out)
+        for lf in (f.v, f.l, o):
+            for d in f.rows:
+                w.i64(lf.stride(d))
+        ev = ('ev', 0, f.D)
+        w.tref(f.v.pt); w.i64(f.v.stride(ev))
+        w.tref(f.l.pt); w.i64(f.l.stride(ev))
+        fdim = ('ax', f.fan_axis, f.F) if f.fan_axis else None
+        w.tref(f.s.pt); w.i64(f.s.stride(fdim) if fdim else 0); w.i64(f.s.stride(ev))
+        w.i32(f.F)
         w.i64(o.stride(fdim) if fdim else 0)
 
 
@@ -924,7 +954,8 @@ class Planner:
         out, op = self.emit_expr(body, nred='all', tag=tag, append=False)
         fan = self._try_normal_fan(opname, operands, body, out, tag) if self.fast_paths else None
         if fan is not None:
-            fan.autodiff_as = op            # adjoints are derived from the generic form of the same factor
+            fan.autodiff_as = op            # adjoints are derived from the generic form of the same factor ...
+            op.fan_twin = fan               # ... unless the fused adjoint kernels apply (build_backward)
             self.fan_by_out[out.id] = fan
             self.emit(fan)
         else:
@@ -1253,6 +1284,7 @@ class Planner:
         all_fwd = []
         seg_of = {}
         sharded_ids = set()
+        seg_ops = set(op for seg in self.fwd_segments for op in seg)
         for si, seg in enumerate(self.fwd_segments):
             for op in seg:
                 lop = getattr(op, 'autodiff_as', None)
@@ -1318,7 +1350,10 @@ class Planner:
                 continue
             out_list = segs[len(self.fwd_segments) - 1 - seg_of[id(op)]]
             gout = adj.get(op.out.id)
-            if isinstance(op, ExprOp):
+            if isinstance(op, ExprOp) and self.fast_paths and getattr(op, 'fan_twin', None) is not None \
+                    and op.fan_twin in seg_ops:
+                self._fan_backward(op, op.fan_twin, gout, out_list, adjoint, needs, contribution_scale)
+            elif isinstance(op, ExprOp):
                 dims = op.keep + op.red
                 for li, lf in enumerate(op.codeobj.leaves):
                     if lf.pt.id not in needs:
@@ -1421,6 +1456,63 @@ class Planner:
         if self.shard_plate is not None:
             plan.global_grads = [n for n in grad_names if self.shard_plate not in self.inputs[n].axes]
         return segs
+
+    def _fan_backward(self, op, fan, gout, out_list, adjoint, needs, contribution_scale):
+        """Adjoint of a materialised normal_fan factor through the fused kernels (reparameterised / VI
+        gradients): R = d out / d(-v) per row, reduced by plain sums into the value and location adjoints;
+        V and Wsum partials, reduced in a fixed order, give the scale adjoint."""
+        D, F = fan.D, fan.F
+        ev = ('ev', 0, D)
+        rows = list(fan.rows)
+        n_rows = _prod(d[2] for d in rows)
+        dummy = self.ws_raw(1, name='fan_bwd_unused')
+        want_rows = [(lf, sg) for lf, sg in ((fan.v, -1.0), (fan.l, 1.0)) if lf.pt.id in needs]
+        if want_rows:
+            R = self.ws_raw(n_rows * D, name='fan_R')
+            out_list.append(NormalFanBwdOp(0, fan, gout, R, dummy, dummy, 1))
+            own = rows + [ev]
+            for lf, sg in want_rows:
+                g = adjoint(lf.pt)
+                kept = [d for d in own if lf.stride(d) != 0]
+                kept.sort(key=lambda d: -lf.stride(d))
+                loop = [d for d in own if lf.stride(d) == 0]
+                n_kept = _prod(d[2] for d in kept)
+                if n_kept != lf.pt.numel:
+                    raise Exception(f"adjoint of {lf.pt}: fan factor does not cover the tensor")
+                scale = sg * contribution_scale(op, lf.pt, g)
+                nsplit = _choose_split(n_kept, _prod(d[2] for d in loop))
+                facs = [(_OwnDims(R, own), 1.0)]
+                if nsplit > 1:
+                    part = self.ws_raw(nsplit * n_kept, name='partial_adj')
+                    out_list.append(ReduceOp(R_SUM, part, kept, loop, facs, nsplit=nsplit))
+                    od = [('fl', 0, n_kept)]
+                    out_list.append(ReduceOp(R_SUM, g, od, [('sp', 0, nsplit)],
+                                             [(_PartialRef(part, od, nsplit), 1.0)], acc=1, scale=scale))
+                else:
+                    out_list.append(ReduceOp(R_SUM, g, kept, loop, facs, acc=1, scale=scale))
+        if fan.s.pt.id in needs:
+            s = fan.s
+            g = adjoint(s.pt)
+            n_cta = int(max(1, min(296, n_rows // 512)))
+            part_v = self.ws_raw(n_cta * F * D, name='fan_V_partial')
+            part_w = self.ws_raw(n_cta * F, name='fan_W_partial')
+            out_list.append(NormalFanBwdOp(1, fan, gout, dummy, part_v, part_w, n_cta))
+            Vt = self.ws_raw(F * D, name='fan_V')
+            Wt = self.ws_raw(F, name='fan_Wsum')
+            for src, dst, n in ((part_v, Vt, F * D), (part_w, Wt, F)):
+                od = [('fl', 0, n)]
+                out_list.append(ReduceOp(R_SUM, dst, od, [('sp', 0, n_cta)], [(_PartialRef(src, od, n_cta), 1.0)]))
+            fdim = ('ax', fan.fan_axis, F) if fan.fan_axis else ('ax', '__nofan', 1)
+            all_dims = [fdim, ev]
+            keep = [d for d in all_dims if s.stride(d) != 0]
+            keep.sort(key=lambda d: -s.stride(d))
+            red = [d for d in all_dims if s.stride(d) == 0 and d[2] > 1]
+            # d out / d scale = T / scale^3 - 1 / scale, so  g_s += V / s^3 - Wsum / s
+            L, MUL, DIV, SUB = VOPS['load'], VOPS['mul'], VOPS['div'], VOPS['sub']
+            instrs = [(L, 0, 0, 0, 0, 0), (L, 1, 1, 0, 0, 0), (L, 2, 2, 0, 0, 0), (MUL, 3, 2, 2, 0, 0), (MUL, 4, 3, 2, 0, 0),
+                      (DIV, 5, 0, 4, 0, 0), (DIV, 6, 1, 2, 0, 0), (SUB, 7, 5, 6, 0, 0)]
+            code = Code(instrs, [], 7, [_OwnDims(Vt, [fdim, ev]), _OwnDims(Wt, [fdim]), s])
+            out_list.append(ExprOp(g, keep, red, code, acc=1, scale=contribution_scale(op, s.pt, g), tag='fan_scale_adj'))
 
     # -- resampling (sample_logpq.py:17-107, reduce_Ks.py:35-83) ---------------------------------
     def build_sampling(self):

@@ -172,6 +172,36 @@ class Emu:
                                      lse_dims=r.od, gout_dims=op.gout_dims if op.gout_dims is not None else r.od,
                                      cadd=r.cadd))
 
+    def op_NormalFanBwdOp(self, op):
+        f = op.fan
+        fdim = ('ax', f.fan_axis, f.F) if f.fan_axis else ('ax', '__nofan', 1)
+        ev = ('ev', 0, f.D)
+        dims = list(f.rows) + [fdim, ev]
+        grid = self.grid(dims)
+        shape = [d[2] for d in dims]
+        v = self.load_leaf(f.v, dims, grid)[0] + t.zeros(shape, dtype=self.dtype)
+        l = self.load_leaf(f.l, dims, grid)[0] + t.zeros(shape, dtype=self.dtype)
+        sc = self.load_leaf(f.s, dims, grid)[0] + t.zeros(shape, dtype=self.dtype)
+        gb, gbase = self.buf(op.gout)
+        o = PL.plain(f.out)
+        G = gb[self.offsets([o.stride(d) if d[0] != 'ev' else 0 for d in dims], grid) + gbase]
+        df = v - l
+        nr = len(f.rows)
+        if op.which == 0:
+            R = (2 * df * G / (2 * sc * sc)).sum(nr)                      # sum over the fan axis -> [rows..., D]
+            out, base = self.buf(op.R)
+            out[base:base + R.numel()] = R.reshape(-1)
+        else:
+            rdims = tuple(range(nr))
+            V = (G * df * df).sum(rdims) if rdims else G * df * df        # [F, D]
+            Ws = G[..., 0].sum(rdims) if rdims else G[..., 0]              # [F]
+            pv, bv = self.buf(op.partial)
+            pw, bw = self.buf(op.partial_w)
+            pv[bv:bv + op.n_cta * V.numel()] = 0
+            pw[bw:bw + op.n_cta * Ws.numel()] = 0
+            pv[bv:bv + V.numel()] = V.reshape(-1)
+            pw[bw:bw + Ws.numel()] = Ws.reshape(-1)
+
     def op_BernDotSumOp(self, op):
         for g in op.gen_ops:
             getattr(self, 'op_' + type(g).__name__)(g)
