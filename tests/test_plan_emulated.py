@@ -147,6 +147,16 @@ def test_fused_paths_selected_and_match_oracle(dtype):
     for k, rr in zip(names, rg):
         assert rel_err(grad_as(comp, grads, k, ipg[k].axes), rr) < 30 * tl, k
     # a VI-style request (gradient w.r.t. the sample) must fall back to the materialised factor
-    comp_vi = Compiled(P, Q, sample, ip, data, grad_names=names + ['z', 'mu_z'])
+    comp_vi = Compiled(P, Q, sample, ip, data, grad_names=names + ['z', 'mu_z', 'psi_z'])
     kinds = [type(op).__name__ for prog in comp_vi.plan.programs for op in prog]
-    assert 'FanLseOp' not in kinds and 'NormalFanOp' in kinds and 'DotOp' in kinds
+    assert 'FanLseOp' not in kinds and 'NormalFanOp' in kinds and 'DotOp' in kinds and 'NormalFanBwdOp' in kinds
+    vnames = names + ['z', 'mu_z', 'psi_z']
+    lp_vi, grads_vi, _ = run_fwd_bwd(comp_vi, comp_vi.canonical_inputs(sample, ip, data))
+    sg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in sample.items()}
+    ipg = {k: NT(v.t.clone().requires_grad_() if k in names else v.t, v.axes) for k, v in ip.items()}
+    ref = O.elbo(P, Q, sg, ipg, data)
+    rg = t.autograd.grad(ref, [ipg[k].t for k in names] + [sg[k].t for k in ('z', 'mu_z', 'psi_z')])
+    assert rel_err(lp_vi, ref) < tl
+    for k, rr in zip(vnames, rg):
+        axes = ipg[k].axes if k in ipg else sg[k].axes
+        assert rel_err(grad_as(comp_vi, grads_vi, k, axes), rr) < 30 * tl, k

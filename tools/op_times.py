@@ -33,9 +33,10 @@ if name.startswith("radon"):
     plan = comp.plan
     tensors = [x.cuda() for x in comp.canonical_inputs(sample, ip, data, elf)]
 else:
-    cfg = bench.WORKLOADS[name]
+    vi = name.endswith("vi")                  # e.g. cfg5vi: gradients w.r.t. the samples too (reparameterised path)
+    cfg = bench.WORKLOADS[name[:-2] if vi else name]
     P, Q, sample, ip, data, params = bench.make_problem(cfg, 0, cfg["M"])
-    comp = Compiled(P, Q, sample, ip, data, grad_names=params)
+    comp = Compiled(P, Q, sample, ip, data, grad_names=params + (['z', 'mu_z', 'psi_z'] if vi else []))
     run = Runner(comp, "cuda:0")
     plan = comp.plan
     tensors = [x.cuda() for x in comp.canonical_inputs(sample, ip, data)]
