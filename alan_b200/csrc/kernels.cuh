@@ -319,11 +319,26 @@ template <int NRED>
 __device__ __forceinline__ i64 red_off(const Dims& d, const Opnd& o, i64 j) {
     if (NRED == 1) return j * o.stride[d.n_a];
     if (NRED == 2) {
-        int s1 = d.size[d.n_a + 1];
+        const unsigned s1 = (unsigned)d.size[d.n_a + 1];
+        if ((j >> 31) == 0) {
+            const unsigned q = (unsigned)j / s1;
+            return (i64)q * o.stride[d.n_a] + (i64)((unsigned)j - q * s1) * o.stride[d.n_a + 1];
+        }
         i64 q = j / s1;
         return q * o.stride[d.n_a] + (j - q * s1) * o.stride[d.n_a + 1];
     }
     i64 off = 0;
+    if ((j >> 31) == 0) {
+        unsigned l = (unsigned)j;
+#pragma unroll 1
+        for (int k = d.nd - 1; k >= d.n_a; --k) {
+            const unsigned s = (unsigned)d.size[k];
+            const unsigned q = l / s;
+            off += (i64)(l - q * s) * o.stride[k];
+            l = q;
+        }
+        return off;
+    }
 #pragma unroll 1
     for (int k = d.nd - 1; k >= d.n_a; --k) {
         int s = d.size[k];
