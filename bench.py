@@ -350,7 +350,11 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
             else:
                 roof = dict(bound="fp32", achieved=m["flops"] / (top_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s")
             roof["frac"] = roof["achieved"] / roof["peak"]
-            roof.update(traffic=None, kernel=f"{m['kind']}:{m['tag']}", kernel_ms=top_ms,
+            # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this command
+            # at cfg-5 on one GPU (profiles/r01_fan_lse_tc_full.md: dram__bytes_read.sum + dram__bytes_write.sum)
+            ncu_traffic = {"FanLseBwdOp": 60.07e6 + 5.50e6, "FanLseOp": 24.06e6 + 0.13e6}
+            traffic = ncu_traffic.get(m["kind"]) if (tc_path and cfg["M"] // max(world, 1) == 10000 and cfg["N"] == 50) else None
+            roof.update(traffic=traffic, kernel=f"{m['kind']}:{m['tag']}", kernel_ms=top_ms,
                         share_of_step=top_ms / total, peak_source=pk["source"],
                         algorithmic_bytes=m["bytes"], algorithmic_flops=m["flops"],
                         hbm_frac=m["bytes"] / (top_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
@@ -422,6 +426,8 @@ def main():
         if rank != 0:
             return
         steps = min(args.steps, 5)
+        if args.scaling == "weak" and args.gpus > 1:          # same job description as the b200 arm at this N
+            cfg = dict(cfg, M=cfg["M"] * args.gpus, name=cfg["name"] + f"_x{args.gpus}_users")
         r = run_reference(args, cfg, iters=steps, warmup=min(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
