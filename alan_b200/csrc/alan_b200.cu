@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "fused.cuh"
 #include "fan_tc.cuh"
+#include "fan_tc2.cuh"
 #include <type_traits>
 #include <cstdlib>
 
@@ -46,6 +47,8 @@ struct alan_b200_plan {
     bool use_graphs = true;
     bool use_seq = false;          // run consecutive small ops as one launch (ALAN_B200_SEQ=1 at plan creation: on)
     bool use_tc = true;            // fan_lse on tcgen05 where the shape allows (ALAN_B200_NO_TC=1 at plan creation: FFMA2 kernel)
+    bool use_tc2 = true;           // dense formulation (fan_tc2.cuh) where the loc is independent of the value's axes
+                                   // (ALAN_B200_TC_BLOCKDIAG=1 at plan creation: block-diagonal kernel only)
     // graphs cannot be captured on / launched into the legacy default stream: calls that arrive on it are
     // forwarded to this private stream, ordered by a pair of events
     mutable cudaStream_t side = nullptr;
@@ -383,7 +386,9 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 }
                 int rc = -1;
                 if constexpr (std::is_same<T, float>::value) {
-                    if (plan->use_tc && tc::fan_lse_tc_supported(p, D)) rc = tc::launch_fan_lse_tc(p, D, bwd != 0, c.stream, c.sm_count);
+                    if (plan->use_tc && plan->use_tc2 && tc::fan_lse_tc2_supported(p, D, bwd != 0))
+                        rc = tc::launch_fan_lse_tc2(p, D, bwd != 0, c.stream, c.sm_count);
+                    else if (plan->use_tc && tc::fan_lse_tc_supported(p, D)) rc = tc::launch_fan_lse_tc(p, D, bwd != 0, c.stream, c.sm_count);
                 }
                 if (rc < 0) rc = launch_fan_lse<T>(p, D, bwd != 0, c.stream, c.sm_count);
                 if (rc) return fail(rc == 1 ? "fan_lse: unsupported event extent" : rc == 2 ? "fan_lse: tile does not fit shared memory" : "fan_lse: strides exceed 32-bit tile addressing");
@@ -489,6 +494,7 @@ int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** 
     // (end-to-end +5..20 %).  ALAN_B200_GRAPH=1 turns it on for host-bound callers.
     p->use_graphs = getenv("ALAN_B200_GRAPH") != nullptr;
     p->use_tc = getenv("ALAN_B200_NO_TC") == nullptr;
+    p->use_tc2 = getenv("ALAN_B200_TC_BLOCKDIAG") == nullptr;
     // Opt-in: halves the launch count of a step, but measured on B200 the device time does not move (the small ops
     // are bound by the latency of their own dependent instruction chains, not by launch overhead).
     p->use_seq = getenv("ALAN_B200_SEQ") != nullptr;

@@ -1,0 +1,535 @@
+// fan_tc2.cuh -- fan_lse on tcgen05 for the case where the Normal's loc does not depend on the value's axes:
+// the DENSE formulation (no block-diagonal operand, the builders touch every value once, not once per loc sample).
+//
+// Contract (fan_lse, fused.cuh):
+//     out[rho, f] = LSE_eps_kappa( b[rho,kappa] - c[f] - sum_d (v[rho,kappa,d] - l[rho,d])^2 w[f,d] ) + cadd
+// Here one rho dim `lam` is special: l depends on lam ONLY, and v and the small factors b do not depend on it
+// (MovieLens-shaped models: v = z[m, K_z, d], l = mu[K_mu, d], w from psi[K_psi, d]: lam = K_mu, f = K_psi).
+// With u = the remaining rho dims ("users") and the wide fan f' = (lam, f), expand the square around a per-d centre
+// cd[d] = mean_lam l[lam,d]  (v' = v - cd, l' = l - cd: identical differences, small cross terms):
+//
+//     log2e S[u,kappa,f'] = sum_d v'^2 (-w log2e) + sum_d v' (2 l' w log2e) + b log2e        - C[f'] log2e
+//                         =         B[(u,kappa), k]  .  A[f', k]                               (k < 2 D + 1)
+//
+//   A (constant per CTA)  rows f' (128 per M tile, up to 4 tiles per CTA = one "group" of 512 fan columns),
+//                         K = 2 D + 1 -> KT;  A_hi in TMEM (tcgen05.st), A_lo in shared memory
+//   B (one stage per block of 4 users)  rows n = (user slot, kappa) = 128,  { v'^2 | v' | b log2e }, hi and lo
+//   D = A B^T (TMEM, 2 stages x 128 columns): lane = f', columns = (user slot, kappa)
+//   C[f'] = sum_d l'^2 w + sum_d log s + D/2 log 2pi does not depend on kappa: it leaves the LSE and is added in
+//   fp32 afterwards.
+// 3xTF32 as in fan_tc.cuh: A_hi B_hi + A_lo B_hi + A_hi B_lo.  15 tcgen05.mma (M128 N128 K8) per (tile, block) at
+// D = 18, against 30 per 16 rho (= 225 per 4 users x 30 lam) in the block-diagonal kernel, and the builders handle
+// n_u Kk D values instead of n_u L Kk D.
+//
+// Roles (11 warps, one persistent CTA per SM; CTA c works on fan group c % NG):
+//   epilogue  2 teams x 4 warps: warp % 4 = TMEM lane quadrant, team e owns user slots 2e, 2e+1 (64 columns) of EVERY
+//             tile; forward: max / ex2 / sum per (user, f'); adjoint: weights accumulated over the tiles of the group
+//             in registers, one fixed-order butterfly per block, team partials combined through shared memory
+//   MMA       1 warp (elected lane), owns the TMEM allocation
+//   builders  2 warps, thread = two B rows (user slot, kappa)
+// The adjoint writes gS[u, lam = g, kappa] for group g (its partial over that group's fan columns) -- the planner's
+// reduce over lam that follows sums the partials; the other lam slots stay zero (zeroed adjoint region).
+#pragma once
+#include "fan_tc.cuh"
+
+namespace tc {
+
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+constexpr int T2_ND = 4;          // user dims (rho without lam)
+constexpr int T2_TILES = 4;       // M tiles (128 fan columns each) per group
+constexpr int T2_US = 4;          // user slots per block: N = 32 T2_US
+constexpr int T2_N = 32 * T2_US;
+constexpr int T2_STAGES = 2;
+constexpr int T2_ACC = 2;
+constexpr int T2_BW = 2;          // builder warps (each thread builds T2_US / T2_BW rows per block)
+constexpr int T2_WARPS = 9 + T2_BW;  // 352 threads: the register file allows 168 per thread (the adjoint keeps 64 accumulators)
+constexpr int T2_MMA_WARP = 8;
+constexpr int T2_TMEM_COLS = 512;
+
+struct Tc2Geom {
+    int sz[T2_ND];                          // user dims, right-aligned (unused: extent 1, stride 0)
+    int vs[T2_ND], os[T2_ND], gs[T2_ND], ss[T2_ND];   // strides of v / out / gout / gS over the user dims
+    int bs[TC_NB][T2_ND];
+    int bk[TC_NB];
+    float bc[TC_NB];
+    int nb;
+    int L, l_lam, o_lam, g_lam, s_lam;      // lam: extent and strides (l, out, gout, gS)
+    int g_f;
+    int n_u, NG, FP;                        // users, fan groups, wide fan extent L F
+    int vec2;
+};
+
+__device__ __forceinline__ void t2_decode(unsigned u, const Tc2Geom& g, int* idx) {
+#pragma unroll
+    for (int k = T2_ND - 1; k >= 0; --k) {
+        const unsigned sz = (unsigned)g.sz[k];
+        const unsigned q = u / sz;
+        idx[k] = (int)(u - q * sz);
+        u = q;
+    }
+}
+__device__ __forceinline__ int t2_dot(const int* idx, const int* st) {
+    int o = 0;
+#pragma unroll
+    for (int k = 0; k < T2_ND; ++k) o += idx[k] * st[k];
+    return o;
+}
+
+template <int D, bool BWD>
+__global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __grid_constant__ FanLseParams<float> p, const __grid_constant__ Tc2Geom geo) {
+    constexpr int KT = (2 * D + 1 + 7) / 8 * 8;                            // K extent (40 at D = 18)
+    constexpr int NC = KT / 4, KSTEPS = KT / 8;
+    constexpr uint32_t LBO = T2_N * 16, SBO = 8 * 16;                      // [chunk][128 rows][16 B]: A_lo tiles and B alike
+    constexpr uint32_t OPER = NC * LBO;                                    // bytes of one operand part (20 KB at D = 18)
+    constexpr uint32_t A_HI = 0, D_COL = T2_TILES * KT;
+    static_assert(T2_TILES * KT + T2_ACC * T2_N <= T2_TMEM_COLS, "TMEM budget");
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T2_N >> 3) << 17) | ((128u >> 4) << 24);
+
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    unsigned char* alo_base = tc_smem;                                     // T2_TILES x OPER
+    unsigned char* stage_base = tc_smem + T2_TILES * OPER;                 // T2_STAGES x (B_hi | B_lo)
+    unsigned char* tail = stage_base + T2_STAGES * 2 * OPER;
+    float* s_cst = reinterpret_cast<float*>(tail);                         // [T2_TILES][128]  C[f'] (natural log units)
+    int* s_ooff = reinterpret_cast<int*>(tail + T2_TILES * 128 * 4);       // [T2_TILES][128]  out offset of f' (-1: padding lane)
+    int* s_goff = s_ooff + T2_TILES * 128;                                 // [T2_TILES][128]  gout offset of f'
+    float* s_red = reinterpret_cast<float*>(s_goff + T2_TILES * 128);      // [2][8 warps][2 users][32]
+    float* s_cd = s_red + 2 * 8 * 2 * 32;                                  // [32] centre per event element
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_cd + 32);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + T2_STAGES;
+    uint64_t* tfull = bars + 2 * T2_STAGES;
+    uint64_t* tempty = bars + 2 * T2_STAGES + T2_ACC;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * T2_STAGES + 2 * T2_ACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float LS = 1.4426950408889634f;
+    const int Kk = p.Kk;
+    const unsigned n_u = (unsigned)geo.n_u;
+    const unsigned n_blocks = (n_u + T2_US - 1) / T2_US;
+    const int grp = blockIdx.x % geo.NG;
+    const unsigned blk0 = blockIdx.x / geo.NG, blk_step = gridDim.x / geo.NG;
+    const int fp_lo = grp * (T2_TILES * 128);
+    const int n_tiles = min(T2_TILES, (geo.FP - fp_lo + 127) / 128);
+
+    // ---------------------------------------------------------------- prologue
+    for (uint32_t i = threadIdx.x; i < (T2_TILES + T2_STAGES * 2) * OPER / 16; i += blockDim.x)
+        reinterpret_cast<float4*>(tc_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == 0) {
+        float c = 0.f;
+        if (lane < D) {
+            for (int j = 0; j < geo.L; ++j) c += p.l[j * geo.l_lam + lane * (int)p.l_ev];
+            c /= (float)geo.L;
+        }
+        s_cd[lane] = c;
+    }
+    __syncthreads();
+    {   // padding rows (kappa >= Kk) carry a hugely negative bias: no column mask in the epilogue
+        const float big = -1.0e30f, bh = __uint_as_float(to_tf32(big)), bl = big - bh;
+        const int npad = 32 - Kk, per_stage = T2_US * npad;
+        for (int i = threadIdx.x; i < T2_STAGES * per_stage; i += blockDim.x) {
+            const int s = i / per_stage, r = i - s * per_stage, us = r / npad, kz = Kk + r - us * npad;
+            const int off = (((2 * D) / 4) * T2_N + 32 * us + kz) * 4 + ((2 * D) & 3);
+            reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER)[off] = bh;
+            reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER)[off] = bl;
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&full[s], 32 * T2_BW); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < T2_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == T2_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(T2_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        // ---------------------------------------------------------------- A operand, once: thread = row of every tile
+        const int row = 32 * warp + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
+        for (int tl = 0; tl < T2_TILES; ++tl) {
+            const int fp = fp_lo + 128 * tl + row;
+            float a[KT];
+#pragma unroll
+            for (int k = 0; k < KT; ++k) a[k] = 0.f;
+            float cst = 0.f;
+            int ooff = -1, goff = 0;
+            if (tl < n_tiles && fp < geo.FP) {
+                const int lam = fp / p.F, f = fp - lam * p.F;
+                float c = 0.f;
+#pragma unroll
+                for (int dd = 0; dd < D; ++dd) {
+                    const float sc = p.s[f * (int)p.s_f + dd * (int)p.s_ev];
+                    const float lc = p.l[lam * geo.l_lam + dd * (int)p.l_ev] - s_cd[dd];
+                    const float w = 1.f / (2.f * (sc * sc));
+                    a[dd] = -w * LS;
+                    a[D + dd] = 2.f * lc * w * LS;
+                    c += lc * lc * w + logf(sc);
+                }
+                a[2 * D] = 1.f;
+                cst = -(c + float(D) * float(HALF_LOG_2PI));
+                ooff = lam * geo.o_lam + f * (int)p.o_f;
+                goff = lam * geo.g_lam + f * geo.g_f;
+            }
+            s_cst[tl * 128 + row] = cst;
+            s_ooff[tl * 128 + row] = ooff;
+            s_goff[tl * 128 + row] = goff;
+            float* alo = reinterpret_cast<float*>(alo_base + (size_t)tl * OPER);
+#pragma unroll
+            for (int g8 = 0; g8 < KT / 8; ++g8) {
+                uint32_t hi[8];
+                float lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float x = a[8 * g8 + e];
+                    hi[e] = to_tf32(x);
+                    lo[e] = x - __uint_as_float(hi[e]);
+                }
+                TC_ST8(lane_base + A_HI + KT * tl + 8 * g8, hi, 0);
+                *reinterpret_cast<float4*>(alo + ((2 * g8) * T2_N + row) * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4*>(alo + ((2 * g8 + 1) * T2_N + row) * 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp < 8) {
+        // ---------------------------------------------------------------- epilogue: team = warp / 4, quadrant = warp % 4
+        const int q = warp & 3, team = warp >> 2, row = 32 * q + lane;
+        const float cadd = p.cadd;
+        // per (tile, user of this team): raw lse / gout of the NEXT block, fetched one block ahead (adjoint)
+        float n_lse[T2_TILES][2], n_g[T2_TILES][2];
+        int n_uoff[2];
+        auto fetch = [&](unsigned blk) {
+#pragma unroll
+            for (int uu = 0; uu < 2; ++uu) {
+                const unsigned u = T2_US * blk + 2 * team + uu;
+                int idx[T2_ND];
+                t2_decode(u < n_u ? u : 0u, geo, idx);
+                const int uo = t2_dot(idx, geo.os);
+                n_uoff[uu] = u < n_u ? uo : -1;
+                if (BWD) {
+                    const int ug = t2_dot(idx, geo.gs);
+#pragma unroll
+                    for (int tl = 0; tl < T2_TILES; ++tl) {
+                        const int oo = s_ooff[tl * 128 + row];
+                        n_lse[tl][uu] = INFINITY; n_g[tl][uu] = 0.f;              // idle rows / users: weight 0
+                        if (u < n_u && oo >= 0 && tl < n_tiles) {
+                            n_lse[tl][uu] = p.lse[uo + oo];
+                            n_g[tl][uu] = p.gout[ug + s_goff[tl * 128 + row]];
+                        }
+                    }
+                }
+            }
+        };
+        if (blk0 < n_blocks) fetch(blk0);
+        unsigned tt = 0;                                                         // accumulator stage counter
+        unsigned it = 0;
+        for (unsigned blk = blk0; blk < n_blocks; blk += blk_step, ++it) {
+            float lz[T2_TILES][2], gz[T2_TILES][2];
+            int uoff[2];
+#pragma unroll
+            for (int uu = 0; uu < 2; ++uu) {
+                uoff[uu] = n_uoff[uu];
+#pragma unroll
+                for (int tl = 0; tl < T2_TILES; ++tl) {
+                    lz[tl][uu] = BWD ? (n_lse[tl][uu] - cadd - s_cst[tl * 128 + row]) * LS : 0.f;
+                    gz[tl][uu] = BWD ? n_g[tl][uu] : 0.f;
+                }
+            }
+            if (blk + blk_step < n_blocks) fetch(blk + blk_step);
+            float acc[2][32];
+            if (BWD) {
+#pragma unroll
+                for (int uu = 0; uu < 2; ++uu)
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) acc[uu][k] = 0.f;
+            }
+#pragma unroll
+            for (int tl = 0; tl < T2_TILES; ++tl) {
+                if (tl < n_tiles) {
+                    const int a = tt % T2_ACC;
+                    const uint32_t pa = (tt / T2_ACC) & 1;
+                    ++tt;
+                    mbar_wait(&tfull[a], pa);
+                    tc_fence_after();
+#pragma unroll
+                    for (int uu = 0; uu < 2; ++uu) {
+                        uint32_t r[32];
+                        TC_LD32(r, tmem + ((uint32_t)(32 * q) << 16) + D_COL + T2_N * a + 64 * team + 32 * uu);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (uu == 1) { tc_fence_before(); mbar_arrive(&tempty[a]); }
+                        if (!BWD) {
+                            float m = __uint_as_float(r[0]);
+#pragma unroll
+                            for (int k = 1; k < 32; ++k) m = fmaxf(m, __uint_as_float(r[k]));
+                            const float2 nm2 = make_float2(-m, -m);
+                            float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+                            for (int k = 0; k < 32; k += 2) {
+                                const float2 d2 = __fadd2_rn(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), nm2);
+                                acc2 = __fadd2_rn(acc2, make_float2(FastExp<float>::ex(d2.x), FastExp<float>::ex(d2.y)));
+                            }
+                            const float sum = acc2.x + acc2.y;
+                            const int oo = s_ooff[tl * 128 + row];
+                            if (uoff[uu] >= 0 && oo >= 0)
+                                p.out[uoff[uu] + oo] = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + (cadd + s_cst[tl * 128 + row]);
+                        } else {
+                            const float2 nl2 = make_float2(-lz[tl][uu], -lz[tl][uu]), g2 = make_float2(gz[tl][uu], gz[tl][uu]);
+#pragma unroll
+                            for (int k = 0; k < 32; k += 2) {
+                                const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), nl2);
+                                const float2 e0 = make_float2(FastExp<float>::ex(d0.x), FastExp<float>::ex(d0.y));
+                                const float2 a2 = __ffma2_rn(e0, g2, make_float2(acc[uu][k], acc[uu][k + 1]));
+                                acc[uu][k] = a2.x; acc[uu][k + 1] = a2.y;
+                            }
+                        }
+                    }
+                }
+            }
+            if (BWD) {
+                // sum over the 32 lanes (f') of this warp: fixed-order butterfly reduce-scatter, lane j ends with kappa = j
+                float* red = s_red + (it & 1) * (8 * 2 * 32);
+#pragma unroll
+                for (int uu = 0; uu < 2; ++uu) {
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const bool up = (lane & off) != 0;
+                            const float send = up ? acc[uu][i] : acc[uu][i + off];
+                            const float mine = up ? acc[uu][i + off] : acc[uu][i];
+                            acc[uu][i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    red[(warp * 2 + uu) * 32 + lane] = acc[uu][0];
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (team == 0) {
+                    // thread (user slot = q, kappa = lane): the four quadrant partials of the owning team, fixed order
+                    const int tm = q >> 1, uu = q & 1;
+                    const float* rp = red + ((tm * 4) * 2 + uu) * 32 + lane;
+                    const float sum = ((rp[0] + rp[64]) + rp[128]) + rp[192];
+                    const unsigned u = T2_US * blk + q;
+                    if (u < n_u && lane < Kk) {
+                        int idx[T2_ND];
+                        t2_decode(u, geo, idx);
+                        p.gS[((i64)t2_dot(idx, geo.ss) + (i64)grp * geo.s_lam) * Kk + lane] = sum;
+                    }
+                }
+            }
+        }
+    } else if (warp == T2_MMA_WARP) {
+        // ---------------------------------------------------------------- MMA issuer
+        unsigned it = 0, tt = 0;
+        for (unsigned blk = blk0; blk < n_blocks; blk += blk_step, ++it) {
+            const int s = it % T2_STAGES;
+            const uint32_t ps = (it / T2_STAGES) & 1;
+            mbar_wait(&full[s], ps);
+            const uint32_t bhi = smem_u32(stage_base + (size_t)s * 2 * OPER), blo = bhi + OPER;
+            for (int tl = 0; tl < n_tiles; ++tl, ++tt) {
+                const int a = tt % T2_ACC;
+                const uint32_t pa = (tt / T2_ACC) & 1;
+                mbar_wait(&tempty[a], pa ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem + D_COL + T2_N * a;
+                const uint32_t ahi = tmem + A_HI + KT * tl;
+                const uint32_t alo = smem_u32(alo_base + (size_t)tl * OPER);
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < KSTEPS; ++j) {
+                        const uint64_t dh = smem_desc(bhi + j * 2 * LBO, LBO, SBO), dl = smem_desc(blo + j * 2 * LBO, LBO, SBO);
+                        const uint64_t da = smem_desc(alo + j * 2 * LBO, LBO, SBO);
+                        mma_tf32_ts(d, ahi + 8 * j, dh, IDESC, j > 0 ? 1u : 0u);
+                        mma_tf32_ss(d, da, dh, IDESC, 1u);
+                        mma_tf32_ts(d, ahi + 8 * j, dl, IDESC, 1u);
+                    }
+                    if (tl == n_tiles - 1) tc_commit(&empty[s]);
+                    tc_commit(&tfull[a]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- builders: thread = rows (user slot, kappa) of
+        // user slots bw and bw + 2
+        const int bw = warp - T2_MMA_WARP - 1, kz = lane;
+        const int vk = (int)p.v_k, vev = (int)p.v_ev, nb = geo.nb, vec2 = geo.vec2;
+        unsigned it = 0;
+        for (unsigned blk = blk0; blk < n_blocks; blk += blk_step, ++it) {
+            const int s = it % T2_STAGES;
+            const uint32_t ps = (it / T2_STAGES) & 1;
+#pragma unroll
+            for (int h = 0; h < T2_US / T2_BW; ++h) {
+                const int us = bw + T2_BW * h, n = 32 * us + kz;
+                const unsigned u = T2_US * blk + us;
+                const bool live = u < n_u && kz < Kk;
+                float t[KT];
+#pragma unroll
+                for (int k = 0; k < KT; ++k) t[k] = 0.f;
+                if (live) {
+                    int idx[T2_ND];
+                    t2_decode(u, geo, idx);
+                    float b = 0.f;
+#pragma unroll
+                    for (int i = 0; i < TC_NB; ++i) if (i < nb) b += geo.bc[i] * p.b[i][t2_dot(idx, geo.bs[i]) + kz * geo.bk[i]];
+                    const float* vp = p.v + t2_dot(idx, geo.vs) + kz * vk;
+                    if (vec2) {
+#pragma unroll
+                        for (int q2 = 0; q2 < D / 2; ++q2) {
+                            const float2 vv = *reinterpret_cast<const float2*>(vp + 2 * q2);
+                            const float d0 = vv.x - s_cd[2 * q2], d1 = vv.y - s_cd[2 * q2 + 1];
+                            t[2 * q2] = d0 * d0; t[2 * q2 + 1] = d1 * d1;
+                            t[D + 2 * q2] = d0; t[D + 2 * q2 + 1] = d1;
+                        }
+                    } else {
+#pragma unroll
+                        for (int dd = 0; dd < D; ++dd) { const float df = vp[dd * vev] - s_cd[dd]; t[dd] = df * df; t[D + dd] = df; }
+                    }
+                    t[2 * D] = b * LS;
+                }
+                if (h == 0) mbar_wait(&empty[s], ps ^ 1);
+                if (kz < Kk) {                   // rows of users >= n_u are written as zeros: finite, masked later
+                    float* bh = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER);
+                    float* bl = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        // the tensor core reads only the 19 TF32 bits of a word: the raw fp32 value IS the "hi" part and
+                        // lo = t - trunc(t) its exact remainder
+                        float4 hh, l;
+                        hh.x = t[4 * c + 0]; l.x = hh.x - __uint_as_float(__float_as_uint(hh.x) & 0xFFFFE000u);
+                        hh.y = t[4 * c + 1]; l.y = hh.y - __uint_as_float(__float_as_uint(hh.y) & 0xFFFFE000u);
+                        hh.z = t[4 * c + 2]; l.z = hh.z - __uint_as_float(__float_as_uint(hh.z) & 0xFFFFE000u);
+                        hh.w = t[4 * c + 3]; l.w = hh.w - __uint_as_float(__float_as_uint(hh.w) & 0xFFFFE000u);
+                        const int off = (c * T2_N + n) * 4;
+                        *reinterpret_cast<float4*>(bh + off) = hh;
+                        *reinterpret_cast<float4*>(bl + off) = l;
+                    }
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(&full[s]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == T2_MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(T2_TMEM_COLS) : "memory");
+    }
+}
+
+// index of the lam dim in p.rd, -1 if the loc is a constant vector (L = 1), -2 if the dense formulation does not apply
+static int fan_lse_tc2_lam(const FanLseParams<float>& p) {
+    if (p.l_k != 0) return -2;
+    int lam = -1;
+    for (int k = 0; k < p.rd.nd; ++k) {
+        if (p.lstride[k] == 0 || p.rd.size[k] == 1) continue;
+        if (lam >= 0) return -2;
+        lam = k;
+    }
+    if (lam < 0) return -1;
+    if (p.vstride[lam] != 0) return -2;
+    for (int i = 0; i < p.nb; ++i) if (p.bstride[i][lam] != 0) return -2;
+    return lam;
+}
+
+static bool fan_lse_tc2_supported(const FanLseParams<float>& p, int D, bool bwd) {
+    const int lam = fan_lse_tc2_lam(p);
+    if (lam == -2) return false;
+    const i64 L = lam >= 0 ? p.rd.size[lam] : 1;
+    const i64 FP = L * p.F, NG = (FP + T2_TILES * 128 - 1) / (T2_TILES * 128);
+    const i64 n_u = p.n_rho / L;
+    if (FP < 96 || NG > 4 || (bwd && NG > L) || p.Kk > 32 || n_u < 16 || p.nb > TC_NB) return false;
+    if (p.rd.nd - (lam >= 0 ? 1 : 0) > T2_ND) return false;
+    const i64 lim = (i64)1 << 31;
+    i64 vspan = (i64)p.Kk * p.v_k + 32 * p.v_ev, ospan = FP * (p.o_f > 0 ? p.o_f : 1), bspan = 0;
+    for (int k = 0; k < p.rd.nd; ++k) {
+        vspan += (i64)p.rd.size[k] * p.vstride[k];
+        ospan += (i64)p.rd.size[k] * p.ostride[k];
+        for (int i = 0; i < p.nb; ++i) { i64 b = (i64)p.rd.size[k] * p.bstride[i][k] + (i64)p.Kk * p.b_k[i]; if (b > bspan) bspan = b; }
+    }
+    if (vspan >= lim || ospan >= lim || bspan >= lim || p.n_rho * (i64)p.Kk >= lim) return false;
+    switch (D) { case 2: case 4: case 6: case 8: case 12: case 16: case 18: return true; }
+    return false;
+}
+
+template <int D>
+static int launch_fan_lse_tc2_D(const FanLseParams<float>& p, bool bwd, cudaStream_t stream, int sm_count) {
+    constexpr int KT = (2 * D + 1 + 7) / 8 * 8;
+    constexpr size_t OPER = (size_t)(KT / 4) * T2_N * 16;
+    const size_t smem = (T2_TILES + T2_STAGES * 2) * OPER + T2_TILES * 128 * 12 + 2 * 8 * 2 * 32 * 4 + 32 * 4 +
+                        (2 * T2_STAGES + 2 * T2_ACC) * 8 + 16;
+    const int lam = fan_lse_tc2_lam(p);
+    Tc2Geom geo;
+    memset(&geo, 0, sizeof(geo));
+    for (int j = 0; j < T2_ND; ++j) geo.sz[j] = 1;
+    geo.L = lam >= 0 ? p.rd.size[lam] : 1;
+    // gS is [rd dims row-major, kappa]: element strides of the rd dims in units of Kk
+    i64 sstride[AB_MAXD];
+    { i64 acc = 1; for (int k = p.rd.nd - 1; k >= 0; --k) { sstride[k] = acc; acc *= p.rd.size[k]; } }
+    const int n_user_dims = p.rd.nd - (lam >= 0 ? 1 : 0);
+    int j = T2_ND - n_user_dims;
+    bool ev2 = (D % 2 == 0) && p.v_ev == 1 && p.v_k % 2 == 0 && ((uintptr_t)p.v % 8 == 0);
+    for (int k = 0; k < p.rd.nd; ++k) {
+        if (k == lam) {
+            geo.l_lam = (int)p.lstride[k]; geo.o_lam = (int)p.ostride[k]; geo.g_lam = (int)p.gstride[k]; geo.s_lam = (int)sstride[k];
+            continue;
+        }
+        geo.sz[j] = p.rd.size[k];
+        geo.vs[j] = (int)p.vstride[k]; geo.os[j] = (int)p.ostride[k]; geo.gs[j] = (int)p.gstride[k]; geo.ss[j] = (int)sstride[k];
+        for (int i = 0; i < p.nb; ++i) geo.bs[i][j] = (int)p.bstride[i][k];
+        ev2 = ev2 && (p.vstride[k] % 2 == 0);
+        ++j;
+    }
+    for (int i = 0; i < p.nb; ++i) { geo.bk[i] = (int)p.b_k[i]; geo.bc[i] = p.bcoeff[i]; }
+    geo.nb = p.nb;
+    geo.g_f = (int)p.g_f;
+    geo.vec2 = ev2 ? 1 : 0;
+    geo.n_u = (int)(p.n_rho / geo.L);
+    geo.FP = geo.L * p.F;
+    geo.NG = (geo.FP + T2_TILES * 128 - 1) / (T2_TILES * 128);
+    const i64 n_blocks = ((i64)geo.n_u + T2_US - 1) / T2_US;
+    i64 per_group = sm_count / geo.NG;
+    if (per_group > n_blocks) per_group = n_blocks;
+    if (per_group < 1) per_group = 1;
+    const int blocks = (int)per_group * geo.NG;
+    if (bwd) {
+        cudaFuncSetAttribute(fan_lse_tc2_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fan_lse_tc2_kernel<D, true><<<blocks, T2_WARPS * 32, smem, stream>>>(p, geo);
+    } else {
+        cudaFuncSetAttribute(fan_lse_tc2_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fan_lse_tc2_kernel<D, false><<<blocks, T2_WARPS * 32, smem, stream>>>(p, geo);
+    }
+    return 0;
+}
+
+static int launch_fan_lse_tc2(const FanLseParams<float>& p, int D, bool bwd, cudaStream_t stream, int sm_count) {
+    switch (D) {
+        case 2: return launch_fan_lse_tc2_D<2>(p, bwd, stream, sm_count);
+        case 4: return launch_fan_lse_tc2_D<4>(p, bwd, stream, sm_count);
+        case 6: return launch_fan_lse_tc2_D<6>(p, bwd, stream, sm_count);
+        case 8: return launch_fan_lse_tc2_D<8>(p, bwd, stream, sm_count);
+        case 12: return launch_fan_lse_tc2_D<12>(p, bwd, stream, sm_count);
+        case 16: return launch_fan_lse_tc2_D<16>(p, bwd, stream, sm_count);
+        case 18: return launch_fan_lse_tc2_D<18>(p, bwd, stream, sm_count);
+    }
+    return 1;
+}
+
+}  // namespace tc
