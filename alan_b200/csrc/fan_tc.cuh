@@ -508,10 +508,12 @@ static int launch_fan_lse_tc_D(const FanLseParams<float>& p, bool bwd, cudaStrea
     geo.g_f = (int)p.g_f;
     geo.vec2 = ev2 ? 1 : 0;
     if (bwd) {
-        cudaFuncSetAttribute(fan_lse_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static const cudaError_t attr_true = cudaFuncSetAttribute(fan_lse_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // once per process
+        (void)attr_true;
         fan_lse_tc_kernel<D, true><<<(int)blocks, TC_WARPS * 32, smem, stream>>>(p, geo);
     } else {
-        cudaFuncSetAttribute(fan_lse_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static const cudaError_t attr_false = cudaFuncSetAttribute(fan_lse_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // once per process
+        (void)attr_false;
         fan_lse_tc_kernel<D, false><<<(int)blocks, TC_WARPS * 32, smem, stream>>>(p, geo);
     }
     return 0;

@@ -11,24 +11,30 @@
 //     log2e S[u,kappa,f'] = sum_d v'^2 (-w log2e) + sum_d v' (2 l' w log2e) + b log2e        - C[f'] log2e
 //                         =         B[(u,kappa), k]  .  A[f', k]                               (k < 2 D + 1)
 //
-//   A (constant per CTA)  rows f' (128 per M tile, up to 4 tiles per CTA = one "group" of 512 fan columns),
-//                         K = 2 D + 1 -> KT;  A_hi in TMEM (tcgen05.st), A_lo in shared memory
-//   B (one stage per block of 4 users)  rows n = (user slot, kappa) = 128,  { v'^2 | v' | b log2e }, hi and lo
+//   A (constant per CTA)  rows f' (128 per M tile, up to 3 tiles per CTA = one "group" of 384 fan columns),
+//                         K = 2 D + 1 -> KT;  A_hi and A_lo in TMEM (tcgen05.st, once)
+//   B (one stage per block of 4 users)  rows n = (user slot, kappa) = 128,  { v'^2 | v' | b log2e }, hi and lo, smem
 //   D = A B^T (TMEM, 2 stages x 128 columns): lane = f', columns = (user slot, kappa)
 //   C[f'] = sum_d l'^2 w + sum_d log s + D/2 log 2pi does not depend on kappa: it leaves the LSE and is added in
 //   fp32 afterwards.
 // 3xTF32 as in fan_tc.cuh: A_hi B_hi + A_lo B_hi + A_hi B_lo.  15 tcgen05.mma (M128 N128 K8) per (tile, block) at
-// D = 18, against 30 per 16 rho (= 225 per 4 users x 30 lam) in the block-diagonal kernel, and the builders handle
-// n_u Kk D values instead of n_u L Kk D.
+// D = 18, i.e. 120 per 4 users, against 30 per 16 rho (= 225 per 4 users x 30 lam) in the block-diagonal kernel, and
+// the builders handle n_u Kk D values instead of n_u L Kk D.
 //
-// Roles (11 warps, one persistent CTA per SM; CTA c works on fan group c % NG):
-//   epilogue  2 teams x 4 warps: warp % 4 = TMEM lane quadrant, team e owns user slots 2e, 2e+1 (64 columns) of EVERY
-//             tile; forward: max / ex2 / sum per (user, f'); adjoint: weights accumulated over the tiles of the group
-//             in registers, one fixed-order butterfly per block, team partials combined through shared memory
+// Roles (21 warps, one persistent CTA per SM; the CTAs are split between the fan groups in proportion to their cost):
+//   epilogue  4 teams x 4 warps: warp % 4 = TMEM lane quadrant, team e owns user slot e (32 columns) of EVERY tile:
+//             four epilogue warps per SM sub-partition keep the MUFU pipe busy through each other's serial sections.
+//             forward: max (FMNMX3 tree) / ex2 / packed sums per (user, f'); adjoint: weights accumulated over the
+//             tiles of the group in registers, one fixed-order butterfly per block, quadrant partials combined
+//             through shared memory in a fixed order
 //   MMA       1 warp (elected lane), owns the TMEM allocation
-//   builders  2 warps, thread = two B rows (user slot, kappa)
+//   builders  4 warps: warp = user slot, lane = kappa; raw loads of the next block are in flight while the current
+//             one is squared, split and stored
 // The adjoint writes gS[u, lam = g, kappa] for group g (its partial over that group's fan columns) -- the planner's
 // reduce over lam that follows sums the partials; the other lam slots stay zero (zeroed adjoint region).
+//
+// Measured on B200, cfg-5 (10 000 users, L = F = 30, D = 18), cycles per CTA (TC_DEBUG_SPIN): forward 240 k, of which
+// the MMA issuer is busy 75 % (87 cycles per MMA) and the epilogue warps 90 %; adjoint 310 k, epilogue-bound.
 #pragma once
 #include "fan_tc.cuh"
 
@@ -40,15 +46,45 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// tcgen05.wait::ld that names the registers of the load it completes ("+r"): the compiler cannot hoist arithmetic on
+// them above the wait (a plain asm volatile only orders against other volatile asm and memory accesses)
+#define TC_WAIT_LD32(r)                                                                                        \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                              \
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),         \
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),   \
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), \
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])  \
+                 :: "memory")
+
+#define TC_LD16(r, addr)                                                                                      \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                    \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"              \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),       \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])  \
+                 : "r"(addr) : "memory")
+#define TC_WAIT_LD16(r)                                                                                        \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                              \
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),         \
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])    \
+                 :: "memory")
+
 constexpr int T2_ND = 4;          // user dims (rho without lam)
-constexpr int T2_TILES = 4;       // M tiles (128 fan columns each) per group
+constexpr int T2_TILES = 3;       // M tiles (128 fan columns each) per group: A_hi and A_lo of three tiles fit TMEM next to
+                                  // two accumulator stages (2 x 3 x 40 + 2 x 128 = 496 columns at D = 18).  Measured
+                                  // alternatives: A_lo or all of A in shared memory (SS MMAs) cost 92 / 105 cycles per MMA
+                                  // against 87 with A in TMEM -- the MMAs then compete for shared-memory bandwidth
+constexpr int T2_MAXG = 8;        // fan groups
+constexpr int T2_BLOCK_COST4 = 7; // per-block cost in quarter tiles (CTA split between groups of unequal tile counts)
 constexpr int T2_US = 4;          // user slots per block: N = 32 T2_US
 constexpr int T2_N = 32 * T2_US;
-constexpr int T2_STAGES = 2;
+constexpr int T2_STAGES = 3;
 constexpr int T2_ACC = 2;
-constexpr int T2_BW = 2;          // builder warps (each thread builds T2_US / T2_BW rows per block)
-constexpr int T2_WARPS = 9 + T2_BW;  // 352 threads: the register file allows 168 per thread (the adjoint keeps 64 accumulators)
-constexpr int T2_MMA_WARP = 8;
+constexpr int T2_BW = T2_US;      // builder warps: warp = user slot, lane = kappa
+constexpr int T2_EPI = 4;         // epilogue teams of 4 warps (one warp per TMEM lane quadrant); 4 teams = 4 epilogue warps per SM
+                                  // sub-partition: warp-level parallelism keeps the MUFU pipe fed through the serial sections
+constexpr int T2_UPT = T2_US / T2_EPI;   // user slots (32 accumulator columns each) per team and tile
+constexpr int T2_MMA_WARP = 4 * T2_EPI;
+constexpr int T2_WARPS = 4 * T2_EPI + 1 + T2_BW;
 constexpr int T2_TMEM_COLS = 512;
 
 struct Tc2Geom {
@@ -61,6 +97,7 @@ struct Tc2Geom {
     int L, l_lam, o_lam, g_lam, s_lam;      // lam: extent and strides (l, out, gout, gS)
     int g_f;
     int n_u, NG, FP;                        // users, fan groups, wide fan extent L F
+    int cta_lo[T2_MAXG + 1];                // CTAs [cta_lo[g], cta_lo[g + 1]) work on fan group g (proportional to its tiles)
     int vec2;
 };
 
@@ -86,19 +123,18 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
     constexpr int NC = KT / 4, KSTEPS = KT / 8;
     constexpr uint32_t LBO = T2_N * 16, SBO = 8 * 16;                      // [chunk][128 rows][16 B]: A_lo tiles and B alike
     constexpr uint32_t OPER = NC * LBO;                                    // bytes of one operand part (20 KB at D = 18)
-    constexpr uint32_t A_HI = 0, D_COL = T2_TILES * KT;
-    static_assert(T2_TILES * KT + T2_ACC * T2_N <= T2_TMEM_COLS, "TMEM budget");
+    constexpr uint32_t A_HI = 0, A_LO = T2_TILES * KT, D_COL = 2 * T2_TILES * KT;
+    static_assert(2 * T2_TILES * KT + T2_ACC * T2_N <= T2_TMEM_COLS, "TMEM budget");
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T2_N >> 3) << 17) | ((128u >> 4) << 24);
 
     extern __shared__ __align__(1024) unsigned char tc_smem[];
-    unsigned char* alo_base = tc_smem;                                     // T2_TILES x OPER
-    unsigned char* stage_base = tc_smem + T2_TILES * OPER;                 // T2_STAGES x (B_hi | B_lo)
+    unsigned char* stage_base = tc_smem;                                   // T2_STAGES x (B_hi | B_lo)
     unsigned char* tail = stage_base + T2_STAGES * 2 * OPER;
     float* s_cst = reinterpret_cast<float*>(tail);                         // [T2_TILES][128]  C[f'] (natural log units)
     int* s_ooff = reinterpret_cast<int*>(tail + T2_TILES * 128 * 4);       // [T2_TILES][128]  out offset of f' (-1: padding lane)
     int* s_goff = s_ooff + T2_TILES * 128;                                 // [T2_TILES][128]  gout offset of f'
-    float* s_red = reinterpret_cast<float*>(s_goff + T2_TILES * 128);      // [2][8 warps][2 users][32]
-    float* s_cd = s_red + 2 * 8 * 2 * 32;                                  // [32] centre per event element
+    float* s_red = reinterpret_cast<float*>(s_goff + T2_TILES * 128);      // [2][team][quadrant][user of team][32]
+    float* s_cd = s_red + 2 * 4 * T2_US * 32;                                  // [32] centre per event element
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_cd + 32);
     uint64_t* full = bars;
     uint64_t* empty = bars + T2_STAGES;
@@ -107,17 +143,24 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * T2_STAGES + 2 * T2_ACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long dbg_k0 = clock64(); (void)dbg_k0;
+    unsigned long long dbg_g0 = 0; (void)dbg_g0;
+#ifdef TC_DEBUG_SPIN
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_g0));
+#endif
     const float LS = 1.4426950408889634f;
     const int Kk = p.Kk;
     const unsigned n_u = (unsigned)geo.n_u;
     const unsigned n_blocks = (n_u + T2_US - 1) / T2_US;
-    const int grp = blockIdx.x % geo.NG;
-    const unsigned blk0 = blockIdx.x / geo.NG, blk_step = gridDim.x / geo.NG;
+    int grp = 0;
+#pragma unroll
+    for (int g = 1; g < T2_MAXG; ++g) if (g < geo.NG && (int)blockIdx.x >= geo.cta_lo[g]) grp = g;
+    const unsigned blk0 = blockIdx.x - geo.cta_lo[grp], blk_step = geo.cta_lo[grp + 1] - geo.cta_lo[grp];
     const int fp_lo = grp * (T2_TILES * 128);
     const int n_tiles = min(T2_TILES, (geo.FP - fp_lo + 127) / 128);
 
     // ---------------------------------------------------------------- prologue
-    for (uint32_t i = threadIdx.x; i < (T2_TILES + T2_STAGES * 2) * OPER / 16; i += blockDim.x)
+    for (uint32_t i = threadIdx.x; i < (T2_STAGES * 2) * OPER / 16; i += blockDim.x)
         reinterpret_cast<float4*>(tc_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp == 0) {
         float c = 0.f;
@@ -140,7 +183,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&full[s], 32 * T2_BW); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < T2_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
+        for (int a = 0; a < T2_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128 * T2_EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == T2_MMA_WARP) {
@@ -152,6 +195,8 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    long long dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0; (void)dbg0; (void)dbg1; (void)dbg2; (void)dbg3;
+    const long long dbg_t0 = clock64(); (void)dbg_t0;
 
     if (warp < 4) {
         // ---------------------------------------------------------------- A operand, once: thread = row of every tile
@@ -184,20 +229,17 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
             s_cst[tl * 128 + row] = cst;
             s_ooff[tl * 128 + row] = ooff;
             s_goff[tl * 128 + row] = goff;
-            float* alo = reinterpret_cast<float*>(alo_base + (size_t)tl * OPER);
 #pragma unroll
             for (int g8 = 0; g8 < KT / 8; ++g8) {
-                uint32_t hi[8];
-                float lo[8];
+                uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float x = a[8 * g8 + e];
                     hi[e] = to_tf32(x);
-                    lo[e] = x - __uint_as_float(hi[e]);
+                    lo[e] = __float_as_uint(x - __uint_as_float(hi[e]));
                 }
                 TC_ST8(lane_base + A_HI + KT * tl + 8 * g8, hi, 0);
-                *reinterpret_cast<float4*>(alo + ((2 * g8) * T2_N + row) * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<float4*>(alo + ((2 * g8 + 1) * T2_N + row) * 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                TC_ST8(lane_base + A_LO + KT * tl + 8 * g8, lo, 0);
             }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -207,17 +249,18 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
     __syncthreads();
     tc_fence_after();
 
-    if (warp < 8) {
+    if (warp < 4 * T2_EPI) {
         // ---------------------------------------------------------------- epilogue: team = warp / 4, quadrant = warp % 4
         const int q = warp & 3, team = warp >> 2, row = 32 * q + lane;
         const float cadd = p.cadd;
-        // per (tile, user of this team): raw lse / gout of the NEXT block, fetched one block ahead (adjoint)
-        float n_lse[T2_TILES][2], n_g[T2_TILES][2];
-        int n_uoff[2];
+        // adjoint: raw lse / gout of the NEXT block are fetched one block ahead (no arithmetic on them before their tile:
+        // an in-order warp stalls on the first use of a pending load)
+        float n_lse[T2_TILES][T2_UPT], n_g[T2_TILES][T2_UPT];
+        int n_uoff[T2_UPT];
         auto fetch = [&](unsigned blk) {
 #pragma unroll
-            for (int uu = 0; uu < 2; ++uu) {
-                const unsigned u = T2_US * blk + 2 * team + uu;
+            for (int uu = 0; uu < T2_UPT; ++uu) {
+                const unsigned u = T2_US * blk + T2_UPT * team + uu;
                 int idx[T2_ND];
                 t2_decode(u < n_u ? u : 0u, geo, idx);
                 const int uo = t2_dot(idx, geo.os);
@@ -239,23 +282,21 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
         if (blk0 < n_blocks) fetch(blk0);
         unsigned tt = 0;                                                         // accumulator stage counter
         unsigned it = 0;
+        const uint32_t ld_base = tmem + ((uint32_t)(32 * q) << 16) + D_COL + 32 * T2_UPT * team;
         for (unsigned blk = blk0; blk < n_blocks; blk += blk_step, ++it) {
-            float lz[T2_TILES][2], gz[T2_TILES][2];
-            int uoff[2];
+            float lz[T2_TILES][T2_UPT], gz[T2_TILES][T2_UPT];
+            int uoff[T2_UPT];
 #pragma unroll
-            for (int uu = 0; uu < 2; ++uu) {
+            for (int uu = 0; uu < T2_UPT; ++uu) {
                 uoff[uu] = n_uoff[uu];
 #pragma unroll
-                for (int tl = 0; tl < T2_TILES; ++tl) {
-                    lz[tl][uu] = BWD ? (n_lse[tl][uu] - cadd - s_cst[tl * 128 + row]) * LS : 0.f;
-                    gz[tl][uu] = BWD ? n_g[tl][uu] : 0.f;
-                }
+                for (int tl = 0; tl < T2_TILES; ++tl) { lz[tl][uu] = BWD ? n_lse[tl][uu] : 0.f; gz[tl][uu] = BWD ? n_g[tl][uu] : 0.f; }
             }
             if (blk + blk_step < n_blocks) fetch(blk + blk_step);
-            float acc[2][32];
+            float acc[T2_UPT][32];
             if (BWD) {
 #pragma unroll
-                for (int uu = 0; uu < 2; ++uu)
+                for (int uu = 0; uu < T2_UPT; ++uu)
 #pragma unroll
                     for (int k = 0; k < 32; ++k) acc[uu][k] = 0.f;
             }
@@ -265,47 +306,71 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                     const int a = tt % T2_ACC;
                     const uint32_t pa = (tt / T2_ACC) & 1;
                     ++tt;
-                    mbar_wait(&tfull[a], pa);
+                    MBAR_WAIT(&tfull[a], pa, dbg0);
                     tc_fence_after();
+                    if (!BWD) {
+                        // all loads of this team first, then the accumulator stage goes straight back to the MMA issuer
+                        uint32_t r[T2_UPT][32];
 #pragma unroll
-                    for (int uu = 0; uu < 2; ++uu) {
-                        uint32_t r[32];
-                        TC_LD32(r, tmem + ((uint32_t)(32 * q) << 16) + D_COL + T2_N * a + 64 * team + 32 * uu);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (uu == 1) { tc_fence_before(); mbar_arrive(&tempty[a]); }
-                        if (!BWD) {
-                            float m = __uint_as_float(r[0]);
+                        for (int uu = 0; uu < T2_UPT; ++uu) TC_LD32(r[uu], ld_base + T2_N * a + 32 * uu);
 #pragma unroll
-                            for (int k = 1; k < 32; ++k) m = fmaxf(m, __uint_as_float(r[k]));
+                        for (int uu = 0; uu < T2_UPT; ++uu) TC_WAIT_LD32(r[uu]);
+                        tc_fence_before();
+                        mbar_arrive(&tempty[a]);
+#pragma unroll
+                        for (int uu = 0; uu < T2_UPT; ++uu) {
+                            // max as a tree of three-input maxima (FMNMX3), then packed subtract / accumulate around the 32 ex2
+                            float m8[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                m8[k] = fmaxf(fmaxf(__uint_as_float(r[uu][4 * k]), __uint_as_float(r[uu][4 * k + 1])),
+                                              fmaxf(__uint_as_float(r[uu][4 * k + 2]), __uint_as_float(r[uu][4 * k + 3])));
+                            const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
                             const float2 nm2 = make_float2(-m, -m);
-                            float2 acc2 = make_float2(0.f, 0.f);
+                            float2 s2[4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) s2[c] = make_float2(0.f, 0.f);
 #pragma unroll
                             for (int k = 0; k < 32; k += 2) {
-                                const float2 d2 = __fadd2_rn(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), nm2);
-                                acc2 = __fadd2_rn(acc2, make_float2(FastExp<float>::ex(d2.x), FastExp<float>::ex(d2.y)));
+                                const float2 d2 = __fadd2_rn(make_float2(__uint_as_float(r[uu][k]), __uint_as_float(r[uu][k + 1])), nm2);
+                                s2[(k >> 1) & 3] = __fadd2_rn(s2[(k >> 1) & 3], make_float2(FastExp<float>::ex(d2.x), FastExp<float>::ex(d2.y)));
                             }
-                            const float sum = acc2.x + acc2.y;
+                            const float2 t2 = __fadd2_rn(__fadd2_rn(s2[0], s2[1]), __fadd2_rn(s2[2], s2[3]));
+                            const float sum = t2.x + t2.y;
                             const int oo = s_ooff[tl * 128 + row];
                             if (uoff[uu] >= 0 && oo >= 0)
                                 p.out[uoff[uu] + oo] = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + (cadd + s_cst[tl * 128 + row]);
-                        } else {
-                            const float2 nl2 = make_float2(-lz[tl][uu], -lz[tl][uu]), g2 = make_float2(gz[tl][uu], gz[tl][uu]);
+                        }
+                    } else {
+                        // 16 columns at a time: the adjoint also holds 32 accumulators per user and the prefetched lse / gout
 #pragma unroll
-                            for (int k = 0; k < 32; k += 2) {
-                                const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), nl2);
-                                const float2 e0 = make_float2(FastExp<float>::ex(d0.x), FastExp<float>::ex(d0.y));
-                                const float2 a2 = __ffma2_rn(e0, g2, make_float2(acc[uu][k], acc[uu][k + 1]));
-                                acc[uu][k] = a2.x; acc[uu][k + 1] = a2.y;
+                        for (int uu = 0; uu < T2_UPT; ++uu) {
+                            const float nl = (cadd + s_cst[tl * 128 + row] - lz[tl][uu]) * LS;
+                            const float2 nl2 = make_float2(nl, nl), g2 = make_float2(gz[tl][uu], gz[tl][uu]);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                uint32_t r[16];
+                                TC_LD16(r, ld_base + T2_N * a + 32 * uu + 16 * h);
+                                TC_WAIT_LD16(r);
+                                if (uu == T2_UPT - 1 && h == 1) { tc_fence_before(); mbar_arrive(&tempty[a]); }
+#pragma unroll
+                                for (int k = 0; k < 16; k += 2) {
+                                    const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), nl2);
+                                    const float2 e0 = make_float2(FastExp<float>::ex(d0.x), FastExp<float>::ex(d0.y));
+                                    const float2 a2 = __ffma2_rn(e0, g2, make_float2(acc[uu][16 * h + k], acc[uu][16 * h + k + 1]));
+                                    acc[uu][16 * h + k] = a2.x; acc[uu][16 * h + k + 1] = a2.y;
+                                }
                             }
                         }
                     }
                 }
             }
             if (BWD) {
-                // sum over the 32 lanes (f') of this warp: fixed-order butterfly reduce-scatter, lane j ends with kappa = j
-                float* red = s_red + (it & 1) * (8 * 2 * 32);
+                // sum over the 32 lanes (f') of this warp: fixed-order butterfly reduce-scatter, lane j ends with kappa = j;
+                // then the four quadrant warps of the team combine through shared memory in a fixed order
+                float* red = s_red + ((it & 1) * T2_EPI + team) * (4 * T2_UPT * 32);
 #pragma unroll
-                for (int uu = 0; uu < 2; ++uu) {
+                for (int uu = 0; uu < T2_UPT; ++uu) {
 #pragma unroll
                     for (int off = 16; off >= 1; off >>= 1) {
 #pragma unroll
@@ -316,15 +381,14 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                             acc[uu][i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
                         }
                     }
-                    red[(warp * 2 + uu) * 32 + lane] = acc[uu][0];
+                    red[(q * T2_UPT + uu) * 32 + lane] = acc[uu][0];
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (team == 0) {
-                    // thread (user slot = q, kappa = lane): the four quadrant partials of the owning team, fixed order
-                    const int tm = q >> 1, uu = q & 1;
-                    const float* rp = red + ((tm * 4) * 2 + uu) * 32 + lane;
-                    const float sum = ((rp[0] + rp[64]) + rp[128]) + rp[192];
-                    const unsigned u = T2_US * blk + q;
+                asm volatile("bar.sync %0, 128;" :: "r"(1 + team) : "memory");
+                if (q < T2_UPT) {
+                    const int uu = q;
+                    const float* rp = red + uu * 32 + lane;
+                    const float sum = ((rp[0] + rp[T2_UPT * 32]) + rp[2 * T2_UPT * 32]) + rp[3 * T2_UPT * 32];
+                    const unsigned u = T2_US * blk + T2_UPT * team + uu;
                     if (u < n_u && lane < Kk) {
                         int idx[T2_ND];
                         t2_decode(u, geo, idx);
@@ -339,23 +403,21 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
         for (unsigned blk = blk0; blk < n_blocks; blk += blk_step, ++it) {
             const int s = it % T2_STAGES;
             const uint32_t ps = (it / T2_STAGES) & 1;
-            mbar_wait(&full[s], ps);
+            MBAR_WAIT(&full[s], ps, dbg0);
             const uint32_t bhi = smem_u32(stage_base + (size_t)s * 2 * OPER), blo = bhi + OPER;
             for (int tl = 0; tl < n_tiles; ++tl, ++tt) {
                 const int a = tt % T2_ACC;
                 const uint32_t pa = (tt / T2_ACC) & 1;
-                mbar_wait(&tempty[a], pa ^ 1);
+                MBAR_WAIT(&tempty[a], pa ^ 1, dbg1);
                 tc_fence_after();
                 const uint32_t d = tmem + D_COL + T2_N * a;
-                const uint32_t ahi = tmem + A_HI + KT * tl;
-                const uint32_t alo = smem_u32(alo_base + (size_t)tl * OPER);
+                const uint32_t ahi = tmem + A_HI + KT * tl, alo = tmem + A_LO + KT * tl;
                 if (elect_one()) {
 #pragma unroll
                     for (int j = 0; j < KSTEPS; ++j) {
                         const uint64_t dh = smem_desc(bhi + j * 2 * LBO, LBO, SBO), dl = smem_desc(blo + j * 2 * LBO, LBO, SBO);
-                        const uint64_t da = smem_desc(alo + j * 2 * LBO, LBO, SBO);
                         mma_tf32_ts(d, ahi + 8 * j, dh, IDESC, j > 0 ? 1u : 0u);
-                        mma_tf32_ss(d, da, dh, IDESC, 1u);
+                        mma_tf32_ts(d, alo + 8 * j, dh, IDESC, 1u);
                         mma_tf32_ts(d, ahi + 8 * j, dl, IDESC, 1u);
                     }
                     if (tl == n_tiles - 1) tc_commit(&empty[s]);
@@ -365,67 +427,103 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
             }
         }
     } else {
-        // ---------------------------------------------------------------- builders: thread = rows (user slot, kappa) of
-        // user slots bw and bw + 2
-        const int bw = warp - T2_MMA_WARP - 1, kz = lane;
+        // ---------------------------------------------------------------- builders: warp = user slot, lane = kappa; the raw
+        // values of the NEXT block are loaded before the current one is written, so the global-load latency overlaps the
+        // wait for the stage and the shared-memory stores
+        const int us = warp - T2_MMA_WARP - 1, kz = lane, n = 32 * us + kz;
         const int vk = (int)p.v_k, vev = (int)p.v_ev, nb = geo.nb, vec2 = geo.vec2;
+        // raw loads only (no arithmetic on the loaded values here: an in-order warp would stall on the first use)
+        float cur[D], nxt[D], cur_b[TC_NB], nxt_b[TC_NB];
+        auto load_raw = [&](unsigned blk, float (&raw)[D], float (&braw)[TC_NB]) {
+            const unsigned u = T2_US * blk + us;
+            const bool live = u < n_u && kz < Kk;
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) raw[dd] = s_cd[dd];                  // idle rows: v' = 0
+#pragma unroll
+            for (int i = 0; i < TC_NB; ++i) braw[i] = 0.f;
+            if (live) {
+                int idx[T2_ND];
+                t2_decode(u, geo, idx);
+#pragma unroll
+                for (int i = 0; i < TC_NB; ++i) if (i < nb) braw[i] = p.b[i][t2_dot(idx, geo.bs[i]) + kz * geo.bk[i]];
+                const float* vp = p.v + t2_dot(idx, geo.vs) + kz * vk;
+                if (vec2) {
+#pragma unroll
+                    for (int q2 = 0; q2 < D / 2; ++q2) {
+                        const float2 vv = *reinterpret_cast<const float2*>(vp + 2 * q2);
+                        raw[2 * q2] = vv.x; raw[2 * q2 + 1] = vv.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int dd = 0; dd < D; ++dd) raw[dd] = vp[dd * vev];
+                }
+            }
+        };
+        if (blk0 < n_blocks) load_raw(blk0, cur, cur_b);
         unsigned it = 0;
         for (unsigned blk = blk0; blk < n_blocks; blk += blk_step, ++it) {
             const int s = it % T2_STAGES;
             const uint32_t ps = (it / T2_STAGES) & 1;
+#ifdef TC_DEBUG_SPIN
+            const long long tb0 = clock64();
+#endif
+            if (blk + blk_step < n_blocks) load_raw(blk + blk_step, nxt, nxt_b);
+            MBAR_WAIT(&empty[s], ps ^ 1, dbg0);
+#ifdef TC_DEBUG_SPIN
+            const long long tb1 = clock64();
+#endif
+            if (kz < Kk) {                       // rows of users >= n_u are written as zeros: finite, masked later
+                float* bh = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER);
+                float* bl = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER);
+                float bsum = 0.f;
 #pragma unroll
-            for (int h = 0; h < T2_US / T2_BW; ++h) {
-                const int us = bw + T2_BW * h, n = 32 * us + kz;
-                const unsigned u = T2_US * blk + us;
-                const bool live = u < n_u && kz < Kk;
-                float t[KT];
+                for (int i = 0; i < TC_NB; ++i) if (i < nb) bsum += geo.bc[i] * cur_b[i];
+                bsum *= LS;
 #pragma unroll
-                for (int k = 0; k < KT; ++k) t[k] = 0.f;
-                if (live) {
-                    int idx[T2_ND];
-                    t2_decode(u, geo, idx);
-                    float b = 0.f;
+                for (int c = 0; c < NC; ++c) {
+                    // the tensor core reads only the 19 TF32 bits of a word: the raw fp32 value IS the "hi" part and
+                    // lo = t - trunc(t) its exact remainder
+                    float tv[4];
 #pragma unroll
-                    for (int i = 0; i < TC_NB; ++i) if (i < nb) b += geo.bc[i] * p.b[i][t2_dot(idx, geo.bs[i]) + kz * geo.bk[i]];
-                    const float* vp = p.v + t2_dot(idx, geo.vs) + kz * vk;
-                    if (vec2) {
-#pragma unroll
-                        for (int q2 = 0; q2 < D / 2; ++q2) {
-                            const float2 vv = *reinterpret_cast<const float2*>(vp + 2 * q2);
-                            const float d0 = vv.x - s_cd[2 * q2], d1 = vv.y - s_cd[2 * q2 + 1];
-                            t[2 * q2] = d0 * d0; t[2 * q2 + 1] = d1 * d1;
-                            t[D + 2 * q2] = d0; t[D + 2 * q2 + 1] = d1;
-                        }
-                    } else {
-#pragma unroll
-                        for (int dd = 0; dd < D; ++dd) { const float df = vp[dd * vev] - s_cd[dd]; t[dd] = df * df; t[D + dd] = df; }
+                    for (int e = 0; e < 4; ++e) {
+                        const int k = 4 * c + e;
+                        const float df = cur[k < D ? k : (k < 2 * D ? k - D : 0)] - s_cd[k < D ? k : (k < 2 * D ? k - D : 0)];
+                        tv[e] = k < D ? df * df : k < 2 * D ? df : k == 2 * D ? bsum : 0.f;
                     }
-                    t[2 * D] = b * LS;
-                }
-                if (h == 0) mbar_wait(&empty[s], ps ^ 1);
-                if (kz < Kk) {                   // rows of users >= n_u are written as zeros: finite, masked later
-                    float* bh = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER);
-                    float* bl = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER);
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        // the tensor core reads only the 19 TF32 bits of a word: the raw fp32 value IS the "hi" part and
-                        // lo = t - trunc(t) its exact remainder
-                        float4 hh, l;
-                        hh.x = t[4 * c + 0]; l.x = hh.x - __uint_as_float(__float_as_uint(hh.x) & 0xFFFFE000u);
-                        hh.y = t[4 * c + 1]; l.y = hh.y - __uint_as_float(__float_as_uint(hh.y) & 0xFFFFE000u);
-                        hh.z = t[4 * c + 2]; l.z = hh.z - __uint_as_float(__float_as_uint(hh.z) & 0xFFFFE000u);
-                        hh.w = t[4 * c + 3]; l.w = hh.w - __uint_as_float(__float_as_uint(hh.w) & 0xFFFFE000u);
-                        const int off = (c * T2_N + n) * 4;
-                        *reinterpret_cast<float4*>(bh + off) = hh;
-                        *reinterpret_cast<float4*>(bl + off) = l;
-                    }
+                    float4 hh, l;
+                    hh.x = tv[0]; l.x = hh.x - __uint_as_float(__float_as_uint(hh.x) & 0xFFFFE000u);
+                    hh.y = tv[1]; l.y = hh.y - __uint_as_float(__float_as_uint(hh.y) & 0xFFFFE000u);
+                    hh.z = tv[2]; l.z = hh.z - __uint_as_float(__float_as_uint(hh.z) & 0xFFFFE000u);
+                    hh.w = tv[3]; l.w = hh.w - __uint_as_float(__float_as_uint(hh.w) & 0xFFFFE000u);
+                    const int off = (c * T2_N + n) * 4;
+                    *reinterpret_cast<float4*>(bh + off) = hh;
+                    *reinterpret_cast<float4*>(bl + off) = l;
                 }
             }
+#ifdef TC_DEBUG_SPIN
+            const long long tb2 = clock64();
+#endif
             fence_async_smem();
             mbar_arrive(&full[s]);
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) cur[dd] = nxt[dd];
+#pragma unroll
+            for (int i = 0; i < TC_NB; ++i) cur_b[i] = nxt_b[i];
+#ifdef TC_DEBUG_SPIN
+            dbg1 += tb2 - tb1;                   // build + store
+            dbg2 += clock64() - tb2;             // fence + arrive
+            dbg3 += tb1 - tb0;                   // load issue + wait for the stage
+#endif
         }
     }
 
+#ifdef TC_DEBUG_SPIN
+    if ((blockIdx.x == 0 || blockIdx.x == 60 || blockIdx.x == 120 || blockIdx.x == 147) && lane == 0 && (warp == 0 || warp == T2_MMA_WARP || warp == T2_MMA_WARP + 1)) {
+        unsigned long long g1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
+        printf("tc2 bwd=%d cta %d warp %d prologue %lld total %lld wait0 %lld wait1 %lld d2 %lld d3 %lld ns %llu\n", (int)BWD, (int)blockIdx.x, warp, dbg_t0 - dbg_k0, clock64() - dbg_t0, dbg0, dbg1, dbg2, dbg3, g1 - dbg_g0);
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == T2_MMA_WARP) {
@@ -455,7 +553,7 @@ static bool fan_lse_tc2_supported(const FanLseParams<float>& p, int D, bool bwd)
     const i64 L = lam >= 0 ? p.rd.size[lam] : 1;
     const i64 FP = L * p.F, NG = (FP + T2_TILES * 128 - 1) / (T2_TILES * 128);
     const i64 n_u = p.n_rho / L;
-    if (FP < 96 || NG > 4 || (bwd && NG > L) || p.Kk > 32 || n_u < 16 || p.nb > TC_NB) return false;
+    if (FP < 96 || NG > T2_MAXG || (bwd && NG > L) || p.Kk > 32 || n_u < 16 || p.nb > TC_NB) return false;
     if (p.rd.nd - (lam >= 0 ? 1 : 0) > T2_ND) return false;
     const i64 lim = (i64)1 << 31;
     i64 vspan = (i64)p.Kk * p.v_k + 32 * p.v_ev, ospan = FP * (p.o_f > 0 ? p.o_f : 1), bspan = 0;
@@ -473,7 +571,7 @@ template <int D>
 static int launch_fan_lse_tc2_D(const FanLseParams<float>& p, bool bwd, cudaStream_t stream, int sm_count) {
     constexpr int KT = (2 * D + 1 + 7) / 8 * 8;
     constexpr size_t OPER = (size_t)(KT / 4) * T2_N * 16;
-    const size_t smem = (T2_TILES + T2_STAGES * 2) * OPER + T2_TILES * 128 * 12 + 2 * 8 * 2 * 32 * 4 + 32 * 4 +
+    const size_t smem = (T2_STAGES * 2) * OPER + T2_TILES * 128 * 12 + 2 * 4 * T2_US * 32 * 4 + 32 * 4 +
                         (2 * T2_STAGES + 2 * T2_ACC) * 8 + 16;
     const int lam = fan_lse_tc2_lam(p);
     Tc2Geom geo;
@@ -505,15 +603,32 @@ static int launch_fan_lse_tc2_D(const FanLseParams<float>& p, bool bwd, cudaStre
     geo.FP = geo.L * p.F;
     geo.NG = (geo.FP + T2_TILES * 128 - 1) / (T2_TILES * 128);
     const i64 n_blocks = ((i64)geo.n_u + T2_US - 1) / T2_US;
-    i64 per_group = sm_count / geo.NG;
-    if (per_group > n_blocks) per_group = n_blocks;
-    if (per_group < 1) per_group = 1;
-    const int blocks = (int)per_group * geo.NG;
+    // CTAs per fan group in proportion to the group's tiles (the last group may be short), each at most n_blocks
+    const int tiles_total = (geo.FP + 127) / 128;
+    int blocks = 0;
+    {
+        // weight of a group = its tiles + a per-block cost measured at ~1.75 tiles (builder + block bookkeeping)
+        int left_cta = sm_count > geo.NG ? sm_count : geo.NG, left_tiles = tiles_total;
+        int left_w = 4 * tiles_total + T2_BLOCK_COST4 * geo.NG;
+        for (int g = 0; g < geo.NG; ++g) {
+            int tg = tiles_total - T2_TILES * g; if (tg > T2_TILES) tg = T2_TILES;
+            int n = (int)(((i64)left_cta * (4 * tg + T2_BLOCK_COST4) + left_w / 2) / left_w);
+            if (n < 1) n = 1;
+            if (n > left_cta - (geo.NG - 1 - g)) n = left_cta - (geo.NG - 1 - g);
+            left_cta -= n; left_tiles -= tg; left_w -= 4 * tg + T2_BLOCK_COST4;
+            if (n > n_blocks) n = (int)n_blocks;
+            geo.cta_lo[g] = blocks;
+            blocks += n;
+        }
+        for (int g = geo.NG; g <= T2_MAXG; ++g) geo.cta_lo[g] = blocks;
+    }
     if (bwd) {
-        cudaFuncSetAttribute(fan_lse_tc2_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static const cudaError_t attr_true = cudaFuncSetAttribute(fan_lse_tc2_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // once per process
+        (void)attr_true;
         fan_lse_tc2_kernel<D, true><<<blocks, T2_WARPS * 32, smem, stream>>>(p, geo);
     } else {
-        cudaFuncSetAttribute(fan_lse_tc2_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static const cudaError_t attr_false = cudaFuncSetAttribute(fan_lse_tc2_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // once per process
+        (void)attr_false;
         fan_lse_tc2_kernel<D, false><<<blocks, T2_WARPS * 32, smem, stream>>>(p, geo);
     }
     return 0;
