@@ -451,12 +451,148 @@ __global__ void __launch_bounds__(256) bern_dot_sum_kernel(const __grid_constant
     }
 }
 
+// Shared-memory staged variant for the common layout: one summed plate dim whose b rows ([n, d] block of one "user")
+// are contiguous, and an innermost kept dim (the K axis of the sample) that neither b nor y carries.  A CTA takes UPC
+// users at a time: their b blocks are read from HBM ONCE with coalesced loads (the thread-per-output kernel above
+// re-reads every 8-byte piece through the LSU from all K threads of a user: LSU-bound at ~12 % of the HBM roofline on
+// B200), padded to 16-byte rows in shared memory, and thread (user, k) walks them with broadcast LDS.128.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" :: "r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+
+#define BDS_THREADS 256
+#define BDS_SMEM_BYTES (40 * 1024)
+template <typename T, int D>
+__global__ void __launch_bounds__(BDS_THREADS) bern_dot_sum_smem_kernel(const __grid_constant__ BernDotParams<T> p, int Kin, int UPC, int NCH) {
+    constexpr int DP = (D + 3) & ~3;                                   // row pitch (elements): 16-byte rows for float
+    extern __shared__ __align__(16) unsigned char bds_smem[];
+    T* xs = reinterpret_cast<T*>(bds_smem);                            // [UPC][NCH][DP]
+    T* ys = xs + (size_t)UPC * NCH * DP;                               // [UPC][NCH]
+    const T* A = (const T*)p.a.ptr;
+    const T* B = (const T*)p.b.ptr;
+    const T* Y = (const T*)p.y.ptr;
+    const int ka = p.d.n_a - 1;                                        // innermost kept dim
+    const i64 n_users = p.n_out / Kin;
+    const int N = (int)p.n_red;
+    const i64 bn = p.b.stride[p.d.n_a], yn = p.y.stride[p.d.n_a];
+    const int tu = threadIdx.x / Kin, tk = threadIdx.x - tu * Kin;     // (user slot, k) of this thread
+    const bool worker = tu < UPC;
+    int idx[AB_MAXD];
+    __shared__ i64 s_bb[BDS_THREADS / 8], s_yb[BDS_THREADS / 8];      // per user slot: base offsets of its b block / y row
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (i64 u0 = (i64)blockIdx.x * UPC; u0 < n_users; u0 += (i64)gridDim.x * UPC) {
+        const i64 u = u0 + tu;
+        const bool live = worker && u < n_users;
+        T ar[D];
+        if (live) {
+            unravel(u * Kin + tk, p.d, 0, p.d.n_a, idx);
+            const i64 ab = dot_stride(p.a, idx, 0, p.d.n_a);
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) ar[dd] = A[ab + dd * p.a_ev];
+        }
+        __syncthreads();                                               // the previous users have been consumed
+        if (threadIdx.x < UPC) {
+            const i64 uu = u0 + threadIdx.x;
+            i64 bb = -1, yb = -1;
+            if (uu < n_users) {
+                unravel(uu * Kin, p.d, 0, p.d.n_a, idx);
+                bb = dot_stride(p.b, idx, 0, p.d.n_a);
+                yb = dot_stride(p.y, idx, 0, p.d.n_a);
+            }
+            s_bb[threadIdx.x] = bb; s_yb[threadIdx.x] = yb;
+        }
+        T acc0 = T(0), acc1 = T(0);
+        for (int n0 = 0; n0 < N; n0 += NCH) {
+            const int nc = min(NCH, N - n0);
+            __syncthreads();                                           // offsets visible; the previous chunk has been consumed
+            // stage: one warp per user slot, consecutive lanes read consecutive (pairs of) elements of the [nc, D] block
+            for (int us = warp; us < UPC; us += BDS_THREADS / 32) {
+                const i64 bb = s_bb[us], yb = s_yb[us];
+                if (bb < 0) continue;
+                const T* src = B + bb + (i64)n0 * bn;
+                T* dst = xs + (size_t)us * NCH * DP;
+                // cp.async (LDGSTS): every copy of the lane is in flight at once, nothing passes through registers
+                if (p.vec2) {
+                    constexpr int H = D / 2 > 0 ? D / 2 : 1;
+                    for (int i = lane; i < nc * H; i += 32) {
+                        const int n = i / H, q = i - n * H;
+                        cp_async<2 * sizeof(T)>(dst + (size_t)n * DP + 2 * q, src + 2 * i);
+                    }
+                } else {
+                    for (int i = lane; i < nc * D; i += 32) {
+                        const int n = i / D, dd = i - n * D;
+                        cp_async<sizeof(T)>(dst + (size_t)n * DP + dd, src + i);
+                    }
+                }
+                for (int n = lane; n < nc; n += 32) ys[us * NCH + n] = Y[yb + (i64)(n0 + n) * yn];
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+            if (live) {
+                const T* xr = xs + (size_t)tu * NCH * DP;
+                const T* yr = ys + tu * NCH;
+#pragma unroll 2
+                for (int n = 0; n < nc; ++n) {
+                    T row[DP];
+                    if (sizeof(T) == 4) {
+#pragma unroll
+                        for (int q = 0; q < DP / 4; ++q)
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(row) + 4 * q) =
+                                *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xr) + (size_t)n * DP + 4 * q);
+                    } else {
+#pragma unroll
+                        for (int dd = 0; dd < D; ++dd) row[dd] = xr[(size_t)n * DP + dd];
+                    }
+                    // packed pairs (FFMA2 in fp32): half the FMA issue slots, two independent chains
+                    typedef typename Pair2<T>::type P2;
+                    P2 l2 = mk2(T(0), T(0)), l3 = mk2(T(0), T(0));
+#pragma unroll
+                    for (int dd = 0; dd + 1 < D; dd += 2) {
+                        if ((dd >> 1) & 1) l3 = fma2(mk2(ar[dd], ar[dd + 1]), mk2(row[dd], row[dd + 1]), l3);
+                        else l2 = fma2(mk2(ar[dd], ar[dd + 1]), mk2(row[dd], row[dd + 1]), l2);
+                    }
+                    T l0 = (l2.x + l3.x), l1 = (l2.y + l3.y);
+                    if (D & 1) l0 += ar[D - 1] * row[D - 1];
+                    const T lp = bern_logits_fast(yr[n], l0 + l1);
+                    if (n & 1) acc1 += lp; else acc0 += lp;
+                }
+            }
+        }
+        if (live) p.out[u * Kin + tk] = (acc0 + acc1) + p.cadd;
+    }
+    (void)ka;
+}
+
 template <typename T, int D>
 static void launch_bern_dot_D(BernDotParams<T> p, cudaStream_t stream, int sm_count) {
     bool v2 = (D % 2 == 0) && p.a_ev == 1 && p.b_ev == 1 && ((uintptr_t)p.a.ptr % (2 * sizeof(T)) == 0) &&
               ((uintptr_t)p.b.ptr % (2 * sizeof(T)) == 0);
     for (int k = 0; k < p.d.nd && v2; ++k) v2 = (p.a.stride[k] % 2 == 0) && (p.b.stride[k] % 2 == 0);
     p.vec2 = v2 ? 1 : 0;
+    // staged variant: one summed dim with contiguous b rows, innermost kept dim absent from b and y, out contiguous
+    const int nred = p.d.nd - p.d.n_a, ka = p.d.n_a - 1;
+    if (nred == 1 && p.d.n_a >= 1 && p.b_ev == 1 && p.b.stride[p.d.n_a] == D && p.b.stride[ka] == 0 && p.y.stride[ka] == 0 &&
+        p.d.size[ka] <= BDS_THREADS && p.d.size[ka] >= 8 && p.n_red >= 2 && p.n_out / p.d.size[ka] >= 64) {
+        constexpr int DP = (D + 3) & ~3;
+        const int Kin = p.d.size[ka];
+        const int UPC = BDS_THREADS / Kin;
+        // 64-bit staging loads: even D, b block bases and the step between summed rows 2-element aligned
+        bool sv2 = (D % 2 == 0) && ((uintptr_t)p.b.ptr % (2 * sizeof(T)) == 0);
+        for (int k = 0; k < p.d.nd && sv2; ++k) sv2 = (p.b.stride[k] % 2 == 0);
+        p.vec2 = sv2 ? 1 : 0;
+        int NCH = (int)(BDS_SMEM_BYTES / ((size_t)UPC * (DP + 1) * sizeof(T)));
+        if (NCH > p.n_red) NCH = (int)p.n_red;
+        if (NCH >= 2) {
+            const size_t smem = (size_t)UPC * NCH * (DP + 1) * sizeof(T);
+            const i64 n_users = p.n_out / Kin;
+            i64 blocks = (n_users + UPC - 1) / UPC, cap = (i64)sm_count * 5;
+            if (blocks > cap) blocks = cap;
+            bern_dot_sum_smem_kernel<T, D><<<(int)blocks, BDS_THREADS, smem, stream>>>(p, Kin, UPC, NCH);
+            return;
+        }
+    }
     i64 blocks = (p.n_out + 255) / 256, cap = (i64)sm_count * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
