@@ -474,6 +474,30 @@ class FanLseOp(Op):
         self._body(w)
 
 
+DENSE_TILES, DENSE_MAXG, DENSE_EVENTS = 3, 8, (2, 4, 6, 8, 12, 16, 18)
+
+
+def dense_fan_geometry(op: 'FanLseOp', itemsize=4):
+    """Mirror of csrc/fan_tc2.cuh fan_lse_tc2_supported: (lam dim, L, number of fan groups) when the dense tcgen05
+    formulation applies to this fused contraction (fp32, loc depends on exactly one rho dim that neither the value
+    nor the small factors carry), else None.  Used by bench.py to describe the kernel that ran."""
+    if itemsize != 4 or op.D not in DENSE_EVENTS or op.l.stride(op.kappa) != 0:
+        return None
+    lam = [d for d in op.rho if d[2] > 1 and op.l.stride(d) != 0]
+    if len(lam) != 1:
+        return None
+    lam = lam[0]
+    if op.v.stride(lam) != 0 or any(lf.stride(lam) != 0 for lf, _ in op.bfactors):
+        return None
+    L = lam[2]
+    FP = L * op.F
+    NG = -(-FP // (DENSE_TILES * 128))
+    n_u = _prod(d[2] for d in op.rho) // L
+    if FP < 96 or NG > DENSE_MAXG or NG > L or op.kappa[2] > 32 or n_u < 16 or len(op.bfactors) > 4 or len(op.rho) - 1 > 4:
+        return None
+    return lam, L, NG
+
+
 class FanLseBwdOp(Op):
     """gS[rho, kappa] = sum_f gout[rho,f] * softmax weight: adjoint of the small-factor sum."""
     code = OP_FAN_LSE

@@ -337,22 +337,36 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
             tc_path = m["kind"] in ("FanLseOp", "FanLseBwdOp") and comp.dtype == t.float32 and \
                 not os.environ.get("ALAN_B200_NO_TC")
             if tc_path:
-                # fan_lse on tcgen05 (csrc/fan_tc.cuh): fp32-accurate 3xTF32, block-diagonal constant operand.
-                # Algorithmic flops against the measured dense bf16 peak; the ceiling this formulation can reach
-                # is peak / 2 (tf32) / 3 (split) / 4 (block-diagonal zeros).
+                from alan_b200.plan import dense_fan_geometry
+                fop = op if m["kind"] == "FanLseOp" else op.fwd
+                dense = None if os.environ.get("ALAN_B200_TC_BLOCKDIAG") else dense_fan_geometry(fop, 4)
                 roof = dict(bound="tensor", achieved=m["flops"] / (top_ms * 1e-3) / 1e12, peak=pk["bf16_tflops"],
                             unit="TFLOP/s")
-                roof["formulation_ceiling"] = pk["bf16_tflops"] / 24
+                if dense is not None:
+                    # fan_lse on tcgen05, dense formulation (csrc/fan_tc2.cuh): fp32-accurate 3xTF32 of the expanded
+                    # square.  Algorithmic flops (2 D per cell) against the measured dense bf16 peak; what this
+                    # formulation can reach is peak / 2 (tf32) / 3 (split) x D / KT (K = 2 D + 1 padded to 8) x the
+                    # used share of the 128-lane tiles and 32-column user slots.
+                    _, L, NG = dense
+                    KT = (2 * fop.D + 1 + 7) // 8 * 8
+                    tiles = -(-(L * fop.F) // 128)
+                    eff = (fop.D / KT) * (L * fop.F / (128.0 * tiles)) * (fop.kappa[2] / 32.0)
+                    roof["formulation_ceiling"] = pk["bf16_tflops"] / 6 * eff
+                    roof["path"] = ("tcgen05.mma kind::tf32, 3xTF32 split of the expanded square, (lam, f) on TMEM lanes, "
+                                    "A in TMEM (UTCHMMA / LDTM in SASS), %d fan groups" % NG)
+                else:
+                    # block-diagonal kernel (csrc/fan_tc.cuh): peak / 2 (tf32) / 3 (split) / 4 (block-diagonal zeros)
+                    roof["formulation_ceiling"] = pk["bf16_tflops"] / 24
+                    roof["path"] = "tcgen05.mma kind::tf32, 3xTF32 split, block-diagonal A in TMEM (UTCHMMA / LDTM in SASS)"
                 roof["frac_of_formulation_ceiling"] = roof["achieved"] / roof["formulation_ceiling"]
-                roof["path"] = "tcgen05.mma kind::tf32, 3xTF32 split, A in TMEM (UTCHMMA / LDTM in SASS)"
             elif t_hbm >= t_fp:
                 roof = dict(bound="hbm", achieved=m["bytes"] / (top_ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s")
             else:
                 roof = dict(bound="fp32", achieved=m["flops"] / (top_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s")
             roof["frac"] = roof["achieved"] / roof["peak"]
             # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this command
-            # at cfg-5 on one GPU (profiles/r01_fan_lse_tc_full.md: dram__bytes_read.sum + dram__bytes_write.sum)
-            ncu_traffic = {"FanLseBwdOp": 60.07e6 + 5.50e6, "FanLseOp": 24.06e6 + 0.13e6}
+            # at cfg-5 on one GPU (profiles/r01_fan_lse_tc2_full.md: dram__bytes_read.sum + dram__bytes_write.sum)
+            ncu_traffic = {"FanLseBwdOp": 60.09e6 + 2.35e6, "FanLseOp": 24.07e6 + 0.64e6}
             traffic = ncu_traffic.get(m["kind"]) if (tc_path and cfg["M"] // max(world, 1) == 10000 and cfg["N"] == 50) else None
             roof.update(traffic=traffic, kernel=f"{m['kind']}:{m['tag']}", kernel_ms=top_ms,
                         share_of_step=top_ms / total, peak_source=pk["source"],
