@@ -45,6 +45,8 @@ struct alan_b200_plan {
     mutable std::vector<int> n_out, n_aux;          // per program, learnt on the first run (-1 = unknown)
     mutable unsigned long long tick = 0;
     bool use_graphs = true;
+    bool graph_auto = false;       // replay only bindings that repeat (see alan_b200_plan_create)
+    mutable std::vector<int> miss_streak;   // per program: captures since the last replay hit (auto mode gives up at 4)
     bool use_seq = false;          // run consecutive small ops as one launch (ALAN_B200_SEQ=1 at plan creation: on)
     bool use_tc = true;            // fan_lse on tcgen05 where the shape allows (ALAN_B200_NO_TC=1 at plan creation: FFMA2 kernel)
     bool use_tc2 = true;           // dense formulation (fan_tc2.cuh) where the loc is independent of the value's axes
@@ -489,10 +491,19 @@ int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** 
     p->graphs.resize(p->n_programs);
     p->n_out.assign(p->n_programs, -1);
     p->n_aux.assign(p->n_programs, -1);
-    // Opt-in: measured on B200 (gpurun_out/bench6*.json) a program replay costs ~30 us of launch latency more than
-    // the already asynchronous per-op launches it replaces (device-timed step +7 %), while saving host time per call
-    // (end-to-end +5..20 %).  ALAN_B200_GRAPH=1 turns it on for host-bound callers.
-    p->use_graphs = getenv("ALAN_B200_GRAPH") != nullptr;
+    // CUDA-graph replay of a program.  Measured on B200: a replay costs ~20 us of launch latency per program (two
+    // programs per step), and saves the 2-4 us gap between each pair of dependent launches: cfg-2 (300 users, 33
+    // launches of a few us) 0.26 -> 0.30 ms per step, cfg-5 (10 000 users) 0.75 -> 0.61 ms.  Default = auto: plans
+    // with a large workspace (>= 32 MB: their kernels run for tens of microseconds) capture a program on the first
+    // call with a binding of pointers and replay it when the binding returns; a caller that passes fresh buffers on
+    // every call stops paying for captures after four in a row without a replay.  ALAN_B200_GRAPH=1 forces replay from the first call, ALAN_B200_GRAPH=0 turns it off.
+    {
+        const char* g = getenv("ALAN_B200_GRAPH");
+        const bool big = p->ws_bytes >= ((size_t)32 << 20);
+        p->use_graphs = g ? (g[0] != '0') : big;
+        p->graph_auto = (g == nullptr) && big;
+    }
+    p->miss_streak.assign(p->n_programs, 0);
     p->use_tc = getenv("ALAN_B200_NO_TC") == nullptr;
     p->use_tc2 = getenv("ALAN_B200_TC_BLOCKDIAG") == nullptr;
     // Opt-in: halves the launch count of a step, but measured on B200 the device time does not move (the small ops
@@ -582,6 +593,7 @@ static int run_graphed(const alan_b200_plan* p, int program, const Ctx& c, const
         for (auto& g : p->graphs[program]) {
             if (g.key == key) {
                 g.last_use = ++p->tick;
+                p->miss_streak[program] = 0;
                 cudaGraphExec_t exec = g.exec;
                 lock.unlock();
                 cudaError_t e = cudaGraphLaunch(exec, c.stream);
@@ -590,6 +602,12 @@ static int run_graphed(const alan_b200_plan* p, int program, const Ctx& c, const
             }
         }
     }
+    if (p->graph_auto && p->miss_streak[program] >= 4) {
+        // auto mode: this caller binds fresh buffers on every call -- captures would never be replayed
+        lock.unlock();
+        return run_direct(p, program, c);
+    }
+    ++p->miss_streak[program];
     // miss: capture this call's launches, instantiate, remember, launch
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
