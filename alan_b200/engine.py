@@ -174,21 +174,62 @@ class Runner:
         if grad_lp is None:
             grad_lp = torch.ones((), dtype=self.dtype, device=self.device)
         grad_lp = grad_lp.to(self.dtype).contiguous()
-        outs = [torch.empty(plan.input_pts[n].shape, dtype=self.dtype, device=self.device)
+        import torch.distributed as dist
+        sharded = bool(plan.global_grads) and dist.is_available() and dist.is_initialized() \
+            and dist.get_world_size(self.pg) > 1
+        flat, views = None, {}
+        if sharded:
+            # the global-parameter gradients live side by side in ONE buffer (slices aligned to 16 bytes), so the
+            # single all-reduce runs in place: no concatenate / copy-back launches around the collective
+            step = 16 // torch.empty((), dtype=self.dtype).element_size()
+            offs, total = {}, 0
+            for n in plan.global_grads:
+                offs[n] = total
+                total += -(-plan.input_pts[n].numel // step) * step
+            flat = torch.zeros(max(total, 1), dtype=self.dtype, device=self.device)
+            for n in plan.global_grads:
+                pt = plan.input_pts[n]
+                views[n] = flat[offs[n]:offs[n] + pt.numel].view(pt.shape)
+        outs = [views[n] if n in views else torch.empty(plan.input_pts[n].shape, dtype=self.dtype, device=self.device)
                 for n in plan.grad_inputs]
         for seg in range(plan.n_bwd):
             self.dp.bwd(seg, tensors, grad_lp, outs)
-        if plan.global_grads:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1:
-                flat = torch.cat([outs[plan.grad_inputs.index(n)].reshape(-1) for n in plan.global_grads])
-                dist.all_reduce(flat, group=self.pg)
-                off = 0
-                for n in plan.global_grads:
-                    o = outs[plan.grad_inputs.index(n)]
-                    o.copy_(flat[off:off + o.numel()].view_as(o))
-                    off += o.numel()
+        if sharded:
+            dist.all_reduce(flat, group=self.pg)
         return dict(zip(plan.grad_inputs, outs))
+
+    def step(self, tensors):
+        """forward_raw + backward_raw as ONE replayed CUDA graph (the collectives of a sharded plan included):
+        a training loop that keeps its device buffers pays one graph launch per step instead of one per
+        program segment plus the eager collectives between them.  The first call with a given binding of
+        input pointers runs eagerly, the second is captured, later ones replay.  Returns (lp, {name: grad});
+        both are STATIC buffers that the next call with the same binding overwrites.  Any failure to
+        capture (e.g. a collective backend that cannot be captured) falls back to the eager path for good."""
+        if not hasattr(self, "_step_graphs"):
+            self._step_graphs, self._step_seen, self._step_off = {}, {}, False
+        key = tuple(int(x.data_ptr()) for x in tensors)
+        ent = self._step_graphs.get(key)
+        if ent is not None:
+            ent[0].replay()
+            return ent[1], ent[2]
+        if self._step_off or self._step_seen.get(key, 0) < 1 or len(self._step_graphs) >= 4:
+            self._step_seen[key] = self._step_seen.get(key, 0) + 1
+            lp = self.forward_raw(tensors)
+            return lp, self.backward_raw(tensors)
+        try:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                lp = self.forward_raw(tensors)
+                grads = self.backward_raw(tensors)
+            g.replay()
+        except Exception:
+            self._step_off = True
+            torch.cuda.synchronize(self.device)
+            lp = self.forward_raw(tensors)
+            return lp, self.backward_raw(tensors)
+        self._step_graphs[key] = (g, lp, grads)
+        return lp, grads
 
     def resample_raw(self, tensors, uniforms):
         """uniforms: list of float64 device tensors, one per sampling step (plan.sample_steps order),

@@ -208,9 +208,11 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
     W = cells(**cfg)
 
     def step():
-        lp = run.forward_raw(tensors)
-        g = run.backward_raw(tensors)
-        return lp, g
+        # Runner.step = forward_raw + backward_raw (replayed as one CUDA graph once the buffers recur);
+        # ALAN_B200_EAGER_STEP=1 keeps the two eager calls
+        if os.environ.get("ALAN_B200_EAGER_STEP"):
+            return run.forward_raw(tensors), run.backward_raw(tensors)
+        return run.step(tensors)
 
     def barrier():
         if world > 1:
@@ -295,7 +297,7 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
                    "l2": "256 MB buffer written between timed steps (L2 flush)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": (f"engine.StreamedRunner.step, plate_1 in {args.chunks} blocks (H2D of block c+1 overlaps block c)"
-                        if streamed is not None else "H2D copies, Runner.forward_raw + backward_raw, D2H")},
+                        if streamed is not None else "H2D copies, Runner.step (forward_raw + backward_raw as one replayed graph), D2H")},
         "gpu_launches": launches * args.steps,
         "lp": float(lp_host),
         "wall_s_timed_region": wall,
@@ -454,8 +456,10 @@ def main():
         return
 
     import torch.distributed as dist
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the single JSON line
+    # keep stdout to the single JSON line: NCCL prints its version banner there at level VERSION, which this image
+    # configures outside the environment (nccl.conf); an explicit environment value wins over the file
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         dist.init_process_group("nccl", device_id=t.device(f"cuda:{local_rank}"))
     line = run_b200(args, cfg, rank, world, local_rank)

@@ -448,6 +448,30 @@ def test_streamed_runner_matches_single_pass(chunks):
         StreamedRunner(P, Q, sample, ip, data, names, 'plate_1', 7, device="cuda:0")
 
 
+def test_runner_step_graph_replay_matches_eager():
+    """Runner.step (forward_raw + backward_raw captured once as a CUDA graph, then replayed) against the two eager
+    calls: bit-identical log-evidence and gradients, on the first (eager), second (captured) and later (replayed)
+    calls, and again after the inputs changed in place."""
+    Compiled, Runner = _engine()
+    P, Q, sample, ip, data, names = _movielens_case(64, 5, 30, 18, seed=41)
+    comp = Compiled(P, Q, sample, ip, data, grad_names=names)
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(sample, ip, data)
+    lp = run.forward_raw(tensors).clone()
+    grads = {k: v.clone() for k, v in run.backward_raw(tensors).items()}
+    for _ in range(4):
+        lp_s, g_s = run.step(tensors)
+        assert t.equal(lp_s, lp) and all(t.equal(g_s[k], grads[k]) for k in names)
+    assert len(run._step_graphs) == 1
+    zi = comp.plan.input_names.index('z')
+    tensors[zi].mul_(1.01)                                   # same buffers, new values: the replay must see them
+    lp2 = run.forward_raw(tensors).clone()
+    g2 = {k: v.clone() for k, v in run.backward_raw(tensors).items()}
+    lp_s, g_s = run.step(tensors)
+    assert not t.equal(lp2, lp)
+    assert t.equal(lp_s, lp2) and all(t.equal(g_s[k], g2[k]) for k in names)
+
+
 @pytest.mark.parametrize("case", ["cfg1_lglp", "cfg3_radon", "cfg4_timeseries"])
 def test_optional_executor_modes_keep_results(case, monkeypatch):
     """ALAN_B200_SEQ=1 (consecutive small ops in one launch) and ALAN_B200_GRAPH=1 (CUDA-graph replay of a
