@@ -30,8 +30,9 @@
 //   MMA       1 warp (elected lane), owns the TMEM allocation
 //   builders  4 warps: warp = user slot, lane = kappa; raw loads of the next block are in flight while the current
 //             one is squared, split and stored
-// The adjoint writes gS[u, lam = g, kappa] for group g (its partial over that group's fan columns) -- the planner's
-// reduce over lam that follows sums the partials; the other lam slots stay zero (zeroed adjoint region).
+// The adjoint writes its partial over fan group g into gS[u, g, kappa] -- the layout the planner commits to when it
+// finds the pattern (plan.py dense_fan_geometry; the reduce that follows sums NG partials per user) -- or, for plans
+// built without it, into gS[u, lam = g, kappa] of the [rho, kappa] layout (the other lam slots stay zero).
 //
 // Measured on B200, cfg-5 (10 000 users, L = F = 30, D = 18), cycles per CTA (TC_DEBUG_SPIN): forward 240 k, of which
 // the MMA issuer is busy 75 % (87 cycles per MMA) and the epilogue warps 90 %; adjoint 310 k, epilogue-bound.
@@ -553,7 +554,7 @@ static bool fan_lse_tc2_supported(const FanLseParams<float>& p, int D, bool bwd)
     const i64 L = lam >= 0 ? p.rd.size[lam] : 1;
     const i64 FP = L * p.F, NG = (FP + T2_TILES * 128 - 1) / (T2_TILES * 128);
     const i64 n_u = p.n_rho / L;
-    if (FP < 96 || NG > T2_MAXG || (bwd && NG > L) || p.Kk > 32 || n_u < 16 || p.nb > TC_NB) return false;
+    if (FP < 96 || NG > T2_MAXG || (bwd && NG > L) || (bwd && p.gs_compact > 0 && p.gs_compact != NG) || p.Kk > 32 || n_u < 16 || p.nb > TC_NB) return false;
     if (p.rd.nd - (lam >= 0 ? 1 : 0) > T2_ND) return false;
     const i64 lim = (i64)1 << 31;
     i64 vspan = (i64)p.Kk * p.v_k + 32 * p.v_ev, ospan = FP * (p.o_f > 0 ? p.o_f : 1), bspan = 0;
@@ -596,6 +597,12 @@ static int launch_fan_lse_tc2_D(const FanLseParams<float>& p, bool bwd, cudaStre
         ++j;
     }
     for (int i = 0; i < p.nb; ++i) { geo.bk[i] = (int)p.b_k[i]; geo.bc[i] = p.bcoeff[i]; }
+    if (p.gs_compact > 0) {
+        // planner-committed layout [users (row-major), fan group, kappa]: nothing but the partials is ever stored
+        i64 acc = p.gs_compact;
+        for (int jj = T2_ND - 1; jj >= T2_ND - n_user_dims; --jj) { geo.ss[jj] = (int)acc; acc *= geo.sz[jj]; }
+        geo.s_lam = 1;
+    }
     geo.nb = p.nb;
     geo.g_f = (int)p.g_f;
     geo.vec2 = ev2 ? 1 : 0;

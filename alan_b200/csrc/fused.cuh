@@ -342,6 +342,7 @@ struct FanLseParams {
     const T* lse; const T* gout;          // bwd
     i64 gstride[AB_MAXD]; i64 g_f;        // bwd: strides of gout over the rho dims / fan axis (0 = broadcast)
     T* gS;                                // bwd: [rho, kappa] contiguous
+    int gs_compact;                       // bwd, dense tcgen05 kernel only: > 0 = gS is [users, gs_compact fan groups, kappa]
     i64 n_rho;
 };
 

@@ -17,6 +17,7 @@ cells x event (the reference's `[M,Kz,d,Kmu,Kpsi]` broadcast never exists).
 from __future__ import annotations
 
 import math
+import os
 import struct
 import types
 import numbers
@@ -443,6 +444,7 @@ class FanLseOp(Op):
         self.out, self.D, self.rho, self.kappa, self.v, self.l, self.s = out, D, rho, kappa, v, l, s
         self.fan_axis, self.F, self.bfactors, self.cadd = fan_axis, F, bfactors, cadd
         self.gen_expr, self.gen_reduce, self.tag = gen_expr, gen_reduce, tag
+        self.dense = None            # (lam dim, L, NG) when the planner commits the adjoint to the dense kernel's gS layout
 
     def _body(self, w):
         w.i32(self.D); w.i32(len(self.rho))
@@ -519,6 +521,8 @@ class FanLseBwdOp(Op):
             st = _strides_like(self.gout, self.gout_dims, f.rho + [fdim])
         for x in st:
             w.i64(x)
+        # > 0: gS is laid out [users, NG fan-group partials, kappa] (csrc/fan_tc2.cuh only); 0: [rho, kappa]
+        w.i32(self.fwd.dense[2] if self.fwd.dense is not None else 0)
 
 
 class DotOp(Op):
@@ -1179,8 +1183,13 @@ class Planner:
         if smem > 190 * 1024 or tile * self.itemsize > 44 * 1024:
             return None
         self.fwd.remove(fan)
-        return FanLseOp(red.out, fan.D, rho, self.axdim(kappa), fan.v, fan.l, fan.s, fan.fan_axis, fan.F,
-                        small, const, fan.autodiff_as, red, tag='fan_lse:' + fan.tag)
+        op = FanLseOp(red.out, fan.D, rho, self.axdim(kappa), fan.v, fan.l, fan.s, fan.fan_axis, fan.F,
+                      small, const, fan.autodiff_as, red, tag='fan_lse:' + fan.tag)
+        # commit the adjoint to the dense tensor-core kernel (compact gS: one slot per fan group instead of one per
+        # lam) unless the caller asked for the other kernels when the plan is built
+        if not (os.environ.get("ALAN_B200_NO_TC") or os.environ.get("ALAN_B200_TC_BLOCKDIAG")):
+            op.dense = dense_fan_geometry(op, self.itemsize)
+        return op
 
     def plate_sum(self, lf: LogicalFactor, plate):
         out_axes = tuple(a for a in lf.axes if a != plate)
@@ -1441,8 +1450,13 @@ class Planner:
             elif isinstance(op, FanLseOp):
                 bs = [(lf, coeff) for lf, coeff in op.bfactors if lf.pt.id in needs]
                 if bs:
-                    rows = op.rho + [op.kappa]
-                    gS = self.ws(tuple(d[1] for d in rows), name='adj:small_factor_sum')
+                    if op.dense is not None:
+                        lam, _, NG = op.dense
+                        rows = [d for d in op.rho if d != lam] + [('sp', 0, NG), op.kappa]
+                        gS = self.ws_raw(_prod(d[2] for d in rows), name='adj:small_factor_sum')
+                    else:
+                        rows = op.rho + [op.kappa]
+                        gS = self.ws(tuple(d[1] for d in rows), name='adj:small_factor_sum')
                     if op.out.id in lazy_bcast:
                         gsmall, gdims = lazy_bcast[op.out.id]
                         out_list.append(FanLseBwdOp(op, gsmall, gS, gout_dims=gdims))

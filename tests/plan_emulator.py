@@ -168,9 +168,21 @@ class Emu:
         rows = f.rho + [f.kappa]
         fdim = [('ax', f.fan_axis, f.F)]
         r = f.gen_reduce
-        self.op_ReduceOp(PL.ReduceOp(PL.R_WSUM, op.gS, rows, fdim, r.factors, lse=r.out, gout=op.gout,
-                                     lse_dims=r.od, gout_dims=op.gout_dims if op.gout_dims is not None else r.od,
-                                     cadd=r.cadd))
+        kw = dict(lse=r.out, gout=op.gout, lse_dims=r.od,
+                  gout_dims=op.gout_dims if op.gout_dims is not None else r.od, cadd=r.cadd)
+        if f.dense is None:
+            self.op_ReduceOp(PL.ReduceOp(PL.R_WSUM, op.gS, rows, fdim, r.factors, **kw))
+            return
+        # compact layout of the dense kernel (csrc/fan_tc2.cuh): gS[users, NG fan-group partials, kappa].  The
+        # emulator puts the whole sum over (lam, f) into partial 0 and zeros into the others.
+        lam, _, NG = f.dense
+        users = [d for d in f.rho if d != lam] + [f.kappa]
+        self.op_ReduceOp(PL.ReduceOp(PL.R_WSUM, op.gS, users, [lam] + fdim, r.factors, **kw))
+        buf, base = self.buf(op.gS)
+        n_u, Kk = math.prod(d[2] for d in users[:-1]), f.kappa[2]
+        full = buf[base:base + n_u * Kk].clone().reshape(n_u, 1, Kk)
+        out = t.cat([full, t.zeros(n_u, NG - 1, Kk, dtype=buf.dtype)], 1)
+        buf[base:base + n_u * NG * Kk] = out.reshape(-1)
 
     def op_NormalFanBwdOp(self, op):
         f = op.fan

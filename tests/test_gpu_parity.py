@@ -356,14 +356,16 @@ def _movielens_case(M_, N_, K, d, seed):
 def _run_paths(P, Q, sample, ip, data, names, monkeypatch):
     """(lp, grads) with fan_lse on the tensor cores and on the FFMA2 kernel (ALAN_B200_NO_TC at plan creation)."""
     Compiled, Runner = _engine()
-    comp = Compiled(P, Q, sample, ip, data, grad_names=names)
-    assert 'FanLseOp' in [type(op).__name__ for prog in comp.plan.programs for op in prog]
     out = {}
     for tc in (True, False):
         if tc:
             monkeypatch.delenv("ALAN_B200_NO_TC", raising=False)
         else:
             monkeypatch.setenv("ALAN_B200_NO_TC", "1")
+        # the plan is built under the same setting: with the tensor cores on, the planner commits the adjoint to the
+        # dense kernel's compact gS layout (plan.py dense_fan_geometry)
+        comp = Compiled(P, Q, sample, ip, data, grad_names=names)
+        assert 'FanLseOp' in [type(op).__name__ for prog in comp.plan.programs for op in prog]
         run = Runner(comp, "cuda:0")
         tensors = run.device_inputs(sample, ip, data)
         lp = run.forward_raw(tensors)
@@ -384,6 +386,38 @@ def test_tcgen05_fan_lse_matches_ffma_kernel(M_, N_, K, d, monkeypatch):
     assert rel_err(lp_tc.cpu(), lp_ff.cpu()) < 2e-6
     for k in names:
         assert rel_err(g_tc[k].cpu(), g_ff[k].cpu()) < 1e-4, k
+
+
+@pytest.mark.parametrize("M_,N_,K,d", [(64, 5, 30, 18), (40, 3, 32, 18), (50, 2, 12, 8)])
+def test_dense_and_block_diagonal_tcgen05_kernels_agree(M_, N_, K, d, monkeypatch):
+    """csrc/fan_tc2.cuh (dense expanded-square GEMM, compact gS) against csrc/fan_tc.cuh (block-diagonal operand,
+    ALAN_B200_TC_BLOCKDIAG=1 when the plan is built and run) on the same inputs; and a plan built for the dense
+    kernel refuses to run with that kernel disabled instead of writing through the wrong gS layout."""
+    Compiled, Runner = _engine()
+    P, Q, sample, ip, data, names = _movielens_case(M_, N_, K, d, seed=23)
+    res = {}
+    for blockdiag in (False, True):
+        if blockdiag:
+            monkeypatch.setenv("ALAN_B200_TC_BLOCKDIAG", "1")
+        else:
+            monkeypatch.delenv("ALAN_B200_TC_BLOCKDIAG", raising=False)
+        comp = Compiled(P, Q, sample, ip, data, grad_names=names)
+        fan = [op for prog in comp.plan.programs for op in prog if type(op).__name__ == 'FanLseOp'][0]
+        assert (fan.dense is None) == blockdiag
+        run = Runner(comp, "cuda:0")
+        tensors = run.device_inputs(sample, ip, data)
+        res[blockdiag] = (run.forward_raw(tensors).clone(), {k: v.clone() for k, v in run.backward_raw(tensors).items()})
+        if not blockdiag:
+            dense_comp = comp
+    assert rel_err(res[False][0].cpu(), res[True][0].cpu()) < 2e-6
+    for k in names:
+        assert rel_err(res[False][1][k].cpu(), res[True][1][k].cpu()) < 1e-4, k
+    run = Runner(dense_comp, "cuda:0")                       # ALAN_B200_TC_BLOCKDIAG still set: kernel disabled
+    tensors = run.device_inputs(sample, ip, data)
+    run.forward_raw(tensors)
+    with pytest.raises(Exception, match="compact gS"):
+        run.backward_raw(tensors)
+    monkeypatch.delenv("ALAN_B200_TC_BLOCKDIAG", raising=False)
 
 
 def test_full_size_cfg5_properties(monkeypatch):
