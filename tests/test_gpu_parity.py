@@ -376,10 +376,15 @@ def _run_paths(P, Q, sample, ip, data, names, monkeypatch):
 
 
 @pytest.mark.parametrize("M_,N_,K,d", [(20, 3, 8, 18), (33, 4, 17, 18), (64, 5, 30, 18), (40, 3, 32, 18),
-                                         (50, 2, 12, 8), (37, 2, 9, 2), (25, 3, 30, 16)])
+                                         (50, 2, 12, 8), (37, 2, 9, 2), (25, 3, 30, 16),
+                                         # every event extent of the dense kernel, ragged user blocks (M % 4 != 0),
+                                         # one / two / three fan groups
+                                         (17, 2, 12, 2), (19, 2, 16, 4), (301, 2, 20, 6), (16, 2, 30, 12), (130, 3, 24, 16)])
 def test_tcgen05_fan_lse_matches_ffma_kernel(M_, N_, K, d, monkeypatch):
     """csrc/fan_tc.cuh (3xTF32 tcgen05.mma, accumulator in TMEM) against csrc/fused.cuh fan_lse2 (fp32 FFMA2) on
-    identical inputs: ragged tiles (n_rho not a multiple of 16), K < 32 padding columns, K = 32, several D."""
+    identical inputs: ragged tiles (n_rho not a multiple of 16), K < 32 padding columns, K = 32, several D.  With
+    the tensor cores on, shapes with K_mu x K_psi >= 96 and >= 16 users run the dense kernel csrc/fan_tc2.cuh (the
+    planner commits them to its compact gS layout), the others the block-diagonal csrc/fan_tc.cuh."""
     P, Q, sample, ip, data, names = _movielens_case(M_, N_, K, d, seed=21)
     out = _run_paths(P, Q, sample, ip, data, names, monkeypatch)
     (lp_tc, g_tc, _, _), (lp_ff, g_ff, _, _) = out[True], out[False]
