@@ -388,7 +388,9 @@ def test_tcgen05_fan_lse_matches_ffma_kernel(M_, N_, K, d, monkeypatch):
     P, Q, sample, ip, data, names = _movielens_case(M_, N_, K, d, seed=21)
     out = _run_paths(P, Q, sample, ip, data, names, monkeypatch)
     (lp_tc, g_tc, _, _), (lp_ff, g_ff, _, _) = out[True], out[False]
-    assert rel_err(lp_tc.cpu(), lp_ff.cpu()) < 2e-6
+    # the log-evidence is a sum over users of terms of either sign: (19, 2, 16, 4) ends at -3.36 from terms of order
+    # 10, so the bound is north_star's 1e-5 (typical agreement: 1e-7)
+    assert rel_err(lp_tc.cpu(), lp_ff.cpu()) < 1e-5
     for k in names:
         assert rel_err(g_tc[k].cpu(), g_ff[k].cpu()) < 1e-4, k
 

@@ -41,11 +41,11 @@ def case(M_, N_, K, d, seed=21):
         ip = {**nt(inp['inputs']), **nt(inp['params'])}
         data = nt(inp['data'])
         names = list(inp['params'])
-        comp = Compiled(P, Q, sample, ip, data, grad_names=names)
         for path, env in (ENV.items() if dtype == t.float32 else [("f64", {})]):
             for k in ("ALAN_B200_TC_BLOCKDIAG", "ALAN_B200_NO_TC"):
                 os.environ.pop(k, None)
             os.environ.update(env)
+            comp = Compiled(P, Q, sample, ip, data, grad_names=names)     # the switches are read when the plan is built
             run = Runner(comp, "cuda:0")
             tensors = run.device_inputs(sample, ip, data)
             lp = run.forward_raw(tensors)
