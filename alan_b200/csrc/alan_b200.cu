@@ -382,6 +382,10 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                     p.b_k[i] = r.i64v();
                 }
                 p.cadd = (T)r.f64();
+                if (!bwd) {
+                    p.psum_rows = r.i32();
+                    if (p.psum_rows > 0) { p.psum = (T*)tref(r, c); p.ps_lam = r.i64v(); p.ps_f = r.i64v(); p.ps_row = r.i64v(); }
+                }
                 if (bwd) {
                     for (int k = 0; k < nrd; ++k) p.gstride[k] = r.i64v();
                     p.g_f = r.i64v();
@@ -391,13 +395,17 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 if constexpr (std::is_same<T, float>::value) {
                     if (plan->use_tc && plan->use_tc2 && tc::fan_lse_tc2_supported(p, D, bwd != 0))
                         rc = tc::launch_fan_lse_tc2(p, D, bwd != 0, c.stream, c.sm_count);
+                    else if (p.psum_rows > 0)
+                        return fail("fan_lse: the plan fuses the plate sum into the dense tensor-core kernel but that kernel is "
+                                    "disabled or does not cover this shape; rebuild the plan with ALAN_B200_NO_TC / "
+                                    "ALAN_B200_TC_BLOCKDIAG set the way the run is");
                     else if (p.gs_compact > 0)
                         return fail("fan_lse adjoint: the plan commits to the dense tensor-core kernel (compact gS layout) but that "
                                     "kernel is disabled or does not cover this shape; rebuild the plan with ALAN_B200_NO_TC / "
                                     "ALAN_B200_TC_BLOCKDIAG set the way the run is");
                     else if (plan->use_tc && tc::fan_lse_tc_supported(p, D)) rc = tc::launch_fan_lse_tc(p, D, bwd != 0, c.stream, c.sm_count);
                 }
-                if (rc < 0 && p.gs_compact > 0) return fail("fan_lse adjoint: compact gS layout needs the fp32 dense tensor-core kernel");
+                if (rc < 0 && (p.gs_compact > 0 || p.psum_rows > 0)) return fail("fan_lse: compact gS layout / fused plate sum need the fp32 dense tensor-core kernel");
                 if (rc < 0) rc = launch_fan_lse<T>(p, D, bwd != 0, c.stream, c.sm_count);
                 if (rc) return fail(rc == 1 ? "fan_lse: unsupported event extent" : rc == 2 ? "fan_lse: tile does not fit shared memory" : "fan_lse: strides exceed 32-bit tile addressing");
                 break;

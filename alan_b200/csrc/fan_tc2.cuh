@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
     unsigned char* tail = stage_base + T2_STAGES * 2 * OPER;
     float* s_cst = reinterpret_cast<float*>(tail);                         // [T2_TILES][128]  C[f'] (natural log units)
     int* s_ooff = reinterpret_cast<int*>(tail + T2_TILES * 128 * 4);       // [T2_TILES][128]  out offset of f' (-1: padding lane)
-    int* s_goff = s_ooff + T2_TILES * 128;                                 // [T2_TILES][128]  gout offset of f'
+    int* s_goff = s_ooff + T2_TILES * 128;                                 // [T2_TILES][128]  gout offset of f' (forward: psum offset)
     float* s_red = reinterpret_cast<float*>(s_goff + T2_TILES * 128);      // [2][team][quadrant][user of team][32]
     float* s_cd = s_red + 2 * 4 * T2_US * 32;                                  // [32] centre per event element
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_cd + 32);
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                 a[2 * D] = 1.f;
                 cst = -(c + float(D) * float(HALF_LOG_2PI));
                 ooff = lam * geo.o_lam + f * (int)p.o_f;
-                goff = lam * geo.g_lam + f * geo.g_f;
+                goff = BWD ? lam * geo.g_lam + f * geo.g_f : lam * (int)p.ps_lam + f * (int)p.ps_f;
             }
             s_cst[tl * 128 + row] = cst;
             s_ooff[tl * 128 + row] = ooff;
@@ -283,6 +283,9 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
         if (blk0 < n_blocks) fetch(blk0);
         unsigned tt = 0;                                                         // accumulator stage counter
         unsigned it = 0;
+        float ps[T2_TILES];                                                      // forward: running sum of out over this team's users
+#pragma unroll
+        for (int tl = 0; tl < T2_TILES; ++tl) ps[tl] = 0.f;
         const uint32_t ld_base = tmem + ((uint32_t)(32 * q) << 16) + D_COL + 32 * T2_UPT * team;
         for (unsigned blk = blk0; blk < n_blocks; blk += blk_step, ++it) {
             float lz[T2_TILES][T2_UPT], gz[T2_TILES][T2_UPT];
@@ -339,8 +342,11 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                             const float2 t2 = __fadd2_rn(__fadd2_rn(s2[0], s2[1]), __fadd2_rn(s2[2], s2[3]));
                             const float sum = t2.x + t2.y;
                             const int oo = s_ooff[tl * 128 + row];
-                            if (uoff[uu] >= 0 && oo >= 0)
-                                p.out[uoff[uu] + oo] = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + (cadd + s_cst[tl * 128 + row]);
+                            if (uoff[uu] >= 0 && oo >= 0) {
+                                const float val = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + (cadd + s_cst[tl * 128 + row]);
+                                p.out[uoff[uu] + oo] = val;
+                                ps[tl] += val;
+                            }
                         }
                     } else {
                         // 16 columns at a time: the adjoint also holds 32 accumulators per user and the prefetched lse / gout
@@ -395,6 +401,39 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                         t2_decode(u, geo, idx);
                         p.gS[((i64)t2_dot(idx, geo.ss) + (i64)grp * geo.s_lam) * Kk + lane] = sum;
                     }
+                }
+            }
+        }
+        if (!BWD && p.psum_rows > 0) {
+            // fused plate sum: the four teams' sums are combined in a fixed order through shared memory (the B stages
+            // are idle by now: every MMA that read them has been consumed above), row `CTA` of the partial buffer gets
+            // the sums for the fan columns of this CTA's group and zeros for the other groups' columns; the rows no
+            // CTA owns are zeroed round-robin.  The reduce that follows adds the rows in order.
+            float* scratch = reinterpret_cast<float*>(stage_base);               // [team][tile][128]
+#pragma unroll
+            for (int tl = 0; tl < T2_TILES; ++tl) scratch[(team * T2_TILES + tl) * 128 + row] = ps[tl];
+            asm volatile("bar.sync 5, %0;" :: "n"(128 * T2_EPI) : "memory");
+            if (team == 0) {
+                float* prow = p.psum + (i64)blockIdx.x * p.ps_row;
+#pragma unroll
+                for (int tl = 0; tl < T2_TILES; ++tl) {
+                    if (tl < n_tiles && s_ooff[tl * 128 + row] >= 0) {
+                        float v = scratch[tl * 128 + row];
+#pragma unroll
+                        for (int e = 1; e < T2_EPI; ++e) v += scratch[(e * T2_TILES + tl) * 128 + row];
+                        prow[s_goff[tl * 128 + row]] = v;
+                    }
+                }
+            }
+            // zeros: the other groups' columns of this CTA's row, and whole rows >= gridDim.x (round-robin over CTAs)
+            const int tid = team * 128 + row;
+            for (int r0 = (int)blockIdx.x; r0 < p.psum_rows; r0 += (int)gridDim.x) {
+                float* zrow = p.psum + (i64)r0 * p.ps_row;
+                const bool own = r0 == (int)blockIdx.x;
+                for (int fp = tid; fp < geo.FP; fp += 128 * T2_EPI) {
+                    if (own && fp >= fp_lo && fp < fp_lo + 128 * n_tiles) continue;
+                    const int lam = fp / p.F, f = fp - lam * p.F;
+                    zrow[lam * (int)p.ps_lam + f * (int)p.ps_f] = 0.f;
                 }
             }
         }
@@ -554,6 +593,7 @@ static bool fan_lse_tc2_supported(const FanLseParams<float>& p, int D, bool bwd)
     const i64 L = lam >= 0 ? p.rd.size[lam] : 1;
     const i64 FP = L * p.F, NG = (FP + T2_TILES * 128 - 1) / (T2_TILES * 128);
     const i64 n_u = p.n_rho / L;
+    if (!bwd && p.psum_rows > 0 && p.psum_rows < NG) return false;
     if (FP < 96 || NG > T2_MAXG || (bwd && NG > L) || (bwd && p.gs_compact > 0 && p.gs_compact != NG) || p.Kk > 32 || n_u < 16 || p.nb > TC_NB) return false;
     if (p.rd.nd - (lam >= 0 ? 1 : 0) > T2_ND) return false;
     const i64 lim = (i64)1 << 31;
@@ -615,7 +655,9 @@ static int launch_fan_lse_tc2_D(const FanLseParams<float>& p, bool bwd, cudaStre
     int blocks = 0;
     {
         // weight of a group = its tiles + a per-block cost measured at ~1.75 tiles (builder + block bookkeeping)
-        int left_cta = sm_count > geo.NG ? sm_count : geo.NG, left_tiles = tiles_total;
+        int max_cta = sm_count;
+        if (!bwd && p.psum_rows > 0 && max_cta > p.psum_rows) max_cta = p.psum_rows;
+        int left_cta = max_cta > geo.NG ? max_cta : geo.NG, left_tiles = tiles_total;
         int left_w = 4 * tiles_total + T2_BLOCK_COST4 * geo.NG;
         for (int g = 0; g < geo.NG; ++g) {
             int tg = tiles_total - T2_TILES * g; if (tg > T2_TILES) tg = T2_TILES;

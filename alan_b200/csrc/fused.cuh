@@ -343,6 +343,8 @@ struct FanLseParams {
     i64 gstride[AB_MAXD]; i64 g_f;        // bwd: strides of gout over the rho dims / fan axis (0 = broadcast)
     T* gS;                                // bwd: [rho, kappa] contiguous
     int gs_compact;                       // bwd, dense tcgen05 kernel only: > 0 = gS is [users, gs_compact fan groups, kappa]
+    T* psum; int psum_rows;               // fwd, dense tcgen05 kernel only: per-(CTA, team) sums of out over the users,
+    i64 ps_lam, ps_f, ps_row;             //      psum[row * ps_row + lam * ps_lam + f * ps_f]
     i64 n_rho;
 };
 

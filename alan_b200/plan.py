@@ -445,6 +445,7 @@ class FanLseOp(Op):
         self.fan_axis, self.F, self.bfactors, self.cadd = fan_axis, F, bfactors, cadd
         self.gen_expr, self.gen_reduce, self.tag = gen_expr, gen_reduce, tag
         self.dense = None            # (lam dim, L, NG) when the planner commits the adjoint to the dense kernel's gS layout
+        self.psum = None             # (partial PT, rows, od) when the dense kernel also sums its output over the users
 
     def _body(self, w):
         w.i32(self.D); w.i32(len(self.rho))
@@ -474,9 +475,18 @@ class FanLseOp(Op):
     def payload(self, w):
         w.i32(0); w.tref(self.out)
         self._body(w)
+        # fused plate sum (csrc/fan_tc2.cuh only): per-(CTA, team) partial sums over the users, [rows, od...]
+        if self.psum is None:
+            w.i32(0)
+        else:
+            part, rows, od = self.psum
+            ref = _PartialRef(part, od, rows)
+            w.i32(rows); w.tref(part)
+            w.i64(ref.stride(self.dense[0])); w.i64(ref.stride(('ax', self.fan_axis, self.F))); w.i64(ref.stride(('sp', 0, rows)))
 
 
 DENSE_TILES, DENSE_MAXG, DENSE_EVENTS = 3, 8, (2, 4, 6, 8, 12, 16, 18)
+FAN_PSUM_ROWS = 160          # partial rows of the fused plate sum: one per CTA of the dense kernel (148 on B200)
 
 
 def dense_fan_geometry(op: 'FanLseOp', itemsize=4):
@@ -1200,8 +1210,18 @@ class Planner:
         n_out = max(1, _prod(d[2] for d in od))
         nsplit = _choose_split(n_out, n)
         fused = self._try_bern_dot_sum(lf, out, od, rd, n) if (self.fast_paths and nsplit == 1) else None
+        fan = self._fan_for_plate_sum(lf, od, rd) if (self.fast_paths and nsplit > 1) else None
         if fused is not None:
             self.emit(fused)
+        elif fan is not None:
+            # the dense fan_lse kernel already holds every out[user, lam, f] in a register: it keeps per-(CTA, team)
+            # running sums over its users and writes them as one partial row per CTA; only those are summed here
+            part = self.ws_raw(FAN_PSUM_ROWS * n_out, name=f'partial[{plate}]')
+            fan.psum = (part, FAN_PSUM_ROWS, od)
+            second = ReduceOp(R_SUM, out, od, [('sp', 0, FAN_PSUM_ROWS)], [(_PartialRef(part, od, FAN_PSUM_ROWS), 1.0)],
+                              cadd=lf.const * n, tag=f'plate_sum:{plate}')
+            second.autodiff_as = ReduceOp(R_SUM, out, od, rd, lf.tensors, cadd=lf.const * n)
+            self.emit(second)
         elif nsplit > 1:
             part = self.ws_raw(nsplit * n_out, name=f'partial[{plate}]')
             first = ReduceOp(R_SUM, part, od, rd, lf.tensors, nsplit=nsplit, tag=f'plate_sum_partial:{plate}')
@@ -1220,6 +1240,26 @@ class Planner:
             self.fwd_segments.append(self.fwd)
             self.fwd = []
         return LogicalFactor([(plain(out), 1.0)], 0.0, out_axes)
+
+    def _fan_for_plate_sum(self, lf, od, rd):
+        """The FanLseOp whose output is the only term of this plate sum, when it runs on the dense tensor-core
+        kernel and the summed plate is exactly its user axis (so the sum can ride in that kernel's epilogue)."""
+        if len(lf.tensors) != 1:
+            return None
+        ref, coeff = lf.tensors[0]
+        if coeff != 1.0 or type(ref) is not LeafRef or ref.rename or ref.mode:
+            return None
+        op = self.producer.get(ref.pt.id)
+        if not isinstance(op, FanLseOp) or op.dense is None or op.psum is not None or op not in self.fwd:
+            return None
+        lam = op.dense[0]
+        users = [d for d in op.rho if d != lam]
+        fdim = ('ax', op.fan_axis, op.F)
+        if [(d[0], d[1]) for d in users] != [(d[0], d[1]) for d in rd]:
+            return None
+        if sorted((d[0], d[1]) for d in od) != sorted((d[0], d[1]) for d in (lam, fdim)):
+            return None
+        return op
 
     def _try_bern_dot_sum(self, lf, out, od, rd, n):
         """Fuse  dot -> Bernoulli(logits) -> plate sum  into csrc/fused.cuh bern_dot_sum_kernel when nobody

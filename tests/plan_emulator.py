@@ -161,6 +161,15 @@ class Emu:
     def op_FanLseOp(self, op):
         self.op_ExprOp(op.gen_expr)
         self.op_ReduceOp(op.gen_reduce)
+        if op.psum is not None:
+            # fused plate sum of the dense kernel: [rows, od...] partial rows; the emulator puts the whole sum over the
+            # users into row 0 and zeros into the others
+            part, rows, od = op.psum
+            users = [d for d in op.rho if d != op.dense[0]]
+            self.op_ReduceOp(PL.ReduceOp(PL.R_SUM, part, od, users, [(PL.plain(op.out), 1.0)]))
+            buf, base = self.buf(part)
+            n_out = math.prod(d[2] for d in od)
+            buf[base + n_out: base + rows * n_out] = 0
 
     def op_FanLseBwdOp(self, op):
         f = op.fwd

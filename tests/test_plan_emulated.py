@@ -162,20 +162,21 @@ def test_fused_paths_selected_and_match_oracle(dtype):
         assert rel_err(grad_as(comp_vi, grads_vi, k, axes), rr) < 30 * tl, k
 
 
-@pytest.mark.parametrize("K,NG", [(12, 1), (20, 2)])
-def test_dense_fan_layout_emulated_matches_oracle(K, NG):
+@pytest.mark.parametrize("K,NG,M_", [(12, 1, 16), (20, 2, 16), (12, 1, 260)])
+def test_dense_fan_layout_emulated_matches_oracle(K, NG, M_):
     """fp32 plans whose fused contraction fits csrc/fan_tc2.cuh commit the adjoint to the compact gS layout
-    [users, NG fan-group partials, kappa] (plan.py dense_fan_geometry); the emulated plan with that layout still
-    reproduces the oracle's log-evidence and RWS gradients."""
+    [users, NG fan-group partials, kappa] (plan.py dense_fan_geometry) and, for long plates, the plate sum to the
+    kernel's partial rows; the emulated plan with those layouts still reproduces the oracle's log-evidence and RWS
+    gradients."""
     from oracle import logpq_oracle as O
     from alan_b200.named import from_torch_named
     dtype = t.float32
     P, Q = models.movielens_model(M)
-    inp = models.movielens_inputs(M=16, N=3, d=18, seed=5, dtype=dtype)
+    inp = models.movielens_inputs(M=M_, N=3, d=18, seed=5, dtype=dtype)
     g = t.Generator().manual_seed(11)
     r = lambda *s: (0.7 * t.randn(s, generator=g, dtype=t.float64)).to(dtype)
     sample = {'mu_z': NT(r(K, 18), ('K_mu_z',)), 'psi_z': NT(r(K, 18) - 0.5, ('K_psi_z',)),
-              'z': NT(r(16, K, 18), ('plate_1', 'K_z'))}
+              'z': NT(r(M_, K, 18), ('plate_1', 'K_z'))}
     ip = {k: from_torch_named(v) for k, v in {**inp['inputs'], **inp['params']}.items()}
     data = {k: from_torch_named(v) for k, v in inp['data'].items()}
     names = list(inp['params'])
@@ -183,7 +184,9 @@ def test_dense_fan_layout_emulated_matches_oracle(K, NG):
     fan = [op for prog in comp.plan.programs for op in prog if type(op).__name__ == 'FanLseOp'][0]
     assert fan.dense is not None and fan.dense[2] == NG
     bwd = [op for prog in comp.plan.programs for op in prog if type(op).__name__ == 'FanLseBwdOp'][0]
-    assert bwd.gS.numel == 16 * NG * K
+    assert bwd.gS.numel == M_ * NG * K
+    # a plate long enough to be summed in two stages rides in the dense kernel's epilogue (fused plate sum)
+    assert (fan.psum is not None) == (M_ >= 256)
     lp, grads, _ = run_fwd_bwd(comp, comp.canonical_inputs(sample, ip, data))
     ipg = {k: NT(v.t.clone().requires_grad_() if k in names else v.t, v.axes) for k, v in ip.items()}
     ref = O.elbo(P, Q, sample, ipg, data)
