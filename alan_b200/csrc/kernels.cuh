@@ -85,7 +85,8 @@ __device__ __forceinline__ void expr_fwd_body(const ExprParams<T>& p, const Norm
             const T* pl = (const T*)p.leaf[n3.nl[1]].ptr + base[n3.nl[1]];
             const T* ps = (const T*)p.leaf[n3.nl[2]].ptr + base[n3.nl[2]];
             const i64 sv = p.leaf[n3.nl[0]].stride[kd], sl = p.leaf[n3.nl[1]].stride[kd], ss = p.leaf[n3.nl[2]].stride[kd];
-            for (i64 r = lane; r < p.n_red; r += nl) sum += normal_lp(pv[r * sv], pl[r * sl], ps[r * ss]);
+#pragma unroll 6
+            for (i64 r = lane; r < p.n_red; r += nl) sum += normal_lp(pv[r * sv], pl[r * sl], ps[r * ss]);   // several loads in flight
         } else
         for (i64 r = lane; r < p.n_red; r += nl) {
             unravel(r, p.d, p.d.n_a, p.d.nd, idx);
@@ -222,13 +223,23 @@ __device__ __forceinline__ void expr_bwd_body(const ExprBwdParams<T>& p, const N
                 const T* pg = (const T*)p.gout.ptr + gbase;
                 const i64 sv = p.leaf[n3.nl[0]].stride[kd], sl = p.leaf[n3.nl[1]].stride[kd], ss = p.leaf[n3.nl[2]].stride[kd],
                           sg = p.gout.stride[kd];
-                for (i64 j = s + (i64)lane * p.nsplit; j < p.n_loop; j += (i64)p.nsplit * nl) {
-                    const T sc = ps[j * ss], df = pv[j * sv] - pl[j * sl], iv = T(1) / (sc * sc);
+                // pointer increments instead of 64-bit index products, one reciprocal per point (none when the scale
+                // does not vary along the loop): the loop was issue-bound at ~65 instructions per point (ncu)
+                const i64 j0 = s + (i64)lane * p.nsplit, step = (i64)p.nsplit * nl;
+                const T* qv = pv + j0 * sv; const T* ql = pl + j0 * sl; const T* qs = ps + j0 * ss; const T* qg = pg + j0 * sg;
+                const i64 dv = step * sv, dl = step * sl, ds = step * ss, dg = step * sg;
+                T iv = T(0), isc = T(0);
+                if (ss == 0 && j0 < p.n_loop) { const T sc = *qs; iv = T(1) / (sc * sc); isc = iv * sc; }
+#pragma unroll 4
+                for (i64 j = j0; j < p.n_loop; j += step) {
+                    if (ss != 0) { const T sc = *qs; iv = T(1) / (sc * sc); isc = iv * sc; }
+                    const T df = *qv - *ql;
                     T g = T(0);
                     if (tv) g -= df * iv;
                     if (tl) g += df * iv;
-                    if (ts) g += (df * df * iv - T(1)) / sc;
-                    sum += g * pg[j * sg];
+                    if (ts) g += (df * df * iv - T(1)) * isc;
+                    sum += g * *qg;
+                    qv += dv; ql += dl; qs += ds; qg += dg;
                 }
             } else
             for (i64 j = s + (i64)lane * p.nsplit; j < p.n_loop; j += (i64)p.nsplit * nl) {
