@@ -377,7 +377,7 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
             roof["frac"] = roof["achieved"] / roof["peak"]
             # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this command
             # at cfg-5 on one GPU (profiles/r01_fan_lse_tc2_full.md: dram__bytes_read.sum + dram__bytes_write.sum)
-            ncu_traffic = {"FanLseBwdOp": 60.09e6 + 2.35e6, "FanLseOp": 24.07e6 + 0.64e6}
+            ncu_traffic = {"FanLseBwdOp": 60.08e6 + 1.30e6, "FanLseOp": 24.07e6 + 0.74e6}
             traffic = ncu_traffic.get(m["kind"]) if (tc_path and cfg["M"] // max(world, 1) == 10000 and cfg["N"] == 50) else None
             roof.update(traffic=traffic, kernel=f"{m['kind']}:{m['tag']}", kernel_ms=top_ms,
                         share_of_step=top_ms / total, peak_source=pk["source"],
