@@ -213,6 +213,8 @@ class Runner:
             ent[0].replay()
             return ent[1], ent[2]
         if self._step_off or self._step_seen.get(key, 0) < 1 or len(self._step_graphs) >= 4:
+            if len(self._step_seen) > 64:                    # a caller that never repeats a binding: keep this bounded
+                self._step_seen.clear()
             self._step_seen[key] = self._step_seen.get(key, 0) + 1
             lp = self.forward_raw(tensors)
             return lp, self.backward_raw(tensors)
