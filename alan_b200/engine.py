@@ -346,7 +346,35 @@ class StreamedRunner:
 
     def step(self, host):
         """host: full-size canonical pinned tensors (see `pin`).  Returns (lp, {name: grad}) on the device;
-        gradients of per-element parameters are full size."""
+        gradients of per-element parameters are full size.  The second call with the same host buffers captures
+        the whole step -- the H2D copies on the copy stream, every block's programs, the tile sum -- into one CUDA
+        graph and later calls replay it (no per-block host work); lp and the gradients are then static buffers."""
+        if not hasattr(self, "_graphs"):
+            self._graphs, self._seen, self._graph_off = {}, {}, False
+        key = tuple(int(h.data_ptr()) for h in host)
+        ent = self._graphs.get(key)
+        if ent is not None:
+            ent[0].replay()
+            return ent[1], ent[2]
+        if self._graph_off or self._seen.get(key, 0) < 1 or len(self._graphs) >= 2:
+            if len(self._seen) > 16:
+                self._seen.clear()
+            self._seen[key] = self._seen.get(key, 0) + 1
+            return self._step_eager(host)
+        try:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                lp, grads = self._step_eager(host)
+            g.replay()
+        except Exception:
+            self._graph_off = True
+            torch.cuda.synchronize(self.device)
+            return self._step_eager(host)
+        self._graphs[key] = (g, lp, grads)
+        return lp, grads
+
+    def _step_eager(self, host):
         plan = self.comp.plan
         cur = torch.cuda.current_stream(self.device)
         if self.dev is None:
