@@ -1,3 +1,7 @@
+#!/usr/bin/env python
+"""Worst relative error of every density family of the factor VM (log-evidence and gradients against the oracle) over
+28 seeds: shows how far tests/test_gpu_parity.py::test_density_families_vs_oracle sits from its tolerances.
+    python tools/family_seed_sweep.py"""
 import sys
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import torch as t

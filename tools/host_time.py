@@ -1,3 +1,7 @@
+#!/usr/bin/env python
+"""Host-side enqueue time of one step (forward_raw / backward_raw, eager) against the device time that follows:
+tells a host-bound step from a device-bound one.  Profiling aid, never a bench line.
+    python tools/host_time.py [cfg5|cfg2]"""
 import os, sys, time
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import torch as t
