@@ -194,3 +194,15 @@ def test_dense_fan_layout_emulated_matches_oracle(K, NG, M_):
     assert rel_err(lp, ref) < 1e-5
     for k, rr in zip(names, rg):
         assert rel_err(grad_as(comp, grads, k, ipg[k].axes), rr) < 3e-4, k
+
+
+def test_importance_sample_through_timeseries_raises_like_the_reference():
+    """`sample_Ks_timeseries` is unfinished upstream (README.md:41-44; IndexError at
+    reduce_Ks.py:223 on torch 2.11), so a resampling program through a Timeseries is refused when the plan is built,
+    with the reference's own explanation, instead of producing indices nobody can check."""
+    from golden_io import load
+    g = load("cfg4_timeseries", "f32")
+    P, Q = models.build("cfg4_timeseries", M, t.float32)
+    Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"])           # log-evidence plan: fine
+    with pytest.raises(Exception, match="Timeseries is unfinished in the reference"):
+        Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"], N=5)
