@@ -128,6 +128,7 @@ class _LogPQFunction(torch.autograd.Function):
     def forward(ctx, runner, *tensors):
         lp = runner.forward_raw(list(tensors))
         ctx.runner = runner
+        ctx.generation = runner.generation
         ctx.save_for_backward(*tensors)
         return lp
 
@@ -135,6 +136,12 @@ class _LogPQFunction(torch.autograd.Function):
     def backward(ctx, grad_lp):
         runner = ctx.runner
         tensors = list(ctx.saved_tensors)
+        if runner.generation != ctx.generation:
+            # another forward ran on this runner's workspace since ours (runners are shared by every Sample of a
+            # Problem with the same signature; `(l1 + l2).backward()` is legal): the adjoint program reads forward
+            # intermediates from the workspace, so recompute ours first -- what autograd's saved tensors give the
+            # reference for free
+            runner.forward_raw(tensors)
         grads = runner.backward_raw(tensors, grad_lp)
         out = [None] * len(tensors)
         for name, g in grads.items():
@@ -152,10 +159,12 @@ class Runner:
         self.dtype = comp.dtype
         self.pg = process_group
         self.lp = torch.zeros((), dtype=self.dtype, device=self.device)
+        self.generation = 0          # bumped by every forward: identifies whose intermediates the workspace holds
 
     # ---- raw calls on canonical device tensors ------------------------------------------
     def forward_raw(self, tensors):
         plan = self.comp.plan
+        self.generation += 1
         lp = torch.empty((), dtype=self.dtype, device=self.device)
         for seg in range(plan.n_fwd):
             self.dp.fwd(seg, tensors, lp)
@@ -210,6 +219,7 @@ class Runner:
         key = tuple(int(x.data_ptr()) for x in tensors)
         ent = self._step_graphs.get(key)
         if ent is not None:
+            self.generation += 1
             ent[0].replay()
             return ent[1], ent[2]
         if self._step_off or self._step_seen.get(key, 0) < 1 or len(self._step_graphs) >= 4:
@@ -283,6 +293,179 @@ class Runner:
     def elbo(self, tensors):
         """Differentiable log-evidence estimate on canonical device tensors."""
         return _LogPQFunction.apply(self, *tensors)
+
+
+class SplitRunner:
+    """`computation_strategy=Split(plate, n)` on one GPU (reference Split.py:44-130, logpq.py:43-57,151-153).
+
+    The plate is processed in blocks of `n` elements (sizes by the reference's rule, strategy.Split.sizes) through
+    ONE block-sized workspace per distinct block size: pass 1 runs the sharded part of the forward program for every
+    block and adds the `[K_parents]` tiles left to right; the replicated top level then gives the log-evidence.
+    The adjoint pass recomputes a block's forward before its backward (the reference wraps every chunk in
+    torch.utils.checkpoint, logpq.py:62-66), so the device memory in use is that of one block.  Per-element
+    gradients are written into slices of full-size outputs, global-parameter gradients are summed over the blocks.
+    Same `forward_raw / backward_raw / comp` surface as `Runner`, so the autograd wrapper works with either."""
+    def __init__(self, P, Q, sample, inputs_params, data, plate, split, extra_log_factors=None, moment_specs=(),
+                 grad_names=(), device=None):
+        self.plate = plate
+        full = {}
+        for d in (sample, inputs_params or {}, data or {}, extra_log_factors or {}):
+            full.update({k: v for k, v in d.items()})
+        M = None
+        for v in full.values():
+            if plate in v.axes:
+                M = v.named_sizes[plate]
+        if M is None:
+            raise Exception(f"Split: no tensor carries the plate {plate}")
+        self.M = M
+        self.block_sizes = split.sizes(M)
+        self.blocks, lo = [], 0
+        for m in self.block_sizes:
+            self.blocks.append((lo, lo + m))
+            lo += m
+
+        def head(d, m):
+            out = {}
+            for k, v in (d or {}).items():
+                if plate in v.axes:
+                    out[k] = NT(v.t.narrow(v.axes.index(plate), 0, m), v.axes)
+                else:
+                    out[k] = v
+            return out
+        self.runs = {}
+        for m in dict.fromkeys(self.block_sizes):
+            comp = Compiled(P, Q, head(sample, m), head(inputs_params, m), head(data, m),
+                            extra_log_factors=head(extra_log_factors, m), moment_specs=moment_specs,
+                            grad_names=list(grad_names), shard_plate=plate, world_size=len(self.block_sizes))
+            if comp.plan.n_fwd != 2:
+                raise Exception(f"Split: {plate} is not a top-level plate of this model (only those can be split here)")
+            self.runs[m] = Runner(comp, device)
+        self.comp = next(iter(self.runs.values())).comp          # names / order / dtype are those of any block plan
+        self.device = next(iter(self.runs.values())).device
+        self.dtype = self.comp.dtype
+        self.generation = 0
+        plan = self.comp.plan
+        self.carries = []
+        for name in plan.input_names:
+            pt = plan.input_pts[name]
+            if plate in pt.axes and pt.axes[0] != plate:
+                raise Exception(f"Split: {name} carries {plate} but not as its outermost axis")
+            self.carries.append(plate in pt.axes)
+        self.one = torch.ones((), dtype=self.dtype, device=self.device)
+
+    def device_inputs(self, sample, inputs_params, data, extra_log_factors=None, differentiable=False):
+        """FULL-SIZE canonical device tensors in plan input order (cf. Runner.device_inputs)."""
+        comp, M = self.comp, self.M
+        src = {}
+        for d in (sample, inputs_params or {}, data or {}):
+            src.update(d)
+        elf = dict(extra_log_factors or {})
+        out = []
+        run0 = next(iter(self.runs.values()))
+        for name in comp.plan.input_names:
+            if name in comp.plan.const_inputs:
+                t = run0.dp.consts[name]
+            elif name.startswith('__J'):
+                _, plates, pos = next(m for m in comp.moment_inputs if m[0] == name)
+                t = torch.zeros([(M if a == self.plate else comp.sizes[a]) for a in plates] + list(pos),
+                                dtype=self.dtype, device=self.device)
+                if differentiable:
+                    t.requires_grad_(True)
+            else:
+                key, role, orig, axes = next(o for o in comp.order if o[0] == name)
+                v = elf[orig] if role == 'elf' else src[orig]
+                t = v.order(axes).t.to(self.device).to(self.dtype).contiguous()
+                if not differentiable or name not in comp.grad_names:
+                    t = t.detach()
+            out.append(t)
+        return out
+
+    def elbo(self, tensors):
+        """Differentiable log-evidence estimate on FULL-SIZE canonical device tensors."""
+        return _LogPQFunction.apply(self, *tensors)
+
+    def _block(self, tensors, b):
+        lo, hi = self.blocks[b]
+        return [x[lo:hi] if c else x for x, c in zip(tensors, self.carries)], self.runs[hi - lo]
+
+    def forward_raw(self, tensors):
+        self.generation += 1
+        plan = self.comp.plan
+        lp = torch.empty((), dtype=self.dtype, device=self.device)
+        total = None
+        for b in range(len(self.blocks)):
+            tens, run = self._block(tensors, b)
+            run.dp.fwd(0, tens, lp)
+            tile = run.dp.ws_view(run.comp.plan.allreduce, self.dtype)
+            total = tile.clone() if total is None else total + tile            # prev_lpq + lp, left to right
+        self.tile = total
+        tens, run = self._block(tensors, len(self.blocks) - 1)
+        run.dp.ws_view(run.comp.plan.allreduce, self.dtype).copy_(total)
+        run.dp.fwd(1, tens, lp)
+        return lp
+
+    def backward_raw(self, tensors, grad_lp=None):
+        plan = self.comp.plan
+        if grad_lp is None:
+            grad_lp = self.one
+        grad_lp = grad_lp.to(self.dtype).contiguous()
+        lp = torch.empty((), dtype=self.dtype, device=self.device)
+        full = {}
+        for n in plan.grad_inputs:
+            pt = plan.input_pts[n]
+            shape = ([self.M] + list(pt.shape[1:])) if self.plate in pt.axes else list(pt.shape)
+            full[n] = torch.zeros(shape, dtype=self.dtype, device=self.device)
+        for b in range(len(self.blocks)):
+            lo, hi = self.blocks[b]
+            tens, run = self._block(tensors, b)
+            bplan = run.comp.plan
+            run.dp.fwd(0, tens, lp)                                            # recompute this block's forward
+            run.dp.ws_view(bplan.allreduce, self.dtype).copy_(self.tile)
+            run.dp.fwd(1, tens, lp)
+            outs, tmp = [], {}
+            for n in bplan.grad_inputs:
+                if n in bplan.global_grads:
+                    tmp[n] = torch.empty(bplan.input_pts[n].shape, dtype=self.dtype, device=self.device)
+                    outs.append(tmp[n])
+                else:
+                    outs.append(full[n][lo:hi])
+            for seg in range(bplan.n_bwd):
+                run.dp.bwd(seg, tens, grad_lp, outs)
+            for n, g in tmp.items():
+                full[n] += g
+        return full
+
+
+class WeightedMoments:
+    """`Marginals.moments` on the device (reference Marginals.py:31-46, moments.py:16-35):
+    out[plates..., *f.shape] = sum_K f(x) * w, as one factor-VM launch and one fixed-order reduction."""
+    def __init__(self, x_nts: dict, w_nt: NT, f, canon, dtype, device=None):
+        from . import runtime
+        from .plan import weighted_moment_plan
+        sizes = {}
+        for v in list(x_nts.values()) + [w_nt]:
+            sizes.update(v.named_sizes)
+        order = lambda axes: tuple(a for a in canon if a in axes)
+        self.x_axes = {k: order(v.axes) for k, v in x_nts.items()}
+        self.w_axes = order(w_nt.axes)
+        sigs = {k: TensorSig('sample', self.x_axes[k], v.pos_shape) for k, v in x_nts.items()}
+        self.plan = weighted_moment_plan(sigs, self.w_axes, f, sizes, dtype, canon)
+        self.dp = runtime.DevicePlan(self.plan, device)
+        self.dtype, self.device = dtype, self.dp.device
+        self.keepalive = f
+
+    def __call__(self, x_nts: dict, w_nt: NT) -> NT:
+        ins = []
+        for name in self.plan.input_names:
+            if name in self.plan.const_inputs:
+                ins.append(self.dp.consts[name])
+            elif name == '__w':
+                ins.append(w_nt.order(self.w_axes).t.detach().to(self.device).to(self.dtype).contiguous())
+            else:
+                ins.append(x_nts[name].order(self.x_axes[name]).t.detach().to(self.device).to(self.dtype).contiguous())
+        out = torch.empty(self.plan.out_shape, dtype=self.dtype, device=self.device)
+        self.dp.run(0, ins, [out])
+        return NT(out, self.plan.out_axes)
 
 
 class StreamedRunner:

@@ -776,6 +776,30 @@ class Planner:
             if s.role in ('sample', 'param'):
                 self.scope[name] = Expr.leaf(self.inputs[name], s.axes, s.pos_shape)
 
+    @classmethod
+    def bare(cls, sig: dict, sizes: dict, dtype, canon):
+        """A planner without a model tree: only inputs, workspace tensors and `emit_expr` / `emit` -- used for the
+        stand-alone weighted sums of `Marginals.moments` (weighted_moment_plan below)."""
+        self = cls.__new__(cls)
+        self.P = self.Q = None
+        self.sig, self.sizes, self.dtype = sig, dict(sizes), dtype
+        self.itemsize = 4 if dtype == torch.float32 else 8
+        self.extra_factors, self.N, self.fast_paths = [], None, False
+        self.shard_plate, self.world_size = None, 1
+        self.plan = Plan()
+        self.plan.dtype, self.plan.sizes = dtype, self.sizes
+        self.all_plates = [a for a in canon if not a.startswith('K_')]
+        self.groups, self.v2g, self.g2plates = [], {}, {}
+        self.canon = list(canon)
+        self.plan.canon_axes = self.canon
+        self.alloc_group = 0
+        self.grad_names, self.needs = [], set()
+        self.fan_by_out, self.producer, self.fwd, self.fwd_segments = {}, {}, [], []
+        self.consts, self.inputs = {}, {}
+        for name, s in sig.items():
+            self._add_input(name, s.axes, s.pos_shape)
+        return self
+
     def set_grad_names(self, names):
         self.grad_names = list(names)
         self.needs = set(self.inputs[n].id for n in self.grad_names)
@@ -1687,6 +1711,41 @@ class Planner:
                 raise Exception(f"importance_sample through a Timeseries is unfinished in the reference "
                                 f"(README.md:41-44) and not provided here (group {g})")
         return ops
+
+
+def weighted_moment_plan(x_sigs: dict, w_axes, f, sizes, dtype, canon) -> Plan:
+    """Plan of `Marginals.moments` (reference Marginals.py:31-46 -> RawMoment.from_marginals, moments.py:16-35):
+
+        out[plates..., *f.shape] = sum_{K axes of w}  f(x_1, ..., x_n) * w
+
+    x_sigs: {varname: TensorSig} of the sample tensors the moment function takes (in argument order);
+    w_axes: named axes of the marginal weights (K axes + plates).  One ExprOp (the traced f times w, nothing
+    summed) into the workspace and one fixed-order ReduceOp over the K axes into output 0."""
+    sig = dict(x_sigs)
+    sig['__w'] = TensorSig('elf', tuple(w_axes), ())
+    pl = Planner.bare(sig, sizes, dtype, canon)
+    xs = [Expr.leaf(pl.inputs[v], s.axes, s.pos_shape) for v, s in x_sigs.items()]
+    fx = trace_function(f, xs)
+    kw = [a for a in w_axes if a.startswith('K_')]
+    for a in fx.axes:
+        if a.startswith('K_') and a not in kw:
+            raise Exception(f"moment function depends on {a}, which the marginal weights do not carry")
+    body = pl._prepare(Expr.make('mul', fx, Expr.leaf(pl.inputs['__w'], tuple(w_axes), ())))
+    prod = pl.emit_expr(body, nred=0, tag='f*w')
+    R = len(body.pos_shape)
+    plates = [a for a in prod.axes if not a.startswith('K_')]
+    ev = [('ev', R - 1 - i, int(body.pos_shape[i])) for i in range(R)]
+    od = [pl.axdim(a) for a in plates] + ev
+    rd = [pl.axdim(a) for a in prod.axes if a.startswith('K_')]
+    out = PT(tuple(plates), body.pos_shape, pl.sizes, 'output', index=0, name='moment')
+    pl.emit(ReduceOp(R_SUM, out, od, rd, [(plain(prod), 1.0)], tag='sum_K f*w'))
+    plan = pl.plan
+    plan.programs = [pl.fwd]
+    plan.n_fwd, plan.n_bwd = 1, 0
+    plan.out_axes, plan.out_shape = tuple(plates), tuple(out.shape)
+    plan.assign_offsets(pl.itemsize)
+    plan.serialize()
+    return plan
 
 
 class _PartialRef(LeafRef):

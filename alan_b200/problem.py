@@ -1,10 +1,12 @@
 """Host-side mirror of the reference's call surface for the logPQ path.
 
     prob = Problem(P, Q, data, inputs=..., params=...)          # reference: src/alan/Problem.py:18-69
-    s = prob.sample_from(samples)                               # samples of Q, K per latent group
+    s = prob.sample(K) / prob.sample_from(samples)              # Problem.py:71-97 (sampling: alan_b200/sampling.py)
     s.elbo_vi() / s.elbo_rws() / s.elbo_nograd()                # Sample.py:110-148
-    s.marginals(joints=...) / s.moments([...]) / s.ess()        # Sample.py:274-346, Marginals.py:31-61
+    s.marginals(joints=...) / s.moments([...])                  # Sample.py:274-346
+    marginals.moments([...]) / .ess() / .min_ess()              # Marginals.py:31-61, moments.py:16-35
     s.importance_sample(N)                                      # Sample.py:185-206
+every one of them taking `computation_strategy=` (no_checkpoint | checkpoint | Split(plate, n)) like the reference.
 
 Same names, argument meaning and error behaviour (Python `Exception` with prose) as the reference for
 this path.  What is NOT here is the step before it: ancestral sampling of Q with permutation
@@ -19,9 +21,10 @@ from typing import Optional, Sequence
 
 import torch
 
-from .engine import Compiled, Runner
+from .engine import Compiled, Runner, SplitRunner, WeightedMoments
 from .model import Plate, Kname, check_PQ
 from .named import NT, from_torch_named
+from .strategy import no_checkpoint, checkpoint, Split, resolve as _resolve_strategy
 from . import runtime
 
 
@@ -64,12 +67,46 @@ class Marginals:
         self.sample, self.weights = sample, weights
 
     def ess(self) -> dict:
-        """1 / sum_K w^2 per latent group (Marginals.py:52-61)."""
+        """1 / sum_K w^2 per latent group (Marginals.py:48-56)."""
         out = {}
         for key, w in self.weights.items():
             if len(key) == 1:
                 kdims = tuple(i for i, a in enumerate(w.axes) if a.startswith("K_"))
                 out[key[0]] = NT(1.0 / (w.t * w.t).sum(kdims), tuple(a for a in w.axes if not a.startswith("K_")))
+        return out
+
+    def min_ess(self) -> float:
+        """Smallest effective sample size over every marginal and plate cell (Marginals.py:58-61)."""
+        ess = {}
+        for key, w in self.weights.items():
+            kdims = tuple(i for i, a in enumerate(w.axes) if a.startswith("K_"))
+            ess[key] = 1.0 / (w.t * w.t).sum(kdims)
+        return min(float(e.min()) for e in ess.values())
+
+    def moments(self, specs):
+        """specs: [(varname or tuple of varnames, f)] -> list of NT `sum_K f(x) w` with axes = plates
+        (Marginals._moments_uniform_input, Marginals.py:31-46 -> RawMoment.from_marginals, moments.py:16-35).
+        Every variable of one spec must belong to groups whose (joint) marginal was computed."""
+        s, p = self.sample, self.sample.problem
+        v2g = p.Q.varname2groupvarname()
+        groups = p.Q.groupvarnames()
+        canon = list(p.P.all_platenames()) + [Kname(g) for g in groups]
+        out = []
+        for v, f in specs:
+            vs = (v,) if isinstance(v, str) else tuple(v)
+            for x in vs:
+                if x not in s.sample:
+                    raise Exception(f"{x} is not a latent variable of Q")
+            key = tuple(sorted(dict.fromkeys(v2g[x] for x in vs), key=groups.index))
+            if key not in self.weights:
+                raise Exception(f"the joint marginal over {key} was not computed; pass joints=[{key}] to marginals()")
+            w = self.weights[key]
+            xs = {x: s.sample[x] for x in vs}
+            ck = ('wm', vs, id(f), tuple((k, x.axes, tuple(x.t.shape)) for k, x in xs.items()), w.axes, tuple(w.t.shape))
+            cache = p._runners
+            if ck not in cache:                       # the entry keeps `f` alive, so its id cannot be recycled
+                cache[ck] = WeightedMoments(xs, w, f, canon, s._dtype(), p.device)
+            out.append(cache[ck](xs, w))
         return out
 
 
@@ -93,25 +130,37 @@ class Sample:
         self._cache = {}
 
     # ------------------------------------------------------------------ engine plumbing
-    def _runner(self, grad_names=(), elf=None, moment_specs=(), N=None) -> Runner:
+    def _runner(self, grad_names=(), elf=None, moment_specs=(), N=None, strategy=None):
         p = self.problem
+        split = _resolve_strategy(strategy)
         sig = tuple(sorted((k, v.axes, tuple(v.t.shape), str(v.t.dtype)) for d in (self.sample, p.inputs_params(), p.data)
                            for k, v in d.items()))
+        # moment functions are identified by id(): the cached runner keeps them alive (an inline lambda would
+        # otherwise be freed and its address reused by the NEXT lambda, silently hitting the wrong plan)
         key = (sig, tuple(grad_names), tuple(sorted((elf or {}).keys(), key=str)),
-               tuple((vs, id(f)) for vs, f in moment_specs), N)
+               tuple((vs, id(f)) for vs, f in moment_specs), N,
+               None if split is None else (split.platename, split.split_size))
         self._cache = p._runners
         if key not in self._cache:
             world = 1
             if p.shard_plate is not None and torch.distributed.is_available() and torch.distributed.is_initialized():
                 world = torch.distributed.get_world_size(p.pg)
-            comp = Compiled(p.P, p.Q, self.sample, p.inputs_params(), p.data, extra_log_factors=elf,
-                            moment_specs=moment_specs, grad_names=list(grad_names), N=N,
-                            shard_plate=p.shard_plate if world > 1 else None, world_size=world)
-            self._cache[key] = Runner(comp, p.device, p.pg)
+            if split is not None and N is None:
+                run = SplitRunner(p.P, p.Q, self.sample, p.inputs_params(), p.data, split.platename, split,
+                                  extra_log_factors=elf, moment_specs=moment_specs, grad_names=list(grad_names),
+                                  device=p.device)
+            else:
+                # resampling keeps every factor of the tree in one workspace: Split is accepted and runs unsplit
+                comp = Compiled(p.P, p.Q, self.sample, p.inputs_params(), p.data, extra_log_factors=elf,
+                                moment_specs=moment_specs, grad_names=list(grad_names), N=N,
+                                shard_plate=p.shard_plate if world > 1 else None, world_size=world)
+                run = Runner(comp, p.device, p.pg)
+            run._keepalive = [f for _, f in moment_specs]
+            self._cache[key] = run
         return self._cache[key]
 
-    def _elbo(self, grad_names):
-        run = self._runner(grad_names)
+    def _elbo(self, grad_names, strategy=None):
+        run = self._runner(grad_names, strategy=strategy)
         p = self.problem
         tens = run.device_inputs(self.sample, p.inputs_params(), p.data, differentiable=bool(grad_names))
         if not grad_names:
@@ -125,20 +174,21 @@ class Sample:
         return names
 
     # ------------------------------------------------------------------ reference surface
-    def elbo_vi(self):
+    def elbo_vi(self, computation_strategy=checkpoint):
         """Reparameterised ELBO: gradients flow to parameters and to the samples (Sample.py:110-122)."""
         if not self.reparam:
             raise Exception("To compute the ELBO with the right gradients for VI you must construct a "
-                            "reparameterised sample using `problem.sample_from(samples, reparam=True)`")
-        return self._elbo(self._diff_names(True))
+                            "reparameterised sample using `problem.sample(K, reparam=True)`")
+        return self._elbo(self._diff_names(True), computation_strategy)
 
-    def elbo_rws(self):
+    def elbo_rws(self, computation_strategy=checkpoint):
         """Samples detached; gradients flow to the parameters only (Sample.py:124-134)."""
-        return self._elbo(self._diff_names(False))
+        return self._elbo(self._diff_names(False), computation_strategy)
 
-    def elbo_nograd(self):
+    def elbo_nograd(self, computation_strategy=checkpoint):
+        """No gradients at all (Sample.py:136-148); Split still bounds the workspace."""
         with torch.no_grad():
-            return self._elbo(())
+            return self._elbo((), computation_strategy)
 
     def _J_axes(self, key):
         g2p = self.problem.Q.groupvarname2platenames()
@@ -149,7 +199,7 @@ class Sample:
                 raise Exception(f"joint marginal {key}: groups must live in the same plates")
         return tuple(Kname(g) for g in gs) + tuple(plates)
 
-    def marginals(self, joints: Sequence = ()) -> Marginals:
+    def marginals(self, joints: Sequence = (), computation_strategy=checkpoint) -> Marginals:
         """Posterior marginals over K for every latent group (+ the requested joints): the gradient of the
         log-evidence w.r.t. zero source terms J (Sample.py:208-289)."""
         v2g = self.problem.Q.varname2groupvarname()
@@ -166,7 +216,7 @@ class Sample:
         for key in keys:
             axes = self._J_axes(key)
             elf[key] = NT(torch.zeros([sizes[a] for a in axes], dtype=dtype), axes)
-        run = self._runner(grad_names=list(elf.keys()), elf=elf)
+        run = self._runner(grad_names=list(elf.keys()), elf=elf, strategy=computation_strategy)
         p = self.problem
         tens = run.device_inputs(self.sample, p.inputs_params(), p.data, elf)
         run.forward_raw(tens)
@@ -177,7 +227,7 @@ class Sample:
             out[key] = NT(grads[name], run.comp.plan.input_pts[name].axes)
         return Marginals(self, out)
 
-    def moments(self, specs):
+    def moments(self, specs, computation_strategy=no_checkpoint):
         """specs: [(varname or tuple of varnames, f)] -> list of NT `E_post[f(x)]` with axes = plates of the
         variables (Sample.py:291-346; gradient w.r.t. the zero source term of the factor sum f(x) * J)."""
         moms = [((v,) if isinstance(v, str) else tuple(v), f) for v, f in specs]
@@ -185,21 +235,21 @@ class Sample:
             for v in vs:
                 if v not in self.sample:
                     raise Exception(f"{v} is not a latent variable of Q")
-        run = self._runner(moment_specs=moms)
+        run = self._runner(moment_specs=moms, strategy=computation_strategy)
         p = self.problem
         tens = run.device_inputs(self.sample, p.inputs_params(), p.data)
         run.forward_raw(tens)
         grads = run.backward_raw(tens)
         return [NT(grads[j], plates) for j, plates, _ in run.comp.moment_inputs]
 
-    def importance_sample(self, N: int, uniforms=None, seed: Optional[int] = None) -> dict:
+    def importance_sample(self, N: int, uniforms=None, seed: Optional[int] = None, computation_strategy=checkpoint) -> dict:
         """N joint posterior samples: K indices drawn top-down over the plate tree, then gathered
         (Sample.py:150-206).  `uniforms` (one float64 tensor `[plates..., N]` per sampling step, in
         `plan.sample_steps` order) makes the draw reproducible and bit-comparable; by default they
         are drawn on the device from `seed`."""
         if N < 1:
             raise Exception("importance_sample needs N >= 1")
-        run = self._runner(N=N)
+        run = self._runner(N=N, strategy=computation_strategy)
         p = self.problem
         plan = run.comp.plan
         tens = run.device_inputs(self.sample, p.inputs_params(), p.data)

@@ -100,8 +100,9 @@ def _ptr_array(tensors):
     return arr
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """The caller's current stream ON `device` (not on whatever device happens to be current)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class DevicePlan:
@@ -129,26 +130,39 @@ class DevicePlan:
         except Exception:
             pass
 
+    # every call enters the plan's device: kernels, graph captures and the stream all belong to it even when the
+    # caller's current device is another GPU
     def fwd(self, segment, inputs, lp_out):
-        check(lib().alan_b200_logpq_fwd(self.handle, segment, _ptr_array(inputs),
-                                        ctypes.c_void_p(lp_out.data_ptr()), ctypes.c_void_p(self.ws.data_ptr()),
-                                        _stream()))
+        with torch.cuda.device(self.device):
+            check(lib().alan_b200_logpq_fwd(self.handle, segment, _ptr_array(inputs),
+                                            ctypes.c_void_p(lp_out.data_ptr()), ctypes.c_void_p(self.ws.data_ptr()),
+                                            _stream(self.device)))
 
     def bwd(self, segment, inputs, grad_lp, grads_out):
-        check(lib().alan_b200_logpq_bwd(self.handle, segment, _ptr_array(inputs),
-                                        ctypes.c_void_p(grad_lp.data_ptr()), _ptr_array(grads_out),
-                                        ctypes.c_void_p(self.ws.data_ptr()), _stream()))
+        with torch.cuda.device(self.device):
+            check(lib().alan_b200_logpq_bwd(self.handle, segment, _ptr_array(inputs),
+                                            ctypes.c_void_p(grad_lp.data_ptr()), _ptr_array(grads_out),
+                                            ctypes.c_void_p(self.ws.data_ptr()), _stream(self.device)))
 
     def resample(self, inputs, uniforms, idx_out):
-        check(lib().alan_b200_resample(self.handle, _ptr_array(inputs), _ptr_array(uniforms),
-                                       _ptr_array(idx_out), ctypes.c_void_p(self.ws.data_ptr()), _stream()))
+        with torch.cuda.device(self.device):
+            check(lib().alan_b200_resample(self.handle, _ptr_array(inputs), _ptr_array(uniforms),
+                                           _ptr_array(idx_out), ctypes.c_void_p(self.ws.data_ptr()),
+                                           _stream(self.device)))
+
+    def run(self, program, inputs, outputs):
+        """Generic program run (alan_b200_run): used by the stand-alone plans (Marginals.moments, Q sampling)."""
+        with torch.cuda.device(self.device):
+            check(lib().alan_b200_run(self.handle, program, _ptr_array(inputs), _ptr_array(outputs),
+                                      ctypes.c_void_p(self.ws.data_ptr()), _stream(self.device)))
 
     def profile(self, program, inputs, outputs, aux):
         """per-op device milliseconds of one program run (CUDA events around every op)."""
         n = len(self.plan.programs[program])
         ms = (ctypes.c_float * max(n, 1))()
-        got = lib().alan_b200_profile(self.handle, program, _ptr_array(inputs), _ptr_array(outputs),
-                                      _ptr_array(aux), ctypes.c_void_p(self.ws.data_ptr()), _stream(), ms, n)
+        with torch.cuda.device(self.device):
+            got = lib().alan_b200_profile(self.handle, program, _ptr_array(inputs), _ptr_array(outputs),
+                                          _ptr_array(aux), ctypes.c_void_p(self.ws.data_ptr()), _stream(self.device), ms, n)
         if got < 0:
             raise Exception("alan_b200: " + lib().alan_b200_last_error().decode())
         return [ms[i] for i in range(got)]
@@ -177,7 +191,8 @@ def lse_eps(x: torch.Tensor) -> torch.Tensor:
         raise Exception("lse_eps: empty input")
     n_red = x.shape[-1]
     out = torch.empty(x.shape[:-1], dtype=x.dtype, device=x.device)
-    check(lib().alan_b200_lse_eps(x.data_ptr(), out.data_ptr(), out.numel(), n_red, _dt(x), _stream()))
+    with torch.cuda.device(x.device):
+        check(lib().alan_b200_lse_eps(x.data_ptr(), out.data_ptr(), out.numel(), n_red, _dt(x), _stream(x.device)))
     return out
 
 
@@ -190,7 +205,9 @@ def logmmexp_chain(ms: torch.Tensor) -> torch.Tensor:
     L = lib()
     levels = torch.empty(L.alan_b200_chain_scratch_elems(outer, T, K), dtype=ms.dtype, device=ms.device)
     out = torch.empty(outer, K, dtype=ms.dtype, device=ms.device)
-    check(L.alan_b200_logmmexp_chain(ms.data_ptr(), levels.data_ptr(), out.data_ptr(), outer, T, K, _dt(ms), _stream()))
+    with torch.cuda.device(ms.device):
+        check(L.alan_b200_logmmexp_chain(ms.data_ptr(), levels.data_ptr(), out.data_ptr(), outer, T, K, _dt(ms),
+                                         _stream(ms.device)))
     return out
 
 
@@ -199,8 +216,10 @@ def normal_logpdf_bcast(value, loc, scale, n_cells, n_event, vs, ls, ss) -> torc
     require_cuda()
     out = torch.empty(n_cells, dtype=value.dtype, device=value.device)
     mk = lambda s: (ctypes.c_int64 * 2)(*s)
-    check(lib().alan_b200_normal_logpdf_bcast(value.data_ptr(), loc.data_ptr(), scale.data_ptr(), out.data_ptr(),
-                                              n_cells, n_event, mk(vs), mk(ls), mk(ss), _dt(value), _stream()))
+    with torch.cuda.device(value.device):
+        check(lib().alan_b200_normal_logpdf_bcast(value.data_ptr(), loc.data_ptr(), scale.data_ptr(), out.data_ptr(),
+                                                  n_cells, n_event, mk(vs), mk(ls), mk(ss), _dt(value),
+                                                  _stream(value.device)))
     return out
 
 
@@ -210,6 +229,7 @@ def gather(x: torch.Tensor, idx: torch.Tensor, outer: int, K: int, inner: int) -
     x, idx = x.contiguous(), idx.contiguous()
     N = idx.shape[0]
     out = torch.empty(N * outer * inner, dtype=x.dtype, device=x.device)
-    check(lib().alan_b200_gather(x.data_ptr(), idx.data_ptr(), out.data_ptr(), x.element_size(), N, outer, K,
-                                 inner, 1, _stream()))
+    with torch.cuda.device(x.device):
+        check(lib().alan_b200_gather(x.data_ptr(), idx.data_ptr(), out.data_ptr(), x.element_size(), N, outer, K,
+                                     inner, 1, _stream(x.device)))
     return out

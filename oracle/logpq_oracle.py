@@ -221,13 +221,22 @@ def ont(x: NT) -> ONT:
 # A1  LSE with eps  (utils.py:207-225)
 # ---------------------------------------------------------------------------
 
+# eps of A1/A5 is finfo(dtype).eps (utils.py:220,507).  `EPS_OF` lets a test evaluate the fp32 SEMANTICS (fp32's eps)
+# in float64 arithmetic: the yardstick for fp32 rounding error (tests/golden_io.py f64_truth).
+EPS_OF = None
+
+
+def _eps(dtype):
+    return t.finfo(EPS_OF if EPS_OF is not None else dtype).eps
+
+
 def lse_eps(x: ONT, axes) -> ONT:
     axes = tuple(a for a in axes if a in x.axes)          # ignore_extra_dims=True (reduce_Ks.py:251)
     if len(axes) == 0:
         return x
     x_max = x.amax(axes)
     s = (x - x_max).exp().sum(axes)
-    return (s + t.finfo(s.t.dtype).eps).log() + x_max
+    return (s + _eps(s.t.dtype)).log() + x_max
 
 
 def logmeanexp(x: ONT, axes) -> ONT:
@@ -381,7 +390,7 @@ def logmmexp(prev, curr):
     prev_max = prev.amax(-1, keepdim=True)
     curr_max = curr.amax(-2, keepdim=True)
     r = (prev - prev_max).exp() @ (curr - curr_max).exp()
-    return (r + t.finfo(r.dtype).eps).log() + prev_max + curr_max
+    return (r + _eps(r.dtype)).log() + prev_max + curr_max
 
 
 def chain_logmmexp(ms):
@@ -403,7 +412,8 @@ def chain_logmmexp(ms):
 # ---------------------------------------------------------------------------
 
 class Ctx:
-    def __init__(self, sample, inputs_params, data, extra_log_factors, all_plates, dtype, split=None):
+    def __init__(self, sample, inputs_params, data, extra_log_factors, all_plates, dtype, split=None,
+                 checkpoint=False):
         self.sample = sample
         self.inputs_params = inputs_params
         self.data = data
@@ -411,6 +421,7 @@ class Ctx:
         self.all_plates = tuple(all_plates)
         self.dtype = dtype
         self.split = split
+        self.checkpoint = checkpoint      # the reference's `checkpoint` strategy (logpq.py:41,62-66)
 
 
 def _elf_at_level(elf, active_plates, all_plates):
@@ -451,7 +462,7 @@ def _slice_ctx(ctx, plate, lo, hi):
                 out[k] = v
         return out
     return Ctx(sl(ctx.sample), sl(ctx.inputs_params), sl(ctx.data), sl(ctx.elf), ctx.all_plates, ctx.dtype,
-               ctx.split)
+               ctx.split, ctx.checkpoint)
 
 
 def split_sizes(orig, size):
@@ -478,7 +489,21 @@ def logPQ_plate(name, P, Q, ctx, scope, active_plates, v2g):
             sub = _slice_ctx(ctx, plate, lo, lo + s)
             sub_scope = {k: (ONT(v.t.narrow(v.axes.index(plate), lo, s), v.axes) if plate in v.axes else v)
                          for k, v in scope.items()}
-            lpq = _logPQ_plate(name, P, Q, sub, sub_scope, active_plates, v2g, lpq)
+            if ctx.checkpoint and t.is_grad_enabled():
+                # logpq.py:62-66: every Split chunk under a non-reentrant torch.utils.checkpoint, so the backward
+                # holds one chunk's intermediates at a time (cfg-5: 200 chunks of 50 users)
+                from torch.utils.checkpoint import checkpoint as _ckpt
+                axes_box = []
+
+                def run(prev_t, sub=sub, sub_scope=sub_scope, lpq=lpq):
+                    prev = None if lpq is None else ONT(prev_t, lpq.axes)
+                    r = _logPQ_plate(name, P, Q, sub, sub_scope, active_plates, v2g, prev)
+                    axes_box[:] = [r.axes]
+                    return r.t
+                out = _ckpt(run, None if lpq is None else lpq.t, use_reentrant=False)
+                lpq = ONT(out, axes_box[0])
+            else:
+                lpq = _logPQ_plate(name, P, Q, sub, sub_scope, active_plates, v2g, lpq)
             lo += s
         return lpq
     return _logPQ_plate(name, P, Q, ctx, scope, active_plates, v2g, None)
@@ -512,14 +537,16 @@ def _logPQ_plate(name, P, Q, ctx, scope, active_plates, v2g, prev_lpq):
     return lp
 
 
-def elbo(P: Plate, Q: Plate, sample, inputs_params, data, extra_log_factors=None, split=None):
-    """Sample._elbo (Sample.py:69-108).  All dict values are NT/ONT; returns a 0-d tensor."""
+def elbo(P: Plate, Q: Plate, sample, inputs_params, data, extra_log_factors=None, split=None, checkpoint=False):
+    """Sample._elbo (Sample.py:69-108).  All dict values are NT/ONT; returns a 0-d tensor.
+    split=(plate, size) is `computation_strategy=Split(plate, size)` (Split.py:44-130); checkpoint=True wraps
+    every chunk in torch.utils.checkpoint like the reference's default strategy (logpq.py:41,62-66)."""
     conv = lambda d: {k: (v if isinstance(v, ONT) else ont(v)) for k, v in (d or {}).items()}
     sample, inputs_params, data, elf = conv(sample), conv(inputs_params), conv(data), conv(extra_log_factors)
     elf = {k: v.sum_pos() for k, v in elf.items()}                # Sample.py:74
     dtype = _working_dtype(sample, inputs_params, data, elf)
     sample, inputs_params, data, elf = [_cast(d, dtype) for d in (sample, inputs_params, data, elf)]
-    ctx = Ctx(sample, inputs_params, data, elf, P.all_platenames(), dtype, split)
+    ctx = Ctx(sample, inputs_params, data, elf, P.all_platenames(), dtype, split, checkpoint)
     lp = logPQ_plate(None, P, Q, ctx, {}, [], Q.varname2groupvarname())
     assert lp.t.ndim == 0, f"elbo has leftover axes {lp.axes}"
     return lp.t

@@ -82,9 +82,20 @@ def test_marginals_moments_ess(case, tag):
         k2 = tuple(sorted(key, key=groups.index))
         mine = marg.weights[k2].order(axes).t.cpu()
         assert rel_err(mine, ref) < 30 * tol(tag), key
-    for grp, e in marg.ess().items():
-        w = marg.weights[(grp,)]
-        assert (e.t > 0.999).all() and (e.t <= w.named_sizes['K_' + grp] * 1.001).all()
+    # ESS = 1 / sum_K w^2 (Marginals.py:52-61) against the same formula on the reference's golden marginals
+    ess = marg.ess()
+    worst = None
+    for key, (ref, axes) in g["marginals"].items():
+        if len(key) != 1:
+            continue
+        grp = key[0]
+        kd = tuple(i for i, a in enumerate(axes) if a.startswith("K_"))
+        ref_ess = 1.0 / (ref.double() ** 2).sum(kd)
+        plates = tuple(a for a in axes if not a.startswith("K_"))
+        mine = ess[grp].order(plates).t.cpu()
+        assert rel_err(mine, ref_ess) < 100 * tol(tag), grp
+        worst = ref_ess.min().item() if worst is None else min(worst, ref_ess.min().item())
+    assert abs(marg.min_ess() - worst) <= 100 * tol(tag) * worst
     moms = s.moments([(v, models.MOMENT_FUNCS[f]) for v, f in g["moment_specs"]])
     for mine, (ref, axes) in zip(moms, g["moments"]):
         assert rel_err(mine.order(axes).t.cpu(), ref) < 30 * tol(tag)
@@ -137,3 +148,97 @@ def test_plans_are_cached_per_problem():
     L2 = s2.elbo_rws()
     assert len(prob._runners) == n
     assert t.equal(L1.detach(), L2.detach())
+
+
+@pytest.mark.parametrize("tag", list(TAGS))
+@pytest.mark.parametrize("case", CASES)
+def test_moments_sample_marginal(case, tag):
+    """The reference's own `test_moments_sample_marginal` (tests/test_problem_vs_itself.py:71-88): `sample.moments`
+    (source-term gradient) and `marginals.moments` (sum_K f(x) w, Marginals.py:31-46) agree on the same sample --
+    same rtol 1e-4 / atol 1e-5 -- and both match the reference's golden moments."""
+    g = load(case, tag)
+    prob, _ = _problem(g, case)
+    s = prob.sample_from({k: NT(*v) for k, v in g["sample"].items()})
+    specs = [(v, models.MOMENT_FUNCS[f]) for v, f in g["moment_specs"]]
+    a = s.moments(specs)
+    b = s.marginals().moments(specs)
+    for ma, mb, (ref, axes) in zip(a, b, g["moments"]):
+        assert ma.axes == mb.axes or set(ma.axes) == set(mb.axes)
+        assert t.allclose(ma.t, mb.order(ma.axes).t, rtol=1e-4, atol=1e-5)
+        assert rel_err(mb.order(axes).t.cpu(), ref) < 30 * tol(tag)
+
+
+def test_inline_moment_lambdas_do_not_alias():
+    """Two different inline lambdas in a row must not hit each other's cached plan (their id() can be recycled once
+    the first is freed; the cache entry keeps the function alive)."""
+    g = load("cfg1_lgl", "f32")
+    prob, _ = _problem(g, "cfg1_lgl")
+    s = prob.sample_from({k: NT(*v) for k, v in g["sample"].items()})
+    m1 = s.moments([('a', lambda x: x)])[0].t.clone()
+    m2 = s.moments([('a', lambda x: x * x)])[0].t.clone()
+    m1b = s.moments([('a', lambda x: x)])[0].t.clone()
+    ref = {f: r for (v, f), (r, _) in zip(g["moment_specs"], g["moments"]) if v == 'a'}
+    assert rel_err(m1.cpu(), ref['mean']) < 3e-4 and rel_err(m2.cpu(), ref['mean2']) < 3e-4
+    assert t.equal(m1, m1b) and not t.equal(m1, m2)
+
+
+def test_interleaved_forwards_keep_their_own_gradients():
+    """`(l1 + l2).backward()` with two samples of one problem: both forwards share a cached runner (one device
+    workspace); each backward must see ITS forward's intermediates (the runner recomputes a stale forward)."""
+    g = load("cfg2_movielens", "f32")
+    grads = []
+    for which in (0, 1, 2):
+        prob, params = _problem(g, "cfg2_movielens", requires_grad=True)
+        s1 = prob.sample_from({k: NT(*v) for k, v in g["sample"].items()})
+        s2 = prob.sample_from({k: NT(v[0] * 0.9 + 0.05, v[1]) for k, v in g["sample"].items()})
+        if which == 0:
+            s1.elbo_rws().backward()
+        elif which == 1:
+            s2.elbo_rws().backward()
+        else:
+            l1, l2 = s1.elbo_rws(), s2.elbo_rws()
+            assert len(prob._runners) == 1
+            (l1 + l2).backward()
+        grads.append({k: v.t.grad.clone() for k, v in params.items()})
+    for k in grads[0]:
+        assert rel_err(grads[2][k], grads[0][k] + grads[1][k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("tag", list(TAGS))
+@pytest.mark.parametrize("case,plate,size", [("cfg1_lgl", "T", 3), ("cfg1_lglp", "T", 4), ("cfg2_movielens", "plate_1", 5),
+                                              ("cfg3_radon", "States", 2), ("ref_dangling", "T", 3)])
+def test_compstrat_split_matches_single_pass(case, plate, size, tag):
+    """The reference's `test_compstrat_elbo_vi / _rws / _moments` (tests/test_problem_vs_itself.py:231-280):
+    no_checkpoint == checkpoint == Split(...) on the same sample -- log-evidence, parameter and sample gradients,
+    marginals and moments.  Split sizes leave a ragged last block on purpose."""
+    from alan_b200.strategy import Split, no_checkpoint, checkpoint
+    g = load(case, tag)
+    res = {}
+    for name, strat in (("none", no_checkpoint), ("ckpt", checkpoint), ("split", Split(plate, size))):
+        prob, params = _problem(g, case, requires_grad=True)
+        sample = {k: NT(v[0].clone().requires_grad_(True), v[1]) for k, v in g["sample"].items()}
+        s = prob.sample_from(sample, reparam=True)
+        L = s.elbo_vi(computation_strategy=strat)
+        L.backward()
+        moms = s.moments([(v, models.MOMENT_FUNCS[f]) for v, f in g["moment_specs"]], computation_strategy=strat)
+        marg = s.marginals(computation_strategy=strat)
+        res[name] = (L.detach().clone(), {k: v.t.grad.clone() for k, v in params.items()},
+                     {k: v.t.grad.clone() for k, v in sample.items()}, [m.t.clone() for m in moms],
+                     {k: w.t.clone() for k, w in marg.weights.items()},
+                     s.elbo_nograd(computation_strategy=strat).clone())
+    tl = tol(tag)
+    assert rel_err(res["none"][0].cpu(), g["elbo"]) < tl
+    assert t.equal(res["none"][0], res["ckpt"][0])
+    a, b = res["none"], res["split"]
+    assert rel_err(b[0], a[0]) < tl and rel_err(b[5], a[0]) < tl
+    for k in a[1]:
+        assert rel_err(b[1][k], a[1][k]) < 30 * tl, k
+    for k in a[2]:
+        assert rel_err(b[2][k], a[2][k]) < 30 * tl, k
+    for x, y in zip(a[3], b[3]):
+        assert t.allclose(x, y, rtol=1e-4, atol=1e-5)                   # upstream's own tolerance for this pair
+    for k in a[4]:
+        assert rel_err(b[4][k], a[4][k]) < 30 * tl, k
+    if case == "cfg3_radon":                       # only top-level plates can be split here; a nested one is refused
+        with pytest.raises(Exception, match="Split"):
+            prob.sample_from({k: NT(*v) for k, v in g["sample"].items()}).elbo_nograd(computation_strategy=Split("Counties", 2))

@@ -13,7 +13,7 @@ import torch as t
 import models
 from alan_b200 import model as M
 from alan_b200.named import NT
-from golden_io import load, rel_err, tol, TAGS
+from golden_io import load, rel_err, elem_err, tol, TAGS
 from uniforms import UniformSource
 
 pytestmark = pytest.mark.gpu
@@ -138,12 +138,34 @@ def test_marginals_and_moments_vs_reference_golden(case, tag):
     lp = run.forward_raw(tensors)
     grads = run.backward_raw(tensors)
     assert rel_err(lp.cpu(), g["elbo"]) < tol(tag)
+    # Two yardsticks.  (1) max-norm against the reference's golden, 30x the log-evidence bound.  (2) TRUE element-
+    # wise relative error (golden_io.elem_err: not blind to small entries): north_star's 1e-5 (fp32) / 1e-10-scale
+    # (fp64) against the golden, OR -- where the reference's own fp32 path does not reach 1e-5 element-wise either
+    # (measured: up to 1.4e-4 on cfg4 marginals, 3.5e-5 on cfg2 moments) -- no worse than 3x the reference's own
+    # fp32 error, both measured against the float64 evaluation of the same fp32 semantics (golden_io.f64_truth).
+    truth = None
+    if tag == "f32":
+        from oracle import logpq_oracle as O
+        from golden_io import f64_truth
+        truth = f64_truth(case, g, models, M, O, joints=[k for k in g["marginals"] if len(k) > 1])
+    etol = 1e-5 if tag == "f32" else 1e-9
+
+    def check(mine, ref, truth_t, what):
+        assert rel_err(mine, ref) < 30 * tol(tag), what
+        e = elem_err(mine, ref)
+        if e < etol:
+            return
+        assert truth_t is not None, f"{what}: element-wise error {e:.2e} against the fp64 golden"
+        e_mine, e_ref = elem_err(mine, truth_t), elem_err(ref, truth_t)
+        print(f"{case} {what}: element-wise {e:.1e} vs golden; vs f64 truth: engine {e_mine:.1e}, reference fp32 {e_ref:.1e}")
+        assert e_mine <= max(etol, 3 * e_ref), f"{what}: element-wise error {e_mine:.2e} vs the f64 truth; the reference's own is {e_ref:.2e}"
     for key, (ref, axes) in g["marginals"].items():
         name = comp.elf_keys[key]
         pt = comp.plan.input_pts[name]
-        assert rel_err(_as(pt.axes, grads[name].cpu(), axes), ref) < 30 * tol(tag), key
-    for (jname, plates, pos), (ref, axes) in zip(comp.moment_inputs, g["moments"]):
-        assert rel_err(_as(plates, grads[jname].cpu(), axes), ref) < 30 * tol(tag), jname
+        tw = truth["marginals"][frozenset(key)] if truth else None
+        check(_as(pt.axes, grads[name].cpu(), axes), ref, NT(tw.t, tw.axes).order(axes).t if truth else None, f"marginal {key}")
+    for i, ((jname, plates, pos), (ref, axes)) in enumerate(zip(comp.moment_inputs, g["moments"])):
+        check(_as(plates, grads[jname].cpu(), axes), ref, truth["moments"][i].order(axes).t if truth else None, f"moment {jname}")
 
 
 @pytest.mark.parametrize("tag", list(TAGS))
@@ -463,6 +485,42 @@ def test_full_size_cfg5_properties(monkeypatch):
     lp_sum = t.empty((), device="cuda:0")
     r.dp.fwd(1, tens, lp_sum)
     assert rel_err(lp_sum.cpu(), lp_tc.cpu()) < 1e-6
+
+
+def test_full_size_cfg5_vs_oracle():
+    """BASELINE cfg-5 at its full size (10 000 users x 50 films, d=18, K=30) -- the configuration the bench line is
+    quoted on -- against the CPU oracle run the way the reference has to run it: `Split('plate_1', 50)` chunks, each
+    under torch.utils.checkpoint (logpq.py:41-66, Split.py:44-130; 200 sequential chunks, ~0.5 GB of intermediates
+    each).  Log-evidence within north_star's 1e-5 relative and all six Q-parameter gradients (global: [18]; per
+    user: [10 000, 18]) against autograd through the oracle."""
+    import bench
+    from oracle import logpq_oracle as O
+    Compiled, Runner = _engine()
+    cfg = bench.WORKLOADS["cfg5"]
+    P, Q, sample, ip, data, names = bench.make_problem(cfg, 0, cfg["M"])
+    comp = Compiled(P, Q, sample, ip, data, grad_names=names)
+    kinds = [type(op).__name__ for prog in comp.plan.programs for op in prog]
+    assert 'FanLseOp' in kinds and 'FanLseBwdOp' in kinds          # the tcgen05 kernels are what is being checked
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(sample, ip, data)
+    lp = run.forward_raw(tensors)
+    grads = run.backward_raw(tensors)
+    t.cuda.synchronize()
+    t.set_num_threads(max(1, (__import__("os").cpu_count() or 1)))
+    ipg = {k: NT(v.t.clone().requires_grad_() if k in names else v.t, v.axes) for k, v in ip.items()}
+    ref = O.elbo(P, Q, sample, ipg, data, split=('plate_1', 50), checkpoint=True)
+    rg = t.autograd.grad(ref, [ipg[k].t for k in names])
+    e = rel_err(lp.cpu(), ref.detach())
+    print(f"cfg5 full size: lp={lp.item():.4f} oracle={ref.item():.4f} rel_err={e:.2e}")
+    assert e < 1e-5
+    for k, r in zip(names, rg):
+        pt = comp.plan.input_pts[k]
+        mine = _as(pt.axes, grads[k].cpu(), ipg[k].axes)
+        eg = rel_err(mine, r)
+        print(f"  grad {k}: max-norm rel err {eg:.2e}")
+        # global-parameter gradients are sums over 10 000 users of terms of either sign, evaluated in fp32 on both
+        # sides (the oracle's chunk sums included): 30x the log-evidence bound, as for every other fp32 gradient
+        assert eg < 30 * 1e-5, k
 
 
 @pytest.mark.parametrize("chunks", [2, 4])

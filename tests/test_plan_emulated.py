@@ -206,3 +206,58 @@ def test_importance_sample_through_timeseries_raises_like_the_reference():
     Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"])           # log-evidence plan: fine
     with pytest.raises(Exception, match="Timeseries is unfinished in the reference"):
         Compiled(P, Q, g["sample_nt"], g["inputs_params_nt"], g["data_nt"], N=5)
+
+
+@pytest.mark.parametrize("tag", list(TAGS))
+@pytest.mark.parametrize("case", CASES)
+def test_marginals_moments_equal_sample_moments(case, tag):
+    """The reference's own pin `test_moments_sample_marginal` (tests/test_problem_vs_itself.py:71-88):
+    `marginals.moments` (sum_K f(x) w, Marginals.py:31-46 / moments.py:16-35 -- here plan.weighted_moment_plan, run by
+    the emulator) equals `sample.moments` (the source-term gradient) on the same sample: rtol 1e-4, atol 1e-5 as
+    upstream, against the reference's golden moments and marginals."""
+    from alan_b200.plan import weighted_moment_plan, TensorSig
+    g = load(case, tag)
+    P, Q = models.build(case, M, TAGS[tag])
+    groups, v2g = Q.groupvarnames(), Q.varname2groupvarname()
+    canon = list(P.all_platenames()) + [M.Kname(x) for x in groups]
+    order = lambda axes: tuple(a for a in canon if a in axes)
+    for (var, fname), (ref, axes) in zip(g["moment_specs"], g["moments"]):
+        x = g["sample_nt"][var]
+        w_t, w_axes = g["marginals"][(v2g[var],)]
+        w = NT(w_t, w_axes)
+        sizes = {**x.named_sizes, **w.named_sizes}
+        xa, wa = order(x.axes), order(w.axes)
+        plan = weighted_moment_plan({var: TensorSig('sample', xa, x.pos_shape)}, wa, models.MOMENT_FUNCS[fname],
+                                    sizes, TAGS[tag], canon)
+        ins = []
+        for name in plan.input_names:
+            if name in plan.const_inputs:
+                ins.append(plan.const_inputs[name])
+            elif name == '__w':
+                ins.append(w.order(wa).t.to(TAGS[tag]).contiguous())
+            else:
+                ins.append(x.order(xa).t.to(TAGS[tag]).contiguous())
+        n_out = 1
+        for s_ in plan.out_shape:
+            n_out *= s_
+        out = t.zeros(max(n_out, 1), dtype=TAGS[tag])
+        emu = Emu(plan, ins, outputs={0: out})
+        emu.run(plan.programs[0])
+        mine = NT(out.reshape(plan.out_shape), plan.out_axes).order(axes).t if plan.out_axes else out.reshape(plan.out_shape)
+        assert t.allclose(mine.double(), ref.double(), rtol=1e-4, atol=1e-5), (var, fname)
+
+
+def test_split_sizes_follow_the_reference_rule():
+    """strategy.Split.sizes = SplitDims (Split.py:84-95): [s, ..., s, rem], one element stolen when rem == 1."""
+    from alan_b200.strategy import Split, resolve, no_checkpoint, checkpoint
+    assert Split('p', 20).sizes(300) == [20] * 15
+    assert Split('p', 20).sizes(305) == [20] * 15 + [5]
+    assert Split('p', 20).sizes(301) == [20] * 14 + [19, 2]
+    assert Split('p', 2).sizes(5) == [2, 2, 1]
+    with pytest.raises(AssertionError):
+        Split('p', 10).sizes(10)
+    assert resolve(None) is None and resolve(no_checkpoint) is None and resolve(checkpoint) is None
+    sp = Split('plate_1', 7)
+    assert resolve(sp) is sp
+    with pytest.raises(Exception, match="computation_strategy"):
+        resolve("nope")
