@@ -110,22 +110,51 @@ class B200:
     """`computation_strategy=B200()`: run the whole plate tree on the B200 engine.
 
     The reference's strategy protocol (`split_args`, src/alan/Split.py:7-14,44-71) is kept so that the
-    object can be passed wherever a strategy is expected; the hook in `Sample._elbo` calls `logPQ`.
+    object can be passed wherever a strategy is expected; the hook in `Sample._elbo` calls `logPQ`
+    (`install_hook` below applies that two-line hook to an imported reference package).
     """
-    def __init__(self, shard_plate=None, process_group=None, device=None):
-        self.shard_plate, self.pg, self.device = shard_plate, process_group, device
+    def __init__(self, shard_plate=None, process_group=None, device=None, split=None):
+        self.shard_plate, self.pg, self.device, self.split = shard_plate, process_group, device, split
         self._cache = {}
 
     def split_args(self, name, sample, inputs_params, extra_log_factors, data, all_platedims):
         return [dict(sample=sample, inputs_params=inputs_params, extra_log_factors=extra_log_factors,
                      data=data, all_platedims=all_platedims)]
 
-    def logPQ(self, P, Q, sample, inputs_params, data, extra_log_factors=None, grad_names=()):
-        nts = nts_from_tree(sample)
-        key = (id(P), id(Q), tuple(sorted((k, tuple(v.t.shape), v.axes) for k, v in nts.items())),
-               tuple(sorted(flatten_tree(extra_log_factors or {}))), tuple(grad_names))
+    def logPQ(self, P, Q, sample, inputs_params, data, extra_log_factors=None, grad_names=None):
+        """The reference's `logPQ_plate(name=None, ...)` (logpq.py:15-60) for a whole model: a 0-d tensor on the
+        device, attached to autograd for every input that requires a gradient (Q / P parameters, reparameterised
+        samples, the source terms J of marginals and moments)."""
+        nts, ips, elf = nts_from_tree(sample), nts_from_tree(inputs_params), nts_from_tree(extra_log_factors or {})
+        dts = nts_from_tree(data)
+        if grad_names is None:
+            grad_names = [k for d in (ips, nts, elf) for k, v in d.items() if v.t.requires_grad]
+        shapes = lambda d: tuple(sorted(((str(k), tuple(v.t.shape), v.axes, str(v.t.dtype)) for k, v in d.items())))
+        key = (id(P), id(Q), shapes(nts), shapes(ips), shapes(dts), shapes(elf), tuple(str(g) for g in grad_names))
         if key not in self._cache:
-            self._cache[key] = compile_from_reference(P, Q, sample, inputs_params, data, extra_log_factors,
-                                                      grad_names, self.shard_plate, self.pg, self.device)
-        runner = self._cache[key]
+            runner = compile_from_reference(P, Q, sample, inputs_params, data, extra_log_factors,
+                                            grad_names, self.shard_plate, self.pg, self.device)
+            self._cache[key] = (runner, P, Q, list(elf.keys()))    # P / Q / keys kept alive: their id() is in the key
+        runner = self._cache[key][0]
         return runner.elbo(tensors_from_reference(runner, sample, inputs_params, data, extra_log_factors))
+
+
+def install_hook(alan_pkg):
+    """Apply INTEGRATION.md's hook to an imported reference package: `Sample._elbo` dispatches to the B200
+    engine when `computation_strategy` is a `B200` instance and is untouched otherwise.  Everything above it
+    (`elbo_vi / elbo_rws / elbo_nograd / marginals / moments`, Sample.py:110-148,208-346) then runs on the GPU
+    with no other change.  Returns a function that removes the hook again."""
+    import sys
+    S = sys.modules[alan_pkg.__name__ + ".Sample"].Sample
+    orig = S._elbo
+
+    def _elbo(self, sample, extra_log_factors, computation_strategy):
+        if isinstance(computation_strategy, B200):
+            return computation_strategy.logPQ(self.P.plate, self.Q.plate, sample, self.problem.inputs_params(),
+                                              self.problem.data, extra_log_factors)
+        return orig(self, sample, extra_log_factors, computation_strategy)
+    S._elbo = _elbo
+
+    def remove():
+        S._elbo = orig
+    return remove

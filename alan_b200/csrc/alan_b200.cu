@@ -153,7 +153,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
             if (code == OP_CHAIN || code == OP_CHAIN_BWD) {
                 r.p = op_begin + 2; Reader q = r;
                 // skip trefs to read T
-                int ntref = (code == OP_CHAIN) ? 3 : 5;
+                int ntref = (code == OP_CHAIN) ? 3 : 6;
                 q.p += 3 * ntref;
                 q.i64v(); i64 T_ = q.i64v();
                 int lv = 0; for (i64 n = T_; n > 1; n = n / 2 + n % 2) lv++;
@@ -477,9 +477,57 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
     return 0;
 }
 
+// Pipe-peak micro-benchmarks (roofline denominators measured in the same process as the bench): 8 independent
+// chains per thread, 2 x 1024-thread CTAs per SM, best of 5 by CUDA events.  which = 0: MUFU.EX2, 1: FFMA.
+template <int MODE>
+__global__ void __launch_bounds__(1024) pipe_peak_kernel(float* out, float seed, int iters) {
+    float a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const float m = seed * 0.5f, c = 0.001f;
+    for (int i = 0; i < iters; ++i) {
+        if (MODE == 0) {
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a0)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a1));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a2)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a3));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a4)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a5));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a6)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a7));
+        } else {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 extern "C" {
 
 int alan_b200_abi_version(void) { return AB_VERSION; }
+
+int alan_b200_pipe_peak(int which, void* scratch, size_t scratch_bytes, double* ops_per_s, void* stream) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail("pipe_peak: no CUDA device");
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = sms * 2, block = 1024, iters = 2048;
+    if (scratch_bytes < (size_t)grid * block * sizeof(float)) return fail("pipe_peak: scratch too small");
+    if (which != 0 && which != 1) return fail("pipe_peak: which must be 0 (MUFU.EX2) or 1 (FFMA)");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 6; ++r) {
+        cudaEventRecord(e0, st);
+        if (which == 0) pipe_peak_kernel<0><<<grid, block, 0, st>>>((float*)scratch, 1.0f + 1e-4f * r, iters);
+        else pipe_peak_kernel<1><<<grid, block, 0, st>>>((float*)scratch, 1.0f + 1e-4f * r, iters);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("pipe_peak: ") + cudaGetErrorString(e));
+    *ops_per_s = 8.0 * iters * (double)grid * block / (best * 1e-3);
+    return 0;
+}
 const char* alan_b200_last_error(void) { return g_err.c_str(); }
 
 int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** out) {

@@ -26,26 +26,44 @@ EXPORTS = [
     "alan_b200_workspace_bytes", "alan_b200_num_inputs", "alan_b200_num_programs",
     "alan_b200_program_launches", "alan_b200_run", "alan_b200_profile", "alan_b200_logpq_fwd", "alan_b200_logpq_bwd",
     "alan_b200_resample", "alan_b200_gather", "alan_b200_lse_eps", "alan_b200_chain_scratch_elems",
-    "alan_b200_logmmexp_chain", "alan_b200_normal_logpdf_bcast",
+    "alan_b200_logmmexp_chain", "alan_b200_normal_logpdf_bcast", "alan_b200_pipe_peak",
 ]
 
 
+def _source_digest():
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc")))
+    files.append(os.path.join(os.path.dirname(_HERE), "include", "alan_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def build_library(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> alan_b200/libalan_b200.so"""
-    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
-    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "alan_b200.h"))
-    if not force and os.path.exists(LIB_PATH):
-        if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
-            return LIB_PATH
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> alan_b200/libalan_b200.so.  Skipped only when the
+    library exists AND was built from exactly these sources and flags (content hash in libalan_b200.so.src)."""
+    digest, stamp = _source_digest(), LIB_PATH + ".src"
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        if verbose:
+            print(f"{LIB_PATH} is up to date with its sources ({digest[:12]})")
+        return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, SRC]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
+    open(stamp, "w").write(digest)
     return LIB_PATH
 
 
 _lib = None
+
+
+def _register_ops():
+    from . import ops  # noqa: F401  (registers torch.ops.alan_b200.*)
 
 
 def lib():
@@ -78,6 +96,7 @@ def lib():
     L.alan_b200_chain_scratch_elems.restype = i64
     L.alan_b200_logmmexp_chain.argtypes = [vp, vp, vp, i64, i64, i64, i32, vp]
     L.alan_b200_normal_logpdf_bcast.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, i32, vp]
+    L.alan_b200_pipe_peak.argtypes = [i32, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_double), vp]
     _lib = L
     return L
 
@@ -130,31 +149,20 @@ class DevicePlan:
         except Exception:
             pass
 
-    # every call enters the plan's device: kernels, graph captures and the stream all belong to it even when the
-    # caller's current device is another GPU
+    # The typed entry points go through the torch custom-op layer (alan_b200/ops.py: torch.ops.alan_b200.*), which
+    # enters the plan's device and passes raw pointers + the caller's current stream on that device to the C ABI.
     def fwd(self, segment, inputs, lp_out):
-        with torch.cuda.device(self.device):
-            check(lib().alan_b200_logpq_fwd(self.handle, segment, _ptr_array(inputs),
-                                            ctypes.c_void_p(lp_out.data_ptr()), ctypes.c_void_p(self.ws.data_ptr()),
-                                            _stream(self.device)))
+        torch.ops.alan_b200.logpq_fwd_into(self.handle.value, segment, list(inputs), lp_out, self.ws)
 
     def bwd(self, segment, inputs, grad_lp, grads_out):
-        with torch.cuda.device(self.device):
-            check(lib().alan_b200_logpq_bwd(self.handle, segment, _ptr_array(inputs),
-                                            ctypes.c_void_p(grad_lp.data_ptr()), _ptr_array(grads_out),
-                                            ctypes.c_void_p(self.ws.data_ptr()), _stream(self.device)))
+        torch.ops.alan_b200.logpq_bwd(self.handle.value, segment, list(inputs), grad_lp, list(grads_out), self.ws)
 
     def resample(self, inputs, uniforms, idx_out):
-        with torch.cuda.device(self.device):
-            check(lib().alan_b200_resample(self.handle, _ptr_array(inputs), _ptr_array(uniforms),
-                                           _ptr_array(idx_out), ctypes.c_void_p(self.ws.data_ptr()),
-                                           _stream(self.device)))
+        torch.ops.alan_b200.resample(self.handle.value, list(inputs), list(uniforms), list(idx_out), self.ws)
 
     def run(self, program, inputs, outputs):
         """Generic program run (alan_b200_run): used by the stand-alone plans (Marginals.moments, Q sampling)."""
-        with torch.cuda.device(self.device):
-            check(lib().alan_b200_run(self.handle, program, _ptr_array(inputs), _ptr_array(outputs),
-                                      ctypes.c_void_p(self.ws.data_ptr()), _stream(self.device)))
+        torch.ops.alan_b200.run(self.handle.value, program, list(inputs), list(outputs), self.ws)
 
     def profile(self, program, inputs, outputs, aux):
         """per-op device milliseconds of one program run (CUDA events around every op)."""
@@ -223,13 +231,21 @@ def normal_logpdf_bcast(value, loc, scale, n_cells, n_event, vs, ls, ss) -> torc
     return out
 
 
+def pipe_peak(which: int, device=None) -> float:
+    """Measured lane-operations per second of one SM pipe (0: MUFU.EX2, 1: FFMA) on `device` -- bench.py's
+    roofline denominators for the MUFU- and FP32-bound kernels, taken in the same process as the bench."""
+    dev = require_cuda(device)
+    scratch = torch.empty(4 * 1024 * 1024, dtype=torch.float32, device=dev)
+    r = ctypes.c_double(0.0)
+    with torch.cuda.device(dev):
+        check(lib().alan_b200_pipe_peak(which, scratch.data_ptr(), scratch.numel() * 4, ctypes.byref(r), _stream(dev)))
+    return r.value
+
+
 def gather(x: torch.Tensor, idx: torch.Tensor, outer: int, K: int, inner: int) -> torch.Tensor:
     """x [outer, K, inner], idx [N, outer] int64 -> out [N, outer, inner] (Sample.py:359-381)."""
     require_cuda()
-    x, idx = x.contiguous(), idx.contiguous()
-    N = idx.shape[0]
-    out = torch.empty(N * outer * inner, dtype=x.dtype, device=x.device)
-    with torch.cuda.device(x.device):
-        check(lib().alan_b200_gather(x.data_ptr(), idx.data_ptr(), out.data_ptr(), x.element_size(), N, outer, K,
-                                     inner, 1, _stream(x.device)))
-    return out
+    return torch.ops.alan_b200.gather(x.contiguous(), idx.contiguous(), outer, K, inner)
+
+
+_register_ops()

@@ -10,11 +10,12 @@ A step = one RWS iteration of the hot path on one batch of synthetic input: forw
 + backward (gradients of every Q parameter) of the MovieLens-shaped model
 (/root/reference/examples/models/movielens/movielens.py:39-74) at K=30, d=18.
 Workloads (BASELINE.json configs): `cfg2` = 300 users x 5 films, `cfg5` = 10 000 users x 50 films.  The
-user plate is sharded across the ranks (this replaces Split's sequential chunks): every GPU holds
-10 000 users of the same model ("scaling": "weak" -- N GPUs evaluate 10 000 N users; the only
-collectives are the all-reduce of the [K_mu, K_psi] tile and of the global-parameter gradients).
-`--scaling strong` keeps 10 000 users in total instead.  The cfg2 numbers (the >=50x target config) are
-measured in the same run at N=1 and reported under "cfg2".
+user plate is sharded across the ranks (this replaces Split's sequential chunks).  Default = what BASELINE.json
+names: the SAME 10 000-user problem split over the N GPUs ("scaling": "strong"; the only collectives are the
+reduction of the [K_mu, K_psi] tile and of the global-parameter gradients); every sharded run is checked against the
+unsharded one on the same inputs ("parity" in the line: log-evidence, global and per-user gradients).  The
+weak-scaling number (10 000 users PER GPU) rides along under "weak"; `--scaling weak` makes it the main line.
+The cfg2 numbers (the >=50x target config) are measured in the same run at N=1 and reported under "cfg2".
 
 Unit of work ("cell") = one (plate element, K tuple) entry of a factor tensor the reference
 materialises:  W = M*K^3 (z) + M*N*K (obs) + M*K (Q of z) + K^2 + 4K.
@@ -45,6 +46,31 @@ UNIT = "cells/s"
 
 def cells(M, N, K, **_):
     return M * K ** 3 + M * N * K + M * K + K * K + 4 * K
+
+
+def config_for(cfg, world, scaling):
+    """The `config` object of a line: the same for the b200 arm and the reference arm at a given N."""
+    if scaling == "weak" and world > 1:
+        cfg = dict(cfg, M=cfg["M"] * world, name=cfg["name"] + f"_x{world}_users")
+    per = (cfg["M"] + world - 1) // world
+    return cfg, {"workload": cfg["name"], "users": cfg["M"], "films": cfg["N"], "d": cfg["d"], "K": cfg["K"],
+                 "cells_per_step": cells(**cfg), "users_per_gpu": per,
+                 "parallelism": f"plate_1 sharded over {world} rank(s)",
+                 "l2": "256 MB buffer written between timed steps (L2 flush)"}
+
+
+def ncu_dram_traffic(kernel_regex):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, parsed from the committed
+    ncu CSV of this command (profiles/ncu_dram_bytes.csv: kernel, read bytes, write bytes, source capture)."""
+    import csv
+    import re
+    path = os.path.join(ROOT, "profiles", "ncu_dram_bytes.csv")
+    if not os.path.exists(path):
+        return None, None
+    for row in csv.DictReader(open(path)):
+        if re.search(kernel_regex, row["kernel"]):
+            return float(row["dram_bytes_read"]) + float(row["dram_bytes_write"]), row.get("capture")
+    return None, None
 
 
 def peaks():
@@ -187,13 +213,69 @@ def op_model(op, itemsize):
 
 
 # ------------------------------------------------------------------------------------------
-def run_b200(args, cfg, rank, world, local_rank, full_report=True):
+def timed_steps(step, flush, steps, warmup, barrier, dev, world):
+    """W warm-up steps, then K steps timed one by one with CUDA events on the launch stream (L2 flushed before
+    each), barrier + synchronize on both sides, max over ranks.  Returns (ms_per_step, wall seconds, last result)."""
+    import torch.distributed as dist
+    out = None
+    for _ in range(warmup):
+        out = step()
+    barrier()
+    ev = [(t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    wall0 = time.time()
+    for s, e in ev:
+        flush.fill_(1.0)
+        s.record()
+        out = step()
+        e.record()
+    barrier()
+    wall = time.time() - wall0
+    tt = t.tensor([sum(s.elapsed_time(e) for s, e in ev)], device=dev, dtype=t.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return tt.item() / steps, wall, out
+
+
+def sharded_parity(cfg, rank, world, lo, hi, dev, lp, grads, plan, params):
+    """Every rank runs the UNSHARDED problem (all users) on its own GPU and compares what the sharded step gave:
+    log-evidence and global-parameter gradients (all-reduced) against the unsharded values, per-user gradients
+    against the corresponding slice.  Raises on a mismatch, so every multi-GPU bench line is a parity check of the
+    NCCL path on hardware."""
+    from alan_b200.engine import Compiled, Runner
+    import torch.distributed as dist
+    P, Q, sample, ip, data, _ = make_problem(cfg, 0, cfg["M"])
+    comp = Compiled(P, Q, sample, ip, data, grad_names=params)
+    run = Runner(comp, dev)
+    tens = [x.to(dev) for x in comp.canonical_inputs(sample, ip, data)]
+    lp1 = run.forward_raw(tens)
+    g1 = run.backward_raw(tens)
+    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp(min=1e-300))
+    out = {"lp_rel_err": rel(lp, lp1), "global_grad_rel_err": 0.0, "per_user_grad_rel_err": 0.0}
+    for n in params:
+        if n in plan.global_grads:
+            out["global_grad_rel_err"] = max(out["global_grad_rel_err"], rel(grads[n], g1[n]))
+        else:
+            out["per_user_grad_rel_err"] = max(out["per_user_grad_rel_err"], rel(grads[n], g1[n][lo:hi]))
+    worst = t.tensor([out[k] for k in sorted(out)], device=dev, dtype=t.float64)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    out = dict(zip(sorted(out), worst.tolist()))
+    out["against"] = "the unsharded plan on the same inputs, run on every rank's own GPU; max over ranks"
+    # fp32 sums over 10 000 users re-associated across shards: 1e-6 on the log-evidence; the global-parameter
+    # gradients are sums of terms of either sign (cancellation): 1e-5
+    if not (out["lp_rel_err"] < 1e-6 and out["global_grad_rel_err"] < 1e-5 and out["per_user_grad_rel_err"] < 1e-5):
+        raise AssertionError(f"sharded run differs from the unsharded one: {out}")
+    del run, tens
+    return out
+
+
+def run_b200(args, cfg0, rank, world, local_rank, scaling=None, full_report=True, short=False):
     import torch.distributed as dist
     from alan_b200.engine import Compiled, Runner
+    scaling = scaling or args.scaling
     dev = t.device(f"cuda:{local_rank}")
     t.cuda.set_device(dev)
-    if args.scaling == "weak" and world > 1:
-        cfg = dict(cfg, M=cfg["M"] * world, name=cfg["name"] + f"_x{world}_users")
+    cfg, config = config_for(cfg0, world, scaling)
     M = cfg["M"]
     per = (M + world - 1) // world
     lo, hi = rank * per, min(M, (rank + 1) * per)
@@ -206,6 +288,7 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
     tensors = [x.to(dev) for x in host]
     flush = t.empty(256 * 1024 * 1024 // 4, dtype=t.float32, device=dev)      # > 126 MB L2
     W = cells(**cfg)
+    steps = min(args.steps, 10) if short else args.steps
 
     def step():
         # Runner.step = forward_raw + backward_raw (replayed as one CUDA graph once the buffers recur);
@@ -219,28 +302,13 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
             dist.barrier()
         t.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        lp, grads = step()       # held exactly like in the timed loop: the same output buffers (and graph bindings) recur
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    sampler_t0 = time.time()
-    ev = [(t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    wall0 = time.time()
-    for s, e in ev:
-        flush.fill_(1.0)
-        s.record()
-        lp, grads = step()
-        e.record()
-    barrier()
-    wall = time.time() - wall0
-    total_ms = sum(s.elapsed_time(e) for s, e in ev)
-    tt = t.tensor([total_ms], device=dev, dtype=t.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms = tt.item()
-    ms_per_step = total_ms / args.steps
+    sampler = ClockSampler(local_rank) if (rank == 0 and not short) else None
+    ms_per_step, wall, (lp, grads) = timed_steps(step, flush, steps, args.warmup, barrier, dev, world)
     value = W / (ms_per_step * 1e-3)
+    launches = sum(run.dp.launches[:plan.n_fwd + plan.n_bwd])
+    if short:
+        return {"value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "config": config,
+                "lp": float(lp)}
     # the timed region lasts ~10 ms, nvidia-smi answers every ~20 ms: every rank keeps running the SAME step loop
     # (untimed, same count on all ranks: the steps contain collectives) so the sampler gets ~0.6 s under this load
     for _ in range(0 if args.device_only else min(3000, int(600.0 / max(ms_per_step, 0.05)) + 1)):
@@ -252,23 +320,27 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
         clocks["sampled"] = "nvidia-smi every 20 ms over the timed steps and an untimed continuation of the same loop (~0.6 s)"
 
     if args.device_only:
-        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
                           "ms_per_step": ms_per_step, "config": {"workload": cfg["name"]},
-                          "gpu_launches": sum(run.dp.launches[:plan.n_fwd + plan.n_bwd]) * args.steps,
+                          "gpu_launches": launches * steps,
                           "note": "device-only short run (profiling aid), not a bench line"}))
         sys.exit(0)
+    parity = None
+    if world > 1 and scaling == "strong":
+        parity = sharded_parity(cfg, rank, world, lo, hi, dev, lp, grads, plan, params)
+
     # ---- e2e: host (pinned) buffers -> device -> fwd+bwd -> lp and gradients back to the host, through the
     # public host-buffer entry point engine.StreamedRunner (the user plate streamed in `--chunks` blocks so that
     # the H2D copy of a block overlaps the kernels of the previous one); --chunks 1 = copy everything, then run
     h2d = sum(x.numel() * x.element_size() for x in host)
     gout_host = None
-    ev2 = [(t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev2 = [(t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)) for _ in range(steps)]
     lp_host = t.empty((), dtype=comp.dtype).pin_memory()
     streamed = None
     if args.chunks > 1 and world == 1 and (hi - lo) % args.chunks == 0:
         from alan_b200.engine import StreamedRunner
         streamed = StreamedRunner(P, Q, sample, ip, data, params, 'plate_1', args.chunks, device=dev)
-    for i in range(args.warmup + args.steps):
+    for i in range(args.warmup + steps):
         k = i - args.warmup
         if k >= 0:
             flush.fill_(1.0)
@@ -289,141 +361,230 @@ def run_b200(args, cfg, rank, world, local_rank, full_report=True):
         t.cuda.synchronize()
     barrier()
     d2h = lp_host.element_size() + sum(g.numel() * g.element_size() for g in gout_host.values())
-    e2e_ms = sum(s.elapsed_time(e) for s, e in ev2)
-    tt = t.tensor([e2e_ms], device=dev, dtype=t.float64)
+    tt = t.tensor([sum(s.elapsed_time(e) for s, e in ev2)], device=dev, dtype=t.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_value = W / (tt.item() / args.steps * 1e-3)
+    e2e_value = W / (tt.item() / steps * 1e-3)
 
-    launches = sum(run.dp.launches[:plan.n_fwd + plan.n_bwd])
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "users": cfg["M"], "films": cfg["N"], "d": cfg["d"], "K": cfg["K"],
-                   "cells_per_step": W, "users_per_gpu": hi - lo,
-                   "parallelism": f"plate_1 sharded over {world} rank(s)",
-                   "l2": "256 MB buffer written between timed steps (L2 flush)"},
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": (f"engine.StreamedRunner.step, plate_1 in {args.chunks} blocks (H2D of block c+1 overlaps block c)"
                         if streamed is not None else "H2D copies, Runner.step (forward_raw + backward_raw as one replayed graph), D2H")},
-        "gpu_launches": launches * args.steps,
+        "gpu_launches": launches * steps,
         "lp": float(lp_host),
         "wall_s_timed_region": wall,
     }
+    if parity is not None:
+        line["parity"] = parity
     if clocks is not None:
         line["clocks"] = clocks
+    if world == 1:
+        line["e2e_api"] = e2e_through_public_api(cfg, dev, flush, steps, args.warmup, W)
 
     # ---- roofline of the dominant kernel: per-op CUDA events in a separate profiled pass
     if rank == 0 and full_report:
-        pk = peaks()
-        nprog = plan.n_fwd + plan.n_bwd
-        acc = {}
-        reps = max(3, min(args.steps, 10))
-        lp_d = t.empty((), dtype=comp.dtype, device=dev)
-        one = t.ones((), dtype=comp.dtype, device=dev)
-        gouts = [t.empty(plan.input_pts[n].shape, dtype=comp.dtype, device=dev) for n in plan.grad_inputs]
-        for rep in range(reps + 1):
-            flush.fill_(1.0)
-            for prog in range(nprog):
-                outs, aux = ([lp_d], []) if prog < plan.n_fwd else (gouts, [one])
-                ms = run.dp.profile(prog, tensors, outs, aux)
-                if rep == 0:
-                    continue
-                for j, m in enumerate(ms):
-                    acc[(prog, j)] = acc.get((prog, j), 0.0) + m / reps
-        t.cuda.synchronize()
-        if acc:
-            total = sum(acc.values())
-            (prog, j), top_ms = max(acc.items(), key=lambda kv: kv[1])
-            op = plan.programs[prog][j]
-            m = op_model(op, 4)
-            clk = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
-            # pipe peaks measured on this pool's B200 (tools/microbench.cu, profiles/r01_microbench.txt):
-            # 121 FMA/clk/SM (FFMA and FFMA2), 15.9 ex2/clk/SM
-            fp32_peak = 148 * 121 * 2 * clk * 1e6 / 1e12                       # TFLOP/s at the clock seen under load
-            mufu_peak = 148 * 15.9 * clk * 1e6                                 # ex2 / s
-            t_hbm = m["bytes"] / (pk["hbm_gbs"] * 1e9)
-            t_fp = m["flops"] / (fp32_peak * 1e12)
-            tc_path = m["kind"] in ("FanLseOp", "FanLseBwdOp") and comp.dtype == t.float32 and \
-                not os.environ.get("ALAN_B200_NO_TC")
-            if tc_path:
-                from alan_b200.plan import dense_fan_geometry
-                fop = op if m["kind"] == "FanLseOp" else op.fwd
-                dense = None if os.environ.get("ALAN_B200_TC_BLOCKDIAG") else dense_fan_geometry(fop, 4)
-                roof = dict(bound="tensor", achieved=m["flops"] / (top_ms * 1e-3) / 1e12, peak=pk["bf16_tflops"],
-                            unit="TFLOP/s")
-                if dense is not None:
-                    # fan_lse on tcgen05, dense formulation (csrc/fan_tc2.cuh): fp32-accurate 3xTF32 of the expanded
-                    # square.  Algorithmic flops (2 D per cell) against the measured dense bf16 peak; what this
-                    # formulation can reach is peak / 2 (tf32) / 3 (split) x D / KT (K = 2 D + 1 padded to 8) x the
-                    # used share of the 128-lane tiles and 32-column user slots.
-                    _, L, NG = dense
-                    KT = (2 * fop.D + 1 + 7) // 8 * 8
-                    tiles = -(-(L * fop.F) // 128)
-                    eff = (fop.D / KT) * (L * fop.F / (128.0 * tiles)) * (fop.kappa[2] / 32.0)
-                    roof["formulation_ceiling"] = pk["bf16_tflops"] / 6 * eff
-                    roof["path"] = ("tcgen05.mma kind::tf32, 3xTF32 split of the expanded square, (lam, f) on TMEM lanes, "
-                                    "A in TMEM (UTCHMMA / LDTM in SASS), %d fan groups" % NG)
-                else:
-                    # block-diagonal kernel (csrc/fan_tc.cuh): peak / 2 (tf32) / 3 (split) / 4 (block-diagonal zeros)
-                    roof["formulation_ceiling"] = pk["bf16_tflops"] / 24
-                    roof["path"] = "tcgen05.mma kind::tf32, 3xTF32 split, block-diagonal A in TMEM (UTCHMMA / LDTM in SASS)"
-                roof["frac_of_formulation_ceiling"] = roof["achieved"] / roof["formulation_ceiling"]
-            elif t_hbm >= t_fp:
-                roof = dict(bound="hbm", achieved=m["bytes"] / (top_ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s")
-            else:
-                roof = dict(bound="fp32", achieved=m["flops"] / (top_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s")
-            roof["frac"] = roof["achieved"] / roof["peak"]
-            # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this command
-            # at cfg-5 on one GPU (profiles/r01_fan_lse_tc2_full.md: dram__bytes_read.sum + dram__bytes_write.sum)
-            ncu_traffic = {"FanLseBwdOp": 60.08e6 + 1.30e6, "FanLseOp": 24.07e6 + 0.74e6}
-            traffic = ncu_traffic.get(m["kind"]) if (tc_path and cfg["M"] // max(world, 1) == 10000 and cfg["N"] == 50) else None
-            roof.update(traffic=traffic, kernel=f"{m['kind']}:{m['tag']}", kernel_ms=top_ms,
-                        share_of_step=top_ms / total, peak_source=pk["source"],
-                        algorithmic_bytes=m["bytes"], algorithmic_flops=m["flops"],
-                        hbm_frac=m["bytes"] / (top_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                        fp32_fma_frac=m["flops"] / (top_ms * 1e-3) / 1e12 / fp32_peak,
-                        timing="per-op CUDA events on the launch stream, separate profiled pass, mean of %d" % reps)
-            if m["kind"] in ("FanLseOp", "FanLseBwdOp"):
-                roof["mufu_frac"] = m["points"] / (top_ms * 1e-3) / mufu_peak   # one ex2 per cell is the algorithmic minimum
-            line["roofline"] = roof
-            tops = sorted(acc.items(), key=lambda kv: -kv[1])[:6]
-            line["top_ops"] = [dict(op=f"{op_model(plan.programs[p][k], 4)['kind']}:{op_model(plan.programs[p][k], 4)['tag']}",
-                                    ms=round(v, 4)) for (p, k), v in tops]
+        line.update(roofline_report(run, comp, plan, tensors, flush, dev, clocks, steps))
     return line
 
 
-def run_reference(args, cfg, sample_users=None, iters=None, warmup=None):
-    """The reference algorithm's CPU port (oracle/) on the host cores.  kind="port": the reference is
-    pure Python over /root/reference, which does not exist on the GPU box."""
-    from oracle import logpq_oracle as O
+def e2e_through_public_api(cfg, dev, flush, steps, warmup, W):
+    """The same metric through the user-facing call surface, nothing prepared outside the timed region:
+    `Problem.sample_from(samples).elbo_rws().backward()` on HOST tensors (pinned; two alternating sets of sample
+    buffers, as a data loader's double buffering would hand them over), so every step pays the per-call
+    canonicalisation (permute / cast), the plan-cache lookup, the H2D copies, the autograd wrapper, the D2H of the
+    log-evidence and of the gradients that autograd carries back to the host parameters."""
+    from alan_b200.problem import Problem
     from alan_b200.named import NT
+    P, Q, sample, ip, data, params = make_problem(cfg, 0, cfg["M"])
+    pin = lambda d: {k: NT(v.t.pin_memory(), v.axes) for k, v in d.items()}
+    par = {k: NT(v.t.clone().pin_memory().requires_grad_(True), v.axes) for k, v in ip.items() if k in params}
+    inp = pin({k: v for k, v in ip.items() if k not in params})
+    prob = Problem(P, Q, pin(data), inputs=inp, params=par, device=dev)
+    sets = [pin(sample), pin({k: NT(v.t.clone(), v.axes) for k, v in sample.items()})]
+    ev = [(t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    h2d = sum(v.t.numel() * v.t.element_size() for d in (sets[0], inp, par, prob.data) for v in d.values())
+    for i in range(warmup + steps):
+        k = i - warmup
+        for v in par.values():
+            v.t.grad = None
+        if k >= 0:
+            flush.fill_(1.0)
+            ev[k][0].record()
+        L = prob.sample_from(sets[i % 2]).elbo_rws()
+        L.backward()
+        lp = float(L)                                   # D2H of the log-evidence; the gradients are already on the host
+        if k >= 0:
+            ev[k][1].record()
+        t.cuda.synchronize()
+    ms = sum(s.elapsed_time(e) for s, e in ev) / steps
+    d2h = 4 + sum(v.t.grad.numel() * 4 for v in par.values())
+    return {"value": W / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "api": "Problem.sample_from(host samples).elbo_rws().backward(); float(lp); gradients in param.grad on the host",
+            "lp": lp}
+
+
+def roofline_report(run, comp, plan, tensors, flush, dev, clocks, steps):
+    from alan_b200 import runtime
+    out = {}
+    pk = peaks()
+    nprog = plan.n_fwd + plan.n_bwd
+    acc = {}
+    reps = max(3, min(steps, 10))
+    lp_d = t.empty((), dtype=comp.dtype, device=dev)
+    one = t.ones((), dtype=comp.dtype, device=dev)
+    gouts = [t.empty(plan.input_pts[n].shape, dtype=comp.dtype, device=dev) for n in plan.grad_inputs]
+    for rep in range(reps + 1):
+        flush.fill_(1.0)
+        for prog in range(nprog):
+            outs, aux = ([lp_d], []) if prog < plan.n_fwd else (gouts, [one])
+            ms = run.dp.profile(prog, tensors, outs, aux)
+            if rep == 0:
+                continue
+            for j, m in enumerate(ms):
+                acc[(prog, j)] = acc.get((prog, j), 0.0) + m / reps
+    t.cuda.synchronize()
+    if not acc:
+        return out
+    total = sum(acc.values())
+    (prog, j), top_ms = max(acc.items(), key=lambda kv: kv[1])
+    op = plan.programs[prog][j]
+    m = op_model(op, 4)
+    # Pipe peaks measured NOW, in this process, on this GPU (alan_b200_pipe_peak: 8 independent chains per thread,
+    # 2 x 1024 threads per SM, best of 5): lane-operations per second at whatever clock the GPU sustains.
+    mufu_peak = runtime.pipe_peak(0, dev)                                  # ex2 / s
+    fp32_peak = 2 * runtime.pipe_peak(1, dev) / 1e12                       # TFLOP/s (FMA = 2 flop)
+    clk = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
+    fan = m["kind"] in ("FanLseOp", "FanLseBwdOp")
+    tc_path = fan and comp.dtype == t.float32 and not os.environ.get("ALAN_B200_NO_TC")
+    hbm_frac = m["bytes"] / (top_ms * 1e-3) / 1e9 / pk["hbm_gbs"]
+    fp32_frac = m["flops"] / (top_ms * 1e-3) / 1e12 / fp32_peak
+    mufu_frac = m["points"] / (top_ms * 1e-3) / mufu_peak if fan else 0.0   # one ex2 per cell is the algorithmic minimum
+    # SURVEY.md §8(d): achieved = max(MUFU ops / MUFU peak, [FP32 flops / FP32 peak when the d-contraction is on the
+    # CUDA cores], HBM bytes / HBM peak) / t.  With the d-contraction on tcgen05 the binding unit is MUFU.
+    cands = {"hbm": hbm_frac, "mufu": mufu_frac}
+    if not tc_path:
+        cands["fp32"] = fp32_frac
+    bound = max(cands, key=cands.get)
+    if bound == "hbm":
+        roof = dict(bound="hbm", achieved=m["bytes"] / (top_ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s",
+                    peak_source=f"MEASURED_PEAKS.json ({pk['source']})")
+    elif bound == "mufu":
+        roof = dict(bound="mufu", achieved=m["points"] / (top_ms * 1e-3) / 1e9, peak=mufu_peak / 1e9, unit="Gex2/s",
+                    peak_source="alan_b200_pipe_peak(MUFU.EX2) measured in this process just now")
+    else:
+        roof = dict(bound="fp32", achieved=m["flops"] / (top_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
+                    peak_source="alan_b200_pipe_peak(FFMA) measured in this process just now")
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    kname = {"FanLseBwdOp": r"fan_lse_tc2_kernel<\d+, *(1|true)>", "FanLseOp": r"fan_lse_tc2_kernel<\d+, *(0|false)>",
+             "BernDotSumOp": r"bern_dot_sum"}.get(m["kind"])
+    traffic, capture = ncu_dram_traffic(kname) if (kname and tc_path and m["points"] == 270000000) else (None, None)
+    roof.update(traffic=traffic, traffic_source=capture, kernel=f"{m['kind']}:{m['tag']}", kernel_ms=top_ms,
+                share_of_step=top_ms / total, algorithmic_bytes=m["bytes"], algorithmic_flops=m["flops"],
+                algorithmic_ex2=m["points"] if fan else 0,
+                hbm_frac=hbm_frac, mufu_frac=mufu_frac, fp32_fma_frac=fp32_frac,
+                mufu_peak_gex2_s=mufu_peak / 1e9, mufu_peak_per_clk_sm=mufu_peak / 148 / (clk * 1e6),
+                fp32_peak_tflops=fp32_peak, sm_mhz_assumed_for_per_clk=clk,
+                timing="per-op CUDA events on the launch stream, separate profiled pass, mean of %d" % reps)
+    if tc_path:
+        from alan_b200.plan import dense_fan_geometry
+        fop = op if m["kind"] == "FanLseOp" else op.fwd
+        dense = None if os.environ.get("ALAN_B200_TC_BLOCKDIAG") else dense_fan_geometry(fop, 4)
+        tens = dict(achieved_tflops=m["flops"] / (top_ms * 1e-3) / 1e12, bf16_peak_tflops=pk["bf16_tflops"])
+        tens["frac_of_bf16_peak"] = tens["achieved_tflops"] / tens["bf16_peak_tflops"]
+        tens["path"] = ("tcgen05.mma kind::tf32, 3xTF32, dense expanded-square GEMM, (lam, f) on TMEM lanes"
+                        if dense is not None else "tcgen05.mma kind::tf32, 3xTF32, block-diagonal A in TMEM")
+        roof["tensor"] = tens
+    out["roofline"] = roof
+    tops = sorted(acc.items(), key=lambda kv: -kv[1])[:6]
+    out["top_ops"] = [dict(op=f"{op_model(plan.programs[p_][k], 4)['kind']}:{op_model(plan.programs[p_][k], 4)['tag']}",
+                           ms=round(v, 4)) for (p_, k), v in tops]
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+def _bounded_users(cfg, budget_s, n_steps, step_time_of):
+    """Users in the CPU sample: one 50-user probe step sets the scale so that `n_steps` steps fit `budget_s`."""
+    t50 = step_time_of(50)
+    users = int(50 * max(1.0, budget_s / max(n_steps, 1) / max(t50, 1e-3)))
+    users = max(50, min(cfg["M"], users // 50 * 50))
+    return users, t50
+
+
+def run_reference(args, cfg, iters=None, warmup=None, budget_s=100.0):
+    """The reference's CPU implementation of the path on the host cores, every thread it can use.
+
+    kind = "reference": the UNMODIFIED reference (alan) imported from baseline/_ref (its pip install; /root/reference/src
+    in the build container) -- `Problem.sample(K)` once, then per step `sample.elbo_rws(computation_strategy=Split(
+    'plate_1', 50)).backward()` on the same Sample, the way cfg-5 has to be run.
+    kind = "port": the oracle's restatement (oracle/logpq_oracle.py) where the reference is not importable.
+    Each step is a BOUNDED sample of the workload (the first `users` users; the cost is linear in users), sized by a
+    probe step so that the requested --steps/--warmup finish within ~`budget_s` seconds."""
     t.set_num_threads(os.cpu_count() or 1)
-    M = cfg["M"]
-    if sample_users is None:
-        sample_users = min(M, max(8, int(2.5e5 // (cfg["K"] ** 3 // 100 + cfg["N"] * 30))))
-        sample_users = min(M, 300 if cfg["N"] <= 5 else 60)
-    P, Q, sample, ip, data, params = make_problem(cfg, 0, sample_users)
-    sub = dict(cfg, M=sample_users)
-    W = cells(**sub)
     iters = iters or args.steps
     warmup = args.warmup if warmup is None else warmup
+    kind = "port"
+    try:
+        from oracle.refcompat import reference_available, import_reference
+        if reference_available() and not os.environ.get("ALAN_B200_REF_PORT"):
+            alan = import_reference()
+            kind = "reference"
+    except Exception as exc:                                   # noqa: BLE001
+        sys.stderr.write(f"reference not importable ({exc}); timing the oracle port\n")
+    import models
 
-    def step():
-        ipg = {k: NT(v.t.clone().requires_grad_() if k in params else v.t, v.axes) for k, v in ip.items()}
-        L = O.elbo(P, Q, sample, ipg, data)
-        t.autograd.grad(L, [ipg[k].t for k in params])
-        return L
+    def make_step(users):
+        P_, Q_, sample, ip, data, params = make_problem(cfg, 0, users)
+        if kind == "reference":
+            Pm, Qm = models.movielens_model(alan, d=cfg["d"])
+            nm = lambda v: v.t.refine_names(*v.axes, *([None] * (v.t.ndim - len(v.axes))))
+            sizes = {'plate_1': users, 'plate_2': cfg["N"]}
+            inputs = {'x': nm(ip['x'])}
+            bp = alan.BoundPlate(Pm, sizes, inputs=inputs)
+            bq = alan.BoundPlate(Qm, sizes, inputs=inputs, extra_opt_params={k: nm(ip[k]).clone() for k in params})
+            prob = alan.Problem(bp, bq, {'obs': nm(data['obs'])})
+            s = prob.sample(cfg["K"], reparam=False)
+            strat = alan.Split('plate_1', 50) if users > 50 else alan.checkpoint
+
+            def step():
+                prob.zero_grad()
+                L = s.elbo_rws(computation_strategy=strat)
+                L.backward()
+                return L.detach()
+            return step
+        from oracle import logpq_oracle as O
+        from alan_b200.named import NT
+
+        def step():
+            ipg = {k: NT(v.t.clone().requires_grad_() if k in params else v.t, v.axes) for k, v in ip.items()}
+            L = O.elbo(P_, Q_, sample, ipg, data, split=('plate_1', 50) if users > 50 else None, checkpoint=users > 50)
+            t.autograd.grad(L, [ipg[k].t for k in params])
+            return L.detach()
+        return step
+
+    def step_time_of(users):
+        st = make_step(users)
+        st()
+        t0 = time.time()
+        st()
+        return time.time() - t0
+    users, t50 = _bounded_users(cfg, budget_s, iters + warmup, step_time_of)
+    step = make_step(users)
     for _ in range(warmup):
         step()
     t0 = time.time()
     for _ in range(iters):
         L = step()
     dt = (time.time() - t0) / iters
-    return dict(value=W / dt, unit=UNIT, cores=t.get_num_threads(), kind="port",
-                sample=f"{sample_users} of {M} users (one Split chunk of plate_1), {iters} fwd+bwd after {warmup} warm-up, "
-                       f"{dt * 1e3:.1f} ms each", ms_per_step=dt * 1e3, lp=float(L))
+    W = cells(**dict(cfg, M=users))
+    how = ("reference alan: Sample.elbo_rws(Split('plate_1', 50)).backward()" if kind == "reference"
+           else "oracle port: elbo(split=('plate_1', 50), checkpoint=True) + autograd.grad")
+    return dict(value=W / dt, unit=UNIT, cores=t.get_num_threads(), kind=kind,
+                sample=f"first {users} of {cfg['M']} users (cost is linear in users), {how}, {iters} fwd+bwd after {warmup} "
+                       f"warm-up, {dt * 1e3:.1f} ms each",
+                ms_per_step=dt * 1e3, lp=float(L), users=users)
 
 
 def main():
@@ -433,11 +594,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=list(WORKLOADS))
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--chunks", type=int, default=1,
                     help="blocks of the user plate in the e2e (host buffer) path; >1 streams them through "
-                         "engine.StreamedRunner (measured slower on B200 today: per-block host work dominates)")
+                         "engine.StreamedRunner")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling run at N > 1")
     ap.add_argument("--device-only", action="store_true",
                     help="skip the e2e / cfg2 / cpu legs (short command for ncu launch lists)")
     args = ap.parse_args()
@@ -450,15 +612,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = min(args.steps, 5)
-        if args.scaling == "weak" and args.gpus > 1:          # same job description as the b200 arm at this N
-            cfg = dict(cfg, M=cfg["M"] * args.gpus, name=cfg["name"] + f"_x{args.gpus}_users")
-        r = run_reference(args, cfg, iters=steps, warmup=min(args.warmup, 1))
+        cfgN, config = config_for(cfg, args.gpus, args.scaling)       # same job description as the b200 arm at this N
+        r = run_reference(args, cfgN, iters=args.steps, warmup=args.warmup, budget_s=150.0)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": cfg["name"], "users": cfg["M"], "films": cfg["N"], "d": cfg["d"], "K": cfg["K"]},
+                "data": "synthetic", "config": config,
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -478,17 +637,21 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=t.device(f"cuda:{local_rank}"))
     line = run_b200(args, cfg, rank, world, local_rank)
+    if world > 1 and not args.no_weak:
+        other = "weak" if args.scaling == "strong" else "strong"
+        extra = run_b200(args, cfg, rank, world, local_rank, scaling=other, full_report=False, short=True)
+        line[other] = extra
     if rank == 0 and world == 1:
         if args.workload != "cfg2":
             small = run_b200(args, WORKLOADS["cfg2"], 0, 1, local_rank, full_report=True)
-            line["cfg2"] = {k: small[k] for k in ("value", "ms_per_step", "e2e", "gpu_launches", "config") if k in small}
+            line["cfg2"] = {k: small[k] for k in ("value", "ms_per_step", "e2e", "e2e_api", "gpu_launches", "config") if k in small}
             if "roofline" in small:
                 line["cfg2"]["roofline"] = small["roofline"]
         if not args.no_cpu_baseline:
-            r = run_reference(args, cfg, iters=3, warmup=1)
+            r = run_reference(args, cfg, iters=3, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
             if args.workload != "cfg2":
-                r2 = run_reference(args, WORKLOADS["cfg2"], iters=3, warmup=1)
+                r2 = run_reference(args, WORKLOADS["cfg2"], iters=3, warmup=1, budget_s=10.0)
                 line["cfg2"]["cpu_baseline"] = {k: r2[k] for k in ("value", "unit", "cores", "kind", "sample")}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)

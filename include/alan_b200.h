@@ -105,6 +105,12 @@ int alan_b200_gather(const void* x, const int64_t* idx, void* out, int elem_byte
                      int64_t N, int64_t outer, int64_t K, int64_t inner, int64_t outer_div,
                      void* stream);
 
+/* Measurement aid (bench.py roofline denominators, measured in the same process as the bench): sustained rate of one
+ * SM pipe over the whole GPU, in lane-operations per second.  which = 0: MUFU.EX2 (the unit that bounds the
+ * log-semiring contraction once its d-contraction runs on the tensor cores), 1: FFMA.
+ * `scratch` is device memory of at least 2 * 1024 * 4 bytes per SM.  Never on the timed path. */
+int alan_b200_pipe_peak(int which, void* scratch, size_t scratch_bytes, double* ops_per_s, void* stream);
+
 /* ---- unit-level ops, exported for the parity tests ---------- */
 
 /* out[o] = log(sum_r exp(x[o, r] - max_r) + eps) + max_r ; x is [n_out, n_red] row-major.

@@ -23,13 +23,43 @@ import os
 import sys
 import warnings
 
-REFERENCE_SRC = "/root/reference/src"
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Where the UNMODIFIED reference package can be imported from: its sources where they lie in the build container,
+# else the `pip install --target baseline/_ref /root/reference` copy that __graft_entry__.build() makes there
+# (git-ignored: never in history; not gpurun-ignored: it travels to the GPU box).
+_CANDIDATES = ["/root/reference/src", os.path.join(_ROOT, "baseline", "_ref")]
+REFERENCE_SRC = next((p for p in _CANDIDATES if os.path.isdir(os.path.join(p, "alan"))), _CANDIDATES[0])
 REFERENCE_TESTS = "/root/reference/tests"
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_SRC, "alan"))
+
+
+def install_reference(verbose=True) -> bool:
+    """`pip install --no-index --no-deps --target baseline/_ref` of the reference (from a /tmp copy: the source tree
+    is read-only and the build writes egg-info).  Build container only; returns False where /root/reference is absent."""
+    import shutil
+    import subprocess
+    import tempfile
+    src = "/root/reference"
+    if not os.path.isdir(os.path.join(src, "src", "alan")):
+        return False
+    target = os.path.join(_ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(target, "alan")):
+        return True
+    tmp = tempfile.mkdtemp(prefix="alan_ref_")
+    try:
+        shutil.copytree(src, os.path.join(tmp, "reference"))
+        cmd = [sys.executable, "-m", "pip", "install", "--no-index", "--no-build-isolation", "--no-deps",
+               "--find-links", "/opt/wheelhouse", "--target", target, os.path.join(tmp, "reference")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose:
+            print("reference install:", "ok" if r.returncode == 0 else r.stdout[-400:] + r.stderr[-400:])
+        return r.returncode == 0
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 _alan = None
@@ -41,7 +71,8 @@ def import_reference():
     if _alan is not None:
         return _alan
     if not reference_available():
-        raise RuntimeError("reference sources not present (expected only in the build container)")
+        raise RuntimeError("the reference is neither at /root/reference/src (build container) nor installed under "
+                           "baseline/_ref (run __graft_entry__.build() in the build container)")
     for p in (_SHIMS, REFERENCE_SRC):
         if p not in sys.path:
             sys.path.insert(0, p)

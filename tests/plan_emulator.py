@@ -354,3 +354,58 @@ class Emu:
             o, obase = self.buf(op.outs[k])
             o[obase:obase + pick.numel()] = (pick % ksz[k]).reshape(-1)
             pick = pick // ksz[k]
+
+
+class EmuRunner:
+    """TEST INFRASTRUCTURE ONLY: the surface of engine.Runner (device_inputs / forward_raw / backward_raw / elbo)
+    executed by the CPU emulator, so that the host-side glue above the C ABI (alan_adapter.B200, the Sample._elbo
+    hook, autograd wiring) can be exercised in the GPU-less build container.  Never imported by the product."""
+    def __init__(self, comp, device=None, process_group=None):
+        self.comp, self.dtype, self.device = comp, comp.dtype, t.device("cpu")
+        self.generation = 0
+        self.emu = None
+
+    def device_inputs(self, sample, inputs_params, data, extra_log_factors=None, differentiable=False):
+        comp = self.comp
+        src = {}
+        for d in (sample, inputs_params or {}, data or {}):
+            src.update(d)
+        elf = dict(extra_log_factors or {})
+        out = []
+        for name in comp.plan.input_names:
+            if name in comp.plan.const_inputs:
+                x = comp.plan.const_inputs[name]
+            elif name.startswith('__J'):
+                _, plates, pos = next(m for m in comp.moment_inputs if m[0] == name)
+                x = t.zeros([comp.sizes[a] for a in plates] + list(pos), dtype=self.dtype)
+            else:
+                key, role, orig, axes = next(o for o in comp.order if o[0] == name)
+                v = elf[orig] if role == 'elf' else src[orig]
+                x = v.order(axes).t.to(self.dtype).contiguous()
+                if not differentiable or name not in comp.grad_names:
+                    x = x.detach()
+            out.append(x)
+        return out
+
+    def forward_raw(self, tensors):
+        plan = self.comp.plan
+        self.generation += 1
+        lp = t.zeros(1, dtype=self.dtype)
+        self.emu = Emu(plan, [x.detach() for x in tensors], outputs={0: lp})
+        for seg in plan.programs[:plan.n_fwd]:
+            self.emu.run(seg)
+        return lp[0].clone()
+
+    def backward_raw(self, tensors, grad_lp=None):
+        plan = self.comp.plan
+        g = t.ones(1, dtype=self.dtype) if grad_lp is None else grad_lp.detach().reshape(1).to(self.dtype)
+        self.emu.outputs = {i: t.zeros(plan.input_pts[n].numel, dtype=self.dtype) for i, n in enumerate(plan.grad_inputs)}
+        self.emu.aux = {0: g}
+        with t.enable_grad():                  # the emulator evaluates adjoint ops with autograd on gathered operands
+            for seg in plan.programs[plan.n_fwd:plan.n_fwd + plan.n_bwd]:
+                self.emu.run(seg)
+        return {n: self.emu.outputs[i].detach().reshape(plan.input_pts[n].shape) for i, n in enumerate(plan.grad_inputs)}
+
+    def elbo(self, tensors):
+        from alan_b200.engine import _LogPQFunction
+        return _LogPQFunction.apply(self, *tensors)

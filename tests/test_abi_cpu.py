@@ -78,3 +78,18 @@ def test_structure_errors_mirror_reference():
     Q = M.Plate(b=M.Normal(0., 1.))
     with pytest.raises(Exception, match="same variables"):
         M.check_PQ(P, Q, set())
+
+
+def test_torch_custom_ops_are_registered_and_refuse_cpu_tensors():
+    """The boundary north_star names: torch.ops.alan_b200.* over the C ABI (alan_b200/ops.py).  CUDA dispatch key
+    only: handing them CPU tensors raises -- there is no CPU path behind the ops."""
+    import torch
+    from alan_b200 import ops
+    for name in ops.OPS:
+        assert hasattr(torch.ops.alan_b200, name), name
+    schema = str(torch.ops.alan_b200.logpq_bwd.default._schema)
+    assert "Tensor[] inputs" in schema and "grads" in schema and "ws" in schema
+    with pytest.raises(NotImplementedError):
+        torch.ops.alan_b200.gather(torch.zeros(2, 3, 4), torch.zeros(1, 2, dtype=torch.long), 2, 3, 4)
+    with pytest.raises(NotImplementedError):
+        torch.ops.alan_b200.logpq_fwd(0, 0, [torch.zeros(3)], torch.zeros(8, dtype=torch.uint8))

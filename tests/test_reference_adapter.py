@@ -56,3 +56,45 @@ def test_adapter_model_tree_roundtrip():
         assert Qm.groupvarnames() == mirror.groupvarnames()
         assert Qm.all_platenames() == mirror.all_platenames()
         assert Qm.varname2groupvarname() == mirror.varname2groupvarname()
+
+
+@pytest.mark.parametrize("case", ["cfg1_lglp", "cfg2_movielens", "cfg3_radon", "model1"])
+def test_b200_strategy_hook_on_live_reference_objects(case, monkeypatch):
+    """`alan_adapter.B200` + `install_hook` from a live reference `Problem.sample(K)`: log-evidence, parameter
+    gradients (through autograd into the reference's own named parameters), marginals and moments, with the plan
+    executed by the CPU emulator (tests/plan_emulator.EmuRunner stands in for engine.Runner here; the same test runs
+    the CUDA engine on the GPU box: tests/test_reference_gpu.py)."""
+    from oracle.refcompat import import_reference
+    from alan_b200 import alan_adapter as A, engine
+    from plan_emulator import EmuRunner
+    alan = import_reference()
+    from alan.utils import generic_dims, generic_order
+    monkeypatch.setattr(engine, "Runner", EmuRunner)
+    prob, K = _problem(alan, case)
+    moms, joints = models.CASES[case][4], models.CASES[case][5]
+    s = prob.sample(K, reparam=False)
+    params = dict(prob.Q._opt_params.to_dict())
+    ref = s.elbo_rws(computation_strategy=alan.no_checkpoint)
+    ref_g = t.autograd.grad(ref, list(params.values()), allow_unused=True)
+    ref_marg = s.marginals(joints=joints, computation_strategy=alan.no_checkpoint)
+    mlist = [((v,), alan.moments.RawMoment(models.MOMENT_FUNCS[f])) for v, f in moms]
+    ref_mom = s._moments_uniform_input(mlist)
+    remove = A.install_hook(alan)
+    try:
+        strat = A.B200()
+        L = s.elbo_rws(computation_strategy=strat)
+        assert rel_err(L.detach(), ref.detach()) < 1e-5
+        g = t.autograd.grad(L, list(params.values()), allow_unused=True)
+        for (n, _), a, b in zip(params.items(), g, ref_g):
+            if b is not None:
+                assert rel_err(a.rename(None), b.rename(None)) < 3e-4, n
+        marg = s.marginals(joints=joints, computation_strategy=strat)
+        for key, w in ref_marg.weights.items():
+            dims = generic_dims(w)
+            assert rel_err(generic_order(marg.weights[key], dims), generic_order(w, dims)) < 3e-4, key
+        mom = s._moments_uniform_input(mlist, computation_strategy=strat)
+        for a, b in zip(mom, ref_mom):
+            dims = generic_dims(b)
+            assert rel_err(generic_order(a, dims), generic_order(b, dims)) < 3e-4
+    finally:
+        remove()
