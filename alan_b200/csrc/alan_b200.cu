@@ -19,7 +19,7 @@
 
 enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
 enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
-       OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13 };
+       OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13, OP_XREDUCE = 14 };
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -51,6 +51,12 @@ struct alan_b200_plan {
     bool use_tc = true;            // fan_lse on tcgen05 where the shape allows (ALAN_B200_NO_TC=1 at plan creation: FFMA2 kernel)
     bool use_tc2 = true;           // dense formulation (fan_tc2.cuh) where the loc is independent of the value's axes
                                    // (ALAN_B200_TC_BLOCKDIAG=1 at plan creation: block-diagonal kernel only)
+    // cross-rank reductions inside programs (OP_XREDUCE): the ranks' symmetric buffers as mapped in this process and
+    // the byte offset of every reduction site in them (alan_b200_plan_set_comm / alan_b200_comm_bytes)
+    int comm_rank = 0, comm_world = 1;
+    char* comm_peer[AB_XR_MAXW] = {nullptr};
+    std::vector<size_t> site_off, site_elems;
+    size_t comm_bytes = 0;
     // graphs cannot be captured on / launched into the legacy default stream: calls that arrive on it are
     // forwarded to this private stream, ordered by a pair of events
     mutable cudaStream_t side = nullptr;
@@ -147,7 +153,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
         if (events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c.stream); events->push_back(e); }
         int code = r.i32();
         int nwords = r.i32();
-        const bool seqable = code == OP_FILL || code == OP_EXPR || code == OP_EXPR_BWD || code == OP_REDUCE;
+        const bool seqable = code == OP_FILL || code == OP_EXPR || code == OP_EXPR_BWD || code == OP_REDUCE || code == OP_XREDUCE;
         if (!seqable) flush();
         if (count_only && !seqable) {
             if (code == OP_CHAIN || code == OP_CHAIN_BWD) {
@@ -236,6 +242,10 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 p.cadd = (T)r.f64();
                 p.nsplit = r.i32();
                 int thread_hint = r.i32();
+                p.m_out = nullptr; p.lo_out = nullptr;
+                if (p.mode == R_LSE_EPS || p.mode == R_LSE) {
+                    if (r.i32()) { p.m_out = (T*)tref(r, c); p.lo_out = (T*)tref(r, c); }
+                }
                 read_dims(r, p.d, p.n_out, p.n_red);
                 p.nf = r.i32();
                 for (int f = 0; f < p.nf; ++f) {
@@ -243,10 +253,14 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                     read_opnd(r, c, p.f[f], p.d.nd, false);
                 }
                 if (p.mode == R_WSUM) {
-                    read_opnd(r, c, p.lse, p.d.nd, false);
+                    read_opnd(r, c, p.lse_m, p.d.nd, false);
+                    read_opnd(r, c, p.lse_lo, p.d.nd, false);
                     read_opnd(r, c, p.gout, p.d.nd, false);
                 }
-                if (batching && p.n_out * p.n_red <= AB_SEQ_POINTS) {
+                // small: few points, or a plain fixed-order sum of partial rows with few outputs (one thread per output
+                    // walks the rows: e.g. the 160 x 900 partial rows of the fused plate sum)
+                if (batching && (p.n_out * p.n_red <= AB_SEQ_POINTS ||
+                                 (p.mode == R_SUM && p.nsplit == 1 && p.n_out <= 1024 && p.n_out * p.n_red <= 64 * AB_SEQ_POINTS))) {
                     if (seq.n == AB_SEQ_MAX) flush();
                     SeqOp<T>& o = seq.op[seq.n++];
                     o.kind = SK_REDUCE; o.warp = reduce_uses_warps(p, thread_hint != 0) ? 1 : 0; o.r = p;
@@ -255,6 +269,25 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 flush();
                 if (count_only) { ++nl; break; }
                 launch_reduce<T>(p, thread_hint != 0, c.stream, c.sm_count);
+                break;
+            }
+            case OP_XREDUCE: {
+                XReduceParams<T> x;
+                memset(&x, 0, sizeof(x));
+                const int site = r.i32();
+                x.n_pieces = r.i32();
+                for (int q = 0; q < x.n_pieces; ++q) { x.piece[q] = (T*)tref(r, c); x.piece_n[q] = r.i64v(); x.n_total += x.piece_n[q]; }
+                if (count_only) { if (!batching) ++nl; else { if (seq.n == AB_SEQ_MAX) flush(); seq.n++; } break; }
+                if (plan->comm_world < 2 || !plan->comm_peer[0])
+                    return fail("this plan reduces across ranks inside its programs (fused collectives): call "
+                                "alan_b200_plan_set_comm with the ranks' symmetric buffers first");
+                if (site < 0 || site >= (int)plan->site_off.size()) return fail("xreduce: unknown site");
+                x.rank = plan->comm_rank; x.world = plan->comm_world;
+                for (int q = 0; q < x.world; ++q) x.site[q] = plan->comm_peer[q] + plan->site_off[site];
+                if (seq.n == AB_SEQ_MAX) flush();
+                SeqOp<T>& o = seq.op[seq.n++];
+                o.kind = SK_XREDUCE; o.warp = 0; o.x = x;
+                if (!batching) flush();
                 break;
             }
             case OP_CHAIN: {
@@ -550,6 +583,33 @@ int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** 
         p->prog_nops.push_back(blob[10 + 2 * i + 1]);
         if ((size_t)p->prog_start.back() > n_words) { delete p; return fail("plan blob: program offset out of range"); }
     }
+    // cross-rank reduction sites: header + two data buffers each, 256-byte aligned
+    for (int i = 0; i < p->n_programs; ++i) {
+        const int32_t* q = blob + p->prog_start[i];
+        for (int k = 0; k < p->prog_nops[i]; ++k) {
+            if ((size_t)(q - blob) + 2 > n_words || q[1] < 2) { delete p; return fail("plan blob: malformed op table"); }
+            if (q[0] == OP_XREDUCE) {
+                const int site = q[2], np = q[3];
+                size_t n = 0;
+                for (int j = 0; j < np; ++j) {
+                    const int32_t* w = q + 4 + 5 * j + 3;                       // tref = 3 words, then the 64-bit count
+                    n += (size_t)(((uint64_t)(uint32_t)w[1] << 32) | (uint32_t)w[0]);
+                }
+                if (site >= (int)p->site_elems.size()) p->site_elems.resize(site + 1, 0);
+                if (n > p->site_elems[site]) p->site_elems[site] = n;
+            }
+            q += q[1];
+        }
+    }
+    {
+        const size_t item = p->dtype == 0 ? 4 : 8;
+        size_t off = 0;
+        for (size_t sgl = 0; sgl < p->site_elems.size(); ++sgl) {
+            p->site_off.push_back(off);
+            off += AB_XR_HDR + ((2 * p->site_elems[sgl] * item + 255) / 256) * 256;
+        }
+        p->comm_bytes = off;
+    }
     p->graphs.resize(p->n_programs);
     p->n_out.assign(p->n_programs, -1);
     p->n_aux.assign(p->n_programs, -1);
@@ -568,9 +628,10 @@ int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** 
     p->miss_streak.assign(p->n_programs, 0);
     p->use_tc = getenv("ALAN_B200_NO_TC") == nullptr;
     p->use_tc2 = getenv("ALAN_B200_TC_BLOCKDIAG") == nullptr;
-    // Opt-in: halves the launch count of a step, but measured on B200 the device time does not move (the small ops
-    // are bound by the latency of their own dependent instruction chains, not by launch overhead).
-    p->use_seq = getenv("ALAN_B200_SEQ") != nullptr;
+    // Consecutive small ops of a program run as ONE single-CTA launch (small_seq_kernel): a plate tree has dozens of
+    // ops over a few hundred points (global latents, top-level contractions, their adjoints) whose launches, not
+    // their arithmetic, are what a step of a small or strongly sharded problem pays for.  ALAN_B200_SEQ=0: one launch per op.
+    { const char* sq = getenv("ALAN_B200_SEQ"); p->use_seq = !(sq && sq[0] == '0'); }
     int dev = 0;
     p->sm_count = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) {
@@ -584,6 +645,23 @@ int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** 
 }
 
 void alan_b200_plan_destroy(alan_b200_plan* p) { delete p; }
+
+size_t alan_b200_comm_bytes(const alan_b200_plan* p) { return p->comm_bytes; }
+
+int alan_b200_plan_set_comm(alan_b200_plan* p, int rank, int world, void* const* peer_buffers, size_t bytes) {
+    if (!p) return fail("null plan");
+    if (world < 1 || world > AB_XR_MAXW) return fail("set_comm: between 1 and 8 ranks");
+    if (rank < 0 || rank >= world) return fail("set_comm: rank out of range");
+    if (bytes < p->comm_bytes) return fail("set_comm: symmetric buffers are smaller than alan_b200_comm_bytes(plan)");
+    std::lock_guard<std::mutex> g(p->mu);
+    p->comm_rank = rank; p->comm_world = world;
+    for (int r = 0; r < world; ++r) {
+        if (!peer_buffers[r]) return fail("set_comm: null peer buffer");
+        p->comm_peer[r] = (char*)peer_buffers[r];
+    }
+    for (auto& v : p->graphs) { for (auto& ge : v) cudaGraphExecDestroy(ge.exec); v.clear(); }     // captured pointers are stale
+    return 0;
+}
 size_t alan_b200_workspace_bytes(const alan_b200_plan* p) { return p->ws_bytes; }
 int alan_b200_num_inputs(const alan_b200_plan* p) { return p->n_inputs; }
 int alan_b200_num_programs(const alan_b200_plan* p) { return p->n_programs; }

@@ -594,6 +594,9 @@ static bool fan_lse_tc2_supported(const FanLseParams<float>& p, int D, bool bwd)
     const i64 FP = L * p.F, NG = (FP + T2_TILES * 128 - 1) / (T2_TILES * 128);
     const i64 n_u = p.n_rho / L;
     if (!bwd && p.psum_rows > 0 && p.psum_rows < NG) return false;
+    // the adjoint writes one partial per fan group: only the planner-committed compact gS layout [users, NG, kappa]
+    // is covered completely (nothing zero-fills adjoint tensors any more: plan.py build_backward)
+    if (bwd && p.gs_compact == 0) return false;
     if (FP < 96 || NG > T2_MAXG || (bwd && NG > L) || (bwd && p.gs_compact > 0 && p.gs_compact != NG) || p.Kk > 32 || n_u < 16 || p.nb > TC_NB) return false;
     if (p.rd.nd - (lam >= 0 ? 1 : 0) > T2_ND) return false;
     const i64 lim = (i64)1 << 31;

@@ -316,7 +316,8 @@ struct ReduceParams {
     int nf;
     Opnd f[AB_MAXL];
     T coeff[AB_MAXL];
-    Opnd lse, gout;         // WSUM only
+    Opnd lse_m, lse_lo, gout;   // WSUM only: (max, log(sum + eps)) of the forward LSE and the adjoint of its output
+    T* m_out; T* lo_out;        // LSE modes, optional: the pair the adjoint needs (null when nothing differentiates the op)
     T* out;
     int acc;
     T scale, cadd;
@@ -369,6 +370,14 @@ __device__ __forceinline__ T factor_sum(const ReduceParams<T>& p, const i64* bas
     return s;
 }
 
+// LSE result from (max m, shifted sum a); also stores the pair (m, lo) when the op is differentiated
+template <typename T>
+__device__ __forceinline__ T lse_finish(const ReduceParams<T>& p, i64 o, T m, T a, bool writer) {
+    const T lo = p.mode == R_LSE_EPS ? ab_log(a + Eps<T>::v()) : ab_log(a);
+    if (writer && p.m_out != nullptr) { p.m_out[o] = m; p.lo_out[o] = lo; }
+    return lo + m;
+}
+
 template <typename T>
 __device__ __forceinline__ void reduce_store(const ReduceParams<T>& p, i64 o, int s, T res) {
     if (p.nsplit > 1) { p.out[(i64)s * p.n_out + o] = res; return; }
@@ -399,13 +408,15 @@ __device__ __forceinline__ void reduce_warp_body(const ReduceParams<T>& p, const
             for (i64 j = lo + lane; j < hi; j += 32) a += factor_sum<T, NRED>(p, base, j);
             res = warp_sum(a);
         } else if (p.mode == R_WSUM) {
-            i64 lbase = dot_stride(p.lse, idx, 0, p.d.n_a), gbase = dot_stride(p.gout, idx, 0, p.d.n_a);
+            i64 mbase = dot_stride(p.lse_m, idx, 0, p.d.n_a), lbase = dot_stride(p.lse_lo, idx, 0, p.d.n_a),
+                gbase = dot_stride(p.gout, idx, 0, p.d.n_a);
             T a = T(0);
             for (i64 j = lo + lane; j < hi; j += 32) {
                 T sv = factor_sum<T, NRED>(p, base, j);
-                T l = ((const T*)p.lse.ptr)[lbase + red_off<NRED>(p.d, p.lse, j)];
+                T mm = ((const T*)p.lse_m.ptr)[mbase + red_off<NRED>(p.d, p.lse_m, j)];
+                T l = ((const T*)p.lse_lo.ptr)[lbase + red_off<NRED>(p.d, p.lse_lo, j)];
                 T g = ((const T*)p.gout.ptr)[gbase + red_off<NRED>(p.d, p.gout, j)];
-                a += g * ab_exp(sv + p.cadd - l);
+                a += g * ab_exp((sv - mm) - l);          // softmax weight exp(s - m) / (sum + eps), as autograd forms it
             }
             res = warp_sum(a);
         } else if (hi - lo <= 128) {
@@ -422,7 +433,7 @@ __device__ __forceinline__ void reduce_warp_body(const ReduceParams<T>& p, const
 #pragma unroll
             for (int q = 0; q < 4; ++q) a += (lo + lane + 32 * q < hi) ? ab_exp(v[q] - m) : T(0);
             a = warp_sum(a);
-            res = (p.mode == R_LSE_EPS ? ab_log(a + Eps<T>::v()) : ab_log(a)) + m;
+            res = lse_finish(p, o, m, a, lane == 0);
         } else {
             T m = neg_inf<T>();
             for (i64 j = lo + lane; j < hi; j += 32) m = ab_max(m, factor_sum<T, NRED>(p, base, j));
@@ -430,7 +441,7 @@ __device__ __forceinline__ void reduce_warp_body(const ReduceParams<T>& p, const
             T a = T(0);
             for (i64 j = lo + lane; j < hi; j += 32) a += ab_exp(factor_sum<T, NRED>(p, base, j) - m);
             a = warp_sum(a);
-            res = (p.mode == R_LSE_EPS ? ab_log(a + Eps<T>::v()) : ab_log(a)) + m;
+            res = lse_finish(p, o, m, a, lane == 0);
         }
         if (lane == 0) reduce_store(p, o, s, res);
     }
@@ -460,13 +471,15 @@ __device__ __forceinline__ void reduce_thread_body(const ReduceParams<T>& p, con
             for (i64 j = lo; j < hi; ++j) a += factor_sum<T, NRED>(p, base, j);
             res = a;
         } else if (p.mode == R_WSUM) {
-            i64 lbase = dot_stride(p.lse, idx, 0, p.d.n_a), gbase = dot_stride(p.gout, idx, 0, p.d.n_a);
+            i64 mbase = dot_stride(p.lse_m, idx, 0, p.d.n_a), lbase = dot_stride(p.lse_lo, idx, 0, p.d.n_a),
+                gbase = dot_stride(p.gout, idx, 0, p.d.n_a);
             T a = T(0);
             for (i64 j = lo; j < hi; ++j) {
                 T sv = factor_sum<T, NRED>(p, base, j);
-                T l = ((const T*)p.lse.ptr)[lbase + red_off<NRED>(p.d, p.lse, j)];
+                T mm = ((const T*)p.lse_m.ptr)[mbase + red_off<NRED>(p.d, p.lse_m, j)];
+                T l = ((const T*)p.lse_lo.ptr)[lbase + red_off<NRED>(p.d, p.lse_lo, j)];
                 T g = ((const T*)p.gout.ptr)[gbase + red_off<NRED>(p.d, p.gout, j)];
-                a += g * ab_exp(sv + p.cadd - l);
+                a += g * ab_exp((sv - mm) - l);
             }
             res = a;
         } else {
@@ -474,7 +487,7 @@ __device__ __forceinline__ void reduce_thread_body(const ReduceParams<T>& p, con
             for (i64 j = lo; j < hi; ++j) m = ab_max(m, factor_sum<T, NRED>(p, base, j));
             T a = T(0);
             for (i64 j = lo; j < hi; ++j) a += ab_exp(factor_sum<T, NRED>(p, base, j) - m);
-            res = (p.mode == R_LSE_EPS ? ab_log(a + Eps<T>::v()) : ab_log(a)) + m;
+            res = lse_finish(p, o, m, a, true);
         }
         reduce_store(p, o, s, res);
     }
@@ -514,6 +527,79 @@ static void launch_reduce(const ReduceParams<T>& p, bool thread_hint, cudaStream
 }
 
 // ------------------------------------------------------------------------------------------
+// C1: cross-rank sum of small tensors over NVLink peer memory, inside the program (no host-issued collective).
+// Every rank owns one symmetric buffer, mapped into every other rank's address space (peer[r]).  Per site:
+//     header  { u32 epoch (local use only); u32 flags[8] (flags[r] is written by rank r) }          256 bytes
+//     data    2 x n_total elements (double-buffered by epoch parity)
+// One call = pack my pieces into data[e & 1] of MY buffer; fence; write e into flags[me] of EVERY rank's header;
+// wait until all of my flags reached e; add all ranks' packs IN RANK ORDER (bit-identical sums on every rank) and
+// unpack in place.  A rank can be at most one epoch ahead of a peer (it cannot pass barrier e + 1 before the peer
+// has signalled e + 1, which the peer does after it has finished reading epoch e), so two data buffers suffice.
+// Remote data is read with volatile loads (peer lines may sit in the local L1); the wait is a bounded spin that
+// traps instead of hanging the GPU if a peer never arrives.  The message is a few KB: what matters is latency
+// (two NVLink traversals), not bandwidth.  reference analogue: `prev_lpq + lp` over Split chunks (logpq.py:151-153).
+// ------------------------------------------------------------------------------------------
+#define AB_XR_MAXW 8
+#define AB_XR_MAXP 16
+#define AB_XR_HDR 256
+template <typename T>
+struct XReduceParams {
+    int rank, world, n_pieces;
+    i64 n_total;
+    char* site[AB_XR_MAXW];               // this site's region in every rank's symmetric buffer (header, then data)
+    T* piece[AB_XR_MAXP];
+    i64 piece_n[AB_XR_MAXP];
+};
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void xreduce_body(const XReduceParams<T>& p, const i64 t0, const i64 tn) {
+    __shared__ unsigned s_epoch;
+    unsigned* my_hdr = reinterpret_cast<unsigned*>(p.site[p.rank]);
+    if (t0 == 0) s_epoch = my_hdr[0] + 1u;
+    __syncthreads();
+    const unsigned e = s_epoch;
+    const i64 buf = (i64)(e & 1u) * p.n_total;
+    T* mine = reinterpret_cast<T*>(p.site[p.rank] + AB_XR_HDR) + buf;
+    i64 off = 0;
+    for (int q = 0; q < p.n_pieces; ++q) {
+        for (i64 i = t0; i < p.piece_n[q]; i += tn) mine[off + i] = p.piece[q][i];
+        off += p.piece_n[q];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t0 < p.world) {
+        st_release_sys_u32(reinterpret_cast<unsigned*>(p.site[t0]) + 1 + p.rank, e);       // "rank me has published epoch e"
+        const unsigned* f = my_hdr + 1 + t0;
+        const long long c0 = clock64();
+        while ((int)(ld_acquire_sys_u32(f) - e) < 0) {
+            if (clock64() - c0 > (1LL << 33)) __trap();                                   // a peer never arrived (~4 s)
+        }
+    }
+    __syncthreads();
+    off = 0;
+    for (int q = 0; q < p.n_pieces; ++q) {
+        for (i64 i = t0; i < p.piece_n[q]; i += tn) {
+            T a = T(0);
+            for (int r = 0; r < p.world; ++r)
+                a += *reinterpret_cast<const volatile T*>(reinterpret_cast<const T*>(p.site[r] + AB_XR_HDR) + buf + off + i);
+            p.piece[q][i] = a;
+        }
+        off += p.piece_n[q];
+    }
+    __syncthreads();
+    if (t0 == 0) my_hdr[0] = e;
+}
+
+// ------------------------------------------------------------------------------------------
 // Small-op sequences.  A plate tree has dozens of ops whose whole iteration space is a few thousand
 // points (global latents, top-level contractions, their adjoints): as separate launches each costs a
 // launch latency plus a drain, several microseconds for nanoseconds of work.  Consecutive small ops of
@@ -521,9 +607,9 @@ static void launch_reduce(const ReduceParams<T>& p, bool thread_hint, cudaStream
 // __syncthreads() between ops (same CTA, so global-memory results of one op are visible to the next).
 // The op bodies are the very same device functions the stand-alone kernels call.
 // ------------------------------------------------------------------------------------------
-enum { SK_EXPR = 0, SK_EXPR_BWD = 1, SK_REDUCE = 2, SK_FILL = 3 };
+enum { SK_EXPR = 0, SK_EXPR_BWD = 1, SK_REDUCE = 2, SK_FILL = 3, SK_XREDUCE = 4 };
 #define AB_SEQ_MAX 16
-#define AB_SEQ_POINTS 2048        // an op is "small" when its iteration space has at most this many points
+#define AB_SEQ_POINTS 4096        // an op is "small" when its iteration space has at most this many points
 
 template <typename T>
 struct SeqOp {
@@ -534,6 +620,7 @@ struct SeqOp {
         ExprParams<T> e;
         ExprBwdParams<T> b;
         ReduceParams<T> r;
+        XReduceParams<T> x;
         struct { void* ptr; i64 nbytes; } f;
     };
     __host__ __device__ SeqOp() {}
@@ -545,6 +632,8 @@ struct SeqParams {
     SeqOp<T> op[AB_SEQ_MAX];
     __host__ __device__ SeqParams() : n(0) {}
 };
+
+static_assert(sizeof(SeqParams<double>) <= 32000, "SeqParams travels as a kernel parameter (32 764-byte limit)");
 
 template <typename T>
 __global__ void __launch_bounds__(1024) small_seq_kernel(const __grid_constant__ SeqParams<T> sp) {
@@ -568,6 +657,10 @@ __global__ void __launch_bounds__(1024) small_seq_kernel(const __grid_constant__
                 for (i64 k = t0; k < o.f.nbytes / 4; k += tn) w[k] = 0u;
                 break;
             }
+            case SK_XREDUCE:
+                __threadfence();                                        // earlier ops' results (other CTAs' writes were
+                xreduce_body<T>(o.x, t0, tn);                           // completed by the launch boundary) -> pack
+                break;
         }
         __syncthreads();
     }

@@ -36,7 +36,7 @@ class Compiled:
     """Plan + the canonical (contiguous, canonical axis order, working dtype) input list."""
     def __init__(self, P: Plate, Q: Plate, sample, inputs_params, data, extra_log_factors=None,
                  moment_specs=(), grad_names=(), N=None, shard_plate=None, world_size=1, dtype=None,
-                 fast_paths=True):
+                 fast_paths=True, fused_collectives=False):
         sample, inputs_params, data = dict(sample), dict(inputs_params or {}), dict(data or {})
         elf = dict(extra_log_factors or {})
         check_PQ(P, Q, set(data.keys()))
@@ -69,7 +69,8 @@ class Compiled:
             if role == 'elf':
                 self.elf_keys[orig] = key
         planner = Planner(P, Q, sig, sizes, self.dtype, want_sample_N=N, shard_plate=shard_plate,
-                          world_size=world_size, fast_paths=fast_paths)
+                          world_size=world_size, fast_paths=fast_paths,
+                          fused_collectives=fused_collectives and world_size > 1 and N is None)
         for orig, key in self.elf_keys.items():
             s = sig[key]
             extra.append((orig, Expr.leaf(planner.inputs[key], s.axes, s.pos_shape)))
@@ -160,6 +161,9 @@ class Runner:
         self.pg = process_group
         self.lp = torch.zeros((), dtype=self.dtype, device=self.device)
         self.generation = 0          # bumped by every forward: identifies whose intermediates the workspace holds
+        if comp.plan.fused_collectives:
+            # the cross-rank sums run inside the programs over NVLink peer memory: map the ranks' symmetric buffers
+            self.dp.attach_symmetric(process_group)
 
     # ---- raw calls on canonical device tensors ------------------------------------------
     def forward_raw(self, tensors):
@@ -185,7 +189,7 @@ class Runner:
         grad_lp = grad_lp.to(self.dtype).contiguous()
         import torch.distributed as dist
         sharded = bool(plan.global_grads) and dist.is_available() and dist.is_initialized() \
-            and dist.get_world_size(self.pg) > 1
+            and dist.get_world_size(self.pg) > 1 and not plan.fused_collectives
         flat, views = None, {}
         if sharded:
             # the global-parameter gradients live side by side in ONE buffer (slices aligned to 16 bytes), so the

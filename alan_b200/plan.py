@@ -34,7 +34,7 @@ MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
 SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
 OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY, OP_DOT, \
-    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD = range(1, 14)
+    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE = range(1, 15)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
 
@@ -289,6 +289,26 @@ class FillRegionOp(FillOp):
         return hi - lo
 
 
+class XReduceOp(Op):
+    """In-program cross-rank sum of small tensors over NVLink peer memory (csrc/kernels.cuh xreduce_body): the
+    pieces are packed into this rank's symmetric buffer, the ranks exchange one flag each, every rank adds all
+    ranks' packs IN RANK ORDER (bit-identical results everywhere) and unpacks in place.  Replaces the host-issued
+    ncclAllReduce between program segments: the message is a few KB, i.e. pure latency."""
+    code = OP_XREDUCE
+    autodiff_as = 'skip'          # adjoint of (sum over ranks) w.r.t. the local partial = the replicated upstream adjoint
+
+    def __init__(self, site, pieces):
+        self.site, self.pieces = site, list(pieces)
+        if len(self.pieces) > 16:
+            raise Exception("more than 16 tensors in one cross-rank reduction")
+        self.out = self.pieces[0]
+
+    def payload(self, w):
+        w.i32(self.site); w.i32(len(self.pieces))
+        for pt in self.pieces:
+            w.tref(pt); w.i64(pt.numel)
+
+
 class ExprOp(Op):
     """out[keep] (+)= scale * sum_red VM(leaves)   (csrc/kernels.cuh expr_fwd_kernel)"""
     code = OP_EXPR
@@ -354,17 +374,27 @@ class ReduceOp(Op):
         self.thread_hint = _outputs_contiguous(factors, od, rd) if thread_hint is None else thread_hint
         self.acc, self.scale, self.cadd, self.nsplit = acc, scale, cadd, nsplit
         self.lse, self.gout, self.lse_dims, self.gout_dims, self.tag = lse, gout, lse_dims, gout_dims, tag
+        # LSE modes whose output is differentiated also store the pair (m, lo) = (max, log(sum exp(s - m) + eps)): the
+        # adjoint forms the softmax weight as exp((s - m) - lo), like autograd does for the reference, instead of
+        # exp(s - lse) with lse = m + lo ROUNDED to the working precision -- at |lse| ~ 4e5 (cfg-5's top level) that
+        # rounding alone is 3e-2 absolute, a 1.5 % error common to every weight.  WSUM: `lse` = (m PT, lo PT).
+        self.m_out = self.lo_out = None
 
     def payload(self, w):
         w.i32(self.mode); w.tref(self.out); w.i32(self.acc); w.f64(self.scale); w.f64(self.cadd); w.i32(self.nsplit)
         w.i32(1 if self.thread_hint else 0)
+        if self.mode in (R_LSE_EPS, R_LSE):
+            w.i32(1 if self.m_out is not None else 0)
+            if self.m_out is not None:
+                w.tref(self.m_out); w.tref(self.lo_out)
         dims = self.od + self.rd
         if len(self.factors) > MAXL:
             raise Exception("contraction step joins more than 10 factor tensors")
         strides = [[lf.stride(d) for d in dims] for lf, _ in self.factors]
         extra = []
         if self.mode == R_WSUM:
-            extra = [(self.lse, self.lse_dims), (self.gout, self.gout_dims)]
+            m_pt, lo_pt = self.lse
+            extra = [(m_pt, self.lse_dims), (lo_pt, self.lse_dims), (self.gout, self.gout_dims)]
             strides += [_strides_like(pt, own, dims) for pt, own in extra]
         sizes, n_a, strides, _ = _coalesce([d[2] for d in dims], len(self.od), strides)
         _write_dims(w, sizes, n_a)
@@ -685,6 +715,7 @@ class Plan:
         self.N = None
         self.canon_axes = None
         self.allreduce = None        # (PT of the tile, n elements) for plate sharding
+        self.fused_collectives = False   # True: the cross-rank sums are XReduceOps inside the programs
         self.global_grads = []       # grads that must be all-reduced across shards
         self.blob = None
         self.retained = {}           # debugging: name -> PT of interesting intermediates
@@ -734,7 +765,8 @@ class Plan:
 # ----------------------------------------------------------------------------------------
 class Planner:
     def __init__(self, P: Plate, Q: Plate, sig: dict, sizes: dict, dtype, extra_factors=(), want_sample_N=None,
-                 shard_plate=None, world_size=1, constants=None, fast_paths=True, grad_names=()):
+                 shard_plate=None, world_size=1, constants=None, fast_paths=True, grad_names=(),
+                 fused_collectives=False):
         """sig: name -> TensorSig for samples, inputs/params, data and tensor-valued extra factors.
         sizes: axis name -> extent (plates and K axes).
         extra_factors: [(key, Expr)] expressions over input leaves, added as log factors at the plate
@@ -745,9 +777,14 @@ class Planner:
         self.N = want_sample_N
         self.fast_paths = fast_paths
         self.shard_plate, self.world_size = shard_plate, world_size
+        # fused_collectives: the cross-rank sums are ops INSIDE the programs (XReduceOp over symmetric memory) instead
+        # of host-issued all-reduces between program segments: a sharded plan then has one forward and one backward
+        # program like an unsharded one
+        self.fused_collectives = bool(fused_collectives) and shard_plate is not None
         self.plan = Plan()
         self.plan.dtype = dtype
         self.plan.sizes = self.sizes
+        self.plan.fused_collectives = self.fused_collectives
         self.all_plates = P.all_platenames()
         self.groups = Q.groupvarnames()
         self.v2g = Q.varname2groupvarname()
@@ -828,6 +865,9 @@ class Planner:
         if not isinstance(getattr(op, 'autodiff_as', None), str):
             if any(p.id in self.needs for p in self.op_inputs(op)):
                 self.needs.add(op.out.id)
+                if isinstance(op, ReduceOp) and op.mode in (R_LSE_EPS, R_LSE) and op.m_out is None:
+                    op.m_out = self.ws(op.out.axes, op.out.pos_shape, name='lse_m')
+                    op.lo_out = self.ws(op.out.axes, op.out.pos_shape, name='lse_lo')
 
     # -- allocation -------------------------------------------------------------------
     def _add_input(self, name, axes, pos_shape):
@@ -1261,8 +1301,11 @@ class Planner:
             self.emit(ReduceOp(R_SUM, out, od, rd, lf.tensors, cadd=lf.const * n, tag=f'plate_sum:{plate}'))
         if plate == self.shard_plate:
             self.plan.allreduce = out
-            self.fwd_segments.append(self.fwd)
-            self.fwd = []
+            if self.fused_collectives:
+                self.fwd.append(XReduceOp(0, [out]))
+            else:
+                self.fwd_segments.append(self.fwd)
+                self.fwd = []
         return LogicalFactor([(plain(out), 1.0)], 0.0, out_axes)
 
     def _fan_for_plate_sum(self, lf, od, rd):
@@ -1502,7 +1545,7 @@ class Planner:
                         mode, facs, kw = R_SUM, [(_OwnDims(gout, op.od), 1.0)], {}
                     else:
                         mode, facs = R_WSUM, op.factors
-                        kw = dict(lse=op.out, gout=gout, lse_dims=op.od, gout_dims=op.od, cadd=op.cadd)
+                        kw = dict(lse=(op.m_out, op.lo_out), gout=gout, lse_dims=op.od, gout_dims=op.od, cadd=op.cadd)
                     if nsplit > 1:
                         part = self.ws_raw(nsplit * n_kept, name='partial_adj')
                         out_list.append(ReduceOp(mode, part, kept, loop, facs, nsplit=nsplit, **kw))
@@ -1550,13 +1593,27 @@ class Planner:
                     gms = adjoint(op.ms)
                     glevels = self.ws_raw(op.levels.numel, name='chain_glevels')
                     out_list.append(ChainBwdOp(op, gout, glevels, gms))
-        # zero the adjoint region and the gradient outputs, then run the reversed ops
-        head = [FillRegionOp(plan)]
-        for n, g in grad_out.items():
-            head.append(FillOp(g, g.numel * self.itemsize))
+        # No zero-fill pass: every adjoint tensor is covered completely by each op that contributes to it (checked
+        # above: "does not cover the tensor"), so its FIRST contribution -- first in execution order -- overwrites
+        # (acc = 0) and only the later ones accumulate.  Gradient outputs that receive no contribution at all
+        # (a parameter the log-evidence does not depend on) are the only tensors still zeroed explicitly.
+        written = set()
+        for seg in segs:
+            for o in seg:
+                dest = o.gleaf if isinstance(o, ExprBwdOp) else getattr(o, 'out', None)
+                if dest is None or not isinstance(o, (ExprBwdOp, ReduceOp, ExprOp)):
+                    continue
+                if o.acc and dest.id not in written and not (isinstance(o, (ExprBwdOp, ReduceOp)) and o.nsplit > 1):
+                    o.acc = 0
+                written.add(dest.id)
+        head = [FillOp(g, g.numel * self.itemsize) for n, g in grad_out.items() if g.id not in written]
         segs[0] = head + segs[0]
         if self.shard_plate is not None:
             plan.global_grads = [n for n in grad_names if self.shard_plate not in self.inputs[n].axes]
+            if self.fused_collectives and plan.global_grads:
+                pieces = [grad_out[n] for n in plan.global_grads]
+                for k in range(0, len(pieces), 16):
+                    segs[-1].append(XReduceOp(1 + k // 16, pieces[k:k + 16]))
         return segs
 
     def _fan_backward(self, op, fan, gout, out_list, adjoint, needs, contribution_scale):

@@ -27,6 +27,7 @@ EXPORTS = [
     "alan_b200_program_launches", "alan_b200_run", "alan_b200_profile", "alan_b200_logpq_fwd", "alan_b200_logpq_bwd",
     "alan_b200_resample", "alan_b200_gather", "alan_b200_lse_eps", "alan_b200_chain_scratch_elems",
     "alan_b200_logmmexp_chain", "alan_b200_normal_logpdf_bcast", "alan_b200_pipe_peak",
+    "alan_b200_comm_bytes", "alan_b200_plan_set_comm",
 ]
 
 
@@ -82,6 +83,9 @@ def lib():
     L.alan_b200_plan_destroy.argtypes = [vp]
     L.alan_b200_workspace_bytes.argtypes = [vp]
     L.alan_b200_workspace_bytes.restype = ctypes.c_size_t
+    L.alan_b200_comm_bytes.argtypes = [vp]
+    L.alan_b200_comm_bytes.restype = ctypes.c_size_t
+    L.alan_b200_plan_set_comm.argtypes = [vp, i32, i32, vp, ctypes.c_size_t]
     L.alan_b200_num_inputs.argtypes = [vp]
     L.alan_b200_num_programs.argtypes = [vp]
     L.alan_b200_program_launches.argtypes = [vp, i32]
@@ -140,6 +144,27 @@ class DevicePlan:
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self.consts = {k: v.to(self.device) for k, v in plan.const_inputs.items()}
         self.launches = [L.alan_b200_program_launches(h, i) for i in range(L.alan_b200_num_programs(h))]
+
+    def attach_symmetric(self, process_group):
+        """Allocate this plan's symmetric buffer (torch.distributed._symmetric_memory: cuMem allocations exchanged
+        between the ranks of one node and mapped into every rank's address space over NVLink), rendezvous, and hand
+        the peer mappings to the plan (alan_b200_plan_set_comm).  Collective: every rank of the group calls it."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        L = lib()
+        nbytes = int(L.alan_b200_comm_bytes(self.handle))
+        if nbytes == 0:
+            return
+        pg = process_group if process_group is not None else dist.group.WORLD
+        with torch.cuda.device(self.device):
+            buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, pg.group_name if hasattr(pg, "group_name") else pg)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=process_group)                      # every rank's buffer is zeroed before anyone signals
+            ptrs = (ctypes.c_void_p * hdl.world_size)(*[int(p) for p in hdl.buffer_ptrs])
+            check(L.alan_b200_plan_set_comm(self.handle, hdl.rank, hdl.world_size, ptrs, nbytes))
+        self._symm = (buf, hdl)
 
     def __del__(self):
         try:

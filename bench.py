@@ -280,10 +280,15 @@ def run_b200(args, cfg0, rank, world, local_rank, scaling=None, full_report=True
     per = (M + world - 1) // world
     lo, hi = rank * per, min(M, (rank + 1) * per)
     P, Q, sample, ip, data, params = make_problem(cfg, lo, hi)
+    # sharded plans reduce the [K_mu, K_psi] tile and the global gradients across ranks INSIDE their programs, over
+    # NVLink peer memory (plan.XReduceOp); ALAN_B200_NCCL=1 keeps the host-issued ncclAllReduce between segments
+    fused = world > 1 and not os.environ.get("ALAN_B200_NCCL")
     comp = Compiled(P, Q, sample, ip, data, grad_names=params,
-                    shard_plate='plate_1' if world > 1 else None, world_size=world)
+                    shard_plate='plate_1' if world > 1 else None, world_size=world, fused_collectives=fused)
     run = Runner(comp, dev)
     plan = comp.plan
+    config = dict(config, collectives=("in-program peer-memory reduction (XReduceOp)" if fused else
+                                       "ncclAllReduce between program segments") if world > 1 else "none")
     host = [x.pin_memory() for x in comp.canonical_inputs(sample, ip, data)]
     tensors = [x.to(dev) for x in host]
     flush = t.empty(256 * 1024 * 1024 // 4, dtype=t.float32, device=dev)      # > 126 MB L2
@@ -384,9 +389,12 @@ def run_b200(args, cfg0, rank, world, local_rank, scaling=None, full_report=True
     if world == 1:
         line["e2e_api"] = e2e_through_public_api(cfg, dev, flush, steps, args.warmup, W)
 
-    # ---- roofline of the dominant kernel: per-op CUDA events in a separate profiled pass
-    if rank == 0 and full_report:
-        line.update(roofline_report(run, comp, plan, tensors, flush, dev, clocks, steps))
+    # ---- roofline of the dominant kernel: per-op CUDA events in a separate profiled pass (every rank runs it when
+    # the programs contain cross-rank reductions; rank 0 reports)
+    if full_report and (rank == 0 or plan.fused_collectives):
+        rep = roofline_report(run, comp, plan, tensors, flush, dev, clocks, steps)
+        if rank == 0:
+            line.update(rep)
     return line
 
 

@@ -44,6 +44,15 @@ const char* alan_b200_last_error(void);
 int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** plan);
 void alan_b200_plan_destroy(alan_b200_plan* plan);
 
+/* Plate sharding across GPUs: plans built with fused collectives reduce the per-shard [K_parents]
+ * tile and the global-parameter gradients ACROSS RANKS inside their programs, through symmetric buffers that every
+ * rank maps into its address space (NVLink peer memory; torch.distributed._symmetric_memory allocates and
+ * exchanges them).  alan_b200_comm_bytes: size each rank's zero-initialised buffer must have (0: the plan has no
+ * such reduction).  alan_b200_plan_set_comm: peer_buffers[r] = rank r's buffer as mapped in THIS process.
+ * replaces: the sequential `prev_lpq + lp` accumulation over Split chunks (src/alan/logpq.py:43-57,151-153). */
+size_t alan_b200_comm_bytes(const alan_b200_plan* plan);
+int alan_b200_plan_set_comm(alan_b200_plan* plan, int rank, int world, void* const* peer_buffers, size_t bytes);
+
 /* Bytes of device workspace the plan needs (factors, adjoints, partials). */
 size_t alan_b200_workspace_bytes(const alan_b200_plan* plan);
 int alan_b200_num_inputs(const alan_b200_plan* plan);

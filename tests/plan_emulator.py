@@ -65,7 +65,7 @@ class Emu:
         self.plan = plan
         self.dtype = plan.dtype
         self.item = 4 if self.dtype == t.float32 else 8
-        self.ws = t.zeros(plan.ws_bytes // self.item + 64, dtype=self.dtype)
+        self.ws = t.full((plan.ws_bytes // self.item + 64,), float('nan'), dtype=self.dtype)   # nothing may rely on a zeroed workspace
         self.inputs = [x.reshape(-1) for x in inputs]
         self.outputs = outputs or {}
         self.aux = aux or {}
@@ -75,7 +75,7 @@ class Emu:
         if pt.space == 'ws':
             if pt.offset is None:             # tensor that only the unfused form of an op would touch
                 if pt.id not in self.side:
-                    self.side[pt.id] = t.zeros(pt.numel, dtype=self.dtype)
+                    self.side[pt.id] = t.full((pt.numel,), float('nan'), dtype=self.dtype)
                 return self.side[pt.id], 0
             return self.ws, pt.offset // self.item
         if pt.space == 'input':
@@ -135,6 +135,16 @@ class Emu:
         for op in ops:
             getattr(self, 'op_' + type(op).__name__)(op)
 
+    def op_XReduceOp(self, op):
+        """cross-rank sum in place (the real collective over gloo when a process group exists, identity otherwise)"""
+        import torch.distributed as dist
+        for pt in op.pieces:
+            buf, base = self.buf(pt)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                x = buf[base:base + pt.numel].clone()
+                dist.all_reduce(x)
+                buf[base:base + pt.numel] = x
+
     def op_FillOp(self, op):
         buf, base = self.buf(op.pt)
         n = op.nbytes // self.item
@@ -177,7 +187,13 @@ class Emu:
         rows = f.rho + [f.kappa]
         fdim = [('ax', f.fan_axis, f.F)]
         r = f.gen_reduce
-        kw = dict(lse=r.out, gout=op.gout, lse_dims=r.od,
+        if r.m_out is None:        # the fused kernel keeps (max, log-sum) in registers; the emulator materialises them
+            r.m_out = PL.PT(r.out.axes, r.out.pos_shape, self.plan.sizes, 'ws', offset=None, name='emu_lse_m')
+            r.lo_out = PL.PT(r.out.axes, r.out.pos_shape, self.plan.sizes, 'ws', offset=None, name='emu_lse_lo')
+        saved = self.buf(r.out)[0][self.buf(r.out)[1]:self.buf(r.out)[1] + r.out.numel].clone()
+        self.op_ReduceOp(r)        # recomputes out (identical) and fills the pair
+        assert t.equal(self.buf(r.out)[0][self.buf(r.out)[1]:self.buf(r.out)[1] + r.out.numel], saved)
+        kw = dict(lse=(r.m_out, r.lo_out), gout=op.gout, lse_dims=r.od,
                   gout_dims=op.gout_dims if op.gout_dims is not None else r.od, cadd=r.cadd)
         if f.dense is None:
             self.op_ReduceOp(PL.ReduceOp(PL.R_WSUM, op.gS, rows, fdim, r.factors, **kw))
@@ -281,17 +297,24 @@ class Emu:
         if op.mode == PL.R_SUM:
             res = s.sum(rdims) if rdims else s
         elif op.mode == PL.R_WSUM:
-            lb, lbase = self.buf(op.lse)
+            m_pt, lo_pt = op.lse
+            mb, mbase = self.buf(m_pt)
+            lb, lbase = self.buf(lo_pt)
             gb, gbase = self.buf(op.gout)
-            l = lb[self.offsets(PL._strides_like(op.lse, op.lse_dims, dims), grid) + lbase]
+            mm = mb[self.offsets(PL._strides_like(m_pt, op.lse_dims, dims), grid) + mbase]
+            l = lb[self.offsets(PL._strides_like(lo_pt, op.lse_dims, dims), grid) + lbase]
             g = gb[self.offsets(PL._strides_like(op.gout, op.gout_dims, dims), grid) + gbase]
-            w = g * t.exp(s + op.cadd - l)
+            w = g * t.exp((s - mm) - l)
             res = w.sum(rdims) if rdims else w
         else:
             m = s.amax(rdims, keepdim=True)
             a = t.exp(s - m).sum(rdims)
             eps = t.finfo(self.dtype).eps if op.mode == PL.R_LSE_EPS else 0.0
             res = t.log(a + eps) + m.reshape(a.shape)
+            if op.m_out is not None:
+                for pt, val in ((op.m_out, m.reshape(a.shape)), (op.lo_out, t.log(a + eps))):
+                    b, base = self.buf(pt)
+                    b[base:base + val.numel()] = val.reshape(-1)
         out, obase = self.buf(op.out)
         n = res.numel()
         if op.nsplit > 1:

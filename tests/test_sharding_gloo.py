@@ -16,7 +16,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, fused=False):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -54,25 +54,35 @@ def _worker(rank, world, port, ret):
         return out
     sample, ip, data = shard(full_sample), shard(full_ip), shard(full_data)
     names = list(inp['params']) + ['mu_z', 'psi_z', 'z']           # VI-style: global AND sharded grads
-    comp = Compiled(P, Q, sample, ip, data, grad_names=names, shard_plate='plate_1', world_size=world)
+    comp = Compiled(P, Q, sample, ip, data, grad_names=names, shard_plate='plate_1', world_size=world,
+                    fused_collectives=fused)
     plan = comp.plan
-    assert plan.n_fwd == 2 and plan.allreduce is not None
+    assert plan.allreduce is not None
     inputs = comp.canonical_inputs(sample, ip, data)
     lp = t.zeros(1, dtype=dtype)
     emu = Emu(plan, inputs, outputs={0: lp})
-    emu.run(plan.programs[0])
-    tile_pt = plan.allreduce
-    tile = emu.ws[tile_pt.offset // 8: tile_pt.offset // 8 + tile_pt.numel]
-    dist.all_reduce(tile)                                            # the single forward exchange
-    emu.run(plan.programs[1])
+    if fused:
+        # the exchanges are ops inside the programs (plan.XReduceOp; the emulator performs them over gloo):
+        # one forward and one backward program, like an unsharded plan
+        kinds = [[type(op).__name__ for op in prog] for prog in plan.programs]
+        assert plan.n_fwd == 1 and plan.n_bwd == 1 and 'XReduceOp' in kinds[0] and kinds[1][-1] == 'XReduceOp'
+        emu.run(plan.programs[0])
+    else:
+        assert plan.n_fwd == 2
+        emu.run(plan.programs[0])
+        tile_pt = plan.allreduce
+        tile = emu.ws[tile_pt.offset // 8: tile_pt.offset // 8 + tile_pt.numel]
+        dist.all_reduce(tile)                                        # the single forward exchange
+        emu.run(plan.programs[1])
     emu.outputs = {i: t.zeros(plan.input_pts[n].numel, dtype=dtype) for i, n in enumerate(plan.grad_inputs)}
     emu.aux = {0: t.ones(1, dtype=dtype)}
     for seg in plan.programs[plan.n_fwd:plan.n_fwd + plan.n_bwd]:
         emu.run(seg)
     grads = {n: emu.outputs[i].reshape(plan.input_pts[n].shape) for i, n in enumerate(plan.grad_inputs)}
     assert set(plan.global_grads) == {n for n in names if 'plate_1' not in plan.input_pts[n].axes}
-    for n in plan.global_grads:                                      # the single backward exchange
-        dist.all_reduce(grads[n])
+    if not fused:
+        for n in plan.global_grads:                                  # the single backward exchange
+            dist.all_reduce(grads[n])
     if rank == 0:
         from oracle import logpq_oracle as O
         sg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in full_sample.items()}
@@ -93,11 +103,12 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_plate_sharding_two_ranks_gloo():
+@pytest.mark.parametrize("fused", [False, True])
+def test_plate_sharding_two_ranks_gloo(fused):
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * int(fused)) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret, fused)) for r in range(2)]
     for p in procs:
         p.start()
     err = ret.get(timeout=240)
