@@ -10,6 +10,7 @@
 
 #include <string>
 #include <vector>
+#include <map>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -47,7 +48,10 @@ struct alan_b200_plan {
     bool use_graphs = true;
     bool graph_auto = false;       // replay only bindings that repeat (see alan_b200_plan_create)
     mutable std::vector<int> miss_streak;   // per program: captures since the last replay hit (auto mode gives up at 4)
-    bool use_seq = false;          // run consecutive small ops as one launch (ALAN_B200_SEQ=1 at plan creation: on)
+    bool use_seq = false;          // run consecutive small ops as one launch (ALAN_B200_SEQ=0 at plan creation: off)
+    i64 seq_points = AB_SEQ_POINTS;   // an op is small up to this many iteration points (ALAN_B200_SEQ_POINTS)
+    bool seq_resident = true;      // small tensors of a sequence live in shared memory for the launch (ALAN_B200_SEQ_RESIDENT=0: global)
+    bool seq_bigsum = false;        // fixed-order sums of partial rows with few outputs also count as small (ALAN_B200_SEQ_BIGSUM=0: no)
     bool use_tc = true;            // fan_lse on tcgen05 where the shape allows (ALAN_B200_NO_TC=1 at plan creation: FFMA2 kernel)
     bool use_tc2 = true;           // dense formulation (fan_tc2.cuh) where the loc is independent of the value's axes
                                    // (ALAN_B200_TC_BLOCKDIAG=1 at plan creation: block-diagonal kernel only)
@@ -145,7 +149,14 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
     auto flush = [&]() {
         if (seq.n == 0) return;
         if (count_only) ++nl;
-        else small_seq_kernel<T><<<1, 1024, 0, c.stream>>>(seq);
+        else {
+            SeqResidency<T> rz;
+            const int smem = plan->seq_resident ? rz.build(seq) : ((seq.n_res = 0), (seq.smem_bytes = (int)((sizeof(SeqOp<T>) + 15) & ~(size_t)15)));
+            static const cudaError_t attr = cudaFuncSetAttribute(small_seq_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                 (int)(AB_RES_TOTAL + 4096));     // once per process and dtype
+            (void)attr;
+            small_seq_kernel<T><<<1, AB_SEQ_THREADS, smem, c.stream>>>(seq);
+        }
         seq.n = 0;
     };
     for (int op_i = 0; op_i < plan->prog_nops[program]; ++op_i) {
@@ -172,7 +183,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
             case OP_FILL: {
                 void* dst = tref(r, c);
                 i64 nbytes = r.i64v();
-                if (batching && nbytes <= 4 * AB_SEQ_POINTS && nbytes % 4 == 0) {
+                if (batching && nbytes <= 4 * plan->seq_points && nbytes % 4 == 0) {
                     if (seq.n == AB_SEQ_MAX) flush();
                     SeqOp<T>& o = seq.op[seq.n++];
                     o.kind = SK_FILL; o.warp = 0; o.f.ptr = dst; o.f.nbytes = nbytes;
@@ -199,7 +210,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 p.n_leaves = r.i32();
                 for (int l = 0; l < p.n_leaves; ++l) read_opnd(r, c, p.leaf[l], p.d.nd, true);
                 read_prog(r, p.prog);
-                if (batching && p.n_out * p.n_red <= AB_SEQ_POINTS) {
+                if (batching && p.n_out * p.n_red <= plan->seq_points) {
                     if (seq.n == AB_SEQ_MAX) flush();
                     SeqOp<T>& o = seq.op[seq.n++];
                     o.kind = SK_EXPR; o.warp = (p.n_red >= 8) ? 1 : 0; o.n3 = detect_normal3(p.prog); o.e = p;
@@ -222,7 +233,7 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 p.n_leaves = r.i32();
                 for (int l = 0; l < p.n_leaves; ++l) read_opnd(r, c, p.leaf[l], p.d.nd, true);
                 read_prog(r, p.prog);
-                if (batching && p.n_kept * p.n_loop <= AB_SEQ_POINTS) {
+                if (batching && p.n_kept * p.n_loop <= plan->seq_points) {
                     if (seq.n == AB_SEQ_MAX) flush();
                     SeqOp<T>& o = seq.op[seq.n++];
                     o.kind = SK_EXPR_BWD; o.warp = (p.n_loop / p.nsplit >= 8) ? 1 : 0; o.n3 = detect_normal3(p.prog); o.b = p;
@@ -259,8 +270,8 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 }
                 // small: few points, or a plain fixed-order sum of partial rows with few outputs (one thread per output
                     // walks the rows: e.g. the 160 x 900 partial rows of the fused plate sum)
-                if (batching && (p.n_out * p.n_red <= AB_SEQ_POINTS ||
-                                 (p.mode == R_SUM && p.nsplit == 1 && p.n_out <= 1024 && p.n_out * p.n_red <= 64 * AB_SEQ_POINTS))) {
+                if (batching && (p.n_out * p.n_red <= plan->seq_points ||
+                                 (plan->seq_bigsum && p.mode == R_SUM && p.nsplit == 1 && p.n_out <= 1024 && p.n_out * p.n_red <= 64 * AB_SEQ_POINTS))) {
                     if (seq.n == AB_SEQ_MAX) flush();
                     SeqOp<T>& o = seq.op[seq.n++];
                     o.kind = SK_REDUCE; o.warp = reduce_uses_warps(p, thread_hint != 0) ? 1 : 0; o.r = p;
@@ -628,10 +639,15 @@ int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** 
     p->miss_streak.assign(p->n_programs, 0);
     p->use_tc = getenv("ALAN_B200_NO_TC") == nullptr;
     p->use_tc2 = getenv("ALAN_B200_TC_BLOCKDIAG") == nullptr;
-    // Consecutive small ops of a program run as ONE single-CTA launch (small_seq_kernel): a plate tree has dozens of
-    // ops over a few hundred points (global latents, top-level contractions, their adjoints) whose launches, not
-    // their arithmetic, are what a step of a small or strongly sharded problem pays for.  ALAN_B200_SEQ=0: one launch per op.
-    { const char* sq = getenv("ALAN_B200_SEQ"); p->use_seq = !(sq && sq[0] == '0'); }
+    // Consecutive small ops of a program can run as ONE single-CTA launch (small_seq_kernel, its small tensors
+    // resident in shared memory).  Measured on B200 (cfg-2 / cfg-5 step, whole step replayed as one CUDA graph):
+    // separate launches 0.143 / 0.495 ms, sequences 0.205 / 0.562 ms, resident sequences 0.219 / 0.577 ms -- inside
+    // a graph a tiny kernel costs ~1.7 us all in, less than the same op costs inside the one-CTA interpreter.
+    // Hence opt-in (ALAN_B200_SEQ=1); cross-rank reductions always run through it (they are single-CTA by nature).
+    { const char* sq = getenv("ALAN_B200_SEQ"); p->use_seq = (sq && sq[0] == '1'); }
+    { const char* sq = getenv("ALAN_B200_SEQ_POINTS"); if (sq) p->seq_points = atoll(sq); }
+    { const char* sq = getenv("ALAN_B200_SEQ_BIGSUM"); p->seq_bigsum = (sq && sq[0] == '1'); }
+    { const char* sq = getenv("ALAN_B200_SEQ_RESIDENT"); p->seq_resident = !(sq && sq[0] == '0'); }
     int dev = 0;
     p->sm_count = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) {

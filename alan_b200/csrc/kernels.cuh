@@ -10,6 +10,7 @@
 // chosen split counts): results are bit-reproducible run to run; no float atomics anywhere.
 #pragma once
 #include "vm.cuh"
+#include <vector>
 
 // ------------------------------------------------------------------------------------------
 // leaf loads
@@ -467,8 +468,17 @@ __device__ __forceinline__ void reduce_thread_body(const ReduceParams<T>& p, con
         for (int f = 0; f < p.nf; ++f) base[f] = dot_stride(p.f[f], idx, 0, p.d.n_a);
         T res;
         if (p.mode == R_SUM) {
+            // eight independent loads in flight, added in index order: same bits as the one-by-one loop
             T a = T(0);
-            for (i64 j = lo; j < hi; ++j) a += factor_sum<T, NRED>(p, base, j);
+            i64 j = lo;
+            for (; j + 8 <= hi; j += 8) {
+                T v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = factor_sum<T, NRED>(p, base, j + q);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) a += v[q];
+            }
+            for (; j < hi; ++j) a += factor_sum<T, NRED>(p, base, j);
             res = a;
         } else if (p.mode == R_WSUM) {
             i64 mbase = dot_stride(p.lse_m, idx, 0, p.d.n_a), lbase = dot_stride(p.lse_lo, idx, 0, p.d.n_a),
@@ -626,20 +636,84 @@ struct SeqOp {
     __host__ __device__ SeqOp() {}
 };
 
+// Resident tensors of a sequence: the small tensors its ops pass to one another (and their small inputs) live in
+// SHARED memory for the duration of the launch.  Without this every op of the sequence pays global-memory round
+// trips for operands its predecessor has just produced (~1 us each with a flushed L2: measured, a 9-op sequence
+// cost MORE than 9 launches inside a CUDA graph); with it an op costs a few hundred cycles.  The host finds the
+// candidates (operand footprint <= AB_RES_TENSOR bytes, AB_RES_TOTAL in all), replaces their pointers in the op
+// parameters by tags (AB_RES_TAG << 48 | offset), and the kernel resolves the tags against its shared-memory
+// base, loads the tensors that are read before they are (completely) written, and writes back every tensor the
+// sequence wrote -- later programs (the adjoint pass) and the big kernels read them from global memory.
+#define AB_RES_MAX 56
+#define AB_RES_TAG 0xA1B2ull
+#define AB_RES_TENSOR (32 * 1024)
+#define AB_RES_TOTAL (160 * 1024)
+struct ResEnt { void* g; int nbytes; int off; int flags; int pad; };      // flags: 1 = load at start, 2 = store at end
+
 template <typename T>
 struct SeqParams {
-    int n;
+    int n, n_res, smem_bytes, pad;
+    ResEnt res[AB_RES_MAX];
     SeqOp<T> op[AB_SEQ_MAX];
-    __host__ __device__ SeqParams() : n(0) {}
+    __host__ __device__ SeqParams() : n(0), n_res(0), smem_bytes(0), pad(0) {}
 };
 
 static_assert(sizeof(SeqParams<double>) <= 32000, "SeqParams travels as a kernel parameter (32 764-byte limit)");
 
+template <typename P>
+__device__ __forceinline__ void res_fix(P*& p, unsigned char* base) {
+    const unsigned long long v = (unsigned long long)p;
+    if ((v >> 48) == AB_RES_TAG) p = reinterpret_cast<P*>(base + (v & 0xFFFFFFFFull));
+}
+
 template <typename T>
-__global__ void __launch_bounds__(1024) small_seq_kernel(const __grid_constant__ SeqParams<T> sp) {
+__device__ void seq_resolve(SeqOp<T>& o, unsigned char* base) {
+    switch (o.kind) {
+        case SK_EXPR:
+            for (int l = 0; l < o.e.n_leaves; ++l) res_fix(o.e.leaf[l].ptr, base);
+            res_fix(o.e.out, base);
+            break;
+        case SK_EXPR_BWD:
+            for (int l = 0; l < o.b.n_leaves; ++l) res_fix(o.b.leaf[l].ptr, base);
+            res_fix(o.b.gout.ptr, base); res_fix(o.b.gleaf, base);
+            break;
+        case SK_REDUCE:
+            for (int f = 0; f < o.r.nf; ++f) res_fix(o.r.f[f].ptr, base);
+            res_fix(o.r.lse_m.ptr, base); res_fix(o.r.lse_lo.ptr, base); res_fix(o.r.gout.ptr, base);
+            res_fix(o.r.out, base); res_fix(o.r.m_out, base); res_fix(o.r.lo_out, base);
+            break;
+        case SK_FILL: res_fix(o.f.ptr, base); break;
+        case SK_XREDUCE:
+            for (int q = 0; q < o.x.n_pieces; ++q) res_fix(o.x.piece[q], base);
+            break;
+    }
+}
+
+#define AB_SEQ_THREADS 512
+template <typename T>
+__global__ void __launch_bounds__(AB_SEQ_THREADS) small_seq_kernel(const __grid_constant__ SeqParams<T> sp) {
+    extern __shared__ __align__(16) unsigned char seq_smem[];
+    constexpr int CUR = (int)((sizeof(SeqOp<T>) + 15) & ~(size_t)15);
+    SeqOp<T>& cur = *reinterpret_cast<SeqOp<T>*>(seq_smem);          // the running op's parameters, tags resolved
+    unsigned char* base = seq_smem + CUR;
     const i64 t0 = threadIdx.x, tn = blockDim.x;
+    for (int e = 0; e < sp.n_res; ++e) {
+        if (!(sp.res[e].flags & 1)) continue;
+        const unsigned* g = reinterpret_cast<const unsigned*>(sp.res[e].g);
+        unsigned* d = reinterpret_cast<unsigned*>(base + sp.res[e].off);
+        for (int k = (int)t0; k < sp.res[e].nbytes / 4; k += (int)tn) d[k] = g[k];
+    }
     for (int i = 0; i < sp.n; ++i) {
-        const SeqOp<T>& o = sp.op[i];
+        __syncthreads();                                             // the previous op is done with `cur` and its results are visible
+        {
+            const unsigned* src = reinterpret_cast<const unsigned*>(&sp.op[i]);
+            unsigned* dst = reinterpret_cast<unsigned*>(seq_smem);
+            for (int k = (int)t0; k < (int)(sizeof(SeqOp<T>) / 4); k += (int)tn) dst[k] = src[k];
+        }
+        __syncthreads();
+        if (t0 == 0) seq_resolve(cur, base);
+        __syncthreads();
+        const SeqOp<T>& o = cur;
         switch (o.kind) {
             case SK_EXPR:
                 if (o.warp) { if (o.n3.on) expr_fwd_body<T, true, true>(o.e, o.n3, t0, tn); else expr_fwd_body<T, true, false>(o.e, o.n3, t0, tn); }
@@ -649,9 +723,12 @@ __global__ void __launch_bounds__(1024) small_seq_kernel(const __grid_constant__
                 if (o.warp) { if (o.n3.on) expr_bwd_body<T, true, true>(o.b, o.n3, t0, tn); else expr_bwd_body<T, true, false>(o.b, o.n3, t0, tn); }
                 else { if (o.n3.on) expr_bwd_body<T, false, true>(o.b, o.n3, t0, tn); else expr_bwd_body<T, false, false>(o.b, o.n3, t0, tn); }
                 break;
-            case SK_REDUCE:
-                if (o.warp) reduce_warp_body<T, 0>(o.r, t0, tn); else reduce_thread_body<T, 0>(o.r, t0, tn);
+            case SK_REDUCE: {
+                const int nred = o.r.d.nd - o.r.d.n_a;
+                if (o.warp) { if (nred == 1) reduce_warp_body<T, 1>(o.r, t0, tn); else reduce_warp_body<T, 0>(o.r, t0, tn); }
+                else { if (nred == 1) reduce_thread_body<T, 1>(o.r, t0, tn); else reduce_thread_body<T, 0>(o.r, t0, tn); }
                 break;
+            }
             case SK_FILL: {
                 unsigned* w = (unsigned*)o.f.ptr;                       // 4-byte granularity (all our tensors)
                 for (i64 k = t0; k < o.f.nbytes / 4; k += tn) w[k] = 0u;
@@ -662,9 +739,106 @@ __global__ void __launch_bounds__(1024) small_seq_kernel(const __grid_constant__
                 xreduce_body<T>(o.x, t0, tn);                           // completed by the launch boundary) -> pack
                 break;
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    for (int e = 0; e < sp.n_res; ++e) {
+        if (!(sp.res[e].flags & 2)) continue;
+        unsigned* g = reinterpret_cast<unsigned*>(sp.res[e].g);
+        const unsigned* d = reinterpret_cast<const unsigned*>(base + sp.res[e].off);
+        for (int k = (int)t0; k < sp.res[e].nbytes / 4; k += (int)tn) g[k] = d[k];
     }
 }
+
+// Host side: decide which operands of the collected ops become resident and tag their pointers.
+template <typename T>
+struct SeqResidency {
+    struct Use { void* base; size_t bytes; bool first_write; size_t first_bytes; bool written; };
+    std::vector<Use> uses;
+    Use& at(const void* p) {
+        for (auto& u : uses) if (u.base == p) return u;
+        uses.push_back(Use{const_cast<void*>(p), 0, false, 0, false});
+        uses.back().first_bytes = (size_t)-1;
+        return uses.back();
+    }
+    void touch(const void* p, size_t bytes, bool write) {
+        if (!p) return;
+        Use& u = at(p);
+        if (u.first_bytes == (size_t)-1) { u.first_write = write; u.first_bytes = bytes; }
+        if (bytes > u.bytes) u.bytes = bytes;
+        if (write) u.written = true;
+    }
+    static size_t fp(const Opnd& o, const Dims& d) {
+        i64 n = 1;
+        for (int k = 0; k < d.nd; ++k) n += (i64)(d.size[k] - 1) * (o.stride[k] < 0 ? -o.stride[k] : o.stride[k]);
+        return (size_t)n * sizeof(T);
+    }
+    template <typename F> static void each(SeqOp<T>& o, F&& f) {      // f(pointer reference, footprint bytes, is write, reads first)
+        switch (o.kind) {
+            case SK_EXPR:
+                for (int l = 0; l < o.e.n_leaves; ++l) f(const_cast<void*&>(o.e.leaf[l].ptr), fp(o.e.leaf[l], o.e.d), false, true);
+                f(reinterpret_cast<void*&>(o.e.out), (size_t)o.e.n_out * sizeof(T), true, o.e.acc != 0);
+                break;
+            case SK_EXPR_BWD:
+                for (int l = 0; l < o.b.n_leaves; ++l) f(const_cast<void*&>(o.b.leaf[l].ptr), fp(o.b.leaf[l], o.b.d), false, true);
+                f(const_cast<void*&>(o.b.gout.ptr), fp(o.b.gout, o.b.d), false, true);
+                f(reinterpret_cast<void*&>(o.b.gleaf), (size_t)o.b.n_kept * o.b.nsplit * sizeof(T), true, o.b.acc != 0 && o.b.nsplit == 1);
+                break;
+            case SK_REDUCE:
+                for (int q = 0; q < o.r.nf; ++q) f(const_cast<void*&>(o.r.f[q].ptr), fp(o.r.f[q], o.r.d), false, true);
+                if (o.r.mode == R_WSUM) {
+                    f(const_cast<void*&>(o.r.lse_m.ptr), fp(o.r.lse_m, o.r.d), false, true);
+                    f(const_cast<void*&>(o.r.lse_lo.ptr), fp(o.r.lse_lo, o.r.d), false, true);
+                    f(const_cast<void*&>(o.r.gout.ptr), fp(o.r.gout, o.r.d), false, true);
+                }
+                f(reinterpret_cast<void*&>(o.r.out), (size_t)o.r.n_out * o.r.nsplit * sizeof(T), true, o.r.acc != 0 && o.r.nsplit == 1);
+                if (o.r.m_out) {
+                    f(reinterpret_cast<void*&>(o.r.m_out), (size_t)o.r.n_out * sizeof(T), true, false);
+                    f(reinterpret_cast<void*&>(o.r.lo_out), (size_t)o.r.n_out * sizeof(T), true, false);
+                }
+                break;
+            case SK_FILL: f(o.f.ptr, (size_t)o.f.nbytes, true, false); break;
+            case SK_XREDUCE:
+                for (int q = 0; q < o.x.n_pieces; ++q) f(reinterpret_cast<void*&>(o.x.piece[q]), (size_t)o.x.piece_n[q] * sizeof(T), true, true);
+                break;
+        }
+    }
+    // returns the dynamic shared-memory bytes of the launch
+    int build(SeqParams<T>& sp) {
+        uses.clear();
+        for (int i = 0; i < sp.n; ++i)
+            each(sp.op[i], [&](void*& p, size_t bytes, bool write, bool reads_first) {
+                if (write && reads_first) touch(p, bytes, false);
+                touch(p, bytes, write);
+            });
+        constexpr int CUR = (int)((sizeof(SeqOp<T>) + 15) & ~(size_t)15);
+        size_t off = 0;
+        sp.n_res = 0;
+        std::vector<int> slot(uses.size(), -1);
+        for (size_t k = 0; k < uses.size(); ++k) {
+            const Use& u = uses[k];
+            const size_t need = (u.bytes + 15) & ~(size_t)15;
+            if (u.bytes == 0 || u.bytes > AB_RES_TENSOR || off + need > AB_RES_TOTAL || sp.n_res == AB_RES_MAX) continue;
+            if (((unsigned long long)u.base >> 48) != 0 || ((unsigned long long)u.base & 3)) continue;
+            ResEnt& e = sp.res[sp.n_res];
+            e.g = u.base; e.nbytes = (int)((u.bytes + 3) & ~(size_t)3); e.off = (int)off; e.pad = 0;
+            const bool covered = u.first_write && u.first_bytes >= u.bytes;      // completely written before any read
+            e.flags = (covered ? 0 : 1) | (u.written ? 2 : 0);
+            slot[k] = sp.n_res++;
+            off += need;
+        }
+        for (int i = 0; i < sp.n; ++i)
+            each(sp.op[i], [&](void*& p, size_t, bool, bool) {
+                if (!p) return;
+                for (size_t k = 0; k < uses.size(); ++k)
+                    if (uses[k].base == p && slot[k] >= 0) {
+                        p = reinterpret_cast<void*>((AB_RES_TAG << 48) | (unsigned long long)sp.res[slot[k]].off);
+                        return;
+                    }
+            });
+        sp.smem_bytes = CUR + (int)off;
+        return sp.smem_bytes;
+    }
+};
 
 // ------------------------------------------------------------------------------------------
 // K5: Timeseries chain.  One CTA per (pair, outer).  reference utils.py:478-510.

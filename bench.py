@@ -204,7 +204,9 @@ def op_model(op, itemsize):
         pts = math.prod(d[2] for d in op.od + op.rd)
         for lf, _ in op.factors:
             add(lf.pt)
-        add(op.lse); add(op.gout); add(op.out)
+        for x in (op.lse if isinstance(op.lse, tuple) else (op.lse,)):
+            add(x)
+        add(op.gout); add(op.out)
         flops = pts * (len(op.factors) + (0 if op.mode == 0 else 3))
         tag = op.tag or ("adjoint" if op.mode == 3 else "sum")
     else:

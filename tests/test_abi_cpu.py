@@ -38,15 +38,16 @@ def test_plan_blob_round_trip_without_gpu(monkeypatch):
     assert L.alan_b200_num_inputs(h) == len(comp.plan.input_names)
     assert L.alan_b200_num_programs(h) == len(comp.plan.programs)
     assert L.alan_b200_workspace_bytes(h) == comp.plan.ws_bytes
-    fused = [L.alan_b200_program_launches(h, i) for i in range(len(comp.plan.programs))]
-    L.alan_b200_plan_destroy(h)
-    # consecutive small ops run as one launch by default; ALAN_B200_SEQ=0 (read when the plan is created): one per op
-    monkeypatch.setenv("ALAN_B200_SEQ", "0")
-    assert L.alan_b200_plan_create(ctypes.c_void_p(blob.data_ptr()), blob.numel(), ctypes.byref(h)) == 0
     for i, prog in enumerate(comp.plan.programs):
         kernels = [op for op in prog if not type(op).__name__.startswith('Fill')]
         assert L.alan_b200_program_launches(h, i) == len(kernels)
-        assert 1 <= fused[i] <= len(kernels)
+    L.alan_b200_plan_destroy(h)
+    # ALAN_B200_SEQ=1 (read when the plan is created): consecutive small ops run as one single-CTA launch
+    monkeypatch.setenv("ALAN_B200_SEQ", "1")
+    assert L.alan_b200_plan_create(ctypes.c_void_p(blob.data_ptr()), blob.numel(), ctypes.byref(h)) == 0
+    fused = [L.alan_b200_program_launches(h, i) for i in range(len(comp.plan.programs))]
+    for i, prog in enumerate(comp.plan.programs):
+        assert 1 <= fused[i] <= len(prog)
     assert sum(fused[:2]) < sum(len(p_) for p_ in comp.plan.programs[:2]) // 2
     L.alan_b200_plan_destroy(h)
     monkeypatch.delenv("ALAN_B200_SEQ")
