@@ -5,6 +5,7 @@
 #include "fused.cuh"
 #include "fan_tc.cuh"
 #include "fan_tc2.cuh"
+#include "qfactor.cuh"
 #include <type_traits>
 #include <cstdlib>
 
@@ -20,7 +21,7 @@
 
 enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
 enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
-       OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13, OP_XREDUCE = 14 };
+       OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13, OP_XREDUCE = 14, OP_NORMAL_Q_BWD = 15 };
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -295,10 +296,10 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 if (site < 0 || site >= (int)plan->site_off.size()) return fail("xreduce: unknown site");
                 x.rank = plan->comm_rank; x.world = plan->comm_world;
                 for (int q = 0; q < x.world; ++q) x.site[q] = plan->comm_peer[q] + plan->site_off[site];
+                if (!batching) { xreduce_kernel<T><<<1, 512, 0, c.stream>>>(x); break; }      // stand-alone: a 0.4 KB parameter block
                 if (seq.n == AB_SEQ_MAX) flush();
                 SeqOp<T>& o = seq.op[seq.n++];
                 o.kind = SK_XREDUCE; o.warp = 0; o.x = x;
-                if (!batching) flush();
                 break;
             }
             case OP_CHAIN: {
@@ -426,6 +427,14 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                     p.b_k[i] = r.i64v();
                 }
                 p.cadd = (T)r.f64();
+                p.qn = r.i32();
+                if (p.qn) {
+                    p.q_l = (const T*)tref(r, c); p.q_s = (const T*)tref(r, c);
+                    for (int k = 0; k < nrd; ++k) p.q_lstride[k] = r.i64v();
+                    for (int k = 0; k < nrd; ++k) p.q_sstride[k] = r.i64v();
+                    p.q_lev = r.i64v(); p.q_sev = r.i64v();
+                    p.q_coeff = (T)r.f64();
+                }
                 if (!bwd) {
                     p.psum_rows = r.i32();
                     if (p.psum_rows > 0) { p.psum = (T*)tref(r, c); p.ps_lam = r.i64v(); p.ps_f = r.i64v(); p.ps_row = r.i64v(); }
@@ -447,8 +456,13 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                         return fail("fan_lse adjoint: the plan commits to the dense tensor-core kernel (compact gS layout) but that "
                                     "kernel is disabled or does not cover this shape; rebuild the plan with ALAN_B200_NO_TC / "
                                     "ALAN_B200_TC_BLOCKDIAG set the way the run is");
+                    else if (p.qn)
+                        return fail("fan_lse: the plan evaluates the Q factor inside the dense tensor-core kernel but that kernel is "
+                                    "disabled or does not cover this shape; rebuild the plan with ALAN_B200_NO_TC / "
+                                    "ALAN_B200_TC_BLOCKDIAG set the way the run is");
                     else if (plan->use_tc && tc::fan_lse_tc_supported(p, D)) rc = tc::launch_fan_lse_tc(p, D, bwd != 0, c.stream, c.sm_count);
                 }
+                if (rc < 0 && p.qn) return fail("fan_lse: the inline Q factor needs the fp32 dense tensor-core kernel");
                 if (rc < 0 && (p.gs_compact > 0 || p.psum_rows > 0)) return fail("fan_lse: compact gS layout / fused plate sum need the fp32 dense tensor-core kernel");
                 if (rc < 0) rc = launch_fan_lse<T>(p, D, bwd != 0, c.stream, c.sm_count);
                 if (rc) return fail(rc == 1 ? "fan_lse: unsupported event extent" : rc == 2 ? "fan_lse: tile does not fit shared memory" : "fan_lse: strides exceed 32-bit tile addressing");
@@ -489,6 +503,29 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 p.F = r.i32();
                 p.o_f = r.i64v();
                 if (launch_fan_bwd<T>(q, D, which, c.stream, c.sm_count)) return fail("fan_bwd: unsupported event extent");
+                break;
+            }
+            case OP_NORMAL_Q_BWD: {
+                NormalQBwdParams<T> p;
+                memset(&p, 0, sizeof(p));
+                const int D = r.i32();
+                const int nu = r.i32();
+                p.ud.nd = nu; p.ud.n_a = nu;
+                p.n_users = 1;
+                for (int k = 0; k < nu; ++k) { p.ud.size[k] = r.i32(); p.n_users *= p.ud.size[k]; }
+                for (int k = 0; k < nu; ++k) p.vstride[k] = r.i64v();
+                for (int k = 0; k < nu; ++k) p.lstride[k] = r.i64v();
+                for (int k = 0; k < nu; ++k) p.sstride[k] = r.i64v();
+                for (int k = 0; k < nu; ++k) p.gstride[k] = r.i64v();
+                p.Kk = r.i32(); p.v_k = r.i64v(); p.v_ev = r.i64v(); p.l_ev = r.i64v(); p.s_ev = r.i64v();
+                p.v = (const T*)tref(r, c); p.l = (const T*)tref(r, c); p.s = (const T*)tref(r, c);
+                p.scale_is_exp = r.i32();
+                p.G = (const T*)tref(r, c); p.g_s = r.i64v(); p.g_k = r.i64v(); p.S = r.i32();
+                p.coeff = (T)r.f64();
+                if (r.i32()) { p.gl = (T*)tref(r, c); p.acc_l = r.i32(); }
+                if (r.i32()) { p.gs = (T*)tref(r, c); p.acc_s = r.i32(); }
+                int rc = launch_normal_q_bwd<T>(p, D, c.stream, c.sm_count);
+                if (rc) return fail(rc == 1 ? "normal_q_bwd: unsupported event extent" : "normal_q_bwd: tile does not fit shared memory");
                 break;
             }
             case OP_BERN_DOT: {

@@ -98,6 +98,8 @@ struct Tc2Geom {
     int L, l_lam, o_lam, g_lam, s_lam;      // lam: extent and strides (l, out, gout, gS)
     int g_f;
     int n_u, NG, FP;                        // users, fan groups, wide fan extent L F
+    int qn, qls[T2_ND], qss[T2_ND], q_lev, q_sev;   // inline Gaussian Q factor: strides of its loc / scale over the user dims
+    float qc;
     int cta_lo[T2_MAXG + 1];                // CTAs [cta_lo[g], cta_lo[g + 1]) work on fan group g (proportional to its tiles)
     int vec2;
 };
@@ -163,13 +165,27 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
     // ---------------------------------------------------------------- prologue
     for (uint32_t i = threadIdx.x; i < (T2_STAGES * 2) * OPER / 16; i += blockDim.x)
         reinterpret_cast<float4*>(tc_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp == 0) {
-        float c = 0.f;
-        if (lane < D) {
-            for (int j = 0; j < geo.L; ++j) c += p.l[j * geo.l_lam + lane * (int)p.l_ev];
-            c /= (float)geo.L;
+    {
+        // centre per event element = mean over lam of the loc: the L x D loc values are fetched by all threads at once
+        // (one global round trip instead of L dependent ones: the loop below used to cost ~15 us of a ~26 us prologue)
+        // into the still unused stage memory, then lane d adds its column in lam order (fixed order: reproducible)
+        float* stage_f = reinterpret_cast<float*>(tc_smem);
+        __syncthreads();                                                   // the zero fill above is complete
+        for (int i = threadIdx.x; i < geo.L * D; i += blockDim.x) {
+            const int j = i / D, dd = i - j * D;
+            stage_f[i] = p.l[j * geo.l_lam + dd * (int)p.l_ev];
         }
-        s_cd[lane] = c;
+        __syncthreads();
+        if (warp == 0) {
+            float c = 0.f;
+            if (lane < D) {
+                for (int j = 0; j < geo.L; ++j) c += stage_f[j * D + lane];
+                c /= (float)geo.L;
+            }
+            s_cd[lane] = c;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < geo.L * D; i += blockDim.x) stage_f[i] = 0.f;     // back to the zero fill
     }
     __syncthreads();
     {   // padding rows (kappa >= Kk) carry a hugely negative bias: no column mask in the epilogue
@@ -474,13 +490,21 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
         const int vk = (int)p.v_k, vev = (int)p.v_ev, nb = geo.nb, vec2 = geo.vec2;
         // raw loads only (no arithmetic on the loaded values here: an in-order warp would stall on the first use)
         float cur[D], nxt[D], cur_b[TC_NB], nxt_b[TC_NB];
-        auto load_raw = [&](unsigned blk, float (&raw)[D], float (&braw)[TC_NB]) {
+        float cur_ql = 0.f, cur_qs = 1.f, nxt_ql = 0.f, nxt_qs = 1.f;          // inline Q factor: lane d holds loc[u, d], scale[u, d]
+        auto load_raw = [&](unsigned blk, float (&raw)[D], float (&braw)[TC_NB], float& ql, float& qs) {
             const unsigned u = T2_US * blk + us;
             const bool live = u < n_u && kz < Kk;
 #pragma unroll
             for (int dd = 0; dd < D; ++dd) raw[dd] = s_cd[dd];                  // idle rows: v' = 0
 #pragma unroll
             for (int i = 0; i < TC_NB; ++i) braw[i] = 0.f;
+            ql = 0.f; qs = 1.f;
+            if (geo.qn && u < n_u && lane < D) {
+                int idx[T2_ND];
+                t2_decode(u, geo, idx);
+                ql = p.q_l[t2_dot(idx, geo.qls) + lane * geo.q_lev];
+                qs = p.q_s[t2_dot(idx, geo.qss) + lane * geo.q_sev];
+            }
             if (live) {
                 int idx[T2_ND];
                 t2_decode(u, geo, idx);
@@ -499,7 +523,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                 }
             }
         };
-        if (blk0 < n_blocks) load_raw(blk0, cur, cur_b);
+        if (blk0 < n_blocks) load_raw(blk0, cur, cur_b, cur_ql, cur_qs);
         unsigned it = 0;
         for (unsigned blk = blk0; blk < n_blocks; blk += blk_step, ++it) {
             const int s = it % T2_STAGES;
@@ -507,15 +531,31 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
 #ifdef TC_DEBUG_SPIN
             const long long tb0 = clock64();
 #endif
-            if (blk + blk_step < n_blocks) load_raw(blk + blk_step, nxt, nxt_b);
+            if (blk + blk_step < n_blocks) load_raw(blk + blk_step, nxt, nxt_b, nxt_ql, nxt_qs);
             MBAR_WAIT(&empty[s], ps ^ 1, dbg0);
 #ifdef TC_DEBUG_SPIN
             const long long tb1 = clock64();
 #endif
+            // inline Gaussian Q factor of this (user, kappa): lane d contributes 1 / (2 s_d^2) and log s_d, every lane
+            // walks the D shuffled pairs in d order (fixed order) against its own value row
+            float qsum = 0.f;
+            if (geo.qn) {
+                const float iv2 = 0.5f / (cur_qs * cur_qs);
+                float lg = lane < D ? logf(cur_qs) : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+#pragma unroll
+                for (int dd = 0; dd < D; ++dd) {
+                    const float l_d = __shfl_sync(0xffffffffu, cur_ql, dd), w_d = __shfl_sync(0xffffffffu, iv2, dd);
+                    const float df = cur[dd] - l_d;
+                    qsum = fmaf(-(df * df), w_d, qsum);
+                }
+                qsum -= lg + float(D) * float(HALF_LOG_2PI);
+            }
             if (kz < Kk) {                       // rows of users >= n_u are written as zeros: finite, masked later
                 float* bh = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER);
                 float* bl = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER);
-                float bsum = 0.f;
+                float bsum = geo.qc * qsum;
 #pragma unroll
                 for (int i = 0; i < TC_NB; ++i) if (i < nb) bsum += geo.bc[i] * cur_b[i];
                 bsum *= LS;
@@ -549,6 +589,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
             for (int dd = 0; dd < D; ++dd) cur[dd] = nxt[dd];
 #pragma unroll
             for (int i = 0; i < TC_NB; ++i) cur_b[i] = nxt_b[i];
+            cur_ql = nxt_ql; cur_qs = nxt_qs;
 #ifdef TC_DEBUG_SPIN
             dbg1 += tb2 - tb1;                   // build + store
             dbg2 += clock64() - tb2;             // fence + arrive
@@ -597,6 +638,7 @@ static bool fan_lse_tc2_supported(const FanLseParams<float>& p, int D, bool bwd)
     // the adjoint writes one partial per fan group: only the planner-committed compact gS layout [users, NG, kappa]
     // is covered completely (nothing zero-fills adjoint tensors any more: plan.py build_backward)
     if (bwd && p.gs_compact == 0) return false;
+    if (p.qn && (lam >= 0 && (p.q_lstride[lam] != 0 || p.q_sstride[lam] != 0))) return false;
     if (FP < 96 || NG > T2_MAXG || (bwd && NG > L) || (bwd && p.gs_compact > 0 && p.gs_compact != NG) || p.Kk > 32 || n_u < 16 || p.nb > TC_NB) return false;
     if (p.rd.nd - (lam >= 0 ? 1 : 0) > T2_ND) return false;
     const i64 lim = (i64)1 << 31;
@@ -636,9 +678,11 @@ static int launch_fan_lse_tc2_D(const FanLseParams<float>& p, bool bwd, cudaStre
         geo.sz[j] = p.rd.size[k];
         geo.vs[j] = (int)p.vstride[k]; geo.os[j] = (int)p.ostride[k]; geo.gs[j] = (int)p.gstride[k]; geo.ss[j] = (int)sstride[k];
         for (int i = 0; i < p.nb; ++i) geo.bs[i][j] = (int)p.bstride[i][k];
+        geo.qls[j] = (int)p.q_lstride[k]; geo.qss[j] = (int)p.q_sstride[k];
         ev2 = ev2 && (p.vstride[k] % 2 == 0);
         ++j;
     }
+    geo.qn = p.qn; geo.q_lev = (int)p.q_lev; geo.q_sev = (int)p.q_sev; geo.qc = p.qn ? (float)p.q_coeff : 0.f;
     for (int i = 0; i < p.nb; ++i) { geo.bk[i] = (int)p.b_k[i]; geo.bc[i] = p.bcoeff[i]; }
     if (p.gs_compact > 0) {
         // planner-committed layout [users (row-major), fan group, kappa]: nothing but the partials is ever stored

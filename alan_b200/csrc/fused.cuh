@@ -345,6 +345,13 @@ struct FanLseParams {
     int gs_compact;                       // bwd, dense tcgen05 kernel only: > 0 = gS is [users, gs_compact fan groups, kappa]
     T* psum; int psum_rows;               // fwd, dense tcgen05 kernel only: per-(CTA, team) sums of out over the users,
     i64 ps_lam, ps_f, ps_row;             //      psum[row * ps_row + lam * ps_lam + f * ps_f]
+    // dense tcgen05 kernel only: one more small factor evaluated IN the kernel from the value rows its builders
+    // already hold,  q_coeff * sum_d log N(v[rho,kappa,d]; q_l[rho,d], q_s[rho,d])  -- the mean-field Gaussian Q
+    // factor of the same latent (north_star (1): densities and the P-minus-Q difference straight into registers)
+    int qn;
+    const T* q_l; const T* q_s;
+    i64 q_lstride[AB_MAXD], q_sstride[AB_MAXD], q_lev, q_sev;
+    T q_coeff;
     i64 n_rho;
 };
 

@@ -598,15 +598,24 @@ __device__ __forceinline__ void xreduce_body(const XReduceParams<T>& p, const i6
     off = 0;
     for (int q = 0; q < p.n_pieces; ++q) {
         for (i64 i = t0; i < p.piece_n[q]; i += tn) {
+            T v[AB_XR_MAXW];
+#pragma unroll
+            for (int r = 0; r < AB_XR_MAXW; ++r)                             // all remote loads in flight at once ...
+                v[r] = r < p.world ? *reinterpret_cast<const volatile T*>(reinterpret_cast<const T*>(p.site[r] + AB_XR_HDR) + buf + off + i) : T(0);
             T a = T(0);
-            for (int r = 0; r < p.world; ++r)
-                a += *reinterpret_cast<const volatile T*>(reinterpret_cast<const T*>(p.site[r] + AB_XR_HDR) + buf + off + i);
+#pragma unroll
+            for (int r = 0; r < AB_XR_MAXW; ++r) if (r < p.world) a += v[r];   // ... added in rank order
             p.piece[q][i] = a;
         }
         off += p.piece_n[q];
     }
     __syncthreads();
     if (t0 == 0) my_hdr[0] = e;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) xreduce_kernel(const __grid_constant__ XReduceParams<T> p) {
+    xreduce_body<T>(p, threadIdx.x, blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------------

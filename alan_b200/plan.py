@@ -34,7 +34,7 @@ MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
 SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
 OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY, OP_DOT, \
-    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE = range(1, 15)
+    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD = range(1, 16)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
 
@@ -476,6 +476,7 @@ class FanLseOp(Op):
         self.gen_expr, self.gen_reduce, self.tag = gen_expr, gen_reduce, tag
         self.dense = None            # (lam dim, L, NG) when the planner commits the adjoint to the dense kernel's gS layout
         self.psum = None             # (partial PT, rows, od) when the dense kernel also sums its output over the users
+        self.qterm = None            # (ExprOp E, loc leaf, scale leaf, coeff): Gaussian Q factor evaluated inside the dense kernel
 
     def _body(self, w):
         w.i32(self.D); w.i32(len(self.rho))
@@ -501,6 +502,15 @@ class FanLseOp(Op):
                 w.i64(lf.stride(d))
             w.i64(lf.stride(self.kappa))
         w.f64(self.cadd)
+        if self.qterm is None:
+            w.i32(0)
+        else:
+            _, ql, qs, qc = self.qterm
+            w.i32(1); w.tref(ql.pt); w.tref(qs.pt)
+            for lf in (ql, qs):
+                for d in self.rho:
+                    w.i64(lf.stride(d))
+            w.i64(ql.stride(ev)); w.i64(qs.stride(ev)); w.f64(qc)
 
     def payload(self, w):
         w.i32(0); w.tref(self.out)
@@ -563,6 +573,39 @@ class FanLseBwdOp(Op):
             w.i64(x)
         # > 0: gS is laid out [users, NG fan-group partials, kappa] (csrc/fan_tc2.cuh only); 0: [rho, kappa]
         w.i32(self.fwd.dense[2] if self.fwd.dense is not None else 0)
+
+
+class NormalQBwdOp(Op):
+    """Whole adjoint of a mean-field Gaussian Q factor in one pass over its value (csrc/qfactor.cuh):
+    G[u, kappa] = coeff * sum_s gS[u, s, kappa];  g_loc += sum_kappa G (v - loc) / scale^2;
+    g_ls += sum_kappa G ((v - loc)^2 / scale^2 - 1)  (or the gradient w.r.t. the scale itself).
+    `gen` = what the generic path would have done (the emulator runs that)."""
+    code = OP_NORMAL_Q_BWD
+
+    def __init__(self, D, users, kappa, v, l, s, scale_is_exp, gS, gS_dims, sdim, coeff, g_l, g_s):
+        self.D, self.users, self.kappa, self.v, self.l, self.s = D, users, kappa, v, l, s
+        self.scale_is_exp, self.gS, self.gS_dims, self.sdim, self.coeff = scale_is_exp, gS, gS_dims, sdim, coeff
+        self.g_l, self.g_s, self.acc_l, self.acc_s = g_l, g_s, 1, 1
+
+    def payload(self, w):
+        w.i32(self.D); w.i32(len(self.users))
+        for d in self.users:
+            w.i32(d[2])
+        gref = _OwnDims(self.gS, self.gS_dims)
+        for lf in (self.v, self.l, self.s, gref):
+            for d in self.users:
+                w.i64(lf.stride(d))
+        ev = ('ev', 0, self.D)
+        w.i32(self.kappa[2]); w.i64(self.v.stride(self.kappa)); w.i64(self.v.stride(ev))
+        w.i64(self.l.stride(ev)); w.i64(self.s.stride(ev))
+        w.tref(self.v.pt); w.tref(self.l.pt); w.tref(self.s.pt); w.i32(1 if self.scale_is_exp else 0)
+        w.tref(self.gS); w.i64(gref.stride(self.sdim) if self.sdim is not None else 0); w.i64(gref.stride(self.kappa))
+        w.i32(self.sdim[2] if self.sdim is not None else 1)
+        w.f64(self.coeff)
+        for g, a in ((self.g_l, self.acc_l), (self.g_s, self.acc_s)):
+            w.i32(1 if g is not None else 0)
+            if g is not None:
+                w.tref(g); w.i32(a)
 
 
 class DotOp(Op):
@@ -795,6 +838,7 @@ class Planner:
         self.alloc_group = 0
         self.grad_names = list(grad_names)
         self.needs = set()
+        self.needs_materialised = set()      # factor tensors someone reads outside the contraction that produced them
         self.fan_by_out = {}
         self.producer = {}
         self.fwd = []
@@ -830,7 +874,7 @@ class Planner:
         self.canon = list(canon)
         self.plan.canon_axes = self.canon
         self.alloc_group = 0
-        self.grad_names, self.needs = [], set()
+        self.grad_names, self.needs, self.needs_materialised = [], set(), set()
         self.fan_by_out, self.producer, self.fwd, self.fwd_segments = {}, {}, [], []
         self.consts, self.inputs = {}, {}
         for name, s in sig.items():
@@ -851,7 +895,8 @@ class Planner:
         if isinstance(op, ChainOp):
             return [op.ms]
         if isinstance(op, FanLseOp):
-            return [lf.pt for lf, _ in op.bfactors] + [op.v.pt, op.l.pt, op.s.pt]
+            q = [op.qterm[1].pt, op.qterm[2].pt] if op.qterm is not None else []
+            return [lf.pt for lf, _ in op.bfactors] + [op.v.pt, op.l.pt, op.s.pt] + q
         if isinstance(op, BernDotSumOp):
             return [op.a.pt, op.b.pt, op.y.pt]
         if isinstance(op, DotOp):
@@ -1263,7 +1308,51 @@ class Planner:
         # lam) unless the caller asked for the other kernels when the plan is built
         if not (os.environ.get("ALAN_B200_NO_TC") or os.environ.get("ALAN_B200_TC_BLOCKDIAG")):
             op.dense = dense_fan_geometry(op, self.itemsize)
+        if op.dense is not None and not os.environ.get("ALAN_B200_NO_QFUSE"):
+            self._try_inline_q(op)
         return op
+
+    def _normal3_parts(self, E):
+        """(value, loc, scale) leaves of an ExprOp that is exactly `sum_d log N(value; loc, scale)` over plain leaves."""
+        if not isinstance(E, ExprOp) or E.acc or E.scale != 1.0 or len(E.red) > 1 or any(d[0] != 'ax' for d in E.keep):
+            return None
+        code = E.codeobj
+        if [ins[0] for ins in code.instrs] != [VOPS['load']] * 3 + [VOPS['Normal']] or len(code.leaves) != 3:
+            return None
+        _, dst, ra, rb, rc, _ = code.instrs[3]
+        if code.res != dst:
+            return None
+        leaf_of = {code.instrs[i][1]: code.leaves[code.instrs[i][2]] for i in range(3)}
+        parts = (leaf_of[ra], leaf_of[rb], leaf_of[rc])
+        if any(type(x) is not LeafRef or x.rename or x.mode for x in parts):
+            return None
+        return parts
+
+    def _try_inline_q(self, op: 'FanLseOp'):
+        """The dense tensor-core kernel's builder warps hold every value row v[u, kappa, :] in registers.  If one of
+        the small factors of the contraction is the Gaussian Q factor of the SAME value tensor with per-user loc and
+        scale (`sum_d log N(v; loc[u,d], scale[u,d])`, nobody else reading it), it is evaluated there: the factor's own
+        pass over v (and its [u, kappa] tensor) disappears from the forward program."""
+        lam = op.dense[0]
+        ev = ('ev', 0, op.D)
+        for i, (lf, c) in enumerate(op.bfactors):
+            E = self.producer.get(lf.pt.id)
+            parts = self._normal3_parts(E)
+            if parts is None or E not in self.fwd or lf.pt.id in self.needs_materialised:
+                continue
+            v, l, sc = parts
+            if v.pt is not op.v.pt or (E.red[0][2] if E.red else 1) != op.D or op.D > 32:
+                continue
+            if [v.stride(d) for d in op.rho + [op.kappa, ev]] != [op.v.stride(d) for d in op.rho + [op.kappa, ev]]:
+                continue
+            if any(x.stride(op.kappa) != 0 or x.stride(lam) != 0 or (op.D > 1 and x.stride(ev) == 0) for x in (l, sc)):
+                continue
+            if set((d[0], d[1]) for d in E.keep) != set((d[0], d[1]) for d in op.rho + [op.kappa] if d != lam):
+                continue
+            self.fwd.remove(E)
+            op.qterm = (E, l, sc, c)
+            op.bfactors = op.bfactors[:i] + op.bfactors[i + 1:]
+            return
 
     def plate_sum(self, lf: LogicalFactor, plate):
         out_axes = tuple(a for a in lf.axes if a != plate)
@@ -1556,7 +1645,8 @@ class Planner:
                         out_list.append(ReduceOp(mode, g, kept, loop, facs, acc=1, scale=scale, **kw))
             elif isinstance(op, FanLseOp):
                 bs = [(lf, coeff) for lf, coeff in op.bfactors if lf.pt.id in needs]
-                if bs:
+                qwant = op.qterm is not None and any(self._q_targets(op.qterm, needs))
+                if bs or qwant:
                     if op.dense is not None:
                         lam, _, NG = op.dense
                         rows = [d for d in op.rho if d != lam] + [('sp', 0, NG), op.kappa]
@@ -1569,7 +1659,15 @@ class Planner:
                         out_list.append(FanLseBwdOp(op, gsmall, gS, gout_dims=gdims))
                     else:
                         out_list.append(FanLseBwdOp(op, gout, gS))
+                    if qwant:
+                        E, _, _, qc = op.qterm
+                        if not self._try_normal_q_bwd(op, None, qc, gS, rows, out_list, adjoint, needs, n_uses,
+                                                      contribution_scale, E=E):
+                            raise Exception("internal: the inline Q factor has no fused adjoint for this shape")
                     for lf, coeff in bs:
+                        if self.fast_paths and self._try_normal_q_bwd(op, lf, coeff, gS, rows, out_list, adjoint, needs,
+                                                                        n_uses, contribution_scale):
+                            continue
                         g = adjoint(lf.pt)
                         kept = [d for d in rows if lf.stride(d) != 0]
                         kept.sort(key=lambda d: -lf.stride(d))
@@ -1600,6 +1698,12 @@ class Planner:
         written = set()
         for seg in segs:
             for o in seg:
+                if isinstance(o, NormalQBwdOp):
+                    for attr, g in (('acc_l', o.g_l), ('acc_s', o.g_s)):
+                        if g is not None:
+                            setattr(o, attr, 1 if g.id in written else 0)
+                            written.add(g.id)
+                    continue
                 dest = o.gleaf if isinstance(o, ExprBwdOp) else getattr(o, 'out', None)
                 if dest is None or not isinstance(o, (ExprBwdOp, ReduceOp, ExprOp)):
                     continue
@@ -1615,6 +1719,68 @@ class Planner:
                 for k in range(0, len(pieces), 16):
                     segs[-1].append(XReduceOp(1 + k // 16, pieces[k:k + 16]))
         return segs
+
+    def _q_targets(self, qterm, needs):
+        """(loc wanted, scale / log-scale wanted) for an inline Q factor."""
+        _, l, sc, _ = qterm
+        A = self.producer.get(sc.pt.id)
+        st = sc.pt
+        if isinstance(A, ExprOp) and [ins[0] for ins in A.codeobj.instrs] == [VOPS['load'], VOPS['exp']]:
+            st = A.codeobj.leaves[0].pt
+        return l.pt.id in needs, st.id in needs
+
+    def _try_normal_q_bwd(self, fanop, lf, coeff, gS, rows, out_list, adjoint, needs, n_uses, contribution_scale, E=None):
+        """Recognise, among the small factors of a fused contraction, the mean-field Gaussian Q factor
+        `sum_d log N(v[u,kappa,d]; loc[u,d], scale[u,d])` (scale possibly `exp` of a log-scale parameter) whose only
+        consumer is this contraction, and emit its whole adjoint as ONE NormalQBwdOp that reads the contraction's
+        adjoint gS directly -- instead of: sum gS over its partial slots, one gather-style ExprBwd per target leaf, the
+        exp adjoint.  Returns False (nothing emitted) when the pattern does not apply."""
+        if E is None:
+            if type(lf) is not LeafRef or lf.rename or lf.mode or n_uses.get(lf.pt.id) != 1:
+                return False
+            E = self.producer.get(lf.pt.id)
+        parts = self._normal3_parts(E)
+        if parts is None:
+            return False
+        v, l, sc = parts
+        D = E.red[0][2] if E.red else 1
+        if D not in self.FAN_EVENT_EXTENTS:
+            return False
+        kappa = fanop.kappa
+        ev = ('ev', 0, D)
+        users = [d for d in E.keep if (d[0], d[1]) != (kappa[0], kappa[1])]
+        if len(users) + 1 != len(E.keep) or v.stride(kappa) == 0 or v.pt.id in needs:
+            return False
+        n_users = _prod(d[2] for d in users)
+        # the scale: a leaf of its own, or exp(log-scale leaf) hoisted into an 'arg' tensor that only this factor reads
+        s_target, scale_is_exp = sc.pt, False
+        A = self.producer.get(sc.pt.id)
+        if isinstance(A, ExprOp) and [ins[0] for ins in A.codeobj.instrs] == [VOPS['load'], VOPS['exp']] \
+                and not A.red and not A.acc and A.scale == 1.0 and n_uses.get(sc.pt.id, 0) <= 1:
+            ls = A.codeobj.leaves[0]
+            if type(ls) is LeafRef and not ls.rename and not ls.mode and ls.pt.shape == sc.pt.shape and ls.pt.axes == sc.pt.axes:
+                s_target, scale_is_exp = ls.pt, True
+        elif A is not None:
+            return False
+        for x in (l, sc):
+            if x.stride(kappa) != 0 or x.pt.numel != n_users * D or any(x.stride(d) == 0 for d in users if d[2] > 1) \
+                    or (D > 1 and x.stride(ev) == 0):
+                return False
+        want_l, want_s = l.pt.id in needs, s_target.id in needs
+        if not (want_l or want_s):
+            return False
+        # gS dims: the users (same order), kappa, and at most one extra dim that is summed (partial slots / loc samples)
+        keys = lambda ds: [(d[0], d[1]) for d in ds]
+        extra = [d for d in rows if (d[0], d[1]) not in keys(users) and (d[0], d[1]) != (kappa[0], kappa[1])]
+        if len(extra) > 1 or [k for k in keys(rows) if k in keys(users)] != keys(users):
+            return False
+        g_l = adjoint(l.pt) if want_l else None
+        g_s = adjoint(s_target) if want_s else None
+        c = coeff * contribution_scale(fanop, l.pt if want_l else s_target, g_l if want_l else g_s)
+        op = NormalQBwdOp(D, users, kappa, v, l, sc, scale_is_exp, gS, rows, extra[0] if extra else None, c, g_l, g_s)
+        op.gen = (E, A if scale_is_exp else None, lf)
+        out_list.append(op)
+        return True
 
     def _fan_backward(self, op, fan, gout, out_list, adjoint, needs, contribution_scale):
         """Adjoint of a materialised normal_fan factor through the fused kernels (reparameterised / VI

@@ -200,6 +200,11 @@ def op_model(op, itemsize):
         pts = rows * op.F
         flops = 2 * pts * op.D + 2 * rows * op.D
         tag = op.tag
+    elif name == "NormalQBwdOp":
+        n_users = math.prod(d[2] for d in op.users)
+        pts = n_users * op.kappa[2]
+        add(op.v.pt); add(op.l.pt); add(op.s.pt); add(op.gS); add(op.g_l); add(op.g_s)
+        flops, tag = pts * op.D * 6, "normal_q_bwd:" + op.gen[0].tag
     elif name == "ReduceOp":
         pts = math.prod(d[2] for d in op.od + op.rd)
         for lf, _ in op.factors:

@@ -169,6 +169,8 @@ class Emu:
         self.ws[lo // self.item: hi // self.item] = 0
 
     def op_FanLseOp(self, op):
+        if op.qterm is not None:           # the fused kernel evaluates the Q factor inline; the emulator materialises it
+            self.op_ExprOp(op.qterm[0])
         self.op_ExprOp(op.gen_expr)
         self.op_ReduceOp(op.gen_reduce)
         if op.psum is not None:
@@ -183,6 +185,8 @@ class Emu:
 
     def op_FanLseBwdOp(self, op):
         f = op.fwd
+        if f.qterm is not None:
+            self.op_ExprOp(f.qterm[0])
         self.op_ExprOp(f.gen_expr)
         rows = f.rho + [f.kappa]
         fdim = [('ax', f.fan_axis, f.F)]
@@ -238,6 +242,41 @@ class Emu:
             pw[bw:bw + op.n_cta * Ws.numel()] = 0
             pv[bv:bv + V.numel()] = V.reshape(-1)
             pw[bw:bw + Ws.numel()] = Ws.reshape(-1)
+
+    def op_NormalQBwdOp(self, op):
+        ev = ('ev', 0, op.D)
+        gdims = list(op.users) + ([op.sdim] if op.sdim is not None else []) + [op.kappa]
+        ggrid = self.grid(gdims)
+        gb, gbase = self.buf(op.gS)
+        gref = PL._OwnDims(op.gS, op.gS_dims)
+        G = gb[self.offsets([gref.stride(d) for d in gdims], ggrid) + gbase]
+        if op.sdim is not None:
+            G = G.sum(len(op.users))
+        G = op.coeff * G                                                  # [users..., kappa]
+        dims = list(op.users) + [op.kappa, ev]
+        grid = self.grid(dims)
+        shape = [d[2] for d in dims]
+        v = self.load_leaf(op.v, dims, grid)[0] + t.zeros(shape, dtype=self.dtype)
+        pdims = list(op.users) + [ev]
+        pgrid = self.grid(pdims)
+        lbuf, lbase = self.buf(op.l.pt)
+        sbuf, sbase = self.buf(op.s.pt)
+        loff = self.offsets([op.l.stride(d) for d in pdims], pgrid)
+        soff = self.offsets([op.s.stride(d) for d in pdims], pgrid)
+        l = lbuf[loff + lbase].clone().requires_grad_()
+        sc = sbuf[soff + sbase].clone().requires_grad_()
+        nu = len(op.users)
+        with t.enable_grad():
+            lp = (-((v - l.unsqueeze(nu)) ** 2) / (2 * sc.unsqueeze(nu) ** 2) - t.log(sc.unsqueeze(nu)) - HALF_LOG_2PI).sum(-1)
+            gl, gs = t.autograd.grad((lp * G).sum(), [l, sc])
+        if op.scale_is_exp:
+            gs = gs * sc.detach()
+        for g, val, off, acc in ((op.g_l, gl, loff, op.acc_l), (op.g_s, gs, soff, op.acc_s)):
+            if g is None:
+                continue
+            b, base = self.buf(g)
+            o = (off + base).reshape(-1)
+            b[o] = b[o] + val.reshape(-1) if acc else val.reshape(-1)
 
     def op_BernDotSumOp(self, op):
         for g in op.gen_ops:
