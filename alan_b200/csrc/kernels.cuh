@@ -653,6 +653,10 @@ struct SeqOp {
 // parameters by tags (AB_RES_TAG << 48 | offset), and the kernel resolves the tags against its shared-memory
 // base, loads the tensors that are read before they are (completely) written, and writes back every tensor the
 // sequence wrote -- later programs (the adjoint pass) and the big kernels read them from global memory.
+// (Writing real shared-memory addresses into the parameters on the host does not work: nvcc assumes that pointers
+// arriving in kernel parameters are global and emits LDG/STG for them, which fault on the shared window.  The copy
+// of each op's parameter block into shared memory, where the tags are resolved, is what this variant pays: with it
+// an op costs ~3 us, so sequences stay opt-in -- see alan_b200_plan_create.)
 #define AB_RES_MAX 56
 #define AB_RES_TAG 0xA1B2ull
 #define AB_RES_TENSOR (32 * 1024)

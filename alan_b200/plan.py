@@ -1308,7 +1308,10 @@ class Planner:
         # lam) unless the caller asked for the other kernels when the plan is built
         if not (os.environ.get("ALAN_B200_NO_TC") or os.environ.get("ALAN_B200_TC_BLOCKDIAG")):
             op.dense = dense_fan_geometry(op, self.itemsize)
-        if op.dense is not None and not os.environ.get("ALAN_B200_NO_QFUSE"):
+        # Opt-in (ALAN_B200_QFUSE=1 when the plan is built): measured on B200 at cfg-5 the builder warps of the dense
+        # kernel are on its critical path (the MMA issuer waits on them ~25 % of the time), so the ~350 cycles per block
+        # the inline Q factor adds to them cost as much (+9 us forward, +12 us adjoint) as the removed pass (23 us).
+        if op.dense is not None and os.environ.get("ALAN_B200_QFUSE") == "1":
             self._try_inline_q(op)
         return op
 

@@ -420,6 +420,33 @@ def test_tcgen05_fan_lse_matches_ffma_kernel(M_, N_, K, d, monkeypatch):
         assert rel_err(g_tc[k].cpu(), g_ff[k].cpu()) < 1e-4, k
 
 
+@pytest.mark.parametrize("M_,N_,K,d", [(130, 3, 24, 16), (64, 5, 30, 18), (301, 2, 20, 6)])
+def test_inline_q_factor_in_dense_kernel(M_, N_, K, d, monkeypatch):
+    """ALAN_B200_QFUSE=1: the Gaussian Q factor of z evaluated by the dense kernel's builder warps (no logQ:z pass, no
+    [u, kappa] factor tensor) against the default plan that materialises it: same log-evidence and gradients."""
+    Compiled, Runner = _engine()
+    P, Q, sample, ip, data, names = _movielens_case(M_, N_, K, d, seed=27)
+    res = {}
+    for fuse in (False, True):
+        if fuse:
+            monkeypatch.setenv("ALAN_B200_QFUSE", "1")
+        else:
+            monkeypatch.delenv("ALAN_B200_QFUSE", raising=False)
+        comp = Compiled(P, Q, sample, ip, data, grad_names=names)
+        fan = [op for prog in comp.plan.programs for op in prog if type(op).__name__ == 'FanLseOp'][0]
+        assert (fan.qterm is not None) == fuse
+        tags = [getattr(op, 'tag', '') for op in comp.plan.programs[0]]
+        assert ('logQ:z' in tags) == (not fuse)
+        assert 'NormalQBwdOp' in [type(op).__name__ for op in comp.plan.programs[1]]
+        run = Runner(comp, "cuda:0")
+        tensors = run.device_inputs(sample, ip, data)
+        res[fuse] = (run.forward_raw(tensors).clone(), {k: v.clone() for k, v in run.backward_raw(tensors).items()})
+    monkeypatch.delenv("ALAN_B200_QFUSE", raising=False)
+    assert rel_err(res[True][0].cpu(), res[False][0].cpu()) < 2e-6
+    for k in names:
+        assert rel_err(res[True][1][k].cpu(), res[False][1][k].cpu()) < 5e-5, k
+
+
 @pytest.mark.parametrize("M_,N_,K,d", [(64, 5, 30, 18), (40, 3, 32, 18), (50, 2, 12, 8)])
 def test_dense_and_block_diagonal_tcgen05_kernels_agree(M_, N_, K, d, monkeypatch):
     """csrc/fan_tc2.cuh (dense expanded-square GEMM, compact gS) against csrc/fan_tc.cuh (block-diagonal operand,
