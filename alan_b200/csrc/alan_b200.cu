@@ -6,6 +6,7 @@
 #include "fan_tc.cuh"
 #include "fan_tc2.cuh"
 #include "qfactor.cuh"
+#include "sampling.cuh"
 #include <type_traits>
 #include <cstdlib>
 
@@ -21,7 +22,8 @@
 
 enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
 enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
-       OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13, OP_XREDUCE = 14, OP_NORMAL_Q_BWD = 15 };
+       OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13, OP_XREDUCE = 14, OP_NORMAL_Q_BWD = 15, OP_PERM = 16, OP_KGATHER = 17,
+       OP_TS_SAMPLE = 18 };
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -503,6 +505,45 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
                 p.F = r.i32();
                 p.o_f = r.i64v();
                 if (launch_fan_bwd<T>(q, D, which, c.stream, c.sm_count)) return fail("fan_bwd: unsupported event extent");
+                break;
+            }
+            case OP_PERM: {
+                const double* u = (const double*)tref(r, c);
+                i64* out = (i64*)tref(r, c);
+                const i64 rows = r.i64v();
+                const int K = r.i32(), mode = r.i32();
+                if ((size_t)K * 8 * sizeof(double) > 48 * 1024) return fail("perm: K too large");
+                perm_kernel<<<grid_for(rows, 8, c), 256, (size_t)K * 8 * sizeof(double), c.stream>>>(u, out, rows, K, mode);
+                break;
+            }
+            case OP_KGATHER: {
+                const T* x = (const T*)tref(r, c);
+                const i64* perm = (const i64*)tref(r, c);
+                T* out = (T*)tref(r, c);
+                const i64 outer = r.i64v(), K = r.i64v(), inner = r.i64v();
+                kgather_kernel<T><<<grid_for(outer * K * inner, 256, c), 256, 0, c.stream>>>(x, perm, out, outer, K, inner);
+                break;
+            }
+            case OP_TS_SAMPLE: {
+                TsSampleParams<T> p;
+                memset(&p, 0, sizeof(p));
+                p.e.out = (T*)tref(r, c);
+                p.e.acc = 0; p.e.scale = T(1);
+                read_dims(r, p.e.d, p.e.n_out, p.e.n_red);
+                p.e.n_leaves = r.i32();
+                for (int l = 0; l < p.e.n_leaves; ++l) read_opnd(r, c, p.e.leaf[l], p.e.d.nd, true);
+                read_prog(r, p.e.prog);
+                p.prev_leaf = r.i32(); p.t_dim = r.i32(); p.k_dim = r.i32();
+                p.init = (const T*)tref(r, c);
+                if (r.i32()) p.perm = (const i64*)tref(r, c);
+                p.n_outer = r.i64v(); p.Tn = r.i32(); p.Kn = r.i32(); p.En = r.i32();
+                const size_t smem = (size_t)2 * p.Kn * p.En * sizeof(T);
+                if (smem > 200 * 1024) return fail("ts_sample: K x event extent does not fit shared memory");
+                if (smem > 48 * 1024)
+                    cudaFuncSetAttribute(ts_sample_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                int threads = p.Kn * p.En; threads = (threads + 31) / 32 * 32; if (threads > 1024) threads = 1024;
+                i64 blocks = p.n_outer < (i64)c.sm_count * 4 ? p.n_outer : (i64)c.sm_count * 4;
+                ts_sample_kernel<T><<<(int)(blocks < 1 ? 1 : blocks), threads, smem, c.stream>>>(p);
                 break;
             }
             case OP_NORMAL_Q_BWD: {

@@ -34,13 +34,13 @@ MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
 SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
 OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY, OP_DOT, \
-    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD = range(1, 16)
+    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD, OP_PERM, OP_KGATHER, OP_TS_SAMPLE = range(1, 19)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
 
 VOPS = {'load': 0, 'const': 1, 'add': 2, 'sub': 3, 'mul': 4, 'div': 5, 'neg': 6, 'exp': 7, 'log': 8, 'sigmoid': 9,
         'square': 10, 'sqrt': 11, 'reciprocal': 12, 'softplus': 13, 'tanh': 14, 'abs': 15, 'log1p': 16, 'pow': 17,
-        'lgamma': 18, 'mov': 19,
+        'lgamma': 18, 'mov': 19, 'lt': 20,
         'Normal': 32, 'Bernoulli_logits': 33, 'Bernoulli_probs': 34, 'LogNormal': 35, 'Laplace': 36,
         'Exponential': 37, 'Gamma': 38, 'Beta': 39, 'Poisson': 40, 'Cauchy': 41, 'HalfNormal': 42, 'Uniform': 43,
         'StudentT': 44, 'NegativeBinomial_logits': 45, 'NegativeBinomial_probs': 46, 'Binomial_logits': 47,
@@ -606,6 +606,61 @@ class NormalQBwdOp(Op):
             w.i32(1 if g is not None else 0)
             if g is not None:
                 w.tref(g); w.i32(a)
+
+
+class PermOp(Op):
+    """perm[rows, K] (int64) from float64 uniforms u[rows, K]: mode 0 = argsort along K (PermutationSampler.perm,
+    reference Sampler.py:143-148), mode 1 = floor(u K) (CategoricalSampler.perm).  csrc/sampling.cuh perm_kernel."""
+    code = OP_PERM
+
+    def __init__(self, u, out, rows, K, mode):
+        self.u, self.out, self.rows, self.K, self.mode = u, out, rows, K, mode
+
+    def payload(self, w):
+        w.tref(self.u); w.tref(self.out); w.i64(self.rows); w.i32(self.K); w.i32(self.mode)
+
+
+class KGatherOp(Op):
+    """out[o, k, i] = x[o, perm[o, k], i]: parent particles permuted along their K axis (Sampler.resample_scope,
+    reference Sampler.py:85-116).  csrc/sampling.cuh kgather_kernel."""
+    code = OP_KGATHER
+
+    def __init__(self, x, perm, out, outer, K, inner):
+        self.x, self.perm, self.out, self.outer, self.K, self.inner = x, perm, out, outer, K, inner
+
+    def payload(self, w):
+        w.tref(self.x); w.tref(self.perm); w.tref(self.out); w.i64(self.outer); w.i64(self.K); w.i64(self.inner)
+
+
+class TsSampleOp(Op):
+    """The T-step recursion of a Timeseries draw in one launch (reference Timeseries.py:89-123): `expr` (an ExprOp,
+    nothing summed, dims [outer..., T, K, event...]) is evaluated step by step with leaf `prev_leaf` = the previous
+    step's draw, permuted along K by perm[outer, t, :] (timeseries_perm).  csrc/sampling.cuh ts_sample_kernel."""
+    code = OP_TS_SAMPLE
+
+    def __init__(self, expr: 'ExprOp', prev_leaf, t_dim, k_dim, init, perm, n_outer, T, K, E):
+        self.expr, self.prev_leaf, self.t_dim, self.k_dim = expr, prev_leaf, t_dim, k_dim
+        self.init, self.perm, self.n_outer, self.T, self.K, self.E = init, perm, n_outer, T, K, E
+        self.out = expr.out
+
+    def payload(self, w):
+        e = self.expr
+        w.tref(e.out)
+        dims = e.keep
+        leaves = e.codeobj.leaves
+        _write_dims(w, [d[2] for d in dims], len(dims))
+        w.i32(len(leaves))
+        for lf in leaves:
+            w.tref(lf.pt); w.i32(lf.mode); w.i32(0)
+            for d in dims:
+                w.i64(lf.stride(d))
+        e.codeobj.write(w)
+        w.i32(self.prev_leaf); w.i32(self.t_dim); w.i32(self.k_dim)
+        w.tref(self.init)
+        w.i32(1 if self.perm is not None else 0)
+        if self.perm is not None:
+            w.tref(self.perm)
+        w.i64(self.n_outer); w.i32(self.T); w.i32(self.K); w.i32(self.E)
 
 
 class DotOp(Op):

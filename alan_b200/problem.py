@@ -9,9 +9,9 @@
 every one of them taking `computation_strategy=` (no_checkpoint | checkpoint | Split(plate, n)) like the reference.
 
 Same names, argument meaning and error behaviour (Python `Exception` with prose) as the reference for
-this path.  What is NOT here is the step before it: ancestral sampling of Q with permutation
-resampling (`Plate.sample`) stays the reference's; `sample_from` takes its
-output (or any `[K, plates..., event]` tensors).  Everything below `Sample` runs in the CUDA engine
+this path.  `sample(K)` draws from Q on the device (ancestral sampling with permuted parent particles,
+SURVEY.md §8 row f-1, alan_b200/sampling.py); `sample_from` takes the reference's samples (or any
+`[K, plates..., event]` tensors) instead.  Everything below `Sample` runs in the CUDA engine
 through the C ABI; there is no CPU fallback.
 """
 from __future__ import annotations
@@ -38,7 +38,7 @@ def _as_nt(x) -> NT:
 
 class Problem:
     def __init__(self, P: Plate, Q: Plate, data: dict, inputs: Optional[dict] = None, params: Optional[dict] = None,
-                 device="cuda", process_group=None, shard_plate=None):
+                 device="cuda", process_group=None, shard_plate=None, platesizes: Optional[dict] = None):
         self.P, self.Q = P, Q
         self.data = {k: _as_nt(v) for k, v in (data or {}).items()}
         self.inputs = {k: _as_nt(v) for k, v in (inputs or {}).items()}
@@ -52,10 +52,45 @@ class Problem:
         # compiled plans + device workspaces, shared by every Sample of this problem with the same tensor signature
         # (the reference re-walks the plate tree on every call; a plan costs ~30 ms to compile, a step ~1 ms)
         self._runners = {}
+        # plate sizes: the reference takes them from BoundPlate(all_platesizes=...); here they follow from the named
+        # axes of data / inputs / parameters, completed by `platesizes` for plates nothing observed spans
+        self.platesizes = dict(platesizes or {})
+        for d in (self.data, self.inputs, self.params):
+            for k, v in d.items():
+                for a, n in v.named_sizes.items():
+                    if self.platesizes.setdefault(a, n) != n:
+                        raise Exception(f"plate {a} has size {self.platesizes[a]} but {k} has {n} elements along it")
 
     def inputs_params(self) -> dict:
         """reference Problem.inputs_params (Problem.py:113-118), flat."""
         return {**self.inputs, **self.params}
+
+    def sample(self, K: int, reparam: bool = True, sampler=None, noise: Optional[dict] = None,
+               seed: Optional[int] = None) -> "Sample":
+        """Draw K particles per latent from Q on the device (reference Problem.sample, Problem.py:71-97 ->
+        BoundPlate._sample -> Plate.sample: ancestral sampling with permuted parent particles).  One program per
+        (shapes, K, sampler), one C-ABI call per draw (alan_b200/sampling.py).  `noise` / `seed` make the draw
+        reproducible (explicit base noise: see QSampler.noise_shapes()).  With `reparam=True` the samples carry
+        requires_grad so that `elbo_vi` returns the pathwise gradient with respect to them."""
+        from .sampling import QSampler, PermutationSampler
+        sampler = sampler or PermutationSampler
+        ip = self.inputs_params()
+        dtype = torch.float64 if any(v.t.dtype == torch.float64 for d in (ip, self.data) for v in d.values()) \
+            else torch.float32
+        key = ('qsample', int(K), sampler, dtype, tuple(sorted((k, v.axes, tuple(v.t.shape)) for k, v in ip.items())))
+        if key not in self._runners:
+            self._runners[key] = QSampler(self.Q, ip, self.platesizes, K, sampler, dtype, self.device)
+        qs = self._runners[key]
+        with torch.no_grad():
+            out = qs.run(ip, noise=noise, seed=seed)
+        v2g = self.Q.varname2groupvarname()
+        smp = {}
+        for name, x in out.items():
+            kax = Kname(v2g[name])
+            axes = (kax,) + tuple(a for a in x.axes if a != kax)           # [K, plates..., event]: the reference's order
+            y = x.order(axes)
+            smp[name] = NT(y.t.contiguous().requires_grad_(bool(reparam)), axes)
+        return Sample(self, smp, reparam)
 
     def sample_from(self, sample: dict, reparam: bool = False) -> "Sample":
         return Sample(self, {k: _as_nt(v) for k, v in sample.items()}, reparam)

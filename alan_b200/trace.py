@@ -16,7 +16,7 @@ import torch
 
 UNARY = {'neg', 'exp', 'log', 'sigmoid', 'square', 'sqrt', 'reciprocal', 'softplus', 'tanh', 'abs', 'log1p',
          'lgamma'}
-BINARY = {'add', 'sub', 'mul', 'div', 'pow'}
+BINARY = {'add', 'sub', 'mul', 'div', 'pow', 'lt'}
 
 
 def _bshape(a, b):

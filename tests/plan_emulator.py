@@ -15,7 +15,7 @@ from alan_b200 import plan as PL
 UN = {6: lambda a: -a, 7: t.exp, 8: t.log, 9: t.sigmoid, 10: lambda a: a * a, 11: t.sqrt,
       12: lambda a: 1 / a, 13: t.nn.functional.softplus, 14: t.tanh, 15: t.abs, 16: t.log1p, 18: t.lgamma,
       19: lambda a: a}
-BI = {2: t.add, 3: t.sub, 4: t.mul, 5: t.div, 17: t.pow}
+BI = {2: t.add, 3: t.sub, 4: t.mul, 5: t.div, 17: t.pow, 20: lambda a, b: (a < b).to(a.dtype)}
 HALF_LOG_2PI = 0.91893853320467274178
 
 
@@ -144,6 +144,51 @@ class Emu:
                 x = buf[base:base + pt.numel].clone()
                 dist.all_reduce(x)
                 buf[base:base + pt.numel] = x
+
+    def op_PermOp(self, op):
+        ub, ubase = self.buf(op.u)
+        u = ub[ubase:ubase + op.rows * op.K].reshape(op.rows, op.K).double()
+        if op.mode == 1:
+            p = (u * op.K).long().clamp(max=op.K - 1)
+        else:
+            p = t.argsort(u, dim=-1, stable=True)
+        self.side[('perm', op.out.id)] = p                      # int64: kept beside the (float) workspace
+
+    def op_KGatherOp(self, op):
+        xb, xbase = self.buf(op.x)
+        x = xb[xbase:xbase + op.outer * op.K * op.inner].reshape(op.outer, op.K, op.inner)
+        p = self.side[('perm', op.perm.id)]
+        out = t.gather(x, 1, p.reshape(op.outer, op.K, 1).expand(op.outer, op.K, op.inner))
+        ob, obase = self.buf(op.out)
+        ob[obase:obase + out.numel()] = out.reshape(-1)
+
+    def op_TsSampleOp(self, op):
+        e = op.expr
+        dims = e.keep
+        ib, ibase = self.buf(op.init)
+        KE = op.K * op.E
+        prev = ib[ibase:ibase + op.n_outer * KE].reshape(op.n_outer, op.K, op.E).clone()
+        perm = self.side[('perm', op.perm.id)].reshape(op.n_outer, op.T, op.K) if op.perm is not None else None
+        ob, obase = self.buf(e.out)
+        sizes = [d[2] for d in dims]
+        grid = self.grid(dims)
+        out = t.zeros(op.n_outer, op.T, op.K, op.E, dtype=self.dtype)
+        for tt in range(op.T):
+            vals = []
+            for li, lf in enumerate(e.codeobj.leaves):
+                if li == op.prev_leaf:
+                    full = prev.reshape(op.n_outer, 1, op.K, op.E).expand(op.n_outer, op.T, op.K, op.E).reshape(sizes)
+                    vals.append(full)
+                else:
+                    vals.append(self.load_leaf(lf, dims, grid)[0] + t.zeros(sizes, dtype=self.dtype))
+            res = (self.vm(e.codeobj, vals) + t.zeros(sizes, dtype=self.dtype)).reshape(op.n_outer, op.T, op.K, op.E)
+            cur = res[:, tt]
+            out[:, tt] = cur
+            if perm is not None:
+                prev = t.gather(cur, 1, perm[:, tt].reshape(op.n_outer, op.K, 1).expand(op.n_outer, op.K, op.E))
+            else:
+                prev = cur
+        ob[obase:obase + out.numel()] = out.reshape(-1)
 
     def op_FillOp(self, op):
         buf, base = self.buf(op.pt)
