@@ -5,6 +5,7 @@
 #include "fused.cuh"
 #include "fan_tc.cuh"
 #include "fan_tc2.cuh"
+#include "fan_tc2b.cuh"
 #include "qfactor.cuh"
 #include "sampling.cuh"
 #include <type_traits>

@@ -102,9 +102,17 @@ struct Tc2Geom {
     float qc;
     int cta_lo[T2_MAXG + 1];                // CTAs [cta_lo[g], cta_lo[g + 1]) work on fan group g (proportional to its tiles)
     int vec2;
+    int flat;                               // only the last user dim has an extent > 1
+    int lg_vec4;                            // adjoint: lse / gout rows of a fan group are contiguous and 16-byte aligned
 };
 
 __device__ __forceinline__ void t2_decode(unsigned u, const Tc2Geom& g, int* idx) {
+    if (g.flat) {                               // one user dim (the common case): no divisions
+#pragma unroll
+        for (int k = 0; k < T2_ND - 1; ++k) idx[k] = 0;
+        idx[T2_ND - 1] = (int)u;
+        return;
+    }
 #pragma unroll
     for (int k = T2_ND - 1; k >= 0; --k) {
         const unsigned sz = (unsigned)g.sz[k];
@@ -613,6 +621,9 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
     }
 }
 
+template <int D>
+static void launch_fan_lse_tc2_adj(const FanLseParams<float>& p, const Tc2Geom& geo, int blocks, cudaStream_t stream);   // fan_tc2b.cuh
+
 // index of the lam dim in p.rd, -1 if the loc is a constant vector (L = 1), -2 if the dense formulation does not apply
 static int fan_lse_tc2_lam(const FanLseParams<float>& p) {
     if (p.l_k != 0) return -2;
@@ -693,9 +704,17 @@ static int launch_fan_lse_tc2_D(const FanLseParams<float>& p, bool bwd, cudaStre
     geo.nb = p.nb;
     geo.g_f = (int)p.g_f;
     geo.vec2 = ev2 ? 1 : 0;
+    geo.flat = 1;
+    for (int jj = 0; jj < T2_ND - 1; ++jj) if (geo.sz[jj] != 1) geo.flat = 0;
     geo.n_u = (int)(p.n_rho / geo.L);
     geo.FP = geo.L * p.F;
     geo.NG = (geo.FP + T2_TILES * 128 - 1) / (T2_TILES * 128);
+    if (bwd) {
+        bool v4 = p.o_f == 1 && geo.o_lam == p.F && p.g_f == 1 && geo.g_lam == p.F && geo.FP % 4 == 0 &&
+                  (uintptr_t)p.lse % 16 == 0 && (uintptr_t)p.gout % 16 == 0;
+        for (int jj = 0; jj < T2_ND; ++jj) v4 = v4 && (geo.sz[jj] == 1 || (geo.os[jj] % 4 == 0 && geo.gs[jj] % 4 == 0));
+        geo.lg_vec4 = v4 ? 1 : 0;
+    }
     const i64 n_blocks = ((i64)geo.n_u + T2_US - 1) / T2_US;
     // CTAs per fan group in proportion to the group's tiles (the last group may be short), each at most n_blocks
     const int tiles_total = (geo.FP + 127) / 128;
@@ -719,9 +738,7 @@ static int launch_fan_lse_tc2_D(const FanLseParams<float>& p, bool bwd, cudaStre
         for (int g = geo.NG; g <= T2_MAXG; ++g) geo.cta_lo[g] = blocks;
     }
     if (bwd) {
-        static const cudaError_t attr_true = cudaFuncSetAttribute(fan_lse_tc2_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // once per process
-        (void)attr_true;
-        fan_lse_tc2_kernel<D, true><<<blocks, T2_WARPS * 32, smem, stream>>>(p, geo);
+        launch_fan_lse_tc2_adj<D>(p, geo, blocks, stream);                 // transposed product: fan_tc2b.cuh
     } else {
         static const cudaError_t attr_false = cudaFuncSetAttribute(fan_lse_tc2_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // once per process
         (void)attr_false;
