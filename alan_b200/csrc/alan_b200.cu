@@ -24,7 +24,7 @@
 enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
 enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
        OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13, OP_XREDUCE = 14, OP_NORMAL_Q_BWD = 15, OP_PERM = 16, OP_KGATHER = 17,
-       OP_TS_SAMPLE = 18 };
+       OP_TS_SAMPLE = 18, OP_DEPS = 19 };
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -45,7 +45,7 @@ struct alan_b200_plan {
     std::vector<int> prog_start, prog_nops;
     int sm_count;
     // graph cache (mutable state behind a const handle: guarded by mu)
-    mutable std::mutex mu;
+    mutable std::mutex mu, mu_par;
     mutable std::vector<std::vector<GraphEntry>> graphs;
     mutable std::vector<int> n_out, n_aux;          // per program, learnt on the first run (-1 = unknown)
     mutable unsigned long long tick = 0;
@@ -69,7 +69,17 @@ struct alan_b200_plan {
     // forwarded to this private stream, ordered by a pair of events
     mutable cudaStream_t side = nullptr;
     mutable cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    // Independent ops of a program on parallel branches: while a program is being CAPTURED into a CUDA graph, an op is
+    // enqueued on one of a few side streams unless it depends (OP_DEPS table written by the planner) on the op before
+    // it, so the instantiated graph carries the program's real dependency DAG instead of a chain -- the dozens of
+    // microsecond-scale ops of the global latents and of the top-level contraction run beside the big kernels and
+    // beside each other (ALAN_B200_PAR=0 at plan creation: chain).
+    bool use_par = true;
+    mutable std::vector<cudaStream_t> par_streams;
+    mutable std::vector<cudaEvent_t> par_events;
     ~alan_b200_plan() {
+        for (auto st : par_streams) cudaStreamDestroy(st);
+        for (auto ev : par_events) cudaEventDestroy(ev);
         for (auto& v : graphs) for (auto& g : v) cudaGraphExecDestroy(g.exec);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
@@ -142,11 +152,87 @@ static void read_prog(Reader& r, VMProg<T>& P) {
     P.res = r.i32();
 }
 
+#define AB_PAR_STREAMS 6
 template <typename T>
-static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool count_only, int* launches,
+static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c0, bool count_only, int* launches,
                    std::vector<cudaEvent_t>* events = nullptr) {
     Reader r{plan->blob.data() + plan->prog_start[program]};
     int nl = 0;
+    Ctx c = c0;                                        // c.stream is switched per op when branches are captured
+    // ---- parallel branches (see alan_b200_plan::use_par): only under stream capture, never for profiling / counting
+    const int n_ops = plan->prog_nops[program];
+    bool par = false;
+    if (plan->use_par && !count_only && events == nullptr && !plan->use_seq && n_ops > 2 &&
+        plan->blob[plan->prog_start[program]] == OP_DEPS) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(c0.stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive) par = true;
+        else cudaGetLastError();
+    }
+    std::vector<std::vector<int>> deps;                // per op: earlier ops it must follow
+    std::vector<int> op_stream;                        // stream slot of every op issued so far (0 = the caller's stream)
+    int last_on[AB_PAR_STREAMS];                       // last op issued on each slot (-1: slot unused so far)
+    cudaStream_t slot_stream[AB_PAR_STREAMS];
+    cudaEvent_t ev_start = nullptr;
+    std::unique_lock<std::mutex> par_lock(plan->mu_par, std::defer_lock);
+    if (par) {
+        par_lock.lock();                               // the plan's side streams and events serve one capture at a time
+        while ((int)plan->par_streams.size() < AB_PAR_STREAMS - 1) {
+            cudaStream_t st = nullptr;
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); par = false; break; }
+            plan->par_streams.push_back(st);
+        }
+        while (par && (int)plan->par_events.size() < n_ops + AB_PAR_STREAMS + 1) {
+            cudaEvent_t ev = nullptr;
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); par = false; break; }
+            plan->par_events.push_back(ev);
+        }
+    }
+    if (par) {
+        slot_stream[0] = c0.stream;
+        for (int k = 1; k < AB_PAR_STREAMS; ++k) slot_stream[k] = plan->par_streams[k - 1];
+        for (int k = 0; k < AB_PAR_STREAMS; ++k) last_on[k] = -1;
+        op_stream.assign(n_ops, 0);
+        ev_start = plan->par_events[n_ops];
+        cudaEventRecord(ev_start, c0.stream);
+    }
+    // event of op i = par_events[i], recorded on the op's stream right after its launches
+    auto par_begin = [&](int op_i) {
+        if (!par) return;
+        const std::vector<int>* d = op_i < (int)deps.size() ? &deps[op_i] : nullptr;
+        int slot = -1;
+        if (!d) slot = 0;                              // no table entry: chain on the caller's stream
+        else {
+            // continue the branch of a dependency that is the tip of its stream (the latest such op) ...
+            int best = -1;
+            for (int dep : *d) if (last_on[op_stream[dep]] == dep && dep > best) best = dep;
+            if (best >= 0) slot = op_stream[best];
+            // ... or open a branch on an unused slot; failing that, queue behind the caller's stream
+            if (slot < 0) for (int k = 0; k < AB_PAR_STREAMS; ++k) if (last_on[k] < 0) { slot = k; break; }
+            if (slot < 0) slot = 0;
+        }
+        if (last_on[slot] < 0 && slot != 0) cudaStreamWaitEvent(slot_stream[slot], ev_start, 0);     // fork
+        if (d) for (int dep : *d) if (op_stream[dep] != slot) cudaStreamWaitEvent(slot_stream[slot], plan->par_events[dep], 0);
+        if (!d && op_i > 0)                            // unknown dependencies: after everything issued so far
+            for (int k = 1; k < AB_PAR_STREAMS; ++k) if (last_on[k] >= 0) cudaStreamWaitEvent(slot_stream[0], plan->par_events[last_on[k]], 0);
+        op_stream[op_i] = slot;
+        last_on[slot] = op_i;
+        c.stream = slot_stream[slot];
+    };
+    auto par_end = [&](int op_i) {
+        if (!par) return;
+        cudaEventRecord(plan->par_events[op_i], c.stream);
+    };
+    auto par_join = [&]() {
+        if (!par) return;
+        for (int k = 1; k < AB_PAR_STREAMS; ++k)
+            if (last_on[k] >= 0) {
+                cudaEventRecord(plan->par_events[n_ops + 1 + k], slot_stream[k]);
+                cudaStreamWaitEvent(slot_stream[0], plan->par_events[n_ops + 1 + k], 0);
+            }
+        c.stream = c0.stream;
+    };
+    // an error return in the middle of a program must still bring the side streams back into the capture
+    struct Joiner { decltype(par_join)& j; bool done; ~Joiner() { if (!done) j(); } } joiner{par_join, false};
     // consecutive small ops are collected and run by one launch of small_seq_kernel (kernels.cuh)
     const bool batching = plan->use_seq && events == nullptr;
     SeqParams<T> seq;
@@ -168,6 +254,16 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
         if (events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c.stream); events->push_back(e); }
         int code = r.i32();
         int nwords = r.i32();
+        if (code == OP_DEPS) {
+            // table of the program's op dependencies: n, then per op its count and the indices of the earlier ops
+            const int n = r.i32();
+            deps.assign(n, {});
+            for (int k = 0; k < n; ++k) { const int m = r.i32(); for (int j = 0; j < m; ++j) deps[k].push_back(r.i32()); }
+            r.p = op_begin + nwords;
+            if (par) { op_stream[op_i] = 0; }
+            continue;
+        }
+        par_begin(op_i);
         const bool seqable = code == OP_FILL || code == OP_EXPR || code == OP_EXPR_BWD || code == OP_REDUCE || code == OP_XREDUCE;
         if (!seqable) flush();
         if (count_only && !seqable) {
@@ -589,8 +685,13 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c, bool c
         if (r.p != op_begin + nwords)
             return fail("blob/executor mismatch in op " + std::to_string(op_i) + " (code " + std::to_string(code) +
                         "): consumed " + std::to_string((long)(r.p - op_begin)) + " of " + std::to_string(nwords) + " words");
+        par_end(op_i);
     }
     flush();
+    par_join();
+    joiner.done = true;
+    c0.max_out = c.max_out > c0.max_out ? c.max_out : c0.max_out;
+    c0.max_aux = c.max_aux > c0.max_aux ? c.max_aux : c0.max_aux;
     if (events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c.stream); events->push_back(e); }
     if (launches) *launches = nl;
     if (!count_only) {
@@ -724,6 +825,7 @@ int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** 
     // a graph a tiny kernel costs ~1.7 us all in, less than the same op costs inside the one-CTA interpreter.
     // Hence opt-in (ALAN_B200_SEQ=1); cross-rank reductions always run through it (they are single-CTA by nature).
     { const char* sq = getenv("ALAN_B200_SEQ"); p->use_seq = (sq && sq[0] == '1'); }
+    { const char* sq = getenv("ALAN_B200_PAR"); p->use_par = !(sq && sq[0] == '0'); }
     { const char* sq = getenv("ALAN_B200_SEQ_POINTS"); if (sq) p->seq_points = atoll(sq); }
     { const char* sq = getenv("ALAN_B200_SEQ_BIGSUM"); p->seq_bigsum = (sq && sq[0] == '1'); }
     { const char* sq = getenv("ALAN_B200_SEQ_RESIDENT"); p->seq_resident = !(sq && sq[0] == '0'); }

@@ -347,6 +347,10 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                         mbar_arrive(&tempty[a]);
 #pragma unroll
                         for (int uu = 0; uu < T2_UPT; ++uu) {
+#ifdef TC_EXP_NOEPI
+                            if (uoff[uu] >= 0 && s_ooff[tl * 128 + row] >= 0) { p.out[uoff[uu] + s_ooff[tl * 128 + row]] = __uint_as_float(r[uu][0]) + __uint_as_float(r[uu][31]); }
+                            continue;
+#endif
                             // max as a tree of three-input maxima (FMNMX3), then packed subtract / accumulate around the 32 ex2
                             float m8[8];
 #pragma unroll
@@ -477,8 +481,13 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                 const uint32_t d = tmem + D_COL + T2_N * a;
                 const uint32_t ahi = tmem + A_HI + KT * tl, alo = tmem + A_LO + KT * tl;
                 if (elect_one()) {
+#ifdef TC_EXP_NOMMA
+                    constexpr int KS_ = 1;
+#else
+                    constexpr int KS_ = KSTEPS;
+#endif
 #pragma unroll
-                    for (int j = 0; j < KSTEPS; ++j) {
+                    for (int j = 0; j < KS_; ++j) {
                         const uint64_t dh = smem_desc(bhi + j * 2 * LBO, LBO, SBO), dl = smem_desc(blo + j * 2 * LBO, LBO, SBO);
                         mma_tf32_ts(d, ahi + 8 * j, dh, IDESC, j > 0 ? 1u : 0u);
                         mma_tf32_ts(d, alo + 8 * j, dh, IDESC, 1u);

@@ -175,6 +175,9 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_adj_kernel(const
         const float* lrow = s_lse;
         const float* grow = s_g;
         auto half = [&](const uint32_t (&r)[16], int col) {
+#ifdef TC_EXP_NOEPI
+            acc[0].x += __uint_as_float(r[0]) + __uint_as_float(r[15]); return;
+#endif
 #pragma unroll
             for (int k = 0; k < 16; k += 4) {
                 const float4 l4 = *reinterpret_cast<const float4*>(lrow + col + k);
@@ -264,8 +267,13 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_adj_kernel(const
                 const uint32_t d = tmem + D_COL + 128 * a;
                 const uint32_t bhi = smem_u32(bc_base + (size_t)tl * 2 * OPER), blo = bhi + OPER;
                 if (elect_one()) {
+#ifdef TC_EXP_NOMMA
+                    constexpr int KS_ = 1;
+#else
+                    constexpr int KS_ = KSTEPS;
+#endif
 #pragma unroll
-                    for (int j = 0; j < KSTEPS; ++j) {
+                    for (int j = 0; j < KS_; ++j) {
                         const uint64_t dh = smem_desc(bhi + j * 2 * LBO, LBO, SBO), dl = smem_desc(blo + j * 2 * LBO, LBO, SBO);
                         mma_tf32_ts(d, ahi + 8 * j, dh, IDESC, j > 0 ? 1u : 0u);
                         mma_tf32_ts(d, alo + 8 * j, dh, IDESC, 1u);

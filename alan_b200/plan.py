@@ -34,7 +34,7 @@ MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
 SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
 OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY, OP_DOT, \
-    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD, OP_PERM, OP_KGATHER, OP_TS_SAMPLE = range(1, 19)
+    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD, OP_PERM, OP_KGATHER, OP_TS_SAMPLE, OP_DEPS = range(1, 20)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
 
@@ -127,6 +127,7 @@ class W:
     def __init__(self):
         self.w = []
         self.seen = {}          # id -> PT of every workspace tensor referenced while writing
+        self.refs = []          # every tensor referenced, in order (dependency analysis: Plan.insert_deps)
 
     def i32(self, v):
         v = int(v)
@@ -141,6 +142,7 @@ class W:
         self.i64(struct.unpack('<q', struct.pack('<d', float(v)))[0])
 
     def tref(self, pt: PT):
+        self.refs.append(pt)
         if pt.space == 'ws':
             self.seen[pt.id] = pt
             self.i32(SP_WS); self.i64(pt.offset if pt.offset is not None else 0)
@@ -257,6 +259,23 @@ class Code:
         for c in self.consts:
             w.f64(c)
         w.i32(self.res)
+
+
+class DepsOp(Op):
+    """Not an operation: the dependency table of the program it opens (op index -> indices of the earlier ops it must
+    follow).  The executor uses it while a program is captured into a CUDA graph to put independent ops on parallel
+    branches (csrc/alan_b200.cu run_ops)."""
+    code = OP_DEPS
+
+    def __init__(self, deps):
+        self.deps = deps
+
+    def payload(self, w):
+        w.i32(len(self.deps))
+        for d in self.deps:
+            w.i32(len(d))
+            for j in d:
+                w.i32(j)
 
 
 class FillOp(Op):
@@ -818,10 +837,40 @@ class Plan:
         self.blob = None
         self.retained = {}           # debugging: name -> PT of interesting intermediates
 
+    def insert_deps(self):
+        """Open every program with its dependency table (DepsOp).  Two ops are ordered when they touch the same
+        workspace or output tensor (inputs and aux tensors are read-only; which of the two writes is not tracked, so two
+        readers of one intermediate stay ordered too -- conservative); ops whose footprint is not a list of tensors
+        (region fills, cross-rank reductions) are ordered against everything."""
+        for pi, prog in enumerate(self.programs):
+            ops = [op for op in prog if not isinstance(op, DepsOp)]
+            if len(ops) <= 2:
+                self.programs[pi] = ops
+                continue
+            last = {}                      # tensor key -> index (in the final program, DepsOp = 0) of its last toucher
+            deps, barrier = [[]], 0        # entry 0: the table itself
+            for k, op in enumerate(ops, start=1):
+                if isinstance(op, (FillRegionOp, XReduceOp)):
+                    deps.append(list(range(1, k)))
+                    barrier = k
+                    last = {}
+                    continue
+                w = W()
+                op.payload(w)
+                keys = {(pt.space, pt.id if pt.space == 'ws' else pt.index) for pt in w.refs if pt.space in ('ws', 'output')}
+                d = {last[key] for key in keys if key in last}
+                if barrier:
+                    d.add(barrier)
+                deps.append(sorted(d))
+                for key in keys:
+                    last[key] = k
+            self.programs[pi] = [DepsOp(deps)] + ops
+
     def assign_offsets(self, itemsize):
         """Dry-run serialisation to find the workspace tensors the emitted ops really touch, then lay
         them out: forward tensors first, adjoints/partials after (one contiguous region to zero)."""
         self.adj_region = (0, 0)
+        self.insert_deps()
         w = W()
         for prog in self.programs:
             for op in prog:

@@ -135,6 +135,11 @@ class Emu:
         for op in ops:
             getattr(self, 'op_' + type(op).__name__)(op)
 
+    def op_DepsOp(self, op):
+        """the dependency table of a program: every listed index precedes its op (a chain satisfies it)"""
+        for k, d in enumerate(op.deps):
+            assert all(0 < j < k for j in d), (k, d)
+
     def op_XReduceOp(self, op):
         """cross-rank sum in place (the real collective over gloo when a process group exists, identity otherwise)"""
         import torch.distributed as dist
