@@ -8,6 +8,7 @@
 #include "fan_tc2b.cuh"
 #include "qfactor.cuh"
 #include "sampling.cuh"
+#include "normal_poly.cuh"
 #include <type_traits>
 #include <cstdlib>
 
@@ -24,7 +25,7 @@
 enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
 enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
        OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13, OP_XREDUCE = 14, OP_NORMAL_Q_BWD = 15, OP_PERM = 16, OP_KGATHER = 17,
-       OP_TS_SAMPLE = 18, OP_DEPS = 19 };
+       OP_TS_SAMPLE = 18, OP_DEPS = 19, OP_NORMAL_POLY_SUM = 20 };
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -602,6 +603,36 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c0, bool 
                 p.F = r.i32();
                 p.o_f = r.i64v();
                 if (launch_fan_bwd<T>(q, D, which, c.stream, c.sm_count)) return fail("fan_bwd: unsupported event extent");
+                break;
+            }
+            case OP_NORMAL_POLY_SUM: {
+                NormalPolyParams<T> p;
+                memset(&p, 0, sizeof(p));
+                p.out = (T*)tref(r, c);
+                p.cadd = (T)r.f64();
+                p.n_row = r.i32(); p.n_k = r.i32(); p.n_z = r.i32();
+                p.d.nd = p.n_row + p.n_k + p.n_z; p.d.n_a = p.n_row + p.n_k;
+                if (p.d.nd > AB_MAXD) return fail("normal_poly_sum: too many dims");
+                p.rows = p.ks = p.zs = 1;
+                for (int k = 0; k < p.d.nd; ++k) {
+                    p.d.size[k] = r.i32();
+                    if (k < p.n_row) p.rows *= p.d.size[k]; else if (k < p.d.n_a) p.ks *= p.d.size[k]; else p.zs *= p.d.size[k];
+                }
+                for (int k = 0; k < p.d.n_a; ++k) p.ostride[k] = r.i64v();
+                p.n_zleaf = r.i32();
+                if (p.n_zleaf > NP_MAXLEAF) return fail("normal_poly_sum: too many leaves");
+                for (int l = 0; l < p.n_zleaf; ++l) read_opnd(r, c, p.zleaf[l], p.d.nd, false);
+                p.n_kleaf = r.i32();
+                if (p.n_kleaf > NP_MAXLEAF) return fail("normal_poly_sum: too many leaves");
+                for (int l = 0; l < p.n_kleaf; ++l) read_opnd(r, c, p.kleaf[l], p.d.nd, false);
+                p.n_zt = r.i32();
+                if (p.n_zt > NP_MAXTERM) return fail("normal_poly_sum: too many terms");
+                for (int t = 0; t < p.n_zt; ++t) { p.zt[t].coeff = r.f64(); p.zt[t].z[0] = r.i32(); p.zt[t].z[1] = r.i32(); p.zt[t].k[0] = r.i32(); p.zt[t].k[1] = r.i32(); }
+                p.n_kt = r.i32();
+                if (p.n_kt > NP_MAXTERM) return fail("normal_poly_sum: too many terms");
+                for (int t = 0; t < p.n_kt; ++t) { p.kt[t].coeff = r.f64(); p.kt[t].z[0] = r.i32(); p.kt[t].z[1] = r.i32(); p.kt[t].k[0] = r.i32(); p.kt[t].k[1] = r.i32(); }
+                p.scale_leaf = r.i32(); p.scale_const = r.f64();
+                if (launch_normal_poly_sum<T>(p, c.stream, c.sm_count)) return fail("normal_poly_sum: unsupported shape");
                 break;
             }
             case OP_PERM: {

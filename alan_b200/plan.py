@@ -34,7 +34,7 @@ MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
 SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
 OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY, OP_DOT, \
-    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD, OP_PERM, OP_KGATHER, OP_TS_SAMPLE, OP_DEPS = range(1, 20)
+    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD, OP_PERM, OP_KGATHER, OP_TS_SAMPLE, OP_DEPS, OP_NORMAL_POLY_SUM = range(1, 21)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
 
@@ -725,6 +725,43 @@ class BernDotSumOp(Op):
                 w.i64(lf.stride(ev))
 
 
+class NormalPolySumOp(Op):
+    """out[rows, K...] = cadd + sum_z log N(value; loc, scale) with `value - loc` a polynomial whose monomials are
+    (Z leaves: tensors over the summed plate) x (K leaves: tensors over K axes), scale a K leaf or a constant
+    (csrc/normal_poly.cuh).  `zterms` / `kterms`: [(coeff, [z leaf ids], [k leaf ids])]; `gen_ops` = the unfused
+    (expression, plate sum) ops it stands for."""
+    code = OP_NORMAL_POLY_SUM
+
+    def __init__(self, out, rows, kd, zd, zleaves, kleaves, zterms, kterms, scale_leaf, scale_const, cadd, gen_ops, tag=''):
+        self.out, self.rows, self.kd, self.zd = out, rows, kd, zd
+        self.zleaves, self.kleaves, self.zterms, self.kterms = zleaves, kleaves, zterms, kterms
+        self.scale_leaf, self.scale_const, self.cadd, self.gen_ops, self.tag = scale_leaf, scale_const, cadd, gen_ops, tag
+
+    def payload(self, w):
+        dims = self.rows + self.kd + self.zd
+        w.tref(self.out); w.f64(self.cadd)
+        w.i32(len(self.rows)); w.i32(len(self.kd)); w.i32(len(self.zd))
+        for d in dims:
+            w.i32(d[2])
+        o = plain(self.out)
+        for d in self.rows + self.kd:
+            w.i64(o.stride(d))
+        for leaves in (self.zleaves, self.kleaves):
+            w.i32(len(leaves))
+            for lf in leaves:
+                w.tref(lf.pt)
+                for d in dims:
+                    w.i64(lf.stride(d))
+        for terms in (self.zterms, self.kterms):
+            w.i32(len(terms))
+            for coeff, zs, ks in terms:
+                w.f64(coeff)
+                for ids in (zs, ks):
+                    ids = list(ids) + [-1, -1]
+                    w.i32(ids[0]); w.i32(ids[1])
+        w.i32(self.scale_leaf); w.f64(self.scale_const)
+
+
 class ChainOp(Op):
     code = OP_CHAIN
 
@@ -1003,6 +1040,8 @@ class Planner:
             return [lf.pt for lf, _ in op.bfactors] + [op.v.pt, op.l.pt, op.s.pt] + q
         if isinstance(op, BernDotSumOp):
             return [op.a.pt, op.b.pt, op.y.pt]
+        if isinstance(op, NormalPolySumOp):
+            return [lf.pt for lf in op.zleaves + op.kleaves]
         if isinstance(op, DotOp):
             return [op.a.pt, op.b.pt]
         return []
@@ -1470,6 +1509,8 @@ class Planner:
         n_out = max(1, _prod(d[2] for d in od))
         nsplit = _choose_split(n_out, n)
         fused = self._try_bern_dot_sum(lf, out, od, rd, n) if (self.fast_paths and nsplit == 1) else None
+        if fused is None and self.fast_paths:
+            fused = self._try_normal_poly_sum(lf, out, od, rd, n)
         fan = self._fan_for_plate_sum(lf, od, rd) if (self.fast_paths and nsplit > 1) else None
         if fused is not None:
             self.emit(fused)
@@ -1523,6 +1564,109 @@ class Planner:
         if sorted((d[0], d[1]) for d in od) != sorted((d[0], d[1]) for d in (lam, fdim)):
             return None
         return op
+
+    def _try_normal_poly_sum(self, lf, out, od, rd, n):
+        """Fuse  Normal(value; polynomial loc, scale)  ->  plate sum  into csrc/normal_poly.cuh when the factor is read
+        by nobody else and no gradient flows through it (marginals, moments, RWS, resampling; the reparameterised
+        path keeps the generic expression and its adjoint).  The polynomial is recovered from the traced program."""
+        if len(lf.tensors) != 1 or len(rd) != 1:
+            return None
+        ref, coeff = lf.tensors[0]
+        if coeff != 1.0 or type(ref) is not LeafRef or ref.rename or ref.mode:
+            return None
+        E = self.producer.get(ref.pt.id)
+        if not isinstance(E, ExprOp) or E not in self.fwd or E.red or E.acc or E.scale != 1.0:
+            return None
+        if ref.pt.id in self.needs or ref.pt.id in self.needs_materialised:
+            return None
+        if set((d[0], d[1]) for d in E.keep) != set((d[0], d[1]) for d in od + rd) or any(d[0] != 'ax' for d in E.keep):
+            return None
+        code = E.codeobj
+        if any(type(x) is not LeafRef or x.rename or x.mode for x in code.leaves):
+            return None
+        if any(x.pt.id in self.needs for x in code.leaves):
+            return None
+        op0, dst, ra, rb, rc, _ = code.instrs[-1]
+        if op0 != VOPS['Normal'] or code.res != dst:
+            return None
+        # registers as polynomials over the leaves: {sorted tuple of leaf indices: coefficient}
+        poly = {}
+        for (op, d, a, b, c, _) in code.instrs[:-1]:
+            if op == VOPS['load']:
+                poly[d] = {(a,): 1.0}
+            elif op == VOPS['const']:
+                poly[d] = {(): float(code.consts[a])}
+            elif op in (VOPS['add'], VOPS['sub']):
+                if a not in poly or b not in poly:
+                    return None
+                out_p = dict(poly[a])
+                sgn = 1.0 if op == VOPS['add'] else -1.0
+                for m, cf in poly[b].items():
+                    out_p[m] = out_p.get(m, 0.0) + sgn * cf
+                poly[d] = out_p
+            elif op == VOPS['mul']:
+                if a not in poly or b not in poly:
+                    return None
+                out_p = {}
+                for m1, c1 in poly[a].items():
+                    for m2, c2 in poly[b].items():
+                        m = tuple(sorted(m1 + m2))
+                        out_p[m] = out_p.get(m, 0.0) + c1 * c2
+                poly[d] = out_p
+            elif op == VOPS['neg']:
+                if a not in poly:
+                    return None
+                poly[d] = {m: -cf for m, cf in poly[a].items()}
+            elif op == VOPS['mov']:
+                if a not in poly:
+                    return None
+                poly[d] = dict(poly[a])
+            else:
+                return None
+        if ra not in poly or rb not in poly or rc not in poly:
+            return None
+        resid = dict(poly[ra])
+        for m, cf in poly[rb].items():
+            resid[m] = resid.get(m, 0.0) - cf
+        resid = {m: cf for m, cf in resid.items() if cf != 0.0}
+        sc = poly[rc]
+        zdim = rd[0]
+        is_z = lambda li: code.leaves[li].stride(zdim) != 0
+        # the scale: one K leaf or a constant
+        if len(sc) != 1:
+            return None
+        (sm, scf), = sc.items()
+        if len(sm) > 1 or (len(sm) == 1 and (scf != 1.0 or is_z(sm[0]))):
+            return None
+        zl, kl = [], []                        # leaf indices of the code, in kernel order
+
+        def slot(lst, li):
+            if li not in lst:
+                lst.append(li)
+            return lst.index(li)
+        zterms, kterms = [], []
+        for m, cf in resid.items():
+            zs = [li for li in m if is_z(li)]
+            ks = [li for li in m if not is_z(li)]
+            if len(zs) > 2 or len(ks) > 2:
+                return None
+            if zs:
+                zterms.append((cf, [slot(zl, li) for li in zs], [slot(kl, li) for li in ks]))
+            else:
+                kterms.append((cf, [], [slot(kl, li) for li in ks]))
+        scale_leaf, scale_const = (-1, float(scf)) if len(sm) == 0 else (slot(kl, sm[0]), 0.0)
+        if not (1 <= len(zterms) <= 6) or len(kterms) > 8 or len(zl) > 8 or len(kl) > 8:
+            return None
+        # rows = the output dims some Z leaf walks; K dims = the others (no Z leaf may depend on them, by construction)
+        zleaves, kleaves = [code.leaves[li] for li in zl], [code.leaves[li] for li in kl]
+        rows = [d for d in od if any(x.stride(d) != 0 for x in zleaves)]
+        kd = [d for d in od if d not in rows]
+        if len(rows) + len(kd) + 1 > MAXD:
+            return None
+        R = ReduceOp(R_SUM, out, od, rd, lf.tensors, cadd=lf.const * n)
+        self.fwd.remove(E)
+        return NormalPolySumOp(out, rows, kd, [zdim], zleaves, kleaves, zterms, kterms, scale_leaf, scale_const,
+                               lf.const * n, [E, R], tag='normal_poly_sum:' + E.tag)
 
     def _try_bern_dot_sum(self, lf, out, od, rd, n):
         """Fuse  dot -> Bernoulli(logits) -> plate sum  into csrc/fused.cuh bern_dot_sum_kernel when nobody
@@ -2121,6 +2265,8 @@ def _iterates(op, plate):
         dims = op.rho + [op.kappa]
     elif isinstance(op, BernDotSumOp):
         dims = op.od + op.rd
+    elif isinstance(op, NormalPolySumOp):
+        dims = op.rows + op.kd + op.zd
     elif isinstance(op, ChainOp):
         return plate in op.ms.axes
     else:

@@ -332,6 +332,31 @@ class Emu:
         for g in op.gen_ops:
             getattr(self, 'op_' + type(g).__name__)(g)
 
+    def op_NormalPolySumOp(self, op):
+        """the fused formula of csrc/normal_poly.cuh evaluated from the op's polynomial (not from the ops it replaced)"""
+        dims = op.rows + op.kd + op.zd
+        grid = self.grid(dims)
+        zv = [self.load_leaf(lf, dims, grid)[0] for lf in op.zleaves]
+        kv = [self.load_leaf(lf, dims, grid)[0] for lf in op.kleaves]
+        shape = [d[2] for d in dims]
+        r = t.zeros(shape, dtype=self.dtype)
+        for coeff, zs, ks in op.zterms + op.kterms:
+            term = t.full(shape, coeff, dtype=self.dtype)
+            for i in zs:
+                term = term * zv[i]
+            for i in ks:
+                term = term * kv[i]
+            r = r + term
+        sc = kv[op.scale_leaf] if op.scale_leaf >= 0 else t.full(shape, op.scale_const, dtype=self.dtype)
+        nz = dims[-1][2]
+        sc0 = sc.select(-1, 0)
+        val = op.cadd - (r * r).sum(-1) / (2 * sc0 * sc0) - nz * (sc0.log() + HALF_LOG_2PI)
+        od = op.rows + op.kd
+        ob, obase = self.buf(op.out)
+        ostr = [PL.plain(op.out).stride(d) for d in od]
+        off = self.offsets(ostr, self.grid(od)) + obase
+        ob[off.reshape(-1)] = val.reshape(-1)
+
     def op_DotOp(self, op):
         self.op_ExprOp(op.autodiff_as)
 
