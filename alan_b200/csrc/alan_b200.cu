@@ -9,6 +9,7 @@
 #include "qfactor.cuh"
 #include "sampling.cuh"
 #include "normal_poly.cuh"
+#include "chain.cuh"
 #include <type_traits>
 #include <cstdlib>
 
@@ -270,12 +271,13 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c0, bool 
         if (count_only && !seqable) {
             if (code == OP_CHAIN || code == OP_CHAIN_BWD) {
                 r.p = op_begin + 2; Reader q = r;
-                // skip trefs to read T
+                // skip trefs to read the extents
                 int ntref = (code == OP_CHAIN) ? 3 : 6;
                 q.p += 3 * ntref;
-                q.i64v(); i64 T_ = q.i64v();
-                int lv = 0; for (i64 n = T_; n > 1; n = n / 2 + n % 2) lv++;
-                nl += lv + 1;
+                i64 outer_ = q.i64v(); i64 T_ = q.i64v(); i64 K_ = q.i64v();
+                ChainPlan cp;
+                if (outer_ <= 65535 && chain_plan<T>(T_, K_, cp)) nl += cp.n_phases;          // segment phases (chain.cuh)
+                else { int lv = 0; for (i64 n = T_; n > 1; n = n / 2 + n % 2) lv++; nl += lv + 1; }
             } else if (code != OP_FILL && code != OP_COPY) nl += 1;
             r.p = op_begin + nwords;
             continue;
@@ -407,7 +409,10 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c0, bool 
                 T* levels = (T*)tref(r, c);
                 T* out = (T*)tref(r, c);
                 i64 outer = r.i64v(), Tn = r.i64v(), K = r.i64v();
+                if (launch_chain_fwd<T>(ms, levels, out, outer, Tn, K, c.stream) == 0) break;     // segment phases (chain.cuh)
                 size_t smem = (size_t)(2 * K * K + 2 * K) * sizeof(T);
+                if (smem > 200 * 1024) return fail("chain: K x K does not fit shared memory");
+                if (outer > 65535) return fail("chain: more than 65535 independent chains");
                 if (smem > 48 * 1024)
                     cudaFuncSetAttribute(chain_level_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 const T* X = ms;
@@ -431,7 +436,10 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c0, bool 
                 T* glevels = (T*)tref(r, c);
                 T* gms = (T*)tref(r, c);
                 i64 outer = r.i64v(), Tn = r.i64v(), K = r.i64v();
+                if (launch_chain_bwd<T>(ms, levels, out, gout, glevels, gms, outer, Tn, K, c.stream) == 0) break;
                 size_t smem = (size_t)(3 * K * K + 4 * K) * sizeof(T);
+                if (smem > 200 * 1024) return fail("chain adjoint: K x K does not fit shared memory");
+                if (outer > 65535) return fail("chain adjoint: more than 65535 independent chains");
                 if (smem > 48 * 1024)
                     cudaFuncSetAttribute(chain_level_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 // level table
@@ -1103,6 +1111,7 @@ int64_t alan_b200_chain_scratch_elems(int64_t outer, int64_t T, int64_t K) {
 
 extern "C++" template <typename T>
 int chain_impl(const void* ms_, void* levels_, void* out_, i64 outer, i64 Tn, i64 K, cudaStream_t st) {
+    if (launch_chain_fwd<T>((const T*)ms_, (T*)levels_, (T*)out_, outer, Tn, K, st) == 0) return 0;
     size_t smem = (size_t)(2 * K * K + 2 * K) * sizeof(T);
     if (smem > 200 * 1024) return 1;
     if (smem > 48 * 1024)

@@ -31,6 +31,33 @@ def gpu_time(fn, reps):
     return ts[len(ts) // 2]
 
 
+def replay_time(fn, reps, inner=20):
+    """Device time of `fn` alone: its launches captured once into a CUDA graph (the engine records the op DAG on
+    parallel branches under capture) and replayed `inner` times back to back, so that neither Python nor launch
+    latency is inside the measurement."""
+    st = t.cuda.Stream()
+    st.wait_stream(t.cuda.current_stream())
+    with t.cuda.stream(st):
+        for _ in range(3):
+            fn()
+    t.cuda.current_stream().wait_stream(st)
+    t.cuda.synchronize()
+    g = t.cuda.CUDAGraph()
+    with t.cuda.graph(g, stream=st):
+        fn()
+    g.replay(); t.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(inner):
+            g.replay()
+        b.record(); t.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / inner)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 def radon_sample(S, C, Z, K, seed=1):
     g = t.Generator().manual_seed(seed)
     r = lambda *s: t.randn(s, generator=g)
@@ -54,8 +81,27 @@ def run_radon(S, C, Z, K=10, N=100):
     cells = S * C * Z * K ** 4 + S * C * (4 * K + K ** 3) + S * (2 * K + K ** 3) + K
     ms_m = gpu_time(lambda: s.marginals(), reps)
     ms_i = gpu_time(lambda: s.importance_sample(N, seed=0), reps)
+    # the same two calls with the inputs already resident and canonical on the device (what the API call adds is the
+    # host-side canonicalisation and H2D copy of the sample, not kernel time)
+    mrun = next(r for k, r in prob._runners.items() if isinstance(k, tuple) and len(k) > 4 and k[4] is None and k[2])
+    mt = mrun.device_inputs(s.sample, prob.inputs_params(), prob.data,
+                            {key: NT(t.zeros(mrun.comp.plan.input_pts[name].shape), mrun.comp.plan.input_pts[name].axes)
+                             for key, name in mrun.comp.elf_keys.items()})
+    dev_m = gpu_time(lambda: (mrun.forward_raw(mt), mrun.backward_raw(mt)), reps)
+    irun = next(r for k, r in prob._runners.items() if isinstance(k, tuple) and len(k) > 4 and k[4] == N)
+    it_ = irun.device_inputs(s.sample, prob.inputs_params(), prob.data)
+    g = t.Generator(device="cuda:0"); g.manual_seed(0)
+    us = [t.rand([irun.comp.sizes[a] for a in batch] + [N], dtype=t.float64, device="cuda:0", generator=g)
+          for batch, _ in irun.comp.plan.sample_steps]
+    dev_i = gpu_time(lambda: (irun.forward_raw(it_), irun.resample_raw(it_, us)), reps)
+    rep_m = replay_time(lambda: (mrun.forward_raw(mt), mrun.backward_raw(mt)), reps)
+    rep_i = replay_time(lambda: (irun.forward_raw(it_), irun.resample_raw(it_, us)), reps)
     return dict(config=f"cfg3 radon S={S} C={C} Z={Z} K={K}", cells=cells, marginals_ms=ms_m,
-                importance_sample_ms=ms_i, N=N, cells_per_s=cells / ((ms_m + ms_i) * 1e-3))
+                importance_sample_ms=ms_i, marginals_device_ms=dev_m, importance_sample_device_ms=dev_i,
+                marginals_graph_replay_ms=rep_m, importance_sample_graph_replay_ms=rep_i,
+                launches=dict(marginals=sum(mrun.dp.launches[:mrun.comp.plan.n_fwd + mrun.comp.plan.n_bwd]),
+                              importance_sample=sum(irun.dp.launches[:irun.comp.plan.n_fwd]) + irun.dp.launches[irun.comp.plan.sample_prog]),
+                N=N, cells_per_s=cells / ((ms_m + ms_i) * 1e-3))
 
 
 def run_timeseries(T=1000, K=16):
@@ -69,7 +115,19 @@ def run_timeseries(T=1000, K=16):
     ms_e = gpu_time(lambda: s.elbo_nograd(), reps)
     ms_m = gpu_time(lambda: s.moments(moms), reps)
     cells = T * K * K + T * K + K
+    erun = s._runner(())
+    et = erun.device_inputs(s.sample, prob.inputs_params(), prob.data)
+    dev_e = gpu_time(lambda: erun.forward_raw(et), reps)
+    mrun = s._runner(moment_specs=[((v,), f) for v, f in moms])
+    mt = mrun.device_inputs(s.sample, prob.inputs_params(), prob.data)
+    dev_m = gpu_time(lambda: (mrun.forward_raw(mt), mrun.backward_raw(mt)), reps)
+    rep_e = replay_time(lambda: erun.forward_raw(et), reps)
+    rep_m = replay_time(lambda: (mrun.forward_raw(mt), mrun.backward_raw(mt)), reps)
     return dict(config=f"cfg4 timeseries T={T} K={K}", cells=cells, elbo_nograd_ms=ms_e, moments_ms=ms_m,
+                elbo_nograd_device_ms=dev_e, moments_device_ms=dev_m,
+                elbo_nograd_graph_replay_ms=rep_e, moments_graph_replay_ms=rep_m,
+                launches=dict(elbo_nograd=sum(erun.dp.launches[:erun.comp.plan.n_fwd]),
+                              moments=sum(mrun.dp.launches[:mrun.comp.plan.n_fwd + mrun.comp.plan.n_bwd])),
                 cells_per_s=cells / ((ms_e + ms_m) * 1e-3))
 
 

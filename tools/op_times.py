@@ -32,6 +32,22 @@ if name.startswith("radon"):
     run = Runner(comp, "cuda:0")
     plan = comp.plan
     tensors = [x.cuda() for x in comp.canonical_inputs(sample, ip, data, elf)]
+elif name.startswith("ts"):
+    # cfg4: Timeseries T=1000, K=16; "ts" = elbo (forward only), "tsm" = moments (forward + adjoint)
+    import models
+    from alan_b200 import model as M
+    from alan_b200.named import NT, from_torch_named
+    T_, K_ = 1000, 16
+    inp = models.timeseries_inputs(T=T_)
+    P, Q = models.timeseries_model(M)
+    g = t.Generator().manual_seed(2)
+    sample = {'init': NT(t.randn(K_, generator=g), ('K_init',)), 'ts': NT(t.randn(T_, K_, generator=g), ('T', 'K_ts'))}
+    data = {'obs': from_torch_named(inp['data']['obs'])}
+    moms = [(('ts',), models.MOMENT_FUNCS['mean']), (('ts',), models.MOMENT_FUNCS['mean2'])] if name == "tsm" else ()
+    comp = Compiled(P, Q, sample, {}, data, moment_specs=moms)
+    run = Runner(comp, "cuda:0")
+    plan = comp.plan
+    tensors = run.device_inputs(sample, {}, data)
 else:
     vi = name.endswith("vi")                  # e.g. cfg5vi: gradients w.r.t. the samples too (reparameterised path)
     cfg = bench.WORKLOADS[name[:-2] if vi else name]
