@@ -26,7 +26,7 @@
 enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
 enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
        OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13, OP_XREDUCE = 14, OP_NORMAL_Q_BWD = 15, OP_PERM = 16, OP_KGATHER = 17,
-       OP_TS_SAMPLE = 18, OP_DEPS = 19, OP_NORMAL_POLY_SUM = 20 };
+       OP_TS_SAMPLE = 18, OP_DEPS = 19, OP_NORMAL_POLY_SUM = 20, OP_PASTE = 21 };
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -641,6 +641,18 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c0, bool 
                 for (int t = 0; t < p.n_kt; ++t) { p.kt[t].coeff = r.f64(); p.kt[t].z[0] = r.i32(); p.kt[t].z[1] = r.i32(); p.kt[t].k[0] = r.i32(); p.kt[t].k[1] = r.i32(); }
                 p.scale_leaf = r.i32(); p.scale_const = r.f64();
                 if (launch_normal_poly_sum<T>(p, c.stream, c.sm_count)) return fail("normal_poly_sum: unsupported shape");
+                break;
+            }
+            case OP_PASTE: {
+                const T* src = (const T*)tref(r, c);
+                T* dst = (T*)tref(r, c);
+                PasteParams p;
+                memset(&p, 0, sizeof(p));
+                p.nd = r.i32();
+                if (p.nd > AB_MAXD) return fail("paste: too many dims");
+                p.total = 1;
+                for (int k = 0; k < p.nd; ++k) { p.size[k] = r.i32(); p.ss[k] = r.i64v(); p.ds[k] = r.i64v(); p.total *= p.size[k]; }
+                paste_kernel<T><<<grid_for(p.total, 256, c), 256, 0, c.stream>>>(src, dst, p);
                 break;
             }
             case OP_PERM: {

@@ -47,6 +47,22 @@ __global__ void kgather_kernel(const E* __restrict__ x, const i64* __restrict__ 
     }
 }
 
+// dst[idx . dstride] = src[idx . sstride] over a small index box (prediction: the posterior block pasted into the extended draw)
+struct PasteParams { int nd; int size[AB_MAXD]; i64 ss[AB_MAXD], ds[AB_MAXD]; i64 total; };
+template <typename E>
+__global__ void paste_kernel(const E* __restrict__ src, E* __restrict__ dst, const __grid_constant__ PasteParams p) {
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < p.total; e += (i64)gridDim.x * blockDim.x) {
+        i64 r = e, so = 0, d_o = 0;
+        for (int k = p.nd - 1; k >= 0; --k) {
+            const i64 q = r / p.size[k];
+            const i64 i = r - q * p.size[k];
+            so += i * p.ss[k]; d_o += i * p.ds[k];
+            r = q;
+        }
+        dst[d_o] = src[so];
+    }
+}
+
 // Timeseries draw.  The expression (ExprParams, nothing summed) is laid out over dims [outer..., T, K, event...] with
 // n_a = nd; leaf `prev_leaf` is the previous state.  out: [outer, T, K, E] contiguous (E = product of the event dims);
 // init: the (already resampled) initial state [outer, K, E]; perm: timeseries_perm [outer, T, K] (null: no permutation).

@@ -34,7 +34,7 @@ MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
 SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
 OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY, OP_DOT, \
-    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD, OP_PERM, OP_KGATHER, OP_TS_SAMPLE, OP_DEPS, OP_NORMAL_POLY_SUM = range(1, 21)
+    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD, OP_PERM, OP_KGATHER, OP_TS_SAMPLE, OP_DEPS, OP_NORMAL_POLY_SUM, OP_PASTE = range(1, 22)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
 
@@ -680,6 +680,25 @@ class TsSampleOp(Op):
         if self.perm is not None:
             w.tref(self.perm)
         w.i64(self.n_outer); w.i32(self.T); w.i32(self.K); w.i32(self.E)
+
+
+class PasteOp(Op):
+    """dst[i0, i1, ...] = src[i0, i1, ...] for i_k < size_k: a block of a smaller tensor written into the leading corner
+    of a larger one (prediction: the posterior sample / the observed data pasted into the extended draw, reference
+    dist.py:256-267).  dims: [(size, src stride, dst stride)].  csrc/sampling.cuh paste_kernel."""
+    code = OP_PASTE
+
+    def __init__(self, src, dst, dims):
+        self.src, self.dst, self.dims, self.out = src, dst, [tuple(int(x) for x in d) for d in dims], dst
+
+    def payload(self, w):
+        w.tref(self.src); w.tref(self.dst)
+        dims = [d for d in self.dims if d[0] > 1] or [(1, 0, 0)]
+        if len(dims) > MAXD:
+            raise Exception("paste: too many dims")
+        w.i32(len(dims))
+        for size, ss, ds in dims:
+            w.i32(size); w.i64(ss); w.i64(ds)
 
 
 class DotOp(Op):

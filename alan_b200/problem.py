@@ -309,7 +309,8 @@ class Sample:
             got = runtime.gather(xc, idx[grp].t.reshape(N, outer), outer, K, inner)
             out[name] = NT(got.reshape([N] + [run.comp.sizes[a] for a in plates] + list(x.pos_shape)),
                            ('N',) + plates)
-        return out
+        from .predict import ImportanceSample
+        return ImportanceSample(p, out, N)             # a dict {varname: NT} with .extend() / .moments() / .dump()
 
     # ------------------------------------------------------------------ helpers
     def _sizes(self):

@@ -159,6 +159,15 @@ class Emu:
             p = t.argsort(u, dim=-1, stable=True)
         self.side[('perm', op.out.id)] = p                      # int64: kept beside the (float) workspace
 
+    def op_PasteOp(self, op):
+        sb, sbase = self.buf(op.src)
+        db, dbase = self.buf(op.dst)
+        dims = [d for d in op.dims if d[0] > 1] or [(1, 0, 0)]
+        grid = t.meshgrid(*[t.arange(d[0]) for d in dims], indexing='ij')
+        so = sum(g * d[1] for g, d in zip(grid, dims)) + sbase
+        do = sum(g * d[2] for g, d in zip(grid, dims)) + dbase
+        db[do.reshape(-1)] = sb[so.reshape(-1)]
+
     def op_KGatherOp(self, op):
         xb, xbase = self.buf(op.x)
         x = xb[xbase:xbase + op.outer * op.K * op.inner].reshape(op.outer, op.K, op.inner)
