@@ -1004,7 +1004,7 @@ __global__ void __launch_bounds__(256) chain_level_bwd_kernel(const T* __restric
 // ------------------------------------------------------------------------------------------
 // K7: posterior resampling of one contraction step (reference reduce_Ks.py:51-75).
 // One thread per (n, plate cell).  lp_j = sum_f coeff_f F_f gathered at the already-sampled
-// parent indices; p_j = exp(double(lp_j) - max); index = first j with cumsum_j >= u * total;
+// parent indices; p_j = exp(lp_j - max) in the factor dtype; index = first j with cumsum_j (float64) >= u * total;
 // j is unravelled row-major over the step's K axes (unravel_index.py:97-100).
 // ------------------------------------------------------------------------------------------
 #define AB_MAXK 4
@@ -1065,13 +1065,15 @@ __global__ void __launch_bounds__(128) sample_kernel(const __grid_constant__ Sam
         const double u = p.u[uoff];
         T m = neg_inf<T>();
         for (i64 j = 0; j < p.ktotal; ++j) m = ab_max(m, sample_lp(p, base, j));
+        // p_j = exp(lp_j - max) in the FACTOR dtype, as the reference forms it before torch.multinomial
+        // (reduce_Ks.py:62-66); the cumulative sum and the comparison with u are in float64
         double total = 0.0;
-        for (i64 j = 0; j < p.ktotal; ++j) total += exp((double)sample_lp(p, base, j) - (double)m);
+        for (i64 j = 0; j < p.ktotal; ++j) total += (double)ab_exp(sample_lp(p, base, j) - m);
         const double thr = u * total;
         double c = 0.0;
         i64 pick = p.ktotal - 1;
         for (i64 j = 0; j < p.ktotal; ++j) {
-            c += exp((double)sample_lp(p, base, j) - (double)m);
+            c += (double)ab_exp(sample_lp(p, base, j) - m);
             if (!(c < thr)) { pick = j; break; }
         }
         for (int k = p.nk - 1; k >= 0; --k) { p.out[k][b] = pick % p.ksize[k]; pick /= p.ksize[k]; }

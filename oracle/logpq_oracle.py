@@ -624,7 +624,8 @@ def inverse_cdf_draw(lp: ONT, kaxes, u: ONT, N_axis="N") -> dict:
 
     lp: log-factor with named axes = batch axes (plates, possibly N) + kaxes.
     u : float64 uniforms with axes = batch axes of lp (without N) + (N,).
-    Rule: p_j = exp(float64(lp_j) - max_j), j row-major over kaxes; c = cumsum(p);
+    Rule: p_j = exp(lp_j - max_j) in the factor dtype (reduce_Ks.py:62-66), then float64: j row-major over kaxes;
+    c = cumsum(p);
     index = first j with c_j >= u * c_last (clamped to the last category).
     Returns {kaxis: integer ONT with axes (N, batch...)}.
     """
@@ -637,10 +638,10 @@ def inverse_cdf_draw(lp: ONT, kaxes, u: ONT, N_axis="N") -> dict:
     order = (N_axis,) + b_noN
     x = lp.order(order + tuple(kaxes))
     ksz = [x.sizes()[k] for k in kaxes]
-    raw = x.t.reshape(*[x.sizes()[a] for a in order], -1).to(t.float64)
+    raw = x.t.reshape(*[x.sizes()[a] for a in order], -1)
     uu = u.order(order).t.to(t.float64)
     m = raw.amax(-1, keepdim=True)
-    p = (raw - m).exp()
+    p = (raw - m).exp().to(t.float64)
     c = p.cumsum(-1)
     thr = (uu * c[..., -1]).unsqueeze(-1)
     flat = (c < thr).sum(-1).clamp(max=raw.shape[-1] - 1)

@@ -492,7 +492,7 @@ class Emu:
         ub, ubase = self.buf(pt)
         u = ub[self.offsets(PL._strides_like(pt, own, op.batch), grid) + ubase]
         m = lp.amax(-1, keepdim=True)
-        p = t.exp(lp.double() - m.double())
+        p = t.exp(lp - m).double()                                 # factor dtype, then float64 (Appendix A8)
         c = p.cumsum(-1)
         thr = (u * c[..., -1]).unsqueeze(-1)
         pick = (c < thr).sum(-1).clamp(max=ktot - 1)

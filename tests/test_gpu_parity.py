@@ -175,8 +175,8 @@ def test_marginals_and_moments_vs_reference_golden(case, tag):
 @pytest.mark.parametrize("case", [c for c in CASES if models.CASES[c][6] is not None])
 def test_resampling_indices(case, tag):
     """(1) bit-exact against the same inverse-CDF rule applied on CPU to the engine's own factor
-    tensors (copied back from the device workspace); (2) against the reference's tree walk
-    (golden), where exp() is taken in a different precision: < 0.1 % may differ."""
+    tensors (copied back from the device workspace); (2) every index equal to the reference's tree walk
+    (golden; exp in the factor dtype, cumulative sum and comparison in float64 on both sides)."""
     from plan_emulator import Emu
     Compiled, Runner = _engine()
     g = load(case, tag)
@@ -207,7 +207,7 @@ def test_resampling_indices(case, tag):
         mine = idx[grp].order(axes).t.cpu()
         total += ref.numel()
         bad += (mine != ref).sum().item()
-    assert bad <= 1e-3 * total, f"{bad}/{total} indices differ from the reference walk"
+    assert bad == 0, f"{bad}/{total} indices differ from the reference walk"
     # gather (index_into_sample) is a bit-exact copy
     from alan_b200 import runtime
     v2g = Q.varname2groupvarname()
@@ -222,6 +222,39 @@ def test_resampling_indices(case, tag):
         ii = idx[grp].t.cpu().reshape(N, outer)
         ref = xc.reshape(outer, K, inner)[t.arange(outer)[None, :], ii]
         assert t.equal(got, ref)
+
+
+@pytest.mark.parametrize("tag", list(TAGS))
+@pytest.mark.parametrize("name", ['cfg2_movielens_300x5_K30', 'cfg3_radon_12x16x10_K10'])
+def test_resampling_indices_baseline_size(name, tag):
+    """BASELINE cfg-2 / cfg-3 shapes, importance_sample(N = 100): 3.0e4 + 7.9e4 indices of the UNMODIFIED reference walk
+    (tests/golden/make_golden_resampling.py; inputs, sample and uniforms regenerated from seeds).  float64: every index
+    must agree.  float32: the device's factor tensors differ from the reference's in the last bits (fused kernels,
+    different summation orders, expf against the host's exp), so a uniform within ~1e-7 of a CDF step can resolve
+    differently: at most 1e-4 of the draws; the count is printed."""
+    import os
+    import resample_cases as RC
+    from golden_io import GOLDEN_DIR
+    from alan_b200.named import from_torch_named
+    Compiled, Runner = _engine()
+    g = t.load(os.path.join(GOLDEN_DIR, f"resample_{name}_{tag}.pt"), weights_only=False)
+    P, Q, inp, sample, K, N = RC.build(name, TAGS[tag], g['seed'])
+    nt = lambda d: {k: from_torch_named(v) if any(n is not None for n in v.names) else NT(v, ()) for k, v in d.items()}
+    ip, data = {**nt(inp['inputs']), **nt(inp['params'])}, nt(inp['data'])
+    comp = Compiled(P, Q, sample, ip, data, N=N)
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(sample, ip, data)
+    run.forward_raw(tensors)
+    src = UniformSource(g["uniform_seed"], N, inp["platesizes"], list(inp["platesizes"]))
+    us = [src.draw(batch)[0] for batch, ks in comp.plan.sample_steps]
+    idx = run.resample_raw(tensors, [u.cuda() for u in us])
+    total = bad = 0
+    for grp, (ref, axes) in g["indices"].items():
+        mine = idx[grp].order(axes).t.cpu()
+        total += ref.numel()
+        bad += (mine != ref.long()).sum().item()
+    print(f"resampling {name} {tag}: {bad} of {total} indices differ from the reference walk")
+    assert total >= 3e4 and bad <= (0 if tag == 'f64' else 1e-4 * total), f"{bad}/{total} indices differ"
 
 
 # ------------------------------------------------------------------------------ oracle at larger sizes
