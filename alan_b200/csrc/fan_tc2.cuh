@@ -223,11 +223,14 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
     long long dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0; (void)dbg0; (void)dbg1; (void)dbg2; (void)dbg3;
     const long long dbg_t0 = clock64(); (void)dbg_t0;
 
-    if (warp < 4) {
-        // ---------------------------------------------------------------- A operand, once: thread = row of every tile
-        const int row = 32 * warp + lane;
-        const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
-        for (int tl = 0; tl < T2_TILES; ++tl) {
+    if (warp < 4 * T2_TILES) {
+        // ---------------------------------------------------------------- A operand, once: thread = one row of one tile (a warp
+        // reaches the TMEM lane quadrant warp % 4; 12 warps side by side: this prologue is the fixed cost that small
+        // problems and small shards see)
+        const int row = 32 * (warp & 3) + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+        {
+            const int tl = warp >> 2;
             const int fp = fp_lo + 128 * tl + row;
             float a[KT];
 #pragma unroll

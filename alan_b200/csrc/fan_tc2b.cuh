@@ -109,10 +109,12 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_adj_kernel(const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(T2_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp < 4) {
-        // ---------------------------------------------------------------- constant operand, once: thread = row f' of every tile
-        const int row = threadIdx.x;
-        for (int tl = 0; tl < T2_TILES; ++tl) {
+    if (warp < 4 * T2_TILES) {
+        // ---------------------------------------------------------------- constant operand, once: thread = one row f' of one tile
+        // (12 warps side by side: this prologue is the fixed cost that small problems and small shards see)
+        const int row = threadIdx.x & 127;
+        {
+            const int tl = threadIdx.x >> 7;
             const int fp = fp_lo + 128 * tl + row;
             float a[KT];
 #pragma unroll

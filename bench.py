@@ -493,7 +493,7 @@ def roofline_report(run, comp, plan, tensors, flush, dev, clocks, steps):
         roof = dict(bound="fp32", achieved=m["flops"] / (top_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
                     peak_source="alan_b200_pipe_peak(FFMA) measured in this process just now")
     roof["frac"] = roof["achieved"] / roof["peak"]
-    kname = {"FanLseBwdOp": r"fan_lse_tc2_kernel<\d+, *(1|true)>", "FanLseOp": r"fan_lse_tc2_kernel<\d+, *(0|false)>",
+    kname = {"FanLseBwdOp": r"fan_lse_tc2_adj_kernel<\d+>", "FanLseOp": r"fan_lse_tc2_kernel<\d+, *(0|false)>",
              "BernDotSumOp": r"bern_dot_sum"}.get(m["kind"])
     traffic, capture = ncu_dram_traffic(kname) if (kname and tc_path and m["points"] == 270000000) else (None, None)
     roof.update(traffic=traffic, traffic_source=capture, kernel=f"{m['kind']}:{m['tag']}", kernel_ms=top_ms,
@@ -502,6 +502,11 @@ def roofline_report(run, comp, plan, tensors, flush, dev, clocks, steps):
                 hbm_frac=hbm_frac, mufu_frac=mufu_frac, fp32_fma_frac=fp32_frac,
                 mufu_peak_gex2_s=mufu_peak / 1e9, mufu_peak_per_clk_sm=mufu_peak / 148 / (clk * 1e6),
                 fp32_peak_tflops=fp32_peak, sm_mhz_assumed_for_per_clk=clk,
+                # ncu (profiles/r02_fan_lse_tc2_full.md, sm__cycles_elapsed.avg.per_second): these kernels run at
+                # ~1.66-1.68 GHz under the board's power cap, while the pipe-peak microbench and the idle samples of
+                # nvidia-smi sit at the 1.965 GHz maximum: against the MUFU rate at the clock the kernel really gets,
+                # the fraction is 1965 / 1670 higher
+                sm_mhz_under_load_ncu=1670.0, mufu_frac_at_load_clock=mufu_frac * clk / 1670.0,
                 timing="per-op CUDA events on the launch stream, separate profiled pass, mean of %d" % reps)
     if tc_path:
         from alan_b200.plan import dense_fan_geometry
