@@ -10,6 +10,7 @@
 #include "sampling.cuh"
 #include "normal_poly.cuh"
 #include "chain.cuh"
+#include "qem.cuh"
 #include <type_traits>
 #include <cstdlib>
 
@@ -1085,6 +1086,34 @@ int alan_b200_gather(const void* x, const int64_t* idx, void* out, int elem_byte
     else if (elem_bytes == 8)
         gather_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x, (const i64*)idx, (double*)out, N, outer, K, inner, outer_div);
     else return fail("gather: element size must be 4 or 8 bytes");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("CUDA launch error: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C++" template <typename T>
+int qem_update_impl(int family, i64 n, double lr, const void* new0, const void* new1, void* mean0, void* mean1,
+                    void* param0, void* param1, cudaStream_t st) {
+    QemParams<T> p;
+    p.family = family; p.n = n; p.lr = (T)lr; p.one_minus_lr = (T)(1.0 - lr);
+    p.m0 = (const T*)new0; p.m1 = (const T*)new1; p.e0 = (T*)mean0; p.e1 = (T*)mean1; p.p0 = (T*)param0; p.p1 = (T*)param1;
+    i64 g = (n + 255) / 256;
+    qem_update_kernel<T><<<(int)(g > 148 * 8 ? 148 * 8 : g), 256, 0, st>>>(p);
+    return 0;
+}
+
+int alan_b200_qem_update(int family, int64_t n, double lr, const void* new0, const void* new1, void* mean0, void* mean1,
+                         void* param0, void* param1, int dtype, void* stream) {
+    if (n <= 0) return 0;
+    if (family < QF_NORMAL || family > QF_BETA) return fail("qem_update: unknown family");
+    const bool two_stats = family == QF_NORMAL || family == QF_GAMMA || family == QF_BETA;
+    const bool two_params = two_stats;
+    if (!new0 || !mean0 || !param0 || (two_stats && (!new1 || !mean1)) || (two_params && !param1))
+        return fail("qem_update: missing moment / mean / parameter buffer for this family");
+    if (!two_stats) { new1 = nullptr; mean1 = nullptr; }
+    if (dtype == 0) qem_update_impl<float>(family, n, lr, new0, new1, mean0, mean1, param0, param1, (cudaStream_t)stream);
+    else if (dtype == 1) qem_update_impl<double>(family, n, lr, new0, new1, mean0, mean1, param0, param1, (cudaStream_t)stream);
+    else return fail("qem_update: dtype must be 0 (f32) or 1 (f64)");
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(std::string("CUDA launch error: ") + cudaGetErrorString(e));
     return 0;

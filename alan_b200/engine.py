@@ -17,7 +17,7 @@ import torch
 
 from .model import Plate, Kname, check_PQ
 from .named import NT
-from .plan import Planner, TensorSig, Plan
+from .plan import Planner, TensorSig, Plan, NONMP_K
 from .trace import Expr, trace_function
 
 
@@ -36,7 +36,7 @@ class Compiled:
     """Plan + the canonical (contiguous, canonical axis order, working dtype) input list."""
     def __init__(self, P: Plate, Q: Plate, sample, inputs_params, data, extra_log_factors=None,
                  moment_specs=(), grad_names=(), N=None, shard_plate=None, world_size=1, dtype=None,
-                 fast_paths=True, fused_collectives=False):
+                 fast_paths=True, fused_collectives=False, nonmp=False):
         sample, inputs_params, data = dict(sample), dict(inputs_params or {}), dict(data or {})
         elf = dict(extra_log_factors or {})
         check_PQ(P, Q, set(data.keys()))
@@ -44,7 +44,7 @@ class Compiled:
         self.dtype = dtype or working_dtype(sample, inputs_params, data, elf)
         all_plates = P.all_platenames()
         groups = Q.groupvarnames()
-        canon = list(all_plates) + [Kname(g) for g in groups]
+        canon = list(all_plates) + ([NONMP_K] if nonmp else [Kname(g) for g in groups])
         sizes = {}
         named = {}
         for role, d in (('sample', sample), ('param', inputs_params), ('data', data), ('elf', elf)):
@@ -70,7 +70,7 @@ class Compiled:
                 self.elf_keys[orig] = key
         planner = Planner(P, Q, sig, sizes, self.dtype, want_sample_N=N, shard_plate=shard_plate,
                           world_size=world_size, fast_paths=fast_paths,
-                          fused_collectives=fused_collectives and world_size > 1 and N is None)
+                          fused_collectives=fused_collectives and world_size > 1 and N is None, nonmp=nonmp)
         for orig, key in self.elf_keys.items():
             s = sig[key]
             extra.append((orig, Expr.leaf(planner.inputs[key], s.axes, s.pos_shape)))

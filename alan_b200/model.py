@@ -50,6 +50,28 @@ def function_arguments(f):
     return tuple(inspect.signature(f).parameters.keys())
 
 
+class Param:
+    """A parameter declared in place, as a direct argument of a distribution (reference src/alan/Param.py)."""
+    def __init__(self, init, ignore_platenames=(), name=None):
+        if isinstance(init, numbers.Number):
+            init = torch.tensor(float(init))
+        if not isinstance(init, torch.Tensor):
+            raise Exception("the initial value of an OptParam / QEMParam must be a number or a tensor")
+        self.init, self.ignore_platenames, self.name = init.detach(), tuple(ignore_platenames), name
+        self.trans = None
+
+
+class OptParam(Param):
+    """Learned by optimisation: `Normal(OptParam(0.), OptParam(1., transformation=t.exp))` (Param.py:17-25)."""
+    def __init__(self, init, transformation=None, ignore_platenames=(), name=None):
+        super().__init__(init, ignore_platenames, name)
+        self.trans = transformation
+
+
+class QEMParam(Param):
+    """Learned by QEM, the moving average of posterior moments (Param.py:27-32, BoundPlate.py:256-296)."""
+
+
 class Dist:
     """One distribution node: a family plus unresolved arguments."""
     is_timeseries = False
@@ -87,9 +109,21 @@ class Dist:
                 self.all_args.extend(function_arguments(v))
             elif isinstance(v, torch.Tensor):
                 v = v.detach()
+            elif isinstance(v, Param):
+                pass                                   # becomes a named parameter when a Problem binds the model (qem.py)
             elif not isinstance(v, numbers.Number):
                 raise Exception(f"{family}.{k}: unsupported argument type {type(v)}")
             self.args[k] = v
+
+        # reference dist.py:140-159
+        self.qem_dist = any(isinstance(v, QEMParam) for v in self.args.values())
+        self.opt_dist = any(isinstance(v, OptParam) for v in self.args.values())
+        if self.qem_dist:
+            vals = list(self.args.values())
+            if not all(isinstance(v, QEMParam) for v in vals) or \
+                    any(set(v.ignore_platenames) != set(vals[0].ignore_platenames) for v in vals[1:]):
+                raise Exception("If one parameter on a distribution is a QEMParam, then all parameters on that "
+                                "distribution should be QEM distributions")
 
     def __repr__(self):
         return f"{self.family}({', '.join(f'{k}={v!r}' for k, v in self.args.items())})"
@@ -139,6 +173,8 @@ class Timeseries:
                             "variable name in the above plate")
         if not isinstance(trans, Dist):
             raise Exception("the second / `trans` argument in a Timeseries should be a distribution")
+        if trans.qem_dist or trans.opt_dist:
+            raise Exception("You can't use QEMParam / OptParam in a timeseries at present")
         self.init = init
         self.trans = trans
         self.all_args = [init, *trans.all_args]

@@ -37,6 +37,7 @@ OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_
     OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD, OP_PERM, OP_KGATHER, OP_TS_SAMPLE, OP_DEPS, OP_NORMAL_POLY_SUM, OP_PASTE = range(1, 22)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
+NONMP_K = 'K_'          # the one K axis every latent shares in a SampleNonMP plan (no group can be named '')
 
 VOPS = {'load': 0, 'const': 1, 'add': 2, 'sub': 3, 'mul': 4, 'div': 5, 'neg': 6, 'exp': 7, 'log': 8, 'sigmoid': 9,
         'square': 10, 'sqrt': 11, 'reciprocal': 12, 'softplus': 13, 'tanh': 14, 'abs': 15, 'log1p': 16, 'pow': 17,
@@ -969,7 +970,7 @@ class Plan:
 class Planner:
     def __init__(self, P: Plate, Q: Plate, sig: dict, sizes: dict, dtype, extra_factors=(), want_sample_N=None,
                  shard_plate=None, world_size=1, constants=None, fast_paths=True, grad_names=(),
-                 fused_collectives=False):
+                 fused_collectives=False, nonmp=False):
         """sig: name -> TensorSig for samples, inputs/params, data and tensor-valued extra factors.
         sizes: axis name -> extent (plates and K axes).
         extra_factors: [(key, Expr)] expressions over input leaves, added as log factors at the plate
@@ -992,7 +993,9 @@ class Planner:
         self.groups = Q.groupvarnames()
         self.v2g = Q.varname2groupvarname()
         self.g2plates = Q.groupvarname2platenames()
-        self.canon = list(self.all_plates) + [Kname(g) for g in self.groups]
+        # nonmp: every latent shares ONE K axis (reference SampleNonMP.py:22-26 `unify_dims`), no K is contracted
+        self.nonmp = bool(nonmp)
+        self.canon = list(self.all_plates) + ([NONMP_K] if self.nonmp else [Kname(g) for g in self.groups])
         self.plan.canon_axes = self.canon
         self.ws_off = 0
         self.alloc_group = 0
@@ -1402,6 +1405,73 @@ class Planner:
         prev = Expr.make('add', shifted, first)
         return {**scope, 'prev': prev}, Kinit
 
+    # -- global importance sampling baseline (SampleNonMP.py:127-203 `non_mp_log_prob`) ---------------
+    def plan_nonmp(self, name, P: Plate, Q: Plate, active, scope):
+        """One plate level of the non-massively-parallel log-probability: every sample carries the single axis
+        NONMP_K, every factor is `[active plates..., K]`, nothing is contracted: log P - log Q per variable, summed
+        over the plates level by level (the plate sums take the same fused paths as the MP plan)."""
+        if name is not None:
+            active = (*active, name)
+        scope = dict(scope)
+        facs, const = [], 0.0
+        for key, e in self.extra_factors:
+            plates = set(a for a in e.axes if a in self.all_plates)
+            if plates == set(active):
+                lf = self._extra_factor(key, e)
+                facs.extend(lf.tensors)
+        for k, dQ in Q.flat_prog.items():
+            dP = P.flat_prog[k]
+            if isinstance(dP, Timeseries) or isinstance(dQ, Timeseries):
+                raise Exception("SampleNonMP does not support a Timeseries (reference SampleNonMP.py:156)")
+            if isinstance(dQ, Plate):
+                lf = self.plan_nonmp(k, dP, dQ, active, scope)
+                facs.extend(lf.tensors); const += lf.const
+                continue
+            if isinstance(dQ, Data):
+                if k not in self.sig or self.sig[k].role != 'data':
+                    raise Exception(f"no data tensor was provided for {k}")
+                s = self.sig[k]
+                value = Expr.leaf(self.inputs[k], s.axes, s.pos_shape)
+                pts = [(self.density(dP, value, scope, tag=f'logP:{k}'), 1.0)]
+            else:
+                if k not in self.sig or self.sig[k].role != 'sample':
+                    raise Exception(f"no sample was provided for latent variable {k}")
+                s = self.sig[k]
+                value = Expr.leaf(self.inputs[k], s.axes, s.pos_shape)
+                pts = [(self.density(dP, value, scope, tag=f'logP:{k}'), 1.0),
+                       (self.density(dQ, value, scope, tag=f'logQ:{k}'), -1.0)]
+                scope[k] = value
+            for pt, coeff in pts:
+                missing = [a for a in active if a not in pt.axes]
+                if missing:
+                    # the reference asserts dims == active plates + K (SampleNonMP.py:176,186-187)
+                    raise Exception(f"non-MP factor of {k} does not span the plates {missing}")
+                facs.append((plain(pt), coeff))
+        if not facs:
+            raise Exception("plate without factors")
+        axes = self.canon_order(_union_axes([lf.pt.axes for lf, _ in facs]))
+        lf = LogicalFactor(facs, const, axes)
+        if name is None:
+            return lf
+        return self.plate_sum(lf, name)
+
+    def build_sampling_nonmp(self):
+        """SampleNonMP._importance_sample_idxs (SampleNonMP.py:71-90): N draws from the categorical over the one K axis
+        with weights exp(lpq - max): one SampleOp on the [K] vector the forward pass left in the workspace."""
+        if self.N is None:
+            raise Exception("resampling program needs the number of posterior samples N")
+        plan = self.plan
+        plan.N = self.N
+        sizes = dict(self.sizes)
+        sizes['N'] = self.N
+        idx = PT(('N',), (), sizes, 'output', index=0, name='idx')
+        plan.sample_groups = [(NONMP_K, ())]
+        u = PT(('N',), (), sizes, 'aux', index=0, name='u0')
+        plan.sample_steps = [((), (NONMP_K,))]
+        nd = [('ax', 'N', self.N)]
+        return [SampleOp(nd, [self.axdim(NONMP_K)], [(lf, coeff, []) for lf, coeff in self.nonmp_lf.tensors], [],
+                         (u, nd), [idx])]
+
     # -- contraction (reduce_Ks.py:236-298) --------------------------------------------------
     def contract(self, lfs, Ks_to_sum, active, level_steps):
         if not lfs:
@@ -1753,12 +1823,21 @@ class Planner:
         if grad_names or not self.grad_names:
             self.set_grad_names(grad_names)
         self.with_sample = with_sample
-        lf = self.plan_plate(None, self.P, self.Q, (), self.scope)
-        if lf.axes != ():
-            raise Exception(f"log-evidence has leftover axes {lf.axes}")
         lp = PT((), (), self.sizes, 'output', index=0, name='lp')
         self.lp_ws = self.ws((), name='lp')
-        self.emit(ReduceOp(R_SUM, self.lp_ws, [], [], lf.tensors, cadd=lf.const, tag='lp'))
+        if self.nonmp:
+            # SampleNonMP._elbo (reference SampleNonMP.py:56-57): logsumexp over the one K axis (no eps) - log K
+            lf = self.plan_nonmp(None, self.P, self.Q, (), self.scope)
+            if tuple(lf.axes) != (NONMP_K,):
+                raise Exception(f"non-MP log-probability has axes {lf.axes}, expected ({NONMP_K},)")
+            self.nonmp_lf = lf
+            self.emit(ReduceOp(R_LSE, self.lp_ws, [], [self.axdim(NONMP_K)], lf.tensors,
+                               cadd=lf.const - math.log(self.sizes[NONMP_K]), tag='lp'))
+        else:
+            lf = self.plan_plate(None, self.P, self.Q, (), self.scope)
+            if lf.axes != ():
+                raise Exception(f"log-evidence has leftover axes {lf.axes}")
+            self.emit(ReduceOp(R_SUM, self.lp_ws, [], [], lf.tensors, cadd=lf.const, tag='lp'))
         self.emit(ReduceOp(R_SUM, lp, [], [], [(plain(self.lp_ws), 1.0)], tag='lp_out'))
         self.fwd_segments.append(self.fwd)
         plan = self.plan
@@ -1769,7 +1848,7 @@ class Planner:
         plan.n_bwd = len(bwd_segments)
         if with_sample:
             plan.sample_prog = len(plan.programs)
-            plan.programs.append(self.build_sampling())
+            plan.programs.append(self.build_sampling_nonmp() if self.nonmp else self.build_sampling())
         plan.assign_offsets(self.itemsize)
         plan.serialize()
         return plan

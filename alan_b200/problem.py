@@ -46,7 +46,6 @@ class Problem:
         dup = set(self.inputs) & set(self.params)
         if dup:
             raise Exception(f"names {sorted(dup)} are used both as inputs and as parameters")
-        check_PQ(P, Q, set(self.data.keys()))
         self.device = runtime.require_cuda(device)
         self.pg, self.shard_plate = process_group, shard_plate
         # compiled plans + device workspaces, shared by every Sample of this problem with the same tensor signature
@@ -60,10 +59,39 @@ class Problem:
                 for a, n in v.named_sizes.items():
                     if self.platesizes.setdefault(a, n) != n:
                         raise Exception(f"plate {a} has size {self.platesizes[a]} but {k} has {n} elements along it")
+        # parameters declared in place (OptParam / QEMParam as distribution arguments): what the reference's BoundPlate
+        # does at construction (BoundPlate.py:100-190) -- named, expanded over the plates of their variable
+        from .qem import bind, QEMState
+        dtype = torch.float64 if any(v.t.dtype == torch.float64 for d in (self.data, self.inputs, self.params)
+                                     for v in d.values()) else torch.float32
+        taken = set(self.inputs) | set(self.params)
+        self.P, optP, qpP, qmP, qvP = bind(P, self.platesizes, taken)
+        self.Q, optQ, qpQ, qmQ, qvQ = bind(Q, self.platesizes, taken | set(optP) | set(qpP))
+        for k, v in {**optP, **optQ}.items():
+            self.params[k] = NT(v.t.to(dtype).detach().requires_grad_(True), v.axes)
+        self._qem = {'P': QEMState(qvP, qpP, qmP, self.device, dtype), 'Q': QEMState(qvQ, qpQ, qmQ, self.device, dtype)}
+        check_PQ(self.P, self.Q, set(self.data.keys()))
 
     def inputs_params(self) -> dict:
-        """reference Problem.inputs_params (Problem.py:113-118), flat."""
-        return {**self.inputs, **self.params}
+        """reference Problem.inputs_params (Problem.py:113-118), flat: inputs, optimised and QEM parameters."""
+        return {**self.inputs, **self.params, **self._qem['P'].params, **self._qem['Q'].params}
+
+    def qem_params(self) -> dict:
+        """Conventional parameters learned by QEM, on the device (reference BoundPlate.qem_params, BoundPlate.py:235-239)."""
+        return {**self._qem['P'].params, **self._qem['Q'].params}
+
+    def qem_means(self) -> dict:
+        """Moving-average mean parameters (BoundPlate.qem_means, BoundPlate.py:241-245)."""
+        return {**self._qem['P'].means, **self._qem['Q'].means}
+
+    def update_qem_params(self, lr: float, sample, computation_strategy=None):
+        """Sample.update_qem_params (Sample.py:351-355): P's QEM distributions, then Q's (whose moments already see
+        P's new parameters, as upstream).  Per side: one `sample.moments` call on the engine, then the fused
+        moving-average + conversion kernel per variable (alan_b200/qem.py)."""
+        kw = {} if computation_strategy is None else {'computation_strategy': computation_strategy}
+        with torch.no_grad():
+            self._qem['P'].update(lr, sample, **kw)
+            self._qem['Q'].update(lr, sample, **kw)
 
     def sample(self, K: int, reparam: bool = True, sampler=None, noise: Optional[dict] = None,
                seed: Optional[int] = None) -> "Sample":
@@ -72,6 +100,16 @@ class Problem:
         (shapes, K, sampler), one C-ABI call per draw (alan_b200/sampling.py).  `noise` / `seed` make the draw
         reproducible (explicit base noise: see QSampler.noise_shapes()).  With `reparam=True` the samples carry
         requires_grad so that `elbo_vi` returns the pathwise gradient with respect to them."""
+        return Sample(self, self._draw(K, reparam, sampler, noise, seed), reparam)
+
+    def sample_nonmp(self, K: int, reparam: bool = True, noise: Optional[dict] = None, seed: Optional[int] = None):
+        """K independent draws of the whole joint from Q and the global importance-sampling estimators on them
+        (reference Problem.sample_nonmp, Problem.py:99-110 -> SampleNonMP; alan_b200/nonmp.py)."""
+        from .sampling import IndependentSampler
+        from .nonmp import SampleNonMP
+        return SampleNonMP(self, self._draw(K, reparam, IndependentSampler, noise, seed), reparam)
+
+    def _draw(self, K, reparam, sampler, noise, seed) -> dict:
         from .sampling import QSampler, PermutationSampler
         sampler = sampler or PermutationSampler
         ip = self.inputs_params()
@@ -90,7 +128,7 @@ class Problem:
             axes = (kax,) + tuple(a for a in x.axes if a != kax)           # [K, plates..., event]: the reference's order
             y = x.order(axes)
             smp[name] = NT(y.t.contiguous().requires_grad_(bool(reparam)), axes)
-        return Sample(self, smp, reparam)
+        return smp
 
     def sample_from(self, sample: dict, reparam: bool = False) -> "Sample":
         return Sample(self, {k: _as_nt(v) for k, v in sample.items()}, reparam)
@@ -276,6 +314,10 @@ class Sample:
         run.forward_raw(tens)
         grads = run.backward_raw(tens)
         return [NT(grads[j], plates) for j, plates, _ in run.comp.moment_inputs]
+
+    def update_qem_params(self, lr: float, computation_strategy=no_checkpoint):
+        """reference Sample.update_qem_params (Sample.py:351-355)."""
+        self.problem.update_qem_params(lr, self, computation_strategy)
 
     def importance_sample(self, N: int, uniforms=None, seed: Optional[int] = None, computation_strategy=checkpoint) -> dict:
         """N joint posterior samples: K indices drawn top-down over the plate tree, then gathered

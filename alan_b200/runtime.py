@@ -27,7 +27,7 @@ EXPORTS = [
     "alan_b200_program_launches", "alan_b200_run", "alan_b200_profile", "alan_b200_logpq_fwd", "alan_b200_logpq_bwd",
     "alan_b200_resample", "alan_b200_gather", "alan_b200_lse_eps", "alan_b200_chain_scratch_elems",
     "alan_b200_logmmexp_chain", "alan_b200_normal_logpdf_bcast", "alan_b200_pipe_peak",
-    "alan_b200_comm_bytes", "alan_b200_plan_set_comm",
+    "alan_b200_comm_bytes", "alan_b200_plan_set_comm", "alan_b200_qem_update",
 ]
 
 
@@ -100,6 +100,7 @@ def lib():
     L.alan_b200_chain_scratch_elems.restype = i64
     L.alan_b200_logmmexp_chain.argtypes = [vp, vp, vp, i64, i64, i64, i32, vp]
     L.alan_b200_normal_logpdf_bcast.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, i32, vp]
+    L.alan_b200_qem_update.argtypes = [i32, i64, ctypes.c_double, vp, vp, vp, vp, vp, vp, i32, vp]
     L.alan_b200_pipe_peak.argtypes = [i32, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_double), vp]
     _lib = L
     return L
@@ -265,6 +266,27 @@ def pipe_peak(which: int, device=None) -> float:
     with torch.cuda.device(dev):
         check(lib().alan_b200_pipe_peak(which, scratch.data_ptr(), scratch.numel() * 4, ctypes.byref(r), _stream(dev)))
     return r.value
+
+
+QEM_FAMILY = {"Normal": 0, "Bernoulli": 1, "Poisson": 2, "Exponential": 3, "HalfNormal": 4, "Gamma": 5, "Beta": 6}
+
+
+def qem_update(family: str, lr: float, new, means, params):
+    """In place: means <- means * (1 - lr) + lr * new, params <- mean2conv(means) for one latent variable
+    (reference BoundPlate.py:256-296, conversions.py:46-296).  `new`, `means`, `params`: lists of same-shape
+    contiguous device tensors (1 or 2 each, per family)."""
+    require_cuda()
+    if family not in QEM_FAMILY:
+        raise Exception(f"QEM: no mean <-> conventional parameter conversion for {family} on the device")
+    ts = list(new) + list(means) + list(params)
+    for x in ts:
+        if not x.is_cuda or not x.is_contiguous() or x.dtype != ts[0].dtype or x.numel() != ts[0].numel():
+            raise Exception("qem_update: moments, means and parameters must be contiguous device tensors of one shape and dtype")
+    ptr = lambda xs, i: xs[i].data_ptr() if i < len(xs) else None
+    x0 = ts[0]
+    with torch.cuda.device(x0.device):
+        check(lib().alan_b200_qem_update(QEM_FAMILY[family], x0.numel(), float(lr), ptr(new, 0), ptr(new, 1), ptr(means, 0),
+                                         ptr(means, 1), ptr(params, 0), ptr(params, 1), _dt(x0), _stream(x0.device)))
 
 
 def gather(x: torch.Tensor, idx: torch.Tensor, outer: int, K: int, inner: int) -> torch.Tensor:

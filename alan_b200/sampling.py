@@ -43,6 +43,13 @@ class CategoricalSampler:
     mode = 1
 
 
+class IndependentSampler:
+    """K independent draws from the full joint: child particle k is conditioned on parent particle k (reference
+    Sampler.py:162-169; the sampler of `Problem.sample_nonmp`).  No permutation tensor: the parent is read under the
+    child's K axis name."""
+    mode = 2
+
+
 NOISE_KIND = {'Normal': 'normal', 'LogNormal': 'normal', 'HalfNormal': 'normal', 'Exponential': 'uniform',
               'Uniform': 'uniform', 'Laplace': 'uniform', 'Bernoulli': 'uniform'}
 
@@ -155,6 +162,14 @@ class QSampler:
                     continue
                 e0 = scope[names[0]]
                 plates0 = tuple(x for x in e0.axes if x != Kp)
+                if self.sampler.mode == 2:                                 # IndependentSampler: perm = arange
+                    for a in names:
+                        e = scope[a]
+                        if e.op != 'leaf' or e.rename or e.mode:
+                            raise Exception(f"internal: {a} is not a plain tensor")
+                        local[a] = Expr.leaf(e.ref, tuple(Kg if x == Kp else x for x in e.axes), e.pos_shape,
+                                             rename={Kg: Kp})
+                    continue
                 perm = self._perm((name, Kp), plates0, Kp)
                 for a in names:
                     e = scope[a]
@@ -166,6 +181,9 @@ class QSampler:
                     pl.fwd.append(KGatherOp(e.ref, perm, out, outer, self.K, inner))
                     local[a] = Expr.leaf(out, out.axes, out.pos_shape)
             ts_perm = None
+            if any(isinstance(d, Timeseries) for d in child.values()) and self.sampler.mode == 2:
+                raise Exception("IndependentSampler does not draw a Timeseries here (SampleNonMP has no Timeseries support "
+                                "upstream either, SampleNonMP.py:156)")
             if any(isinstance(d, Timeseries) for d in child.values()):
                 ts_perm = self._perm((name, 'timeseries'), tuple(active), Kg)
             # ---- the draws, in program order; later members of a Group see the earlier ones (dist.py:60-70)

@@ -114,6 +114,17 @@ int alan_b200_gather(const void* x, const int64_t* idx, void* out, int elem_byte
                      int64_t N, int64_t outer, int64_t K, int64_t inner, int64_t outer_div,
                      void* stream);
 
+/* QEM parameter update of ONE latent variable, elementwise and in place:
+ *     mean_s  <- mean_s * (1 - lr) + lr * new_s            (s = 0, 1: the family's sufficient statistics)
+ *     params  <- mean2conv(mean_0, mean_1)                  (conventional parameters of the family)
+ * family: 0 Normal (mean, mean2 -> loc, scale), 1 Bernoulli (mean -> probs), 2 Poisson (mean -> rate),
+ *         3 Exponential (mean -> rate), 4 HalfNormal (mean2 -> scale), 5 Gamma (mean_log, mean -> concentration, rate),
+ *         6 Beta (mean_log, mean_log1m -> concentration1, concentration0).  Unused second buffers may be NULL.
+ * replaces: BoundPlate._update_qem_moving_avg + _update_qem_convparams (src/alan/BoundPlate.py:256-296) and
+ * conversions.*Conversion.mean2conv (src/alan/conversions.py:46-296).  dtype: 0 = f32, 1 = f64. */
+int alan_b200_qem_update(int family, int64_t n, double lr, const void* new0, const void* new1, void* mean0, void* mean1,
+                         void* param0, void* param1, int dtype, void* stream);
+
 /* Measurement aid (bench.py roofline denominators, measured in the same process as the bench): sustained rate of one
  * SM pipe over the whole GPU, in lane-operations per second.  which = 0: MUFU.EX2 (the unit that bounds the
  * log-semiring contraction once its d-contraction runs on the tensor cores), 1: FFMA.

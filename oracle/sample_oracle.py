@@ -81,7 +81,11 @@ def resample_scope(scope: dict, group, K_axis, noise, mode):
             continue
         x0 = scope[names[0]]
         plates0 = tuple(a for a in x0.axes if a != Kp)
-        perm = perm_from_uniform(noise[(group, Kp)], mode)                  # [plates0..., K]
+        if mode == 2:                                                       # IndependentSampler: arange (Sampler.py:162-169)
+            Kn = x0.sizes()[Kp]
+            perm = t.arange(Kn).expand([x0.sizes()[a] for a in plates0] + [Kn])
+        else:
+            perm = perm_from_uniform(noise[(group, Kp)], mode)              # [plates0..., K]
         for n in names:
             x = scope[n].order(plates0 + (Kp,))
             idx = perm.reshape(list(perm.shape) + [1] * x.pos_ndim).expand(list(perm.shape) + list(x.t.shape[len(x.axes):]))

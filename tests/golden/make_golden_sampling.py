@@ -37,6 +37,8 @@ CASES = {
     'cfg1_lgl': ('cfg1_lgl', 'Q', 5), 'cfg1_lglp': ('cfg1_lglp', 'Q', 4), 'cfg2_movielens': ('cfg2_movielens', 'Q', 6),
     'cfg3_radon': ('cfg3_radon', 'Q', 4), 'model1': ('model1', 'Q', 5), 'ref_corr_q': ('ref_corr_q', 'Q', 6),
     'cfg4_timeseries_P': ('cfg4_timeseries', 'P', 5),
+    # IndependentSampler (Sampler.py:162-169, the sampler of Problem.sample_nonmp): child particle k sees parent particle k
+    'cfg1_lglp_indep': ('cfg1_lglp', 'Q', 4, 'indep'), 'cfg3_radon_indep': ('cfg3_radon', 'Q', 4, 'indep'),
 }
 
 
@@ -67,7 +69,8 @@ class Noise:
 
 
 def run_case(name, dtype, seed=0):
-    case, side, K = CASES[name]
+    case, side, K = CASES[name][:3]
+    indep = len(CASES[name]) > 3 and CASES[name][3] == 'indep'
     model, inputs_fn, kw, _, _, _, _ = models.CASES[case]
     t.set_default_dtype(dtype)
     t.manual_seed(seed)
@@ -162,7 +165,7 @@ def run_case(name, dtype, seed=0):
     S.PermutationSampler.perm = staticmethod(perm)
     D.Dist.sample = sample
     try:
-        tree, g2K = bp._sample(K, False, alan.PermutationSampler, all_platedims)
+        tree, g2K = bp._sample(K, False, S.IndependentSampler if indep else alan.PermutationSampler, all_platedims)
     finally:
         S.Sampler.resample_scope = classmethod(orig_rs)
         S.PermutationSampler.perm = orig_perm
@@ -177,6 +180,7 @@ def run_case(name, dtype, seed=0):
         out_samples[k] = (generic_order(v, [*pl, *kd]).detach().clone(), tuple(str(d) for d in [*pl, *kd]))
     return {
         'case': case, 'side': side, 'K': K, 'dtype': str(dtype), 'platesizes': inp['platesizes'],
+        'sampler_mode': 2 if indep else 0,
         'params': {k: named_plain(v) for k, v in (inp['params'].items() if side == 'Q' else [])},
         'inputs': {k: named_plain(v) for k, v in inp['inputs'].items()},
         'noise': dict(noise.store), 'noise_kinds': dict(noise.kinds),
@@ -185,7 +189,7 @@ def run_case(name, dtype, seed=0):
 
 
 def main():
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):
         for dtype in (t.float32, t.float64):
             out = run_case(name, dtype)
             tag = 'f32' if dtype == t.float32 else 'f64'

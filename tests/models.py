@@ -339,3 +339,88 @@ def build(case, ns, dtype=t.float32):
         return CASES[case][0](ns)
     finally:
         t.set_default_dtype(old)
+
+
+# --------------------------------------------------------------------------- QEM
+def qem_model1_model(ns):
+    """/root/reference/tests/model1.py:5-30 with its own parameter declarations: QEMParam on a Group member,
+    OptParam and a named extra parameter in a plate."""
+    P = ns.Plate(
+        ab=ns.Group(
+            a=ns.Normal(0, 1),
+            b=ns.Normal("a", 1),
+        ),
+        c=ns.Normal(0, lambda a: a.exp()),
+        p1=ns.Plate(
+            d=ns.Normal("a", 1),
+            p2=ns.Plate(
+                e=ns.Normal("d", 1.),
+            ),
+        ),
+    )
+    Q = ns.Plate(
+        ab=ns.Group(
+            a=ns.Normal(ns.QEMParam(0.), ns.QEMParam(1.)),
+            b=ns.Normal("a", 1),
+        ),
+        c=ns.Normal(0, lambda a: a.exp()),
+        p1=ns.Plate(
+            d=ns.Normal(ns.OptParam(0.), "d_scale"),
+            p2=ns.Plate(
+                e=ns.Data(),
+            ),
+        ),
+    )
+    return P, Q
+
+
+def qem_model1_inputs(p1=4, p2=4, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    return dict(platesizes={'p1': p1, 'p2': p2}, data={'e': r(p1, p2).refine_names('p1', 'p2')}, inputs={},
+                params={'d_scale': t.ones(p1, dtype=dtype).refine_names('p1')})
+
+
+def qem_families_model(ns):
+    """Every family with a mean <-> conventional conversion on the device (conversions.py:46-296): global and plated
+    QEM latents, a QEM distribution on the P side too (BoundPlate._update_qem_params runs for P and for Q)."""
+    P = ns.Plate(
+        g=ns.Gamma(2., 2.),
+        bt=ns.Beta(2., 3.),
+        ex=ns.Exponential(1.5),
+        hn=ns.HalfNormal(1.2),
+        m=ns.Normal(ns.QEMParam(0.3), ns.QEMParam(1.5)),
+        p1=ns.Plate(
+            w=ns.Gamma(3., 3.),
+            bn=ns.Bernoulli(probs=0.3),
+            v=ns.Normal('m', 1.),
+            y=ns.Normal(lambda g, ex, w, bn, bt, v: g - ex + w * bn + bt + v, lambda hn: hn + 0.5),
+        ),
+    )
+    Q = ns.Plate(
+        g=ns.Gamma(ns.QEMParam(2.5), ns.QEMParam(2.)),
+        bt=ns.Beta(ns.QEMParam(2.), ns.QEMParam(2.)),
+        ex=ns.Exponential(ns.QEMParam(1.)),
+        hn=ns.HalfNormal(ns.QEMParam(1.)),
+        m=ns.Normal(0., 2.),
+        p1=ns.Plate(
+            w=ns.Gamma(ns.QEMParam(3.), ns.QEMParam(2.5)),
+            bn=ns.Bernoulli(probs=ns.QEMParam(0.4)),
+            v=ns.Normal(ns.QEMParam(0.), ns.QEMParam(1.)),
+            y=ns.Data(),
+        ),
+    )
+    return P, Q
+
+
+def qem_families_inputs(p1=6, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    return dict(platesizes={'p1': p1}, data={'y': (0.5 + t.randn(p1, generator=g, dtype=t.float64)).to(dtype).refine_names('p1')},
+                inputs={}, params={})
+
+
+QEM_CASES = {
+    # name: (model builder, inputs builder, kwargs, K, learning rates of the successive updates)
+    'qem_model1': (qem_model1_model, qem_model1_inputs, dict(p1=4, p2=4), 10, (0.1, 0.3)),
+    'qem_families': (qem_families_model, qem_families_inputs, dict(p1=6), 12, (0.2, 0.5, 0.1)),
+}

@@ -16,7 +16,8 @@ from alan_b200.named import NT
 from golden_io import GOLDEN_DIR, TAGS
 
 pytestmark = pytest.mark.gpu
-CASES = ['cfg1_lgl', 'cfg1_lglp', 'cfg2_movielens', 'cfg3_radon', 'model1', 'ref_corr_q', 'cfg4_timeseries_P']
+CASES = ['cfg1_lgl', 'cfg1_lglp', 'cfg2_movielens', 'cfg3_radon', 'model1', 'ref_corr_q', 'cfg4_timeseries_P',
+         'cfg1_lglp_indep', 'cfg3_radon_indep']          # *_indep: IndependentSampler (Problem.sample_nonmp)
 
 
 def load(case, tag):
@@ -40,10 +41,11 @@ def close(a, b, tag):
 @pytest.mark.parametrize("tag", list(TAGS))
 @pytest.mark.parametrize("case", CASES)
 def test_sampling_matches_reference_walk(case, tag):
-    from alan_b200.sampling import QSampler, PermutationSampler
+    from alan_b200.sampling import QSampler, PermutationSampler, IndependentSampler
     g = load(case, tag)
     ip = params_of(g)
-    qs = QSampler(plate_of(g), ip, g['platesizes'], g['K'], PermutationSampler, TAGS[tag], 'cuda:0')
+    sampler = IndependentSampler if g.get('sampler_mode', 0) == 2 else PermutationSampler
+    qs = QSampler(plate_of(g), ip, g['platesizes'], g['K'], sampler, TAGS[tag], 'cuda:0')
     out = qs.run(ip, noise={k: g['noise'][k] for k in qs.noise_shapes()})
     assert set(out) == set(g['samples'])
     for var, (ref, axes) in g['samples'].items():

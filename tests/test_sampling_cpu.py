@@ -13,7 +13,8 @@ from alan_b200 import model as M
 from alan_b200.named import NT
 from golden_io import GOLDEN_DIR, TAGS
 
-CASES = ['cfg1_lgl', 'cfg1_lglp', 'cfg2_movielens', 'cfg3_radon', 'model1', 'ref_corr_q', 'cfg4_timeseries_P']
+CASES = ['cfg1_lgl', 'cfg1_lglp', 'cfg2_movielens', 'cfg3_radon', 'model1', 'ref_corr_q', 'cfg4_timeseries_P',
+         'cfg1_lglp_indep', 'cfg3_radon_indep']          # *_indep: IndependentSampler (Problem.sample_nonmp)
 
 
 def load(case, tag):
@@ -34,7 +35,7 @@ def params_of(g):
 def test_sampling_oracle_matches_reference_walk(case, tag):
     from oracle.sample_oracle import sample_q
     g = load(case, tag)
-    out = sample_q(plate_of(g), params_of(g), g['noise'], g['K'], 0, TAGS[tag])
+    out = sample_q(plate_of(g), params_of(g), g['noise'], g['K'], g.get('sampler_mode', 0), TAGS[tag])
     assert set(out) == set(g['samples'])
     for k, (ref, axes) in g['samples'].items():
         assert t.equal(out[k].order(axes).t, ref), k
@@ -43,11 +44,12 @@ def test_sampling_oracle_matches_reference_walk(case, tag):
 @pytest.mark.parametrize("tag", list(TAGS))
 @pytest.mark.parametrize("case", CASES)
 def test_sampling_program_emulated_matches_reference_walk(case, tag):
-    from alan_b200.sampling import QSampler, PermutationSampler
+    from alan_b200.sampling import QSampler, PermutationSampler, IndependentSampler
     from plan_emulator import Emu
     g = load(case, tag)
     ip = params_of(g)
-    qs = QSampler(plate_of(g), ip, g['platesizes'], g['K'], PermutationSampler, TAGS[tag])
+    sampler = IndependentSampler if g.get('sampler_mode', 0) == 2 else PermutationSampler
+    qs = QSampler(plate_of(g), ip, g['platesizes'], g['K'], sampler, TAGS[tag])
     shapes = qs.noise_shapes()
     assert set(shapes) <= set(g['noise'])
     for key, (kind, shape, dt) in shapes.items():
