@@ -59,7 +59,9 @@ def test_qem_update_kernel_vs_oracle(family, tag):
             'Gamma': dict(concentration=0.3 + 6 * r(), rate=0.2 + 4 * r()),
             'Beta': dict(concentration1=0.3 + 6 * r(), concentration0=0.3 + 6 * r())}[family]
     new = [m.to(dt) for m in QO.conv2mean(family, conv)]
-    old = [(m + 0.1 * r() * m.abs()).to(dt) for m in QO.conv2mean(family, conv)]
+    # the running means come from perturbed parameters: the mean-parameter space is convex, so the average is valid
+    old = [m.to(dt) for m in QO.conv2mean(family, {k: v * (0.8 + 0.4 * r()) if family != 'Bernoulli' else v * r()
+                                                    for k, v in conv.items()})]
     lr = 0.3
     want_means = [o.clone().mul_(1 - lr).add_(m, alpha=lr) for o, m in zip(old, new)]
     want = QO.mean2conv(family, want_means)
@@ -72,7 +74,7 @@ def test_qem_update_kernel_vs_oracle(family, tag):
     from alan_b200.qem import CONV_ARGS
     for arg, got in zip(CONV_ARGS[family], params):
         ok = t.isfinite(want[arg])
-        assert ok.double().mean() > 0.99
+        assert ok.double().mean() > 0.999
         assert elem_err(got.cpu()[ok], want[arg][ok]) < tol, arg
 
 
