@@ -11,6 +11,7 @@
 #include "normal_poly.cuh"
 #include "chain.cuh"
 #include "qem.cuh"
+#include "mvn.cuh"
 #include <type_traits>
 #include <cstdlib>
 
@@ -27,7 +28,7 @@
 enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
 enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
        OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13, OP_XREDUCE = 14, OP_NORMAL_Q_BWD = 15, OP_PERM = 16, OP_KGATHER = 17,
-       OP_TS_SAMPLE = 18, OP_DEPS = 19, OP_NORMAL_POLY_SUM = 20, OP_PASTE = 21 };
+       OP_TS_SAMPLE = 18, OP_DEPS = 19, OP_NORMAL_POLY_SUM = 20, OP_PASTE = 21, OP_MVN_PREP = 22 };
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -654,6 +655,21 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c0, bool 
                 p.total = 1;
                 for (int k = 0; k < p.nd; ++k) { p.size[k] = r.i32(); p.ss[k] = r.i64v(); p.ds[k] = r.i64v(); p.total *= p.size[k]; }
                 paste_kernel<T><<<grid_for(p.total, 256, c), 256, 0, c.stream>>>(src, dst, p);
+                break;
+            }
+            case OP_MVN_PREP: {
+                const T* S = (const T*)tref(r, c);
+                T* L = (T*)tref(r, c);
+                T* W = (T*)tref(r, c);
+                T* cst = (T*)tref(r, c);
+                const i64 n_mat = r.i64v();
+                const int d = r.i32(), mode = r.i32();
+                if (d < 1 || d > AB_MVN_MAXD) return fail("MultivariateNormal: event size must be between 1 and 64");
+                const size_t smem = 2 * (size_t)d * d * sizeof(T);
+                static const cudaError_t attr = cudaFuncSetAttribute(mvn_prep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                     (int)(2 * AB_MVN_MAXD * AB_MVN_MAXD * sizeof(T)));
+                (void)attr;
+                mvn_prep_kernel<T><<<grid_for(n_mat, 1, c), 32, smem, c.stream>>>(S, L, W, cst, n_mat, d, mode);
                 break;
             }
             case OP_PERM: {

@@ -38,9 +38,11 @@ FAMILIES = {
     "StudentT": ("df", "loc", "scale"),
     "NegativeBinomial": ("total_count", "probs", "logits"),
     "Binomial": ("total_count", "probs", "logits"),
+    "MultivariateNormal": ("loc", "covariance_matrix", "precision_matrix", "scale_tril"),
 }
 # arguments that torch.distributions leaves as None unless given
 _OPTIONAL = {"probs", "logits"}
+_MATRIX_ARGS = ("covariance_matrix", "precision_matrix", "scale_tril")
 # arguments whose constraint is discrete (dist.py:311-318 keeps these as ints)
 DISCRETE_ARGS = {("NegativeBinomial", "total_count"), ("Binomial", "total_count")}
 
@@ -92,7 +94,9 @@ class Dist:
                 raise Exception(f"{family}: argument {k} given twice")
             bound[k] = v
         bound = {k: v for k, v in bound.items() if v is not None}
-        required = [n for n in names if n not in _OPTIONAL]
+        required = [n for n in names if n not in _OPTIONAL and n not in _MATRIX_ARGS]
+        if family == "MultivariateNormal" and sum(n in bound for n in _MATRIX_ARGS) != 1:
+            raise Exception("Exactly one of covariance_matrix or precision_matrix or scale_tril may be specified.")
         for n in required:
             if n not in bound:
                 raise Exception(f"Wrong number of arguments provided to {family}")
@@ -150,6 +154,7 @@ Uniform = _make("Uniform")
 StudentT = _make("StudentT")
 NegativeBinomial = _make("NegativeBinomial")
 Binomial = _make("Binomial")
+MultivariateNormal = _make("MultivariateNormal")
 
 
 class Data:

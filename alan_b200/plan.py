@@ -34,7 +34,8 @@ MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
 SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
 OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY, OP_DOT, \
-    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD, OP_PERM, OP_KGATHER, OP_TS_SAMPLE, OP_DEPS, OP_NORMAL_POLY_SUM, OP_PASTE = range(1, 22)
+    OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD, OP_PERM, OP_KGATHER, OP_TS_SAMPLE, OP_DEPS, OP_NORMAL_POLY_SUM, OP_PASTE, \
+    OP_MVN_PREP = range(1, 23)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
 NONMP_K = 'K_'          # the one K axis every latent shares in a SampleNonMP plan (no group can be named '')
@@ -702,6 +703,22 @@ class PasteOp(Op):
             w.i32(size); w.i64(ss); w.i64(ds)
 
 
+class MvnPrepOp(Op):
+    """csrc/mvn.cuh: the matrix argument of a MultivariateNormal -> scale_tril L, its inverse W and the constant
+    c = -sum log L_ii - d/2 log 2 pi, one warp per matrix.  mode: 0 covariance_matrix, 1 precision_matrix, 2 scale_tril."""
+    code = OP_MVN_PREP
+    MODES = {'covariance_matrix': 0, 'precision_matrix': 1, 'scale_tril': 2}
+
+    def __init__(self, S, L, W, c, n_mat, d, mode):
+        self.S, self.L, self.W, self.c, self.n_mat, self.d, self.mode = S, L, W, c, n_mat, d, mode
+        self.out = W
+
+    def payload(self, w):
+        for pt in (self.S, self.L, self.W, self.c):
+            w.tref(pt)
+        w.i64(self.n_mat); w.i32(self.d); w.i32(self.mode)
+
+
 class DotOp(Op):
     """out[keep] = sum_e a * b   (csrc/fused.cuh dot_kernel)"""
     code = OP_DOT
@@ -1248,6 +1265,8 @@ class Planner:
     def density(self, dist: Dist, value: Expr, scope, tag) -> PT:
         """One factor tensor: sum over every positional dim of log p(value; args)
         (TorchDimDist.py:157-162)."""
+        if dist.family == 'MultivariateNormal':
+            return self._mvn_density(dist, value, scope, tag)
         args = {k: self.resolve_arg(dist.family, k, v, scope) for k, v in dist.args.items()}
         if dist.family in ('Bernoulli',):
             opname = 'Bernoulli_logits' if 'logits' in args else 'Bernoulli_probs'
@@ -1273,6 +1292,54 @@ class Planner:
         else:
             self.emit(op)
         return out
+
+    # -- MultivariateNormal (dist.py:323-359 -> torch.distributions.MultivariateNormal) -----------------------------
+    def mvn_parts(self, dist: Dist, scope):
+        """-> (loc Expr, L leaf, W leaf, c leaf, d): the matrix argument is factorised once per matrix by MvnPrepOp; the
+        density and the draw are then ordinary expressions over the cells."""
+        args = {k: self.resolve_arg(dist.family, k, v, scope) for k, v in dist.args.items()}
+        which = [k for k in MvnPrepOp.MODES if k in args]
+        if len(which) != 1:
+            raise Exception("Exactly one of covariance_matrix or precision_matrix or scale_tril may be specified.")
+        S = self.materialize(self._prepare(args[which[0]]), tag=f'mvn:{which[0]}')
+        if S.op != 'leaf' or len(S.pos_shape) != 2 or S.pos_shape[0] != S.pos_shape[1]:
+            raise Exception(f"MultivariateNormal: {which[0]} must be a square matrix over the event dim "
+                            f"(unnamed batch dims are not supported), got positional shape {S.pos_shape}")
+        d = S.pos_shape[0]
+        if d > 64:
+            raise Exception("MultivariateNormal: event sizes above 64 are not supported by the device factorisation")
+        if S.ref.id in self.needs:
+            raise Exception(f"the gradient with respect to the {which[0]} of a MultivariateNormal is not provided "
+                            f"(gradients flow to its value and loc)")
+        if S.rename or S.mode:
+            raise Exception("internal: the matrix argument of a MultivariateNormal must be a plain tensor")
+        cache = getattr(self, '_mvn_cache', None)
+        if cache is None:
+            cache = self._mvn_cache = {}
+        key = (S.ref.id, which[0])
+        if key not in cache:
+            axes = tuple(S.ref.axes)
+            L = self.ws(axes, (d, d), name='mvn:L')
+            W = self.ws(axes, (d, d), name='mvn:W')
+            c = self.ws(axes, (), name='mvn:c')
+            op = MvnPrepOp(S.ref, L, W, c, _prod(self.sizes[a] for a in axes), d, MvnPrepOp.MODES[which[0]])
+            op.autodiff_as = 'skip'
+            self.emit(op)
+            cache[key] = (L, W, c)
+        L, W, c = cache[key]
+        lf = lambda pt: Expr.leaf(pt, pt.axes, pt.pos_shape)
+        return self._prepare(args['loc']), lf(L), lf(W), lf(c), d
+
+    def _mvn_density(self, dist, value, scope, tag) -> PT:
+        loc, L, W, c, d = self.mvn_parts(dist, scope)
+        value = self._prepare(value)
+        if value.pos_shape[-1:] != (d,) or len(value.pos_shape) != 1 or loc.pos_shape not in ((d,), ()):
+            raise Exception(f"MultivariateNormal: value / loc must be vectors of the event size {d} "
+                            f"(got {value.pos_shape} and {loc.pos_shape})")
+        mk = Expr.make
+        z = mk('sumlast', mk('mul', W, mk('sub', value, loc)))            # W (x - loc): [cells..., d]
+        body = mk('sub', c, mk('mul', Expr.const(0.5), mk('sumlast', mk('square', z))))
+        return self.emit_expr(self._prepare(body), nred='all', tag=tag)
 
     FAN_EVENT_EXTENTS = (1, 2, 3, 4, 6, 8, 12, 16, 18, 24, 32)
 

@@ -19,7 +19,7 @@ how sampling parity is defined (tests/test_sampling_*.py: identical samples for 
 own RNG stream depends on torchdim's internal dim order).
 
 Families with a closed-form transform are drawn natively: Normal, LogNormal, HalfNormal, Exponential, Uniform,
-Laplace, Bernoulli.  The rejection-sampled ones (Gamma, Beta, StudentT, Poisson, Binomial, NegativeBinomial) raise.
+Laplace, Bernoulli, MultivariateNormal (loc + scale_tril eps, the factor from csrc/mvn.cuh).  The rejection-sampled ones (Gamma, Beta, StudentT, Poisson, Binomial, NegativeBinomial) raise.
 """
 from __future__ import annotations
 
@@ -51,7 +51,7 @@ class IndependentSampler:
 
 
 NOISE_KIND = {'Normal': 'normal', 'LogNormal': 'normal', 'HalfNormal': 'normal', 'Exponential': 'uniform',
-              'Uniform': 'uniform', 'Laplace': 'uniform', 'Bernoulli': 'uniform'}
+              'Uniform': 'uniform', 'Laplace': 'uniform', 'Bernoulli': 'uniform', 'MultivariateNormal': 'normal'}
 
 
 def _draw_expr(family, args, noise: Expr) -> Expr:
@@ -191,6 +191,15 @@ class QSampler:
                 axes = tuple(active) + (Kg,)
                 if isinstance(d, Timeseries):
                     out = self._timeseries(var, d, active, Kg, local, ts_perm)
+                elif d.family == 'MultivariateNormal':
+                    # loc + L eps with L = scale_tril from the device factorisation (torch's rsample)
+                    loc, L, _, _, dd = pl.mvn_parts(d, local)
+                    npt = self._noise_input(var, 'normal', axes, (dd,))
+                    eps = Expr.leaf(npt, axes, (dd,))
+                    body = pl._prepare(Expr.make('add', loc, Expr.make('sumlast', Expr.make('mul', L, eps))))
+                    out = PT(axes, (dd,), pl.sizes, 'output', index=len(self.outputs), name=var)
+                    pl.emit_expr(body, nred=0, tag=f'draw:{var}', out=out)
+                    self.outputs.append((var, axes, (dd,)))
                 else:
                     args = {k: pl.resolve_arg(d.family, k, v, local) for k, v in d.args.items()}
                     shape = ()

@@ -268,6 +268,16 @@ def dist_log_prob(dist: Dist, value: ONT, scope: dict, dtype) -> ONT:
     (TorchDimDist.py:157-162)."""
     args = {k: resolve_arg(v, scope, dtype) for k, v in dist.args.items()}
     names = list(args.keys())
+    if dist.family == 'MultivariateNormal':
+        # event-aware alignment (TorchDimDist.py:44-62): loc / value are vectors, the matrix argument has event_dim 2
+        mname = [k for k in names if k != 'loc'][0]
+        (rv, rloc, rmat_as_vec), axes = _align([value, args['loc'], ONT(args[mname].t[..., 0], args[mname].axes)])
+        mat = args[mname]
+        perm = [mat.axes.index(a) for a in axes if a in mat.axes] + [len(mat.axes), len(mat.axes) + 1]
+        shape = [mat.sizes()[a] if a in mat.axes else 1 for a in axes] + list(mat.t.shape[-2:])
+        rmat = mat.t.permute(perm).reshape(shape)
+        d = td.MultivariateNormal(rloc, validate_args=False, **{mname: rmat})
+        return ONT(d.log_prob(rv), axes)
     raw, axes = _align([value] + [args[k] for k in names])
     rv, rargs = raw[0], dict(zip(names, raw[1:]))
     d = getattr(td, dist.family)(**rargs, validate_args=False)

@@ -57,8 +57,24 @@ def transform(family, args: dict, noise):
     raise Exception(f"oracle: no transform for {family}")
 
 
+def scale_tril_of(name, M: t.Tensor) -> t.Tensor:
+    """torch.distributions.MultivariateNormal.__init__: the scale_tril it keeps for rsample."""
+    if name == 'scale_tril':
+        return M
+    if name == 'covariance_matrix':
+        return t.linalg.cholesky(M)
+    Lf = t.linalg.cholesky(t.flip(M, (-2, -1)))                       # _precision_to_scale_tril
+    L_inv = t.transpose(t.flip(Lf, (-2, -1)), -2, -1)
+    return t.linalg.solve_triangular(L_inv, t.eye(M.shape[-1], dtype=M.dtype), upper=False)
+
+
 def draw(dist, scope, eps: ONT, dtype) -> ONT:
     args = {k: resolve_arg(v, scope, dtype) for k, v in dist.args.items()}
+    if dist.family == 'MultivariateNormal':                            # loc + scale_tril @ eps (torch's rsample)
+        mname = [k for k in args if k != 'loc'][0]
+        L = ONT(scale_tril_of(mname, args[mname].t), args[mname].axes)
+        res = args['loc'] + (L @ eps)
+        return ONT(res.order(eps.axes).t.expand(eps.t.shape).contiguous(), eps.axes)
     names = list(args)
     raw, axes = _align([eps] + [args[k] for k in names])
     out = transform(dist.family, dict(zip(names, raw[1:])), raw[0])

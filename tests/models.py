@@ -424,3 +424,74 @@ QEM_CASES = {
     'qem_model1': (qem_model1_model, qem_model1_inputs, dict(p1=4, p2=4), 10, (0.1, 0.3)),
     'qem_families': (qem_families_model, qem_families_inputs, dict(p1=6), 12, (0.2, 0.5, 0.1)),
 }
+
+
+# --------------------------------------------------------------------------- MultivariateNormal (row f-2)
+def _mvn_consts(F, dtype):
+    g = t.Generator().manual_seed(1234 + F)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64)
+    A, B, C = r(F, F), r(F, F), r(F, F)
+    return dict(prior_mean=r(F).to(dtype), prior_cov=(A @ A.mT + 0.5 * t.eye(F, dtype=t.float64)).to(dtype),
+                ap_mean=r(F).to(dtype), ap_cov=(B @ B.mT + 2 * t.eye(F, dtype=t.float64)).to(dtype),
+                like_cov=(C @ C.mT + 0.5 * t.eye(F, dtype=t.float64)).to(dtype))
+
+
+def mvn_model(ns, F=3):
+    """/root/reference/tests/linear_multivariate_gaussian_param.py:25-45: a MultivariateNormal latent with a plated
+    MultivariateNormal likelihood; constants positional (loc, covariance_matrix)."""
+    c = _mvn_consts(F, t.get_default_dtype())
+    P = ns.Plate(
+        a=ns.MultivariateNormal(c['prior_mean'], c['prior_cov']),
+        T=ns.Plate(
+            d=ns.MultivariateNormal('a', c['like_cov']),
+        ),
+    )
+    Q = ns.Plate(
+        a=ns.MultivariateNormal('qa_loc', c['ap_cov']),
+        T=ns.Plate(
+            d=ns.Data(),
+        ),
+    )
+    return P, Q
+
+
+def mvn_inputs(T=10, F=3, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    return dict(platesizes={'T': T}, data={'d': (1.5 + r(T, F)).refine_names('T', None)}, inputs={},
+                params={'qa_loc': _mvn_consts(F, dtype)['ap_mean'].clone()})
+
+
+def mvn2_model(ns, F=4):
+    """precision_matrix and scale_tril arguments, a latent-dependent loc through a lambda, a plated MvN latent whose
+    Q depends on its parent (mixture Q), Normal data on one coordinate pair."""
+    c = _mvn_consts(F, t.get_default_dtype())
+    prec = t.linalg.inv(c['prior_cov'].double()).to(c['prior_cov'].dtype)
+    prec = 0.5 * (prec + prec.mT)
+    tril = t.linalg.cholesky(c['like_cov'].double()).to(c['like_cov'].dtype)
+    P = ns.Plate(
+        a=ns.MultivariateNormal(c['prior_mean'], precision_matrix=prec),
+        T=ns.Plate(
+            z=ns.MultivariateNormal(lambda a: 0.5 * a, scale_tril=tril),
+            d=ns.MultivariateNormal('z', c['ap_cov']),
+        ),
+    )
+    Q = ns.Plate(
+        a=ns.MultivariateNormal('qa_loc', scale_tril=tril),
+        T=ns.Plate(
+            z=ns.MultivariateNormal(lambda a, qz_b: 0.3 * a + qz_b, precision_matrix=prec),
+            d=ns.Data(),
+        ),
+    )
+    return P, Q
+
+
+def mvn2_inputs(T=6, F=4, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    return dict(platesizes={'T': T}, data={'d': (0.5 + r(T, F)).refine_names('T', None)}, inputs={},
+                params={'qa_loc': _mvn_consts(F, dtype)['ap_mean'].clone(), 'qz_b': (0.1 * r(T, F)).refine_names('T', None)})
+
+
+CASES['mvn'] = (mvn_model, mvn_inputs, dict(T=10), 5, [('a', 'mean'), ('a', 'mean2')], [], 6)
+CASES['mvn2'] = (mvn2_model, mvn2_inputs, dict(T=6), 4, [('a', 'mean'), ('z', 'mean2')], [], 5)

@@ -159,6 +159,25 @@ class Emu:
             p = t.argsort(u, dim=-1, stable=True)
         self.side[('perm', op.out.id)] = p                      # int64: kept beside the (float) workspace
 
+    def op_MvnPrepOp(self, op):
+        """csrc/mvn.cuh with torch.linalg: scale_tril, its inverse and the log-normaliser per matrix."""
+        sb, sbase = self.buf(op.S)
+        d, n = op.d, op.n_mat
+        S = sb[sbase:sbase + n * d * d].reshape(n, d, d)
+        if op.mode == 0:
+            L = t.linalg.cholesky(S)
+        elif op.mode == 2:
+            L = S.tril()
+        else:                                                       # torch's _precision_to_scale_tril
+            Lf = t.linalg.cholesky(t.flip(S, (-2, -1)))
+            L_inv = t.transpose(t.flip(Lf, (-2, -1)), -2, -1)
+            L = t.linalg.solve_triangular(L_inv, t.eye(d, dtype=S.dtype), upper=False)
+        W = t.linalg.solve_triangular(L, t.eye(d, dtype=S.dtype).expand(n, d, d), upper=False)
+        c = -L.diagonal(dim1=-2, dim2=-1).log().sum(-1) - 0.5 * d * math.log(2 * math.pi)
+        for pt, x in ((op.L, L), (op.W, W), (op.c, c)):
+            b, base = self.buf(pt)
+            b[base:base + x.numel()] = x.reshape(-1)
+
     def op_PasteOp(self, op):
         sb, sbase = self.buf(op.src)
         db, dbase = self.buf(op.dst)

@@ -139,3 +139,18 @@ def test_problem_sample_feeds_the_logpq_path():
         assert float((w.t.sum(kd) - 1).abs().max()) < 1e-4, key
     post = s.importance_sample(7, seed=0)
     assert post['z'].t.shape[0] == 7
+
+
+@pytest.mark.parametrize("tag", list(TAGS))
+@pytest.mark.parametrize("case", ['mvn', 'mvn2'])
+def test_mvn_sampling_vs_oracle(case, tag):
+    """MultivariateNormal draws (row f-2): loc + scale_tril eps with the factor computed on the device (csrc/mvn.cuh)
+    from covariance / precision / scale_tril arguments, against the oracle on the same base noise."""
+    from test_sampling_cpu import mvn_sampling_case
+    qs, ip, noise, want = mvn_sampling_case(case, tag)
+    qs.device = 'cuda:0'
+    out = qs.run(ip, noise=noise)
+    tol = 3e-6 if tag == 'f32' else 1e-12
+    for var in want:
+        mine, ref = out[var].order(want[var].axes).t.cpu(), want[var].t
+        assert (mine - ref).abs().max() <= tol * max(1.0, float(ref.abs().max())), var

@@ -80,3 +80,47 @@ def test_unsupported_family_raises():
     Q = M.Plate(p=M.Beta(1., 1.))
     with pytest.raises(Exception, match="not supported"):
         QSampler(Q, {}, {}, 4)
+
+
+def mvn_sampling_case(case, tag, K=6, sampler=None):
+    """QSampler of an MvN model + base noise + what the oracle draws from it (loc + scale_tril eps, torch's rsample)."""
+    from alan_b200.sampling import QSampler, PermutationSampler
+    from oracle.sample_oracle import sample_q
+    dt = TAGS[tag]
+    _, inputs_fn, kw = models.CASES[case][:3]
+    inp = inputs_fn(**kw, dtype=dt)
+    _, Q = models.build(case, M, dt)
+    nt = lambda d: {k: NT(v.rename(None), tuple(n for n in v.names if n is not None)) for k, v in d.items()}
+    ip = nt(inp['params'])
+    qs = QSampler(Q, ip, inp['platesizes'], K, sampler or PermutationSampler, dt)
+    g = t.Generator().manual_seed(21)
+    noise = {}
+    for key, (kind, shape, ndt) in qs.noise_shapes().items():
+        noise[key] = (t.randn if kind == 'normal' else t.rand)(shape, dtype=t.float64, generator=g).to(ndt)
+    want = sample_q(Q, ip, noise, K, 0, dt)
+    return qs, ip, noise, want
+
+
+@pytest.mark.parametrize("tag", list(TAGS))
+@pytest.mark.parametrize("case", ['mvn', 'mvn2'])
+def test_mvn_sampling_program_emulated_vs_oracle(case, tag):
+    from plan_emulator import Emu
+    qs, ip, noise, want = mvn_sampling_case(case, tag)
+    ins = []
+    by_input = {name: noise[key] for key, kind, axes, pos, name in qs.noise}
+    for name in qs.plan.input_names:
+        if name in qs.plan.const_inputs:
+            ins.append(qs.plan.const_inputs[name])
+        elif name in by_input:
+            ins.append(by_input[name].contiguous())
+        else:
+            axes = next(a for k, a in qs.param_order if k == name)
+            ins.append(ip[name].order(axes).t.to(TAGS[tag]).contiguous())
+    outs = {i: t.zeros(max(1, int(t.tensor([qs.pl.sizes[a] for a in axes] + list(pos)).prod())), dtype=TAGS[tag])
+            for i, (_, axes, pos) in enumerate(qs.outputs)}
+    Emu(qs.plan, ins, outputs=outs).run(qs.plan.programs[0])
+    tol = 3e-6 if tag == 'f32' else 1e-12
+    for i, (var, axes, pos) in enumerate(qs.outputs):
+        mine = outs[i].reshape([qs.pl.sizes[a] for a in axes] + list(pos))
+        ref = want[var].order(axes).t
+        assert (mine - ref).abs().max() <= tol * max(1.0, float(ref.abs().max())), var
