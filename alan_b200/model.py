@@ -39,6 +39,7 @@ FAMILIES = {
     "NegativeBinomial": ("total_count", "probs", "logits"),
     "Binomial": ("total_count", "probs", "logits"),
     "MultivariateNormal": ("loc", "covariance_matrix", "precision_matrix", "scale_tril"),
+    "Dirichlet": ("concentration",),
 }
 # arguments that torch.distributions leaves as None unless given
 _OPTIONAL = {"probs", "logits"}
@@ -155,6 +156,7 @@ StudentT = _make("StudentT")
 NegativeBinomial = _make("NegativeBinomial")
 Binomial = _make("Binomial")
 MultivariateNormal = _make("MultivariateNormal")
+Dirichlet = _make("Dirichlet")
 
 
 class Data:

@@ -1267,6 +1267,8 @@ class Planner:
         (TorchDimDist.py:157-162)."""
         if dist.family == 'MultivariateNormal':
             return self._mvn_density(dist, value, scope, tag)
+        if dist.family == 'Dirichlet':
+            return self._dirichlet_density(dist, value, scope, tag)
         args = {k: self.resolve_arg(dist.family, k, v, scope) for k, v in dist.args.items()}
         if dist.family in ('Bernoulli',):
             opname = 'Bernoulli_logits' if 'logits' in args else 'Bernoulli_probs'
@@ -1339,6 +1341,20 @@ class Planner:
         mk = Expr.make
         z = mk('sumlast', mk('mul', W, mk('sub', value, loc)))            # W (x - loc): [cells..., d]
         body = mk('sub', c, mk('mul', Expr.const(0.5), mk('sumlast', mk('square', z))))
+        return self.emit_expr(self._prepare(body), nred='all', tag=tag)
+
+    def _dirichlet_density(self, dist, value, scope, tag) -> PT:
+        """torch.distributions.Dirichlet.log_prob over the last positional dim (the simplex), as expressions:
+        sum_j xlogy(alpha_j - 1, x_j) + lgamma(sum_j alpha_j) - sum_j lgamma(alpha_j)."""
+        alpha = self._prepare(self.resolve_arg(dist.family, 'concentration', dist.args['concentration'], scope))
+        value = self._prepare(value)
+        if len(value.pos_shape) != 1 or len(alpha.pos_shape) != 1 or alpha.pos_shape != value.pos_shape:
+            raise Exception(f"Dirichlet: value and concentration must be vectors of one size "
+                            f"(got {value.pos_shape} and {alpha.pos_shape})")
+        mk = Expr.make
+        body = mk('sub', mk('add', mk('sumlast', mk('mul', mk('sub', alpha, Expr.const(1.0)), mk('log', value))),
+                            mk('lgamma', mk('sumlast', alpha))),
+                  mk('sumlast', mk('lgamma', alpha)))
         return self.emit_expr(self._prepare(body), nred='all', tag=tag)
 
     FAN_EVENT_EXTENTS = (1, 2, 3, 4, 6, 8, 12, 16, 18, 24, 32)

@@ -495,3 +495,33 @@ def mvn2_inputs(T=6, F=4, seed=0, dtype=t.float32):
 
 CASES['mvn'] = (mvn_model, mvn_inputs, dict(T=10), 5, [('a', 'mean'), ('a', 'mean2')], [], 6)
 CASES['mvn2'] = (mvn2_model, mvn2_inputs, dict(T=6), 4, [('a', 'mean'), ('z', 'mean2')], [], 5)
+
+
+# --------------------------------------------------------------------------- Dirichlet (row f-2)
+def dirichlet_model(ns):
+    """A simplex-valued global latent and a plated one whose concentration depends on it (dist.py:323-359 family list)."""
+    P = ns.Plate(
+        p=ns.Dirichlet(t.tensor([1.5, 2.0, 0.7, 3.0])),
+        T=ns.Plate(
+            q=ns.Dirichlet(lambda p: 1.0 + 4.0 * p),
+            y=ns.Normal(lambda q, w: q @ w, 0.7),
+        ),
+    )
+    Q = ns.Plate(
+        p=ns.Dirichlet('qp_conc'),
+        T=ns.Plate(
+            q=ns.Dirichlet(lambda p, qq_w: 0.5 + qq_w * p),
+            y=ns.Data(),
+        ),
+    )
+    return P, Q
+
+
+def dirichlet_inputs(T=5, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    return dict(platesizes={'T': T}, data={'y': t.randn(T, generator=g, dtype=t.float64).to(dtype).refine_names('T')},
+                inputs={'w': t.tensor([1.0, -2.0, 0.5, 3.0], dtype=dtype)},
+                params={'qp_conc': t.tensor([2.0, 2.5, 1.2, 2.2], dtype=dtype), 'qq_w': t.tensor(3.0, dtype=dtype)})
+
+
+CASES['dirichlet'] = (dirichlet_model, dirichlet_inputs, dict(T=5), 4, [('p', 'mean'), ('q', 'mean2')], [], 5)
