@@ -28,7 +28,7 @@
 enum { SP_WS = 0, SP_INPUT = 1, SP_OUTPUT = 2, SP_AUX = 3 };
 enum { OP_FILL = 1, OP_EXPR = 2, OP_EXPR_BWD = 3, OP_REDUCE = 4, OP_CHAIN = 5, OP_CHAIN_BWD = 6, OP_SAMPLE = 7,
        OP_NORMAL_FAN = 8, OP_COPY = 9, OP_DOT = 10, OP_FAN_LSE = 11, OP_BERN_DOT = 12, OP_FAN_BWD = 13, OP_XREDUCE = 14, OP_NORMAL_Q_BWD = 15, OP_PERM = 16, OP_KGATHER = 17,
-       OP_TS_SAMPLE = 18, OP_DEPS = 19, OP_NORMAL_POLY_SUM = 20, OP_PASTE = 21, OP_MVN_PREP = 22 };
+       OP_TS_SAMPLE = 18, OP_DEPS = 19, OP_NORMAL_POLY_SUM = 20, OP_PASTE = 21, OP_MVN_PREP = 22, OP_RSEQ = 23 };
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -154,6 +154,49 @@ static void read_prog(Reader& r, VMProg<T>& P) {
     int nc = r.i32();
     for (int i = 0; i < nc; ++i) P.consts[i] = (T)r.f64();
     P.res = r.i32();
+}
+
+template <typename T>
+static void parse_reduce(Reader& r, const Ctx& c, ReduceParams<T>& p, int& thread_hint) {
+    p.mode = r.i32();
+    p.out = (T*)tref(r, c);
+    p.acc = r.i32();
+    p.scale = (T)r.f64();
+    p.cadd = (T)r.f64();
+    p.nsplit = r.i32();
+    thread_hint = r.i32();
+    p.m_out = nullptr; p.lo_out = nullptr;
+    if (p.mode == R_LSE_EPS || p.mode == R_LSE) {
+        if (r.i32()) { p.m_out = (T*)tref(r, c); p.lo_out = (T*)tref(r, c); }
+    }
+    read_dims(r, p.d, p.n_out, p.n_red);
+    p.nf = r.i32();
+    for (int f = 0; f < p.nf; ++f) {
+        p.coeff[f] = (T)r.f64();
+        read_opnd(r, c, p.f[f], p.d.nd, false);
+    }
+    if (p.mode == R_WSUM) {
+        read_opnd(r, c, p.lse_m, p.d.nd, false);
+        read_opnd(r, c, p.lse_lo, p.d.nd, false);
+        read_opnd(r, c, p.gout, p.d.nd, false);
+    }
+}
+
+// returns an error message or nullptr
+template <typename T>
+static const char* parse_xreduce(Reader& r, const Ctx& c, const alan_b200_plan* plan, XReduceParams<T>& x, bool dry) {
+    memset(&x, 0, sizeof(x));
+    const int site = r.i32();
+    x.n_pieces = r.i32();
+    for (int q = 0; q < x.n_pieces; ++q) { x.piece[q] = (T*)tref(r, c); x.piece_n[q] = r.i64v(); x.n_total += x.piece_n[q]; }
+    if (dry) return nullptr;
+    if (plan->comm_world < 2 || !plan->comm_peer[0])
+        return "this plan reduces across ranks inside its programs (fused collectives): call "
+               "alan_b200_plan_set_comm with the ranks' symmetric buffers first";
+    if (site < 0 || site >= (int)plan->site_off.size()) return "xreduce: unknown site";
+    x.rank = plan->comm_rank; x.world = plan->comm_world;
+    for (int q = 0; q < x.world; ++q) x.site[q] = plan->comm_peer[q] + plan->site_off[site];
+    return nullptr;
 }
 
 #define AB_PAR_STREAMS 6
@@ -349,30 +392,43 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c0, bool 
                 launch_expr_bwd<T>(p, c.stream, c.sm_count);
                 break;
             }
+            case OP_RSEQ: {
+                // a run of small reductions (and at most one cross-rank sum) as one single-CTA launch (kernels.cuh)
+                const int n = r.i32();
+                if (n < 1 || n > AB_RSEQ_MAX) return fail("reduction sequence: bad op count");
+                RSeqParams<T> sp;
+                memset(&sp, 0, sizeof(sp));
+                sp.n = n;
+                std::vector<ReduceParams<T>> full(n);
+                std::vector<int> hint(n, 0);
+                bool has_x = false, compact = true;
+                for (int k = 0; k < n; ++k) {
+                    const int32_t* sub = r.p;
+                    const int sub_code = r.i32();
+                    const int sub_words = r.i32();
+                    if (sub_code == OP_REDUCE) {
+                        parse_reduce<T>(r, c, full[k], hint[k]);
+                        compact = rc_from(full[k], reduce_uses_warps(full[k], hint[k] != 0), sp.op[k]) && compact;
+                    } else if (sub_code == OP_XREDUCE) {
+                        if (has_x) return fail("reduction sequence: more than one cross-rank reduction");
+                        has_x = true;
+                        const char* err = parse_xreduce<T>(r, c, plan, sp.x, count_only);
+                        if (err) return fail(err);
+                        sp.op[k].kind = RS_XREDUCE;
+                    } else return fail("reduction sequence: unsupported member op");
+                    r.p = sub + sub_words;
+                }
+                if (compact) { reduce_seq_kernel<T><<<1, AB_RSEQ_THREADS, 0, c.stream>>>(sp); break; }
+                for (int k = 0; k < n; ++k) {                     // a member exceeds the compact form: one launch each
+                    if (sp.op[k].kind == RS_XREDUCE) xreduce_kernel<T><<<1, 512, 0, c.stream>>>(sp.x);
+                    else launch_reduce<T>(full[k], hint[k] != 0, c.stream, c.sm_count);
+                }
+                break;
+            }
             case OP_REDUCE: {
                 ReduceParams<T> p;
-                p.mode = r.i32();
-                p.out = (T*)tref(r, c);
-                p.acc = r.i32();
-                p.scale = (T)r.f64();
-                p.cadd = (T)r.f64();
-                p.nsplit = r.i32();
-                int thread_hint = r.i32();
-                p.m_out = nullptr; p.lo_out = nullptr;
-                if (p.mode == R_LSE_EPS || p.mode == R_LSE) {
-                    if (r.i32()) { p.m_out = (T*)tref(r, c); p.lo_out = (T*)tref(r, c); }
-                }
-                read_dims(r, p.d, p.n_out, p.n_red);
-                p.nf = r.i32();
-                for (int f = 0; f < p.nf; ++f) {
-                    p.coeff[f] = (T)r.f64();
-                    read_opnd(r, c, p.f[f], p.d.nd, false);
-                }
-                if (p.mode == R_WSUM) {
-                    read_opnd(r, c, p.lse_m, p.d.nd, false);
-                    read_opnd(r, c, p.lse_lo, p.d.nd, false);
-                    read_opnd(r, c, p.gout, p.d.nd, false);
-                }
+                int thread_hint = 0;
+                parse_reduce<T>(r, c, p, thread_hint);
                 // small: few points, or a plain fixed-order sum of partial rows with few outputs (one thread per output
                     // walks the rows: e.g. the 160 x 900 partial rows of the fused plate sum)
                 if (batching && (p.n_out * p.n_red <= plan->seq_points ||
@@ -389,17 +445,11 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c0, bool 
             }
             case OP_XREDUCE: {
                 XReduceParams<T> x;
-                memset(&x, 0, sizeof(x));
-                const int site = r.i32();
-                x.n_pieces = r.i32();
-                for (int q = 0; q < x.n_pieces; ++q) { x.piece[q] = (T*)tref(r, c); x.piece_n[q] = r.i64v(); x.n_total += x.piece_n[q]; }
+                {
+                    const char* err = parse_xreduce<T>(r, c, plan, x, count_only);
+                    if (err) return fail(err);
+                }
                 if (count_only) { if (!batching) ++nl; else { if (seq.n == AB_SEQ_MAX) flush(); seq.n++; } break; }
-                if (plan->comm_world < 2 || !plan->comm_peer[0])
-                    return fail("this plan reduces across ranks inside its programs (fused collectives): call "
-                                "alan_b200_plan_set_comm with the ranks' symmetric buffers first");
-                if (site < 0 || site >= (int)plan->site_off.size()) return fail("xreduce: unknown site");
-                x.rank = plan->comm_rank; x.world = plan->comm_world;
-                for (int q = 0; q < x.world; ++q) x.site[q] = plan->comm_peer[q] + plan->site_off[site];
                 if (!batching) { xreduce_kernel<T><<<1, 512, 0, c.stream>>>(x); break; }      // stand-alone: a 0.4 KB parameter block
                 if (seq.n == AB_SEQ_MAX) flush();
                 SeqOp<T>& o = seq.op[seq.n++];

@@ -619,6 +619,162 @@ __global__ void __launch_bounds__(512) xreduce_kernel(const __grid_constant__ XR
 }
 
 // ------------------------------------------------------------------------------------------
+// Reduction sequences (plan.py ReduceSeqOp): a run of consecutive SMALL reductions -- the top-level contractions, their
+// adjoints, the cross-rank sum between them -- in one single-CTA launch, __syncthreads() between the ops.  The
+// parameter blocks stay in kernel-parameter space and are read with a uniform index (no staging copy: gathering a
+// 1.4 KB block with one word per thread serialises on the constant cache, which is what made the general small-op
+// sequences below cost as much as the launches they replaced).
+// ------------------------------------------------------------------------------------------
+#define AB_RSEQ_MAX 12
+#define AB_RSEQ_THREADS 512
+#define RC_MAXD 4
+#define RC_MAXF 4
+enum { RS_REDUCE = 0, RS_XREDUCE = 2 };
+
+// A reduction in ~0.3 KB instead of the 1.4 KB of ReduceParams: <= 4 (coalesced) dims, <= 4 factors, 32-bit strides.
+// Why it matters: kernel parameters live in the constant bank and arrive COLD; a small op walks its parameter block
+// through dependent constant-cache misses (~0.3 us each), which is where a microsecond-scale op spends its time.
+template <typename T>
+struct RCompact {
+    T* out; T* m_out; T* lo_out;
+    const T* f[RC_MAXF]; const T* lse_m; const T* lse_lo; const T* gout;
+    int fs[RC_MAXF][RC_MAXD]; int ms[RC_MAXD], ls[RC_MAXD], gs[RC_MAXD];
+    int size[RC_MAXD];
+    int nd, n_a, mode, nf, acc, nsplit, warp, kind;
+    int n_out, n_red;
+    T coeff[RC_MAXF]; T scale, cadd;
+};
+
+template <typename T>
+struct RSeqParams {
+    int n, pad;
+    RCompact<T> op[AB_RSEQ_MAX];
+    XReduceParams<T> x;                   // at most one cross-rank reduction per sequence
+};
+
+template <typename T>
+__device__ __forceinline__ T rc_fsum(const RCompact<T>& p, const int* base, const int* ir) {
+    T s = T(0);
+#pragma unroll 1
+    for (int f = 0; f < p.nf; ++f) {
+        int off = base[f];
+        for (int k = p.n_a; k < p.nd; ++k) off += ir[k] * p.fs[f][k];
+        s += p.coeff[f] * p.f[f][off];
+    }
+    return s;
+}
+__device__ __forceinline__ void rc_unravel(int l, const int* size, int lo, int hi, int* idx) {
+    for (int k = hi - 1; k >= lo; --k) { const int q = l / size[k]; idx[k] = l - q * size[k]; l = q; }
+}
+__device__ __forceinline__ int rc_dot(const int* idx, const int* st, int lo, int hi) {
+    int off = 0;
+    for (int k = lo; k < hi; ++k) off += idx[k] * st[k];
+    return off;
+}
+
+// Same arithmetic, in the same order, as reduce_thread_body / reduce_warp_body (bit-identical results).
+template <typename T>
+__device__ void rc_body(const RCompact<T>& p, const int t0, const int tn) {
+    const bool warp = p.warp != 0;
+    const int lane = warp ? (t0 & 31) : 0, L = warp ? 32 : 1;
+    const int worker = warp ? (t0 >> 5) : t0, nworkers = warp ? (tn >> 5) : tn;
+    const int total = p.n_out * p.nsplit;
+    const int chunk = (p.n_red + p.nsplit - 1) / p.nsplit;
+    int idx[RC_MAXD], base[RC_MAXF];
+    for (int w = worker; w < total; w += nworkers) {
+        const int o = w % p.n_out, s = w / p.n_out;
+        const int lo = s * chunk, hi = lo + chunk < p.n_red ? lo + chunk : p.n_red;
+        rc_unravel(o, p.size, 0, p.n_a, idx);
+        for (int f = 0; f < p.nf; ++f) base[f] = rc_dot(idx, p.fs[f], 0, p.n_a);
+        T res;
+        if (p.mode == R_SUM) {
+            T a = T(0);
+            for (int j = lo + lane; j < hi; j += L) { rc_unravel(j, p.size, p.n_a, p.nd, idx); a += rc_fsum(p, base, idx); }
+            res = warp ? warp_sum(a) : a;
+        } else if (p.mode == R_WSUM) {
+            const int mb = rc_dot(idx, p.ms, 0, p.n_a), lb = rc_dot(idx, p.ls, 0, p.n_a), gb = rc_dot(idx, p.gs, 0, p.n_a);
+            T a = T(0);
+            for (int j = lo + lane; j < hi; j += L) {
+                rc_unravel(j, p.size, p.n_a, p.nd, idx);
+                const T sv = rc_fsum(p, base, idx);
+                const T mm = p.lse_m[mb + rc_dot(idx, p.ms, p.n_a, p.nd)];
+                const T l = p.lse_lo[lb + rc_dot(idx, p.ls, p.n_a, p.nd)];
+                const T g = p.gout[gb + rc_dot(idx, p.gs, p.n_a, p.nd)];
+                a += g * ab_exp((sv - mm) - l);
+            }
+            res = warp ? warp_sum(a) : a;
+        } else {
+            T m = neg_inf<T>();
+            for (int j = lo + lane; j < hi; j += L) { rc_unravel(j, p.size, p.n_a, p.nd, idx); m = ab_max(m, rc_fsum(p, base, idx)); }
+            if (warp) m = warp_max(m);
+            T a = T(0);
+            for (int j = lo + lane; j < hi; j += L) { rc_unravel(j, p.size, p.n_a, p.nd, idx); a += ab_exp(rc_fsum(p, base, idx) - m); }
+            if (warp) a = warp_sum(a);
+            const T lg = p.mode == R_LSE_EPS ? ab_log(a + Eps<T>::v()) : ab_log(a);
+            if (lane == 0 && p.m_out != nullptr) { p.m_out[o] = m; p.lo_out[o] = lg; }
+            res = lg + m;
+        }
+        if (lane == 0) {
+            if (p.nsplit > 1) p.out[s * p.n_out + o] = res;
+            else {
+                const T v = p.scale * res + (p.mode == R_WSUM ? T(0) : p.cadd);
+                p.out[o] = p.acc ? p.out[o] + v : v;
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(AB_RSEQ_THREADS) reduce_seq_kernel(const __grid_constant__ RSeqParams<T> sp) {
+    __shared__ __align__(16) RCompact<T> s_op[AB_RSEQ_MAX];
+    const int t0 = threadIdx.x, tn = blockDim.x, lane = t0 & 31, wid = t0 >> 5, nw = tn >> 5;
+    {
+        // parameter blocks -> shared memory: every warp fetches whole 64-byte lines with warp-uniform addresses (one
+        // constant-cache transaction per word, the cold misses of different warps overlap)
+        const unsigned* src = reinterpret_cast<const unsigned*>(&sp.op[0]);
+        unsigned* dst = reinterpret_cast<unsigned*>(s_op);
+        const int nwords = sp.n * (int)(sizeof(RCompact<T>) / 4);
+        for (int line = wid; line * 16 < nwords; line += nw) {
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+                const int k = line * 16 + w;
+                if (k < nwords) { const unsigned v = src[k]; if (lane == w) dst[k] = v; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = 0; i < sp.n; ++i) {
+        if (i) __syncthreads();                   // same CTA: the previous op's global-memory results are visible
+        if (s_op[i].kind == RS_XREDUCE) { __threadfence(); xreduce_body<T>(sp.x, (i64)t0, (i64)tn); continue; }
+        rc_body<T>(s_op[i], t0, tn);
+    }
+}
+
+// host: ReduceParams -> RCompact when it fits (else the sequence runs as separate launches)
+template <typename T>
+static bool rc_from(const ReduceParams<T>& p, bool warp, RCompact<T>& c) {
+    memset(&c, 0, sizeof(c));
+    if (p.d.nd > RC_MAXD || p.nf > RC_MAXF) return false;
+    if (p.n_out * p.nsplit > 0x3fffffff || p.n_red > 0x3fffffff) return false;
+    auto fits = [&](const Opnd& o, int* st) {
+        if (o.mode != 0) return false;
+        for (int k = 0; k < p.d.nd; ++k) { if (o.stride[k] > 0x3fffffff || o.stride[k] < -0x3fffffff) return false; st[k] = (int)o.stride[k]; }
+        return true;
+    };
+    for (int f = 0; f < p.nf; ++f) { if (!fits(p.f[f], c.fs[f])) return false; c.f[f] = (const T*)p.f[f].ptr; c.coeff[f] = p.coeff[f]; }
+    if (p.mode == R_WSUM) {
+        if (!fits(p.lse_m, c.ms) || !fits(p.lse_lo, c.ls) || !fits(p.gout, c.gs)) return false;
+        c.lse_m = (const T*)p.lse_m.ptr; c.lse_lo = (const T*)p.lse_lo.ptr; c.gout = (const T*)p.gout.ptr;
+    }
+    for (int k = 0; k < p.d.nd; ++k) c.size[k] = p.d.size[k];
+    c.out = p.out; c.m_out = p.m_out; c.lo_out = p.lo_out;
+    c.nd = p.d.nd; c.n_a = p.d.n_a; c.mode = p.mode; c.nf = p.nf; c.acc = p.acc; c.nsplit = p.nsplit;
+    c.warp = warp ? 1 : 0; c.kind = RS_REDUCE;
+    c.n_out = (int)p.n_out; c.n_red = (int)p.n_red; c.scale = p.scale; c.cadd = p.cadd;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
 // Small-op sequences.  A plate tree has dozens of ops whose whole iteration space is a few thousand
 // points (global latents, top-level contractions, their adjoints): as separate launches each costs a
 // launch latency plus a drain, several microseconds for nanoseconds of work.  Consecutive small ops of

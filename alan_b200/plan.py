@@ -35,7 +35,7 @@ MAGIC, VERSION = 0x0A1AB200, 1
 SP_WS, SP_INPUT, SP_OUTPUT, SP_AUX = 0, 1, 2, 3
 OP_FILL, OP_EXPR, OP_EXPR_BWD, OP_REDUCE, OP_CHAIN, OP_CHAIN_BWD, OP_SAMPLE, OP_NORMAL_FAN, OP_COPY, OP_DOT, \
     OP_FAN_LSE, OP_BERN_DOT, OP_FAN_BWD, OP_XREDUCE, OP_NORMAL_Q_BWD, OP_PERM, OP_KGATHER, OP_TS_SAMPLE, OP_DEPS, OP_NORMAL_POLY_SUM, OP_PASTE, \
-    OP_MVN_PREP = range(1, 23)
+    OP_MVN_PREP, OP_RSEQ = range(1, 24)
 R_SUM, R_LSE_EPS, R_LSE, R_WSUM = 0, 1, 2, 3
 HOIST_RATIO = 16
 NONMP_K = 'K_'          # the one K axis every latent shares in a SampleNonMP plan (no group can be named '')
@@ -703,6 +703,65 @@ class PasteOp(Op):
             w.i32(size); w.i64(ss); w.i64(ds)
 
 
+class ReduceSeqOp(Op):
+    """A run of consecutive SMALL reductions (top-level contractions, their adjoints, the cross-rank sum between them)
+    executed by ONE single-CTA launch (csrc/kernels.cuh reduce_seq_kernel): the ops run back to back with a
+    __syncthreads() between them instead of a launch latency + drain each (~4 us per dependent graph node for
+    nanoseconds of work).  Built by `fuse_small_reductions` after the programs are complete; to the dependency
+    analysis it is one op touching the union of its members' tensors."""
+    code = OP_RSEQ
+    MAX_OPS, MAX_POINTS = 12, 16384
+    # Measured on B200 (profiles/r02_small_ops.md): a member costs ~4.5 us inside the single CTA (a serial chain of ~2000
+    # dependent instructions per warp task, IPC 0.25: ncu), about what a dependent node of a replayed CUDA graph costs,
+    # and separate nodes overlap with the rest of the program's DAG.  Runs of 4-5 members (MovieLens top level) LOSE
+    # 14 us per step, runs of 7-9 (radon-shaped trees) are neutral (0.251 vs 0.256 ms per marginals() replay, 34 vs 48
+    # launches): only long runs are fused.
+    MIN_OPS = int(os.environ.get('ALAN_B200_RSEQ_MIN', '6'))
+
+    def __init__(self, ops):
+        self.ops = list(ops)
+        self.is_barrier = any(isinstance(o, XReduceOp) for o in self.ops)
+        self.tag = '+'.join(getattr(o, 'tag', '') or type(o).__name__ for o in self.ops)
+
+    def payload(self, w):
+        w.i32(len(self.ops))
+        for o in self.ops:
+            o.serialize(w)
+
+
+def fuse_small_reductions(prog):
+    """Wrap maximal runs of consecutive small ReduceOps (and XReduceOps between / beside them) into ReduceSeqOps."""
+    def small(o):
+        if type(o) is XReduceOp:
+            return True
+        if type(o) is not ReduceOp:
+            return False
+        pts = _prod(d[2] for d in o.od + o.rd)
+        return pts * max(len(o.factors), 1) <= ReduceSeqOp.MAX_POINTS
+    out, run = [], []
+
+    def close():
+        nonlocal run
+        n_red = sum(type(o) is ReduceOp for o in run)
+        n_x = sum(type(o) is XReduceOp for o in run)
+        if n_red + n_x >= max(ReduceSeqOp.MIN_OPS, 2):
+            out.append(ReduceSeqOp(run))
+        else:
+            out.extend(run)
+        run = []
+    for o in prog:
+        if small(o) and len(run) < ReduceSeqOp.MAX_OPS and not (type(o) is XReduceOp and any(type(x) is XReduceOp for x in run)):
+            run.append(o)
+        else:
+            close()
+            if small(o):
+                run.append(o)
+            else:
+                out.append(o)
+    close()
+    return out
+
+
 class MvnPrepOp(Op):
     """csrc/mvn.cuh: the matrix argument of a MultivariateNormal -> scale_tril L, its inverse W and the constant
     c = -sum log L_ii - d/2 log 2 pi, one warp per matrix.  mode: 0 covariance_matrix, 1 precision_matrix, 2 scale_tril."""
@@ -924,7 +983,7 @@ class Plan:
             last = {}                      # tensor key -> index (in the final program, DepsOp = 0) of its last toucher
             deps, barrier = [[]], 0        # entry 0: the table itself
             for k, op in enumerate(ops, start=1):
-                if isinstance(op, (FillRegionOp, XReduceOp)):
+                if isinstance(op, (FillRegionOp, XReduceOp)) or getattr(op, 'is_barrier', False):
                     deps.append(list(range(1, k)))
                     barrier = k
                     last = {}
@@ -944,6 +1003,8 @@ class Plan:
         """Dry-run serialisation to find the workspace tensors the emitted ops really touch, then lay
         them out: forward tensors first, adjoints/partials after (one contiguous region to zero)."""
         self.adj_region = (0, 0)
+        if os.environ.get('ALAN_B200_RSEQ', '1') != '0':       # read when the plan is BUILT
+            self.programs = [fuse_small_reductions([o for o in prog if not isinstance(o, DepsOp)]) for prog in self.programs]
         self.insert_deps()
         w = W()
         for prog in self.programs:

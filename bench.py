@@ -214,6 +214,10 @@ def op_model(op, itemsize):
         add(op.gout); add(op.out)
         flops = pts * (len(op.factors) + (0 if op.mode == 0 else 3))
         tag = op.tag or ("adjoint" if op.mode == 3 else "sum")
+    elif name == "ReduceSeqOp":
+        parts = [op_model(o, itemsize) for o in op.ops]
+        pts, flops, nbytes = sum(m["points"] for m in parts), sum(m["flops"] for m in parts), sum(m["bytes"] for m in parts)
+        tag = "+".join(m["tag"] for m in parts)[:60]
     else:
         pts, tag = 0, name
     return dict(kind=name, tag=tag, bytes=nbytes, flops=flops, points=pts)

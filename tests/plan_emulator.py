@@ -135,6 +135,10 @@ class Emu:
         for op in ops:
             getattr(self, 'op_' + type(op).__name__)(op)
 
+    def op_ReduceSeqOp(self, op):
+        """a run of small reductions in one launch: same results as the ops one by one"""
+        self.run(op.ops)
+
     def op_DepsOp(self, op):
         """the dependency table of a program: every listed index precedes its op (a chain satisfies it)"""
         for k, d in enumerate(op.deps):

@@ -64,7 +64,9 @@ def _worker(rank, world, port, ret, fused=False):
     if fused:
         # the exchanges are ops inside the programs (plan.XReduceOp; the emulator performs them over gloo):
         # one forward and one backward program, like an unsharded plan
-        kinds = [[type(op).__name__ for op in prog] for prog in plan.programs]
+        # (small reductions next to them ride in the same single-CTA launch: plan.ReduceSeqOp -- flattened here)
+        flat = lambda prog: [m for op in prog for m in (op.ops if type(op).__name__ == 'ReduceSeqOp' else [op])]
+        kinds = [[type(op).__name__ for op in flat(prog)] for prog in plan.programs]
         assert plan.n_fwd == 1 and plan.n_bwd == 1 and 'XReduceOp' in kinds[0] and kinds[1][-1] == 'XReduceOp'
         emu.run(plan.programs[0])
     else:
