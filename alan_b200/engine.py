@@ -608,3 +608,79 @@ class StreamedRunner:
         for n, g in gsum.items():
             self.grads[n].copy_(g)
         return lp, self.grads
+
+
+class PipelinedRunner:
+    """Host-batch entry point of a training loop: one log-evidence + gradient step per submitted batch of HOST
+    tensors, two batches in flight.
+
+    What the reference's loop does per iteration -- move the minibatch to the device, `elbo_rws().backward()`, read
+    the loss (examples/runner.py:120-160) -- is three serial phases.  Here they run on three streams: the H2D copy
+    of batch s+1 (copy stream, into the idle one of two device input sets) overlaps the kernels of batch s (compute
+    stream; `Runner.step`, one replayed CUDA graph per input set) and the D2H of batch s-1's results (read-back
+    stream, into that batch's pinned host buffers).  Steady state costs max(copy, compute) per step instead of their
+    sum; on cfg-5 the copy (61 MB over PCIe) is the longer of the two.
+
+        h = pipe.submit(host_tensors)        # canonical pinned host tensors (see `pin`); returns a ticket
+        lp, grads = pipe.result(h)           # blocks until THAT batch's results are on the host (pinned tensors,
+                                             # valid until two more batches have been submitted)
+    """
+    def __init__(self, comp: Compiled, device=None, process_group=None, depth: int = 2, runner: "Runner" = None):
+        self.run = runner if runner is not None else Runner(comp, device, process_group)
+        self.comp, self.device, self.dtype = comp, self.run.device, comp.dtype
+        self.depth = int(depth)
+        plan = comp.plan
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.back_stream = torch.cuda.Stream(device=self.device)
+        mk = lambda: [torch.empty(plan.input_pts[n].shape, dtype=self.dtype, device=self.device) for n in plan.input_names]
+        self.dev = [mk() for _ in range(self.depth)]
+        self.lp_host = [torch.empty((), dtype=self.dtype).pin_memory() for _ in range(self.depth)]
+        self.g_host = [{n: torch.empty(plan.input_pts[n].shape, dtype=self.dtype).pin_memory() for n in plan.grad_inputs}
+                       for _ in range(self.depth)]
+        self.g_dev = [None] * self.depth             # device result buffers of each slot (static once its graph exists)
+        self.landed = [torch.cuda.Event() for _ in range(self.depth)]       # H2D of the slot's batch finished
+        self.computed = [torch.cuda.Event() for _ in range(self.depth)]     # step on the slot finished
+        self.read = [torch.cuda.Event() for _ in range(self.depth)]         # D2H of the slot's results finished
+        self.free = [torch.cuda.Event() for _ in range(self.depth)]         # the slot's device results were copied out
+        self.n = 0
+        self.before_step = None                      # optional callable run on the compute stream before every step
+
+    def pin(self, sample, inputs_params, data):
+        """Canonical host tensors in pinned memory, in plan input order (what `submit` consumes)."""
+        return [x.pin_memory() for x in self.comp.canonical_inputs(sample, inputs_params, data)]
+
+    def submit(self, host) -> int:
+        slot = self.n % self.depth
+        cur = torch.cuda.current_stream(self.device)
+        if self.n >= self.depth:
+            # the slot's previous batch: its kernels have read the device inputs, its results have left the device
+            self.copy_stream.wait_event(self.computed[slot])
+            cur.wait_event(self.free[slot])
+            self.read[slot].synchronize()            # its host result buffers are about to be reused
+        with torch.cuda.stream(self.copy_stream):
+            for d, h in zip(self.dev[slot], host):
+                d.copy_(h, non_blocking=True)
+            self.landed[slot].record(self.copy_stream)
+        cur.wait_event(self.landed[slot])
+        if self.before_step is not None:
+            self.before_step()
+        lp, grads = self.run.step(self.dev[slot])
+        self.computed[slot].record(cur)
+        self.back_stream.wait_event(self.computed[slot])
+        with torch.cuda.stream(self.back_stream):
+            self.lp_host[slot].copy_(lp, non_blocking=True)
+            for n, g in grads.items():
+                self.g_host[slot][n].copy_(g, non_blocking=True)
+            self.free[slot].record(self.back_stream)
+            self.read[slot].record(self.back_stream)
+        # results of an eager (not yet captured) step are fresh tensors: keep them alive until they are copied out
+        self.g_dev[slot] = (lp, grads)
+        self.n += 1
+        return self.n - 1
+
+    def result(self, ticket: int):
+        if ticket < self.n - self.depth or ticket >= self.n:
+            raise Exception(f"batch {ticket} is not in flight (submitted so far: {self.n}, depth {self.depth})")
+        slot = ticket % self.depth
+        self.read[slot].synchronize()
+        return self.lp_host[slot], self.g_host[slot]

@@ -7,7 +7,7 @@ import torch as t
 
 import models
 from alan_b200 import model as M
-from alan_b200.named import NT
+from alan_b200.named import NT, from_torch_named
 from golden_io import load, rel_err, tol, TAGS
 from uniforms import UniformSource
 
@@ -242,3 +242,46 @@ def test_compstrat_split_matches_single_pass(case, plate, size, tag):
     if case == "cfg3_radon":                       # only top-level plates can be split here; a nested one is refused
         with pytest.raises(Exception, match="Split"):
             prob.sample_from({k: NT(*v) for k, v in g["sample"].items()}).elbo_nograd(computation_strategy=Split("Counties", 2))
+
+
+def test_pipelined_runner_matches_single_steps():
+    """engine.PipelinedRunner (two host batches in flight: H2D of s+1 over the kernels of s over the D2H of s-1) returns,
+    for every submitted batch, exactly what Runner.step returns for that batch alone."""
+    from alan_b200.engine import Compiled, Runner, PipelinedRunner
+    P, Q = models.build('cfg2_movielens', M, t.float32)
+    inp = models.movielens_inputs(M=64, N=5, dtype=t.float32)
+    nt = lambda d: {k: from_torch_named(v) if any(n is not None for n in v.names) else NT(v, ()) for k, v in d.items()}
+    ip, data = {**nt(inp['inputs']), **nt(inp['params'])}, nt(inp['data'])
+    K, d = 8, 18
+    g = t.Generator().manual_seed(4)
+    def sample(seed_scale):
+        return {'mu_z': NT(seed_scale * t.randn(K, d, generator=g), ('K_mu_z',)),
+                'psi_z': NT(0.3 * t.randn(K, d, generator=g), ('K_psi_z',)),
+                'z': NT(seed_scale * t.randn(64, K, d, generator=g), ('plate_1', 'K_z'))}
+    batches = [sample(0.5 + 0.1 * i) for i in range(7)]
+    comp = Compiled(P, Q, batches[0], ip, data, grad_names=list(inp['params']))
+    ref = Runner(comp, 'cuda:0')
+    want = []
+    for b in batches:
+        tens = [x.cuda() for x in comp.canonical_inputs(b, ip, data)]
+        lp = ref.forward_raw(tens)
+        gr = ref.backward_raw(tens)
+        want.append((lp.cpu().clone(), {n: v.cpu().clone() for n, v in gr.items()}))
+    pipe = PipelinedRunner(comp, 'cuda:0')
+    hosts = [pipe.pin(b, ip, data) for b in batches]
+    got = []
+    tk_prev = None
+    for h in hosts:
+        tk = pipe.submit(h)
+        if tk_prev is not None:
+            lp, gr = pipe.result(tk_prev)
+            got.append((lp.clone(), {n: v.clone() for n, v in gr.items()}))
+        tk_prev = tk
+    lp, gr = pipe.result(tk_prev)
+    got.append((lp.clone(), {n: v.clone() for n, v in gr.items()}))
+    with pytest.raises(Exception, match="not in flight"):
+        pipe.result(0)
+    for (lw, gw), (lg, gg) in zip(want, got):
+        assert t.equal(lw, lg)
+        for n in gw:
+            assert t.equal(gw[n], gg[n]), n
