@@ -1157,6 +1157,19 @@ int alan_b200_gather(const void* x, const int64_t* idx, void* out, int elem_byte
     return 0;
 }
 
+int alan_b200_widen_u8(const void* src, void* dst, int64_t n, int dtype, void* stream) {
+    if (n <= 0) return 0;
+    if (((uintptr_t)src % 16) || ((uintptr_t)dst % 16)) return fail("widen_u8: source and destination must be 16-byte aligned");
+    i64 g = (n / 16 + 255) / 256;
+    const int grid = (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+    if (dtype == 0) widen_u8_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)src, (float*)dst, n);
+    else if (dtype == 1) widen_u8_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)src, (double*)dst, n);
+    else return fail("widen_u8: dtype must be 0 (f32) or 1 (f64)");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("CUDA launch error: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C++" template <typename T>
 int qem_update_impl(int family, i64 n, double lr, const void* new0, const void* new1, void* mean0, void* mean1,
                     void* param0, void* param1, cudaStream_t st) {

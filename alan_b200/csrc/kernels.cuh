@@ -1253,3 +1253,31 @@ __global__ void gather_kernel(const E* __restrict__ x, const i64* __restrict__ i
         out[e] = x[(o * K + k) * inner + in];
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// widen: byte-typed inputs (binary features, 0/1 observations, small counts) travel over PCIe as bytes and become
+// the working dtype here, 16 bytes per thread per pass (the reference keeps such inputs as float tensors on the
+// host: examples/models/movielens/movielens.py:11-22; their values are exact in either type).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) widen_u8_kernel(const unsigned char* __restrict__ src, T* __restrict__ dst, i64 n) {
+    const i64 nv = n / 16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (i64)gridDim.x * blockDim.x) {
+        const uint4 v = s4[i];
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        T* o = dst + i * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (sizeof(T) == 4) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(o) + 4 * q) =
+                    make_float4((float)(w[q] & 255u), (float)((w[q] >> 8) & 255u), (float)((w[q] >> 16) & 255u), (float)(w[q] >> 24));
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) o[4 * q + b] = (T)((w[q] >> (8 * b)) & 255u);
+            }
+        }
+    }
+    for (i64 i = nv * 16 + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        dst[i] = (T)src[i];
+}

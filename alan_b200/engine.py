@@ -32,6 +32,17 @@ def working_dtype(*dicts):
     return dt
 
 
+def _to_working(t, dtype, device=None):
+    """Move to `device` (if given) and cast to the working dtype.  uint8 / bool tensors cross PCIe as bytes and are
+    widened on the device by the library's own kernel (alan_b200_widen_u8), not as four-byte floats."""
+    from . import runtime
+    if device is not None:
+        t = t.to(device)
+    if t.dtype in runtime.NARROW_DTYPES and t.is_cuda:
+        return runtime.widen(t.contiguous(), dtype=dtype)
+    return t.to(dtype).contiguous()
+
+
 class Compiled:
     """Plan + the canonical (contiguous, canonical axis order, working dtype) input list."""
     def __init__(self, P: Plate, Q: Plate, sample, inputs_params, data, extra_log_factors=None,
@@ -97,8 +108,10 @@ class Compiled:
             return self.elf_keys[name]
         return name
 
-    def canonical_inputs(self, sample, inputs_params, data, extra_log_factors=None, device=None):
-        """Permute every tensor to canonical axis order, make it contiguous in the working dtype."""
+    def canonical_inputs(self, sample, inputs_params, data, extra_log_factors=None, device=None, keep_narrow=False):
+        """Permute every tensor to canonical axis order, make it contiguous in the working dtype.  keep_narrow=True
+        leaves uint8 / bool tensors in their one-byte type (host staging of PipelinedRunner: they are widened on the
+        device after the copy)."""
         src = {}
         for d in (sample, inputs_params or {}, data or {}):
             src.update(d)
@@ -115,9 +128,10 @@ class Compiled:
                 v = elf[orig] if role == 'elf' else src[orig]
                 t = v.order(axes).t
             t = t.detach()
-            if device is not None:
-                t = t.to(device)
-            out.append(t.to(self.dtype).contiguous())
+            if keep_narrow and t.dtype in (torch.uint8, torch.bool):
+                out.append((t.to(device) if device is not None else t).contiguous())
+            else:
+                out.append(_to_working(t, self.dtype, device))
         return out
 
 
@@ -288,7 +302,7 @@ class Runner:
             else:
                 key, role, orig, axes = next(o for o in comp.order if o[0] == name)
                 v = elf[orig] if role == 'elf' else src[orig]
-                t = v.order(axes).t.to(self.device).to(self.dtype).contiguous()
+                t = _to_working(v.order(axes).t, self.dtype, self.device)
                 if name not in comp.grad_names:
                     t = t.detach()
             out.append(t)
@@ -644,12 +658,16 @@ class PipelinedRunner:
         self.free = [torch.cuda.Event() for _ in range(self.depth)]         # the slot's device results were copied out
         self.n = 0
         self.before_step = None                      # optional callable run on the compute stream before every step
+        self.stage = [{} for _ in range(self.depth)]  # per slot: input index -> one-byte device staging buffer
 
     def pin(self, sample, inputs_params, data):
-        """Canonical host tensors in pinned memory, in plan input order (what `submit` consumes)."""
-        return [x.pin_memory() for x in self.comp.canonical_inputs(sample, inputs_params, data)]
+        """Canonical host tensors in pinned memory, in plan input order (what `submit` consumes).  uint8 / bool
+        tensors (binary features, 0/1 observations) stay one byte per element: they cross PCIe as bytes and are
+        widened on the device right after their copy (alan_b200_widen_u8)."""
+        return [x.pin_memory() for x in self.comp.canonical_inputs(sample, inputs_params, data, keep_narrow=True)]
 
     def submit(self, host) -> int:
+        from . import runtime
         slot = self.n % self.depth
         cur = torch.cuda.current_stream(self.device)
         if self.n >= self.depth:
@@ -658,8 +676,15 @@ class PipelinedRunner:
             cur.wait_event(self.free[slot])
             self.read[slot].synchronize()            # its host result buffers are about to be reused
         with torch.cuda.stream(self.copy_stream):
-            for d, h in zip(self.dev[slot], host):
-                d.copy_(h, non_blocking=True)
+            for i, (d, h) in enumerate(zip(self.dev[slot], host)):
+                if h.dtype in runtime.NARROW_DTYPES:
+                    st = self.stage[slot].get(i)
+                    if st is None or st.dtype != h.dtype:
+                        st = self.stage[slot][i] = torch.empty(d.shape, dtype=h.dtype, device=self.device)
+                    st.copy_(h, non_blocking=True)
+                    runtime.widen(st, d)             # on the copy stream, straight after the bytes have landed
+                else:
+                    d.copy_(h, non_blocking=True)
             self.landed[slot].record(self.copy_stream)
         cur.wait_event(self.landed[slot])
         if self.before_step is not None:

@@ -27,7 +27,7 @@ EXPORTS = [
     "alan_b200_program_launches", "alan_b200_run", "alan_b200_profile", "alan_b200_logpq_fwd", "alan_b200_logpq_bwd",
     "alan_b200_resample", "alan_b200_gather", "alan_b200_lse_eps", "alan_b200_chain_scratch_elems",
     "alan_b200_logmmexp_chain", "alan_b200_normal_logpdf_bcast", "alan_b200_pipe_peak",
-    "alan_b200_comm_bytes", "alan_b200_plan_set_comm", "alan_b200_qem_update",
+    "alan_b200_comm_bytes", "alan_b200_plan_set_comm", "alan_b200_qem_update", "alan_b200_widen_u8",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
     L.alan_b200_logmmexp_chain.argtypes = [vp, vp, vp, i64, i64, i64, i32, vp]
     L.alan_b200_normal_logpdf_bcast.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, i32, vp]
     L.alan_b200_qem_update.argtypes = [i32, i64, ctypes.c_double, vp, vp, vp, vp, vp, vp, i32, vp]
+    L.alan_b200_widen_u8.argtypes = [vp, vp, i64, i32, vp]
     L.alan_b200_pipe_peak.argtypes = [i32, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_double), vp]
     _lib = L
     return L
@@ -287,6 +288,23 @@ def qem_update(family: str, lr: float, new, means, params):
     with torch.cuda.device(x0.device):
         check(lib().alan_b200_qem_update(QEM_FAMILY[family], x0.numel(), float(lr), ptr(new, 0), ptr(new, 1), ptr(means, 0),
                                          ptr(means, 1), ptr(params, 0), ptr(params, 1), _dt(x0), _stream(x0.device)))
+
+
+NARROW_DTYPES = (torch.uint8, torch.bool)
+
+
+def widen(src: torch.Tensor, dst: torch.Tensor = None, dtype=torch.float32) -> torch.Tensor:
+    """uint8 / bool device tensor -> working dtype (alan_b200_widen_u8); `dst` may be a preallocated buffer."""
+    require_cuda()
+    if src.dtype not in NARROW_DTYPES or not src.is_cuda or not src.is_contiguous():
+        raise Exception("widen: source must be a contiguous uint8 / bool device tensor")
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=dtype, device=src.device)
+    if dst.numel() != src.numel() or not dst.is_contiguous() or dst.device != src.device:
+        raise Exception("widen: destination must be a contiguous tensor of the same size on the same device")
+    with torch.cuda.device(src.device):
+        check(lib().alan_b200_widen_u8(src.data_ptr(), dst.data_ptr(), src.numel(), _dt(dst), _stream(src.device)))
+    return dst
 
 
 def gather(x: torch.Tensor, idx: torch.Tensor, outer: int, K: int, inner: int) -> torch.Tensor:

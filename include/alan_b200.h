@@ -114,6 +114,13 @@ int alan_b200_gather(const void* x, const int64_t* idx, void* out, int elem_byte
                      int64_t N, int64_t outer, int64_t K, int64_t inner, int64_t outer_div,
                      void* stream);
 
+/* Byte-typed inputs: dst[i] = (working dtype) src[i] for n uint8 / bool elements (both pointers 16-byte aligned).
+ * Binary features, 0/1 observations and small counts cross PCIe as bytes (a quarter of the fp32 traffic) and are widened
+ * on the device; the values are exact in either type.
+ * replaces: the float copies of the binary covariates / observations that the reference loads and moves to the
+ * device (examples/models/movielens/movielens.py:11-22, `prob.to(device)` at :98).  dtype: 0 = f32, 1 = f64. */
+int alan_b200_widen_u8(const void* src, void* dst, int64_t n, int dtype, void* stream);
+
 /* QEM parameter update of ONE latent variable, elementwise and in place:
  *     mean_s  <- mean_s * (1 - lr) + lr * new_s            (s = 0, 1: the family's sufficient statistics)
  *     params  <- mean2conv(mean_0, mean_1)                  (conventional parameters of the family)

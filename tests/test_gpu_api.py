@@ -285,3 +285,60 @@ def test_pipelined_runner_matches_single_steps():
         assert t.equal(lw, lg)
         for n in gw:
             assert t.equal(gw[n], gg[n]), n
+
+
+@pytest.mark.parametrize("dt", [t.float32, t.float64])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 4099, 1 << 20])
+def test_widen_u8_bit_exact(n, dt):
+    """alan_b200_widen_u8 (byte-typed inputs widened on the device) against torch's own cast, ragged tails included."""
+    from alan_b200 import runtime
+    src = t.randint(0, 256, (n,), dtype=t.uint8, generator=t.Generator().manual_seed(n)).cuda()
+    assert t.equal(runtime.widen(src, dtype=dt).cpu(), src.cpu().to(dt))
+    b = (src > 127)
+    assert t.equal(runtime.widen(b, dtype=dt).cpu(), b.cpu().to(dt))
+    with pytest.raises(Exception, match="uint8"):
+        runtime.widen(src.float())
+
+
+def test_byte_typed_inputs_match_float_inputs():
+    """Binary covariates / 0-1 observations handed over as uint8 (PipelinedRunner.pin keeps them one byte per element,
+    the device widens them) give bit for bit what the float copies give, through the pipelined entry point and through
+    the Problem API."""
+    from alan_b200.engine import Compiled, PipelinedRunner
+    from alan_b200.problem import Problem
+    P, Q = models.build('cfg2_movielens', M, t.float32)
+    inp = models.movielens_inputs(M=64, N=5, dtype=t.float32)
+    nt = lambda d: {k: from_torch_named(v) if any(n is not None for n in v.names) else NT(v, ()) for k, v in d.items()}
+    ip, data = {**nt(inp['inputs']), **nt(inp['params'])}, nt(inp['data'])
+    assert set(ip['x'].t.unique().tolist()) <= {0.0, 1.0} and set(data['obs'].t.unique().tolist()) <= {0.0, 1.0}
+    ip8 = dict(ip, x=NT(ip['x'].t.to(t.uint8), ip['x'].axes))
+    data8 = dict(data, obs=NT(data['obs'].t.to(t.bool), data['obs'].axes))
+    K, d = 8, 18
+    g = t.Generator().manual_seed(5)
+    smp = {'mu_z': NT(0.6 * t.randn(K, d, generator=g), ('K_mu_z',)), 'psi_z': NT(0.3 * t.randn(K, d, generator=g), ('K_psi_z',)),
+           'z': NT(0.6 * t.randn(64, K, d, generator=g), ('plate_1', 'K_z'))}
+    comp = Compiled(P, Q, smp, ip, data, grad_names=list(inp['params']))
+    pipe = PipelinedRunner(comp, 'cuda:0')
+    hf, h8 = pipe.pin(smp, ip, data), pipe.pin(smp, ip8, data8)
+    assert sum(x.numel() * x.element_size() for x in h8) < sum(x.numel() * x.element_size() for x in hf)
+    assert {x.dtype for x in h8} == {t.float32, t.uint8, t.bool}
+    res = []
+    for h in (hf, h8, h8, hf, h8):
+        lp, gr = pipe.result(pipe.submit(h))
+        res.append((lp.clone(), {n: v.clone() for n, v in gr.items()}))
+    for lp, gr in res[1:]:
+        assert t.equal(lp, res[0][0])
+        for n in gr:
+            assert t.equal(gr[n], res[0][1][n]), n
+    # the Problem API: uint8 inputs / data are moved as bytes and widened by the library's kernel
+    names = list(inp['params'])
+    out = []
+    for i_, d_ in ((ip, data), (ip8, data8)):
+        par = {k: NT(i_[k].t.clone().requires_grad_(True), i_[k].axes) for k in names}
+        prob = Problem(P, Q, d_, inputs={k: v for k, v in i_.items() if k not in names}, params=par, device='cuda:0')
+        L = prob.sample_from(smp).elbo_rws()
+        L.backward()
+        out.append((L.detach().cpu(), {k: par[k].t.grad.clone() for k in names}))
+    assert t.equal(out[0][0], out[1][0])
+    for k in names:
+        assert t.equal(out[0][1][k], out[1][1][k]), k
