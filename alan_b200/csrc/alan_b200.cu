@@ -794,6 +794,12 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c0, bool 
                 read_opnd(r, c, p.a, p.d.nd, false); p.a_ev = r.i64v();
                 read_opnd(r, c, p.b, p.d.nd, false); p.b_ev = r.i64v();
                 read_opnd(r, c, p.y, p.d.nd, false);
+                p.side = r.i32();
+                if (p.side) {
+                    p.qout = (T*)tref(r, c);
+                    read_opnd(r, c, p.ql, p.d.nd, false); p.ql_ev = r.i64v();
+                    read_opnd(r, c, p.qs, p.d.nd, false); p.qs_ev = r.i64v();
+                }
                 if (launch_bern_dot<T>(p, D, c.stream, c.sm_count)) return fail("bern_dot_sum: unsupported event extent");
                 break;
             }

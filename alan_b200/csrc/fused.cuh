@@ -404,6 +404,12 @@ struct BernDotParams {
     T* out;
     i64 n_out, n_red;
     int vec2;               // a / b rows are contiguous and 2-element aligned
+    // side output (plan.py Planner.fuse_side_factors): qout[o] = sum_d log N(a[o, d]; ql[o, d], qs[o, d]) -- a Gaussian
+    // factor of the same rows (logQ(z) of a mean-field Q), evaluated from the registers that hold a[o, :] anyway
+    int side;
+    Opnd ql, qs;
+    i64 ql_ev, qs_ev;
+    T* qout;
 };
 
 // log Bernoulli(y; logits = x) = y x - softplus(x) = -(1 - y) x + min(x, 0) - log1p(exp(-|x|)).  fp32: the
@@ -436,6 +442,15 @@ __global__ void __launch_bounds__(256) bern_dot_sum_kernel(const __grid_constant
 #pragma unroll
             for (int dd = 0; dd < D; ++dd) ar[dd] = A[ab + dd * p.a_ev];
         }
+        if (p.side) {
+            const T* L = (const T*)p.ql.ptr;
+            const T* S = (const T*)p.qs.ptr;
+            const i64 lb = dot_stride(p.ql, idx, 0, p.d.n_a), sb = dot_stride(p.qs, idx, 0, p.d.n_a);
+            T q = T(0);
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) q += normal_lp(ar[dd], L[lb + dd * p.ql_ev], S[sb + dd * p.qs_ev]);
+            p.qout[o] = q;
+        }
         T acc = T(0);
         for (i64 n = 0; n < p.n_red; ++n) {
             i64 bo = bb, yo = yb;
@@ -465,7 +480,10 @@ __global__ void __launch_bounds__(256) bern_dot_sum_kernel(const __grid_constant
 // are contiguous, and an innermost kept dim (the K axis of the sample) that neither b nor y carries.  A CTA takes UPC
 // users at a time: their b blocks are read from HBM ONCE with coalesced loads (the thread-per-output kernel above
 // re-reads every 8-byte piece through the LSU from all K threads of a user: LSU-bound at ~12 % of the HBM roofline on
-// B200), padded to 16-byte rows in shared memory, and thread (user, k) walks them with broadcast LDS.128.
+// B200), padded to 16-byte rows in shared memory, and every thread walks them with broadcast LDS.128.  A thread owns
+// KPT consecutive k of one user.  KPT = 2 halves the shared-memory reads per cell but was measured SLOWER at cfg-5
+// (62 us against 45: three resident CTAs instead of five; ncu shows the kernel issue- and latency-bound, 58 % issue
+// utilisation with 7 of 16 warp slots filled, not LDS-bound), so it is opt-in (ALAN_B200_BDS_KPT=2).
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -474,46 +492,60 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
 
 #define BDS_THREADS 256
 #define BDS_SMEM_BYTES (40 * 1024)
-template <typename T, int D>
+#define BDS_SMEM_BYTES2 (72 * 1024)
+#define BDS_MAX_UPC 32
+template <typename T, int D, int KPT>
 __global__ void __launch_bounds__(BDS_THREADS) bern_dot_sum_smem_kernel(const __grid_constant__ BernDotParams<T> p, int Kin, int UPC, int NCH) {
     constexpr int DP = (D + 3) & ~3;                                   // row pitch (elements): 16-byte rows for float
     extern __shared__ __align__(16) unsigned char bds_smem[];
     T* xs = reinterpret_cast<T*>(bds_smem);                            // [UPC][NCH][DP]
     T* ys = xs + (size_t)UPC * NCH * DP;                               // [UPC][NCH]
+    T* ql_s = ys + (size_t)UPC * NCH;                                  // [UPC][DP]   side factor: loc
+    T* qi_s = ql_s + (size_t)UPC * DP;                                 // [UPC][DP]   1 / scale
+    T* qc_s = qi_s + (size_t)UPC * DP;                                 // [UPC]       -(sum log scale) - D/2 log 2 pi
     const T* A = (const T*)p.a.ptr;
     const T* B = (const T*)p.b.ptr;
     const T* Y = (const T*)p.y.ptr;
-    const int ka = p.d.n_a - 1;                                        // innermost kept dim
     const i64 n_users = p.n_out / Kin;
     const int N = (int)p.n_red;
     const i64 bn = p.b.stride[p.d.n_a], yn = p.y.stride[p.d.n_a];
-    const int tu = threadIdx.x / Kin, tk = threadIdx.x - tu * Kin;     // (user slot, k) of this thread
+    const int TPU = (Kin + KPT - 1) / KPT;                             // threads per user
+    const int tu = threadIdx.x / TPU, tk = (threadIdx.x - tu * TPU) * KPT;   // (user slot, first k) of this thread
     const bool worker = tu < UPC;
     int idx[AB_MAXD];
-    __shared__ i64 s_bb[BDS_THREADS / 8], s_yb[BDS_THREADS / 8];      // per user slot: base offsets of its b block / y row
+    __shared__ i64 s_bb[BDS_MAX_UPC], s_yb[BDS_MAX_UPC], s_lb[BDS_MAX_UPC], s_sb[BDS_MAX_UPC];   // per user slot: base offsets
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (i64 u0 = (i64)blockIdx.x * UPC; u0 < n_users; u0 += (i64)gridDim.x * UPC) {
         const i64 u = u0 + tu;
         const bool live = worker && u < n_users;
-        T ar[D];
-        if (live) {
-            unravel(u * Kin + tk, p.d, 0, p.d.n_a, idx);
-            const i64 ab = dot_stride(p.a, idx, 0, p.d.n_a);
+        T ar[KPT][D];
 #pragma unroll
-            for (int dd = 0; dd < D; ++dd) ar[dd] = A[ab + dd * p.a_ev];
+        for (int j = 0; j < KPT; ++j) {
+            if (live && tk + j < Kin) {
+                unravel(u * Kin + tk + j, p.d, 0, p.d.n_a, idx);
+                const i64 ab = dot_stride(p.a, idx, 0, p.d.n_a);
+#pragma unroll
+                for (int dd = 0; dd < D; ++dd) ar[j][dd] = A[ab + dd * p.a_ev];
+            } else {
+#pragma unroll
+                for (int dd = 0; dd < D; ++dd) ar[j][dd] = T(0);
+            }
         }
         __syncthreads();                                               // the previous users have been consumed
         if (threadIdx.x < UPC) {
             const i64 uu = u0 + threadIdx.x;
-            i64 bb = -1, yb = -1;
+            i64 bb = -1, yb = -1, lb = 0, sb = 0;
             if (uu < n_users) {
                 unravel(uu * Kin, p.d, 0, p.d.n_a, idx);
                 bb = dot_stride(p.b, idx, 0, p.d.n_a);
                 yb = dot_stride(p.y, idx, 0, p.d.n_a);
+                if (p.side) { lb = dot_stride(p.ql, idx, 0, p.d.n_a); sb = dot_stride(p.qs, idx, 0, p.d.n_a); }
             }
-            s_bb[threadIdx.x] = bb; s_yb[threadIdx.x] = yb;
+            s_bb[threadIdx.x] = bb; s_yb[threadIdx.x] = yb; s_lb[threadIdx.x] = lb; s_sb[threadIdx.x] = sb;
         }
-        T acc0 = T(0), acc1 = T(0);
+        T acc0[KPT], acc1[KPT];
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) acc0[j] = acc1[j] = T(0);
         for (int n0 = 0; n0 < N; n0 += NCH) {
             const int nc = min(NCH, N - n0);
             __syncthreads();                                           // offsets visible; the previous chunk has been consumed
@@ -537,6 +569,22 @@ __global__ void __launch_bounds__(BDS_THREADS) bern_dot_sum_smem_kernel(const __
                     }
                 }
                 for (int n = lane; n < nc; n += 32) ys[us * NCH + n] = Y[yb + (i64)(n0 + n) * yn];
+                if (p.side && n0 == 0) {
+                    // the user's loc, 1 / scale and log-normaliser, once per user (not once per (user, k, d))
+                    const T* L = (const T*)p.ql.ptr;
+                    const T* S = (const T*)p.qs.ptr;
+                    const i64 lb = s_lb[us], sb = s_sb[us];
+                    T ls = T(0);
+                    for (int dd = lane; dd < D; dd += 32) {
+                        const T sv = S[sb + dd * p.qs_ev];
+                        ql_s[us * DP + dd] = L[lb + dd * p.ql_ev];
+                        qi_s[us * DP + dd] = T(1) / sv;
+                        ls += ab_log(sv);
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
+                    if (lane == 0) qc_s[us] = -ls - T(D) * T(HALF_LOG_2PI);
+                }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();
@@ -555,24 +603,50 @@ __global__ void __launch_bounds__(BDS_THREADS) bern_dot_sum_smem_kernel(const __
 #pragma unroll
                         for (int dd = 0; dd < D; ++dd) row[dd] = xr[(size_t)n * DP + dd];
                     }
-                    // packed pairs (FFMA2 in fp32): half the FMA issue slots, two independent chains
+                    const T yv = yr[n];
+                    // packed pairs (FFMA2 in fp32): half the FMA issue slots, two independent chains per k
                     typedef typename Pair2<T>::type P2;
-                    P2 l2 = mk2(T(0), T(0)), l3 = mk2(T(0), T(0));
 #pragma unroll
-                    for (int dd = 0; dd + 1 < D; dd += 2) {
-                        if ((dd >> 1) & 1) l3 = fma2(mk2(ar[dd], ar[dd + 1]), mk2(row[dd], row[dd + 1]), l3);
-                        else l2 = fma2(mk2(ar[dd], ar[dd + 1]), mk2(row[dd], row[dd + 1]), l2);
+                    for (int j = 0; j < KPT; ++j) {
+                        P2 l2 = mk2(T(0), T(0)), l3 = mk2(T(0), T(0));
+#pragma unroll
+                        for (int dd = 0; dd + 1 < D; dd += 2) {
+                            if ((dd >> 1) & 1) l3 = fma2(mk2(ar[j][dd], ar[j][dd + 1]), mk2(row[dd], row[dd + 1]), l3);
+                            else l2 = fma2(mk2(ar[j][dd], ar[j][dd + 1]), mk2(row[dd], row[dd + 1]), l2);
+                        }
+                        T l0 = (l2.x + l3.x), l1 = (l2.y + l3.y);
+                        if (D & 1) l0 += ar[j][D - 1] * row[D - 1];
+                        const T lp = bern_logits_fast(yv, l0 + l1);
+                        if ((n0 + n) & 1) acc1[j] += lp; else acc0[j] += lp;      // by the row's own parity: the order does not depend on NCH
                     }
-                    T l0 = (l2.x + l3.x), l1 = (l2.y + l3.y);
-                    if (D & 1) l0 += ar[D - 1] * row[D - 1];
-                    const T lp = bern_logits_fast(yr[n], l0 + l1);
-                    if (n & 1) acc1 += lp; else acc0 += lp;
                 }
             }
         }
-        if (live) p.out[u * Kin + tk] = (acc0 + acc1) + p.cadd;
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) {
+                if (tk + j >= Kin) continue;
+                p.out[u * Kin + tk + j] = (acc0[j] + acc1[j]) + p.cadd;
+                if (p.side) {
+                    T q0 = T(0), q1 = T(0);
+#pragma unroll
+                    for (int dd = 0; dd < D; ++dd) {
+                        const T tt = (ar[j][dd] - ql_s[tu * DP + dd]) * qi_s[tu * DP + dd];
+                        if (dd & 1) q1 = fma(tt, tt, q1); else q0 = fma(tt, tt, q0);
+                    }
+                    p.qout[u * Kin + tk + j] = qc_s[tu] - T(0.5) * (q0 + q1);
+                }
+            }
+        }
     }
-    (void)ka;
+}
+
+template <typename T, int D, int KPT>
+static void launch_bern_dot_smem(const BernDotParams<T>& p, int Kin, int UPC, int NCH, size_t smem, int blocks, cudaStream_t stream) {
+    static const cudaError_t attr = cudaFuncSetAttribute(bern_dot_sum_smem_kernel<T, D, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         BDS_SMEM_BYTES2 + 8 * 1024);       // once per process and instantiation
+    (void)attr;
+    bern_dot_sum_smem_kernel<T, D, KPT><<<blocks, BDS_THREADS, smem, stream>>>(p, Kin, UPC, NCH);
 }
 
 template <typename T, int D>
@@ -581,25 +655,35 @@ static void launch_bern_dot_D(BernDotParams<T> p, cudaStream_t stream, int sm_co
               ((uintptr_t)p.b.ptr % (2 * sizeof(T)) == 0);
     for (int k = 0; k < p.d.nd && v2; ++k) v2 = (p.a.stride[k] % 2 == 0) && (p.b.stride[k] % 2 == 0);
     p.vec2 = v2 ? 1 : 0;
-    // staged variant: one summed dim with contiguous b rows, innermost kept dim absent from b and y, out contiguous
+    // staged variant: one summed dim with contiguous b rows, innermost kept dim absent from b and y (and from the side
+    // factor's loc / scale), out contiguous
     const int nred = p.d.nd - p.d.n_a, ka = p.d.n_a - 1;
     if (nred == 1 && p.d.n_a >= 1 && p.b_ev == 1 && p.b.stride[p.d.n_a] == D && p.b.stride[ka] == 0 && p.y.stride[ka] == 0 &&
+        (!p.side || (p.ql.stride[ka] == 0 && p.qs.stride[ka] == 0)) &&
         p.d.size[ka] <= BDS_THREADS && p.d.size[ka] >= 8 && p.n_red >= 2 && p.n_out / p.d.size[ka] >= 64) {
         constexpr int DP = (D + 3) & ~3;
         const int Kin = p.d.size[ka];
-        const int UPC = BDS_THREADS / Kin;
+        const char* e_kpt = getenv("ALAN_B200_BDS_KPT");                 // tuning aids
+        const char* e_cap = getenv("ALAN_B200_BDS_CAP");
+        const char* e_smem = getenv("ALAN_B200_BDS_SMEM_KB");
+        const int KPT = (Kin >= 16 && sizeof(T) == 4 && e_kpt && atoi(e_kpt) == 2) ? 2 : 1;
+        const int TPU = (Kin + KPT - 1) / KPT;
+        const int UPC = BDS_THREADS / TPU;
         // 64-bit staging loads: even D, b block bases and the step between summed rows 2-element aligned
         bool sv2 = (D % 2 == 0) && ((uintptr_t)p.b.ptr % (2 * sizeof(T)) == 0);
         for (int k = 0; k < p.d.nd && sv2; ++k) sv2 = (p.b.stride[k] % 2 == 0);
         p.vec2 = sv2 ? 1 : 0;
-        int NCH = (int)(BDS_SMEM_BYTES / ((size_t)UPC * (DP + 1) * sizeof(T)));
+        const size_t side_bytes = (size_t)UPC * (2 * DP + 1) * sizeof(T);
+        const size_t budget = e_smem ? (size_t)atoi(e_smem) * 1024 : (KPT == 2 ? BDS_SMEM_BYTES2 : BDS_SMEM_BYTES);
+        int NCH = (int)(budget / ((size_t)UPC * (DP + 1) * sizeof(T)));
         if (NCH > p.n_red) NCH = (int)p.n_red;
-        if (NCH >= 2) {
-            const size_t smem = (size_t)UPC * NCH * (DP + 1) * sizeof(T);
+        if (NCH >= 2 && UPC <= BDS_MAX_UPC) {
+            const size_t smem = (size_t)UPC * NCH * (DP + 1) * sizeof(T) + side_bytes;
             const i64 n_users = p.n_out / Kin;
-            i64 blocks = (n_users + UPC - 1) / UPC, cap = (i64)sm_count * 5;
-            if (blocks > cap) blocks = cap;
-            bern_dot_sum_smem_kernel<T, D><<<(int)blocks, BDS_THREADS, smem, stream>>>(p, Kin, UPC, NCH);
+            i64 blocks = (n_users + UPC - 1) / UPC, cap = (i64)sm_count * (e_cap ? atoi(e_cap) : (KPT == 2 ? 3 : 5));
+            if (blocks > cap) blocks = cap;             // (equal trip counts per CTA measured slower: 50 us against 45 at cfg-5)
+            if (KPT == 2) launch_bern_dot_smem<T, D, 2>(p, Kin, UPC, NCH, smem, (int)blocks, stream);
+            else launch_bern_dot_smem<T, D, 1>(p, Kin, UPC, NCH, smem, (int)blocks, stream);
             return;
         }
     }

@@ -39,8 +39,7 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
                  :: "r"(tc::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
 }
 
-#define NQB_THREADS 256
-template <typename T, int D>
+template <typename T, int D, int NQB_THREADS>
 __global__ void __launch_bounds__(NQB_THREADS) normal_q_bwd_kernel(const __grid_constant__ NormalQBwdParams<T> p, int UPB, int bulk) {
     extern __shared__ __align__(128) unsigned char nqb_smem[];
     const int Kk = p.Kk, row = Kk * D, KP = Kk | 1;
@@ -119,9 +118,9 @@ __global__ void __launch_bounds__(NQB_THREADS) normal_q_bwd_kernel(const __grid_
     }
 }
 
-template <typename T, int D>
-static int launch_normal_q_bwd_D(const NormalQBwdParams<T>& p, cudaStream_t stream, int sm_count) {
-    int UPB = NQB_THREADS / D;
+template <typename T, int D, int NT>
+static int launch_normal_q_bwd_DT(const NormalQBwdParams<T>& p, cudaStream_t stream, int sm_count) {
+    int UPB = NT / D;
     if (UPB < 1) return 1;
     const size_t row = (size_t)p.Kk * D;
     const size_t per_user = (2 * row + (size_t)(p.Kk | 1)) * sizeof(T);
@@ -134,15 +133,30 @@ static int launch_normal_q_bwd_D(const NormalQBwdParams<T>& p, cudaStream_t stre
         i64 expect = (i64)row;
         for (int k = p.ud.nd - 1; k >= 0 && bulk; --k) { bulk = p.vstride[k] == expect; expect *= p.ud.size[k]; }
     }
+    if (bulk && ((size_t)UPB * row * sizeof(T)) % 16 != 0) bulk = false;              // every tile start stays 16-byte aligned
     const i64 tiles = (p.n_users + UPB - 1) / UPB;
+    // resident CTAs per SM: bounded by shared memory (227 KB) and by 2048 threads; every CTA gets the same trip count
+    i64 per_sm = (i64)((220 * 1024) / (smem + 1024));
+    if (per_sm > 2048 / NT) per_sm = 2048 / NT;
+    if (per_sm < 1) per_sm = 1;
+    const i64 cap = (i64)sm_count * per_sm;
     i64 blocks = tiles;
-    const i64 cap = (i64)sm_count * (smem > 100 * 1024 ? 1 : 2);
-    if (blocks > cap) blocks = cap;
+    if (blocks > cap) { const i64 trips = (tiles + cap - 1) / cap; blocks = (tiles + trips - 1) / trips; }
     if (blocks < 1) blocks = 1;
-    static const cudaError_t attr = cudaFuncSetAttribute(normal_q_bwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    static const cudaError_t attr = cudaFuncSetAttribute(normal_q_bwd_kernel<T, D, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     (void)attr;
-    normal_q_bwd_kernel<T, D><<<(int)blocks, NQB_THREADS, smem, stream>>>(p, UPB, bulk ? 1 : 0);
+    normal_q_bwd_kernel<T, D, NT><<<(int)blocks, NT, smem, stream>>>(p, UPB, bulk ? 1 : 0);
     return 0;
+}
+
+template <typename T, int D>
+static int launch_normal_q_bwd_D(const NormalQBwdParams<T>& p, cudaStream_t stream, int sm_count) {
+    // smaller CTAs = more tiles in flight per SM at different phases (copy / wait / arithmetic / store) when there are
+    // enough users to fill them; ALAN_B200_NQB_THREADS overrides (tuning aid)
+    const char* e = getenv("ALAN_B200_NQB_THREADS");
+    const int nt = e ? atoi(e) : 256;
+    if (nt == 128 && D <= 64) return launch_normal_q_bwd_DT<T, D, 128>(p, stream, sm_count);
+    return launch_normal_q_bwd_DT<T, D, 256>(p, stream, sm_count);
 }
 
 template <typename T>

@@ -805,20 +805,30 @@ class BernDotSumOp(Op):
     def __init__(self, out, od, rd, D, a, b, y, cadd, gen_ops, tag=''):
         self.out, self.od, self.rd, self.D, self.a, self.b, self.y = out, od, rd, D, a, b, y
         self.cadd, self.gen_ops, self.tag = cadd, gen_ops, tag
+        # (ExprOp E, loc leaf, scale leaf): `E.out[od] = sum_e log N(a; loc, scale)`, a Gaussian factor of the SAME rows
+        # `a` that the kernel holds in registers anyway, written as a second output (Planner.fuse_side_factors)
+        self.side = None
 
     def payload(self, w):
         w.tref(self.out); w.f64(self.cadd); w.i32(self.D)
         dims = self.od + self.rd
-        strides = [[lf.stride(d) for d in dims] for lf in (self.a, self.b, self.y)]
+        leaves = [self.a, self.b, self.y] + ([self.side[1], self.side[2]] if self.side is not None else [])
+        strides = [[lf.stride(d) for d in dims] for lf in leaves]
         sizes, n_a, strides, _ = _coalesce([d[2] for d in dims], len(self.od), strides)
         _write_dims(w, sizes, n_a)
         ev = ('ev', 0, self.D)
-        for lf, st, has_ev in zip((self.a, self.b, self.y), strides, (True, True, False)):
+
+        def opnd(lf, st, has_ev):
             w.tref(lf.pt)
             for x in st:
                 w.i64(x)
             if has_ev:
                 w.i64(lf.stride(ev))
+        opnd(self.a, strides[0], True); opnd(self.b, strides[1], True); opnd(self.y, strides[2], False)
+        w.i32(0 if self.side is None else 1)
+        if self.side is not None:
+            w.tref(self.side[0].out)
+            opnd(self.side[1], strides[3], True); opnd(self.side[2], strides[4], True)
 
 
 class NormalPolySumOp(Op):
@@ -1139,7 +1149,7 @@ class Planner:
             q = [op.qterm[1].pt, op.qterm[2].pt] if op.qterm is not None else []
             return [lf.pt for lf, _ in op.bfactors] + [op.v.pt, op.l.pt, op.s.pt] + q
         if isinstance(op, BernDotSumOp):
-            return [op.a.pt, op.b.pt, op.y.pt]
+            return [op.a.pt, op.b.pt, op.y.pt] + ([op.side[1].pt, op.side[2].pt] if op.side is not None else [])
         if isinstance(op, NormalPolySumOp):
             return [lf.pt for lf in op.zleaves + op.kleaves]
         if isinstance(op, DotOp):
@@ -1939,6 +1949,39 @@ class Planner:
         self.fwd.remove(Dt)
         return BernDotSumOp(out, od, rd, D, a, b, y, lf.const * n, [Dt, E, R], tag='bern_dot_sum:' + E.tag)
 
+    def fuse_side_factors(self):
+        """Run after the adjoint programs have been derived (they see the unfused ops).  The Bernoulli-dot-sum kernel
+        keeps every row a[o, :] (the sample z[u, k, :] at cfg-2 / cfg-5) in registers.  A Gaussian factor of the same
+        rows with per-row-group loc and scale, `E.out[o] = sum_e log N(a[o, e]; loc, scale)` -- the mean-field Q factor
+        logQ(z) -- becomes a second output of that kernel: its own pass over `a` disappears from the forward program
+        (cfg-5: 23 us and 21.6 MB of reads).  E stays the op the adjoint was derived from."""
+        for seg in self.plan.programs[:self.plan.n_fwd]:
+            for B in [o for o in seg if isinstance(o, BernDotSumOp) and o.side is None]:
+                ev = ('ev', 0, B.D)
+                for E in [o for o in seg if isinstance(o, ExprOp)]:
+                    parts = self._normal3_parts(E)
+                    if parts is None or (E.red[0][2] if E.red else 1) != B.D or E.out.space != 'ws':
+                        continue
+                    v, l, sc = parts
+                    keyset = lambda ds: set((d[0], d[1]) for d in ds)
+                    if v.pt is not B.a.pt or keyset(E.keep) != keyset(B.od):
+                        continue
+                    if [v.stride(d) for d in B.od + [ev]] != [B.a.stride(d) for d in B.od + [ev]]:
+                        continue
+                    if [plain(E.out).stride(d) for d in B.od] != [plain(B.out).stride(d) for d in B.od]:
+                        continue
+                    if B.D > 1 and (l.stride(ev) == 0 or sc.stride(ev) == 0):
+                        continue
+                    iB, iE = seg.index(B), seg.index(E)
+                    lo, hi = min(iB, iE), max(iB, iE)
+                    first = seg[lo]
+                    if any(first.out.id in (x.id for x in self.op_inputs(o)) for o in seg[lo + 1:hi]):
+                        continue                    # somebody between the two reads the earlier one's output
+                    B.side = (E, l, sc)
+                    seg[hi] = B
+                    del seg[lo]
+                    break
+
     def chain(self, lf: LogicalFactor, T_axis, Kinit, Kts):
         """logpq.py:131-143: order to [T, Kprev, Kcurr] (other axes batch), chain_logmmexp, logsumexp."""
         outer = tuple(a for a in lf.axes if a not in (T_axis, Kinit, Kts))
@@ -1988,6 +2031,8 @@ class Planner:
         plan.programs = list(self.fwd_segments)
         plan.n_fwd = len(self.fwd_segments)
         bwd_segments = self.build_backward(grad_names)
+        if self.fast_paths and os.environ.get("ALAN_B200_NO_SIDE") != "1":       # read when the plan is BUILT
+            self.fuse_side_factors()
         plan.programs += bwd_segments
         plan.n_bwd = len(bwd_segments)
         if with_sample:

@@ -363,6 +363,8 @@ class Emu:
     def op_BernDotSumOp(self, op):
         for g in op.gen_ops:
             getattr(self, 'op_' + type(g).__name__)(g)
+        if op.side is not None:            # the Gaussian factor of the same rows, a second output of the fused kernel
+            self.op_ExprOp(op.side[0])
 
     def op_NormalPolySumOp(self, op):
         """the fused formula of csrc/normal_poly.cuh evaluated from the op's polynomial (not from the ops it replaced)"""

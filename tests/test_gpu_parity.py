@@ -469,7 +469,9 @@ def test_inline_q_factor_in_dense_kernel(M_, N_, K, d, monkeypatch):
         fan = [op for prog in comp.plan.programs for op in prog if type(op).__name__ == 'FanLseOp'][0]
         assert (fan.qterm is not None) == fuse
         tags = [getattr(op, 'tag', '') for op in comp.plan.programs[0]]
-        assert ('logQ:z' in tags) == (not fuse)
+        # by default the factor is its own pass or the second output of bern_dot_sum (Planner.fuse_side_factors)
+        own = 'logQ:z' in tags or any(getattr(op, 'side', None) is not None for op in comp.plan.programs[0])
+        assert own == (not fuse)
         assert 'NormalQBwdOp' in [type(op).__name__ for op in comp.plan.programs[1]]
         run = Runner(comp, "cuda:0")
         tensors = run.device_inputs(sample, ip, data)
@@ -797,3 +799,62 @@ def test_density_families_vs_oracle(family, dtype):
             assert float(grads[k].abs().max()) == 0.0, k
             continue
         assert rel_err(grads[k].cpu().reshape(rr.shape), rr) < 50 * tl, k
+
+
+@pytest.mark.parametrize("dtype", [t.float32, t.float64])
+@pytest.mark.parametrize("M_,N_,K", [(64, 5, 30), (300, 5, 30), (130, 50, 17), (70, 9, 8), (33, 7, 17)])
+def test_bern_dot_sum_side_factor_and_k_pairs(dtype, M_, N_, K, monkeypatch):
+    """bern_dot_sum with the mean-field Q factor logQ(z) as a second output (Planner.fuse_side_factors) and two k per
+    thread, against the same plan with the factor as its own pass (ALAN_B200_NO_SIDE=1 when the plan is built) and one k
+    per thread (default; two with ALAN_B200_BDS_KPT=2), and against the oracle.  The Bernoulli sums keep their summation order, so lp
+    and every gradient differ only through the Q factor's rounding; ragged K (17: the last thread of a user owns one
+    k), user counts that leave partial CTAs, and shapes the staged kernel refuses (M=33 < 64 users: thread-per-output
+    kernel with the side factor)."""
+    from oracle import logpq_oracle as O
+    Compiled, Runner = _engine()
+    from alan_b200.plan import BernDotSumOp
+    P, Q = models.movielens_model(M)
+    inp = models.movielens_inputs(M=M_, N=N_, d=18, seed=5, dtype=dtype)
+    inp['event_shapes'] = {'mu_z': (18,), 'psi_z': (18,), 'z': (18,)}
+    sample = _random_sample(P, Q, inp, K, dtype, 12)
+    ip = {**_nt(inp['inputs']), **_nt(inp['params'])}
+    data = _nt(inp['data'])
+    names = list(inp['params'])
+    res = {}
+    fusable = None
+    for mode in ("noside", "side", "kpt2"):
+        monkeypatch.delenv("ALAN_B200_NO_SIDE", raising=False)
+        monkeypatch.delenv("ALAN_B200_BDS_KPT", raising=False)
+        if mode == "noside":
+            monkeypatch.setenv("ALAN_B200_NO_SIDE", "1")
+        if mode == "kpt2":
+            monkeypatch.setenv("ALAN_B200_BDS_KPT", "2")
+        comp = Compiled(P, Q, sample, ip, data, grad_names=names)
+        bds = [op for op in comp.plan.programs[0] if isinstance(op, BernDotSumOp)]
+        tags = [getattr(op, 'tag', '') for op in comp.plan.programs[0]]
+        if mode == "noside":
+            # the factor is fused when it is exactly `three loads + Normal` (the exp of a log-scale hoisted into its own
+            # tensor, as at the K = 30 shapes); an inline exp keeps its own pass
+            E = next(op for op in comp.plan.programs[0] if getattr(op, 'tag', '') == 'logQ:z')
+            fusable = comp.planner._normal3_parts(E) is not None
+            assert fusable or K != 30
+        assert len(bds) == 1 and (bds[0].side is not None) == (mode != "noside" and fusable)
+        assert ('logQ:z' in tags) == (mode == "noside" or not fusable)
+        run = Runner(comp, "cuda:0")
+        tensors = run.device_inputs(sample, ip, data)
+        lp = run.forward_raw(tensors)
+        grads = run.backward_raw(tensors)
+        res[mode] = (lp.cpu(), {k: v.cpu() for k, v in grads.items()}, comp)
+    ipg = {k: NT(v.t.clone().requires_grad_() if k in names else v.t, v.axes) for k, v in ip.items()}
+    ref = O.elbo(P, Q, sample, ipg, data)
+    rg = t.autograd.grad(ref, [ipg[k].t for k in names])
+    tl = 1e-5 if dtype == t.float32 else 1e-10
+    for mode, (lp, grads, comp) in res.items():
+        assert rel_err(lp, ref) < tl, mode
+        for k, r in zip(names, rg):
+            pt = comp.plan.input_pts[k]
+            assert rel_err(_as(pt.axes, grads[k], ipg[k].axes), r) < 30 * tl, (mode, k)
+    # one or two k per thread: the same arithmetic in the same order
+    assert t.equal(res["side"][0], res["kpt2"][0])
+    for k in names:
+        assert t.equal(res["side"][1][k], res["kpt2"][1][k]), k
