@@ -40,6 +40,19 @@ FAMILIES = {
     "Binomial": ("total_count", "probs", "logits"),
     "MultivariateNormal": ("loc", "covariance_matrix", "precision_matrix", "scale_tril"),
     "Dirichlet": ("concentration",),
+    # densities composed from the factor VM's primitive operations (plan.py COMPOSED)
+    "Gumbel": ("loc", "scale"),
+    "Weibull": ("scale", "concentration"),
+    "Pareto": ("scale", "alpha"),
+    "HalfCauchy": ("scale",),
+    "Chi2": ("df",),
+    "Geometric": ("probs", "logits"),
+    "Kumaraswamy": ("concentration1", "concentration0"),
+    "FisherSnedecor": ("df1", "df2"),
+    "RelaxedBernoulli": ("temperature", "probs", "logits"),
+    "OneHotCategorical": ("probs", "logits"),
+    "Categorical": ("probs", "logits"),
+    "Multinomial": ("total_count", "probs", "logits"),
 }
 # arguments that torch.distributions leaves as None unless given
 _OPTIONAL = {"probs", "logits"}
@@ -95,7 +108,12 @@ class Dist:
                 raise Exception(f"{family}: argument {k} given twice")
             bound[k] = v
         bound = {k: v for k, v in bound.items() if v is not None}
-        required = [n for n in names if n not in _OPTIONAL and n not in _MATRIX_ARGS]
+        if family == "Multinomial" and "total_count" in bound:
+            # the reference turns every number into a tensor (dist.py:311-318) and torch then refuses it
+            raise Exception("Multinomial: inhomogeneous total_count is not supported (leave it at its default of 1, "
+                            "as the reference requires)")
+        required = [n for n in names if n not in _OPTIONAL and n not in _MATRIX_ARGS
+                    and not (family == "Multinomial" and n == "total_count")]
         if family == "MultivariateNormal" and sum(n in bound for n in _MATRIX_ARGS) != 1:
             raise Exception("Exactly one of covariance_matrix or precision_matrix or scale_tril may be specified.")
         for n in required:
@@ -157,6 +175,18 @@ NegativeBinomial = _make("NegativeBinomial")
 Binomial = _make("Binomial")
 MultivariateNormal = _make("MultivariateNormal")
 Dirichlet = _make("Dirichlet")
+Gumbel = _make("Gumbel")
+Weibull = _make("Weibull")
+Pareto = _make("Pareto")
+HalfCauchy = _make("HalfCauchy")
+Chi2 = _make("Chi2")
+Geometric = _make("Geometric")
+Kumaraswamy = _make("Kumaraswamy")
+FisherSnedecor = _make("FisherSnedecor")
+RelaxedBernoulli = _make("RelaxedBernoulli")
+OneHotCategorical = _make("OneHotCategorical")
+Categorical = _make("Categorical")
+Multinomial = _make("Multinomial")
 
 
 class Data:

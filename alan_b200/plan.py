@@ -28,7 +28,7 @@ import torch
 
 from .model import Plate, Dist, Data, Timeseries, datagroup, Kname, function_arguments, DISCRETE_ARGS
 from .path import greedy_path
-from .trace import Expr, trace_function, UNARY, BINARY
+from .trace import Expr, Proxy, trace_function, UNARY, BINARY
 
 MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
@@ -55,6 +55,97 @@ DENSITY_ARGS = {
     'Beta': ('concentration1', 'concentration0'), 'Poisson': ('rate',), 'HalfNormal': ('scale',),
     'Uniform': ('low', 'high'), 'StudentT': ('df', 'loc', 'scale'),
 }
+
+
+# Families whose log-density is COMPOSED from the VM's primitive operations (no opcode of their own): each entry is
+# (argument order, function of Proxy operands restating torch.distributions.<family>.log_prob -- the file it follows is
+# named on each -- with the transform chains of TransformedDistribution families written out).  Values outside the
+# support are not masked to -inf (the reference runs with validate_args off and would return the same finite formula).
+def _softplus(x):
+    return Proxy(Expr.make('softplus', x.expr))
+
+
+def _probs_to_logits(p):                         # torch distributions/utils.py probs_to_logits(is_binary=True)
+    return p.log() - (-p).log1p()
+
+
+def _lp_gumbel(x, loc, scale):                   # torch gumbel.py:68-71
+    y = (loc - x) / scale
+    return (y - y.exp()) - scale.log()
+
+
+def _lp_weibull(x, scale, k):                    # weibull.py: Exponential(1) -> PowerTransform(1/k) -> AffineTransform(0, scale)
+    x1 = x / scale
+    x0 = x1.pow(k)
+    return -x0 - ((x1 / x0) / k).abs().log() - scale.abs().log()
+
+
+def _lp_pareto(x, scale, alpha):                 # pareto.py: Exponential(alpha) -> ExpTransform -> AffineTransform(0, scale)
+    x0 = (x / scale).log()
+    return (alpha.log() - alpha * x0) - x0 - scale.abs().log()
+
+
+def _lp_halfcauchy(x, scale):                    # half_cauchy.py:68-75 over cauchy.py:78-84
+    return -math.log(math.pi) - scale.log() - ((x / scale) ** 2).log1p() + math.log(2)
+
+
+def _lp_chi2(x, df):                             # chi2.py: Gamma(0.5 df, 0.5); gamma.py:85-93
+    c = df * 0.5
+    return c * math.log(0.5) + (c - 1.0) * x.log() - x * 0.5 - c.lgamma()
+
+
+def _lp_geometric(x, p):                         # geometric.py:114-121
+    return x * (-p).log1p() + p.log()
+
+
+def _lp_kumaraswamy(x, a, b):                    # kumaraswamy.py: Uniform(0,1) -> Power(1/b) -> Affine(1,-1) -> Power(1/a)
+    return a.log() + b.log() + (a - 1.0) * x.log() + (b - 1.0) * (-(x.pow(a))).log1p()
+
+
+def _lp_fisher_snedecor(x, df1, df2):            # fishersnedecor.py:88-98
+    ct1, ct2, ct3 = df1 * 0.5, df2 * 0.5, df1 / df2
+    t1 = (ct1 + ct2).lgamma() - ct1.lgamma() - ct2.lgamma()
+    t2 = ct1 * ct3.log() + (ct1 - 1.0) * x.log()
+    t3 = (ct1 + ct2) * (ct3 * x).log1p()
+    return t1 + t2 - t3
+
+
+def _lp_logit_relaxed_bernoulli(x, temperature, logits):       # relaxed_bernoulli.py:107-112
+    diff = logits - x * temperature
+    return temperature.log() + diff - 2.0 * diff.exp().log1p()
+
+
+def _lp_relaxed_bernoulli(y, temperature, logits):             # relaxed_bernoulli.py:115-148: ... -> SigmoidTransform
+    x = y.log() - (-y).log1p()
+    return _lp_logit_relaxed_bernoulli(x, temperature, logits) + _softplus(-x) + _softplus(x)
+
+
+def _lp_one_hot_categorical(v, logits):          # one_hot_categorical.py:104-108 over categorical.py:66-67,137-143
+    return (v * logits).sum(-1) - logits.exp().sum(-1).log() * v.sum(-1)
+
+
+def _lp_categorical(v, logits, iota):             # categorical.py:137-143: the class index selects one normalised logit
+    lt = lambda a, b: Proxy(Expr.make('lt', a.expr, b.expr))
+    onehot = 1.0 - lt(iota, v) - lt(v, iota)      # [j == v] for exact integers, over the last positional dim
+    return (onehot * logits).sum(-1) - logits.exp().sum(-1).log()
+
+
+def _lp_multinomial(v, logits):                  # multinomial.py:121-132 (total_count = 1: see model.Dist)
+    norm = logits - logits.exp().sum(-1).log()
+    return (v.sum(-1) + 1.0).lgamma() - (v + 1.0).lgamma().sum(-1) + (norm * v).sum(-1)
+
+
+COMPOSED = {
+    'Gumbel': (('loc', 'scale'), _lp_gumbel), 'Weibull': (('scale', 'concentration'), _lp_weibull),
+    'Pareto': (('scale', 'alpha'), _lp_pareto), 'HalfCauchy': (('scale',), _lp_halfcauchy), 'Chi2': (('df',), _lp_chi2),
+    'Geometric': (('probs',), _lp_geometric), 'Kumaraswamy': (('concentration1', 'concentration0'), _lp_kumaraswamy),
+    'FisherSnedecor': (('df1', 'df2'), _lp_fisher_snedecor),
+    'RelaxedBernoulli': (('temperature', 'logits'), _lp_relaxed_bernoulli),
+    'OneHotCategorical': (('logits',), _lp_one_hot_categorical), 'Multinomial': (('logits',), _lp_multinomial),
+    'Categorical': (('logits',), _lp_categorical),
+}
+# how the missing one of (probs, logits) is obtained from the given one, per family
+_VECTOR_FAMILIES = ('OneHotCategorical', 'Multinomial', 'Categorical')
 
 
 # ----------------------------------------------------------------------------------------
@@ -1237,14 +1328,20 @@ class Planner:
             pt = self.emit_expr(body, nred=0, tag=tag or 'expr')
         return Expr.leaf(pt, pt.axes, pt.pos_shape)
 
-    def _prepare(self, e: Expr, space=None) -> Expr:
-        """Replace inner reductions (and cheap-to-hoist subtrees) by materialised leaves."""
+    def _prepare(self, e: Expr, space=None, memo=None) -> Expr:
+        """Replace inner reductions (and cheap-to-hoist subtrees) by materialised leaves.  Shared subexpressions stay
+        shared (one VM register, one materialised tensor), they are not copied per use."""
         if e.op in ('leaf', 'const'):
             return e
+        memo = {} if memo is None else memo
+        if id(e) in memo:
+            return memo[id(e)][1]
         if e.op == 'sumlast':
-            return self.materialize(e)
-        args = [self._prepare(a, space) for a in e.args]
-        out = Expr(e.op, args, e.axes, e.pos_shape)
+            out = self.materialize(e)
+        else:
+            args = [self._prepare(a, space, memo) for a in e.args]
+            out = Expr(e.op, args, e.axes, e.pos_shape)
+        memo[id(e)] = (e, out)               # keeps `e` alive: ids are not reused while the memo exists
         return out
 
     def _hoist_args(self, args, space_numel):
@@ -1340,6 +1437,8 @@ class Planner:
             return self._mvn_density(dist, value, scope, tag)
         if dist.family == 'Dirichlet':
             return self._dirichlet_density(dist, value, scope, tag)
+        if dist.family in COMPOSED:
+            return self._composed_density(dist, value, scope, tag)
         args = {k: self.resolve_arg(dist.family, k, v, scope) for k, v in dist.args.items()}
         if dist.family in ('Bernoulli',):
             opname = 'Bernoulli_logits' if 'logits' in args else 'Bernoulli_probs'
@@ -1412,6 +1511,33 @@ class Planner:
         mk = Expr.make
         z = mk('sumlast', mk('mul', W, mk('sub', value, loc)))            # W (x - loc): [cells..., d]
         body = mk('sub', c, mk('mul', Expr.const(0.5), mk('sumlast', mk('square', z))))
+        return self.emit_expr(self._prepare(body), nred='all', tag=tag)
+
+    def _composed_density(self, dist, value, scope, tag) -> PT:
+        """Families of COMPOSED: the torch log_prob restated over traced operands, lowered like any model lambda."""
+        order, fn = COMPOSED[dist.family]
+        args = {k: Proxy(self.resolve_arg(dist.family, k, v, scope)) for k, v in dist.args.items()}
+        vec = dist.family in _VECTOR_FAMILIES
+        if 'logits' in order and 'logits' not in args:
+            p = args.pop('probs')
+            # binary families: logit(p); vector families: log of the normalised probabilities (categorical.py:60-65)
+            args['logits'] = (p.log() - p.sum(-1).log()) if vec else _probs_to_logits(p)
+        if 'probs' in order and 'probs' not in args:
+            args['probs'] = args.pop('logits').sigmoid()                  # geometric.py: logits_to_probs(is_binary=True)
+        v = Proxy(value)
+        extra = []
+        if dist.family == 'Categorical':
+            # value = the class index (a scalar per cell), probs / logits = one vector over the last positional dim
+            lshape = args['logits'].expr.pos_shape
+            if value.pos_shape != () or len(lshape) != 1:
+                raise Exception(f"Categorical: the value must be a scalar class index and probs / logits one vector "
+                                f"(got positional shapes {value.pos_shape} and {lshape})")
+            iota = self.const_input(torch.arange(lshape[0], dtype=torch.float64))
+            extra = [Proxy(Expr.leaf(iota, (), iota.pos_shape))]
+        elif vec and (len(value.pos_shape) < 1 or args['logits'].expr.pos_shape[-1:] != value.pos_shape[-1:]):
+            raise Exception(f"{dist.family}: value and probs / logits must be vectors of one size over the last "
+                            f"positional dim (got {value.pos_shape} and {args['logits'].expr.pos_shape})")
+        body = fn(v, *[args[k] for k in order], *extra).expr
         return self.emit_expr(self._prepare(body), nred='all', tag=tag)
 
     def _dirichlet_density(self, dist, value, scope, tag) -> PT:

@@ -278,6 +278,15 @@ def dist_log_prob(dist: Dist, value: ONT, scope: dict, dtype) -> ONT:
         rmat = mat.t.permute(perm).reshape(shape)
         d = td.MultivariateNormal(rloc, validate_args=False, **{mname: rmat})
         return ONT(d.log_prob(rv), axes)
+    if dist.family == 'Categorical':
+        # event-aware alignment (TorchDimDist.py:44-62): the value is a class index per cell, probs / logits carry the
+        # event dim; torch broadcasts the index against the batch dims of the argument
+        (aname, arg), = args.items()
+        (rv, _), axes = _align([value, ONT(arg.t[..., 0], arg.axes)])
+        perm = [arg.axes.index(a) for a in axes if a in arg.axes] + [len(arg.axes)]
+        shape = [arg.sizes()[a] if a in arg.axes else 1 for a in axes] + [arg.t.shape[-1]]
+        d = td.Categorical(**{aname: arg.t.permute(perm).reshape(shape)}, validate_args=False)
+        return ONT(d.log_prob(rv), axes)
     raw, axes = _align([value] + [args[k] for k in names])
     rv, rargs = raw[0], dict(zip(names, raw[1:]))
     d = getattr(td, dist.family)(**rargs, validate_args=False)

@@ -1,6 +1,6 @@
 """Generate golden vectors by running the UNMODIFIED reference in the build container.
 
-    python tests/golden/make_golden.py            # writes tests/golden/<case>_<dtype>.pt
+    python tests/golden/make_golden.py [case ...]  # writes tests/golden/<case>_<dtype>.pt (default: every case)
 
 The reference sources are imported from /root/reference/src through oracle/refcompat.py
 (runtime compat patches for torch 2.11, none on the logPQ arithmetic path; opt_einsum is
@@ -159,7 +159,10 @@ def run_case(name, dtype, seed=0):
 
 
 def main():
+    only = sys.argv[1:]                       # optional: the cases to (re)generate; default all
     for name in models.CASES:
+        if only and name not in only:
+            continue
         for dtype in (t.float32, t.float64):
             out = run_case(name, dtype)
             tag = 'f32' if dtype == t.float32 else 'f64'

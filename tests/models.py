@@ -525,3 +525,63 @@ def dirichlet_inputs(T=5, seed=0, dtype=t.float32):
 
 
 CASES['dirichlet'] = (dirichlet_model, dirichlet_inputs, dict(T=5), 4, [('p', 'mean'), ('q', 'mean2')], [], 5)
+
+
+# --------------------------------------------------------------------------- vector-valued likelihoods (row f-2)
+def vector_family_case(ns, family, dtype, seed=0, T=9, K=5, J=4):
+    """A simplex-valued latent `p` and a vector of scores `s` feeding a OneHotCategorical / Multinomial / Categorical likelihood
+    (through probs and through logits): returns (P, Q, sample, params, data) as named tensors."""
+    from alan_b200.named import NT
+    Fam = getattr(ns, family)
+    P = ns.Plate(p=ns.Dirichlet(t.tensor([1.5, 2.0, 0.7, 3.0], dtype=dtype)), s=ns.Normal(t.zeros(J, dtype=dtype), 1.0),
+                 T=ns.Plate(y=Fam(probs='p'), w=Fam(logits=lambda s: 1.5 * s)))
+    Q = ns.Plate(p=ns.Dirichlet('qp_conc'), s=ns.Normal('s_loc', lambda s_ls: s_ls.exp()),
+                 T=ns.Plate(y=ns.Data(), w=ns.Data()))
+    g = t.Generator().manual_seed(seed)
+    r = lambda *sh: t.randn(sh, generator=g, dtype=t.float64).to(dtype)
+    if family == 'Categorical':                                   # the value is the class index itself
+        onehot = lambda: t.randint(0, J, (T,), generator=g).to(dtype)
+    else:
+        onehot = lambda: t.nn.functional.one_hot(t.randint(0, J, (T,), generator=g), J).to(dtype)
+    data = {'y': NT(onehot(), ('T',)), 'w': NT(onehot(), ('T',))}
+    params = {'qp_conc': NT(t.tensor([2.0, 2.5, 1.2, 2.2], dtype=dtype), ()), 's_loc': NT(0.1 * r(J), ()),
+              's_ls': NT(-0.5 + 0.1 * r(J), ())}
+    p = t.distributions.Dirichlet(t.tensor([2.0, 2.5, 1.2, 2.2], dtype=t.float64)).sample((K,)).to(dtype)
+    sample = {'p': NT(p, ('K_p',)), 's': NT(0.6 * r(K, J), ('K_s',))}
+    return P, Q, sample, params, data
+
+
+# --------------------------------------------------------------------------- Categorical + composed families (row f-2)
+def families_model(ns, J=4, F=3):
+    """A softmax-regression likelihood like the reference's examples/examples/mnist_classification.py:30-40
+    (`Categorical(logits=...)` of a matrix-valued latent times a plated covariate), next to Gumbel and Weibull
+    likelihoods of a scalar latent: families whose density the B200 planner composes from VM primitives."""
+    dt = t.get_default_dtype()
+    P = ns.Plate(
+        w=ns.Normal(t.zeros(J, F, dtype=dt), 1.0),
+        s=ns.Normal(0., 1.),
+        T=ns.Plate(
+            y=ns.Categorical(logits=lambda w, x: w @ x),
+            g=ns.Gumbel('s', 1.3),
+            wb=ns.Weibull(lambda s: s.exp(), 1.7),
+        ),
+    )
+    Q = ns.Plate(
+        w=ns.Normal('w_loc', lambda w_ls: w_ls.exp()),
+        s=ns.Normal('s_loc', 0.8),
+        T=ns.Plate(y=ns.Data(), g=ns.Data(), wb=ns.Data()),
+    )
+    return P, Q
+
+
+def families_inputs(T=7, J=4, F=3, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    return dict(platesizes={'T': T},
+                data={'y': t.randint(0, J, (T,), generator=g).to(dtype).refine_names('T'),
+                      'g': (0.3 + 1.2 * r(T)).refine_names('T'), 'wb': (r(T).abs() + 0.2).refine_names('T')},
+                inputs={'x': r(T, F).refine_names('T', None)},
+                params={'w_loc': 0.2 * r(J, F), 'w_ls': -0.6 + 0.1 * r(J, F), 's_loc': 0.1 * r()})
+
+
+CASES['families'] = (families_model, families_inputs, dict(T=7), 4, [('s', 'mean'), ('w', 'mean2')], [], 5)

@@ -759,6 +759,19 @@ _FAMILIES = {
                                lambda r, n: (r(n).abs() * 3).floor()),
     'Binomial_logits': (lambda ns: ns.Binomial(7, logits='a'), lambda r, n: (r(n).abs() * 2).floor().clamp(max=7)),
     'Binomial_probs': (lambda ns: ns.Binomial(7, probs=lambda a: a.sigmoid()), lambda r, n: (r(n).abs() * 2).floor().clamp(max=7)),
+    # families composed from the VM's primitive operations (plan.py COMPOSED)
+    'Gumbel': (lambda ns: ns.Gumbel('a', lambda b: b.exp()), lambda r, n: r(n)),
+    'Weibull': (lambda ns: ns.Weibull(lambda a: a.exp(), lambda b: b.exp() + 0.5), lambda r, n: r(n).abs() + 0.2),
+    'Pareto': (lambda ns: ns.Pareto(0.1, lambda a: a.exp() + 0.5), lambda r, n: r(n).abs() + 0.2),
+    'HalfCauchy': (lambda ns: ns.HalfCauchy(lambda a: a.exp()), lambda r, n: r(n).abs() + 0.1),
+    'Chi2': (lambda ns: ns.Chi2(lambda a: a.exp() + 1.0), lambda r, n: r(n).abs() + 0.2),
+    'Geometric_probs': (lambda ns: ns.Geometric(probs=lambda a: a.sigmoid()), lambda r, n: (r(n).abs() * 3).floor()),
+    'Geometric_logits': (lambda ns: ns.Geometric(logits='a'), lambda r, n: (r(n).abs() * 3).floor()),
+    'Kumaraswamy': (lambda ns: ns.Kumaraswamy(lambda a: a.exp() + 0.5, lambda b: b.exp() + 0.5), lambda r, n: r(n).sigmoid()),
+    'FisherSnedecor': (lambda ns: ns.FisherSnedecor(lambda a: a.exp() + 2.0, 5.0), lambda r, n: r(n).abs() + 0.2),
+    'RelaxedBernoulli_logits': (lambda ns: ns.RelaxedBernoulli(0.7, logits='a'), lambda r, n: r(n).sigmoid()),
+    'RelaxedBernoulli_probs': (lambda ns: ns.RelaxedBernoulli(lambda b: b.exp() + 0.3, probs=lambda a: a.sigmoid()),
+                               lambda r, n: r(n).sigmoid()),
 }
 
 
@@ -858,3 +871,28 @@ def test_bern_dot_sum_side_factor_and_k_pairs(dtype, M_, N_, K, monkeypatch):
     assert t.equal(res["side"][0], res["kpt2"][0])
     for k in names:
         assert t.equal(res["side"][1][k], res["kpt2"][1][k]), k
+
+
+@pytest.mark.parametrize("dtype", [t.float32, t.float64])
+@pytest.mark.parametrize("family", ["OneHotCategorical", "Multinomial", "Categorical"])
+def test_vector_families_vs_oracle(family, dtype):
+    """OneHotCategorical / Multinomial likelihoods over the last positional dim (probs from a Dirichlet latent, logits
+    from a traced lambda), densities composed from the VM's primitive operations: log-evidence and every gradient
+    against torch.distributions + autograd in the oracle."""
+    from oracle import logpq_oracle as O
+    Compiled, Runner = _engine()
+    P, Q, sample, params, data = models.vector_family_case(M, family, dtype)
+    names = ['p', 's'] + list(params)
+    comp = Compiled(P, Q, sample, params, data, grad_names=names)
+    run = Runner(comp, "cuda:0")
+    tensors = run.device_inputs(sample, params, data)
+    lp = run.forward_raw(tensors)
+    grads = run.backward_raw(tensors)
+    sg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in sample.items()}
+    pg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in params.items()}
+    ref = O.elbo(P, Q, sg, pg, data)
+    rg = t.autograd.grad(ref, [sg['p'].t, sg['s'].t] + [pg[k].t for k in params], allow_unused=True)
+    tl = 2e-5 if dtype == t.float32 else 1e-10
+    assert t.isfinite(ref) and rel_err(lp.cpu(), ref) < tl
+    for k, rr in zip(names, rg):
+        assert rel_err(grads[k].cpu().reshape(rr.shape), rr) < 50 * tl, k

@@ -261,3 +261,70 @@ def test_split_sizes_follow_the_reference_rule():
     assert resolve(sp) is sp
     with pytest.raises(Exception, match="computation_strategy"):
         resolve("nope")
+
+
+@pytest.mark.parametrize("dtype", [t.float32, t.float64])
+@pytest.mark.parametrize("family", ["OneHotCategorical", "Multinomial", "Categorical"])
+def test_vector_families_vs_oracle(family, dtype):
+    """OneHotCategorical / Multinomial (densities composed from the VM's primitive operations, plan.py COMPOSED) through
+    the plan emulator against torch.distributions + autograd in the oracle."""
+    from oracle import logpq_oracle as O
+    P, Q, sample, params, data = models.vector_family_case(M, family, dtype)
+    names = ['p', 's'] + list(params)
+    comp = Compiled(P, Q, sample, params, data, grad_names=names)
+    lp, grads, _ = run_fwd_bwd(comp, comp.canonical_inputs(sample, params, data))
+    sg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in sample.items()}
+    pg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in params.items()}
+    ref = O.elbo(P, Q, sg, pg, data)
+    rg = t.autograd.grad(ref, [sg['p'].t, sg['s'].t] + [pg[k].t for k in params], allow_unused=True)
+    tl = 2e-5 if dtype == t.float32 else 1e-10
+    assert t.isfinite(ref) and rel_err(lp, ref) < tl
+    for k, rr in zip(names, rg):
+        assert rel_err(grads[k].reshape(rr.shape), rr) < 50 * tl, k
+    with pytest.raises(Exception, match="total_count"):
+        M.Multinomial(3, probs='p')
+
+
+COMPOSED_SCALAR = {
+    'Gumbel': (lambda ns: ns.Gumbel('a', lambda b: b.exp()), lambda r, n: r(n)),
+    'Weibull': (lambda ns: ns.Weibull(lambda a: a.exp(), lambda b: b.exp() + 0.5), lambda r, n: r(n).abs() + 0.2),
+    'Pareto': (lambda ns: ns.Pareto(0.1, lambda a: a.exp() + 0.5), lambda r, n: r(n).abs() + 0.2),
+    'HalfCauchy': (lambda ns: ns.HalfCauchy(lambda a: a.exp()), lambda r, n: r(n).abs() + 0.1),
+    'Chi2': (lambda ns: ns.Chi2(lambda a: a.exp() + 1.0), lambda r, n: r(n).abs() + 0.2),
+    'Geometric': (lambda ns: ns.Geometric(logits='a'), lambda r, n: (r(n).abs() * 3).floor()),
+    'Kumaraswamy': (lambda ns: ns.Kumaraswamy(lambda a: a.exp() + 0.5, lambda b: b.exp() + 0.5), lambda r, n: r(n).sigmoid()),
+    'FisherSnedecor': (lambda ns: ns.FisherSnedecor(lambda a: a.exp() + 2.0, 5.0), lambda r, n: r(n).abs() + 0.2),
+    'RelaxedBernoulli': (lambda ns: ns.RelaxedBernoulli(lambda b: b.exp() + 0.3, probs=lambda a: a.sigmoid()),
+                         lambda r, n: r(n).sigmoid()),
+}
+
+
+@pytest.mark.parametrize("family", list(COMPOSED_SCALAR))
+def test_composed_scalar_families_vs_oracle(family):
+    """The scalar families whose density is composed from VM primitives (plan.py COMPOSED), float64, through the plan
+    emulator against torch.distributions + autograd (the GPU twin, both dtypes: test_density_families_vs_oracle)."""
+    import zlib
+    from oracle import logpq_oracle as O
+    like, gen = COMPOSED_SCALAR[family]
+    P = M.Plate(a=M.Normal(0., 1.), b=M.Normal(-0.3, 0.5), T=M.Plate(y=like(M)))
+    Q = M.Plate(a=M.Normal('a_loc', lambda a_ls: a_ls.exp()), b=M.Normal('b_loc', lambda b_ls: b_ls.exp()),
+                T=M.Plate(y=M.Data()))
+    g = t.Generator().manual_seed(zlib.crc32(family.encode()) % 1000)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64)
+    data = {'y': NT(gen(r, 11), ('T',))}
+    params = {'a_loc': NT(0.1 * r(), ()), 'a_ls': NT(-0.5 + 0.1 * r(), ()), 'b_loc': NT(-0.3 + 0.1 * r(), ()),
+              'b_ls': NT(-0.7 + 0.1 * r(), ())}
+    sample = {'a': NT(0.6 * r(4), ('K_a',)), 'b': NT(-0.3 + 0.4 * r(4), ('K_b',))}
+    names = ['a', 'b'] + list(params)
+    comp = Compiled(P, Q, sample, params, data, grad_names=names)
+    lp, grads, _ = run_fwd_bwd(comp, comp.canonical_inputs(sample, params, data))
+    sg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in sample.items()}
+    pg = {k: NT(v.t.clone().requires_grad_(), v.axes) for k, v in params.items()}
+    ref = O.elbo(P, Q, sg, pg, data)
+    rg = t.autograd.grad(ref, [sg['a'].t, sg['b'].t] + [pg[k].t for k in params], allow_unused=True)
+    assert t.isfinite(ref) and rel_err(lp, ref) < 1e-10
+    for k, rr in zip(names, rg):
+        if rr is None:
+            assert float(grads[k].abs().max()) == 0.0, k
+            continue
+        assert rel_err(grads[k].reshape(rr.shape), rr) < 1e-8, k
