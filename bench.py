@@ -592,7 +592,7 @@ def _bounded_users(cfg, budget_s, n_steps, step_time_of):
     return users, t50
 
 
-def run_reference(args, cfg, iters=None, warmup=None, budget_s=100.0):
+def run_reference(args, cfg, iters=None, warmup=None, budget_s=100.0, device="cpu"):
     """The reference's CPU implementation of the path on the host cores, every thread it can use.
 
     kind = "reference": the UNMODIFIED reference (alan) imported from baseline/_ref (its pip install; /root/reference/src
@@ -624,6 +624,8 @@ def run_reference(args, cfg, iters=None, warmup=None, budget_s=100.0):
             bp = alan.BoundPlate(Pm, sizes, inputs=inputs)
             bq = alan.BoundPlate(Qm, sizes, inputs=inputs, extra_opt_params={k: nm(ip[k]).clone() for k in params})
             prob = alan.Problem(bp, bq, {'obs': nm(data['obs'])})
+            if device != "cpu":
+                prob.to(device)                # the reference's own route to a GPU: ATen kernels on materialised tensors
             s = prob.sample(cfg["K"], reparam=False)
             strat = alan.Split('plate_1', 50) if users > 50 else alan.checkpoint
 
@@ -631,6 +633,8 @@ def run_reference(args, cfg, iters=None, warmup=None, budget_s=100.0):
                 prob.zero_grad()
                 L = s.elbo_rws(computation_strategy=strat)
                 L.backward()
+                if device != "cpu":
+                    t.cuda.synchronize()
                 return L.detach()
             return step
         from oracle import logpq_oracle as O
@@ -732,6 +736,17 @@ def main():
             if args.workload != "cfg2":
                 r2 = run_reference(args, WORKLOADS["cfg2"], iters=3, warmup=1, budget_s=10.0)
                 line["cfg2"]["cpu_baseline"] = {k: r2[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            # secondary: the UNMODIFIED reference on this same B200 through `problem.to('cuda')`
+            # -- ATen kernels over the materialised torchdim tensors -- separates "GPU vs CPU" from "fused vs
+            # materialised".  A reported comparison, never the reference arm; any failure is recorded, not raised.
+            try:
+                rg = run_reference(args, cfg, iters=3, warmup=1, budget_s=6.0, device=f"cuda:{local_rank}")
+                if rg["kind"] == "reference":
+                    line["reference_on_gpu"] = {"value": rg["value"], "unit": UNIT, "ms_per_step": rg["ms_per_step"],
+                                                "sample": rg["sample"], "device": "the same B200, ATen kernels, "
+                                                "Sample.elbo_rws(Split('plate_1', 50)).backward()"}
+            except Exception as exc:                           # noqa: BLE001
+                line["reference_on_gpu"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     os.close(saved_stdout)
