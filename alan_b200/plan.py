@@ -2132,26 +2132,51 @@ class Planner:
         return LogicalFactor([(plain(out), 1.0)], 0.0, out.axes)
 
     # -- top level ----------------------------------------------------------------------------
+    def _last_contraction_as_root(self, lf):
+        """The op that may write the log-evidence itself: `lp = t + const` with `t` the scalar output of the reduction
+        emitted last (the top-level contraction over the last K axis), which nobody else reads."""
+        if len(lf.tensors) != 1 or lf.tensors[0][1] != 1.0 or os.environ.get("ALAN_B200_NO_TAILFOLD") == "1":
+            return None
+        ref = lf.tensors[0][0]
+        if type(ref) is not LeafRef or ref.rename or ref.mode or not self.fwd:
+            return None
+        op = self.fwd[-1]
+        if not isinstance(op, ReduceOp) or op.out is not ref.pt or op.out.space != 'ws' or op.out.shape != () \
+                or op.nsplit != 1 or op.acc or op.scale != 1.0 or op.mode not in (R_SUM, R_LSE_EPS, R_LSE) \
+                or getattr(op, 'autodiff_as', None) is not None or ref.pt.id in self.needs_materialised:
+            return None
+        return op
+
     def build(self, grad_names=(), with_sample=False) -> Plan:
         if grad_names or not self.grad_names:
             self.set_grad_names(grad_names)
         self.with_sample = with_sample
+        # The log-evidence is written straight into output 0 by the op that produces it: the microsecond-scale ops at
+        # the end of the forward program are a chain of DEPENDENT launches (~4 us each under graph replay,
+        # profiles/r02_small_ops.md), so neither a copy (`lp_out`) nor a one-term sum (`lp`) follows the last contraction.
         lp = PT((), (), self.sizes, 'output', index=0, name='lp')
-        self.lp_ws = self.ws((), name='lp')
+        self.lp_ws = lp                          # the root of the adjoint program (build_backward seeds its adjoint)
         if self.nonmp:
             # SampleNonMP._elbo (reference SampleNonMP.py:56-57): logsumexp over the one K axis (no eps) - log K
             lf = self.plan_nonmp(None, self.P, self.Q, (), self.scope)
             if tuple(lf.axes) != (NONMP_K,):
                 raise Exception(f"non-MP log-probability has axes {lf.axes}, expected ({NONMP_K},)")
             self.nonmp_lf = lf
-            self.emit(ReduceOp(R_LSE, self.lp_ws, [], [self.axdim(NONMP_K)], lf.tensors,
+            self.emit(ReduceOp(R_LSE, lp, [], [self.axdim(NONMP_K)], lf.tensors,
                                cadd=lf.const - math.log(self.sizes[NONMP_K]), tag='lp'))
         else:
             lf = self.plan_plate(None, self.P, self.Q, (), self.scope)
             if lf.axes != ():
                 raise Exception(f"log-evidence has leftover axes {lf.axes}")
-            self.emit(ReduceOp(R_SUM, self.lp_ws, [], [], lf.tensors, cadd=lf.const, tag='lp'))
-        self.emit(ReduceOp(R_SUM, lp, [], [], [(plain(self.lp_ws), 1.0)], tag='lp_out'))
+            root = self._last_contraction_as_root(lf)
+            if root is not None:
+                old = root.out
+                root.out, root.cadd, root.tag = lp, root.cadd + lf.const, 'lp:' + root.tag
+                self.producer[lp.id] = root
+                if old.id in self.needs:
+                    self.needs.add(lp.id)
+            else:
+                self.emit(ReduceOp(R_SUM, lp, [], [], lf.tensors, cadd=lf.const, tag='lp'))
         self.fwd_segments.append(self.fwd)
         plan = self.plan
         plan.programs = list(self.fwd_segments)
@@ -2237,7 +2262,7 @@ class Planner:
             return 1.0 if is_partial else 1.0 / self.world_size
 
         for op in reversed(all_fwd):
-            if op.out.space == 'output':
+            if op.out.space == 'output' and op.out is not self.lp_ws:
                 continue
             if op.out.id not in needs or (op.out.id not in adj and op.out.id not in lazy_bcast):
                 continue
