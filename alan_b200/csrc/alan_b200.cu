@@ -955,6 +955,10 @@ int alan_b200_plan_create(const int32_t* blob, size_t n_words, alan_b200_plan** 
     { const char* sq = getenv("ALAN_B200_SEQ_RESIDENT"); p->seq_resident = !(sq && sq[0] == '0'); }
     int dev = 0;
     p->sm_count = 148;
+    if (const char* e = getenv("ALAN_B200_WAIT_HINT_NS")) {          // tuning aid: mbarrier.try_wait suspend-time hint (fan_tc.cuh)
+        const unsigned v = (unsigned)atoi(e);
+        cudaMemcpyToSymbol(tc::g_wait_hint_ns, &v, sizeof(v));
+    }
     if (cudaGetDevice(&dev) == cudaSuccess) {
         int n = 0;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) p->sm_count = n;

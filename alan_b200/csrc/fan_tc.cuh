@@ -38,16 +38,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting warp sleeps until the phase completes (or the hint, in nanoseconds,
+// runs out) instead of polling -- the polling loops of the builder / MMA warps were 16 % of all issued warp instructions
+// of the dense forward kernel (ncu, round 2), taken from the sub-partitions' epilogue warps.
+// (ALAN_B200_WAIT_HINT_NS, read when a plan is created, sets the hint: tuning aid.)
+__constant__ unsigned g_wait_hint_ns = 100000u;
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(g_wait_hint_ns) : "memory");
     return ok != 0;
 }
-// Bounded spin: a protocol bug must fault (trap), never hang the GPU.
+// Bounded wait (~2 s): a protocol bug must fault (trap), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin)
-        if (spin > (1u << 26)) __trap();
+        if (spin > (1u << 22)) __trap();
 }
 #ifdef TC_DEBUG_SPIN
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc) {

@@ -38,8 +38,25 @@
 // the MMA issuer is busy 75 % (87 cycles per MMA) and the epilogue warps 90 %; adjoint 310 k, epilogue-bound.
 #pragma once
 #include "fan_tc.cuh"
+#include <cuda_fp16.h>
 
 namespace tc {
+
+// kind::f16 twin of mma_tf32_ts (A in TMEM as packed fp16 pairs, B in shared memory as fp16): M = 128, K = 16
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// x = hi + lo with hi, lo fp16 (11 significant bits each: 22 bits of x, the dropped lo x lo product is 2^-22 relative);
+// two values per call, packed the way the tensor core reads a 32-bit word (the lower K index in the lower half)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 back = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - back.x, x1 - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -128,15 +145,27 @@ __device__ __forceinline__ int t2_dot(const int* idx, const int* st) {
     return o;
 }
 
-template <int D, bool BWD>
+// H16: the operands as fp16 pairs (hi, lo) instead of 3xTF32 -- products hi.hi + lo.hi + hi.lo as kind::f16 MMAs of
+// K = 16: 9 MMAs per (tile, block) at D = 18 (K = 48) instead of 15 (K = 40 in steps of 8).  The bias b log2e is carried
+// by three K columns (A entries 4096, 1, 1; B entries q0 = fp16(b'/4096), q1 = fp16(b' - 4096 q0), q2 = the rest): 33 bits.
+// STAG: the four epilogue teams work as two pairs, pair g on the accumulator stage g (every other tile), each team on two
+// of the stage's four user slots.  With all teams on the same tile the warps of a sub-partition run in lockstep -- all
+// in their issue-bound phase (TMEM read, max tree, sums, log, store), then all in their MUFU-bound phase (32 ex2 each) --
+// and the two phases add up; two pairs half a period apart overlap one pair's ex2 with the other pair's issue phase.
+// Measured at cfg-5 on one box (fan_lse forward, us): 3xTF32 140.1, STAG 138.5-128 (no gain: the MMA issuer is then the
+// limit), H16 140.5 (no gain either: with all teams in lockstep the epilogue is), H16 + STAG 126.6 (-10 %).  A second group
+// of builder warps (two blocks in flight) changed nothing: 139.1.  H16 + STAG is opt-in (ALAN_B200_TC_F16=1
+// ALAN_B200_TC_STAG=1, D = 18): fp16 overflows where 3xTF32 does not (|v - centre| > 255, scale < 0.005 -> inf / NaN lp).
+template <int D, bool BWD, bool H16 = false, bool STAG = false>
 __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __grid_constant__ FanLseParams<float> p, const __grid_constant__ Tc2Geom geo) {
-    constexpr int KT = (2 * D + 1 + 7) / 8 * 8;                            // K extent (40 at D = 18)
-    constexpr int NC = KT / 4, KSTEPS = KT / 8;
+    constexpr int KT = H16 ? (2 * D + 3 + 15) / 16 * 16 : (2 * D + 1 + 7) / 8 * 8;   // K extent (40 at D = 18; 48 as fp16)
+    constexpr int NC = H16 ? KT / 8 : KT / 4, KSTEPS = H16 ? KT / 16 : KT / 8;       // 16-byte chunks per row, MMAs per product
+    constexpr int ACOLS = H16 ? KT / 2 : KT;                                // TMEM columns of one A part of one tile
     constexpr uint32_t LBO = T2_N * 16, SBO = 8 * 16;                      // [chunk][128 rows][16 B]: A_lo tiles and B alike
     constexpr uint32_t OPER = NC * LBO;                                    // bytes of one operand part (20 KB at D = 18)
-    constexpr uint32_t A_HI = 0, A_LO = T2_TILES * KT, D_COL = 2 * T2_TILES * KT;
-    static_assert(2 * T2_TILES * KT + T2_ACC * T2_N <= T2_TMEM_COLS, "TMEM budget");
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T2_N >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t A_HI = 0, A_LO = T2_TILES * ACOLS, D_COL = 2 * T2_TILES * ACOLS;
+    static_assert(2 * T2_TILES * ACOLS + T2_ACC * T2_N <= T2_TMEM_COLS, "TMEM budget");
+    constexpr uint32_t IDESC = (1u << 4) | ((H16 ? 0u : 2u) << 7) | ((H16 ? 0u : 2u) << 10) | ((uint32_t)(T2_N >> 3) << 17) | ((128u >> 4) << 24);
 
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     unsigned char* stage_base = tc_smem;                                   // T2_STAGES x (B_hi | B_lo)
@@ -201,14 +230,20 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
         const int npad = 32 - Kk, per_stage = T2_US * npad;
         for (int i = threadIdx.x; i < T2_STAGES * per_stage; i += blockDim.x) {
             const int s = i / per_stage, r = i - s * per_stage, us = r / npad, kz = Kk + r - us * npad;
-            const int off = (((2 * D) / 4) * T2_N + 32 * us + kz) * 4 + ((2 * D) & 3);
-            reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER)[off] = bh;
-            reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER)[off] = bl;
+            if (H16) {
+                // the first bias piece (its A entry is 4096): -60000 x 4096 = -2.5e8 in log2 units
+                const int off = (((2 * D) / 8) * T2_N + 32 * us + kz) * 8 + ((2 * D) & 7);
+                reinterpret_cast<__half*>(stage_base + (size_t)s * 2 * OPER)[off] = __float2half_rn(-60000.f);
+            } else {
+                const int off = (((2 * D) / 4) * T2_N + 32 * us + kz) * 4 + ((2 * D) & 3);
+                reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER)[off] = bh;
+                reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER)[off] = bl;
+            }
         }
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&full[s], 32 * T2_BW); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < T2_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128 * T2_EPI); }
+        for (int a = 0; a < T2_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], STAG ? 128 * (T2_EPI / 2) : 128 * T2_EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == T2_MMA_WARP) {
@@ -249,7 +284,8 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                     a[D + dd] = 2.f * lc * w * LS;
                     c += lc * lc * w + logf(sc);
                 }
-                a[2 * D] = 1.f;
+                a[2 * D] = H16 ? 4096.f : 1.f;
+                if (H16) { a[2 * D + 1] = 1.f; a[2 * D + 2] = 1.f; }
                 cst = -(c + float(D) * float(HALF_LOG_2PI));
                 ooff = lam * geo.o_lam + f * (int)p.o_f;
                 goff = BWD ? lam * geo.g_lam + f * geo.g_f : lam * (int)p.ps_lam + f * (int)p.ps_f;
@@ -258,16 +294,20 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
             s_ooff[tl * 128 + row] = ooff;
             s_goff[tl * 128 + row] = goff;
 #pragma unroll
-            for (int g8 = 0; g8 < KT / 8; ++g8) {
+            for (int g8 = 0; g8 < ACOLS / 8; ++g8) {
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float x = a[8 * g8 + e];
-                    hi[e] = to_tf32(x);
-                    lo[e] = __float_as_uint(x - __uint_as_float(hi[e]));
+                    if (H16) {
+                        split_f16x2(a[16 * g8 + 2 * e], a[16 * g8 + 2 * e + 1], hi[e], lo[e]);
+                    } else {
+                        const float x = a[8 * g8 + e];
+                        hi[e] = to_tf32(x);
+                        lo[e] = __float_as_uint(x - __uint_as_float(hi[e]));
+                    }
                 }
-                TC_ST8(lane_base + A_HI + KT * tl + 8 * g8, hi, 0);
-                TC_ST8(lane_base + A_LO + KT * tl + 8 * g8, lo, 0);
+                TC_ST8(lane_base + A_HI + ACOLS * tl + 8 * g8, hi, 0);
+                TC_ST8(lane_base + A_LO + ACOLS * tl + 8 * g8, lo, 0);
             }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -283,12 +323,16 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
         const float cadd = p.cadd;
         // adjoint: raw lse / gout of the NEXT block are fetched one block ahead (no arithmetic on them before their tile:
         // an in-order warp stalls on the first use of a pending load)
-        float n_lse[T2_TILES][T2_UPT], n_g[T2_TILES][T2_UPT];
-        int n_uoff[T2_UPT];
+        static_assert(!STAG || (!BWD && T2_ACC == 2 && T2_EPI == 4 && T2_US == 4), "staggered epilogue: forward, two stages, four teams");
+        constexpr int UPT = STAG ? 2 : T2_UPT;                                   // user slots per team and tile
+        const int ubase = STAG ? 2 * (team & 1) : T2_UPT * team;                 // first user slot of this team
+        const unsigned my_stage = (unsigned)(team >> 1);                         // STAG: this team's accumulator stage
+        float n_lse[T2_TILES][UPT], n_g[T2_TILES][UPT];
+        int n_uoff[UPT];
         auto fetch = [&](unsigned blk) {
 #pragma unroll
-            for (int uu = 0; uu < T2_UPT; ++uu) {
-                const unsigned u = T2_US * blk + T2_UPT * team + uu;
+            for (int uu = 0; uu < UPT; ++uu) {
+                const unsigned u = T2_US * blk + ubase + uu;
                 int idx[T2_ND];
                 t2_decode(u < n_u ? u : 0u, geo, idx);
                 const int uo = t2_dot(idx, geo.os);
@@ -313,21 +357,21 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
         float ps[T2_TILES];                                                      // forward: running sum of out over this team's users
 #pragma unroll
         for (int tl = 0; tl < T2_TILES; ++tl) ps[tl] = 0.f;
-        const uint32_t ld_base = tmem + ((uint32_t)(32 * q) << 16) + D_COL + 32 * T2_UPT * team;
+        const uint32_t ld_base = tmem + ((uint32_t)(32 * q) << 16) + D_COL + 32 * ubase;
         for (unsigned blk = blk0; blk < n_blocks; blk += blk_step, ++it) {
-            float lz[T2_TILES][T2_UPT], gz[T2_TILES][T2_UPT];
-            int uoff[T2_UPT];
+            float lz[T2_TILES][UPT], gz[T2_TILES][UPT];
+            int uoff[UPT];
 #pragma unroll
-            for (int uu = 0; uu < T2_UPT; ++uu) {
+            for (int uu = 0; uu < UPT; ++uu) {
                 uoff[uu] = n_uoff[uu];
 #pragma unroll
                 for (int tl = 0; tl < T2_TILES; ++tl) { lz[tl][uu] = BWD ? n_lse[tl][uu] : 0.f; gz[tl][uu] = BWD ? n_g[tl][uu] : 0.f; }
             }
             if (blk + blk_step < n_blocks) fetch(blk + blk_step);
-            float acc[T2_UPT][32];
+            float acc[BWD ? UPT : 1][32];
             if (BWD) {
 #pragma unroll
-                for (int uu = 0; uu < T2_UPT; ++uu)
+                for (int uu = 0; uu < UPT; ++uu)
 #pragma unroll
                     for (int k = 0; k < 32; ++k) acc[uu][k] = 0.f;
             }
@@ -337,19 +381,20 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                     const int a = tt % T2_ACC;
                     const uint32_t pa = (tt / T2_ACC) & 1;
                     ++tt;
+                    if (STAG && (unsigned)a != my_stage) continue;              // the other pair of teams takes this tile
                     MBAR_WAIT(&tfull[a], pa, dbg0);
                     tc_fence_after();
                     if (!BWD) {
                         // all loads of this team first, then the accumulator stage goes straight back to the MMA issuer
-                        uint32_t r[T2_UPT][32];
+                        uint32_t r[UPT][32];
 #pragma unroll
-                        for (int uu = 0; uu < T2_UPT; ++uu) TC_LD32(r[uu], ld_base + T2_N * a + 32 * uu);
+                        for (int uu = 0; uu < UPT; ++uu) TC_LD32(r[uu], ld_base + T2_N * a + 32 * uu);
 #pragma unroll
-                        for (int uu = 0; uu < T2_UPT; ++uu) TC_WAIT_LD32(r[uu]);
+                        for (int uu = 0; uu < UPT; ++uu) TC_WAIT_LD32(r[uu]);
                         tc_fence_before();
                         mbar_arrive(&tempty[a]);
 #pragma unroll
-                        for (int uu = 0; uu < T2_UPT; ++uu) {
+                        for (int uu = 0; uu < UPT; ++uu) {
 #ifdef TC_EXP_NOEPI
                             if (uoff[uu] >= 0 && s_ooff[tl * 128 + row] >= 0) { p.out[uoff[uu] + s_ooff[tl * 128 + row]] = __uint_as_float(r[uu][0]) + __uint_as_float(r[uu][31]); }
                             continue;
@@ -374,7 +419,11 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                             const float sum = t2.x + t2.y;
                             const int oo = s_ooff[tl * 128 + row];
                             if (uoff[uu] >= 0 && oo >= 0) {
-                                const float val = logf(sum + Eps<float>::v()) + m * 0.6931471805599453f + (cadd + s_cst[tl * 128 + row]);
+                                // sum is in [1, 32] (max-shifted): lg2.approx is within 2^-21 absolute there, against values of
+                                // magnitude 10-100 whose own fp32 spacing is 1e-6 .. 8e-6; libdevice logf costs ~25 instructions
+                                float l2;
+                                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(sum + Eps<float>::v()));
+                                const float val = (l2 + m) * 0.6931471805599453f + (cadd + s_cst[tl * 128 + row]);
                                 p.out[uoff[uu] + oo] = val;
                                 ps[tl] += val;
                             }
@@ -482,7 +531,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                 MBAR_WAIT(&tempty[a], pa ^ 1, dbg1);
                 tc_fence_after();
                 const uint32_t d = tmem + D_COL + T2_N * a;
-                const uint32_t ahi = tmem + A_HI + KT * tl, alo = tmem + A_LO + KT * tl;
+                const uint32_t ahi = tmem + A_HI + ACOLS * tl, alo = tmem + A_LO + ACOLS * tl;
                 if (elect_one()) {
 #ifdef TC_EXP_NOMMA
                     constexpr int KS_ = 1;
@@ -492,9 +541,15 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
 #pragma unroll
                     for (int j = 0; j < KS_; ++j) {
                         const uint64_t dh = smem_desc(bhi + j * 2 * LBO, LBO, SBO), dl = smem_desc(blo + j * 2 * LBO, LBO, SBO);
-                        mma_tf32_ts(d, ahi + 8 * j, dh, IDESC, j > 0 ? 1u : 0u);
-                        mma_tf32_ts(d, alo + 8 * j, dh, IDESC, 1u);
-                        mma_tf32_ts(d, ahi + 8 * j, dl, IDESC, 1u);
+                        if (H16) {
+                            mma_f16_ts(d, ahi + 8 * j, dh, IDESC, j > 0 ? 1u : 0u);
+                            mma_f16_ts(d, alo + 8 * j, dh, IDESC, 1u);
+                            mma_f16_ts(d, ahi + 8 * j, dl, IDESC, 1u);
+                        } else {
+                            mma_tf32_ts(d, ahi + 8 * j, dh, IDESC, j > 0 ? 1u : 0u);
+                            mma_tf32_ts(d, alo + 8 * j, dh, IDESC, 1u);
+                            mma_tf32_ts(d, ahi + 8 * j, dl, IDESC, 1u);
+                        }
                     }
                     if (tl == n_tiles - 1) tc_commit(&empty[s]);
                     tc_commit(&tfull[a]);
@@ -579,6 +634,34 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
 #pragma unroll
                 for (int i = 0; i < TC_NB; ++i) if (i < nb) bsum += geo.bc[i] * cur_b[i];
                 bsum *= LS;
+                if (H16) {
+                    // bias pieces: b' = 4096 q0 + q1 + q2, every piece an fp16 value (their lo parts are exactly zero)
+                    const float q0 = __half2float(__float2half_rn(bsum * (1.f / 4096.f)));
+                    const float r1 = fmaf(-4096.f, q0, bsum);
+                    const float q1 = __half2float(__float2half_rn(r1));
+                    const float q2 = r1 - q1;
+                    unsigned char* bhb = stage_base + (size_t)s * 2 * OPER;
+                    unsigned char* blb = bhb + OPER;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        float tv[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int k = 8 * c + e;
+                            const int dd = k < D ? k : (k < 2 * D ? k - D : 0);
+                            const float df = cur[dd] - s_cd[dd];
+                            tv[e] = k < D ? df * df : k < 2 * D ? df : k == 2 * D ? q0 : k == 2 * D + 1 ? q1 : k == 2 * D + 2 ? q2 : 0.f;
+                        }
+                        uint4 hh, l;
+                        split_f16x2(tv[0], tv[1], hh.x, l.x);
+                        split_f16x2(tv[2], tv[3], hh.y, l.y);
+                        split_f16x2(tv[4], tv[5], hh.z, l.z);
+                        split_f16x2(tv[6], tv[7], hh.w, l.w);
+                        const int off = (c * T2_N + n) * 16;
+                        *reinterpret_cast<uint4*>(bhb + off) = hh;
+                        *reinterpret_cast<uint4*>(blb + off) = l;
+                    }
+                } else {
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     // the tensor core reads only the 19 TF32 bits of a word: the raw fp32 value IS the "hi" part and
@@ -598,6 +681,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                     const int off = (c * T2_N + n) * 4;
                     *reinterpret_cast<float4*>(bh + off) = hh;
                     *reinterpret_cast<float4*>(bl + off) = l;
+                }
                 }
             }
 #ifdef TC_DEBUG_SPIN
@@ -680,8 +764,11 @@ template <int D>
 static int launch_fan_lse_tc2_D(const FanLseParams<float>& p, bool bwd, cudaStream_t stream, int sm_count) {
     constexpr int KT = (2 * D + 1 + 7) / 8 * 8;
     constexpr size_t OPER = (size_t)(KT / 4) * T2_N * 16;
-    const size_t smem = (T2_STAGES * 2) * OPER + T2_TILES * 128 * 12 + 2 * 4 * T2_US * 32 * 4 + 32 * 4 +
-                        (2 * T2_STAGES + 2 * T2_ACC) * 8 + 16;
+    constexpr size_t TAIL = T2_TILES * 128 * 12 + 2 * 4 * T2_US * 32 * 4 + 32 * 4 + (2 * T2_STAGES + 2 * T2_ACC) * 8 + 16;
+    const size_t smem = (T2_STAGES * 2) * OPER + TAIL;
+    // the fp16-pair formulation of the forward (9 MMAs per tile and block instead of 15): ALAN_B200_TC_F16=1
+    const char* e16 = getenv("ALAN_B200_TC_F16");
+    const bool h16 = e16 && atoi(e16) == 1;
     const int lam = fan_lse_tc2_lam(p);
     Tc2Geom geo;
     memset(&geo, 0, sizeof(geo));
@@ -754,6 +841,25 @@ static int launch_fan_lse_tc2_D(const FanLseParams<float>& p, bool bwd, cudaStre
     } else {
         static const cudaError_t attr_false = cudaFuncSetAttribute(fan_lse_tc2_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // once per process
         (void)attr_false;
+        const char* est = getenv("ALAN_B200_TC_STAG");
+        const bool stag = est && atoi(est) == 1;
+        if constexpr (D == 18) {
+            constexpr int KT16 = (2 * D + 3 + 15) / 16 * 16;
+            constexpr size_t OPER16 = (size_t)(KT16 / 8) * T2_N * 16;
+            const size_t smem16 = (T2_STAGES * 2) * OPER16 + TAIL;
+#define T2_LAUNCH_VARIANT(H, S, SM)                                                                                       \
+            {                                                                                                             \
+                static const cudaError_t av = cudaFuncSetAttribute(fan_lse_tc2_kernel<D, false, H, S>,                     \
+                                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM)); \
+                (void)av;                                                                                                 \
+                fan_lse_tc2_kernel<D, false, H, S><<<blocks, T2_WARPS * 32, (SM), stream>>>(p, geo);                        \
+                return 0;                                                                                                 \
+            }
+            if (h16 && stag) T2_LAUNCH_VARIANT(true, true, smem16)
+            if (h16) T2_LAUNCH_VARIANT(true, false, smem16)
+            if (stag) T2_LAUNCH_VARIANT(false, true, smem)
+#undef T2_LAUNCH_VARIANT
+        }
         fan_lse_tc2_kernel<D, false><<<blocks, T2_WARPS * 32, smem, stream>>>(p, geo);
     }
     return 0;

@@ -896,3 +896,30 @@ def test_vector_families_vs_oracle(family, dtype):
     assert t.isfinite(ref) and rel_err(lp.cpu(), ref) < tl
     for k, rr in zip(names, rg):
         assert rel_err(grads[k].cpu().reshape(rr.shape), rr) < 50 * tl, k
+
+
+@pytest.mark.parametrize("M_,N_,K", [(64, 5, 30), (301, 4, 30), (130, 3, 24)])
+@pytest.mark.parametrize("variant", ["f16", "stag", "f16_stag"])
+def test_dense_forward_variants_match_default(M_, N_, K, variant, monkeypatch):
+    """Opt-in variants of the dense fan_lse forward (csrc/fan_tc2.cuh, D = 18): operands as fp16 (hi, lo) pairs with
+    kind::f16 MMAs (ALAN_B200_TC_F16=1: 9 MMAs per tile and block instead of 15) and the staggered epilogue
+    (ALAN_B200_TC_STAG=1: two pairs of teams half a period apart), against the default 3xTF32 kernel and the FFMA2
+    kernel on the same inputs.  The switches are read at LAUNCH, the plan is the same."""
+    P, Q, sample, ip, data, names = _movielens_case(M_, N_, K, 18, seed=31)
+    out = _run_paths(P, Q, sample, ip, data, names, monkeypatch)
+    (lp_tc, g_tc, run, tensors), (lp_ff, g_ff, _, _) = out[True], out[False]
+    if "f16" in variant:
+        monkeypatch.setenv("ALAN_B200_TC_F16", "1")
+    if "stag" in variant:
+        monkeypatch.setenv("ALAN_B200_TC_STAG", "1")
+    lp = run.forward_raw(tensors).clone()
+    grads = {k: v.clone() for k, v in run.backward_raw(tensors).items()}
+    monkeypatch.delenv("ALAN_B200_TC_F16", raising=False)
+    monkeypatch.delenv("ALAN_B200_TC_STAG", raising=False)
+    # against the default tensor-core kernel (stag: the same products, the fused plate sum adds each team's users in a
+    # different, still fixed, order; f16: 22-bit operands instead of 3xTF32's 21) and against the FFMA2 kernel
+    assert rel_err(lp.cpu(), lp_tc.cpu()) < 1e-5
+    assert rel_err(lp.cpu(), lp_ff.cpu()) < 1e-5
+    for k in names:
+        assert rel_err(grads[k].cpu(), g_tc[k].cpu()) < 5e-5, k
+        assert rel_err(grads[k].cpu(), g_ff[k].cpu()) < 2e-4, k

@@ -13,7 +13,10 @@ from alan_b200 import model as M
 from alan_b200.named import NT, from_torch_named
 from alan_b200.engine import Compiled, Runner
 
-ENV = {"tc2": {}, "blockdiag": {"ALAN_B200_TC_BLOCKDIAG": "1"}, "ffma": {"ALAN_B200_NO_TC": "1"}}
+ENV = {"tc2": {}, "tc2_f16": {"ALAN_B200_TC_F16": "1"}, "tc2_stag": {"ALAN_B200_TC_STAG": "1"},
+       "tc2_f16_stag": {"ALAN_B200_TC_F16": "1", "ALAN_B200_TC_STAG": "1"},
+       "tc2_nbg2": {"ALAN_B200_TC_NBG": "2"},
+       "tc2_all": {"ALAN_B200_TC_F16": "1", "ALAN_B200_TC_STAG": "1", "ALAN_B200_TC_NBG": "2"}, "blockdiag": {"ALAN_B200_TC_BLOCKDIAG": "1"}, "ffma": {"ALAN_B200_NO_TC": "1"}}
 
 
 def nt(d):
@@ -42,7 +45,7 @@ def case(M_, N_, K, d, seed=21):
         data = nt(inp['data'])
         names = list(inp['params'])
         for path, env in (ENV.items() if dtype == t.float32 else [("f64", {})]):
-            for k in ("ALAN_B200_TC_BLOCKDIAG", "ALAN_B200_NO_TC"):
+            for k in ("ALAN_B200_TC_BLOCKDIAG", "ALAN_B200_NO_TC", "ALAN_B200_TC_F16", "ALAN_B200_TC_STAG"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             comp = Compiled(P, Q, sample, ip, data, grad_names=names)     # the switches are read when the plan is built
