@@ -32,6 +32,9 @@ def working_dtype(*dicts):
     return dt
 
 
+NARROW_MIN_NUMEL = 1 << 18          # uint8 / bool host tensors of at least this many elements cross PCIe as bytes
+
+
 def _to_working(t, dtype, device=None):
     """Move to `device` (if given) and cast to the working dtype.  uint8 / bool tensors cross PCIe as bytes and are
     widened on the device by the library's own kernel (alan_b200_widen_u8), not as four-byte floats."""
@@ -128,7 +131,9 @@ class Compiled:
                 v = elf[orig] if role == 'elf' else src[orig]
                 t = v.order(axes).t
             t = t.detach()
-            if keep_narrow and t.dtype in (torch.uint8, torch.bool):
+            # (small tensors are widened here, on the host: below ~1 MB saved the extra copy + widen launch costs more
+            # than the bytes -- cfg-2's 27 KB of covariates: 0.153 -> 0.186 ms per pipelined step when kept narrow)
+            if keep_narrow and t.dtype in (torch.uint8, torch.bool) and t.numel() >= NARROW_MIN_NUMEL:
                 out.append((t.to(device) if device is not None else t).contiguous())
             else:
                 out.append(_to_working(t, self.dtype, device))
