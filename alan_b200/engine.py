@@ -39,6 +39,8 @@ def _to_working(t, dtype, device=None):
     """Move to `device` (if given) and cast to the working dtype.  uint8 / bool tensors cross PCIe as bytes and are
     widened on the device by the library's own kernel (alan_b200_widen_u8), not as four-byte floats."""
     from . import runtime
+    if t.dtype == dtype and t.is_contiguous() and (device is None or t.device == device):
+        return t                                     # already canonical: the common case in a training loop
     if device is not None:
         t = t.to(device)
     if t.dtype in runtime.NARROW_DTYPES and t.is_cuda:
@@ -74,12 +76,14 @@ class Compiled:
                 named[key] = (role, k, v)
         self.sizes = sizes
         self.canon = canon
+        self.order_by_name = {}
         sig, self.order, self.elf_keys = {}, [], {}
         extra = []
         for key, (role, orig, v) in named.items():
             axes = tuple(a for a in canon if a in v.axes)
             sig[key] = TensorSig(role, axes, v.pos_shape, requires_grad=False)
             self.order.append((key, role, orig, axes))
+            self.order_by_name[key] = (key, role, orig, axes)
             if role == 'elf':
                 self.elf_keys[orig] = key
         planner = Planner(P, Q, sig, sizes, self.dtype, want_sample_N=N, shard_plate=shard_plate,
@@ -127,7 +131,7 @@ class Compiled:
                 _, plates, pos = next(m for m in self.moment_inputs if m[0] == name)
                 t = torch.zeros([self.sizes[a] for a in plates] + list(pos), dtype=self.dtype)
             else:
-                key, role, orig, axes = next(o for o in self.order if o[0] == name)
+                key, role, orig, axes = self.order_by_name[name]
                 v = elf[orig] if role == 'elf' else src[orig]
                 t = v.order(axes).t
             t = t.detach()
@@ -305,7 +309,7 @@ class Runner:
                 t = torch.zeros([comp.sizes[a] for a in plates] + list(pos), dtype=self.dtype, device=self.device)
                 t.requires_grad_(True)
             else:
-                key, role, orig, axes = next(o for o in comp.order if o[0] == name)
+                key, role, orig, axes = comp.order_by_name[name]
                 v = elf[orig] if role == 'elf' else src[orig]
                 t = _to_working(v.order(axes).t, self.dtype, self.device)
                 if name not in comp.grad_names:

@@ -38,6 +38,8 @@ class NT:
     def order(self, axes: Sequence[str]) -> "NT":
         """Permute the named dims into `axes` order (must be the same set)."""
         axes = tuple(axes)
+        if axes == self.axes:
+            return self
         if set(axes) != set(self.axes):
             raise Exception(f"order(): {axes} is not a permutation of {self.axes}")
         perm = [self.axes.index(a) for a in axes] + list(range(len(self.axes), self.t.ndim))
