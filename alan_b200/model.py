@@ -52,6 +52,8 @@ FAMILIES = {
     "RelaxedBernoulli": ("temperature", "probs", "logits"),
     "OneHotCategorical": ("probs", "logits"),
     "Categorical": ("probs", "logits"),
+    "ContinuousBernoulli": ("probs", "logits"),
+    "RelaxedOneHotCategorical": ("temperature", "probs", "logits"),
     "Multinomial": ("total_count", "probs", "logits"),
 }
 # arguments that torch.distributions leaves as None unless given
@@ -186,6 +188,8 @@ FisherSnedecor = _make("FisherSnedecor")
 RelaxedBernoulli = _make("RelaxedBernoulli")
 OneHotCategorical = _make("OneHotCategorical")
 Categorical = _make("Categorical")
+ContinuousBernoulli = _make("ContinuousBernoulli")
+RelaxedOneHotCategorical = _make("RelaxedOneHotCategorical")
 Multinomial = _make("Multinomial")
 
 

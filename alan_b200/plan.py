@@ -28,7 +28,7 @@ import torch
 
 from .model import Plate, Dist, Data, Timeseries, datagroup, Kname, function_arguments, DISCRETE_ARGS
 from .path import greedy_path
-from .trace import Expr, Proxy, trace_function, UNARY, BINARY
+from .trace import Expr, Proxy, _as_proxy, trace_function, UNARY, BINARY
 
 MAXD, MAXL, MAXI, MAXC, NREG = 10, 10, 32, 16, 32
 MAGIC, VERSION = 0x0A1AB200, 1
@@ -130,6 +130,32 @@ def _lp_categorical(v, logits, iota):             # categorical.py:137-143: the 
     return (onehot * logits).sum(-1) - logits.exp().sum(-1).log()
 
 
+def _lp_relaxed_one_hot_categorical(y, temperature, logits):    # relaxed_categorical.py:83-96 (ExpRelaxedCategorical) -> ExpTransform
+    J = float(logits.expr.pos_shape[-1])
+    x = y.log()
+    score = logits - x * temperature
+    lse = score.exp().sum(-1).log()
+    return score.sum(-1) - J * lse + math.lgamma(J) + (J - 1.0) * temperature.log() - x.sum(-1)
+
+
+def _lp_continuous_bernoulli(x, logits, p, hoist):              # continuous_bernoulli.py:160-205, lims = (0.499, 0.501)
+    lt = lambda a, b: Proxy(Expr.make('lt', _as_proxy(a).expr, _as_proxy(b).expr))
+    # torch.where(c, a, b) as c a + (1 - c) b with c in {0, 1}: both branches are finite by torch's own construction
+    outside = hoist((1.0 - lt(0.499, p)) + lt(0.501, p))         # le(p, 0.499) | gt(p, 0.501)
+    cut = hoist(outside * p + (1.0 - outside) * 0.499)
+    below = 1.0 - lt(0.5, cut)                                   # le(cut, 0.5)
+    cut_below = below * cut
+    ge = 1.0 - lt(cut, 0.5)
+    cut_above = ge * cut + (1.0 - ge)
+    first = hoist(((-cut).log1p() - cut.log()).abs().log())
+    second = hoist(below * (-2.0 * cut_below).log1p() + (1.0 - below) * (2.0 * cut_above - 1.0).log())
+    log_norm = first - second
+    xx = (p - 0.5) ** 2
+    taylor = math.log(2.0) + (4.0 / 3.0 + 104.0 / 45.0 * xx) * xx
+    norm = hoist(outside * log_norm + (1.0 - outside) * taylor)
+    return Proxy(Expr.make('Bernoulli_logits', x.expr, logits.expr)) + norm
+
+
 def _lp_multinomial(v, logits):                  # multinomial.py:121-132 (total_count = 1: see model.Dist)
     norm = logits - logits.exp().sum(-1).log()
     return (v.sum(-1) + 1.0).lgamma() - (v + 1.0).lgamma().sum(-1) + (norm * v).sum(-1)
@@ -143,9 +169,11 @@ COMPOSED = {
     'RelaxedBernoulli': (('temperature', 'logits'), _lp_relaxed_bernoulli),
     'OneHotCategorical': (('logits',), _lp_one_hot_categorical), 'Multinomial': (('logits',), _lp_multinomial),
     'Categorical': (('logits',), _lp_categorical),
+    'RelaxedOneHotCategorical': (('temperature', 'logits'), _lp_relaxed_one_hot_categorical),
+    'ContinuousBernoulli': (('logits', 'probs'), _lp_continuous_bernoulli),
 }
 # how the missing one of (probs, logits) is obtained from the given one, per family
-_VECTOR_FAMILIES = ('OneHotCategorical', 'Multinomial', 'Categorical')
+_VECTOR_FAMILIES = ('OneHotCategorical', 'Multinomial', 'Categorical', 'RelaxedOneHotCategorical')
 
 
 # ----------------------------------------------------------------------------------------
@@ -1518,12 +1546,14 @@ class Planner:
         order, fn = COMPOSED[dist.family]
         args = {k: Proxy(self.resolve_arg(dist.family, k, v, scope)) for k, v in dist.args.items()}
         vec = dist.family in _VECTOR_FAMILIES
+        both = 'logits' in order and 'probs' in order                    # ContinuousBernoulli uses the two of them
         if 'logits' in order and 'logits' not in args:
-            p = args.pop('probs')
+            p = args['probs'] if both else args.pop('probs')
             # binary families: logit(p); vector families: log of the normalised probabilities (categorical.py:60-65)
             args['logits'] = (p.log() - p.sum(-1).log()) if vec else _probs_to_logits(p)
         if 'probs' in order and 'probs' not in args:
-            args['probs'] = args.pop('logits').sigmoid()                  # geometric.py: logits_to_probs(is_binary=True)
+            lg = args['logits'] if both else args.pop('logits')
+            args['probs'] = lg.sigmoid()                                  # logits_to_probs(is_binary=True)
         v = Proxy(value)
         extra = []
         if dist.family == 'Categorical':
@@ -1537,6 +1567,10 @@ class Planner:
         elif vec and (len(value.pos_shape) < 1 or args['logits'].expr.pos_shape[-1:] != value.pos_shape[-1:]):
             raise Exception(f"{dist.family}: value and probs / logits must be vectors of one size over the last "
                             f"positional dim (got {value.pos_shape} and {args['logits'].expr.pos_shape})")
+        if dist.family == 'ContinuousBernoulli':
+            # the normaliser depends on the parameter only and is longer than one VM program: its pieces are
+            # materialised (hoisted) tensors of the parameter's shape, like any `arg` of a density
+            extra = [lambda e: Proxy(self.materialize(self._prepare(e.expr), tag='arg'))]
         body = fn(v, *[args[k] for k in order], *extra).expr
         return self.emit_expr(self._prepare(body), nred='all', tag=tag)
 

@@ -278,15 +278,32 @@ def dist_log_prob(dist: Dist, value: ONT, scope: dict, dtype) -> ONT:
         rmat = mat.t.permute(perm).reshape(shape)
         d = td.MultivariateNormal(rloc, validate_args=False, **{mname: rmat})
         return ONT(d.log_prob(rv), axes)
-    if dist.family == 'Categorical':
-        # event-aware alignment (TorchDimDist.py:44-62): the value is a class index per cell, probs / logits carry the
-        # event dim; torch broadcasts the index against the batch dims of the argument
-        (aname, arg), = args.items()
-        (rv, _), axes = _align([value, ONT(arg.t[..., 0], arg.axes)])
-        perm = [arg.axes.index(a) for a in axes if a in arg.axes] + [len(arg.axes)]
-        shape = [arg.sizes()[a] if a in arg.axes else 1 for a in axes] + [arg.t.shape[-1]]
-        d = td.Categorical(**{aname: arg.t.permute(perm).reshape(shape)}, validate_args=False)
-        return ONT(d.log_prob(rv), axes)
+    if dist.family in ('Categorical', 'RelaxedOneHotCategorical'):
+        # event-aware alignment (TorchDimDist.py:44-77): every argument is laid out [unnamed batch dims, named axes,
+        # its own event dims] with event_dim taken from the torch distribution's constraints, the value likewise with
+        # the support's event_dim; what is left after log_prob are the named axes and the unnamed batch dims
+        D = getattr(td, dist.family)
+        # (torch lists no constraint for `temperature`, a scalar per cell -- which is why the reference itself cannot
+        # construct the Relaxed* families: KeyError at TorchDimDist.py:47)
+        ev = [D.support.event_dim] + [D.arg_constraints[k].event_dim if k in D.arg_constraints else 0 for k in names]
+        xs = [value] + [args[k] for k in names]
+        axes = []
+        for x in xs:
+            for a in x.axes:
+                if a not in axes:
+                    axes.append(a)
+        nb = [x.t.ndim - len(x.axes) - e for x, e in zip(xs, ev)]
+        B = max(nb)
+        raw = []
+        for x, e, b in zip(xs, ev, nb):
+            perm = [x.axes.index(a) for a in axes if a in x.axes] + list(range(len(x.axes), x.t.ndim))
+            r = x.t.permute(perm)
+            pos = list(r.shape[len(x.axes):])
+            it = iter(r.shape[:len(x.axes)])
+            shape = [next(it) if a in x.axes else 1 for a in axes] + [1] * (B - b) + pos
+            raw.append(r.reshape(shape))
+        d = D(**dict(zip(names, raw[1:])), validate_args=False)
+        return ONT(d.log_prob(raw[0]), tuple(axes)).sum_pos()
     raw, axes = _align([value] + [args[k] for k in names])
     rv, rargs = raw[0], dict(zip(names, raw[1:]))
     d = getattr(td, dist.family)(**rargs, validate_args=False)

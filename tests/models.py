@@ -533,13 +533,19 @@ def vector_family_case(ns, family, dtype, seed=0, T=9, K=5, J=4):
     (through probs and through logits): returns (P, Q, sample, params, data) as named tensors."""
     from alan_b200.named import NT
     Fam = getattr(ns, family)
-    P = ns.Plate(p=ns.Dirichlet(t.tensor([1.5, 2.0, 0.7, 3.0], dtype=dtype)), s=ns.Normal(t.zeros(J, dtype=dtype), 1.0),
-                 T=ns.Plate(y=Fam(probs='p'), w=Fam(logits=lambda s: 1.5 * s)))
+    if family != 'RelaxedOneHotCategorical':
+        P = ns.Plate(p=ns.Dirichlet(t.tensor([1.5, 2.0, 0.7, 3.0], dtype=dtype)), s=ns.Normal(t.zeros(J, dtype=dtype), 1.0),
+                     T=ns.Plate(y=Fam(probs='p'), w=Fam(logits=lambda s: 1.5 * s)))
     Q = ns.Plate(p=ns.Dirichlet('qp_conc'), s=ns.Normal('s_loc', lambda s_ls: s_ls.exp()),
                  T=ns.Plate(y=ns.Data(), w=ns.Data()))
     g = t.Generator().manual_seed(seed)
     r = lambda *sh: t.randn(sh, generator=g, dtype=t.float64).to(dtype)
-    if family == 'Categorical':                                   # the value is the class index itself
+    if family == 'RelaxedOneHotCategorical':                      # points of the open simplex, temperature first
+        P = ns.Plate(p=ns.Dirichlet(t.tensor([1.5, 2.0, 0.7, 3.0], dtype=dtype)), s=ns.Normal(t.zeros(J, dtype=dtype), 1.0),
+                     T=ns.Plate(y=Fam(0.7, probs='p'), w=Fam(1.3, logits=lambda s: 1.5 * s)))
+        dir_ = t.distributions.Dirichlet(t.full((J,), 2.0, dtype=t.float64))
+        onehot = lambda: dir_.sample((T,)).to(dtype)
+    elif family == 'Categorical':                                 # the value is the class index itself
         onehot = lambda: t.randint(0, J, (T,), generator=g).to(dtype)
     else:
         onehot = lambda: t.nn.functional.one_hot(t.randint(0, J, (T,), generator=g), J).to(dtype)

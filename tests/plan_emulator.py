@@ -414,7 +414,12 @@ class Emu:
         gbuf, gbase = self.buf(op.gout)
         gstr = PL._strides_like(op.gout, f.keep, dims)
         go = gbuf[self.offsets(gstr, grid) + gbase]
-        (g,) = t.autograd.grad((res * go).sum(), vals[op.target])
+        if res.requires_grad:
+            (g,) = t.autograd.grad((res * go).sum(), vals[op.target], allow_unused=True)
+        else:
+            g = None                 # piecewise-constant expression (comparisons only): the VM's derivative is zero
+        if g is None:
+            g = t.zeros(shape, dtype=self.dtype)
         _, off, mask = loaded[op.target]
         off = off + t.zeros(shape, dtype=t.long)
         if mask is not None:

@@ -772,6 +772,9 @@ _FAMILIES = {
     'RelaxedBernoulli_logits': (lambda ns: ns.RelaxedBernoulli(0.7, logits='a'), lambda r, n: r(n).sigmoid()),
     'RelaxedBernoulli_probs': (lambda ns: ns.RelaxedBernoulli(lambda b: b.exp() + 0.3, probs=lambda a: a.sigmoid()),
                                lambda r, n: r(n).sigmoid()),
+    # the normaliser's stable / Taylor branches: a ~ N(0, 0.6) puts sigmoid(a) on both sides of (0.499, 0.501]
+    'ContinuousBernoulli_probs': (lambda ns: ns.ContinuousBernoulli(probs=lambda a: a.sigmoid()), lambda r, n: r(n).sigmoid()),
+    'ContinuousBernoulli_logits': (lambda ns: ns.ContinuousBernoulli(logits=lambda a: 0.002 * a), lambda r, n: r(n).sigmoid()),
 }
 
 
@@ -874,7 +877,7 @@ def test_bern_dot_sum_side_factor_and_k_pairs(dtype, M_, N_, K, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", [t.float32, t.float64])
-@pytest.mark.parametrize("family", ["OneHotCategorical", "Multinomial", "Categorical"])
+@pytest.mark.parametrize("family", ["OneHotCategorical", "Multinomial", "Categorical", "RelaxedOneHotCategorical"])
 def test_vector_families_vs_oracle(family, dtype):
     """OneHotCategorical / Multinomial likelihoods over the last positional dim (probs from a Dirichlet latent, logits
     from a traced lambda), densities composed from the VM's primitive operations: log-evidence and every gradient

@@ -264,7 +264,7 @@ def test_split_sizes_follow_the_reference_rule():
 
 
 @pytest.mark.parametrize("dtype", [t.float32, t.float64])
-@pytest.mark.parametrize("family", ["OneHotCategorical", "Multinomial", "Categorical"])
+@pytest.mark.parametrize("family", ["OneHotCategorical", "Multinomial", "Categorical", "RelaxedOneHotCategorical"])
 def test_vector_families_vs_oracle(family, dtype):
     """OneHotCategorical / Multinomial (densities composed from the VM's primitive operations, plan.py COMPOSED) through
     the plan emulator against torch.distributions + autograd in the oracle."""
@@ -296,6 +296,8 @@ COMPOSED_SCALAR = {
     'FisherSnedecor': (lambda ns: ns.FisherSnedecor(lambda a: a.exp() + 2.0, 5.0), lambda r, n: r(n).abs() + 0.2),
     'RelaxedBernoulli': (lambda ns: ns.RelaxedBernoulli(lambda b: b.exp() + 0.3, probs=lambda a: a.sigmoid()),
                          lambda r, n: r(n).sigmoid()),
+    'ContinuousBernoulli': (lambda ns: ns.ContinuousBernoulli(probs=lambda a: a.sigmoid()), lambda r, n: r(n).sigmoid()),
+    'ContinuousBernoulli_taylor': (lambda ns: ns.ContinuousBernoulli(logits=lambda a: 0.002 * a), lambda r, n: r(n).sigmoid()),
 }
 
 
