@@ -34,6 +34,10 @@ __device__ __forceinline__ float  ab_max(float a, float b)   { return fmaxf(a, b
 __device__ __forceinline__ double ab_max(double a, double b) { return fmax(a, b); }
 __device__ __forceinline__ float  ab_abs(float a)  { return fabsf(a); }
 __device__ __forceinline__ double ab_abs(double a) { return fabs(a); }
+__device__ __forceinline__ float  ab_cos(float a)  { return cosf(a); }
+__device__ __forceinline__ double ab_cos(double a) { return cos(a); }
+__device__ __forceinline__ float  ab_sin(float a)  { return sinf(a); }
+__device__ __forceinline__ double ab_sin(double a) { return sin(a); }
 
 template <typename T> __device__ __forceinline__ T warp_max(T v) {
 #pragma unroll

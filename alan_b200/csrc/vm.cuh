@@ -13,7 +13,7 @@
 enum VOp {
     V_LOAD = 0, V_CONST = 1, V_ADD = 2, V_SUB = 3, V_MUL = 4, V_DIV = 5, V_NEG = 6, V_EXP = 7, V_LOG = 8,
     V_SIGMOID = 9, V_SQUARE = 10, V_SQRT = 11, V_RECIP = 12, V_SOFTPLUS = 13, V_TANH = 14, V_ABS = 15,
-    V_LOG1P = 16, V_POW = 17, V_LGAMMA = 18, V_MOV = 19, V_LT = 20,
+    V_LOG1P = 16, V_POW = 17, V_LGAMMA = 18, V_MOV = 19, V_LT = 20, V_COS = 21, V_SIN = 22,
     V_NORMAL = 32, V_BERN_LOGITS = 33, V_BERN_PROBS = 34, V_LOGNORMAL = 35, V_LAPLACE = 36,
     V_EXPONENTIAL = 37, V_GAMMA = 38, V_BETA = 39, V_POISSON = 40, V_CAUCHY = 41, V_HALFNORMAL = 42,
     V_UNIFORM = 43, V_STUDENTT = 44, V_NEGBIN_LOGITS = 45, V_NEGBIN_PROBS = 46, V_BINOM_LOGITS = 47, V_BINOM_PROBS = 48
@@ -116,6 +116,8 @@ __device__ __forceinline__ T vm_eval(const VMProg<T>& P, const T* leaf, T* reg) 
             case V_LGAMMA: y = ab_lgamma(a); break;
             case V_MOV: y = a; break;
             case V_LT: y = a < b ? T(1) : T(0); break;       // sampling transforms (Bernoulli draw = u < p); no gradient
+            case V_COS: y = ab_cos(a); break;
+            case V_SIN: y = ab_sin(a); break;
             case V_NORMAL: y = normal_lp(a, b, reg[ic]); break;
             case V_BERN_LOGITS: y = bern_logits_lp(a, b); break;
             case V_BERN_PROBS: y = bern_logits_lp(a, probs_to_logits(b)); break;
@@ -187,6 +189,8 @@ __device__ __forceinline__ void vm_eval_batch(const VMProg<T>& P, const T (*leaf
             case V_LGAMMA: VMB(ab_lgamma(a));
             case V_MOV: VMB(a);
             case V_LT: VMB(a < b ? T(1) : T(0));
+            case V_COS: VMB(ab_cos(a));
+            case V_SIN: VMB(ab_sin(a));
             case V_NORMAL: VMB(normal_lp(a, b, c));
             case V_BERN_LOGITS: VMB(bern_logits_lp(a, b));
             case V_BERN_PROBS: VMB(bern_logits_lp(a, probs_to_logits(b)));
@@ -253,6 +257,8 @@ __device__ __forceinline__ T vm_grad(const VMProg<T>& P, const T* reg, T* adj, i
                         if (a > T(0)) adj[ib] += g * y * ab_log(a); break;
             case V_LGAMMA: adj[ia] += g * ab_digamma(a); break;
             case V_MOV: adj[ia] += g; break;
+            case V_COS: adj[ia] -= g * ab_sin(a); break;
+            case V_SIN: adj[ia] += g * ab_cos(a); break;
             case V_NORMAL: { T s = reg[ic]; T d = a - b; T iv = T(1) / (s * s);
                 adj[ia] -= g * d * iv; adj[ib] += g * d * iv; adj[ic] += g * (d * d * iv - T(1)) / s; break; }
             case V_BERN_LOGITS: { T sg = ab_sigmoid(b);

@@ -53,6 +53,7 @@ FAMILIES = {
     "OneHotCategorical": ("probs", "logits"),
     "Categorical": ("probs", "logits"),
     "ContinuousBernoulli": ("probs", "logits"),
+    "VonMises": ("loc", "concentration"),
     "RelaxedOneHotCategorical": ("temperature", "probs", "logits"),
     "Multinomial": ("total_count", "probs", "logits"),
 }
@@ -189,6 +190,7 @@ RelaxedBernoulli = _make("RelaxedBernoulli")
 OneHotCategorical = _make("OneHotCategorical")
 Categorical = _make("Categorical")
 ContinuousBernoulli = _make("ContinuousBernoulli")
+VonMises = _make("VonMises")
 RelaxedOneHotCategorical = _make("RelaxedOneHotCategorical")
 Multinomial = _make("Multinomial")
 

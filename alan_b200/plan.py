@@ -42,7 +42,7 @@ NONMP_K = 'K_'          # the one K axis every latent shares in a SampleNonMP pl
 
 VOPS = {'load': 0, 'const': 1, 'add': 2, 'sub': 3, 'mul': 4, 'div': 5, 'neg': 6, 'exp': 7, 'log': 8, 'sigmoid': 9,
         'square': 10, 'sqrt': 11, 'reciprocal': 12, 'softplus': 13, 'tanh': 14, 'abs': 15, 'log1p': 16, 'pow': 17,
-        'lgamma': 18, 'mov': 19, 'lt': 20,
+        'lgamma': 18, 'mov': 19, 'lt': 20, 'cos': 21, 'sin': 22,
         'Normal': 32, 'Bernoulli_logits': 33, 'Bernoulli_probs': 34, 'LogNormal': 35, 'Laplace': 36,
         'Exponential': 37, 'Gamma': 38, 'Beta': 39, 'Poisson': 40, 'Cauchy': 41, 'HalfNormal': 42, 'Uniform': 43,
         'StudentT': 44, 'NegativeBinomial_logits': 45, 'NegativeBinomial_probs': 46, 'Binomial_logits': 47,
@@ -156,6 +156,30 @@ def _lp_continuous_bernoulli(x, logits, p, hoist):              # continuous_ber
     return Proxy(Expr.make('Bernoulli_logits', x.expr, logits.expr)) + norm
 
 
+_I0_SMALL = [1.0, 3.5156229, 3.0899424, 1.2067492, 0.2659732, 0.360768e-1, 0.45813e-2]            # von_mises.py:14-22
+_I0_LARGE = [0.39894228, 0.1328592e-1, 0.225319e-2, -0.157565e-2, 0.916281e-2, -0.2057706e-1, 0.2635537e-1,
+             -0.1647633e-1, 0.392377e-2]
+
+
+def _horner(y, coef):                            # von_mises.py _eval_poly
+    res = coef[-1]
+    for c in reversed(coef[:-1]):
+        res = c + y * res
+    return res
+
+
+def _lp_von_mises(x, loc, kappa, hoist):          # von_mises.py:146-154 over _log_modified_bessel_fn (:47-71), order 0
+    lt = lambda a, b: Proxy(Expr.make('lt', _as_proxy(a).expr, _as_proxy(b).expr))
+    kappa = hoist(kappa)                          # the concentration itself (an expression of parameters / samples) once
+    ys = kappa / 3.75
+    small = hoist(_horner(ys * ys, _I0_SMALL).log())
+    poly_large = hoist(_horner(3.75 / kappa, _I0_LARGE))
+    large = hoist(kappa - 0.5 * kappa.log() + poly_large.log())
+    is_small = lt(kappa, 3.75)
+    log_i0 = hoist(is_small * small + (1.0 - is_small) * large)
+    return kappa * (x - loc).cos() - math.log(2.0 * math.pi) - log_i0
+
+
 def _lp_multinomial(v, logits):                  # multinomial.py:121-132 (total_count = 1: see model.Dist)
     norm = logits - logits.exp().sum(-1).log()
     return (v.sum(-1) + 1.0).lgamma() - (v + 1.0).lgamma().sum(-1) + (norm * v).sum(-1)
@@ -171,6 +195,7 @@ COMPOSED = {
     'Categorical': (('logits',), _lp_categorical),
     'RelaxedOneHotCategorical': (('temperature', 'logits'), _lp_relaxed_one_hot_categorical),
     'ContinuousBernoulli': (('logits', 'probs'), _lp_continuous_bernoulli),
+    'VonMises': (('loc', 'concentration'), _lp_von_mises),
 }
 # how the missing one of (probs, logits) is obtained from the given one, per family
 _VECTOR_FAMILIES = ('OneHotCategorical', 'Multinomial', 'Categorical', 'RelaxedOneHotCategorical')
@@ -1567,7 +1592,7 @@ class Planner:
         elif vec and (len(value.pos_shape) < 1 or args['logits'].expr.pos_shape[-1:] != value.pos_shape[-1:]):
             raise Exception(f"{dist.family}: value and probs / logits must be vectors of one size over the last "
                             f"positional dim (got {value.pos_shape} and {args['logits'].expr.pos_shape})")
-        if dist.family == 'ContinuousBernoulli':
+        if dist.family in ('ContinuousBernoulli', 'VonMises'):
             # the normaliser depends on the parameter only and is longer than one VM program: its pieces are
             # materialised (hoisted) tensors of the parameter's shape, like any `arg` of a density
             extra = [lambda e: Proxy(self.materialize(self._prepare(e.expr), tag='arg'))]

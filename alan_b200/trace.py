@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 UNARY = {'neg', 'exp', 'log', 'sigmoid', 'square', 'sqrt', 'reciprocal', 'softplus', 'tanh', 'abs', 'log1p',
-         'lgamma'}
+         'lgamma', 'cos', 'sin'}
 BINARY = {'add', 'sub', 'mul', 'div', 'pow', 'lt'}
 
 
@@ -99,6 +99,8 @@ class Proxy:
     def sqrt(self): return _mk('sqrt', self)
     def reciprocal(self): return _mk('reciprocal', self)
     def tanh(self): return _mk('tanh', self)
+    def cos(self): return _mk('cos', self)
+    def sin(self): return _mk('sin', self)
     def abs(self): return _mk('abs', self)
     def log1p(self): return _mk('log1p', self)
     def lgamma(self): return _mk('lgamma', self)
@@ -164,7 +166,7 @@ def _matmul(a, b):
 _TORCH_FUNCS = {
     torch.exp: 'exp', torch.log: 'log', torch.sigmoid: 'sigmoid', torch.square: 'square', torch.sqrt: 'sqrt',
     torch.reciprocal: 'reciprocal', torch.tanh: 'tanh', torch.abs: 'abs', torch.log1p: 'log1p',
-    torch.lgamma: 'lgamma', torch.neg: 'neg', torch.negative: 'neg',
+    torch.lgamma: 'lgamma', torch.neg: 'neg', torch.negative: 'neg', torch.cos: 'cos', torch.sin: 'sin',
     torch.add: 'add', torch.sub: 'sub', torch.mul: 'mul', torch.div: 'div', torch.true_divide: 'div',
     torch.matmul: 'matmul', torch.pow: 'pow', torch.nn.functional.softplus: 'softplus',
     torch.nn.functional.sigmoid: 'sigmoid',

@@ -14,7 +14,7 @@ from alan_b200 import plan as PL
 
 UN = {6: lambda a: -a, 7: t.exp, 8: t.log, 9: t.sigmoid, 10: lambda a: a * a, 11: t.sqrt,
       12: lambda a: 1 / a, 13: t.nn.functional.softplus, 14: t.tanh, 15: t.abs, 16: t.log1p, 18: t.lgamma,
-      19: lambda a: a}
+      19: lambda a: a, 21: t.cos, 22: t.sin}
 BI = {2: t.add, 3: t.sub, 4: t.mul, 5: t.div, 17: t.pow, 20: lambda a, b: (a < b).to(a.dtype)}
 HALF_LOG_2PI = 0.91893853320467274178
 

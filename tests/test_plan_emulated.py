@@ -298,6 +298,9 @@ COMPOSED_SCALAR = {
                          lambda r, n: r(n).sigmoid()),
     'ContinuousBernoulli': (lambda ns: ns.ContinuousBernoulli(probs=lambda a: a.sigmoid()), lambda r, n: r(n).sigmoid()),
     'ContinuousBernoulli_taylor': (lambda ns: ns.ContinuousBernoulli(logits=lambda a: 0.002 * a), lambda r, n: r(n).sigmoid()),
+    # concentrations on both sides of 3.75: the small and the large branch of log I0
+    'VonMises': (lambda ns: ns.VonMises('a', lambda b: 3.0 + 4.0 * b.exp()), lambda r, n: 2.0 * r(n).tanh()),
+    'VonMises_small': (lambda ns: ns.VonMises(0.3, lambda b: b.exp()), lambda r, n: 2.0 * r(n).tanh()),
 }
 
 
