@@ -714,12 +714,14 @@ static int run_ops(const alan_b200_plan* plan, int program, const Ctx& c0, bool 
                 T* cst = (T*)tref(r, c);
                 const i64 n_mat = r.i64v();
                 const int d = r.i32(), mode = r.i32();
+                const int rank = r.i32();
+                const T* Dg = rank > 0 ? (const T*)tref(r, c) : nullptr;
                 if (d < 1 || d > AB_MVN_MAXD) return fail("MultivariateNormal: event size must be between 1 and 64");
                 const size_t smem = 2 * (size_t)d * d * sizeof(T);
                 static const cudaError_t attr = cudaFuncSetAttribute(mvn_prep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                                      (int)(2 * AB_MVN_MAXD * AB_MVN_MAXD * sizeof(T)));
                 (void)attr;
-                mvn_prep_kernel<T><<<grid_for(n_mat, 1, c), 32, smem, c.stream>>>(S, L, W, cst, n_mat, d, mode);
+                mvn_prep_kernel<T><<<grid_for(n_mat, 1, c), 32, smem, c.stream>>>(S, L, W, cst, n_mat, d, mode, Dg, rank);
                 break;
             }
             case OP_PERM: {

@@ -11,7 +11,7 @@
 #pragma once
 #include "common.cuh"
 
-enum { MVN_COV = 0, MVN_PREC = 1, MVN_TRIL = 2 };
+enum { MVN_COV = 0, MVN_PREC = 1, MVN_TRIL = 2, MVN_LOWRANK = 3 };   // 3: S = cov_factor [d, r], covariance = S S^T + diag(Dg)
 #define AB_MVN_MAXD 64
 
 // in-place lower Cholesky of the symmetric A[d][d] (row-major, leading dimension d) by one warp
@@ -51,14 +51,24 @@ __device__ void mvn_tri_inverse(const T* A, T* B, int d, int lane) {
 
 template <typename T>
 __global__ void __launch_bounds__(32) mvn_prep_kernel(const T* __restrict__ S, T* __restrict__ L, T* __restrict__ W,
-                                                      T* __restrict__ c, i64 n_mat, int d, int mode) {
+                                                      T* __restrict__ c, i64 n_mat, int d, int mode,
+                                                      const T* __restrict__ Dg, int r) {
     extern __shared__ __align__(16) unsigned char mvn_smem[];
     T* A = reinterpret_cast<T*>(mvn_smem);            // [d][d]
     T* B = A + d * d;                                 // [d][d]
     const int lane = threadIdx.x;
     for (i64 m = blockIdx.x; m < n_mat; m += gridDim.x) {
         const T* Sm = S + m * d * d;
-        if (mode == MVN_PREC) { for (int e = lane; e < d * d; e += 32) A[e] = Sm[(d - 1 - e / d) * d + (d - 1 - e % d)]; }
+        if (mode == MVN_LOWRANK) {
+            // LowRankMultivariateNormal: covariance = F F^T + diag(Dg), F = cov_factor [d, r] of this matrix
+            const T* F = S + m * d * r;
+            for (int e = lane; e < d * d; e += 32) {
+                const int i = e / d, j = e % d;
+                T acc = (i == j) ? Dg[m * d + i] : T(0);
+                for (int k = 0; k < r; ++k) acc += F[i * r + k] * F[j * r + k];
+                A[e] = acc;
+            }
+        } else if (mode == MVN_PREC) { for (int e = lane; e < d * d; e += 32) A[e] = Sm[(d - 1 - e / d) * d + (d - 1 - e % d)]; }
         else { for (int e = lane; e < d * d; e += 32) A[e] = Sm[e]; }
         __syncwarp();
         if (mode == MVN_TRIL) { for (int e = lane; e < d * d; e += 32) if (e % d > e / d) A[e] = T(0); __syncwarp(); }

@@ -54,6 +54,7 @@ FAMILIES = {
     "Categorical": ("probs", "logits"),
     "ContinuousBernoulli": ("probs", "logits"),
     "VonMises": ("loc", "concentration"),
+    "LowRankMultivariateNormal": ("loc", "cov_factor", "cov_diag"),
     "RelaxedOneHotCategorical": ("temperature", "probs", "logits"),
     "Multinomial": ("total_count", "probs", "logits"),
 }
@@ -191,6 +192,7 @@ OneHotCategorical = _make("OneHotCategorical")
 Categorical = _make("Categorical")
 ContinuousBernoulli = _make("ContinuousBernoulli")
 VonMises = _make("VonMises")
+LowRankMultivariateNormal = _make("LowRankMultivariateNormal")
 RelaxedOneHotCategorical = _make("RelaxedOneHotCategorical")
 Multinomial = _make("Multinomial")
 

@@ -912,14 +912,20 @@ class MvnPrepOp(Op):
     code = OP_MVN_PREP
     MODES = {'covariance_matrix': 0, 'precision_matrix': 1, 'scale_tril': 2}
 
-    def __init__(self, S, L, W, c, n_mat, d, mode):
+    def __init__(self, S, L, W, c, n_mat, d, mode, low_rank=None):
         self.S, self.L, self.W, self.c, self.n_mat, self.d, self.mode = S, L, W, c, n_mat, d, mode
+        # mode 3 (LowRankMultivariateNormal): S is the factor [n_mat, d, r] and low_rank = (diagonal PT [n_mat, d], r);
+        # the covariance S S^T + diag(.) is formed in shared memory and factorised like mode 0
+        self.low_rank = low_rank
         self.out = W
 
     def payload(self, w):
         for pt in (self.S, self.L, self.W, self.c):
             w.tref(pt)
         w.i64(self.n_mat); w.i32(self.d); w.i32(self.mode)
+        w.i32(self.low_rank[1] if self.low_rank else 0)
+        if self.low_rank:
+            w.tref(self.low_rank[0])
 
 
 class DotOp(Op):
@@ -1486,7 +1492,7 @@ class Planner:
     def density(self, dist: Dist, value: Expr, scope, tag) -> PT:
         """One factor tensor: sum over every positional dim of log p(value; args)
         (TorchDimDist.py:157-162)."""
-        if dist.family == 'MultivariateNormal':
+        if dist.family in ('MultivariateNormal', 'LowRankMultivariateNormal'):
             return self._mvn_density(dist, value, scope, tag)
         if dist.family == 'Dirichlet':
             return self._dirichlet_density(dist, value, scope, tag)
@@ -1523,6 +1529,8 @@ class Planner:
         """-> (loc Expr, L leaf, W leaf, c leaf, d): the matrix argument is factorised once per matrix by MvnPrepOp; the
         density and the draw are then ordinary expressions over the cells."""
         args = {k: self.resolve_arg(dist.family, k, v, scope) for k, v in dist.args.items()}
+        if dist.family == 'LowRankMultivariateNormal':
+            return self._low_rank_parts(args)
         which = [k for k in MvnPrepOp.MODES if k in args]
         if len(which) != 1:
             raise Exception("Exactly one of covariance_matrix or precision_matrix or scale_tril may be specified.")
@@ -1548,6 +1556,43 @@ class Planner:
             W = self.ws(axes, (d, d), name='mvn:W')
             c = self.ws(axes, (), name='mvn:c')
             op = MvnPrepOp(S.ref, L, W, c, _prod(self.sizes[a] for a in axes), d, MvnPrepOp.MODES[which[0]])
+            op.autodiff_as = 'skip'
+            self.emit(op)
+            cache[key] = (L, W, c)
+        L, W, c = cache[key]
+        lf = lambda pt: Expr.leaf(pt, pt.axes, pt.pos_shape)
+        return self._prepare(args['loc']), lf(L), lf(W), lf(c), d
+
+    def _low_rank_parts(self, args):
+        """LowRankMultivariateNormal(loc, cov_factor [d, r], cov_diag [d]) (torch lowrank_multivariate_normal.py): the
+        covariance cov_factor cov_factor^T + diag(cov_diag) is formed and factorised per matrix by MvnPrepOp (mode 3);
+        torch evaluates the same density through the capacitance matrix (Woodbury), equal up to rounding."""
+        Wf = self.materialize(self._prepare(args['cov_factor']), tag='mvn:cov_factor')
+        Dg = self.materialize(self._prepare(args['cov_diag']), tag='mvn:cov_diag')
+        if Wf.op != 'leaf' or Dg.op != 'leaf' or len(Wf.pos_shape) != 2 or Dg.pos_shape != Wf.pos_shape[:1]:
+            raise Exception(f"LowRankMultivariateNormal: cov_factor must be a [d, r] matrix and cov_diag a [d] vector over "
+                            f"the event dim (got positional shapes {Wf.pos_shape} and {Dg.pos_shape})")
+        if tuple(Wf.ref.axes) != tuple(Dg.ref.axes):
+            raise Exception(f"LowRankMultivariateNormal: cov_factor and cov_diag must vary over the same plates / K axes "
+                            f"(got {Wf.ref.axes} and {Dg.ref.axes})")
+        d, r = Wf.pos_shape
+        if d > 64:
+            raise Exception("LowRankMultivariateNormal: event sizes above 64 are not supported by the device factorisation")
+        if Wf.ref.id in self.needs or Dg.ref.id in self.needs:
+            raise Exception("the gradient with respect to cov_factor / cov_diag of a LowRankMultivariateNormal is not "
+                            "provided (gradients flow to its value and loc)")
+        if Wf.rename or Wf.mode or Dg.rename or Dg.mode:
+            raise Exception("internal: the matrix arguments of a LowRankMultivariateNormal must be plain tensors")
+        cache = getattr(self, '_mvn_cache', None)
+        if cache is None:
+            cache = self._mvn_cache = {}
+        key = (Wf.ref.id, Dg.ref.id, 'low_rank')
+        if key not in cache:
+            axes = tuple(Wf.ref.axes)
+            L = self.ws(axes, (d, d), name='mvn:L')
+            W = self.ws(axes, (d, d), name='mvn:W')
+            c = self.ws(axes, (), name='mvn:c')
+            op = MvnPrepOp(Wf.ref, L, W, c, _prod(self.sizes[a] for a in axes), d, 3, low_rank=(Dg.ref, r))
             op.autodiff_as = 'skip'
             self.emit(op)
             cache[key] = (L, W, c)

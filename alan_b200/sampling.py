@@ -191,7 +191,7 @@ class QSampler:
                 axes = tuple(active) + (Kg,)
                 if isinstance(d, Timeseries):
                     out = self._timeseries(var, d, active, Kg, local, ts_perm)
-                elif d.family == 'MultivariateNormal':
+                elif d.family in ('MultivariateNormal', 'LowRankMultivariateNormal'):
                     # loc + L eps with L = scale_tril from the device factorisation (torch's rsample)
                     loc, L, _, _, dd = pl.mvn_parts(d, local)
                     npt = self._noise_input(var, 'normal', axes, (dd,))

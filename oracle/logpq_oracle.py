@@ -278,7 +278,7 @@ def dist_log_prob(dist: Dist, value: ONT, scope: dict, dtype) -> ONT:
         rmat = mat.t.permute(perm).reshape(shape)
         d = td.MultivariateNormal(rloc, validate_args=False, **{mname: rmat})
         return ONT(d.log_prob(rv), axes)
-    if dist.family in ('Categorical', 'RelaxedOneHotCategorical'):
+    if dist.family in ('Categorical', 'RelaxedOneHotCategorical', 'LowRankMultivariateNormal'):
         # event-aware alignment (TorchDimDist.py:44-77): every argument is laid out [unnamed batch dims, named axes,
         # its own event dims] with event_dim taken from the torch distribution's constraints, the value likewise with
         # the support's event_dim; what is left after log_prob are the named axes and the unnamed batch dims

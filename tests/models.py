@@ -591,3 +591,38 @@ def families_inputs(T=7, J=4, F=3, seed=0, dtype=t.float32):
 
 
 CASES['families'] = (families_model, families_inputs, dict(T=7), 4, [('s', 'mean'), ('w', 'mean2')], [], 5)
+
+
+# --------------------------------------------------------------------------- LowRankMultivariateNormal (row f-2)
+def _lowrank_consts(F, R, dtype):
+    g = t.Generator().manual_seed(4321 + F)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64)
+    return dict(prior_mean=r(F).to(dtype), prior_fac=(0.8 * r(F, R)).to(dtype), prior_diag=(0.5 + r(F).abs()).to(dtype),
+                ap_mean=r(F).to(dtype), ap_fac=(0.6 * r(F, R)).to(dtype), ap_diag=(1.0 + r(F).abs()).to(dtype),
+                like_fac=(0.7 * r(F, R)).to(dtype), like_diag=(0.4 + r(F).abs()).to(dtype))
+
+
+def lowrank_model(ns, F=4, R=2):
+    """The reference's multivariate-Gaussian test model (tests/linear_multivariate_gaussian_param.py:25-45) with every
+    covariance given in low-rank-plus-diagonal form (dist.py:323-359 `LowRankMultivariateNormal`, positional arguments
+    loc, cov_factor, cov_diag)."""
+    c = _lowrank_consts(F, R, t.get_default_dtype())
+    P = ns.Plate(
+        a=ns.LowRankMultivariateNormal(c['prior_mean'], c['prior_fac'], c['prior_diag']),
+        T=ns.Plate(d=ns.LowRankMultivariateNormal('a', c['like_fac'], c['like_diag'])),
+    )
+    Q = ns.Plate(
+        a=ns.LowRankMultivariateNormal('qa_loc', c['ap_fac'], c['ap_diag']),
+        T=ns.Plate(d=ns.Data()),
+    )
+    return P, Q
+
+
+def lowrank_inputs(T=8, F=4, R=2, seed=0, dtype=t.float32):
+    g = t.Generator().manual_seed(seed)
+    r = lambda *s: t.randn(s, generator=g, dtype=t.float64).to(dtype)
+    return dict(platesizes={'T': T}, data={'d': (0.5 + r(T, F)).refine_names('T', None)}, inputs={},
+                params={'qa_loc': _lowrank_consts(F, R, dtype)['ap_mean'].clone()})
+
+
+CASES['lowrank'] = (lowrank_model, lowrank_inputs, dict(T=8), 5, [('a', 'mean'), ('a', 'mean2')], [], 6)

@@ -167,8 +167,14 @@ class Emu:
         """csrc/mvn.cuh with torch.linalg: scale_tril, its inverse and the log-normaliser per matrix."""
         sb, sbase = self.buf(op.S)
         d, n = op.d, op.n_mat
-        S = sb[sbase:sbase + n * d * d].reshape(n, d, d)
-        if op.mode == 0:
+        if op.mode == 3:                                            # low rank: factor [n, d, r] + diagonal [n, d]
+            Dg_pt, r = op.low_rank
+            F = sb[sbase:sbase + n * d * r].reshape(n, d, r)
+            db, dbase = self.buf(Dg_pt)
+            S = F @ F.mT + t.diag_embed(db[dbase:dbase + n * d].reshape(n, d))
+        else:
+            S = sb[sbase:sbase + n * d * d].reshape(n, d, d)
+        if op.mode in (0, 3):
             L = t.linalg.cholesky(S)
         elif op.mode == 2:
             L = S.tril()
