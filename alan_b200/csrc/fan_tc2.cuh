@@ -160,6 +160,7 @@ template <int D, bool BWD, bool H16 = false, bool STAG = false>
 __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __grid_constant__ FanLseParams<float> p, const __grid_constant__ Tc2Geom geo) {
     constexpr int KT = H16 ? (2 * D + 3 + 15) / 16 * 16 : (2 * D + 1 + 7) / 8 * 8;   // K extent (40 at D = 18; 48 as fp16)
     constexpr int NC = H16 ? KT / 8 : KT / 4, KSTEPS = H16 ? KT / 16 : KT / 8;       // 16-byte chunks per row, MMAs per product
+    static_assert(!H16 || KT - (2 * D + 3) >= 4, "fp16 operands: four spare K columns carry the mask of the padding rows");
     constexpr int ACOLS = H16 ? KT / 2 : KT;                                // TMEM columns of one A part of one tile
     constexpr uint32_t LBO = T2_N * 16, SBO = 8 * 16;                      // [chunk][128 rows][16 B]: A_lo tiles and B alike
     constexpr uint32_t OPER = NC * LBO;                                    // bytes of one operand part (20 KB at D = 18)
@@ -231,9 +232,14 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
         for (int i = threadIdx.x; i < T2_STAGES * per_stage; i += blockDim.x) {
             const int s = i / per_stage, r = i - s * per_stage, us = r / npad, kz = Kk + r - us * npad;
             if (H16) {
-                // the first bias piece (its A entry is 4096): -60000 x 4096 = -2.5e8 in log2 units
-                const int off = (((2 * D) / 8) * T2_N + 32 * us + kz) * 8 + ((2 * D) & 7);
-                reinterpret_cast<__half*>(stage_base + (size_t)s * 2 * OPER)[off] = __float2half_rn(-60000.f);
+                // the first bias piece (its A entry is 4096): -60000 x 4096 = -2.5e8 in log2 units, and the spare K columns
+                // (A entries 32768, outside the per-CTA scaling; live rows hold 0 there): -60000 x 32768 each.  With the
+                // operands scaled to |A'| < 2^14, v'^2 < 2^14 a live column is above -(D 2^28 + D 2^21 + 2^28) = -5.2e9
+                // in the accumulator's units, the padding rows sit at -(KT - 2 D - 3) x 2.0e9 (-1.8e10 at D = 18)
+                __half* bhh = reinterpret_cast<__half*>(stage_base + (size_t)s * 2 * OPER);
+                bhh[(((2 * D) / 8) * T2_N + 32 * us + kz) * 8 + ((2 * D) & 7)] = __float2half_rn(-60000.f);
+                for (int k = 2 * D + 3; k < KT; ++k)
+                    bhh[((k / 8) * T2_N + 32 * us + kz) * 8 + (k & 7)] = __float2half_rn(-60000.f);
             } else {
                 const int off = (((2 * D) / 4) * T2_N + 32 * us + kz) * 4 + ((2 * D) & 3);
                 reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER)[off] = bh;
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
         }
     }
     if (threadIdx.x == 0) {
+        if (H16) reinterpret_cast<int*>(s_red)[33] = 0;                    // max |A| of this CTA (the adjoint's s_red is idle here)
         for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&full[s], 32 * T2_BW); mbar_init(&empty[s], 1); }
         for (int a = 0; a < T2_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], STAG ? 128 * (T2_EPI / 2) : 128 * T2_EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -293,6 +300,22 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
             s_cst[tl * 128 + row] = cst;
             s_ooff[tl * 128 + row] = ooff;
             s_goff[tl * 128 + row] = goff;
+            if (H16) {
+                // fp16 range: the constant operand of this CTA is scaled by a power of two so that max |A| < 2^14 (small
+                // scales give 1 / (2 s^2) beyond 65504); the epilogue undoes it inside its first FFMA2
+                float rmax = 0.f;
+#pragma unroll
+                for (int k = 0; k < KT; ++k) rmax = fmaxf(rmax, fabsf(a[k]));
+                rmax = warp_max(rmax);
+                if (lane == 0) atomicMax(reinterpret_cast<int*>(s_red) + 33, __float_as_int(rmax));
+                asm volatile("bar.sync 7, %0;" :: "n"(128 * T2_TILES) : "memory");
+                const float amax = __int_as_float(reinterpret_cast<int*>(s_red)[33]);
+                const int ea = amax > 16384.f ? ilogbf(amax) - 13 : 0;
+                const float sa = exp2f((float)-ea);
+#pragma unroll
+                for (int k = 0; k < KT; ++k) a[k] = k < 2 * D + 3 ? a[k] * sa : 32768.f;   // spare columns: the padding rows' mask
+                if (warp == 0 && lane == 0) s_red[32] = exp2f((float)ea);
+            }
 #pragma unroll
             for (int g8 = 0; g8 < ACOLS / 8; ++g8) {
                 uint32_t hi[8], lo[8];
@@ -352,6 +375,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
             }
         };
         if (blk0 < n_blocks) fetch(blk0);
+        const float sc_a = H16 ? s_red[32] : 1.f;                                // 2^ea of this CTA's constant operand
         unsigned tt = 0;                                                         // accumulator stage counter
         unsigned it = 0;
         float ps[T2_TILES];                                                      // forward: running sum of out over this team's users
@@ -385,6 +409,12 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                     MBAR_WAIT(&tfull[a], pa, dbg0);
                     tc_fence_after();
                     if (!BWD) {
+                        // H16: the accumulator carries the powers of two of the operand scalings (A per CTA, B per block and
+                        // user), undone inside the subtraction of the maximum (an FFMA2 for the FADD2); the factors are read
+                        // here so that the shared-memory latency hides behind the TMEM loads
+                        float scu[UPT];
+#pragma unroll
+                        for (int uu = 0; uu < UPT; ++uu) scu[uu] = H16 ? sc_a * s_red[(it & 7) * T2_US + ubase + uu] : 1.f;
                         // all loads of this team first, then the accumulator stage goes straight back to the MMA issuer
                         uint32_t r[UPT][32];
 #pragma unroll
@@ -405,14 +435,17 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                             for (int k = 0; k < 8; ++k)
                                 m8[k] = fmaxf(fmaxf(__uint_as_float(r[uu][4 * k]), __uint_as_float(r[uu][4 * k + 1])),
                                               fmaxf(__uint_as_float(r[uu][4 * k + 2]), __uint_as_float(r[uu][4 * k + 3])));
-                            const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+                            const float sc = scu[uu];
+                            const float2 sc2 = make_float2(sc, sc);
+                            const float m = sc * fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
                             const float2 nm2 = make_float2(-m, -m);
                             float2 s2[4];
 #pragma unroll
                             for (int c = 0; c < 4; ++c) s2[c] = make_float2(0.f, 0.f);
 #pragma unroll
                             for (int k = 0; k < 32; k += 2) {
-                                const float2 d2 = __fadd2_rn(make_float2(__uint_as_float(r[uu][k]), __uint_as_float(r[uu][k + 1])), nm2);
+                                const float2 rk = make_float2(__uint_as_float(r[uu][k]), __uint_as_float(r[uu][k + 1]));
+                                const float2 d2 = H16 ? __ffma2_rn(rk, sc2, nm2) : __fadd2_rn(rk, nm2);
                                 s2[(k >> 1) & 3] = __fadd2_rn(s2[(k >> 1) & 3], make_float2(FastExp<float>::ex(d2.x), FastExp<float>::ex(d2.y)));
                             }
                             const float2 t2 = __fadd2_rn(__fadd2_rn(s2[0], s2[1]), __fadd2_rn(s2[2], s2[3]));
@@ -627,6 +660,22 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                 }
                 qsum -= lg + float(D) * float(HALF_LOG_2PI);
             }
+            float bsc = 1.f;
+            float dfv[D];
+            if (H16) {
+                // fp16 range: the rows of this user (all kappa) are scaled by a power of two so that max v'^2 < 2^14; the
+                // factor goes to the epilogue through a ring of slots indexed by the block counter.  Exponent arithmetic
+                // on the bit patterns (non-negative floats order as unsigned integers: one REDUX for the warp maximum)
+                float dmax = 0.f;
+#pragma unroll
+                for (int dd = 0; dd < D; ++dd) { dfv[dd] = cur[dd] - s_cd[dd]; dmax = fmaxf(dmax, fabsf(dfv[dd])); }
+                const float dm = __uint_as_float(__reduce_max_sync(0xffffffffu, kz < Kk ? __float_as_uint(dmax) : 0u));
+                const int eb = max((int)(__float_as_uint(dm * dm) >> 23) - 127 - 13, 0);      // floor(log2 max v'^2) - 13
+                bsc = __uint_as_float((unsigned)(127 - eb) << 23);
+                if (lane == 0) s_red[(it & 7) * T2_US + us] = __uint_as_float((unsigned)(127 + eb) << 23);
+#pragma unroll
+                for (int dd = 0; dd < D; ++dd) dfv[dd] *= bsc;
+            }
             if (kz < Kk) {                       // rows of users >= n_u are written as zeros: finite, masked later
                 float* bh = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER);
                 float* bl = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER + OPER);
@@ -635,6 +684,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                 for (int i = 0; i < TC_NB; ++i) if (i < nb) bsum += geo.bc[i] * cur_b[i];
                 bsum *= LS;
                 if (H16) {
+                    bsum *= bsc;
                     // bias pieces: b' = 4096 q0 + q1 + q2, every piece an fp16 value (their lo parts are exactly zero)
                     const float q0 = __half2float(__float2half_rn(bsum * (1.f / 4096.f)));
                     const float r1 = fmaf(-4096.f, q0, bsum);
@@ -649,8 +699,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                         for (int e = 0; e < 8; ++e) {
                             const int k = 8 * c + e;
                             const int dd = k < D ? k : (k < 2 * D ? k - D : 0);
-                            const float df = cur[dd] - s_cd[dd];
-                            tv[e] = k < D ? df * df : k < 2 * D ? df : k == 2 * D ? q0 : k == 2 * D + 1 ? q1 : k == 2 * D + 2 ? q2 : 0.f;
+                            tv[e] = k < D ? (cur[dd] - s_cd[dd]) * dfv[dd] : k < 2 * D ? dfv[dd] : k == 2 * D ? q0 : k == 2 * D + 1 ? q1 : k == 2 * D + 2 ? q2 : 0.f;
                         }
                         uint4 hh, l;
                         split_f16x2(tv[0], tv[1], hh.x, l.x);

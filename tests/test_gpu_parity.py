@@ -929,3 +929,29 @@ def test_dense_forward_variants_match_default(M_, N_, K, variant, monkeypatch):
     for k in names:
         assert rel_err(grads[k].cpu(), g_tc[k].cpu()) < 5e-5, k
         assert rel_err(grads[k].cpu(), g_ff[k].cpu()) < 2e-4, k
+
+
+@pytest.mark.parametrize("regime", ["small_scale", "far", "both"])
+@pytest.mark.parametrize("variant", ["f16", "f16_stag"])
+def test_dense_forward_f16_range(regime, variant, monkeypatch):
+    """fp16 (hi, lo) operands outside the plain fp16 range: scales of ~0.002 (1 / (2 s^2) beyond 65504) and values
+    hundreds of scales from the centre ((v - centre)^2 beyond 65504).  The kernel scales the constant operand per CTA and
+    the value rows per (block, user) by powers of two and undoes both inside the epilogue's first FFMA2
+    (csrc/fan_tc2.cuh), so the result must stay finite and agree with the 3xTF32 and the FFMA2 kernels."""
+    P, Q, sample, ip, data, names = _movielens_case(130, 3, 24, 18, seed=37)
+    if regime in ("small_scale", "both"):
+        sample['psi_z'].t.sub_(6.5)
+    if regime in ("far", "both"):
+        sample['z'].t.mul_(400.0)
+    out = _run_paths(P, Q, sample, ip, data, names, monkeypatch)
+    (lp_tc, _, run, tensors), (lp_ff, _, _, _) = out[True], out[False]
+    monkeypatch.setenv("ALAN_B200_TC_F16", "1")
+    if "stag" in variant:
+        monkeypatch.setenv("ALAN_B200_TC_STAG", "1")
+    lp = run.forward_raw(tensors).clone()
+    monkeypatch.delenv("ALAN_B200_TC_F16", raising=False)
+    monkeypatch.delenv("ALAN_B200_TC_STAG", raising=False)
+    assert t.isfinite(lp_ff).all() and t.isfinite(lp).all()
+    print(regime, variant, float(lp), float(lp_tc), float(lp_ff), rel_err(lp.cpu(), lp_ff.cpu()), rel_err(lp_tc.cpu(), lp_ff.cpu()))
+    # the fp32 FFMA2 kernel is the yardstick; the 3xTF32 kernel's own distance from it is the scale of what is attainable
+    assert rel_err(lp.cpu(), lp_ff.cpu()) < max(1e-5, 4 * rel_err(lp_tc.cpu(), lp_ff.cpu()))
