@@ -154,8 +154,17 @@ __device__ __forceinline__ int t2_dot(const int* idx, const int* st) {
 // and the two phases add up; two pairs half a period apart overlap one pair's ex2 with the other pair's issue phase.
 // Measured at cfg-5 on one box (fan_lse forward, us): 3xTF32 140.1, STAG 138.5-128 (no gain: the MMA issuer is then the
 // limit), H16 140.5 (no gain either: with all teams in lockstep the epilogue is), H16 + STAG 126.6 (-10 %).  A second group
-// of builder warps (two blocks in flight) changed nothing: 139.1.  H16 + STAG is opt-in (ALAN_B200_TC_F16=1
-// ALAN_B200_TC_STAG=1, D = 18): fp16 overflows where 3xTF32 does not (|v - centre| > 255, scale < 0.005 -> inf / NaN lp).
+// of builder warps (two blocks in flight) changed nothing: 139.1.
+// fp16 range: plain fp16 operands overflow where 3xTF32 does not (|v - centre| > 255, scale < 0.005), so H16 scales the
+// constant operand per CTA (2^-ea: max |A'| < 2^14) and the value rows per (block, user) (2^-eb: max v'^2 < 2^14; the
+// usual case eb = 0 is a maximum, a vote and a uniform branch in the builder) and undoes both in the epilogue's first
+// FFMA2 (d = r 2^(ea + eb) - m instead of the FADD2 r - m); 2^eb travels through a ring of shared-memory slots read once
+// per block and team.  The padding rows' mask rides the spare K columns (A entries 32768 outside the scaling) so that it
+// stays below every live column at any scale.  Limits: scale > ~4e-6 (beyond it the unit bias columns 2^-ea leave fp16:
+// the kernel writes NaN, loudly).  Cost of the scaling, bisected at cfg-5 on one box (H16 + STAG, us): none 124.6,
+// per-CTA only 125.3, both 128.4 with a ring read per tile and user (LDS shares the MIO queue with the saturated MUFU),
+// ~127 with one read per block; against 3xTF32 on the same boxes 132.4-137.5: -2.5 .. -4 % instead of -6 .. -10 %.
+// H16 + STAG stays opt-in (ALAN_B200_TC_F16=1 ALAN_B200_TC_STAG=1, D = 18; the whole GPU suite passes with both set).
 template <int D, bool BWD, bool H16 = false, bool STAG = false>
 __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __grid_constant__ FanLseParams<float> p, const __grid_constant__ Tc2Geom geo) {
     constexpr int KT = H16 ? (2 * D + 3 + 15) / 16 * 16 : (2 * D + 1 + 7) / 8 * 8;   // K extent (40 at D = 18; 48 as fp16)
@@ -314,7 +323,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                 const float sa = exp2f((float)-ea);
 #pragma unroll
                 for (int k = 0; k < KT; ++k) a[k] = k < 2 * D + 3 ? a[k] * sa : 32768.f;   // spare columns: the padding rows' mask
-                if (warp == 0 && lane == 0) s_red[32] = exp2f((float)ea);
+                if (warp == 0 && lane == 0) s_red[32] = ea <= 24 ? exp2f((float)ea) : NAN;    // 2^-ea must stay an fp16 value
             }
 #pragma unroll
             for (int g8 = 0; g8 < ACOLS / 8; ++g8) {
@@ -376,6 +385,10 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
         };
         if (blk0 < n_blocks) fetch(blk0);
         const float sc_a = H16 ? s_red[32] : 1.f;                                // 2^ea of this CTA's constant operand
+        float scu[UPT];                                                          // H16: 2^(ea + eb) of this team's users, current block
+        unsigned sc_it = ~0u;
+#pragma unroll
+        for (int uu = 0; uu < UPT; ++uu) scu[uu] = 1.f;
         unsigned tt = 0;                                                         // accumulator stage counter
         unsigned it = 0;
         float ps[T2_TILES];                                                      // forward: running sum of out over this team's users
@@ -410,11 +423,19 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                     tc_fence_after();
                     if (!BWD) {
                         // H16: the accumulator carries the powers of two of the operand scalings (A per CTA, B per block and
-                        // user), undone inside the subtraction of the maximum (an FFMA2 for the FADD2); the factors are read
-                        // here so that the shared-memory latency hides behind the TMEM loads
-                        float scu[UPT];
+                        // user), undone inside the subtraction of the maximum (an FFMA2 for the FADD2).  The factors of this
+                        // team's users are read once per block, at its first tile, ahead of the TMEM loads (a shared-memory
+                        // read per tile and user measured 3 us at cfg-5: LDS shares the MIO queue with the saturated MUFU)
+                        if (H16 && sc_it != it) {
+                            sc_it = it;
+                            if (UPT == 2) {
+                                const float2 v2 = *reinterpret_cast<const float2*>(&s_red[(it & 7) * T2_US + ubase]);
+                                scu[0] = sc_a * v2.x; scu[UPT - 1] = sc_a * v2.y;
+                            } else {
 #pragma unroll
-                        for (int uu = 0; uu < UPT; ++uu) scu[uu] = H16 ? sc_a * s_red[(it & 7) * T2_US + ubase + uu] : 1.f;
+                                for (int uu = 0; uu < UPT; ++uu) scu[uu] = sc_a * s_red[(it & 7) * T2_US + ubase + uu];
+                            }
+                        }
                         // all loads of this team first, then the accumulator stage goes straight back to the MMA issuer
                         uint32_t r[UPT][32];
 #pragma unroll
@@ -664,17 +685,22 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
             float dfv[D];
             if (H16) {
                 // fp16 range: the rows of this user (all kappa) are scaled by a power of two so that max v'^2 < 2^14; the
-                // factor goes to the epilogue through a ring of slots indexed by the block counter.  Exponent arithmetic
-                // on the bit patterns (non-negative floats order as unsigned integers: one REDUX for the warp maximum)
+                // factor goes to the epilogue through a ring of slots indexed by the block counter.  The usual case (every
+                // |v'| < 128: no scaling) costs the maximum, a vote and a uniform branch; otherwise exponent arithmetic on
+                // the bit patterns (non-negative floats order as unsigned integers: one REDUX for the warp maximum)
                 float dmax = 0.f;
 #pragma unroll
                 for (int dd = 0; dd < D; ++dd) { dfv[dd] = cur[dd] - s_cd[dd]; dmax = fmaxf(dmax, fabsf(dfv[dd])); }
-                const float dm = __uint_as_float(__reduce_max_sync(0xffffffffu, kz < Kk ? __float_as_uint(dmax) : 0u));
-                const int eb = max((int)(__float_as_uint(dm * dm) >> 23) - 127 - 13, 0);      // floor(log2 max v'^2) - 13
-                bsc = __uint_as_float((unsigned)(127 - eb) << 23);
-                if (lane == 0) s_red[(it & 7) * T2_US + us] = __uint_as_float((unsigned)(127 + eb) << 23);
+                float unsc = 1.f;
+                if (__any_sync(0xffffffffu, kz < Kk && !(dmax < 128.f))) {
+                    const float dm = __uint_as_float(__reduce_max_sync(0xffffffffu, kz < Kk ? __float_as_uint(dmax) : 0u));
+                    const int eb = max((int)(__float_as_uint(dm * dm) >> 23) - 127 - 13, 0);  // floor(log2 max v'^2) - 13
+                    bsc = __uint_as_float((unsigned)(127 - eb) << 23);
+                    unsc = __uint_as_float((unsigned)(127 + eb) << 23);
 #pragma unroll
-                for (int dd = 0; dd < D; ++dd) dfv[dd] *= bsc;
+                    for (int dd = 0; dd < D; ++dd) dfv[dd] *= bsc;
+                }
+                if (lane == 0) s_red[(it & 7) * T2_US + us] = unsc;
             }
             if (kz < Kk) {                       // rows of users >= n_u are written as zeros: finite, masked later
                 float* bh = reinterpret_cast<float*>(stage_base + (size_t)s * 2 * OPER);
