@@ -665,6 +665,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
 #ifdef TC_DEBUG_SPIN
             const long long tb1 = clock64();
 #endif
+#ifndef TC_EXP_NOBUILD                   // timing experiment: the builders arrive without building (operands stay zero)
             // inline Gaussian Q factor of this (user, kappa): lane d contributes 1 / (2 s_d^2) and log s_d, every lane
             // walks the D shuffled pairs in d order (fixed order) against its own value row
             float qsum = 0.f;
@@ -759,6 +760,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32, 1) fan_lse_tc2_kernel(const __g
                 }
                 }
             }
+#endif
 #ifdef TC_DEBUG_SPIN
             const long long tb2 = clock64();
 #endif
